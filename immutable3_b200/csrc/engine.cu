@@ -1,0 +1,761 @@
+// engine.cu — the C ABI of include/imm3.h: SegmentManager upload path + query execution.
+//
+//  imm3_open        = new SegmentManager(dataDir)            SegmentManager.scala:20-112
+//                     + staging of every owned segment into HBM through pinned async copies
+//  imm3_query*      = Engine.execute, Project branch         Engine.scala:158-198
+//                     = ScanOp -> SelectOp* -> ProjectOp      Scan.scala, Select.scala, Project.scala
+//  result accessors = Iterator[Row] / Row                    Project.scala:17-81, Record.scala:3-14
+//
+// HBM layout: one arena per (table, column) holding the owned segments' block bytes back to back in
+// canonical order.  For DENSE_* columns that is a flat array of values indexed by the canonical row
+// ordinal (blocks and segments need no per-block metadata on the device); the arena is padded to a
+// whole tile so the last TMA bulk copy stays in bounds.  For PFOR_INT columns it is the stream of
+// big-endian words plus a word offset per block.
+//
+// There is no CPU execution path in this file: every query runs the CUDA kernels of kernels.cu.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kernels.hpp"
+#include "plan.hpp"
+#include "store.hpp"
+
+using namespace imm3;
+
+#define CUDA_TRY(expr)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t e_ = (expr);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(e_ == cudaErrorMemoryAllocation ? IMM3_ERR_OOM : IMM3_ERR_CUDA, "%s: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                       \
+    } while (0)
+
+namespace {
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+// Grow-only cache of device / pinned-host buffers: result columns are handed back on
+// imm3_result_free and reused by the next query (cudaMalloc / cudaMallocHost cost milliseconds).
+struct BufPool {
+    bool pinned_host = false;
+    std::vector<Buf> free_list;
+    int acquire(size_t bytes, Buf* out) {
+        if (bytes < 256) bytes = 256;
+        int best = -1;
+        for (size_t i = 0; i < free_list.size(); i++)
+            if (free_list[i].cap >= bytes && (best < 0 || free_list[i].cap < free_list[(size_t)best].cap)) best = (int)i;
+        if (best >= 0) {
+            *out = free_list[(size_t)best];
+            free_list.erase(free_list.begin() + best);
+            return 0;
+        }
+        // drop the largest cached buffer that is too small, so the pool does not accumulate
+        if (!free_list.empty()) {
+            size_t big = 0;
+            for (size_t i = 1; i < free_list.size(); i++)
+                if (free_list[i].cap > free_list[big].cap) big = i;
+            if (pinned_host) cudaFreeHost(free_list[big].p); else cudaFree(free_list[big].p);
+            free_list.erase(free_list.begin() + (long)big);
+        }
+        size_t cap = bytes + bytes / 8;
+        cap = (cap + 255) & ~(size_t)255;
+        void* p = nullptr;
+        cudaError_t e = pinned_host ? cudaMallocHost(&p, cap) : cudaMalloc(&p, cap);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            release_all();
+            e = pinned_host ? cudaMallocHost(&p, cap) : cudaMalloc(&p, cap);
+        }
+        if (e != cudaSuccess)
+            return fail(IMM3_ERR_OOM, "%s of %zu bytes failed: %s", pinned_host ? "cudaMallocHost" : "cudaMalloc", cap,
+                        cudaGetErrorString(e));
+        out->p = p;
+        out->cap = cap;
+        return 0;
+    }
+    void release(Buf b) {
+        if (b.p) free_list.push_back(b);
+    }
+    void release_all() {
+        for (auto& b : free_list) {
+            if (pinned_host) cudaFreeHost(b.p); else cudaFree(b.p);
+        }
+        free_list.clear();
+    }
+};
+
+}  // namespace
+
+struct imm3_db {
+    std::string dir;
+    int device = 0, rank = 0, world = 1;
+    uint32_t flags = 0;
+    bool host_only = false;
+    std::vector<TableStore> tables;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ScanCtrl* d_ctrl = nullptr;
+    ScanCtrl* h_ctrl = nullptr;
+    unsigned long long* d_status = nullptr;
+    size_t status_cap = 0;
+    uint32_t epoch = 0;
+    int num_sms = 0;
+    BufPool dev_pool, host_pool;
+    Buf d_bitmap, h_bitmap;
+    std::string explain_buf;
+};
+
+struct imm3_result {
+    imm3_db* db = nullptr;
+    int ncols = 0;
+    std::vector<std::string> names;
+    std::vector<int> types, widths;
+    std::vector<Buf> d_cols, h_cols;
+    int64_t local_count = 0;
+    int64_t fetched = 0;
+    double device_ms = 0;
+    int launches = 0;
+    int64_t alg_bytes = 0;
+};
+
+namespace {
+
+TableStore* find_table(imm3_db* db, const char* name) {
+    if (!name) { set_error("table name is NULL"); return nullptr; }
+    for (auto& t : db->tables)
+        if (t.meta.name == name) return &t;
+    // SegmentManager.getTable, SegmentManager.scala:89-92
+    fail(IMM3_ERR_NOT_FOUND, "Table %s does not exist in SegmentManager", name);
+    return nullptr;
+}
+
+int use_device(imm3_db* db) {
+    if (db->host_only) return fail(IMM3_ERR_STATE, "handle was opened with IMM3_OPEN_HOST_ONLY: no device work (there is no CPU fallback)");
+    CUDA_TRY(cudaSetDevice(db->device));
+    return 0;
+}
+
+// ---- SegmentManager upload path: files -> pinned staging -> HBM --------------------------------
+constexpr size_t kStageBytes = 32u << 20;
+
+int upload_column(imm3_db* db, ColumnStore& col, int64_t nrows, uint8_t* stage[2], cudaEvent_t stage_ev[2], int* cur) {
+    const bool dense = col.meta.codec != IMM3_CODEC_PFOR_INT;
+    const size_t payload = (size_t)col.encoded_bytes;
+    size_t arena = dense ? (size_t)((nrows + kTileRows - 1) / kTileRows) * kTileRows * (size_t)col.meta.width : payload;
+    arena += 256;
+    CUDA_TRY(cudaMalloc(&col.d_arena, arena));
+    col.arena_bytes = arena;
+    if (db->flags & IMM3_OPEN_KEEP_HOST) {
+        CUDA_TRY(cudaMallocHost(&col.h_mirror, payload ? payload : 1));
+        size_t at = 0;
+        for (auto& sf : col.segs) {
+            FileMap fm;
+            int rc = fm.open(sf.path, (size_t)sf.nbytes);
+            if (rc) return rc;
+            if (sf.nbytes) std::memcpy(col.h_mirror + at, fm.data, (size_t)sf.nbytes);
+            at += (size_t)sf.nbytes;
+        }
+        if (payload) CUDA_TRY(cudaMemcpyAsync(col.d_arena, col.h_mirror, payload, cudaMemcpyHostToDevice, db->stream));
+    } else {
+        // double-buffered pinned staging ring; a buffer is refilled only after its previous copy retired
+        size_t at = 0, fill = 0;
+        auto flush = [&]() -> int {
+            if (!fill) return 0;
+            CUDA_TRY(cudaMemcpyAsync(col.d_arena + at, stage[*cur], fill, cudaMemcpyHostToDevice, db->stream));
+            CUDA_TRY(cudaEventRecord(stage_ev[*cur], db->stream));
+            at += fill;
+            fill = 0;
+            *cur ^= 1;
+            CUDA_TRY(cudaEventSynchronize(stage_ev[*cur]));
+            return 0;
+        };
+        for (auto& sf : col.segs) {
+            FileMap fm;
+            int rc = fm.open(sf.path, (size_t)sf.nbytes);
+            if (rc) return rc;
+            size_t done = 0;
+            while (done < (size_t)sf.nbytes) {
+                size_t take = std::min(kStageBytes - fill, (size_t)sf.nbytes - done);
+                std::memcpy(stage[*cur] + fill, fm.data + done, take);
+                fill += take;
+                done += take;
+                if (fill == kStageBytes && (rc = flush())) return rc;
+            }
+        }
+        int rc = flush();
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaMemsetAsync(col.d_arena + payload, 0, arena - payload, db->stream));
+    if (!dense) {
+        CUDA_TRY(cudaMalloc(&col.d_word_off, col.word_off.size() * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemcpyAsync(col.d_word_off, col.word_off.data(), col.word_off.size() * sizeof(uint32_t),
+                                 cudaMemcpyHostToDevice, db->stream));
+    }
+    return 0;
+}
+
+int upload_all(imm3_db* db) {
+    uint8_t* stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int cur = 0, rc = 0;
+    const bool ring = !(db->flags & IMM3_OPEN_KEEP_HOST);
+    if (ring)
+        for (int i = 0; i < 2; i++) {
+            CUDA_TRY(cudaMallocHost(&stage[i], kStageBytes));
+            CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventRecord(ev[i], db->stream));
+        }
+    for (auto& t : db->tables) {
+        for (auto& c : t.cols)
+            if ((rc = upload_column(db, c, t.nrows, stage, ev, &cur))) break;
+        if (rc) break;
+        CUDA_TRY(cudaMalloc(&t.d_row_start, t.row_start.size() * sizeof(uint64_t)));
+        CUDA_TRY(cudaMemcpyAsync(t.d_row_start, t.row_start.data(), t.row_start.size() * sizeof(uint64_t),
+                                 cudaMemcpyHostToDevice, db->stream));
+    }
+    cudaError_t e = cudaStreamSynchronize(db->stream);
+    for (int i = 0; i < 2; i++) {
+        if (stage[i]) cudaFreeHost(stage[i]);
+        if (ev[i]) cudaEventDestroy(ev[i]);
+    }
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(IMM3_ERR_CUDA, "upload: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+void free_device_side(imm3_db* db) {
+    if (db->host_only) return;
+    cudaSetDevice(db->device);
+    if (db->stream) cudaStreamSynchronize(db->stream);
+    for (auto& t : db->tables) {
+        for (auto& c : t.cols) {
+            if (c.d_arena) cudaFree(c.d_arena);
+            if (c.d_word_off) cudaFree(c.d_word_off);
+            if (c.h_mirror) cudaFreeHost(c.h_mirror);
+        }
+        if (t.d_row_start) cudaFree(t.d_row_start);
+    }
+    db->dev_pool.release_all();
+    db->host_pool.release_all();
+    if (db->d_bitmap.p) cudaFree(db->d_bitmap.p);
+    if (db->h_bitmap.p) cudaFreeHost(db->h_bitmap.p);
+    if (db->d_status) cudaFree(db->d_status);
+    if (db->d_ctrl) cudaFree(db->d_ctrl);
+    if (db->h_ctrl) cudaFreeHost(db->h_ctrl);
+    if (db->ev0) cudaEventDestroy(db->ev0);
+    if (db->ev1) cudaEventDestroy(db->ev1);
+    if (db->own_stream) cudaStreamDestroy(db->own_stream);
+    cudaGetLastError();
+}
+
+// ---- query planning on top of the logical plan --------------------------------------------------
+struct Prepared {
+    TableStore* table = nullptr;
+    LogicalPlan lp;
+    bool block_mode = false;
+    ScanPlan sp;
+    size_t dyn_smem = 0;
+    int grid = 0;
+};
+
+const char* kernel_name(const imm3_db* db, const TableStore& t, const LogicalPlan& lp, bool* block_mode) {
+    bool blocks = lp.uses_pfor || (db->flags & IMM3_OPEN_FORCE_BLOCKS);  // tests: cross-check the two kernels
+    (void)t;
+    *block_mode = blocks;
+    if (lp.always_empty) return "none(always_empty)";
+    return blocks ? "scan_blocks" : ((db->flags & IMM3_OPEN_NO_TMA) ? "scan_dense(direct)" : "scan_dense(tma)");
+}
+
+int prepare(imm3_db* db, const char* table, const imm3_pred* preds, int npreds, const char* const* proj, int nproj,
+            int64_t limit, Prepared* pr) {
+    pr->table = find_table(db, table);
+    if (!pr->table) return IMM3_ERR_NOT_FOUND;
+    int rc = build_logical_plan(pr->table->meta, preds, npreds, proj, nproj, limit, &pr->lp);
+    if (rc) return rc;
+    kernel_name(db, *pr->table, pr->lp, &pr->block_mode);
+    return 0;
+}
+
+// Fill the device plan (everything but result pointers and the bitmap).
+int fill_scan_plan(imm3_db* db, Prepared* pr) {
+    TableStore& t = *pr->table;
+    const LogicalPlan& lp = pr->lp;
+    ScanPlan& sp = pr->sp;
+    std::memset(&sp, 0, sizeof sp);
+    sp.nrows = t.nrows;
+    sp.limit = lp.limit > 0 ? lp.limit : INT64_MAX;
+    sp.row_start = t.d_row_start;
+    sp.max_block_rows = t.max_block_rows;
+    sp.nfilter = (int)lp.filters.size();
+    sp.nproj = (int)lp.proj.size();
+    std::vector<int> pfor_cols;
+    auto pfor_slot = [&](int ci) -> int {
+        if (t.cols[(size_t)ci].meta.codec != IMM3_CODEC_PFOR_INT) return -1;
+        for (size_t i = 0; i < pfor_cols.size(); i++)
+            if (pfor_cols[i] == ci) return (int)i;
+        pfor_cols.push_back(ci);
+        return (int)pfor_cols.size() - 1;
+    };
+    int lit_at = 0;
+    for (int i = 0; i < sp.nfilter; i++) {
+        const LogicalFilter& lf = lp.filters[(size_t)i];
+        const ColumnStore& c = t.cols[(size_t)lf.col_idx];
+        FilterCol& f = sp.filter[i];
+        f.width = c.meta.width;
+        f.kind = lf.kind;
+        f.pfor_slot = pfor_slot(lf.col_idx);
+        f.base = f.pfor_slot >= 0 ? nullptr : c.d_arena;
+        f.smem_off = -1;
+        if (lf.kind == kFilterStrMatch) {
+            f.nlit = (int)lf.lits.size();
+            f.lit_off = lit_at;
+            for (auto& s : lf.lits) {
+                std::memcpy(sp.lits + lit_at, s.data(), (size_t)f.width);
+                lit_at += f.width;
+            }
+        } else {
+            f.lo = (int32_t)lf.lo;
+            f.span = (uint32_t)(lf.hi - lf.lo);
+        }
+    }
+    for (int i = 0; i < sp.nproj; i++) {
+        const int ci = lp.proj[(size_t)i];
+        const ColumnStore& c = t.cols[(size_t)ci];
+        ProjCol& p = sp.proj[i];
+        p.width = c.meta.width;
+        p.pfor_slot = pfor_slot(ci);
+        p.base = p.pfor_slot >= 0 ? nullptr : c.d_arena;
+        p.filter_idx = -1;
+        for (int k = 0; k < sp.nfilter; k++)
+            if (lp.filters[(size_t)k].col_idx == ci) p.filter_idx = k;
+    }
+    sp.npfor = (int)pfor_cols.size();
+    for (int i = 0; i < sp.npfor; i++) {
+        const ColumnStore& c = t.cols[(size_t)pfor_cols[(size_t)i]];
+        sp.pfor[i].words = reinterpret_cast<const uint32_t*>(c.d_arena);
+        sp.pfor[i].word_off = c.d_word_off;
+    }
+    if (++db->epoch >= 0x3FFFFFu) {  // 22-bit tag wrapped: clear the status words once
+        if (db->d_status) CUDA_TRY(cudaMemsetAsync(db->d_status, 0, db->status_cap * sizeof(unsigned long long), db->stream));
+        db->epoch = 1;
+    }
+    sp.epoch = db->epoch;
+
+    int occ = 0;
+    if (pr->block_mode) {
+        if (t.max_block_rows > kMaxBlockRows)
+            return fail(IMM3_ERR_UNSUPPORTED, "block-mode kernel stages blocks of at most %d rows, table %s has a block of %d",
+                        kMaxBlockRows, t.meta.name.c_str(), t.max_block_rows);
+        sp.ntiles = t.nblocks;
+        pr->dyn_smem = blocks_kernel_smem_bytes(sp.npfor, t.max_block_rows);
+        CUDA_TRY(blocks_kernel_occupancy(pr->dyn_smem, &occ));
+    } else {
+        sp.ntiles = (t.nrows + kTileRows - 1) / kTileRows;
+        // TMA staging: every filter column gets a tile slot inside a stage if the ring fits the budget.
+        int stage_bytes = 0;
+        for (int i = 0; i < sp.nfilter; i++) stage_bytes += kTileRows * sp.filter[i].width;
+        int stages = 0;
+        if (!(db->flags & IMM3_OPEN_NO_TMA) && stage_bytes > 0 && stage_bytes * 2 <= 160 * 1024) {
+            stages = (48 * 1024) / stage_bytes;
+            stages = std::max(2, std::min(kMaxStages, stages));
+            int off = 0;
+            for (int i = 0; i < sp.nfilter; i++) {
+                sp.filter[i].smem_off = off;
+                off += kTileRows * sp.filter[i].width;
+            }
+        }
+        sp.stages = stages;
+        sp.stage_bytes = stage_bytes;
+        pr->dyn_smem = (size_t)stages * (size_t)stage_bytes;
+        CUDA_TRY(dense_kernel_occupancy(pr->dyn_smem, &occ));
+    }
+    if (sp.ntiles >= (int64_t)0x7FFFFFFF) return fail(IMM3_ERR_UNSUPPORTED, "too many tiles (%lld)", (long long)sp.ntiles);
+    if (occ < 1) return fail(IMM3_ERR_CUDA, "kernel does not fit on an SM (dynamic shared memory %zu bytes)", pr->dyn_smem);
+    const int64_t persistent = (int64_t)db->num_sms * occ;
+    pr->grid = (int)std::max<int64_t>(1, std::min<int64_t>(sp.ntiles, persistent));
+    if ((size_t)sp.ntiles > db->status_cap) {
+        if (db->d_status) CUDA_TRY(cudaFree(db->d_status));
+        db->d_status = nullptr;
+        size_t cap = (size_t)sp.ntiles + (size_t)sp.ntiles / 4 + 1024;
+        CUDA_TRY(cudaMalloc(&db->d_status, cap * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemsetAsync(db->d_status, 0, cap * sizeof(unsigned long long), db->stream));
+        db->status_cap = cap;
+    }
+    return 0;
+}
+
+// Launch the fused kernel and wait for the match count.
+int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total) {
+    CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
+    if (pr->block_mode) CUDA_TRY(launch_scan_blocks(pr->sp, db->d_ctrl, db->d_status, pr->grid, pr->dyn_smem, db->stream));
+    else CUDA_TRY(launch_scan_dense(pr->sp, db->d_ctrl, db->d_status, pr->grid, pr->dyn_smem, db->stream));
+    CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
+    CUDA_TRY(cudaMemcpyAsync(db->h_ctrl, db->d_ctrl, sizeof(ScanCtrl), cudaMemcpyDeviceToHost, db->stream));
+    CUDA_TRY(cudaStreamSynchronize(db->stream));
+    if (db->h_ctrl->error) return fail(IMM3_ERR_CUDA, "kernel watchdog fired (code %u)", db->h_ctrl->error);
+    float f = 0;
+    CUDA_TRY(cudaEventElapsedTime(&f, db->ev0, db->ev1));
+    *ms = f;
+    *total = (int64_t)db->h_ctrl->total;
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* imm3_last_error(void) { return last_error(); }
+int imm3_abi_version(void) { return IMM3_ABI_VERSION; }
+
+int imm3_open(const char* data_dir, const imm3_open_opts* opts, imm3_db** out) {
+    if (!data_dir || !out) return fail(IMM3_ERR_INVALID_ARG, "imm3_open: NULL argument");
+    imm3_open_opts o = {0, 0, 1, 0};
+    if (opts) o = *opts;
+    if (o.world < 1 || o.rank < 0 || o.rank >= o.world) return fail(IMM3_ERR_INVALID_ARG, "imm3_open: rank %d of world %d", o.rank, o.world);
+    std::unique_ptr<imm3_db> db(new imm3_db());
+    db->dir = data_dir;
+    db->device = o.device;
+    db->rank = o.rank;
+    db->world = o.world;
+    db->flags = o.flags;
+    db->host_only = (o.flags & IMM3_OPEN_HOST_ONLY) != 0;
+    db->host_pool.pinned_host = true;
+    int rc = load_tables(db->dir, o.rank, o.world, &db->tables);
+    if (rc) return rc;
+    if (!db->host_only) {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) {
+            cudaGetLastError();
+            return fail(IMM3_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                        e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        }
+        if (o.device < 0 || o.device >= ndev) return fail(IMM3_ERR_INVALID_ARG, "imm3_open: device %d of %d", o.device, ndev);
+        auto body = [&]() -> int {
+            CUDA_TRY(cudaSetDevice(db->device));
+            cudaDeviceProp prop;
+            CUDA_TRY(cudaGetDeviceProperties(&prop, db->device));
+            if (prop.major < 10) return fail(IMM3_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", db->device, prop.major, prop.minor);
+            db->num_sms = prop.multiProcessorCount;
+            CUDA_TRY(cudaStreamCreateWithFlags(&db->own_stream, cudaStreamNonBlocking));
+            db->stream = db->own_stream;
+            CUDA_TRY(cudaEventCreate(&db->ev0));
+            CUDA_TRY(cudaEventCreate(&db->ev1));
+            CUDA_TRY(cudaMalloc(&db->d_ctrl, sizeof(ScanCtrl)));
+            CUDA_TRY(cudaMemsetAsync(db->d_ctrl, 0, sizeof(ScanCtrl), db->stream));
+            CUDA_TRY(cudaMallocHost(&db->h_ctrl, sizeof(ScanCtrl)));
+            return upload_all(db.get());
+        };
+        rc = body();
+        if (rc) {
+            std::string why = last_error();
+            free_device_side(db.get());
+            return fail(rc, "%s", why.c_str());
+        }
+    }
+    *out = db.release();
+    return 0;
+}
+
+int imm3_close(imm3_db* db) {
+    if (!db) return 0;
+    free_device_side(db);
+    delete db;
+    return 0;
+}
+
+int imm3_table_count(imm3_db* db) { return db ? (int)db->tables.size() : IMM3_ERR_INVALID_ARG; }
+
+const char* imm3_table_name(imm3_db* db, int idx) {
+    if (!db || idx < 0 || idx >= (int)db->tables.size()) return nullptr;
+    return db->tables[(size_t)idx].meta.name.c_str();
+}
+
+int imm3_table_info(imm3_db* db, const char* table, imm3_table_desc* out) {
+    if (!db || !out) return fail(IMM3_ERR_INVALID_ARG, "imm3_table_info: NULL argument");
+    TableStore* t = find_table(db, table);
+    if (!t) return IMM3_ERR_NOT_FOUND;
+    out->ncols = (int)t->cols.size();
+    out->block_size = t->meta.block_size;
+    out->nsegments = t->nsegments;
+    out->seg_begin = t->seg_begin;
+    out->seg_end = t->seg_end;
+    out->nrows = t->nrows;
+    out->nblocks = t->nblocks;
+    out->resident_bytes = 0;
+    for (auto& c : t->cols) out->resident_bytes += c.encoded_bytes;
+    return 0;
+}
+
+int imm3_column_info(imm3_db* db, const char* table, int col_idx, imm3_column_desc* out) {
+    if (!db || !out) return fail(IMM3_ERR_INVALID_ARG, "imm3_column_info: NULL argument");
+    TableStore* t = find_table(db, table);
+    if (!t) return IMM3_ERR_NOT_FOUND;
+    if (col_idx < 0 || col_idx >= (int)t->cols.size()) return fail(IMM3_ERR_NOT_FOUND, "column index %d out of range", col_idx);
+    const ColumnStore& c = t->cols[(size_t)col_idx];
+    std::memset(out, 0, sizeof *out);
+    snprintf(out->name, sizeof out->name, "%s", c.meta.name.c_str());
+    out->column_type = c.meta.ctype;
+    out->codec = c.meta.codec;
+    out->width = c.meta.width;
+    out->encoded_bytes = c.encoded_bytes;
+    return 0;
+}
+
+int imm3_segment_file_id(imm3_db* db, const char* table, int canonical_idx, int32_t* out_id) {
+    if (!db || !out_id) return fail(IMM3_ERR_INVALID_ARG, "imm3_segment_file_id: NULL argument");
+    TableStore* t = find_table(db, table);
+    if (!t) return IMM3_ERR_NOT_FOUND;
+    if (canonical_idx < 0 || canonical_idx >= t->nsegments) return fail(IMM3_ERR_NOT_FOUND, "segment index %d out of range", canonical_idx);
+    *out_id = t->file_ids[(size_t)canonical_idx];
+    return 0;
+}
+
+int imm3_set_stream(imm3_db* db, void* cuda_stream) {
+    if (!db) return fail(IMM3_ERR_INVALID_ARG, "imm3_set_stream: db is NULL");
+    int rc = use_device(db);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(db->stream));
+    db->stream = cuda_stream ? (cudaStream_t)cuda_stream : db->own_stream;
+    return 0;
+}
+
+int imm3_sync(imm3_db* db) {
+    if (!db) return fail(IMM3_ERR_INVALID_ARG, "imm3_sync: db is NULL");
+    int rc = use_device(db);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(db->stream));
+    return 0;
+}
+
+int imm3_reupload(imm3_db* db, const char* table, const char* const* cols, int ncols, int64_t* out_bytes) {
+    if (!db) return fail(IMM3_ERR_INVALID_ARG, "imm3_reupload: db is NULL");
+    int rc = use_device(db);
+    if (rc) return rc;
+    if (!(db->flags & IMM3_OPEN_KEEP_HOST)) return fail(IMM3_ERR_STATE, "imm3_reupload needs IMM3_OPEN_KEEP_HOST");
+    TableStore* t = find_table(db, table);
+    if (!t) return IMM3_ERR_NOT_FOUND;
+    int64_t bytes = 0;
+    for (auto& c : t->cols) {
+        bool want = ncols <= 0 || !cols;
+        for (int i = 0; !want && i < ncols; i++) want = cols[i] && c.meta.name == cols[i];
+        if (!want || !c.encoded_bytes) continue;
+        CUDA_TRY(cudaMemcpyAsync(c.d_arena, c.h_mirror, (size_t)c.encoded_bytes, cudaMemcpyHostToDevice, db->stream));
+        bytes += c.encoded_bytes;
+    }
+    if (ncols > 0 && cols)
+        for (int i = 0; i < ncols; i++) {
+            bool found = false;
+            for (auto& c : t->cols) found = found || (cols[i] && c.meta.name == cols[i]);
+            if (!found) return fail(IMM3_ERR_NOT_FOUND, "Column %s does not exist in table %s", cols[i] ? cols[i] : "(null)", t->meta.name.c_str());
+        }
+    if (out_bytes) *out_bytes = bytes;
+    return 0;
+}
+
+int imm3_explain(imm3_db* db, const char* table, const imm3_pred* preds, int npreds, const char* const* proj_cols,
+                 int nproj, int64_t limit, const char** json) {
+    if (!db || !json) return fail(IMM3_ERR_INVALID_ARG, "imm3_explain: NULL argument");
+    Prepared pr;
+    int rc = prepare(db, table, preds, npreds, proj_cols, nproj, limit, &pr);
+    if (rc) return rc;
+    bool bm;
+    db->explain_buf = explain_json(pr.lp, kernel_name(db, *pr.table, pr.lp, &bm));
+    *json = db->explain_buf.c_str();
+    return 0;
+}
+
+int imm3_query_begin(imm3_db* db, const char* table, const imm3_pred* preds, int npreds, const char* const* proj_cols,
+                     int nproj, int64_t limit, imm3_result** out) {
+    if (!db || !out) return fail(IMM3_ERR_INVALID_ARG, "imm3_query_begin: NULL argument");
+    Prepared pr;
+    int rc = prepare(db, table, preds, npreds, proj_cols, nproj, limit, &pr);  // validation before any device work
+    if (rc) return rc;
+    if ((rc = use_device(db))) return rc;
+    TableStore& t = *pr.table;
+    std::unique_ptr<imm3_result> r(new imm3_result());
+    r->db = db;
+    r->ncols = (int)pr.lp.proj.size();
+    const int64_t capacity = limit > 0 ? std::min<int64_t>(limit, t.nrows) : t.nrows;
+    auto give_back = [&]() {
+        for (auto& b : r->d_cols) db->dev_pool.release(b);
+        r->d_cols.clear();
+    };
+    for (int i = 0; i < r->ncols; i++) {
+        const ColumnMeta& c = t.meta.cols[(size_t)pr.lp.proj[(size_t)i]];
+        r->names.push_back(c.name);
+        r->types.push_back(c.ctype);
+        r->widths.push_back(c.width);
+        Buf b;
+        if ((rc = db->dev_pool.acquire((size_t)capacity * (size_t)c.width, &b))) { give_back(); return rc; }
+        r->d_cols.push_back(b);
+        r->h_cols.emplace_back();
+    }
+    if (!pr.lp.always_empty && t.nrows > 0) {
+        if ((rc = fill_scan_plan(db, &pr))) { give_back(); return rc; }
+        for (int i = 0; i < r->ncols; i++) pr.sp.proj[i].out = (uint8_t*)r->d_cols[(size_t)i].p;
+        pr.sp.bitmap = nullptr;
+        if ((rc = run_scan(db, &pr, &r->device_ms, &r->local_count))) { give_back(); return rc; }
+        r->launches = 1;
+    }
+    // Algorithmic bytes: filter columns' encoded bytes once + per surviving row the
+    // project-only widths read and every projected width written (+ 4 B/block for PFOR offsets).
+    {
+        int64_t a = 0, per_row = 0;
+        std::vector<int> seen;
+        for (auto& f : pr.lp.filters) {
+            const ColumnStore& c = t.cols[(size_t)f.col_idx];
+            a += c.encoded_bytes + (c.meta.codec == IMM3_CODEC_PFOR_INT ? 4 * t.nblocks : 0);
+            seen.push_back(f.col_idx);
+        }
+        for (int ci : pr.lp.proj) {
+            per_row += t.cols[(size_t)ci].meta.width;
+            if (std::find(seen.begin(), seen.end(), ci) == seen.end()) {
+                per_row += t.cols[(size_t)ci].meta.width;
+                seen.push_back(ci);
+            }
+        }
+        r->alg_bytes = a + per_row * r->local_count;
+    }
+    *out = r.release();
+    return 0;
+}
+
+int64_t imm3_result_local_count(const imm3_result* r) { return r ? r->local_count : IMM3_ERR_INVALID_ARG; }
+
+int imm3_result_fetch(imm3_result* r, int64_t nrows) {
+    if (!r) return fail(IMM3_ERR_INVALID_ARG, "imm3_result_fetch: result is NULL");
+    if (nrows < 0 || nrows > r->local_count) return fail(IMM3_ERR_INVALID_ARG, "imm3_result_fetch: %lld rows of %lld", (long long)nrows, (long long)r->local_count);
+    imm3_db* db = r->db;
+    int rc = use_device(db);
+    if (rc) return rc;
+    for (int i = 0; i < r->ncols; i++) {
+        const size_t bytes = (size_t)nrows * (size_t)r->widths[(size_t)i];
+        if (r->h_cols[(size_t)i].cap < bytes || !r->h_cols[(size_t)i].p) {
+            db->host_pool.release(r->h_cols[(size_t)i]);
+            r->h_cols[(size_t)i] = Buf();
+            if ((rc = db->host_pool.acquire(bytes, &r->h_cols[(size_t)i]))) return rc;
+        }
+        if (bytes) CUDA_TRY(cudaMemcpyAsync(r->h_cols[(size_t)i].p, r->d_cols[(size_t)i].p, bytes, cudaMemcpyDeviceToHost, db->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(db->stream));
+    r->fetched = nrows;
+    return 0;
+}
+
+int imm3_query(imm3_db* db, const char* table, const imm3_pred* preds, int npreds, const char* const* proj_cols,
+               int nproj, int64_t limit, imm3_result** out) {
+    imm3_result* r = nullptr;
+    int rc = imm3_query_begin(db, table, preds, npreds, proj_cols, nproj, limit, &r);
+    if (rc) return rc;
+    if ((rc = imm3_result_fetch(r, r->local_count))) {
+        std::string why = last_error();
+        imm3_result_free(r);
+        return fail(rc, "%s", why.c_str());
+    }
+    *out = r;
+    return 0;
+}
+
+int imm3_query_sql(imm3_db* db, const char* sql, imm3_result** out) {
+    if (!db || !out) return fail(IMM3_ERR_INVALID_ARG, "imm3_query_sql: NULL argument");
+    ParsedQuery q;
+    int rc = parse_sql(sql, &q);
+    if (rc) return rc;
+    std::vector<const char*> proj;
+    for (auto& s : q.proj) proj.push_back(s.c_str());
+    return imm3_query(db, q.table.c_str(), q.preds.data(), (int)q.preds.size(), proj.data(), (int)proj.size(), q.limit, out);
+}
+
+int64_t imm3_result_nrows(const imm3_result* r) { return r ? r->fetched : IMM3_ERR_INVALID_ARG; }
+int imm3_result_ncols(const imm3_result* r) { return r ? r->ncols : IMM3_ERR_INVALID_ARG; }
+int imm3_result_col_type(const imm3_result* r, int c) { return (r && c >= 0 && c < r->ncols) ? r->types[(size_t)c] : IMM3_ERR_INVALID_ARG; }
+int imm3_result_col_width(const imm3_result* r, int c) { return (r && c >= 0 && c < r->ncols) ? r->widths[(size_t)c] : IMM3_ERR_INVALID_ARG; }
+const char* imm3_result_col_name(const imm3_result* r, int c) { return (r && c >= 0 && c < r->ncols) ? r->names[(size_t)c].c_str() : nullptr; }
+const void* imm3_result_col_data(const imm3_result* r, int c) { return (r && c >= 0 && c < r->ncols) ? r->h_cols[(size_t)c].p : nullptr; }
+const void* imm3_result_col_device(const imm3_result* r, int c) { return (r && c >= 0 && c < r->ncols) ? r->d_cols[(size_t)c].p : nullptr; }
+double imm3_result_device_ms(const imm3_result* r) { return r ? r->device_ms : -1.0; }
+int imm3_result_kernel_launches(const imm3_result* r) { return r ? r->launches : IMM3_ERR_INVALID_ARG; }
+int64_t imm3_result_algorithmic_bytes(const imm3_result* r) { return r ? r->alg_bytes : IMM3_ERR_INVALID_ARG; }
+
+// Row.toString = xs.mkString("Row(", ",", ")")  (Record.scala:13)
+int imm3_result_format_row(const imm3_result* r, int64_t row, char* buf, size_t buflen) {
+    if (!r || !buf || row < 0 || row >= r->fetched) return fail(IMM3_ERR_INVALID_ARG, "imm3_result_format_row: bad arguments");
+    std::string s = "Row(";
+    for (int c = 0; c < r->ncols; c++) {
+        if (c) s += ",";
+        const uint8_t* p = (const uint8_t*)r->h_cols[(size_t)c].p + (size_t)row * (size_t)r->widths[(size_t)c];
+        if (r->types[(size_t)c] == IMM3_COL_INT) {
+            int32_t v;
+            std::memcpy(&v, p, 4);
+            s += std::to_string(v);
+        } else if (r->types[(size_t)c] == IMM3_COL_TINYINT) {
+            s += std::to_string((int)(int8_t)p[0]);
+        } else {
+            s.append((const char*)p, (size_t)r->widths[(size_t)c]);
+        }
+    }
+    s += ")";
+    if (s.size() + 1 > buflen) return fail(IMM3_ERR_INVALID_ARG, "imm3_result_format_row: buffer too small (%zu needed)", s.size() + 1);
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+
+int imm3_result_free(imm3_result* r) {
+    if (!r) return 0;
+    for (auto& b : r->d_cols) r->db->dev_pool.release(b);
+    for (auto& b : r->h_cols) r->db->host_pool.release(b);
+    delete r;
+    return 0;
+}
+
+int imm3_filter_bitmap(imm3_db* db, const char* table, const imm3_pred* preds, int npreds, const uint32_t** words,
+                       int64_t* nwords, int64_t* nselected) {
+    if (!db || !words || !nwords || !nselected) return fail(IMM3_ERR_INVALID_ARG, "imm3_filter_bitmap: NULL argument");
+    Prepared pr;
+    int rc = prepare(db, table, preds, npreds, nullptr, 0, 0, &pr);
+    if (rc) return rc;
+    if ((rc = use_device(db))) return rc;
+    TableStore& t = *pr.table;
+    const size_t need_words = (size_t)((t.nrows + kTileRows - 1) / kTileRows) * (kTileRows / 32) + 2;
+    if (db->d_bitmap.cap < need_words * 4) {
+        if (db->d_bitmap.p) cudaFree(db->d_bitmap.p);
+        if (db->h_bitmap.p) cudaFreeHost(db->h_bitmap.p);
+        db->d_bitmap = Buf();
+        db->h_bitmap = Buf();
+        CUDA_TRY(cudaMalloc(&db->d_bitmap.p, need_words * 4));
+        db->d_bitmap.cap = need_words * 4;
+        CUDA_TRY(cudaMallocHost(&db->h_bitmap.p, need_words * 4));
+        db->h_bitmap.cap = need_words * 4;
+    }
+    CUDA_TRY(cudaMemsetAsync(db->d_bitmap.p, 0, need_words * 4, db->stream));
+    int64_t total = 0;
+    if (!pr.lp.always_empty && t.nrows > 0) {
+        if ((rc = fill_scan_plan(db, &pr))) return rc;
+        pr.sp.bitmap = (uint32_t*)db->d_bitmap.p;
+        pr.sp.limit = INT64_MAX;
+        double ms;
+        if ((rc = run_scan(db, &pr, &ms, &total))) return rc;
+    }
+    const size_t out_words = (size_t)((t.nrows + 31) / 32);
+    if (out_words) CUDA_TRY(cudaMemcpyAsync(db->h_bitmap.p, db->d_bitmap.p, out_words * 4, cudaMemcpyDeviceToHost, db->stream));
+    CUDA_TRY(cudaStreamSynchronize(db->stream));
+    *words = (const uint32_t*)db->h_bitmap.p;
+    *nwords = (int64_t)out_words;
+    *nselected = total;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,753 @@
+// kernels.cu — sm_100a kernels of the scan -> filter -> project path.
+//
+// Two persistent, single-pass kernels.  Both fuse, per tile:
+//   decode (ScanOp / DenseCodec*.decode / sorted-int codec; Scan.scala:28-70, DenseCodec.scala:34-74,
+//           PFORCodec.scala:12-28)
+//   -> conjunctive RangeFilter / MatchFilter into a selection mask (Select.scala:14-165)
+//   -> warp popc/ballot stream compaction into a tile-local selection vector
+//   -> device-wide exclusive prefix over tiles (decoupled look-back, so canonical row order and an
+//      exact LIMIT cut need no second pass; Project.scala:37-80)
+//   -> Project gather of the select-list columns into column-major result buffers.
+//
+//  * scan_dense_kernel  — tables whose touched columns are all DENSE_*.  Columns live in HBM as flat
+//    arrays in canonical row order, a tile is kTileRows consecutive rows, filter columns are staged
+//    tile-by-tile into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier) through a
+//    multi-stage ring, each lane owns 32 consecutive rows (= one 32-bit word of the selection
+//    bitmap) and evaluates its predicate with SIMD-within-a-register compares.
+//  * scan_blocks_kernel — anything touching a PFOR_INT column (or forced for cross-checking): a tile
+//    is one reference block; the sorted-int codec is unpacked in shared memory (bit-unpack + warp
+//    scans of the deltas), dense columns of the same rows are read row-per-lane.
+//
+// Tiles are handed out by an atomic ticket so a tile only ever waits on tiles that are already
+// running (forward progress without relying on block scheduling order).  No spin is unbounded: a
+// watchdog traps instead of hanging the GPU.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kernels.hpp"
+#include "plan.hpp"
+
+namespace imm3 {
+
+// =============================================================================================
+// PTX helpers
+// =============================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier.
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg128(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+constexpr unsigned long long kWatchdogNs = 4000000000ull;  // 4 s: far beyond any legitimate wait
+
+__device__ __noinline__ void watchdog_trap(ScanCtrl* ctrl, unsigned code) {
+    atomicExch(&ctrl->error, code);
+    __threadfence_system();
+    __trap();
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, ScanCtrl* ctrl) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = globaltimer_ns();
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > kWatchdogNs) watchdog_trap(ctrl, 1);
+    }
+}
+
+// =============================================================================================
+// Tile status words for the decoupled look-back: [63:24] value, [23:2] epoch, [1:0] state
+// =============================================================================================
+constexpr unsigned kStateNone = 0, kStateAggregate = 1, kStatePrefix = 2;
+
+__device__ __forceinline__ unsigned long long pack_status(uint32_t epoch, unsigned state, unsigned long long value) {
+    return (value << 24) | ((unsigned long long)(epoch & 0x3FFFFFu) << 2) | state;
+}
+
+// Exclusive prefix of tile `tile` (sum of the selected-row counts of all earlier tiles), computed
+// by one full warp.  Returns -1 if the LIMIT was reached while waiting (the tile is then dead: the
+// tile that set `done` had already seen every earlier tile published, so a tile still waiting on
+// an unpublished predecessor lies beyond the cut).
+__device__ long long lookback_exclusive(const unsigned long long* status, long long tile, uint32_t epoch, ScanCtrl* ctrl,
+                                        int lane) {
+    long long running = 0;
+    long long pos = tile - 1;
+    uint64_t t0 = 0;
+    unsigned spins = 0;
+    for (;;) {
+        const long long idx = pos - lane;
+        unsigned state = kStatePrefix;  // virtual tile -1 carries prefix 0
+        unsigned long long value = 0;
+        if (idx >= 0) {
+            const unsigned long long st = ld_relaxed_u64(status + idx);
+            state = (unsigned)(st & 3u);
+            if (((st >> 2) & 0x3FFFFFu) != (epoch & 0x3FFFFFu)) state = kStateNone;
+            value = st >> 24;
+        }
+        const unsigned inv = __ballot_sync(0xFFFFFFFFu, state == kStateNone);
+        const unsigned pre = __ballot_sync(0xFFFFFFFFu, state == kStatePrefix);
+        const int p = pre ? (__ffs(pre) - 1) : 32;
+        const unsigned need = (p >= 31) ? 0xFFFFFFFFu : ((2u << p) - 1u);  // lanes 0..p
+        if (inv & need) {
+            if (__any_sync(0xFFFFFFFFu, ld_relaxed_u32(&ctrl->done) != 0u)) return -1;
+            if (spins == 0) t0 = globaltimer_ns();
+            if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > kWatchdogNs) watchdog_trap(ctrl, 2);
+            __nanosleep(40);
+            continue;
+        }
+        unsigned long long c = ((need >> lane) & 1u) ? value : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+        running += (long long)c;
+        if (p < 32) return running;
+        pos -= 32;
+    }
+}
+
+// Publish this tile's count, resolve its exclusive prefix, publish the inclusive prefix, and do
+// the LIMIT / total bookkeeping.  Called by warp 0 only; returns the exclusive prefix (-1 = dead).
+__device__ long long resolve_tile(const ScanPlan& P, ScanCtrl* ctrl, unsigned long long* status, long long tile,
+                                  unsigned tile_count, int lane) {
+    long long excl = 0;
+    if (tile == 0) {
+        if (lane == 0) st_relaxed_u64(status + tile, pack_status(P.epoch, kStatePrefix, tile_count));
+    } else {
+        if (lane == 0) st_relaxed_u64(status + tile, pack_status(P.epoch, kStateAggregate, tile_count));
+        excl = lookback_exclusive(status, tile, P.epoch, ctrl, lane);
+        if (excl < 0) return -1;
+        if (lane == 0) st_relaxed_u64(status + tile, pack_status(P.epoch, kStatePrefix, (unsigned long long)excl + tile_count));
+    }
+    if (lane == 0) {
+        const long long incl = excl + (long long)tile_count;
+        if (excl < P.limit && incl >= P.limit) {  // this tile crosses the LIMIT (Project.scala:73-77)
+            ctrl->total = (unsigned long long)P.limit;
+            __threadfence();
+            atomicExch(&ctrl->done, 1u);
+        } else if (tile == P.ntiles - 1 && incl < P.limit) {
+            ctrl->total = (unsigned long long)incl;
+        }
+    }
+    return excl;
+}
+
+// Last CTA out resets the control block for the next launch on this stream.
+__device__ __forceinline__ void cta_exit(ScanCtrl* ctrl) {
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(&ctrl->exited, 1u);
+        if (prev == gridDim.x - 1) {
+            ctrl->ticket = 0;
+            ctrl->done = 0;
+            ctrl->exited = 0;
+        }
+    }
+}
+
+// Copy `n_emit` selected cells of one projected column: out[(excl + o)] = cell(sel(o)).
+template <typename RowOf, typename Load8, typename Load32>
+__device__ __forceinline__ void emit_column_generic(uint8_t* out, int width, long long excl, int n_emit, int nthreads,
+                                                    RowOf row_of, Load8 load8, Load32 load32) {
+    (void)load32;
+    for (int o = threadIdx.x; o < n_emit; o += nthreads) {
+        const int r = row_of(o);
+        uint8_t* dst = out + (excl + o) * (long long)width;
+        for (int b = 0; b < width; b++) dst[b] = (uint8_t)load8(r * width + b);
+    }
+}
+
+// =============================================================================================
+// Dense kernel
+// =============================================================================================
+struct DenseShared {
+    unsigned long long mbar[kMaxStages];
+    unsigned int ticket[kMaxStages];
+    int issued[kMaxStages];
+    unsigned int warp_cnt[kDenseThreads / 32];
+    long long tile_excl;
+    unsigned int done;
+    unsigned short sel[kTileRows];
+};
+
+// TINYINT range over the lane's 32 consecutive rows (two 16-byte chunks).  Values are biased to
+// unsigned order (x ^ 0x80) and tested in 16-bit SWAR lanes:  bit 8 of (e + 256 - lo) says e >= lo,
+// bit 8 of ((256 | hi) - e) says e <= hi.
+__device__ __forceinline__ uint32_t swar_i8_word(uint32_t x, uint32_t c1, uint32_t c2) {
+    const uint32_t y = x ^ 0x80808080u;
+    const uint32_t e = y & 0x00FF00FFu;
+    const uint32_t o = (y >> 8) & 0x00FF00FFu;
+    const uint32_t pe = (e + c1) & (c2 - e);
+    const uint32_t po = (o + c1) & (c2 - o);
+    const uint32_t z = ((pe >> 8) & 0x00010001u) | ((po >> 7) & 0x00020002u);
+    return (z | (z >> 14)) & 0xFu;
+}
+__device__ __forceinline__ uint32_t swar_i8_chunk(const uint4& v, uint32_t c1, uint32_t c2) {
+    return swar_i8_word(v.x, c1, c2) | (swar_i8_word(v.y, c1, c2) << 4) | (swar_i8_word(v.z, c1, c2) << 8) |
+           (swar_i8_word(v.w, c1, c2) << 12);
+}
+__device__ __forceinline__ uint32_t range_i32_chunk(const uint4& v, uint32_t lo, uint32_t span) {
+    return (uint32_t)((v.x - lo) <= span) | ((uint32_t)((v.y - lo) <= span) << 1) | ((uint32_t)((v.z - lo) <= span) << 2) |
+           ((uint32_t)((v.w - lo) <= span) << 3);
+}
+// Two 2-byte cells per word; a halfword of t is zero iff bit 15/31 of hz is set.
+__device__ __forceinline__ uint32_t zero_halfwords(uint32_t t) {
+    return ~(((t & 0x7FFF7FFFu) + 0x7FFF7FFFu) | t) & 0x80008000u;
+}
+
+__device__ __forceinline__ uint32_t dense_eval_filter(const ScanPlan& P, const FilterCol& f, bool staged, uint32_t stage_addr,
+                                                      long long tile_row0, int warp, int lane) {
+    // Byte offset of the lane's 32 rows inside the column tile.
+    const uint32_t lane_off = (uint32_t)((warp * 1024 + lane * 32) * f.width);
+    const uint32_t saddr = stage_addr + (uint32_t)f.smem_off + lane_off;
+    const uint8_t* gptr = f.base + tile_row0 * f.width + lane_off;
+    uint32_t mask = 0;
+    if (f.kind == kFilterI8Range) {
+        const uint32_t lo_b = ((uint32_t)f.lo ^ 0x80u) & 0xFFu;
+        const uint32_t hi_b = lo_b + f.span;
+        const uint32_t c1 = (0x100u - lo_b) * 0x00010001u;
+        const uint32_t c2 = (0x100u | hi_b) * 0x00010001u;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int q = (c + lane) & 1;  // rotate so the 8 lanes of a quarter-warp hit distinct banks
+            const uint4 v = staged ? lds128(saddr + 16u * q) : ldg128(gptr + 16 * q);
+            mask |= swar_i8_chunk(v, c1, c2) << (16 * q);
+        }
+    } else if (f.kind == kFilterI32Range) {
+        const uint32_t lo = (uint32_t)f.lo, span = f.span;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int q = (c + lane) & 7;
+            const uint4 v = staged ? lds128(saddr + 16u * q) : ldg128(gptr + 16 * q);
+            mask |= range_i32_chunk(v, lo, span) << (4 * q);
+        }
+    } else if (f.width == 2) {
+        uint32_t acc[4] = {0, 0, 0, 0};  // per chunk: 8 pass bits
+        for (int l = 0; l < f.nlit; l++) {
+            const uint32_t lit = (uint32_t)P.lits[f.lit_off + 2 * l] | ((uint32_t)P.lits[f.lit_off + 2 * l + 1] << 8);
+            const uint32_t ll = lit * 0x00010001u;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int q = (c + lane) & 3;
+                const uint4 v = staged ? lds128(saddr + 16u * q) : ldg128(gptr + 16 * q);
+                const uint32_t h0 = zero_halfwords(v.x ^ ll), h1 = zero_halfwords(v.y ^ ll);
+                const uint32_t h2 = zero_halfwords(v.z ^ ll), h3 = zero_halfwords(v.w ^ ll);
+                const uint32_t bits = ((h0 >> 15) & 1u) | ((h0 >> 30) & 2u) | (((h1 >> 15) & 1u) << 2) | (((h1 >> 30) & 2u) << 2) |
+                                      (((h2 >> 15) & 1u) << 4) | (((h2 >> 30) & 2u) << 4) | (((h3 >> 15) & 1u) << 6) |
+                                      (((h3 >> 30) & 2u) << 6);
+                acc[c] |= bits << (8 * q);
+            }
+        }
+        mask = acc[0] | acc[1] | acc[2] | acc[3];
+    } else {
+        // Generic k-byte cells: row-per-lane compare, ballot gives the bitmap word of rows 32j..32j+31,
+        // which lane j keeps.
+        const int k = f.width;
+        const uint32_t wbase_s = stage_addr + (uint32_t)f.smem_off + (uint32_t)(warp * 1024 * k);
+        const uint8_t* wbase_g = f.base + (tile_row0 + warp * 1024) * k;
+        for (int j = 0; j < 32; j++) {
+            const int r = j * 32 + lane;
+            bool hit = false;
+            for (int l = 0; l < f.nlit && !hit; l++) {
+                bool eq = true;
+                for (int b = 0; b < k; b++) {
+                    const uint32_t cell = staged ? lds_u8(wbase_s + (uint32_t)(r * k + b)) : (uint32_t)__ldg(wbase_g + r * k + b);
+                    eq = eq && (cell == (uint32_t)P.lits[f.lit_off + l * k + b]);
+                }
+                hit = eq;
+            }
+            const uint32_t w = __ballot_sync(0xFFFFFFFFu, hit);
+            if (lane == j) mask = w;
+        }
+    }
+    return mask;
+}
+
+extern __shared__ __align__(128) uint8_t dyn_smem[];
+
+__global__ void __launch_bounds__(kDenseThreads) scan_dense_kernel(const __grid_constant__ ScanPlan P, ScanCtrl* ctrl,
+                                                                     unsigned long long* status) {
+    __shared__ DenseShared S;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool staged = P.stages > 0;
+    const int ring = staged ? P.stages : 2;
+    const uint32_t dyn_addr = smem_u32(dyn_smem);
+    const unsigned ntiles = (unsigned)P.ntiles;
+
+    // Hand out the next tile to ring slot `slot` and, if staging, start its bulk copies.
+    auto refill = [&](int slot) {
+        const unsigned t = atomicAdd(&ctrl->ticket, 1u);
+        S.ticket[slot] = t;
+        S.issued[slot] = 0;
+        if (staged && t < ntiles) {
+            const uint32_t bar = smem_u32(&S.mbar[slot]);
+            uint32_t total = 0;
+            for (int i = 0; i < P.nfilter; i++)
+                if (P.filter[i].smem_off >= 0) total += (uint32_t)(kTileRows * P.filter[i].width);
+            if (total) {
+                mbar_arrive_expect_tx(bar, total);
+                for (int i = 0; i < P.nfilter; i++) {
+                    const FilterCol& f = P.filter[i];
+                    if (f.smem_off < 0) continue;
+                    const uint32_t bytes = (uint32_t)(kTileRows * f.width);
+                    tma_load_1d(dyn_addr + (uint32_t)slot * (uint32_t)P.stage_bytes + (uint32_t)f.smem_off,
+                                f.base + (long long)t * bytes, bytes, bar);
+                }
+                S.issued[slot] = 1;
+            }
+        }
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < ring; s++) mbar_init(smem_u32(&S.mbar[s]), 1);
+        fence_mbar_init();
+        for (int s = 0; s < ring; s++) refill(s);
+    }
+
+    int it = 0;
+    for (;; ++it) {
+        const int slot = it % ring;
+        if (tid == 0) S.done = ld_relaxed_u32(&ctrl->done);
+        __syncthreads();  // (A) ticket/issued/done of this slot are visible; previous tile fully retired
+        const unsigned tile = S.ticket[slot];
+        if (tile >= ntiles || S.done) break;
+        const long long tile_row0 = (long long)tile * kTileRows;
+        const uint32_t stage_addr = dyn_addr + (uint32_t)slot * (uint32_t)P.stage_bytes;
+        if (S.issued[slot]) mbar_wait(smem_u32(&S.mbar[slot]), (uint32_t)((it / ring) & 1), ctrl);
+
+        // ---- decode + conjunctive filter: one bitmap word per lane ----
+        uint32_t mask;
+        {
+            const long long row0 = tile_row0 + warp * 1024 + lane * 32;
+            const long long left = P.nrows - row0;
+            mask = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
+        }
+        for (int i = 0; i < P.nfilter; i++) {
+            const FilterCol& f = P.filter[i];
+            mask &= dense_eval_filter(P, f, staged && f.smem_off >= 0, stage_addr, tile_row0, warp, lane);
+        }
+        if (P.bitmap) P.bitmap[(tile_row0 >> 5) + warp * 32 + lane] = mask;
+
+        // ---- ranks: warp scan of popcounts, then across the 4 warps ----
+        const unsigned cnt = __popc(mask);
+        unsigned incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) S.warp_cnt[warp] = incl;
+        __syncthreads();  // (B)
+        unsigned warp_base = 0, tile_count = 0;
+#pragma unroll
+        for (int w = 0; w < kDenseThreads / 32; w++) {
+            const unsigned c = S.warp_cnt[w];
+            if (w < warp) warp_base += c;
+            tile_count += c;
+        }
+
+        // warp 0 resolves the tile's global offset while everyone builds the selection vector
+        if (warp == 0) {
+            const long long excl = resolve_tile(P, ctrl, status, tile, tile_count, lane);
+            if (lane == 0) S.tile_excl = excl;
+        }
+        if (!P.bitmap) {
+            unsigned o = warp_base + incl - cnt;
+            uint32_t m = mask;
+            const unsigned base_row = (unsigned)(warp * 1024 + lane * 32);
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                S.sel[o++] = (unsigned short)(base_row + b);
+            }
+        }
+        __syncthreads();  // (C) selection vector + tile_excl visible
+
+        // ---- Project: gather the select-list columns of the surviving rows ----
+        const long long excl = S.tile_excl;
+        if (!P.bitmap && excl >= 0 && excl < P.limit) {
+            const long long room = P.limit - excl;
+            const int n_emit = room < (long long)tile_count ? (int)room : (int)tile_count;
+            for (int pc = 0; pc < P.nproj; pc++) {
+                const ProjCol& pj = P.proj[pc];
+                const int w = pj.width;
+                const bool from_smem = staged && pj.filter_idx >= 0 && P.filter[pj.filter_idx].smem_off >= 0;
+                const uint32_t sbase = stage_addr + (from_smem ? (uint32_t)P.filter[pj.filter_idx].smem_off : 0u);
+                const uint8_t* gbase = pj.base + tile_row0 * w;
+                uint8_t* out = pj.out + excl * w;
+                if (w == 4) {
+                    for (int o = tid; o < n_emit; o += kDenseThreads) {
+                        const uint32_t r = S.sel[o];
+                        uint32_t v;
+                        if (from_smem) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sbase + r * 4u));
+                        else v = __ldg(reinterpret_cast<const uint32_t*>(gbase) + r);
+                        reinterpret_cast<uint32_t*>(out)[o] = v;
+                    }
+                } else if (w == 1) {
+                    for (int o = tid; o < n_emit; o += kDenseThreads) {
+                        const uint32_t r = S.sel[o];
+                        out[o] = (uint8_t)(from_smem ? lds_u8(sbase + r) : (uint32_t)__ldg(gbase + r));
+                    }
+                } else if (w == 2) {
+                    for (int o = tid; o < n_emit; o += kDenseThreads) {
+                        const uint32_t r = S.sel[o];
+                        uint32_t v;
+                        if (from_smem) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(sbase + r * 2u));
+                        else v = __ldg(reinterpret_cast<const uint16_t*>(gbase) + r);
+                        reinterpret_cast<uint16_t*>(out)[o] = (uint16_t)v;
+                    }
+                } else {
+                    for (int o = tid; o < n_emit; o += kDenseThreads) {
+                        const uint32_t r = S.sel[o];
+                        for (int b = 0; b < w; b++)
+                            out[(long long)o * w + b] =
+                                (uint8_t)(from_smem ? lds_u8(sbase + r * (uint32_t)w + b) : (uint32_t)__ldg(gbase + (long long)r * w + b));
+                    }
+                }
+            }
+        }
+        __syncthreads();  // (D) the slot's tile and the selection vector are free again
+        if (tid == 0) refill(slot);
+    }
+
+    // Drain bulk copies that were started for tiles this CTA will never process (LIMIT exit).
+    if (staged) {
+        for (int j = it; j < it + ring; j++) {
+            const int slot = j % ring;
+            if (S.ticket[slot] < ntiles && S.issued[slot]) mbar_wait(smem_u32(&S.mbar[slot]), (uint32_t)((j / ring) & 1), ctrl);
+        }
+    }
+    cta_exit(ctrl);
+}
+
+// =============================================================================================
+// Block-mode kernel (sorted-integer codec and general fallback)
+// =============================================================================================
+struct BlockShared {
+    unsigned int ticket;
+    unsigned int done;
+    unsigned int warp_cnt[kBlockThreads / 32];
+    long long tile_excl;
+    unsigned int vb_start;
+};
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// Decode one PFOR_INT block (PFORCodecInt.encode's inverse) into vals[0..n).
+// W: scratch for the byte-swapped words; mb_pos/mb_bits/mb_tot/mb_base: per-mini-block scratch.
+__device__ void pfor_decode_block(const PforCol& pc, long long blk, int n, uint32_t* W, uint32_t* vals,
+                                  unsigned short* mb_pos, unsigned char* mb_bits, uint32_t* mb_tot, uint32_t* mb_base,
+                                  BlockShared& S) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t w0 = pc.word_off[blk], w1 = pc.word_off[blk + 1];
+    const int nw = (int)(w1 - w0) - 2;  // PFORCodecInt.encode appends 8 zero bytes (PFORCodec.scala:20)
+    for (int i = tid; i < nw; i += kBlockThreads) W[i] = bswap32(__ldg(pc.words + w0 + i));  // putInt is big-endian
+    __syncthreads();
+    const int packed = n & ~31, nmini = packed >> 5;
+    if (tid == 0) {  // walk the headers: one word per 128-value super-block, then one per left-over mini-block
+        int ip = 1, m = 0, s = 0;
+        for (; s + 128 <= packed; s += 128) {
+            const uint32_t h = W[ip++];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int b = (int)((h >> (24 - 8 * q)) & 0xFFu);
+                mb_pos[m] = (unsigned short)ip;
+                mb_bits[m] = (unsigned char)b;
+                ip += b;
+                m++;
+            }
+        }
+        for (; s < packed; s += 32) {
+            const int b = (int)W[ip++];
+            mb_pos[m] = (unsigned short)ip;
+            mb_bits[m] = (unsigned char)b;
+            ip += b;
+            m++;
+        }
+        S.vb_start = (unsigned)ip;
+    }
+    __syncthreads();
+    for (int m = warp; m < nmini; m += kBlockThreads / 32) {
+        const int b = mb_bits[m];
+        const int p = mb_pos[m];
+        uint32_t d;
+        if (b == 32) {
+            d = W[p + lane];  // raw values, not deltas
+        } else if (b == 0) {
+            d = 0;
+        } else {
+            const int off = lane * b, wi = p + (off >> 5), sh = off & 31;
+            const uint32_t lo = W[wi];
+            const uint32_t hi = (sh + b > 32) ? W[wi + 1] : 0u;
+            d = __funnelshift_r(lo, hi, sh) & ((1u << b) - 1u);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {  // running sum of the deltas inside the mini-block
+                const uint32_t nb = __shfl_up_sync(0xFFFFFFFFu, d, o);
+                if (lane >= o) d += nb;
+            }
+        }
+        vals[m * 32 + lane] = d;
+        if (lane == 31) mb_tot[m] = d;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t base = 0;  // initvalue = 0 at every block
+        for (int m = 0; m < nmini; m++) {
+            mb_base[m] = base;
+            base = (mb_bits[m] == 32) ? mb_tot[m] : base + mb_tot[m];
+        }
+        // var-byte remainder (n % 32 values): 7-bit groups, low first, last byte has bit 7 set
+        int ip = (int)S.vb_start, sh = 0, shift = 0;
+        uint32_t v = 0;
+        for (int k = packed; k < n;) {
+            const uint32_t c = W[ip] >> sh;
+            sh += 8;
+            ip += sh >> 5;
+            sh &= 31;
+            v += (c & 127u) << shift;
+            if (c & 128u) {
+                base += v;
+                vals[k++] = base;
+                v = 0;
+                shift = 0;
+            } else {
+                shift += 7;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < packed; i += kBlockThreads) {
+        const int m = i >> 5;
+        if (mb_bits[m] != 32) vals[i] += mb_base[m];
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kBlockThreads) scan_blocks_kernel(const __grid_constant__ ScanPlan P, ScanCtrl* ctrl,
+                                                                      unsigned long long* status) {
+    __shared__ BlockShared S;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int kWarps = kBlockThreads / 32;
+
+    // carve the dynamic shared memory
+    const int maxb = (P.max_block_rows + 31) & ~31;
+    const int nmb = maxb / 32;
+    uint32_t* vals = reinterpret_cast<uint32_t*>(dyn_smem);  // [npfor][maxb]
+    uint32_t* W = vals + (size_t)(P.npfor > 0 ? P.npfor : 0) * maxb;
+    const int wcap = P.npfor > 0 ? (maxb + nmb + 64) : 0;
+    uint32_t* bm = W + wcap;          // [nmb]   selection bitmap words of the block
+    uint32_t* woff = bm + nmb;        // [nmb+1] exclusive popcount prefix
+    uint32_t* mb_tot = woff + nmb + 1;
+    uint32_t* mb_base = mb_tot + nmb;
+    unsigned short* mb_pos = reinterpret_cast<unsigned short*>(mb_base + nmb);
+    unsigned char* mb_bits = reinterpret_cast<unsigned char*>(mb_pos + nmb);
+
+    const unsigned ntiles = (unsigned)P.ntiles;
+    for (;;) {
+        if (tid == 0) {
+            S.ticket = atomicAdd(&ctrl->ticket, 1u);
+            S.done = ld_relaxed_u32(&ctrl->done);
+        }
+        __syncthreads();
+        const unsigned blk = S.ticket;
+        if (blk >= ntiles || S.done) break;
+        const long long R0 = (long long)P.row_start[blk];
+        const int n = (int)((long long)P.row_start[blk + 1] - R0);
+        const int nwords = (n + 31) >> 5;
+
+        for (int s = 0; s < P.npfor; s++)
+            pfor_decode_block(P.pfor[s], blk, n, W, vals + (size_t)s * maxb, mb_pos, mb_bits, mb_tot, mb_base, S);
+
+        // ---- conjunctive filter, row per lane; ballot builds the block's bitmap words ----
+        for (int wd = warp; wd < nwords; wd += kWarps) {
+            const int i = wd * 32 + lane;
+            bool pass = i < n;
+            for (int fi = 0; fi < P.nfilter; fi++) {
+                const FilterCol& f = P.filter[fi];
+                if (f.kind == kFilterI32Range) {
+                    uint32_t v = 0;
+                    if (pass) v = f.pfor_slot >= 0 ? vals[(size_t)f.pfor_slot * maxb + i]
+                                                   : __ldg(reinterpret_cast<const uint32_t*>(f.base) + R0 + i);
+                    pass = pass && ((v - (uint32_t)f.lo) <= f.span);
+                } else if (f.kind == kFilterI8Range) {
+                    int v = 0;
+                    if (pass) v = (int)(signed char)__ldg(f.base + R0 + i);
+                    pass = pass && ((uint32_t)(v - f.lo) <= f.span);
+                } else {
+                    bool hit = false;
+                    if (pass) {
+                        const uint8_t* cell = f.base + (R0 + i) * f.width;
+                        for (int l = 0; l < f.nlit && !hit; l++) {
+                            bool eq = true;
+                            for (int b = 0; b < f.width; b++) eq = eq && (__ldg(cell + b) == P.lits[f.lit_off + l * f.width + b]);
+                            hit = eq;
+                        }
+                    }
+                    pass = pass && hit;
+                }
+            }
+            const uint32_t word = __ballot_sync(0xFFFFFFFFu, pass);
+            if (lane == 0) bm[wd] = word;
+        }
+        __syncthreads();
+
+        // ---- exclusive scan of the word popcounts (nwords <= kBlockThreads) ----
+        const unsigned cnt = tid < nwords ? __popc(bm[tid]) : 0u;
+        unsigned incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        if (lane == 31) S.warp_cnt[warp] = incl;
+        __syncthreads();
+        unsigned warp_base = 0, tile_count = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; w++) {
+            const unsigned c = S.warp_cnt[w];
+            if (w < warp) warp_base += c;
+            tile_count += c;
+        }
+        if (tid < nwords) woff[tid] = warp_base + incl - cnt;
+
+        if (warp == 0) {
+            const long long excl = resolve_tile(P, ctrl, status, blk, tile_count, lane);
+            if (lane == 0) S.tile_excl = excl;
+        }
+        if (P.bitmap) {  // blocks start at arbitrary bit positions of the global bitmap
+            for (int wd = tid; wd < nwords; wd += kBlockThreads) {
+                const uint32_t word = bm[wd];
+                if (!word) continue;
+                const long long g = R0 + (long long)wd * 32;
+                const int sh = (int)(g & 31);
+                atomicOr(&P.bitmap[g >> 5], word << sh);
+                if (sh) atomicOr(&P.bitmap[(g >> 5) + 1], word >> (32 - sh));
+            }
+        }
+        __syncthreads();
+
+        // ---- Project ----
+        const long long excl = S.tile_excl;
+        if (!P.bitmap && excl >= 0 && excl < P.limit) {
+            const long long room = P.limit - excl;
+            const unsigned n_emit = room < (long long)tile_count ? (unsigned)room : tile_count;
+            for (int wd = warp; wd < nwords; wd += kWarps) {
+                const uint32_t word = bm[wd];
+                if (!((word >> lane) & 1u)) continue;
+                const unsigned rank = woff[wd] + __popc(word & ((1u << lane) - 1u));
+                if (rank >= n_emit) continue;
+                const int i = wd * 32 + lane;
+                for (int pc = 0; pc < P.nproj; pc++) {
+                    const ProjCol& pj = P.proj[pc];
+                    uint8_t* dst = pj.out + (excl + rank) * pj.width;
+                    if (pj.pfor_slot >= 0) {
+                        *reinterpret_cast<uint32_t*>(dst) = vals[(size_t)pj.pfor_slot * maxb + i];
+                    } else if (pj.width == 4) {
+                        *reinterpret_cast<uint32_t*>(dst) = __ldg(reinterpret_cast<const uint32_t*>(pj.base) + R0 + i);
+                    } else {
+                        const uint8_t* src = pj.base + (R0 + i) * pj.width;
+                        for (int b = 0; b < pj.width; b++) dst[b] = __ldg(src + b);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    cta_exit(ctrl);
+}
+
+// =============================================================================================
+// Launchers
+// =============================================================================================
+size_t blocks_kernel_smem_bytes(int npfor, int max_block_rows) {
+    const size_t maxb = (size_t)((max_block_rows + 31) & ~31), nmb = maxb / 32;
+    size_t words = (size_t)npfor * maxb + (npfor > 0 ? maxb + nmb + 64 : 0) + nmb + (nmb + 1) + nmb + nmb;
+    return words * 4 + nmb * 2 + nmb + 64;
+}
+
+static cudaError_t configure_once() {
+    static cudaError_t rc = [] {
+        cudaError_t e = cudaFuncSetAttribute(scan_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(scan_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    }();
+    return rc;
+}
+
+cudaError_t dense_kernel_occupancy(size_t dyn_smem, int* blocks_per_sm) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, scan_dense_kernel, kDenseThreads, dyn_smem);
+}
+cudaError_t blocks_kernel_occupancy(size_t dyn_smem, int* blocks_per_sm) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, scan_blocks_kernel, kBlockThreads, dyn_smem);
+}
+
+cudaError_t launch_scan_dense(const ScanPlan& plan, ScanCtrl* ctrl, unsigned long long* status, int grid, size_t dyn_smem,
+                              cudaStream_t stream) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    scan_dense_kernel<<<grid, kDenseThreads, dyn_smem, stream>>>(plan, ctrl, status);
+    return cudaGetLastError();
+}
+cudaError_t launch_scan_blocks(const ScanPlan& plan, ScanCtrl* ctrl, unsigned long long* status, int grid, size_t dyn_smem,
+                               cudaStream_t stream) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    scan_blocks_kernel<<<grid, kBlockThreads, dyn_smem, stream>>>(plan, ctrl, status);
+    return cudaGetLastError();
+}
+
+}  // namespace imm3

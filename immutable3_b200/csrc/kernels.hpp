@@ -1,0 +1,19 @@
+// kernels.hpp — host-callable launchers of kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+
+#include "plan.hpp"
+
+namespace imm3 {
+
+size_t blocks_kernel_smem_bytes(int npfor, int max_block_rows);
+cudaError_t dense_kernel_occupancy(size_t dyn_smem, int* blocks_per_sm);
+cudaError_t blocks_kernel_occupancy(size_t dyn_smem, int* blocks_per_sm);
+cudaError_t launch_scan_dense(const ScanPlan& plan, ScanCtrl* ctrl, unsigned long long* status, int grid, size_t dyn_smem,
+                              cudaStream_t stream);
+cudaError_t launch_scan_blocks(const ScanPlan& plan, ScanCtrl* ctrl, unsigned long long* status, int grid, size_t dyn_smem,
+                               cudaStream_t stream);
+
+}  // namespace imm3

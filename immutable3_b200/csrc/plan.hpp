@@ -1,0 +1,125 @@
+// plan.hpp — the query plan handed to the kernels (POD, passed as a __grid_constant__ parameter)
+// and the host-side planner that produces it from the reference's Query shape
+// (Query.scala:3-46 flattened by Engine.resolveSelectOps / PipelineThread.runOps,
+// Engine.scala:108-128, 237-245).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "common.hpp"
+
+namespace imm3 {
+
+constexpr int kMaxFilterCols = 8;   // distinct columns carrying predicates
+constexpr int kMaxProjCols = 16;    // select-list length (duplicates allowed, Project.scala:55-57)
+constexpr int kMaxPforCols = 4;     // PFOR_INT columns touched by one query
+constexpr int kLitPoolBytes = 512;  // MATCH literals of all filter columns, packed
+constexpr int kTileRows = 4096;     // dense kernel: rows per tile (4 warps x 32 lanes x 32 rows)
+constexpr int kDenseThreads = 128;
+constexpr int kBlockThreads = 256;  // block-mode kernel: threads per CTA
+constexpr int kMaxBlockRows = 8192; // block-mode kernel: largest reference block it stages
+constexpr int kMaxStages = 4;
+
+enum FilterKind : int32_t {
+    kFilterI8Range = 0,   // TINYINT: lo <= v <= hi   (merged GT/LT/EQ, Select.scala:53-165)
+    kFilterI32Range = 1,  // INT
+    kFilterStrMatch = 2,  // STRING(k): cell equals one of nlit literals (Select.scala:25-51)
+};
+
+struct FilterCol {
+    const uint8_t* base;  // device arena of the column (dense) or nullptr (PFOR: decoded in shared memory)
+    int32_t width;        // bytes per decoded value
+    int32_t kind;         // FilterKind
+    int32_t lo;           // ranges: inclusive lower bound
+    uint32_t span;        // ranges: (uint32)(hi - lo)
+    int32_t nlit;         // match: number of literals (each `width` bytes) ...
+    int32_t lit_off;      // ... at lits[lit_off]
+    int32_t smem_off;     // dense kernel: byte offset of this column's tile inside a stage, -1 = read from global
+    int32_t pfor_slot;    // block kernel: index into ScanPlan::pfor, -1 = dense column
+};
+
+struct ProjCol {
+    const uint8_t* base;  // device arena (dense) or nullptr (PFOR)
+    uint8_t* out;         // device result column
+    int32_t width;
+    int32_t filter_idx;   // >= 0: same column as filter[filter_idx] (its staged tile can be reused)
+    int32_t pfor_slot;
+    int32_t pad;
+};
+
+struct PforCol {
+    const uint32_t* words;     // device arena viewed as big-endian 32-bit words
+    const uint32_t* word_off;  // nblocks+1 word offsets of the blocks (file order = canonical order)
+};
+
+struct ScanPlan {
+    int64_t nrows;        // rows in the owned slice
+    int64_t limit;        // rows wanted (INT64_MAX = unlimited)
+    int64_t ntiles;       // dense: ceil(nrows / kTileRows); block mode: number of reference blocks
+    const uint64_t* row_start;  // block mode: nblocks+1 canonical row ordinals
+    uint32_t* bitmap;     // filter-bitmap mode: selection bitmap out (else nullptr)
+    uint32_t epoch;       // tags the tile-status words of this launch
+    int32_t nfilter;
+    int32_t nproj;
+    int32_t npfor;
+    int32_t stages;       // dense: TMA pipeline depth (0 = direct loads, no staging)
+    int32_t stage_bytes;  // dense: bytes of one stage
+    int32_t max_block_rows;  // block mode: rows of the largest block (shared-memory sizing)
+    int32_t pad;
+    FilterCol filter[kMaxFilterCols];
+    ProjCol proj[kMaxProjCols];
+    PforCol pfor[kMaxPforCols];
+    uint8_t lits[kLitPoolBytes];
+};
+
+// Device-resident control block of one db (reset by the last CTA of every launch).
+struct ScanCtrl {
+    unsigned int ticket;   // next tile to hand out
+    unsigned int done;     // LIMIT reached: later tiles are dead
+    unsigned int exited;   // CTAs that have left the kernel
+    unsigned int error;    // watchdog: a bounded spin expired (never hang the GPU)
+    unsigned long long total;  // rows emitted (min(limit, matches)) or matches in bitmap mode
+    unsigned long long pad;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Host-side logical plan (independent of device pointers; testable on CPU through imm3_explain).
+// ---------------------------------------------------------------------------------------------
+struct LogicalFilter {
+    int col_idx = -1;          // index in TableMeta::cols
+    int kind = 0;              // FilterKind
+    int64_t lo = 0, hi = 0;    // inclusive range after merging every GT/LT/EQ on the column
+    std::vector<std::string> lits;  // k-byte literals surviving the intersection of all Match lists
+};
+
+struct LogicalPlan {
+    const TableMeta* table = nullptr;
+    std::vector<LogicalFilter> filters;   // one per distinct filter column, first-appearance order
+    std::vector<int> proj;                // column indices in select-list order
+    int64_t limit = 0;                    // <= 0: unlimited
+    bool always_empty = false;            // a predicate can never hold (lo > hi, no literal of length k)
+    bool uses_pfor = false;
+    // Narrowed constants per input predicate, for imm3_explain and the tests of SURVEY.md §8c.
+    struct Narrowed { std::string col; int op; int32_t ival; int8_t bval; };
+    std::vector<Narrowed> narrowed;
+};
+
+int build_logical_plan(const TableMeta& table, const imm3_pred* preds, int npreds, const char* const* proj_cols,
+                       int nproj, int64_t limit, LogicalPlan* out);
+std::string explain_json(const LogicalPlan& lp, const char* kernel);
+
+// SQLParser.parseAll restatement (SQLParser.scala:8-129) for the Project form of the grammar.
+struct ParsedQuery {
+    std::string table;
+    std::vector<std::string> pred_cols;
+    std::vector<imm3_pred> preds;              // .col / .strs point into the vectors below
+    std::vector<std::vector<std::string>> pred_strs;
+    std::vector<std::vector<const char*>> pred_str_ptrs;
+    std::vector<std::string> proj;
+    int64_t limit = 0;
+    void fix_pointers();
+};
+int parse_sql(const char* sql, ParsedQuery* out);
+
+}  // namespace imm3

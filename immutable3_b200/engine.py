@@ -1,0 +1,421 @@
+"""Host-side mirror of the reference's Table / SegmentManager / Query / Engine interface.
+
+Same names and argument meaning as the Scala (so the parity tests read like reference usage):
+
+    sm = SegmentManager(data_dir)                       # SegmentManager.scala:20
+    table = sm.getTable("test_100m")                    # SegmentManager.scala:89
+    engine = Engine(sm)                                 # Engine.scala:81
+    query = Query(table.name,
+                  And(Select("age", GT(18)), Select("age", LT(30))),
+                  Project(["id", "age"], 10))           # Query.scala:3-46
+    for row in engine.execute(query): print(row)        # Engine.scala:158, SqlCli.scala:70-73
+
+Everything here is thin: the ADT is flattened to the imm3_pred list of include/imm3.h and handed to
+the CUDA library.  There is no compute and no fallback on this side.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Iterator, List, Optional, Sequence, Union
+
+import numpy as np
+
+from . import _lib as L
+
+# ------------------------------------------------------------------------------------------------
+# Query ADT (Query.scala:3-46)
+# ------------------------------------------------------------------------------------------------
+
+
+class SelectCondition:
+    pass
+
+
+@dataclass(frozen=True)
+class Match(SelectCondition):
+    values: Sequence[str]
+
+
+@dataclass(frozen=True)
+class NotMatch(SelectCondition):
+    values: Sequence[str]
+
+
+@dataclass(frozen=True)
+class EQ(SelectCondition):
+    eq: float
+
+
+@dataclass(frozen=True)
+class GT(SelectCondition):
+    gt: float
+
+
+@dataclass(frozen=True)
+class LT(SelectCondition):
+    lt: float
+
+
+class NoOp(SelectCondition):
+    pass
+
+
+class SelectADT:
+    pass
+
+
+@dataclass(frozen=True)
+class And(SelectADT):
+    op1: SelectADT
+    op2: SelectADT
+
+
+@dataclass(frozen=True)
+class Or(SelectADT):
+    op1: SelectADT
+    op2: SelectADT
+
+
+@dataclass(frozen=True)
+class Select(SelectADT):
+    col: str
+    cond: SelectCondition
+
+
+class _NoSelect(SelectADT):
+    def __repr__(self):
+        return "NoSelect"
+
+
+NoSelect = _NoSelect()
+
+
+@dataclass(frozen=True)
+class Project:
+    cols: Sequence[str]
+    limit: int = 0
+
+
+@dataclass(frozen=True)
+class Query:
+    table: str
+    select: SelectADT
+    project: Project
+
+
+def flatten_select(sel: SelectADT) -> List[Select]:
+    """Leaves of the select tree in the order PipelineThread.runOps applies them
+    (Engine.scala:237-245: rec(n2)(rec(n1)(x)) — n1 first; the AND/OR tag is ignored, so `Or`
+    is evaluated as a conjunction exactly like the reference)."""
+    if isinstance(sel, (And, Or)):
+        return flatten_select(sel.op1) + flatten_select(sel.op2)
+    if isinstance(sel, Select):
+        return [sel]
+    if sel is NoSelect or isinstance(sel, _NoSelect):
+        return []
+    raise TypeError(f"not a SelectADT: {sel!r}")
+
+
+def _pred_array(leaves: Sequence[Select]):
+    """imm3_pred[] + the ctypes objects that must stay alive while it is used."""
+    n = len(leaves)
+    arr = (L.Pred * max(1, n))()
+    keep = []
+    for i, leaf in enumerate(leaves):
+        arr[i].col = leaf.col.encode()
+        c = leaf.cond
+        if isinstance(c, GT):
+            arr[i].op, arr[i].num = L.OP_GT, float(c.gt)
+        elif isinstance(c, LT):
+            arr[i].op, arr[i].num = L.OP_LT, float(c.lt)
+        elif isinstance(c, EQ):
+            arr[i].op, arr[i].num = L.OP_EQ, float(c.eq)
+        elif isinstance(c, (Match, NotMatch)):
+            arr[i].op = L.OP_MATCH if isinstance(c, Match) else L.OP_NOTMATCH
+            strs = L.cstr_array(list(c.values))
+            keep.append(strs)
+            arr[i].strs = C.cast(strs, C.POINTER(C.c_char_p))
+            arr[i].nstrs = len(c.values)
+        else:
+            arr[i].op = L.OP_NOOP
+    return arr, n, keep
+
+
+# ------------------------------------------------------------------------------------------------
+# Row / result (Record.scala:3-14, Project.scala:17-81)
+# ------------------------------------------------------------------------------------------------
+
+
+class Row(tuple):
+    def __repr__(self):  # Row.toString: xs.mkString("Row(", ",", ")")
+        return "Row(" + ",".join(str(x) for x in self) + ")"
+
+    __str__ = __repr__
+
+
+_NP = {L.COL_INT: np.dtype("<i4"), L.COL_TINYINT: np.dtype("i1")}
+
+
+class Result:
+    """Rows of one query in canonical order, column-major (owns an imm3_result)."""
+
+    def __init__(self, handle: int, lib):
+        self._h = handle
+        self._lib = lib
+
+    # -- two-phase API (sharded execution) --
+    @property
+    def local_count(self) -> int:
+        return int(self._lib.imm3_result_local_count(self._h))
+
+    def fetch(self, nrows: int) -> "Result":
+        L.check(self._lib.imm3_result_fetch(self._h, int(nrows)))
+        return self
+
+    # -- accessors --
+    @property
+    def nrows(self) -> int:
+        return int(self._lib.imm3_result_nrows(self._h))
+
+    @property
+    def ncols(self) -> int:
+        return int(self._lib.imm3_result_ncols(self._h))
+
+    @property
+    def device_ms(self) -> float:
+        return float(self._lib.imm3_result_device_ms(self._h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.imm3_result_kernel_launches(self._h))
+
+    @property
+    def algorithmic_bytes(self) -> int:
+        return int(self._lib.imm3_result_algorithmic_bytes(self._h))
+
+    def col_name(self, c: int) -> str:
+        return self._lib.imm3_result_col_name(self._h, c).decode()
+
+    def col_type(self, c: int) -> int:
+        return int(self._lib.imm3_result_col_type(self._h, c))
+
+    def col_width(self, c: int) -> int:
+        return int(self._lib.imm3_result_col_width(self._h, c))
+
+    def column(self, c: int) -> np.ndarray:
+        """Copy of column c: int32 / int8 array, or an S<k> bytes array for STRING(k)."""
+        n, w, t = self.nrows, self.col_width(c), self.col_type(c)
+        dt = _NP.get(t, np.dtype(f"S{w}"))
+        if n == 0:
+            return np.empty(0, dtype=dt)
+        ptr = self._lib.imm3_result_col_data(self._h, c)
+        raw = (C.c_uint8 * (n * w)).from_address(ptr)
+        return np.frombuffer(raw, dtype=dt, count=n).copy()
+
+    def columns(self) -> List[np.ndarray]:
+        return [self.column(c) for c in range(self.ncols)]
+
+    def format_row(self, i: int) -> str:
+        buf = C.create_string_buffer(4096)
+        L.check(self._lib.imm3_result_format_row(self._h, i, buf, len(buf)))
+        return buf.value.decode("utf-8", "replace")
+
+    def __iter__(self) -> Iterator[Row]:
+        cols = self.columns()
+        types = [self.col_type(c) for c in range(self.ncols)]
+        for i in range(self.nrows):
+            yield Row(
+                cols[c][i].decode("utf-8", "replace") if types[c] == L.COL_STRING else int(cols[c][i])
+                for c in range(len(cols))
+            )
+
+    def __len__(self):
+        return self.nrows
+
+    def close(self):
+        if self._h:
+            self._lib.imm3_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# Table / Column / SegmentManager (Table.scala:9, Column.scala:18, SegmentManager.scala:20-112)
+# ------------------------------------------------------------------------------------------------
+
+
+@dataclass(frozen=True)
+class Column:
+    name: str
+    columnType: str  # "INT" | "TINYINT" | "STRING"
+    codec: str       # "PFOR_INT" | "DENSE_INT" | "DENSE_TINYINT" | "DENSE_STRING"
+    width: int
+    encoded_bytes: int = 0
+
+
+@dataclass(frozen=True)
+class Table:
+    name: str
+    columns: Sequence[Column]
+    blockSize: int
+    nsegments: int = 0
+    seg_begin: int = 0
+    seg_end: int = 0
+    nrows: int = 0
+    nblocks: int = 0
+    resident_bytes: int = 0
+
+    def getColumn(self, colName: str) -> Column:
+        for c in self.columns:
+            if c.name == colName:
+                return c
+        raise KeyError(f"Column {colName} does not exist in table {self.name}")
+
+
+_CT = ["INT", "TINYINT", "STRING"]
+_CODEC = ["PFOR_INT", "DENSE_INT", "DENSE_TINYINT", "DENSE_STRING"]
+
+
+class SegmentManager:
+    """`new SegmentManager(dataDir)`: discovers every table under data_dir and stages this
+    handle's canonical segment slice into HBM (imm3_open)."""
+
+    def __init__(self, dataDir: str, device: int = 0, rank: int = 0, world: int = 1, flags: int = 0):
+        self._lib = L.lib()
+        self._h = C.c_void_p()
+        opts = L.OpenOpts(device, rank, world, flags)
+        L.check(self._lib.imm3_open(str(dataDir).encode(), C.byref(opts), C.byref(self._h)))
+        self.dataDir = str(dataDir)
+        self.rank, self.world, self.flags = rank, world, flags
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def tables(self) -> List[Table]:
+        n = self._lib.imm3_table_count(self._h)
+        return [self.getTable(self._lib.imm3_table_name(self._h, i).decode()) for i in range(n)]
+
+    def getTable(self, tableName: str) -> Table:
+        d = L.TableDesc()
+        L.check(self._lib.imm3_table_info(self._h, tableName.encode(), C.byref(d)))
+        cols = []
+        for i in range(d.ncols):
+            cd = L.ColumnDesc()
+            L.check(self._lib.imm3_column_info(self._h, tableName.encode(), i, C.byref(cd)))
+            cols.append(Column(cd.name.decode(), _CT[cd.column_type], _CODEC[cd.codec], cd.width, cd.encoded_bytes))
+        return Table(tableName, cols, d.block_size, d.nsegments, d.seg_begin, d.seg_end, d.nrows, d.nblocks, d.resident_bytes)
+
+    def getTableSegmentCount(self, tableName: str) -> int:
+        return self.getTable(tableName).nsegments
+
+    def segmentFileIds(self, tableName: str) -> List[int]:
+        """Numeric ids of the segment files in canonical (file-name-sorted) order."""
+        out = []
+        v = C.c_int32()
+        for i in range(self.getTableSegmentCount(tableName)):
+            L.check(self._lib.imm3_segment_file_id(self._h, tableName.encode(), i, C.byref(v)))
+            out.append(v.value)
+        return out
+
+    def reupload(self, tableName: str, cols: Optional[Sequence[str]] = None) -> int:
+        n = C.c_int64()
+        if cols:
+            arr = L.cstr_array(list(cols))
+            L.check(self._lib.imm3_reupload(self._h, tableName.encode(), C.cast(arr, C.POINTER(C.c_char_p)), len(cols), C.byref(n)))
+        else:
+            L.check(self._lib.imm3_reupload(self._h, tableName.encode(), None, 0, C.byref(n)))
+        return n.value
+
+    def set_stream(self, cuda_stream: int):
+        L.check(self._lib.imm3_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def sync(self):
+        L.check(self._lib.imm3_sync(self._h))
+
+    def close(self):
+        if self._h:
+            self._lib.imm3_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# Engine (Engine.scala:81-232, Project branch)
+# ------------------------------------------------------------------------------------------------
+
+
+class Engine:
+    def __init__(self, sm: SegmentManager):
+        self.sm = sm
+        self._lib = sm._lib
+
+    def _call(self, fn, query: Query):
+        if not isinstance(query.project, Project):
+            raise L.Imm3Error(L.ERR_UNSUPPORTED, "only Project queries are on the scan/filter/project path")
+        preds, npreds, keep = _pred_array(flatten_select(query.select))
+        proj = L.cstr_array(list(query.project.cols))
+        out = C.c_void_p()
+        L.check(fn(self.sm.handle, query.table.encode(), preds, npreds, C.cast(proj, C.POINTER(C.c_char_p)),
+                   len(query.project.cols), int(query.project.limit), C.byref(out)))
+        del keep
+        return Result(out, self._lib)
+
+    def execute(self, query: Query) -> Result:
+        """Engine.execute: the rows of the query in canonical order (iterate for Row objects)."""
+        return self._call(self._lib.imm3_query, query)
+
+    def begin(self, query: Query) -> Result:
+        """First phase of a sharded query: kernels done, local match count known, nothing fetched."""
+        return self._call(self._lib.imm3_query_begin, query)
+
+    def execute_sql(self, sql: str) -> Result:
+        """Same text as `SqlCli -q` (SQLParser.scala)."""
+        out = C.c_void_p()
+        L.check(self._lib.imm3_query_sql(self.sm.handle, sql.encode(), C.byref(out)))
+        return Result(out, self._lib)
+
+    def filter_bitmap(self, table: str, select: SelectADT):
+        """Selection bitmap of the conjunction (uint32 words, bit i of word w = canonical row 32w+i)."""
+        preds, npreds, keep = _pred_array(flatten_select(select))
+        words = C.POINTER(C.c_uint32)()
+        nwords, nsel = C.c_int64(), C.c_int64()
+        L.check(self._lib.imm3_filter_bitmap(self.sm.handle, table.encode(), preds, npreds, C.byref(words), C.byref(nwords), C.byref(nsel)))
+        del keep
+        arr = np.ctypeslib.as_array(words, shape=(max(1, nwords.value),))[: nwords.value].copy() if nwords.value else np.empty(0, np.uint32)
+        return arr, nsel.value
+
+    def explain(self, query: Query) -> dict:
+        import json
+
+        preds, npreds, keep = _pred_array(flatten_select(query.select))
+        proj = L.cstr_array(list(query.project.cols))
+        js = C.c_char_p()
+        L.check(self._lib.imm3_explain(self.sm.handle, query.table.encode(), preds, npreds, C.cast(proj, C.POINTER(C.c_char_p)),
+                                       len(query.project.cols), int(query.project.limit), C.byref(js)))
+        del keep
+        return json.loads(js.value.decode())
