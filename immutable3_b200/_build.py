@@ -1,4 +1,4 @@
-"""Build recipe for libimm3gpu.so (nvcc, sm_100a only) and the CPU oracle.
+"""Build recipe for libimm3gpu.so (nvcc, sm_100a only).
 
 The shared library is built IN-TREE (immutable3_b200/libimm3gpu.so) so that it travels to the GPU
 box with the repo snapshot; it is git-ignored.  nvcc cross-compiles without a GPU.
@@ -14,8 +14,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libimm3gpu.so")
-ORACLE_DIR = os.path.join(ROOT, "oracle")
-ORACLE_LIB = os.path.join(ORACLE_DIR, "liborc.so")
 
 SOURCES = ["meta.cpp", "writer.cpp", "plan.cpp", "sql.cpp", "store.cpp", "kernels.cu", "engine.cu"]
 HEADERS = ["common.hpp", "json_min.hpp", "plan.hpp", "store.hpp", "kernels.hpp", "../../include/imm3.h"]
@@ -75,16 +73,6 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
-def build_oracle(force: bool = False) -> str:
-    deps = [os.path.join(ORACLE_DIR, f) for f in ("oracle.c", "oracle.h", "Makefile")]
-    if force or _stale(ORACLE_LIB, deps):
-        r = subprocess.run(["make", "-C", ORACLE_DIR, "-B", "liborc.so"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-        if r.returncode:
-            raise RuntimeError("oracle build failed:\n" + r.stdout)
-    return ORACLE_LIB
-
-
 if __name__ == "__main__":
     build_lib(force="--force" in sys.argv, verbose=True)
-    build_oracle(force="--force" in sys.argv)
     print(LIB)

@@ -22,9 +22,8 @@ def _built_libraries():
     except RuntimeError:
         if not os.path.exists(_build.LIB):
             raise
-    try:
-        _build.build_oracle()
-    except RuntimeError:
-        if not os.path.exists(_build.ORACLE_LIB):
-            raise
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import build_oracle
+
+    build_oracle.build_oracle()
     yield

@@ -1,0 +1,293 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle, bit-exact, on the
+same tables and queries — rows, values and order.  Every test needs a GPU."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from helpers import STATES, conj, make_table, oracle_preds
+from immutable3_b200 import (And, EQ, Engine, GT, Imm3Error, LT, Match, NoSelect, OPEN_FORCE_BLOCKS, OPEN_KEEP_HOST, OPEN_NO_TMA,
+                             Or, Project, Query, SegmentManager, Select)
+from immutable3_b200 import _lib as L
+from immutable3_b200.dist import limit_split
+from immutable3_b200.loader import synth_write
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = {"tma": 0, "direct": OPEN_NO_TMA, "blocks": OPEN_FORCE_BLOCKS}
+
+
+@pytest.fixture(scope="module")
+def world(tmp_path_factory):
+    d = tmp_path_factory.mktemp("gpu")
+    rng = np.random.default_rng(7)
+    tables = {}
+    tables["t"] = make_table(d, "t", 50_000, 64, 5, seed=2)                               # 156 segments: lexicographic order matters
+    tables["neg"] = make_table(d, "neg", 20_000, 32, 10, seed=3, id_mode="random")        # full int8 / int32 ranges
+    tables["p"] = make_table(d, "p", 30_000, 1024, 3, seed=4, id_codec="PFOR_INT", id_mode="steps")
+    tables["pr"] = make_table(d, "pr", 5_000, 128, 4, seed=5, id_codec="PFOR_INT", id_mode="random")  # unsorted -> b=32 raw mini-blocks
+    tables["ps"] = make_table(d, "ps", 9_000, 1000, 2, seed=6, id_codec="PFOR_INT")       # block size not a multiple of 32: var-byte tails
+    n = 12_345
+    extra = [("name:DENSE_STRING:size=5", np.array([b"alice", b"bobby", b"carol", b"dave_", b"erin#"], "S5")[rng.integers(0, 5, n)]),
+             ("code:DENSE_STRING:size=1", np.array([b"x", b"y", b"z"], "S1")[rng.integers(0, 3, n)]),
+             ("zip:DENSE_STRING:size=4", np.array([b"1234", b"9876", b"0000"], "S4")[rng.integers(0, 3, n)]),
+             ("score:DENSE_INT", rng.integers(-1000, 1000, n).astype(np.int32))]
+    tables["wide"] = make_table(d, "wide", n, 100, 7, seed=8, extra_cols=extra)
+    tables["test_100"] = make_table(d, "test_100", 100, 1024, 1000, seed=2)               # README config 1
+    tables["one"] = make_table(d, "one", 1, 8, 2, seed=2)
+    tables["tile"] = make_table(d, "tile", 8192, 1024, 1000, seed=2)                      # exactly two dense tiles
+    tables["tile1"] = make_table(d, "tile1", 4097, 1024, 1000, seed=2)
+    orc = O.Oracle(d)
+    sms = {k: SegmentManager(d, flags=f) for k, f in VARIANTS.items()}
+    yield d, tables, orc, sms
+    for s in sms.values():
+        s.close()
+    orc.close()
+
+
+def check(orc, sm, table, select, proj, limit=0, variant=""):
+    exp = orc.query(table, oracle_preds(select), proj, limit=limit)
+    with Engine(sm).execute(Query(table, select, Project(proj, limit))) as got:
+        assert got.nrows == exp.nrows, (variant, table, select, proj, limit, got.nrows, exp.nrows)
+        for c in range(len(proj)):
+            a, b = got.column(c), exp.columns[c]
+            if not np.array_equal(a, b):
+                bad = int(np.flatnonzero(a != b)[0])
+                raise AssertionError(f"{variant} {table} {select} col {proj[c]} limit {limit}: first mismatch at row {bad}: got {a[bad]!r} want {b[bad]!r}")
+        return got.nrows
+
+
+QUERIES_T = [
+    (conj(Select("age", GT(18)), Select("age", LT(30))), ["id", "age"]),                                   # C2
+    (conj(Select("state", Match(["CA"])), Select("age", GT(18)), Select("age", LT(30))), ["id", "state", "age"]),  # C3
+    (conj(Select("age", GT(0)), Select("state", Match(["DC", "CT"]))), ["age", "state"]),                  # Engine.scala:39-46
+    (Select("age", GT(30)), ["age", "state", "id"]),                                                       # Engine.scala:48-52
+    (conj(Select("id", GT(30_000)), Select("id", LT(31_500))), ["id"]),                                    # C4 shape (dense twin)
+    (Select("age", EQ(7)), ["id"]),
+    (Select("id", EQ(5 + 3 * 777)), ["id", "age", "state"]),
+    (NoSelect, ["id", "state", "age"]),
+    (NoSelect, ["age"]),
+    (Select("age", LT(1)), ["id"]),
+    (Or(Select("age", GT(50)), Select("age", LT(10))), ["id"]),                                            # OR == AND: empty
+    (Select("state", Match(["CAL"])), ["id"]),                                                             # wrong length: empty
+    (Select("age", GT(98)), ["state", "state", "id", "age", "id"]),                                        # duplicates, select-list order
+    (conj(Select("age", GT(10)), Select("id", LT(100_000)), Select("state", Match(STATES[:25])), Select("age", LT(90))), ["state", "id"]),
+]
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_dense_table_queries(world, variant):
+    d, tables, orc, sms = world
+    total = 0
+    for sel, proj in QUERIES_T:
+        total += check(orc, sms[variant], "t", sel, proj, 0, variant)
+    assert total > 50_000
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_limit_is_an_exact_cut_in_canonical_order(world, variant):
+    d, tables, orc, sms = world
+    sel = conj(Select("age", GT(18)), Select("age", LT(30)))
+    full = check(orc, sms[variant], "t", sel, ["id", "age"], 0, variant)
+    for limit in (1, 2, 10, 63, 64, 65, 4095, 4096, 4097, full - 1, full, full + 1, 10**9):
+        check(orc, sms[variant], "t", sel, ["id", "age"], limit, variant)
+    for limit in (1, 10, 49_999, 50_000, 50_001):
+        check(orc, sms[variant], "t", NoSelect, ["id"], limit, variant)
+    check(orc, sms[variant], "t", Select("age", EQ(127)), ["id"], 5, variant)  # nothing matches, LIMIT never reached
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_narrowing_and_signed_ranges(world, variant):
+    d, tables, orc, sms = world
+    for sel in [Select("age", GT(200)), Select("age", EQ(300)), Select("age", LT(1e10)), Select("age", GT(-129)), Select("age", LT(-128)),
+                Select("age", GT(126)), Select("age", LT(-127)), Select("age", EQ(-128)), Select("age", EQ(127)),
+                Select("id", GT(3e9)), Select("id", LT(3e9)), Select("id", LT(-3e9)), Select("id", GT(-3e9)), Select("id", EQ(-2**31)),
+                Select("id", EQ(2**31 - 1)), Select("id", GT(2**31 - 2)), Select("id", LT(-2**31 + 1)), Select("id", EQ(float("nan"))),
+                conj(Select("id", GT(-1000.9)), Select("id", LT(1000.9))), conj(Select("id", GT(-3e9)), Select("age", LT(-5))),
+                conj(Select("age", GT(-100)), Select("age", LT(100)), Select("age", GT(-50)), Select("age", LT(50)))]:
+        check(orc, sms[variant], "neg", sel, ["id", "age"], 0, variant)
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_string_widths_and_extra_columns(world, variant):
+    d, tables, orc, sms = world
+    for sel, proj in [
+        (Select("name", Match(["carol"])), ["id", "name"]),
+        (Select("name", Match(["alice", "erin#", "nobody"])), ["name", "code", "zip", "score"]),
+        (Select("code", Match(["y"])), ["code", "id"]),
+        (Select("zip", Match(["9876", "0000"])), ["zip", "age"]),
+        (conj(Select("zip", Match(["1234"])), Select("code", Match(["x", "z"])), Select("score", GT(0)), Select("age", LT(50)), Select("state", Match(["TX", "NY", "CA"]))), ["id", "name", "score"]),
+        (conj(Select("score", GT(-10)), Select("score", LT(10))), ["score", "name"]),
+        (NoSelect, ["name", "code", "zip", "score", "id", "state", "age"]),
+    ]:
+        check(orc, sms[variant], "wide", sel, proj, 0, variant)
+        check(orc, sms[variant], "wide", sel, proj, 17, variant)
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_edge_sizes(world, variant):
+    d, tables, orc, sms = world
+    sel = conj(Select("age", GT(18)), Select("age", LT(30)))
+    for table in ("test_100", "one", "tile", "tile1"):
+        for limit in (0, 1, 10):
+            check(orc, sms[variant], table, sel, ["id", "age"], limit, variant)
+            check(orc, sms[variant], table, NoSelect, ["id", "state", "age"], limit, variant)
+    check(orc, sms[variant], "t", NoSelect, [], 0, variant)  # empty select list: only the row count
+
+
+def test_readme_cli_query_and_row_format(world):
+    d, tables, orc, sms = world
+    sql = "select id, age from test_100 where (age > 18 and age < 30) limit 10"      # README.md:6
+    exp = orc.query("test_100", [("age", O.OP_GT, 18), ("age", O.OP_LT, 30)], ["id", "age"], limit=10, fmt_rows=10)
+    assert exp.ref_throw == 0  # inside the reference's own well-defined domain
+    for variant, sm in sms.items():
+        with Engine(sm).execute_sql(sql) as got:
+            assert [got.format_row(i) for i in range(got.nrows)] == exp.format_rows(), variant
+            assert [str(r) for r in got] == exp.format_rows()
+    with Engine(sms["tma"]).execute_sql("select state, id from t where (state = 'CA' and age > 18 and age < 30) limit 3") as got:
+        e2 = orc.query("t", [("state", O.OP_MATCH, ["CA"]), ("age", O.OP_GT, 18), ("age", O.OP_LT, 30)], ["state", "id"], limit=3, fmt_rows=3)
+        assert [got.format_row(i) for i in range(got.nrows)] == e2.format_rows()
+
+
+@pytest.mark.parametrize("table", ["p", "pr", "ps"])
+def test_sorted_int_codec_tables(world, table):
+    d, tables, orc, sms = world
+    sm = sms["tma"]  # PFOR columns always take the block-mode kernel
+    ids = tables[table]["id"]
+    lo, hi = int(np.percentile(ids, 40)), int(np.percentile(ids, 60))
+    for sel, proj in [
+        (conj(Select("id", GT(lo)), Select("id", LT(hi))), ["id"]),                                        # C4
+        (conj(Select("id", GT(lo)), Select("id", LT(hi)), Select("age", GT(18)), Select("age", LT(30))), ["id", "age", "state"]),
+        (NoSelect, ["id"]),
+        (NoSelect, ["id", "age", "state"]),
+        (Select("age", GT(90)), ["id"]),                                                                   # PFOR column only projected
+        (Select("state", Match(["CA", "NY"])), ["state", "id"]),
+        (Select("id", EQ(int(ids[len(ids) // 2]))), ["id", "age"]),
+        (Select("id", GT(3e9)), ["id"]),
+    ]:
+        for limit in (0, 1, 100, 1025):
+            check(orc, sm, table, sel, proj, limit, "pfor")
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_selection_bitmap(world, variant):
+    d, tables, orc, sms = world
+    for table, sel in [("t", conj(Select("age", GT(18)), Select("age", LT(30)))), ("t", NoSelect), ("t", Select("state", Match(["CA"]))),
+                       ("neg", Select("id", GT(0))), ("wide", Select("name", Match(["dave_"]))), ("tile1", Select("age", LT(50))),
+                       ("p", Select("id", GT(1000))), ("ps", Select("age", GT(50)))]:
+        got, nsel = Engine(sms[variant]).filter_bitmap(table, sel)
+        want, wsel = orc.filter_bitmap(table, oracle_preds(sel))
+        assert nsel == wsel and np.array_equal(got, want), (variant, table, sel)
+
+
+def test_errors_come_back_as_status_codes_not_hangs(world):
+    d, tables, orc, sms = world
+    eng = Engine(sms["tma"])
+    for q, status in [(Query("t", Select("state", GT(1)), Project(["id"])), L.ERR_UNSUPPORTED),
+                      (Query("t", Select("age", Match(["x"])), Project(["id"])), L.ERR_UNSUPPORTED),
+                      (Query("t", NoSelect, Project(["nope"])), L.ERR_NOT_FOUND),
+                      (Query("missing", NoSelect, Project(["id"])), L.ERR_NOT_FOUND)]:
+        with pytest.raises(Imm3Error) as e:
+            eng.execute(q)
+        assert e.value.status == status
+    check(orc, sms["tma"], "t", Select("age", GT(18)), ["id"], 10)  # the handle is still usable afterwards
+
+
+@pytest.mark.parametrize("nshards", [2, 3, 8])
+def test_segment_sharded_execution_matches_the_whole(world, nshards):
+    """N handles (one per rank, here all on cuda:0) over contiguous canonical slices: concatenating
+    what limit_split lets each rank emit equals the single-handle / oracle result."""
+    d, tables, orc, sms = world
+    shards = [SegmentManager(d, rank=r, world=nshards) for r in range(nshards)]
+    try:
+        for table, sel, proj in [("t", conj(Select("age", GT(18)), Select("age", LT(30))), ["id", "age"]),
+                                 ("t", conj(Select("id", GT(30_000)), Select("id", LT(31_500))), ["id"]),
+                                 ("p", Select("age", GT(50)), ["id", "state"])]:
+            for limit in (0, 1, 10, 1000, 10**7):
+                q = Query(table, sel, Project(proj, limit))
+                handles = [Engine(s).begin(q) for s in shards]
+                counts = [h.local_count for h in handles]
+                offsets, takes = limit_split(counts, limit)
+                parts = [h.fetch(t).columns() for h, t in zip(handles, takes)]
+                exp = orc.query(table, oracle_preds(sel), proj, limit=limit)
+                assert sum(takes) == exp.nrows, (table, limit, counts)
+                for c in range(len(proj)):
+                    assert np.array_equal(np.concatenate([p[c] for p in parts]), exp.columns[c]), (table, sel, limit, c)
+                for h in handles:
+                    h.close()
+    finally:
+        for s in shards:
+            s.close()
+
+
+def test_reupload_from_pinned_host_mirror(world):
+    d, tables, orc, sms = world
+    with SegmentManager(d, flags=OPEN_KEEP_HOST) as sm:
+        sel = conj(Select("age", GT(18)), Select("age", LT(30)))
+        check(orc, sm, "t", sel, ["id", "age"])
+        assert sm.reupload("t", ["age", "id"]) == 5 * 50_000
+        check(orc, sm, "t", sel, ["id", "age"])
+        assert sm.reupload("t") == 7 * 50_000
+        check(orc, sm, "p", Select("id", GT(100)), ["id"])
+        sm.reupload("p")
+        check(orc, sm, "p", Select("id", GT(100)), ["id"])
+
+
+def test_repeated_queries_reuse_buffers_and_epochs(world):
+    d, tables, orc, sms = world
+    sel = conj(Select("age", GT(18)), Select("age", LT(30)))
+    for i in range(40):
+        check(orc, sms["tma"], "t", sel, ["id", "age"], [0, 7, 5000][i % 3])
+
+
+def test_full_size_synthetic_properties(tmp_path_factory):
+    """BASELINE-shaped synthetic table (id = row index, B=1024, S=1000) at a size the oracle would need
+    minutes for: checked through size-independent properties computed with numpy from the files."""
+    d = tmp_path_factory.mktemp("syn")
+    n = 12_000_000  # 12 segments: canonical order 0,1,10,11,2,...
+    synth_write(d, "syn", n)
+    order = sorted(range(12), key=lambda i: f"id_{i}.dat")
+    age = np.concatenate([np.fromfile(d / "syn" / f"age_{i}.dat", np.int8) for i in order])
+    ids = np.concatenate([np.fromfile(d / "syn" / f"id_{i}.dat", "<i4") for i in order])
+    st = np.concatenate([np.fromfile(d / "syn" / f"state_{i}.dat", "S2") for i in order])
+    for flags in (0, OPEN_NO_TMA):
+        with SegmentManager(d, flags=flags) as sm:
+            eng = Engine(sm)
+            m = (age > 18) & (age < 30)
+            with eng.execute(Query("syn", conj(Select("age", GT(18)), Select("age", LT(30))), Project(["id", "age"]))) as r:     # C2
+                assert r.nrows == int(m.sum()) and np.array_equal(r.column(0), ids[m]) and np.array_equal(r.column(1), age[m])
+                assert r.algorithmic_bytes == n + r.nrows * 9 and r.kernel_launches == 1
+            m3 = m & (st == b"CA")
+            with eng.execute(Query("syn", conj(Select("state", Match(["CA"])), Select("age", GT(18)), Select("age", LT(30))), Project(["id", "state", "age"]))) as r:  # C3
+                assert r.nrows == int(m3.sum()) and np.array_equal(r.column(0), ids[m3]) and np.all(r.column(1) == b"CA")
+            lo, hi = n // 2 - n // 200, n // 2 + n // 200
+            with eng.execute(Query("syn", conj(Select("id", GT(lo)), Select("id", LT(hi))), Project(["id"]))) as r:             # C4, dense twin
+                mm = (ids > lo) & (ids < hi)
+                assert r.nrows == hi - lo - 1 and np.array_equal(r.column(0), ids[mm])
+            with eng.execute(Query("syn", Select("age", LT(50)), Project(["id"], 10))) as r:
+                assert np.array_equal(r.column(0), ids[age < 50][:10])
+            bm, nsel = eng.filter_bitmap("syn", Select("age", LT(50)))
+            assert nsel == int((age < 50).sum())
+            assert np.array_equal(np.unpackbits(bm.view(np.uint8), bitorder="little")[:n].astype(bool), age < 50)
+
+
+def test_full_size_sorted_int_codec_properties(tmp_path_factory):
+    d = tmp_path_factory.mktemp("synp")
+    n = 6_000_000
+    synth_write(d, "synp", n, id_codec=L.CODEC_PFOR_INT)
+    order = sorted(range(6), key=lambda i: f"id_{i}.dat")
+    age = np.concatenate([np.fromfile(d / "synp" / f"age_{i}.dat", np.int8) for i in order])
+    per = 1024 * 1000 + 1
+    ids = np.concatenate([np.arange(i * per, min(n, (i + 1) * per), dtype=np.int32) for i in order])
+    with SegmentManager(d) as sm:
+        eng = Engine(sm)
+        assert sm.getTable("synp").resident_bytes < 3.4 * n   # ~0.29 B/row for the id column
+        lo, hi = n // 2 - n // 200, n // 2 + n // 200
+        with eng.execute(Query("synp", conj(Select("id", GT(lo)), Select("id", LT(hi))), Project(["id"]))) as r:               # C4
+            mm = (ids > lo) & (ids < hi)
+            assert r.nrows == hi - lo - 1 and np.array_equal(r.column(0), ids[mm])
+        with eng.execute(Query("synp", conj(Select("age", EQ(7))), Project(["id", "age"]))) as r:
+            assert np.array_equal(r.column(0), ids[age == 7]) and np.all(r.column(1) == 7)
+        with eng.execute(Query("synp", NoSelect, Project(["id"]))) as r:
+            assert np.array_equal(r.column(0), ids)
