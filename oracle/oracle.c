@@ -78,6 +78,10 @@ int8_t orc_d2b(double d) { return (int8_t)(uint8_t)((uint32_t)orc_d2i(d) & 0xFFu
 int64_t orc_dense_decode(const uint8_t* bytes, int64_t nbytes, int width, uint8_t* out_cells) {
     uint8_t chunk[256];
     if (width <= 0 || width > (int)sizeof chunk) return -1;
+    if (nbytes % width == 0) { /* whole values only: every read fills the chunk, the cells ARE the bytes */
+        memcpy(out_cells, bytes, (size_t)nbytes);
+        return nbytes / width;
+    }
     memset(chunk, 0, (size_t)width);
     int64_t pos = 0, n = 0;
     while (pos < nbytes) {
@@ -861,18 +865,29 @@ static void run_segment(const plan_t* pl, int seg, int want_bitmap, seg_out_t* o
                 snprintf(o->errmsg, sizeof o->errmsg, "column %s shorter than batch", p->col->name);
                 goto out;
             }
+            /* `for (x <- 0 until vec.size) if (!(data(x) OP c)) vec.selected.remove(x)`: a bit survives iff the
+             * predicate holds.  Evaluated one 64-row bitmap word at a time (same result, no per-row branch). */
+#define ORC_PASS(TYPE, DATA, EXPR)                                                          \
+    do {                                                                                    \
+        const TYPE* d = (const TYPE*)(DATA);                                                \
+        for (int64_t w = 0; w < nw; w++) {                                                  \
+            const int64_t x0 = w * 64, xe = x0 + 64 < vec_size ? x0 + 64 : vec_size;        \
+            uint64_t m = 0;                                                                 \
+            for (int64_t x = x0; x < xe; x++) m |= (uint64_t)(EXPR) << (x - x0);            \
+            bits[w] &= m;                                                                   \
+        }                                                                                   \
+    } while (0)
             if (p->col->ctype == ORC_COL_INT) {
-                const int32_t* d = ints[u];
-                int32_t c = p->ival;
-                if (p->op == ORC_OP_GT) { for (int64_t x = 0; x < vec_size; x++) if (!(d[x] > c)) bits[x >> 6] &= ~(1ull << (x & 63)); }
-                else if (p->op == ORC_OP_LT) { for (int64_t x = 0; x < vec_size; x++) if (!(d[x] < c)) bits[x >> 6] &= ~(1ull << (x & 63)); }
-                else { for (int64_t x = 0; x < vec_size; x++) if (!(d[x] == c)) bits[x >> 6] &= ~(1ull << (x & 63)); }
+                const int32_t c = p->ival;
+                if (p->op == ORC_OP_GT) ORC_PASS(int32_t, ints[u], d[x] > c);
+                else if (p->op == ORC_OP_LT) ORC_PASS(int32_t, ints[u], d[x] < c);
+                else ORC_PASS(int32_t, ints[u], d[x] == c);
             } else if (p->col->ctype == ORC_COL_TINYINT) {
-                const int8_t* d = (const int8_t*)cells[u];
-                int8_t c = p->bval;
-                if (p->op == ORC_OP_GT) { for (int64_t x = 0; x < vec_size; x++) if (!(d[x] > c)) bits[x >> 6] &= ~(1ull << (x & 63)); }
-                else if (p->op == ORC_OP_LT) { for (int64_t x = 0; x < vec_size; x++) if (!(d[x] < c)) bits[x >> 6] &= ~(1ull << (x & 63)); }
-                else { for (int64_t x = 0; x < vec_size; x++) if (d[x] != c) bits[x >> 6] &= ~(1ull << (x & 63)); }
+                const int8_t c = p->bval;
+                if (p->op == ORC_OP_GT) ORC_PASS(int8_t, cells[u], d[x] > c);
+                else if (p->op == ORC_OP_LT) ORC_PASS(int8_t, cells[u], d[x] < c);
+                else ORC_PASS(int8_t, cells[u], d[x] == c);
+#undef ORC_PASS
             } else {
                 /* matchValues.contains(data(x)), Select.scala:37 — String equality; with ASCII cells and
                  * literals this is "same length k and same bytes". */
