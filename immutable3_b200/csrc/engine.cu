@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -150,7 +151,7 @@ constexpr size_t kStageBytes = 32u << 20;
 int upload_column(imm3_db* db, ColumnStore& col, int64_t nrows, uint8_t* stage[2], cudaEvent_t stage_ev[2], int* cur) {
     const bool dense = col.meta.codec != IMM3_CODEC_PFOR_INT;
     const size_t payload = (size_t)col.encoded_bytes;
-    size_t arena = dense ? (size_t)((nrows + kTileRows - 1) / kTileRows) * kTileRows * (size_t)col.meta.width : payload;
+    size_t arena = dense ? (size_t)((nrows + kDenseMaxTileRows - 1) / kDenseMaxTileRows) * kDenseMaxTileRows * (size_t)col.meta.width : payload;
     arena += 256;
     CUDA_TRY(cudaMalloc(&col.d_arena, arena));
     col.arena_bytes = arena;
@@ -359,24 +360,38 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
         pr->dyn_smem = blocks_kernel_smem_bytes(sp.npfor, t.max_block_rows);
         CUDA_TRY(blocks_kernel_occupancy(pr->dyn_smem, &occ));
     } else {
-        sp.ntiles = (t.nrows + kTileRows - 1) / kTileRows;
-        // TMA staging: every filter column gets a tile slot inside a stage if the ring fits the budget.
-        int stage_bytes = 0;
-        for (int i = 0; i < sp.nfilter; i++) stage_bytes += kTileRows * sp.filter[i].width;
+        // Tile = 8192 * W rows.  W = 2 while one stage (a tile of every filter column) stays within
+        // 32 KiB, else 1: a 3-deep TMA ring then leaves room for 2-3 CTAs (18-27 warps) per SM.  Filter
+        // sets wider than 56 KiB per stage fall back to direct global loads.
+        int row_bytes = 0;
+        for (int i = 0; i < sp.nfilter; i++) row_bytes += sp.filter[i].width;
+        int W = (kDenseTileRowsPerWord * 2 * row_bytes <= 32 * 1024) ? 2 : 1;
+        if (const char* e = getenv("IMM3_DENSE_W")) {  // tuning / A-B knob
+            int v = atoi(e);
+            if (v == 1 || v == 2 || v == 4) W = v;
+        }
+        const int tile_rows = kDenseTileRowsPerWord * W;
+        sp.words_per_lane = W;
+        sp.ntiles = (t.nrows + tile_rows - 1) / tile_rows;
+        const int stage_bytes = tile_rows * row_bytes;
         int stages = 0;
-        if (!(db->flags & IMM3_OPEN_NO_TMA) && stage_bytes > 0 && stage_bytes * 2 <= 160 * 1024) {
-            stages = (48 * 1024) / stage_bytes;
-            stages = std::max(2, std::min(kMaxStages, stages));
+        if (!(db->flags & IMM3_OPEN_NO_TMA) && stage_bytes > 0 && stage_bytes <= 56 * 1024) {
+            stages = 3;  // tile j in E, tile j+1 in F, tile j+2 in flight
+            if (const char* e = getenv("IMM3_DENSE_STAGES")) {
+                int v = atoi(e);
+                if (v >= 3 && v <= kMaxStages) stages = v;
+            }
             int off = 0;
             for (int i = 0; i < sp.nfilter; i++) {
                 sp.filter[i].smem_off = off;
-                off += kTileRows * sp.filter[i].width;
+                off += tile_rows * sp.filter[i].width;
             }
         }
+        while (stages > 3 && (size_t)stages * (size_t)stage_bytes > 200 * 1024) stages--;
         sp.stages = stages;
         sp.stage_bytes = stage_bytes;
         pr->dyn_smem = (size_t)stages * (size_t)stage_bytes;
-        CUDA_TRY(dense_kernel_occupancy(pr->dyn_smem, &occ));
+        CUDA_TRY(dense_kernel_occupancy(W, pr->dyn_smem, &occ));
     }
     if (sp.ntiles >= (int64_t)0x7FFFFFFF) return fail(IMM3_ERR_UNSUPPORTED, "too many tiles (%lld)", (long long)sp.ntiles);
     if (occ < 1) return fail(IMM3_ERR_CUDA, "kernel does not fit on an SM (dynamic shared memory %zu bytes)", pr->dyn_smem);
@@ -729,7 +744,7 @@ int imm3_filter_bitmap(imm3_db* db, const char* table, const imm3_pred* preds, i
     if (rc) return rc;
     if ((rc = use_device(db))) return rc;
     TableStore& t = *pr.table;
-    const size_t need_words = (size_t)((t.nrows + kTileRows - 1) / kTileRows) * (kTileRows / 32) + 2;
+    const size_t need_words = (size_t)((t.nrows + kDenseMaxTileRows - 1) / kDenseMaxTileRows) * (kDenseMaxTileRows / 32) + 2;
     if (db->d_bitmap.cap < need_words * 4) {
         if (db->d_bitmap.p) cudaFree(db->d_bitmap.p);
         if (db->h_bitmap.p) cudaFreeHost(db->h_bitmap.p);

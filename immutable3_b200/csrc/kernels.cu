@@ -116,42 +116,55 @@ __device__ __forceinline__ unsigned long long pack_status(uint32_t epoch, unsign
 }
 
 // Exclusive prefix of tile `tile` (sum of the selected-row counts of all earlier tiles), computed
-// by one full warp.  Returns -1 if the LIMIT was reached while waiting (the tile is then dead: the
-// tile that set `done` had already seen every earlier tile published, so a tile still waiting on
-// an unpublished predecessor lies beyond the cut).
+// by one full warp polling a window of 128 predecessor status words at a time (4 per lane).
+// Returns -1 if the LIMIT was reached while waiting (the tile is then dead: the tile that set
+// `done` had already seen every earlier tile published, so a tile still waiting on an unpublished
+// predecessor lies beyond the cut).
 __device__ long long lookback_exclusive(const unsigned long long* status, long long tile, uint32_t epoch, ScanCtrl* ctrl,
                                         int lane) {
     long long running = 0;
     long long pos = tile - 1;
     uint64_t t0 = 0;
     unsigned spins = 0;
+    const unsigned ep = epoch & 0x3FFFFFu;
     for (;;) {
-        const long long idx = pos - lane;
-        unsigned state = kStatePrefix;  // virtual tile -1 carries prefix 0
-        unsigned long long value = 0;
-        if (idx >= 0) {
-            const unsigned long long st = ld_relaxed_u64(status + idx);
-            state = (unsigned)(st & 3u);
-            if (((st >> 2) & 0x3FFFFFu) != (epoch & 0x3FFFFFu)) state = kStateNone;
-            value = st >> 24;
+        unsigned long long st[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const long long idx = pos - 4 * lane - k;  // lane 0 / k 0 is the nearest predecessor
+            st[k] = idx >= 0 ? ld_relaxed_u64(status + idx) : pack_status(epoch, kStatePrefix, 0);  // virtual tile -1: prefix 0
         }
-        const unsigned inv = __ballot_sync(0xFFFFFFFFu, state == kStateNone);
-        const unsigned pre = __ballot_sync(0xFFFFFFFFu, state == kStatePrefix);
+        unsigned long long lsum = 0;
+        bool lpre = false, linv = false;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            unsigned state = (unsigned)(st[k] & 3u);
+            if (((st[k] >> 2) & 0x3FFFFFu) != ep) state = kStateNone;
+            if (!lpre && !linv) {
+                if (state == kStateNone) linv = true;
+                else {
+                    lsum += st[k] >> 24;
+                    lpre = state == kStatePrefix;
+                }
+            }
+        }
+        const unsigned inv = __ballot_sync(0xFFFFFFFFu, linv);
+        const unsigned pre = __ballot_sync(0xFFFFFFFFu, lpre);
         const int p = pre ? (__ffs(pre) - 1) : 32;
         const unsigned need = (p >= 31) ? 0xFFFFFFFFu : ((2u << p) - 1u);  // lanes 0..p
         if (inv & need) {
             if (__any_sync(0xFFFFFFFFu, ld_relaxed_u32(&ctrl->done) != 0u)) return -1;
             if (spins == 0) t0 = globaltimer_ns();
             if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > kWatchdogNs) watchdog_trap(ctrl, 2);
-            __nanosleep(40);
+            __nanosleep(20);
             continue;
         }
-        unsigned long long c = ((need >> lane) & 1u) ? value : 0ull;
+        unsigned long long c = ((need >> lane) & 1u) ? lsum : 0ull;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
         running += (long long)c;
         if (p < 32) return running;
-        pos -= 32;
+        pos -= 128;
     }
 }
 
@@ -194,30 +207,51 @@ __device__ __forceinline__ void cta_exit(ScanCtrl* ctrl) {
     }
 }
 
-// Copy `n_emit` selected cells of one projected column: out[(excl + o)] = cell(sel(o)).
-template <typename RowOf, typename Load8, typename Load32>
-__device__ __forceinline__ void emit_column_generic(uint8_t* out, int width, long long excl, int n_emit, int nthreads,
-                                                    RowOf row_of, Load8 load8, Load32 load32) {
-    (void)load32;
-    for (int o = threadIdx.x; o < n_emit; o += nthreads) {
-        const int r = row_of(o);
-        uint8_t* dst = out + (excl + o) * (long long)width;
-        for (int b = 0; b < width; b++) dst[b] = (uint8_t)load8(r * width + b);
-    }
-}
-
 // =============================================================================================
 // Dense kernel
+//
+// CTA = 8 compute warps + 1 control warp.  A tile is 8192*W consecutive rows (W = 1, 2 or 4 bitmap
+// words per lane): warp w owns rows [w*1024*W, (w+1)*1024*W) of the tile, split into W sub-spans of
+// 1024 rows in which lane l owns rows [32*l, 32*l+32) = one 32-bit word of the selection bitmap.
+//
+// The tiles of a CTA are software-pipelined so that nothing waits on the device-wide prefix:
+//
+//   compute warps :  F(0) | F(1) E(0) | F(2) E(1) | ...
+//       F(j) "filter" : wait for tile j's bytes (TMA -> shared memory, mbarrier), evaluate the conjunction
+//                       with SWAR compares, popc + warp/CTA scan -> every lane knows the tile-local rank
+//                       of its first selected row; PUBLISH the tile count.  The lane keeps its bitmap
+//                       words and ranks in registers.
+//       E(j) "emit"   : pick up the tile's global offset (resolved while F(j+1) ran), walk the set bits
+//                       four at a time: gather the projected cells (staged filter columns from shared
+//                       memory, other columns from global memory) and store them at offset + rank.
+//                       Then recycle the tile's ring slot (ticket + TMA bulk copies).
+//   control warp  :  for each tile in order: take its count, publish it, run the decoupled look-back,
+//                    hand the exclusive offset back.  It overlaps F(j+1)/E(j) of the compute warps.
+//
+// Publishing count(j+1) BEFORE emitting tile j matters: tickets are drawn ahead (for the TMA ring), so
+// a CTA busy emitting would otherwise sit on an un-counted earlier tile that every later tile in the
+// grid has to wait for.  Hand-offs are two-entry rings guarded by mbarriers (count_full, excl_full).
 // =============================================================================================
+constexpr int kComputeThreads = 256;
+constexpr int kComputeWarps = kComputeThreads / 32;
+constexpr unsigned kNoMoreTiles = 0xFFFFFFFFu;
+
 struct DenseShared {
-    unsigned long long mbar[kMaxStages];
+    unsigned long long mbar_full[kMaxStages];  // TMA bytes of a ring slot have landed
+    unsigned long long mbar_count[2];          // compute -> control: tile_count / tile_id valid
+    unsigned long long mbar_excl[2];           // control -> compute: tile_excl valid
     unsigned int ticket[kMaxStages];
     int issued[kMaxStages];
-    unsigned int warp_cnt[kDenseThreads / 32];
-    long long tile_excl;
-    unsigned int done;
-    unsigned short sel[kTileRows];
+    unsigned int warp_cnt[2][kComputeWarps];
+    unsigned int tile_count[2];
+    unsigned int tile_id[2];
+    long long tile_excl[2];
 };
+
+__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 
 // TINYINT range over the lane's 32 consecutive rows (two 16-byte chunks).  Values are biased to
 // unsigned order (x ^ 0x80) and tested in 16-bit SWAR lanes:  bit 8 of (e + 256 - lo) says e >= lo,
@@ -239,15 +273,16 @@ __device__ __forceinline__ uint32_t range_i32_chunk(const uint4& v, uint32_t lo,
     return (uint32_t)((v.x - lo) <= span) | ((uint32_t)((v.y - lo) <= span) << 1) | ((uint32_t)((v.z - lo) <= span) << 2) |
            ((uint32_t)((v.w - lo) <= span) << 3);
 }
-// Two 2-byte cells per word; a halfword of t is zero iff bit 15/31 of hz is set.
+// Two 2-byte cells per word; a halfword of t is zero iff bit 15/31 of the result is set.
 __device__ __forceinline__ uint32_t zero_halfwords(uint32_t t) {
     return ~(((t & 0x7FFF7FFFu) + 0x7FFF7FFFu) | t) & 0x80008000u;
 }
 
-__device__ __forceinline__ uint32_t dense_eval_filter(const ScanPlan& P, const FilterCol& f, bool staged, uint32_t stage_addr,
-                                                      long long tile_row0, int warp, int lane) {
-    // Byte offset of the lane's 32 rows inside the column tile.
-    const uint32_t lane_off = (uint32_t)((warp * 1024 + lane * 32) * f.width);
+// Selection word of the lane's 32 rows for one filter column.  `span_row` = tile-relative row of the
+// 1024-row sub-span this warp is evaluating.
+__device__ __noinline__ uint32_t dense_eval_filter(const ScanPlan& P, const FilterCol& f, bool staged, uint32_t stage_addr,
+                                                      long long tile_row0, int span_row, int lane) {
+    const uint32_t lane_off = (uint32_t)((span_row + lane * 32) * f.width);  // bytes into the column tile
     const uint32_t saddr = stage_addr + (uint32_t)f.smem_off + lane_off;
     const uint8_t* gptr = f.base + tile_row0 * f.width + lane_off;
     uint32_t mask = 0;
@@ -292,8 +327,8 @@ __device__ __forceinline__ uint32_t dense_eval_filter(const ScanPlan& P, const F
         // Generic k-byte cells: row-per-lane compare, ballot gives the bitmap word of rows 32j..32j+31,
         // which lane j keeps.
         const int k = f.width;
-        const uint32_t wbase_s = stage_addr + (uint32_t)f.smem_off + (uint32_t)(warp * 1024 * k);
-        const uint8_t* wbase_g = f.base + (tile_row0 + warp * 1024) * k;
+        const uint32_t wbase_s = stage_addr + (uint32_t)f.smem_off + (uint32_t)(span_row * k);
+        const uint8_t* wbase_g = f.base + (tile_row0 + span_row) * k;
         for (int j = 0; j < 32; j++) {
             const int r = j * 32 + lane;
             bool hit = false;
@@ -312,161 +347,238 @@ __device__ __forceinline__ uint32_t dense_eval_filter(const ScanPlan& P, const F
     return mask;
 }
 
+// One projected cell of width <= 8 as a 64-bit value, from the staged tile or from global memory.
+__device__ __forceinline__ unsigned long long load_cell(bool from_smem, uint32_t sbase, const uint8_t* gbase, uint32_t r, int w) {
+    if (w == 4) {
+        uint32_t v;
+        if (from_smem) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sbase + r * 4u));
+        else v = __ldg(reinterpret_cast<const uint32_t*>(gbase) + r);
+        return v;
+    }
+    if (w == 1) return from_smem ? lds_u8(sbase + r) : (uint32_t)__ldg(gbase + r);
+    if (w == 2) {
+        uint32_t v;
+        if (from_smem) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(sbase + r * 2u));
+        else v = __ldg(reinterpret_cast<const uint16_t*>(gbase) + r);
+        return v;
+    }
+    unsigned long long v = 0;  // 3,5,6,7,8: byte-wise, little-endian packing
+    for (int b = 0; b < w; b++)
+        v |= (unsigned long long)(from_smem ? lds_u8(sbase + r * (uint32_t)w + b) : (uint32_t)__ldg(gbase + (long long)r * w + b)) << (8 * b);
+    return v;
+}
+__device__ __forceinline__ void store_cell(uint8_t* out, long long idx, int w, unsigned long long v) {
+    if (w == 4) reinterpret_cast<uint32_t*>(out)[idx] = (uint32_t)v;
+    else if (w == 1) out[idx] = (uint8_t)v;
+    else if (w == 2) reinterpret_cast<uint16_t*>(out)[idx] = (uint16_t)v;
+    else
+        for (int b = 0; b < w; b++) out[idx * w + b] = (uint8_t)(v >> (8 * b));
+}
+
 extern __shared__ __align__(128) uint8_t dyn_smem[];
 
-__global__ void __launch_bounds__(kDenseThreads) scan_dense_kernel(const __grid_constant__ ScanPlan P, ScanCtrl* ctrl,
+template <int W>
+__global__ void __launch_bounds__(kDenseThreads, 3) scan_dense_kernel(const __grid_constant__ ScanPlan P, ScanCtrl* ctrl,
                                                                      unsigned long long* status) {
+    constexpr int kTile = kDenseTileRowsPerWord * W;  // rows per tile
+    constexpr int kWarpSpan = 1024 * W;               // rows per compute warp
     __shared__ DenseShared S;
+    const uint32_t ring_addr = smem_u32(dyn_smem);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool is_ctrl = warp == kComputeWarps;
     const bool staged = P.stages > 0;
-    const int ring = staged ? P.stages : 2;
-    const uint32_t dyn_addr = smem_u32(dyn_smem);
+    const int ring = staged ? P.stages : 3;
     const unsigned ntiles = (unsigned)P.ntiles;
 
-    // Hand out the next tile to ring slot `slot` and, if staging, start its bulk copies.
-    auto refill = [&](int slot) {
-        const unsigned t = atomicAdd(&ctrl->ticket, 1u);
-        S.ticket[slot] = t;
-        S.issued[slot] = 0;
-        if (staged && t < ntiles) {
-            const uint32_t bar = smem_u32(&S.mbar[slot]);
-            uint32_t total = 0;
-            for (int i = 0; i < P.nfilter; i++)
-                if (P.filter[i].smem_off >= 0) total += (uint32_t)(kTileRows * P.filter[i].width);
-            if (total) {
-                mbar_arrive_expect_tx(bar, total);
+    if (tid == 0) {
+        for (int s = 0; s < kMaxStages; s++) mbar_init(smem_u32(&S.mbar_full[s]), 1);
+        for (int e = 0; e < 2; e++) {
+            mbar_init(smem_u32(&S.mbar_count[e]), 1);
+            mbar_init(smem_u32(&S.mbar_excl[e]), 1);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (is_ctrl) {
+        // ---------------- control warp: counts in, exclusive offsets out ----------------
+        for (unsigned j = 0;; j++) {
+            const int e = (int)(j & 1u);
+            mbar_wait(smem_u32(&S.mbar_count[e]), (j >> 1) & 1u, ctrl);
+            const unsigned cnt = S.tile_count[e];
+            if (cnt == kNoMoreTiles) break;
+            const long long excl = resolve_tile(P, ctrl, status, S.tile_id[e], cnt, lane);
+            if (lane == 0) {
+                S.tile_excl[e] = excl;
+                mbar_arrive(smem_u32(&S.mbar_excl[e]));
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------- compute warps ----------------
+        // Hand out the next tile to ring slot `slot` and, if staging, start its bulk copies (thread 0).
+        auto refill = [&](int slot) {
+            unsigned t = kNoMoreTiles;
+            if (!ld_relaxed_u32(&ctrl->done)) t = atomicAdd(&ctrl->ticket, 1u);  // after LIMIT: stop drawing tiles
+            S.ticket[slot] = t;
+            S.issued[slot] = 0;
+            if (staged && t < ntiles) {
+                const uint32_t bar = smem_u32(&S.mbar_full[slot]);
+                mbar_arrive_expect_tx(bar, (uint32_t)P.stage_bytes);
                 for (int i = 0; i < P.nfilter; i++) {
                     const FilterCol& f = P.filter[i];
-                    if (f.smem_off < 0) continue;
-                    const uint32_t bytes = (uint32_t)(kTileRows * f.width);
-                    tma_load_1d(dyn_addr + (uint32_t)slot * (uint32_t)P.stage_bytes + (uint32_t)f.smem_off,
+                    const uint32_t bytes = (uint32_t)(kTile * f.width);
+                    tma_load_1d(ring_addr + (uint32_t)slot * (uint32_t)P.stage_bytes + (uint32_t)f.smem_off,
                                 f.base + (long long)t * bytes, bytes, bar);
                 }
                 S.issued[slot] = 1;
             }
-        }
-    };
+        };
+        if (tid == 0)
+            for (int s = 0; s < ring; s++) refill(s);
+        bar_sync(1, kComputeThreads);
 
-    if (tid == 0) {
-        for (int s = 0; s < ring; s++) mbar_init(smem_u32(&S.mbar[s]), 1);
-        fence_mbar_init();
-        for (int s = 0; s < ring; s++) refill(s);
-    }
+        // Per-lane state of the tile being filtered (cur) and of the tile waiting to be emitted (prev).
+        uint32_t m_cur[W], m_prev[W];
+        unsigned rank_cur[W], rank_prev[W];
+        long long row0_cur = 0, row0_prev = 0;
+        int slot_cur = 0, slot_prev = 0;
+        int slotF = 0;
+        uint32_t parF = 0;
 
-    int it = 0;
-    for (;; ++it) {
-        const int slot = it % ring;
-        if (tid == 0) S.done = ld_relaxed_u32(&ctrl->done);
-        __syncthreads();  // (A) ticket/issued/done of this slot are visible; previous tile fully retired
-        const unsigned tile = S.ticket[slot];
-        if (tile >= ntiles || S.done) break;
-        const long long tile_row0 = (long long)tile * kTileRows;
-        const uint32_t stage_addr = dyn_addr + (uint32_t)slot * (uint32_t)P.stage_bytes;
-        if (S.issued[slot]) mbar_wait(smem_u32(&S.mbar[slot]), (uint32_t)((it / ring) & 1), ctrl);
-
-        // ---- decode + conjunctive filter: one bitmap word per lane ----
-        uint32_t mask;
-        {
-            const long long row0 = tile_row0 + warp * 1024 + lane * 32;
-            const long long left = P.nrows - row0;
-            mask = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
-        }
-        for (int i = 0; i < P.nfilter; i++) {
-            const FilterCol& f = P.filter[i];
-            mask &= dense_eval_filter(P, f, staged && f.smem_off >= 0, stage_addr, tile_row0, warp, lane);
-        }
-        if (P.bitmap) P.bitmap[(tile_row0 >> 5) + warp * 32 + lane] = mask;
-
-        // ---- ranks: warp scan of popcounts, then across the 4 warps ----
-        const unsigned cnt = __popc(mask);
-        unsigned incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += n;
-        }
-        if (lane == 31) S.warp_cnt[warp] = incl;
-        __syncthreads();  // (B)
-        unsigned warp_base = 0, tile_count = 0;
-#pragma unroll
-        for (int w = 0; w < kDenseThreads / 32; w++) {
-            const unsigned c = S.warp_cnt[w];
-            if (w < warp) warp_base += c;
-            tile_count += c;
-        }
-
-        // warp 0 resolves the tile's global offset while everyone builds the selection vector
-        if (warp == 0) {
-            const long long excl = resolve_tile(P, ctrl, status, tile, tile_count, lane);
-            if (lane == 0) S.tile_excl = excl;
-        }
-        if (!P.bitmap) {
-            unsigned o = warp_base + incl - cnt;
-            uint32_t m = mask;
-            const unsigned base_row = (unsigned)(warp * 1024 + lane * 32);
-            while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                S.sel[o++] = (unsigned short)(base_row + b);
+        // F(j): returns false when the CTA has run out of tiles.
+        auto filter_tile = [&](unsigned j) -> bool {
+            const int e = (int)(j & 1u);
+            const int slot = slotF;
+            const unsigned tile = S.ticket[slot];
+            if (tile >= ntiles) {
+                if (tid == 0) {
+                    S.tile_count[e] = kNoMoreTiles;
+                    mbar_arrive(smem_u32(&S.mbar_count[e]));
+                }
+                return false;
             }
-        }
-        __syncthreads();  // (C) selection vector + tile_excl visible
+            const long long tile_row0 = (long long)tile * kTile;
+            const uint32_t stage_addr = ring_addr + (uint32_t)slot * (uint32_t)P.stage_bytes;
+            if (S.issued[slot]) mbar_wait(smem_u32(&S.mbar_full[slot]), parF, ctrl);
+            if (++slotF == ring) { slotF = 0; parF ^= 1u; }
 
-        // ---- Project: gather the select-list columns of the surviving rows ----
-        const long long excl = S.tile_excl;
-        if (!P.bitmap && excl >= 0 && excl < P.limit) {
-            const long long room = P.limit - excl;
-            const int n_emit = room < (long long)tile_count ? (int)room : (int)tile_count;
-            for (int pc = 0; pc < P.nproj; pc++) {
-                const ProjCol& pj = P.proj[pc];
-                const int w = pj.width;
-                const bool from_smem = staged && pj.filter_idx >= 0 && P.filter[pj.filter_idx].smem_off >= 0;
-                const uint32_t sbase = stage_addr + (from_smem ? (uint32_t)P.filter[pj.filter_idx].smem_off : 0u);
-                const uint8_t* gbase = pj.base + tile_row0 * w;
-                uint8_t* out = pj.out + excl * w;
-                if (w == 4) {
-                    for (int o = tid; o < n_emit; o += kDenseThreads) {
-                        const uint32_t r = S.sel[o];
-                        uint32_t v;
-                        if (from_smem) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sbase + r * 4u));
-                        else v = __ldg(reinterpret_cast<const uint32_t*>(gbase) + r);
-                        reinterpret_cast<uint32_t*>(out)[o] = v;
-                    }
-                } else if (w == 1) {
-                    for (int o = tid; o < n_emit; o += kDenseThreads) {
-                        const uint32_t r = S.sel[o];
-                        out[o] = (uint8_t)(from_smem ? lds_u8(sbase + r) : (uint32_t)__ldg(gbase + r));
-                    }
-                } else if (w == 2) {
-                    for (int o = tid; o < n_emit; o += kDenseThreads) {
-                        const uint32_t r = S.sel[o];
-                        uint32_t v;
-                        if (from_smem) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(sbase + r * 2u));
-                        else v = __ldg(reinterpret_cast<const uint16_t*>(gbase) + r);
-                        reinterpret_cast<uint16_t*>(out)[o] = (uint16_t)v;
-                    }
-                } else {
-                    for (int o = tid; o < n_emit; o += kDenseThreads) {
-                        const uint32_t r = S.sel[o];
-                        for (int b = 0; b < w; b++)
-                            out[(long long)o * w + b] =
-                                (uint8_t)(from_smem ? lds_u8(sbase + r * (uint32_t)w + b) : (uint32_t)__ldg(gbase + (long long)r * w + b));
+            // decode + conjunctive filter: W bitmap words per lane, then ranks
+            unsigned incl[W], sub_tot[W];
+            unsigned warp_total = 0;
+#pragma unroll
+            for (int s = 0; s < W; s++) {
+                const int span_row = warp * kWarpSpan + s * 1024;
+                const long long left = P.nrows - (tile_row0 + span_row + lane * 32);
+                uint32_t mask = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
+                for (int i = 0; i < P.nfilter; i++)
+                    mask &= dense_eval_filter(P, P.filter[i], staged, stage_addr, tile_row0, span_row, lane);
+                m_cur[s] = mask;
+                if (P.bitmap) P.bitmap[((tile_row0 + span_row) >> 5) + lane] = mask;
+                unsigned x = __popc(mask);
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned n = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                    if (lane >= o) x += n;
+                }
+                incl[s] = x;
+                sub_tot[s] = __shfl_sync(0xFFFFFFFFu, x, 31);
+                warp_total += sub_tot[s];
+            }
+            if (lane == 0) S.warp_cnt[e][warp] = warp_total;
+            bar_sync(1, kComputeThreads);
+            unsigned warp_base = 0, tile_count = 0;
+#pragma unroll
+            for (int w = 0; w < kComputeWarps; w++) {
+                const unsigned c = S.warp_cnt[e][w];
+                if (w < warp) warp_base += c;
+                tile_count += c;
+            }
+            if (tid == 0) {  // publish the count as early as possible: the control warp starts the look-back
+                S.tile_count[e] = tile_count;
+                S.tile_id[e] = tile;
+                mbar_arrive(smem_u32(&S.mbar_count[e]));
+            }
+#pragma unroll
+            for (int s = 0; s < W; s++) {  // tile-local rank of the lane's first selected row of word s
+                rank_cur[s] = warp_base + incl[s] - __popc(m_cur[s]);
+                warp_base += sub_tot[s];
+            }
+            row0_cur = tile_row0;
+            slot_cur = slot;
+            return true;
+        };
+
+        // E(j): emit the rows of the tile held in *_prev and recycle its ring slot.
+        auto emit_tile = [&](unsigned j) {
+            const int e = (int)(j & 1u);
+            mbar_wait(smem_u32(&S.mbar_excl[e]), (j >> 1) & 1u, ctrl);
+            const long long excl = S.tile_excl[e];
+            const uint32_t stage_addr = ring_addr + (uint32_t)slot_prev * (uint32_t)P.stage_bytes;
+            if (!P.bitmap && excl >= 0 && excl < P.limit) {
+#pragma unroll
+                for (int s = 0; s < W; s++) {
+                    uint32_t mm = m_prev[s];
+                    const unsigned iters = (__reduce_max_sync(0xFFFFFFFFu, (unsigned)__popc(mm)) + 3u) >> 2;
+                    long long g = excl + rank_prev[s];  // global ordinal of the lane's next selected row
+                    const uint32_t row_base = (uint32_t)(warp * kWarpSpan + s * 1024 + lane * 32);
+                    for (unsigned it = 0; it < iters; it++) {
+                        uint32_t r[4];
+                        bool ok[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            ok[k] = mm != 0u;
+                            r[k] = row_base + (uint32_t)(ok[k] ? (__ffs(mm) - 1) : 0);
+                            mm &= mm - 1u;
+                        }
+                        for (int pc = 0; pc < P.nproj; pc++) {
+                            const ProjCol& pj = P.proj[pc];
+                            const int w = pj.width;
+                            const bool from_smem = staged && pj.filter_idx >= 0;
+                            const uint32_t sbase = stage_addr + (from_smem ? (uint32_t)P.filter[pj.filter_idx].smem_off : 0u);
+                            const uint8_t* gbase = pj.base + row0_prev * w;
+                            if (w <= 8) {
+                                unsigned long long v[4];
+#pragma unroll
+                                for (int k = 0; k < 4; k++) v[k] = ok[k] ? load_cell(from_smem, sbase, gbase, r[k], w) : 0ull;  // 4 gathers in flight
+#pragma unroll
+                                for (int k = 0; k < 4; k++)
+                                    if (ok[k] && g + k < P.limit) store_cell(pj.out, g + k, w, v[k]);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 4; k++)
+                                    if (ok[k] && g + k < P.limit)
+                                        for (int b = 0; b < w; b++)
+                                            pj.out[(g + k) * w + b] = (uint8_t)(from_smem ? lds_u8(sbase + r[k] * (uint32_t)w + b)
+                                                                                          : (uint32_t)__ldg(gbase + (long long)r[k] * w + b));
+                            }
+                        }
+                        g += 4;
                     }
                 }
             }
-        }
-        __syncthreads();  // (D) the slot's tile and the selection vector are free again
-        if (tid == 0) refill(slot);
-    }
+            bar_sync(1, kComputeThreads);  // every warp is done with the slot's bytes
+            if (tid == 0) refill(slot_prev);
+        };
 
-    // Drain bulk copies that were started for tiles this CTA will never process (LIMIT exit).
-    if (staged) {
-        for (int j = it; j < it + ring; j++) {
-            const int slot = j % ring;
-            if (S.ticket[slot] < ntiles && S.issued[slot]) mbar_wait(smem_u32(&S.mbar[slot]), (uint32_t)((j / ring) & 1), ctrl);
+        unsigned j = 0;
+        bool more = filter_tile(0);
+        while (more) {
+#pragma unroll
+            for (int s = 0; s < W; s++) {
+                m_prev[s] = m_cur[s];
+                rank_prev[s] = rank_cur[s];
+            }
+            row0_prev = row0_cur;
+            slot_prev = slot_cur;
+            const bool next = filter_tile(j + 1);
+            emit_tile(j);
+            more = next;
+            j++;
         }
     }
+    __syncthreads();
     cta_exit(ctrl);
 }
 
@@ -717,17 +829,23 @@ size_t blocks_kernel_smem_bytes(int npfor, int max_block_rows) {
 
 static cudaError_t configure_once() {
     static cudaError_t rc = [] {
-        cudaError_t e = cudaFuncSetAttribute(scan_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(scan_dense_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(scan_dense_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(scan_dense_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(scan_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     }();
     return rc;
 }
 
-cudaError_t dense_kernel_occupancy(size_t dyn_smem, int* blocks_per_sm) {
+cudaError_t dense_kernel_occupancy(int words_per_lane, size_t dyn_smem, int* blocks_per_sm) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, scan_dense_kernel, kDenseThreads, dyn_smem);
+    if (words_per_lane == 4) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, scan_dense_kernel<4>, kDenseThreads, dyn_smem);
+    if (words_per_lane == 2) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, scan_dense_kernel<2>, kDenseThreads, dyn_smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, scan_dense_kernel<1>, kDenseThreads, dyn_smem);
 }
 cudaError_t blocks_kernel_occupancy(size_t dyn_smem, int* blocks_per_sm) {
     cudaError_t e = configure_once();
@@ -739,7 +857,9 @@ cudaError_t launch_scan_dense(const ScanPlan& plan, ScanCtrl* ctrl, unsigned lon
                               cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    scan_dense_kernel<<<grid, kDenseThreads, dyn_smem, stream>>>(plan, ctrl, status);
+    if (plan.words_per_lane == 4) scan_dense_kernel<4><<<grid, kDenseThreads, dyn_smem, stream>>>(plan, ctrl, status);
+    else if (plan.words_per_lane == 2) scan_dense_kernel<2><<<grid, kDenseThreads, dyn_smem, stream>>>(plan, ctrl, status);
+    else scan_dense_kernel<1><<<grid, kDenseThreads, dyn_smem, stream>>>(plan, ctrl, status);
     return cudaGetLastError();
 }
 cudaError_t launch_scan_blocks(const ScanPlan& plan, ScanCtrl* ctrl, unsigned long long* status, int grid, size_t dyn_smem,

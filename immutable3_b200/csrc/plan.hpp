@@ -15,8 +15,9 @@ constexpr int kMaxFilterCols = 8;   // distinct columns carrying predicates
 constexpr int kMaxProjCols = 16;    // select-list length (duplicates allowed, Project.scala:55-57)
 constexpr int kMaxPforCols = 4;     // PFOR_INT columns touched by one query
 constexpr int kLitPoolBytes = 512;  // MATCH literals of all filter columns, packed
-constexpr int kTileRows = 4096;     // dense kernel: rows per tile (4 warps x 32 lanes x 32 rows)
-constexpr int kDenseThreads = 128;
+constexpr int kDenseTileRowsPerWord = 8192;  // dense kernel: 8 compute warps x 32 lanes x 32 rows per bitmap word
+constexpr int kDenseMaxTileRows = 4 * kDenseTileRowsPerWord;  // tile = 8192 * W rows, W in {1, 2, 4}
+constexpr int kDenseThreads = 288;  // 8 compute warps + 1 control warp (tickets, TMA, look-back)
 constexpr int kBlockThreads = 256;  // block-mode kernel: threads per CTA
 constexpr int kMaxBlockRows = 8192; // block-mode kernel: largest reference block it stages
 constexpr int kMaxStages = 4;
@@ -56,7 +57,7 @@ struct PforCol {
 struct ScanPlan {
     int64_t nrows;        // rows in the owned slice
     int64_t limit;        // rows wanted (INT64_MAX = unlimited)
-    int64_t ntiles;       // dense: ceil(nrows / kTileRows); block mode: number of reference blocks
+    int64_t ntiles;       // dense: ceil(nrows / (8192 * W)); block mode: number of reference blocks
     const uint64_t* row_start;  // block mode: nblocks+1 canonical row ordinals
     uint32_t* bitmap;     // filter-bitmap mode: selection bitmap out (else nullptr)
     uint32_t epoch;       // tags the tile-status words of this launch
@@ -66,7 +67,7 @@ struct ScanPlan {
     int32_t stages;       // dense: TMA pipeline depth (0 = direct loads, no staging)
     int32_t stage_bytes;  // dense: bytes of one stage
     int32_t max_block_rows;  // block mode: rows of the largest block (shared-memory sizing)
-    int32_t pad;
+    int32_t words_per_lane;  // dense: W (tile = 8192 * W rows)
     FilterCol filter[kMaxFilterCols];
     ProjCol proj[kMaxProjCols];
     PforCol pfor[kMaxPforCols];

@@ -136,6 +136,23 @@ def test_edge_sizes(world, variant):
     check(orc, sms[variant], "t", NoSelect, [], 0, variant)  # empty select list: only the row count
 
 
+@pytest.mark.parametrize("w,stages", [(1, 3), (1, 4), (2, 3), (2, 4), (4, 3), (4, 4)])
+def test_dense_tile_shapes(world, w, stages, monkeypatch):
+    """Every tile size (8192*W rows) and TMA ring depth gives the same rows: multi-round selection vectors
+    (NoSelect fills a tile with matches), partial last tiles, LIMIT cuts inside and across tiles."""
+    d, tables, orc, sms = world
+    monkeypatch.setenv("IMM3_DENSE_W", str(w))
+    monkeypatch.setenv("IMM3_DENSE_STAGES", str(stages))
+    for variant in ("tma", "direct"):
+        for sel, proj in QUERIES_T[:5] + [(NoSelect, ["id", "state", "age"])]:
+            for limit in (0, 10, 8191, 8193, 20_000):
+                check(orc, sms[variant], "t", sel, proj, limit, f"{variant}/W{w}/S{stages}")
+        check(orc, sms[variant], "wide", Select("name", Match(["carol"])), ["id", "name", "zip"], 0, f"{variant}/W{w}")
+        got, nsel = Engine(sms[variant]).filter_bitmap("t", Select("age", LT(50)))
+        want, wsel = orc.filter_bitmap("t", oracle_preds(Select("age", LT(50))))
+        assert nsel == wsel and np.array_equal(got, want)
+
+
 def test_readme_cli_query_and_row_format(world):
     d, tables, orc, sms = world
     sql = "select id, age from test_100 where (age > 18 and age < 30) limit 10"      # README.md:6
