@@ -43,6 +43,13 @@ WORKLOADS = {
     "c3": ("C3 test_100m: select id, state, age from test_100m where (state = 'CA' and age > 18 and age < 30)", "DENSE_INT"),
     "c4": ("C4 sorted-int-codec id: select id from t where (id > L and id < H), 1% window", "PFOR_INT"),
     "c4dense": ("C4 dense-id twin: select id from t where (id > L and id < H), 1% window", "DENSE_INT"),
+    # experiments (same test_100m table as c2): isolate the cost of each stage of the fused kernel
+    "x_age": ("X select age where (age > 18 and age < 30)", "DENSE_INT"),
+    "x_id": ("X select id where (age > 18 and age < 30)", "DENSE_INT"),
+    "x_count": ("X select <nothing> where (age > 18 and age < 30)", "DENSE_INT"),
+    "x_none": ("X select id, age where age = 127 (no match)", "DENSE_INT"),
+    "x_all": ("X select id, age (no predicate)", "DENSE_INT"),
+    "x_1pct": ("X select id, age where age = 7", "DENSE_INT"),
 }
 
 
@@ -51,6 +58,17 @@ def build_query(workload: str, table: str, total_rows: int):
 
     if workload == "c2":
         return Query(table, And(Select("age", GT(18)), Select("age", LT(30))), Project(["id", "age"]))
+    if workload.startswith("x_"):
+        from immutable3_b200 import EQ, NoSelect
+        sel = And(Select("age", GT(18)), Select("age", LT(30)))
+        proj = {"x_age": ["age"], "x_id": ["id"], "x_count": []}.get(workload, ["id", "age"])
+        if workload == "x_none":
+            sel = Select("age", EQ(127))
+        if workload == "x_all":
+            sel = NoSelect
+        if workload == "x_1pct":
+            sel = Select("age", EQ(7))
+        return Query(table, sel, Project(proj))
     if workload == "c3":
         return Query(table, And(And(Select("state", Match(["CA"])), Select("age", GT(18))), Select("age", LT(30))),
                      Project(["id", "state", "age"]))
@@ -82,7 +100,8 @@ def canonical_ids(nseg: int):
 
 def data_dir_for(args, world: int) -> str:
     base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
-    return os.path.join(base, f"imm3_bench_{args.workload}_{args.rows}x{world}")
+    kind = "c2" if args.workload in ("c2", "c3") or args.workload.startswith("x_") else args.workload
+    return os.path.join(base, f"imm3_bench_{kind}_{args.rows}x{world}")
 
 
 def ensure_table(args, rank: int, world: int, barrier):
@@ -94,7 +113,7 @@ def ensure_table(args, rank: int, world: int, barrier):
 
     total = args.rows * world
     d = data_dir_for(args, world)
-    table = "test_100m" if args.workload in ("c2", "c3") else "test_ids"
+    table = "test_100m" if args.workload in ("c2", "c3") or args.workload.startswith("x_") else "test_ids"
     marker = os.path.join(d, table, f".complete_{rank}_{world}")
     codec = L.CODEC_PFOR_INT if WORKLOADS[args.workload][1] == "PFOR_INT" else L.CODEC_DENSE_INT
     nseg = synth_segments(total, BLOCK, SEGMENT)

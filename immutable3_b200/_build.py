@@ -41,19 +41,19 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build_lib(force: bool = False, verbose: bool = False) -> str:
+def build_lib(force: bool = False, verbose: bool = False, extra_flags=(), out_path: str = LIB, objdir_name: str = "build") -> str:
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
-    if not force and not _stale(LIB, deps):
-        return LIB
-    objdir = os.path.join(HERE, "build")
+    if not force and not _stale(out_path, deps):
+        return out_path
+    objdir = os.path.join(HERE, objdir_name)
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for s in srcs:
         o = os.path.join(objdir, os.path.basename(s) + ".o")
         objs.append(o)
-        cmd = [_nvcc(), *NVCC_FLAGS, "-x", "cu", "-c", s, "-o", o]
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra_flags, "-x", "cu", "-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for cmd, p in procs:
@@ -61,7 +61,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         log.append("$ " + " ".join(cmd) + "\n" + out)
         if p.returncode:
             raise RuntimeError("nvcc failed:\n" + log[-1])
-    link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out_path, *objs]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log.append("$ " + " ".join(link) + "\n" + r.stdout)
     if r.returncode:
@@ -70,7 +70,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    return LIB
+    return out_path
 
 
 if __name__ == "__main__":

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libimm3gpu.so")
+LIB_PATH = os.environ.get("IMM3_LIB") or os.path.join(HERE, "libimm3gpu.so")  # IMM3_LIB: experiment builds
 
 OK = 0
 ERR_NOT_FOUND, ERR_UNSUPPORTED, ERR_BAD_FORMAT, ERR_CUDA, ERR_OOM, ERR_INVALID_ARG, ERR_IO, ERR_STATE = range(-1, -9, -1)

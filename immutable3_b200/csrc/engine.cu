@@ -112,6 +112,7 @@ struct imm3_db {
     int num_sms = 0;
     BufPool dev_pool, host_pool;
     Buf d_bitmap, h_bitmap;
+    Buf d_span_cnt, d_tile_cnt, d_tile_off;  // multi-pass pipeline scratch (grow-only)
     std::string explain_buf;
 };
 
@@ -248,6 +249,9 @@ void free_device_side(imm3_db* db) {
     db->dev_pool.release_all();
     db->host_pool.release_all();
     if (db->d_bitmap.p) cudaFree(db->d_bitmap.p);
+    if (db->d_span_cnt.p) cudaFree(db->d_span_cnt.p);
+    if (db->d_tile_cnt.p) cudaFree(db->d_tile_cnt.p);
+    if (db->d_tile_off.p) cudaFree(db->d_tile_off.p);
     if (db->h_bitmap.p) cudaFreeHost(db->h_bitmap.p);
     if (db->d_status) cudaFree(db->d_status);
     if (db->d_ctrl) cudaFree(db->d_ctrl);
@@ -263,6 +267,8 @@ struct Prepared {
     TableStore* table = nullptr;
     LogicalPlan lp;
     bool block_mode = false;
+    bool multipass = false;   // dense tables: filter -> scan -> emit kernels instead of the fused single pass
+    int grid_emit = 0;
     ScanPlan sp;
     size_t dyn_smem = 0;
     int grid = 0;
@@ -276,6 +282,18 @@ const char* kernel_name(const imm3_db* db, const TableStore& t, const LogicalPla
     return blocks ? "scan_blocks" : ((db->flags & IMM3_OPEN_NO_TMA) ? "scan_dense(direct)" : "scan_dense(tma)");
 }
 
+// Dense tables have two execution paths.  The fused single-pass kernel stops early once a LIMIT is
+// satisfied; the three-kernel pipeline (filter -> scan -> emit) has no cross-CTA dependencies and is the
+// faster one whenever the whole table has to be scanned anyway.
+bool choose_multipass(const LogicalPlan& lp, bool block_mode) {
+    if (block_mode) return false;
+    if (const char* e = getenv("IMM3_PATH")) {
+        if (!strcmp(e, "fused")) return false;
+        if (!strcmp(e, "multi")) return true;
+    }
+    return lp.limit <= 0 || lp.limit > (1 << 20);
+}
+
 int prepare(imm3_db* db, const char* table, const imm3_pred* preds, int npreds, const char* const* proj, int nproj,
             int64_t limit, Prepared* pr) {
     pr->table = find_table(db, table);
@@ -283,6 +301,7 @@ int prepare(imm3_db* db, const char* table, const imm3_pred* preds, int npreds, 
     int rc = build_logical_plan(pr->table->meta, preds, npreds, proj, nproj, limit, &pr->lp);
     if (rc) return rc;
     kernel_name(db, *pr->table, pr->lp, &pr->block_mode);
+    pr->multipass = choose_multipass(pr->lp, pr->block_mode);
     return 0;
 }
 
@@ -350,6 +369,7 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
         db->epoch = 1;
     }
     sp.epoch = db->epoch;
+    if (const char* e = getenv("IMM3_DEBUG")) sp.debug = (uint32_t)atoi(e);
 
     int occ = 0;
     if (pr->block_mode) {
@@ -375,23 +395,43 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
         sp.ntiles = (t.nrows + tile_rows - 1) / tile_rows;
         const int stage_bytes = tile_rows * row_bytes;
         int stages = 0;
-        if (!(db->flags & IMM3_OPEN_NO_TMA) && stage_bytes > 0 && stage_bytes <= 56 * 1024) {
-            stages = 3;  // tile j in E, tile j+1 in F, tile j+2 in flight
-            if (const char* e = getenv("IMM3_DENSE_STAGES")) {
-                int v = atoi(e);
-                if (v >= 3 && v <= kMaxStages) stages = v;
-            }
+        const bool can_stage = !(db->flags & IMM3_OPEN_NO_TMA) && stage_bytes > 0 && stage_bytes <= 56 * 1024;
+        if (can_stage) {
             int off = 0;
             for (int i = 0; i < sp.nfilter; i++) {
                 sp.filter[i].smem_off = off;
                 off += tile_rows * sp.filter[i].width;
             }
         }
-        while (stages > 3 && (size_t)stages * (size_t)stage_bytes > 200 * 1024) stages--;
-        sp.stages = stages;
-        sp.stage_bytes = stage_bytes;
-        pr->dyn_smem = (size_t)stages * (size_t)stage_bytes;
-        CUDA_TRY(dense_kernel_occupancy(W, pr->dyn_smem, &occ));
+        if (pr->multipass) {
+            // K1 streams: as deep a ring as ~96 KiB allows (tiles are statically strided, so depth is free)
+            if (can_stage) stages = std::max(2, std::min(kMaxFilterStages, (96 * 1024) / stage_bytes));
+            if (const char* e = getenv("IMM3_FILTER_STAGES")) {
+                int v = atoi(e);
+                if (can_stage && v >= 2 && v <= kMaxFilterStages && (size_t)v * stage_bytes <= 200 * 1024) stages = v;
+            }
+            sp.stages = stages;
+            sp.stage_bytes = stage_bytes;
+            pr->dyn_smem = (size_t)stages * (size_t)stage_bytes;
+            CUDA_TRY(filter_kernel_occupancy(W, pr->dyn_smem, &occ));
+            int occ_emit = 0;
+            CUDA_TRY(emit_kernel_occupancy(&occ_emit));
+            const int64_t nspans = sp.ntiles * (tile_rows / 1024);
+            pr->grid_emit = (int)std::max<int64_t>(1, std::min<int64_t>((nspans + 7) / 8, (int64_t)db->num_sms * std::max(1, occ_emit)));
+        } else {
+            if (can_stage) {
+                stages = 3;  // tile j in E, tile j+1 in F, tile j+2 in flight
+                if (const char* e = getenv("IMM3_DENSE_STAGES")) {
+                    int v = atoi(e);
+                    if (v >= 3 && v <= kMaxStages) stages = v;
+                }
+                while (stages > 3 && 16 * 1024 + (size_t)stages * (size_t)stage_bytes > 200 * 1024) stages--;
+            }
+            sp.stages = stages;
+            sp.stage_bytes = stage_bytes;
+            pr->dyn_smem = 16 * 1024 + (size_t)stages * (size_t)stage_bytes;  // warp-private selection lists + TMA ring
+            CUDA_TRY(dense_kernel_occupancy(W, pr->dyn_smem, &occ));
+        }
     }
     if (sp.ntiles >= (int64_t)0x7FFFFFFF) return fail(IMM3_ERR_UNSUPPORTED, "too many tiles (%lld)", (long long)sp.ntiles);
     if (occ < 1) return fail(IMM3_ERR_CUDA, "kernel does not fit on an SM (dynamic shared memory %zu bytes)", pr->dyn_smem);
@@ -408,12 +448,46 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
     return 0;
 }
 
-// Launch the fused kernel and wait for the match count.
-int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total) {
-    CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
-    if (pr->block_mode) CUDA_TRY(launch_scan_blocks(pr->sp, db->d_ctrl, db->d_status, pr->grid, pr->dyn_smem, db->stream));
-    else CUDA_TRY(launch_scan_dense(pr->sp, db->d_ctrl, db->d_status, pr->grid, pr->dyn_smem, db->stream));
-    CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
+int ensure_buf(Buf* b, size_t bytes) {
+    if (b->cap >= bytes) return 0;
+    if (b->p) cudaFree(b->p);
+    *b = Buf();
+    size_t cap = bytes + bytes / 8 + 4096;
+    CUDA_TRY(cudaMalloc(&b->p, cap));
+    b->cap = cap;
+    return 0;
+}
+
+// Launch the kernels of one query and wait for the match count.
+int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launches) {
+    if (pr->multipass) {
+        const int64_t tile_rows = (int64_t)kDenseTileRowsPerWord * pr->sp.words_per_lane;
+        const int64_t ntiles = pr->sp.ntiles, nspans = ntiles * (tile_rows / 1024);
+        int rc;
+        if (!pr->sp.bitmap) {
+            if ((rc = ensure_buf(&db->d_bitmap, (size_t)(ntiles * tile_rows / 32 + 2) * 4))) return rc;
+            pr->sp.bitmap = (uint32_t*)db->d_bitmap.p;
+        }
+        if ((rc = ensure_buf(&db->d_span_cnt, (size_t)nspans * 4))) return rc;
+        if ((rc = ensure_buf(&db->d_tile_cnt, (size_t)ntiles * 4))) return rc;
+        if ((rc = ensure_buf(&db->d_tile_off, (size_t)(ntiles + 1) * 8))) return rc;
+        CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
+        CUDA_TRY(launch_filter(pr->sp, pr->sp.bitmap, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p, pr->grid, pr->dyn_smem, db->stream));
+        CUDA_TRY(launch_tile_scan((const uint32_t*)db->d_tile_cnt.p, (unsigned long long*)db->d_tile_off.p, ntiles, pr->sp.limit, db->d_ctrl, db->stream));
+        *launches = 2;
+        if (pr->sp.nproj > 0) {
+            CUDA_TRY(launch_emit(pr->sp, pr->sp.bitmap, (const uint32_t*)db->d_span_cnt.p, (const unsigned long long*)db->d_tile_off.p,
+                                 (int)(tile_rows / 1024), nspans, pr->grid_emit, db->stream));
+            *launches = 3;
+        }
+        CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
+    } else {
+        CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
+        if (pr->block_mode) CUDA_TRY(launch_scan_blocks(pr->sp, db->d_ctrl, db->d_status, pr->grid, pr->dyn_smem, db->stream));
+        else CUDA_TRY(launch_scan_dense(pr->sp, db->d_ctrl, db->d_status, pr->grid, pr->dyn_smem, db->stream));
+        CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
+        *launches = 1;
+    }
     CUDA_TRY(cudaMemcpyAsync(db->h_ctrl, db->d_ctrl, sizeof(ScanCtrl), cudaMemcpyDeviceToHost, db->stream));
     CUDA_TRY(cudaStreamSynchronize(db->stream));
     if (db->h_ctrl->error) return fail(IMM3_ERR_CUDA, "kernel watchdog fired (code %u)", db->h_ctrl->error);
@@ -622,8 +696,7 @@ int imm3_query_begin(imm3_db* db, const char* table, const imm3_pred* preds, int
         if ((rc = fill_scan_plan(db, &pr))) { give_back(); return rc; }
         for (int i = 0; i < r->ncols; i++) pr.sp.proj[i].out = (uint8_t*)r->d_cols[(size_t)i].p;
         pr.sp.bitmap = nullptr;
-        if ((rc = run_scan(db, &pr, &r->device_ms, &r->local_count))) { give_back(); return rc; }
-        r->launches = 1;
+        if ((rc = run_scan(db, &pr, &r->device_ms, &r->local_count, &r->launches))) { give_back(); return rc; }
     }
     // Algorithmic bytes: filter columns' encoded bytes once + per surviving row the
     // project-only widths read and every projected width written (+ 4 B/block for PFOR offsets).
@@ -745,13 +818,10 @@ int imm3_filter_bitmap(imm3_db* db, const char* table, const imm3_pred* preds, i
     if ((rc = use_device(db))) return rc;
     TableStore& t = *pr.table;
     const size_t need_words = (size_t)((t.nrows + kDenseMaxTileRows - 1) / kDenseMaxTileRows) * (kDenseMaxTileRows / 32) + 2;
-    if (db->d_bitmap.cap < need_words * 4) {
-        if (db->d_bitmap.p) cudaFree(db->d_bitmap.p);
+    if ((rc = ensure_buf(&db->d_bitmap, need_words * 4))) return rc;
+    if (db->h_bitmap.cap < need_words * 4) {
         if (db->h_bitmap.p) cudaFreeHost(db->h_bitmap.p);
-        db->d_bitmap = Buf();
         db->h_bitmap = Buf();
-        CUDA_TRY(cudaMalloc(&db->d_bitmap.p, need_words * 4));
-        db->d_bitmap.cap = need_words * 4;
         CUDA_TRY(cudaMallocHost(&db->h_bitmap.p, need_words * 4));
         db->h_bitmap.cap = need_words * 4;
     }
@@ -762,7 +832,8 @@ int imm3_filter_bitmap(imm3_db* db, const char* table, const imm3_pred* preds, i
         pr.sp.bitmap = (uint32_t*)db->d_bitmap.p;
         pr.sp.limit = INT64_MAX;
         double ms;
-        if ((rc = run_scan(db, &pr, &ms, &total))) return rc;
+        int launches;
+        if ((rc = run_scan(db, &pr, &ms, &total, &launches))) return rc;
     }
     const size_t out_words = (size_t)((t.nrows + 31) / 32);
     if (out_words) CUDA_TRY(cudaMemcpyAsync(db->h_bitmap.p, db->d_bitmap.p, out_words * 4, cudaMemcpyDeviceToHost, db->stream));

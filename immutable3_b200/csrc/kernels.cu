@@ -92,7 +92,7 @@ __device__ __forceinline__ uint4 ldg128(const uint8_t* p) { return __ldg(reinter
 constexpr unsigned long long kWatchdogNs = 4000000000ull;  // 4 s: far beyond any legitimate wait
 
 __device__ __noinline__ void watchdog_trap(ScanCtrl* ctrl, unsigned code) {
-    atomicExch(&ctrl->error, code);
+    if (ctrl) atomicExch(&ctrl->error, code);
     __threadfence_system();
     __trap();
 }
@@ -177,7 +177,7 @@ __device__ long long resolve_tile(const ScanPlan& P, ScanCtrl* ctrl, unsigned lo
         if (lane == 0) st_relaxed_u64(status + tile, pack_status(P.epoch, kStatePrefix, tile_count));
     } else {
         if (lane == 0) st_relaxed_u64(status + tile, pack_status(P.epoch, kStateAggregate, tile_count));
-        excl = lookback_exclusive(status, tile, P.epoch, ctrl, lane);
+        excl = (P.debug & 1u) ? (long long)tile * 1800 : lookback_exclusive(status, tile, P.epoch, ctrl, lane);
         if (excl < 0) return -1;
         if (lane == 0) st_relaxed_u64(status + tile, pack_status(P.epoch, kStatePrefix, (unsigned long long)excl + tile_count));
     }
@@ -232,6 +232,9 @@ __device__ __forceinline__ void cta_exit(ScanCtrl* ctrl) {
 // a CTA busy emitting would otherwise sit on an un-counted earlier tile that every later tile in the
 // grid has to wait for.  Hand-offs are two-entry rings guarded by mbarriers (count_full, excl_full).
 // =============================================================================================
+#ifndef IMM3_DENSE_MIN_BLOCKS
+#define IMM3_DENSE_MIN_BLOCKS 3  // register budget: 3 CTAs (27 warps) per SM
+#endif
 constexpr int kComputeThreads = 256;
 constexpr int kComputeWarps = kComputeThreads / 32;
 constexpr unsigned kNoMoreTiles = 0xFFFFFFFFu;
@@ -347,43 +350,102 @@ __device__ __noinline__ uint32_t dense_eval_filter(const ScanPlan& P, const Filt
     return mask;
 }
 
-// One projected cell of width <= 8 as a 64-bit value, from the staged tile or from global memory.
-__device__ __forceinline__ unsigned long long load_cell(bool from_smem, uint32_t sbase, const uint8_t* gbase, uint32_t r, int w) {
-    if (w == 4) {
-        uint32_t v;
-        if (from_smem) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sbase + r * 4u));
-        else v = __ldg(reinterpret_cast<const uint32_t*>(gbase) + r);
-        return v;
-    }
-    if (w == 1) return from_smem ? lds_u8(sbase + r) : (uint32_t)__ldg(gbase + r);
-    if (w == 2) {
-        uint32_t v;
-        if (from_smem) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(sbase + r * 2u));
-        else v = __ldg(reinterpret_cast<const uint16_t*>(gbase) + r);
-        return v;
-    }
-    unsigned long long v = 0;  // 3,5,6,7,8: byte-wise, little-endian packing
-    for (int b = 0; b < w; b++)
-        v |= (unsigned long long)(from_smem ? lds_u8(sbase + r * (uint32_t)w + b) : (uint32_t)__ldg(gbase + (long long)r * w + b)) << (8 * b);
+// Typed shared-memory loads for the projected cells of staged columns.
+template <typename T> __device__ __forceinline__ T lds_cell(uint32_t addr);
+template <> __device__ __forceinline__ uint8_t lds_cell<uint8_t>(uint32_t addr) { return (uint8_t)lds_u8(addr); }
+template <> __device__ __forceinline__ uint16_t lds_cell<uint16_t>(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void store_cell(uint8_t* out, long long idx, int w, unsigned long long v) {
-    if (w == 4) reinterpret_cast<uint32_t*>(out)[idx] = (uint32_t)v;
-    else if (w == 1) out[idx] = (uint8_t)v;
-    else if (w == 2) reinterpret_cast<uint16_t*>(out)[idx] = (uint16_t)v;
-    else
-        for (int b = 0; b < w; b++) out[idx * w + b] = (uint8_t)(v >> (8 * b));
+template <> __device__ __forceinline__ uint32_t lds_cell<uint32_t>(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+template <> __device__ __forceinline__ unsigned long long lds_cell<unsigned long long>(uint32_t addr) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+
+// Cooperative emission of one 1024-row word-span by one warp: entry i of the warp-private selection
+// list (row index inside the span) goes to out[g0 + i].  Lanes take consecutive entries, so stores are
+// coalesced and every lane carries four independent gathers.
+template <typename T, bool FROM_SMEM>
+__device__ __forceinline__ void emit_span(const unsigned short* sel_w, int n, int lane, uint32_t sbase, const T* __restrict__ gbase,
+                                          T* __restrict__ out, long long g0, long long limit) {
+    const long long room = limit - g0;
+    if (room <= 0) return;
+    if (room < (long long)n) n = (int)room;
+    for (int i0 = 0; i0 < n; i0 += 128) {
+        T v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = i0 + k * 32 + lane;
+            if (i < n) {
+                const uint32_t r = sel_w[i];
+                v[k] = FROM_SMEM ? lds_cell<T>(sbase + r * (uint32_t)sizeof(T)) : __ldg(gbase + r);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = i0 + k * 32 + lane;
+            if (i < n) out[g0 + i] = v[k];
+        }
+    }
+}
+// Any other cell width: byte-wise.
+__device__ __forceinline__ void emit_span_bytes(const unsigned short* sel_w, int n, int lane, bool from_smem, uint32_t sbase,
+                                                const uint8_t* __restrict__ gbase, uint8_t* __restrict__ out, int w, long long g0,
+                                                long long limit) {
+    const long long room = limit - g0;
+    if (room <= 0) return;
+    if (room < (long long)n) n = (int)room;
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t r = sel_w[i];
+        for (int b = 0; b < w; b++)
+            out[(g0 + i) * w + b] = (uint8_t)(from_smem ? lds_u8(sbase + r * (uint32_t)w + b) : (uint32_t)__ldg(gbase + (long long)r * w + b));
+    }
+}
+
+// All projected columns of one span (kept out of line: the kernel body stays small and lean on registers).
+__device__ __noinline__ void emit_span_all(const ScanPlan& P, const unsigned short* sel_w, int n, int lane, bool staged,
+                                           uint32_t stage_addr, int span_row, long long tile_row0, long long g0) {
+    for (int pc = 0; pc < P.nproj; pc++) {
+        const ProjCol& pj = P.proj[pc];
+        const int w = pj.width;
+        const bool from_smem = staged && pj.filter_idx >= 0;
+        const uint32_t sbase = stage_addr + (from_smem ? (uint32_t)P.filter[pj.filter_idx].smem_off : 0u) + (uint32_t)(span_row * w);
+        const uint8_t* gbase = pj.base + (tile_row0 + span_row) * w;
+        if (w == 4) {
+            if (from_smem) emit_span<uint32_t, true>(sel_w, n, lane, sbase, nullptr, (uint32_t*)pj.out, g0, P.limit);
+            else emit_span<uint32_t, false>(sel_w, n, lane, 0u, (const uint32_t*)gbase, (uint32_t*)pj.out, g0, P.limit);
+        } else if (w == 1) {
+            if (from_smem) emit_span<uint8_t, true>(sel_w, n, lane, sbase, nullptr, pj.out, g0, P.limit);
+            else emit_span<uint8_t, false>(sel_w, n, lane, 0u, gbase, pj.out, g0, P.limit);
+        } else if (w == 2) {
+            if (from_smem) emit_span<uint16_t, true>(sel_w, n, lane, sbase, nullptr, (uint16_t*)pj.out, g0, P.limit);
+            else emit_span<uint16_t, false>(sel_w, n, lane, 0u, (const uint16_t*)gbase, (uint16_t*)pj.out, g0, P.limit);
+        } else if (w == 8) {
+            if (from_smem) emit_span<unsigned long long, true>(sel_w, n, lane, sbase, nullptr, (unsigned long long*)pj.out, g0, P.limit);
+            else emit_span<unsigned long long, false>(sel_w, n, lane, 0u, (const unsigned long long*)gbase, (unsigned long long*)pj.out, g0, P.limit);
+        } else {
+            emit_span_bytes(sel_w, n, lane, from_smem, sbase, gbase, pj.out, w, g0, P.limit);
+        }
+    }
 }
 
 extern __shared__ __align__(128) uint8_t dyn_smem[];
 
 template <int W>
-__global__ void __launch_bounds__(kDenseThreads, 3) scan_dense_kernel(const __grid_constant__ ScanPlan P, ScanCtrl* ctrl,
+__global__ void __launch_bounds__(kDenseThreads, IMM3_DENSE_MIN_BLOCKS) scan_dense_kernel(const __grid_constant__ ScanPlan P, ScanCtrl* ctrl,
                                                                      unsigned long long* status) {
     constexpr int kTile = kDenseTileRowsPerWord * W;  // rows per tile
     constexpr int kWarpSpan = 1024 * W;               // rows per compute warp
     __shared__ DenseShared S;
-    const uint32_t ring_addr = smem_u32(dyn_smem);
+    // dynamic shared memory: [8 warp-private selection lists of 1024 uint16][TMA ring]
+    const uint32_t ring_addr = smem_u32(dyn_smem) + kComputeWarps * 1024 * 2;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool is_ctrl = warp == kComputeWarps;
@@ -439,13 +501,16 @@ __global__ void __launch_bounds__(kDenseThreads, 3) scan_dense_kernel(const __gr
             for (int s = 0; s < ring; s++) refill(s);
         bar_sync(1, kComputeThreads);
 
-        // Per-lane state of the tile being filtered (cur) and of the tile waiting to be emitted (prev).
+        // Per-lane state of the tile being filtered (cur) and of the tile waiting to be emitted (prev): the
+        // bitmap words and the tile-local rank of the warp's first selected row.  The in-warp ranks are
+        // recomputed at emit time (a 5-step shuffle scan) rather than carried in registers.
         uint32_t m_cur[W], m_prev[W];
-        unsigned rank_cur[W], rank_prev[W];
+        unsigned wbase_cur = 0, wbase_prev = 0;  // tile-local rank of the warp's first selected row
         long long row0_cur = 0, row0_prev = 0;
         int slot_cur = 0, slot_prev = 0;
         int slotF = 0;
         uint32_t parF = 0;
+        unsigned short* sel_w = reinterpret_cast<unsigned short*>(dyn_smem) + warp * 1024;
 
         // F(j): returns false when the CTA has run out of tiles.
         auto filter_tile = [&](unsigned j) -> bool {
@@ -465,8 +530,7 @@ __global__ void __launch_bounds__(kDenseThreads, 3) scan_dense_kernel(const __gr
             if (++slotF == ring) { slotF = 0; parF ^= 1u; }
 
             // decode + conjunctive filter: W bitmap words per lane, then ranks
-            unsigned incl[W], sub_tot[W];
-            unsigned warp_total = 0;
+            unsigned lane_total = 0;
 #pragma unroll
             for (int s = 0; s < W; s++) {
                 const int span_row = warp * kWarpSpan + s * 1024;
@@ -476,16 +540,9 @@ __global__ void __launch_bounds__(kDenseThreads, 3) scan_dense_kernel(const __gr
                     mask &= dense_eval_filter(P, P.filter[i], staged, stage_addr, tile_row0, span_row, lane);
                 m_cur[s] = mask;
                 if (P.bitmap) P.bitmap[((tile_row0 + span_row) >> 5) + lane] = mask;
-                unsigned x = __popc(mask);
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned n = __shfl_up_sync(0xFFFFFFFFu, x, o);
-                    if (lane >= o) x += n;
-                }
-                incl[s] = x;
-                sub_tot[s] = __shfl_sync(0xFFFFFFFFu, x, 31);
-                warp_total += sub_tot[s];
+                lane_total += __popc(mask);
             }
+            const unsigned warp_total = __reduce_add_sync(0xFFFFFFFFu, lane_total);
             if (lane == 0) S.warp_cnt[e][warp] = warp_total;
             bar_sync(1, kComputeThreads);
             unsigned warp_base = 0, tile_count = 0;
@@ -500,11 +557,7 @@ __global__ void __launch_bounds__(kDenseThreads, 3) scan_dense_kernel(const __gr
                 S.tile_id[e] = tile;
                 mbar_arrive(smem_u32(&S.mbar_count[e]));
             }
-#pragma unroll
-            for (int s = 0; s < W; s++) {  // tile-local rank of the lane's first selected row of word s
-                rank_cur[s] = warp_base + incl[s] - __popc(m_cur[s]);
-                warp_base += sub_tot[s];
-            }
+            wbase_cur = warp_base;
             row0_cur = tile_row0;
             slot_cur = slot;
             return true;
@@ -517,45 +570,36 @@ __global__ void __launch_bounds__(kDenseThreads, 3) scan_dense_kernel(const __gr
             const long long excl = S.tile_excl[e];
             const uint32_t stage_addr = ring_addr + (uint32_t)slot_prev * (uint32_t)P.stage_bytes;
             if (!P.bitmap && excl >= 0 && excl < P.limit) {
+                unsigned wrank = wbase_prev;
 #pragma unroll
                 for (int s = 0; s < W; s++) {
                     uint32_t mm = m_prev[s];
-                    const unsigned iters = (__reduce_max_sync(0xFFFFFFFFu, (unsigned)__popc(mm)) + 3u) >> 2;
-                    long long g = excl + rank_prev[s];  // global ordinal of the lane's next selected row
-                    const uint32_t row_base = (uint32_t)(warp * kWarpSpan + s * 1024 + lane * 32);
-                    for (unsigned it = 0; it < iters; it++) {
-                        uint32_t r[4];
-                        bool ok[4];
+                    const unsigned cnt = (unsigned)__popc(mm);
+                    unsigned incl = cnt;
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            ok[k] = mm != 0u;
-                            r[k] = row_base + (uint32_t)(ok[k] ? (__ffs(mm) - 1) : 0);
-                            mm &= mm - 1u;
-                        }
-                        for (int pc = 0; pc < P.nproj; pc++) {
-                            const ProjCol& pj = P.proj[pc];
-                            const int w = pj.width;
-                            const bool from_smem = staged && pj.filter_idx >= 0;
-                            const uint32_t sbase = stage_addr + (from_smem ? (uint32_t)P.filter[pj.filter_idx].smem_off : 0u);
-                            const uint8_t* gbase = pj.base + row0_prev * w;
-                            if (w <= 8) {
-                                unsigned long long v[4];
-#pragma unroll
-                                for (int k = 0; k < 4; k++) v[k] = ok[k] ? load_cell(from_smem, sbase, gbase, r[k], w) : 0ull;  // 4 gathers in flight
-#pragma unroll
-                                for (int k = 0; k < 4; k++)
-                                    if (ok[k] && g + k < P.limit) store_cell(pj.out, g + k, w, v[k]);
-                            } else {
-#pragma unroll
-                                for (int k = 0; k < 4; k++)
-                                    if (ok[k] && g + k < P.limit)
-                                        for (int b = 0; b < w; b++)
-                                            pj.out[(g + k) * w + b] = (uint8_t)(from_smem ? lds_u8(sbase + r[k] * (uint32_t)w + b)
-                                                                                          : (uint32_t)__ldg(gbase + (long long)r[k] * w + b));
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                        if (lane >= o) incl += nb;
+                    }
+                    const int n = (int)__shfl_sync(0xFFFFFFFFu, incl, 31);
+                    const long long g0 = excl + wrank;
+                    wrank += (unsigned)n;
+                    if (n == 0) continue;  // warp-uniform
+                    // warp-private selection list of this 1024-row span, from the register bitmap words
+                    {
+                        unsigned o = incl - cnt;
+                        const unsigned iters = __reduce_max_sync(0xFFFFFFFFu, cnt);
+                        for (unsigned it = 0; it < iters; it++) {
+                            if (mm) {
+                                sel_w[o++] = (unsigned short)(lane * 32 + __ffs(mm) - 1);
+                                mm &= mm - 1u;
                             }
                         }
-                        g += 4;
                     }
+                    __syncwarp();
+                    const int span_row = warp * kWarpSpan + s * 1024;
+                    emit_span_all(P, sel_w, n, lane, staged, stage_addr, span_row, row0_prev, g0);
+                    __syncwarp();  // the list is rebuilt for the next span
                 }
             }
             bar_sync(1, kComputeThreads);  // every warp is done with the slot's bytes
@@ -566,10 +610,8 @@ __global__ void __launch_bounds__(kDenseThreads, 3) scan_dense_kernel(const __gr
         bool more = filter_tile(0);
         while (more) {
 #pragma unroll
-            for (int s = 0; s < W; s++) {
-                m_prev[s] = m_cur[s];
-                rank_prev[s] = rank_cur[s];
-            }
+            for (int s = 0; s < W; s++) m_prev[s] = m_cur[s];
+            wbase_prev = wbase_cur;
             row0_prev = row0_cur;
             slot_prev = slot_cur;
             const bool next = filter_tile(j + 1);
@@ -819,6 +861,182 @@ __global__ void __launch_bounds__(kBlockThreads) scan_blocks_kernel(const __grid
 }
 
 // =============================================================================================
+// Multi-pass pipeline for unlimited (or large-LIMIT) queries on dense tables
+//
+//   K1 filter_kernel : persistent CTAs stream the filter columns through a deep TMA ring (tiles are
+//                      statically strided over the CTAs: no ordering, no tickets), evaluate the
+//                      conjunction and write the selection BITMAP (one word per lane, coalesced) plus
+//                      the match count of every 1024-row span and of every tile.
+//   K2 scan_kernel   : exclusive prefix sum of the tile counts (device-wide offsets, LIMIT clamp, total).
+//   K3 emit_kernel   : one warp per 1024-row span, no inter-warp dependency at all: span offset =
+//                      tile offset + the counts of the earlier spans of the tile; ballot/popc compaction
+//                      of the bitmap word into a warp-private selection vector; cooperative, coalesced
+//                      Project gather of the select-list columns.
+// Every stage is embarrassingly parallel, so none of them can be held up by a slow CTA the way a
+// chained single-pass scan is; the price is the bitmap round trip (1 bit/row written + read).
+// =============================================================================================
+struct FilterShared {
+    unsigned long long mbar_full[kMaxFilterStages];
+    unsigned int warp_cnt[2][kComputeWarps];
+};
+
+template <int W>
+__global__ void __launch_bounds__(kComputeThreads) filter_kernel(const __grid_constant__ ScanPlan P, uint32_t* __restrict__ bitmap,
+                                                                   uint32_t* __restrict__ span_cnt, uint32_t* __restrict__ tile_cnt) {
+    constexpr int kTile = kDenseTileRowsPerWord * W;
+    constexpr int kWarpSpan = 1024 * W;
+    __shared__ FilterShared S;
+    const uint32_t ring_addr = smem_u32(dyn_smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool staged = P.stages > 0;
+    const int ring = staged ? P.stages : 1;
+    const long long ntiles = P.ntiles;
+
+    auto issue = [&](long long tile, int slot) {  // thread 0
+        const uint32_t bar = smem_u32(&S.mbar_full[slot]);
+        mbar_arrive_expect_tx(bar, (uint32_t)P.stage_bytes);
+        for (int i = 0; i < P.nfilter; i++) {
+            const FilterCol& f = P.filter[i];
+            const uint32_t bytes = (uint32_t)(kTile * f.width);
+            tma_load_1d(ring_addr + (uint32_t)slot * (uint32_t)P.stage_bytes + (uint32_t)f.smem_off, f.base + tile * bytes, bytes, bar);
+        }
+    };
+    if (tid == 0) {
+        for (int s = 0; s < kMaxFilterStages; s++) mbar_init(smem_u32(&S.mbar_full[s]), 1);
+        fence_mbar_init();
+        if (staged)
+            for (int s = 0; s < ring; s++) {
+                const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+                if (t < ntiles) issue(t, s);
+            }
+    }
+    __syncthreads();
+
+    int slot = 0;
+    uint32_t parity = 0;
+    unsigned it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        const long long tile_row0 = tile * kTile;
+        const uint32_t stage_addr = ring_addr + (uint32_t)slot * (uint32_t)P.stage_bytes;
+        if (staged) mbar_wait(smem_u32(&S.mbar_full[slot]), parity, nullptr);
+        unsigned warp_total = 0;
+#pragma unroll
+        for (int s = 0; s < W; s++) {
+            const int span_row = warp * kWarpSpan + s * 1024;
+            const long long left = P.nrows - (tile_row0 + span_row + lane * 32);
+            uint32_t mask = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
+            for (int i = 0; i < P.nfilter; i++)
+                mask &= dense_eval_filter(P, P.filter[i], staged, stage_addr, tile_row0, span_row, lane);
+            bitmap[((tile_row0 + span_row) >> 5) + lane] = mask;
+            const unsigned c = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(mask));
+            if (lane == 0) span_cnt[(tile_row0 + span_row) >> 10] = c;
+            warp_total += c;
+        }
+        const int e = (int)(it & 1u);
+        if (lane == 0) S.warp_cnt[e][warp] = warp_total;
+        __syncthreads();  // every warp has consumed the slot's bytes
+        if (tid == 0) {
+            unsigned c = 0;
+#pragma unroll
+            for (int w = 0; w < kComputeWarps; w++) c += S.warp_cnt[e][w];
+            tile_cnt[tile] = c;
+            const long long next = tile + (long long)ring * gridDim.x;
+            if (staged && next < ntiles) issue(next, slot);
+        }
+        if (++slot == ring) { slot = 0; parity ^= 1u; }
+    }
+}
+
+// Exclusive scan of the tile counts by one CTA (<= a few hundred thousand values), LIMIT clamp of the total.
+__global__ void __launch_bounds__(1024) scan_kernel(const uint32_t* __restrict__ tile_cnt, unsigned long long* __restrict__ tile_off,
+                                                      long long ntiles, long long limit, ScanCtrl* ctrl) {
+    __shared__ unsigned long long warp_sums[32];
+    __shared__ unsigned long long carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (long long base = 0; base < ntiles; base += 4096) {
+        unsigned long long v[4], run = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const long long i = base + (long long)tid * 4 + k;
+            v[k] = i < ntiles ? tile_cnt[i] : 0u;
+            run += v[k];
+        }
+        unsigned long long incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = warp_sums[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long nb = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+                if (lane >= o) wi += nb;
+            }
+            warp_sums[lane] = wi - w;  // exclusive
+        }
+        __syncthreads();
+        unsigned long long excl = carry_s + warp_sums[warp] + incl - run;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const long long i = base + (long long)tid * 4 + k;
+            if (i < ntiles) tile_off[i] = excl;
+            excl += v[k];
+        }
+        __syncthreads();
+        if (tid == 1023) carry_s = excl;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        tile_off[ntiles] = carry_s;
+        ctrl->total = carry_s < (unsigned long long)limit ? carry_s : (unsigned long long)limit;
+    }
+}
+
+__global__ void __launch_bounds__(kComputeThreads) emit_kernel(const __grid_constant__ ScanPlan P, const uint32_t* __restrict__ bitmap,
+                                                                 const uint32_t* __restrict__ span_cnt,
+                                                                 const unsigned long long* __restrict__ tile_off, int spans_per_tile,
+                                                                 long long nspans) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned short* sel_w = reinterpret_cast<unsigned short*>(dyn_smem) + warp * 1024;
+    for (long long p = (long long)blockIdx.x * kComputeWarps + warp; p < nspans; p += (long long)gridDim.x * kComputeWarps) {
+        const long long t = p / spans_per_tile;
+        const int k = (int)(p - t * spans_per_tile);
+        // counts of the spans of this tile: lane i holds span i (spans_per_tile <= 32)
+        const unsigned c = lane < spans_per_tile && t * spans_per_tile + lane < nspans ? __ldg(span_cnt + t * spans_per_tile + lane) : 0u;
+        const int n = (int)__shfl_sync(0xFFFFFFFFu, c, k);
+        if (n == 0) continue;
+        const unsigned before = __reduce_add_sync(0xFFFFFFFFu, lane < k ? c : 0u);
+        const long long g0 = (long long)__ldg(tile_off + t) + before;
+        if (g0 >= P.limit) continue;
+        uint32_t mm = __ldg(bitmap + p * 32 + lane);
+        const unsigned cnt = (unsigned)__popc(mm);
+        unsigned incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        unsigned o = incl - cnt;
+        const unsigned iters = __reduce_max_sync(0xFFFFFFFFu, cnt);
+        for (unsigned it = 0; it < iters; it++) {
+            if (mm) {
+                sel_w[o++] = (unsigned short)(lane * 32 + __ffs(mm) - 1);
+                mm &= mm - 1u;
+            }
+        }
+        __syncwarp();
+        emit_span_all(P, sel_w, n, lane, false, 0u, 0, p * 1024, g0);
+        __syncwarp();
+    }
+}
+
+// =============================================================================================
 // Launchers
 // =============================================================================================
 size_t blocks_kernel_smem_bytes(int npfor, int max_block_rows) {
@@ -834,6 +1052,12 @@ static cudaError_t configure_once() {
         e = cudaFuncSetAttribute(scan_dense_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(scan_dense_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(filter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(scan_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     }();
@@ -862,6 +1086,40 @@ cudaError_t launch_scan_dense(const ScanPlan& plan, ScanCtrl* ctrl, unsigned lon
     else scan_dense_kernel<1><<<grid, kDenseThreads, dyn_smem, stream>>>(plan, ctrl, status);
     return cudaGetLastError();
 }
+cudaError_t filter_kernel_occupancy(int words_per_lane, size_t dyn_smem, int* blocks_per_sm) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    if (words_per_lane == 4) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, filter_kernel<4>, kComputeThreads, dyn_smem);
+    if (words_per_lane == 2) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, filter_kernel<2>, kComputeThreads, dyn_smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, filter_kernel<1>, kComputeThreads, dyn_smem);
+}
+cudaError_t emit_kernel_occupancy(int* blocks_per_sm) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, emit_kernel, kComputeThreads, kComputeWarps * 1024 * 2);
+}
+cudaError_t launch_filter(const ScanPlan& plan, uint32_t* bitmap, uint32_t* span_cnt, uint32_t* tile_cnt, int grid, size_t dyn_smem,
+                          cudaStream_t stream) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    if (plan.words_per_lane == 4) filter_kernel<4><<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt);
+    else if (plan.words_per_lane == 2) filter_kernel<2><<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt);
+    else filter_kernel<1><<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt);
+    return cudaGetLastError();
+}
+cudaError_t launch_tile_scan(const uint32_t* tile_cnt, unsigned long long* tile_off, long long ntiles, long long limit, ScanCtrl* ctrl,
+                             cudaStream_t stream) {
+    scan_kernel<<<1, 1024, 0, stream>>>(tile_cnt, tile_off, ntiles, limit, ctrl);
+    return cudaGetLastError();
+}
+cudaError_t launch_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* span_cnt, const unsigned long long* tile_off,
+                        int spans_per_tile, long long nspans, int grid, cudaStream_t stream) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    emit_kernel<<<grid, kComputeThreads, kComputeWarps * 1024 * 2, stream>>>(plan, bitmap, span_cnt, tile_off, spans_per_tile, nspans);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_scan_blocks(const ScanPlan& plan, ScanCtrl* ctrl, unsigned long long* status, int grid, size_t dyn_smem,
                                cudaStream_t stream) {
     cudaError_t e = configure_once();

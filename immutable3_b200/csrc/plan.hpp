@@ -21,6 +21,7 @@ constexpr int kDenseThreads = 288;  // 8 compute warps + 1 control warp (tickets
 constexpr int kBlockThreads = 256;  // block-mode kernel: threads per CTA
 constexpr int kMaxBlockRows = 8192; // block-mode kernel: largest reference block it stages
 constexpr int kMaxStages = 4;
+constexpr int kMaxFilterStages = 8;  // TMA ring depth of the multi-pass filter kernel
 
 enum FilterKind : int32_t {
     kFilterI8Range = 0,   // TINYINT: lo <= v <= hi   (merged GT/LT/EQ, Select.scala:53-165)
@@ -68,6 +69,8 @@ struct ScanPlan {
     int32_t stage_bytes;  // dense: bytes of one stage
     int32_t max_block_rows;  // block mode: rows of the largest block (shared-memory sizing)
     int32_t words_per_lane;  // dense: W (tile = 8192 * W rows)
+    uint32_t debug;          // IMM3_DEBUG env bits (timing experiments only; bit 0: skip the look-back -> WRONG offsets)
+    uint32_t pad2;
     FilterCol filter[kMaxFilterCols];
     ProjCol proj[kMaxProjCols];
     PforCol pfor[kMaxPforCols];

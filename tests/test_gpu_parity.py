@@ -15,7 +15,11 @@ from immutable3_b200.loader import synth_write
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = {"tma": 0, "direct": OPEN_NO_TMA, "blocks": OPEN_FORCE_BLOCKS}
+# variant -> (imm3_open flags, IMM3_PATH): the fused single-pass kernel with TMA staging / direct loads, the
+# block-mode kernel forced onto dense tables, and the three-kernel filter->scan->emit pipeline.
+VARIANT_DEFS = {"tma": (0, "fused"), "direct": (OPEN_NO_TMA, "fused"), "blocks": (OPEN_FORCE_BLOCKS, "fused"),
+                "multi": (0, "multi"), "multi_direct": (OPEN_NO_TMA, "multi"), "auto": (0, "")}
+VARIANTS = {k: v[0] for k, v in VARIANT_DEFS.items()}
 
 
 @pytest.fixture(scope="module")
@@ -41,12 +45,22 @@ def world(tmp_path_factory):
     orc = O.Oracle(d)
     sms = {k: SegmentManager(d, flags=f) for k, f in VARIANTS.items()}
     yield d, tables, orc, sms
+    os.environ.pop("IMM3_PATH", None)
     for s in sms.values():
         s.close()
     orc.close()
 
 
+def set_path(variant):
+    path = VARIANT_DEFS.get(variant.split("/")[0], (0, ""))[1]
+    if path:
+        os.environ["IMM3_PATH"] = path
+    else:
+        os.environ.pop("IMM3_PATH", None)
+
+
 def check(orc, sm, table, select, proj, limit=0, variant=""):
+    set_path(variant)
     exp = orc.query(table, oracle_preds(select), proj, limit=limit)
     with Engine(sm).execute(Query(table, select, Project(proj, limit))) as got:
         assert got.nrows == exp.nrows, (variant, table, select, proj, limit, got.nrows, exp.nrows)
@@ -143,11 +157,12 @@ def test_dense_tile_shapes(world, w, stages, monkeypatch):
     d, tables, orc, sms = world
     monkeypatch.setenv("IMM3_DENSE_W", str(w))
     monkeypatch.setenv("IMM3_DENSE_STAGES", str(stages))
-    for variant in ("tma", "direct"):
+    for variant in ("tma", "direct", "multi", "multi_direct"):
         for sel, proj in QUERIES_T[:5] + [(NoSelect, ["id", "state", "age"])]:
             for limit in (0, 10, 8191, 8193, 20_000):
                 check(orc, sms[variant], "t", sel, proj, limit, f"{variant}/W{w}/S{stages}")
         check(orc, sms[variant], "wide", Select("name", Match(["carol"])), ["id", "name", "zip"], 0, f"{variant}/W{w}")
+        set_path(variant)
         got, nsel = Engine(sms[variant]).filter_bitmap("t", Select("age", LT(50)))
         want, wsel = orc.filter_bitmap("t", oracle_preds(Select("age", LT(50))))
         assert nsel == wsel and np.array_equal(got, want)
@@ -193,6 +208,7 @@ def test_selection_bitmap(world, variant):
     for table, sel in [("t", conj(Select("age", GT(18)), Select("age", LT(30)))), ("t", NoSelect), ("t", Select("state", Match(["CA"]))),
                        ("neg", Select("id", GT(0))), ("wide", Select("name", Match(["dave_"]))), ("tile1", Select("age", LT(50))),
                        ("p", Select("id", GT(1000))), ("ps", Select("age", GT(50)))]:
+        set_path(variant)
         got, nsel = Engine(sms[variant]).filter_bitmap(table, sel)
         want, wsel = orc.filter_bitmap(table, oracle_preds(sel))
         assert nsel == wsel and np.array_equal(got, want), (variant, table, sel)
@@ -268,13 +284,14 @@ def test_full_size_synthetic_properties(tmp_path_factory):
     age = np.concatenate([np.fromfile(d / "syn" / f"age_{i}.dat", np.int8) for i in order])
     ids = np.concatenate([np.fromfile(d / "syn" / f"id_{i}.dat", "<i4") for i in order])
     st = np.concatenate([np.fromfile(d / "syn" / f"state_{i}.dat", "S2") for i in order])
-    for flags in (0, OPEN_NO_TMA):
+    for flags, path in ((0, "fused"), (OPEN_NO_TMA, "fused"), (0, "multi"), (0, "")):
+        set_path({"fused": "tma", "multi": "multi", "": "auto"}[path])
         with SegmentManager(d, flags=flags) as sm:
             eng = Engine(sm)
             m = (age > 18) & (age < 30)
             with eng.execute(Query("syn", conj(Select("age", GT(18)), Select("age", LT(30))), Project(["id", "age"]))) as r:     # C2
                 assert r.nrows == int(m.sum()) and np.array_equal(r.column(0), ids[m]) and np.array_equal(r.column(1), age[m])
-                assert r.algorithmic_bytes == n + r.nrows * 9 and r.kernel_launches == 1
+                assert r.algorithmic_bytes == n + r.nrows * 9 and r.kernel_launches == (1 if path == "fused" else 3)
             m3 = m & (st == b"CA")
             with eng.execute(Query("syn", conj(Select("state", Match(["CA"])), Select("age", GT(18)), Select("age", LT(30))), Project(["id", "state", "age"]))) as r:  # C3
                 assert r.nrows == int(m3.sum()) and np.array_equal(r.column(0), ids[m3]) and np.all(r.column(1) == b"CA")
