@@ -317,6 +317,7 @@ def main():
     # ---- value: table resident, CUDA-event time of the fused kernel ----
     sampler = ClockSampler(local_rank)
     kernel_ms, alg_bytes, launches, local_rows = [], 0, 0, 0
+    stage_ms = [[], []]
     for i in range(args.warmup):
         flush_l2(i)
         with eng.begin(query) as r:
@@ -328,6 +329,8 @@ def main():
         flush_l2(i)
         with eng.begin(query) as r:
             kernel_ms.append(r.device_ms)
+            stage_ms[0].append(r.stage_ms(0))
+            stage_ms[1].append(r.stage_ms(1))
             alg_bytes = r.algorithmic_bytes
             launches += r.kernel_launches
             local_rows = r.local_count
@@ -392,7 +395,8 @@ def main():
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": recorded_traffic(args.workload), "peak_source": peak_src, "kernel": "scan_dense_kernel" if args.workload != "c4" else "scan_blocks_kernel",
-                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms_mean": launch_ms, "launch_ms_min": min(kernel_ms)}
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms_mean": launch_ms, "launch_ms_min": min(kernel_ms),
+                "stage_ms_mean": [statistics.mean(stage_ms[0]), statistics.mean(stage_ms[1])]}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     cpu = None

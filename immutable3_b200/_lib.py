@@ -68,6 +68,7 @@ SIGNATURES = {
     "imm3_result_format_row": (C.c_int, [_P, C.c_int64, C.c_char_p, C.c_size_t]),
     "imm3_result_device_ms": (C.c_double, [_P]),
     "imm3_result_kernel_launches": (C.c_int, [_P]),
+    "imm3_result_stage_ms": (C.c_double, [_P, C.c_int]),
     "imm3_result_algorithmic_bytes": (C.c_int64, [_P]),
     "imm3_result_free": (C.c_int, [_P]),
     "imm3_filter_bitmap": (C.c_int, [_P, C.c_char_p, C.POINTER(Pred), C.c_int, C.POINTER(C.POINTER(C.c_uint32)),

@@ -103,7 +103,7 @@ struct imm3_db {
     bool host_only = false;
     std::vector<TableStore> tables;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
     ScanCtrl* d_ctrl = nullptr;
     ScanCtrl* h_ctrl = nullptr;
     unsigned long long* d_status = nullptr;
@@ -125,6 +125,7 @@ struct imm3_result {
     int64_t local_count = 0;
     int64_t fetched = 0;
     double device_ms = 0;
+    double stage_ms[2] = {0, 0};
     int launches = 0;
     int64_t alg_bytes = 0;
 };
@@ -258,6 +259,7 @@ void free_device_side(imm3_db* db) {
     if (db->h_ctrl) cudaFreeHost(db->h_ctrl);
     if (db->ev0) cudaEventDestroy(db->ev0);
     if (db->ev1) cudaEventDestroy(db->ev1);
+    if (db->ev_mid) cudaEventDestroy(db->ev_mid);
     if (db->own_stream) cudaStreamDestroy(db->own_stream);
     cudaGetLastError();
 }
@@ -459,7 +461,8 @@ int ensure_buf(Buf* b, size_t bytes) {
 }
 
 // Launch the kernels of one query and wait for the match count.
-int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launches) {
+int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launches, double* stage_ms = nullptr) {
+    bool have_mid = false;
     if (pr->multipass) {
         const int64_t tile_rows = (int64_t)kDenseTileRowsPerWord * pr->sp.words_per_lane;
         const int64_t ntiles = pr->sp.ntiles, nspans = ntiles * (tile_rows / 1024);
@@ -472,13 +475,15 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
         if ((rc = ensure_buf(&db->d_tile_cnt, (size_t)ntiles * 4))) return rc;
         if ((rc = ensure_buf(&db->d_tile_off, (size_t)(ntiles + 1) * 8))) return rc;
         CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
-        CUDA_TRY(launch_filter(pr->sp, pr->sp.bitmap, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p, pr->grid, pr->dyn_smem, db->stream));
-        CUDA_TRY(launch_tile_scan((const uint32_t*)db->d_tile_cnt.p, (unsigned long long*)db->d_tile_off.p, ntiles, pr->sp.limit, db->d_ctrl, db->stream));
-        *launches = 2;
+        CUDA_TRY(launch_filter(pr->sp, pr->sp.bitmap, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
+                               (unsigned long long*)db->d_tile_off.p, db->d_ctrl, pr->grid, pr->dyn_smem, db->stream));
+        *launches = 1;
+        CUDA_TRY(cudaEventRecord(db->ev_mid, db->stream));
+        have_mid = true;
         if (pr->sp.nproj > 0) {
             CUDA_TRY(launch_emit(pr->sp, pr->sp.bitmap, (const uint32_t*)db->d_span_cnt.p, (const unsigned long long*)db->d_tile_off.p,
                                  (int)(tile_rows / 1024), nspans, pr->grid_emit, db->stream));
-            *launches = 3;
+            *launches = 2;
         }
         CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
     } else {
@@ -494,6 +499,17 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
     float f = 0;
     CUDA_TRY(cudaEventElapsedTime(&f, db->ev0, db->ev1));
     *ms = f;
+    if (stage_ms) {
+        stage_ms[0] = f;
+        stage_ms[1] = 0;
+        if (have_mid) {
+            float a = 0, b = 0;
+            CUDA_TRY(cudaEventElapsedTime(&a, db->ev0, db->ev_mid));
+            CUDA_TRY(cudaEventElapsedTime(&b, db->ev_mid, db->ev1));
+            stage_ms[0] = a;
+            stage_ms[1] = b;
+        }
+    }
     *total = (int64_t)db->h_ctrl->total;
     return 0;
 }
@@ -542,6 +558,7 @@ int imm3_open(const char* data_dir, const imm3_open_opts* opts, imm3_db** out) {
             db->stream = db->own_stream;
             CUDA_TRY(cudaEventCreate(&db->ev0));
             CUDA_TRY(cudaEventCreate(&db->ev1));
+            CUDA_TRY(cudaEventCreate(&db->ev_mid));
             CUDA_TRY(cudaMalloc(&db->d_ctrl, sizeof(ScanCtrl)));
             CUDA_TRY(cudaMemsetAsync(db->d_ctrl, 0, sizeof(ScanCtrl), db->stream));
             CUDA_TRY(cudaMallocHost(&db->h_ctrl, sizeof(ScanCtrl)));
@@ -696,7 +713,7 @@ int imm3_query_begin(imm3_db* db, const char* table, const imm3_pred* preds, int
         if ((rc = fill_scan_plan(db, &pr))) { give_back(); return rc; }
         for (int i = 0; i < r->ncols; i++) pr.sp.proj[i].out = (uint8_t*)r->d_cols[(size_t)i].p;
         pr.sp.bitmap = nullptr;
-        if ((rc = run_scan(db, &pr, &r->device_ms, &r->local_count, &r->launches))) { give_back(); return rc; }
+        if ((rc = run_scan(db, &pr, &r->device_ms, &r->local_count, &r->launches, r->stage_ms))) { give_back(); return rc; }
     }
     // Algorithmic bytes: filter columns' encoded bytes once + per surviving row the
     // project-only widths read and every projected width written (+ 4 B/block for PFOR offsets).
@@ -776,6 +793,7 @@ const void* imm3_result_col_data(const imm3_result* r, int c) { return (r && c >
 const void* imm3_result_col_device(const imm3_result* r, int c) { return (r && c >= 0 && c < r->ncols) ? r->d_cols[(size_t)c].p : nullptr; }
 double imm3_result_device_ms(const imm3_result* r) { return r ? r->device_ms : -1.0; }
 int imm3_result_kernel_launches(const imm3_result* r) { return r ? r->launches : IMM3_ERR_INVALID_ARG; }
+double imm3_result_stage_ms(const imm3_result* r, int stage) { return (r && stage >= 0 && stage < 2) ? r->stage_ms[stage] : -1.0; }
 int64_t imm3_result_algorithmic_bytes(const imm3_result* r) { return r ? r->alg_bytes : IMM3_ERR_INVALID_ARG; }
 
 // Row.toString = xs.mkString("Row(", ",", ")")  (Record.scala:13)

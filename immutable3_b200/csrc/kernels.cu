@@ -232,6 +232,9 @@ __device__ __forceinline__ void cta_exit(ScanCtrl* ctrl) {
 // a CTA busy emitting would otherwise sit on an un-counted earlier tile that every later tile in the
 // grid has to wait for.  Hand-offs are two-entry rings guarded by mbarriers (count_full, excl_full).
 // =============================================================================================
+#ifndef IMM3_EMIT_MIN_BLOCKS
+#define IMM3_EMIT_MIN_BLOCKS 2
+#endif
 #ifndef IMM3_DENSE_MIN_BLOCKS
 #define IMM3_DENSE_MIN_BLOCKS 3  // register budget: 3 CTAs (27 warps) per SM
 #endif
@@ -281,73 +284,93 @@ __device__ __forceinline__ uint32_t zero_halfwords(uint32_t t) {
     return ~(((t & 0x7FFF7FFFu) + 0x7FFF7FFFu) | t) & 0x80008000u;
 }
 
-// Selection word of the lane's 32 rows for one filter column.  `span_row` = tile-relative row of the
-// 1024-row sub-span this warp is evaluating.
-__device__ __noinline__ uint32_t dense_eval_filter(const ScanPlan& P, const FilterCol& f, bool staged, uint32_t stage_addr,
-                                                      long long tile_row0, int span_row, int lane) {
-    const uint32_t lane_off = (uint32_t)((span_row + lane * 32) * f.width);  // bytes into the column tile
-    const uint32_t saddr = stage_addr + (uint32_t)f.smem_off + lane_off;
-    const uint8_t* gptr = f.base + tile_row0 * f.width + lane_off;
-    uint32_t mask = 0;
+// Selection words of the lane for one filter column: word s covers the lane's 32 rows of the 1024-row
+// sub-span starting at tile-relative row `warp_row + s*1024`.  masks[s] is AND-ed in place.  One
+// out-of-line call per (tile, filter column) keeps the kernels small and amortises the setup.
+template <int W>
+__device__ __noinline__ void dense_eval_filter(const ScanPlan& P, const FilterCol& f, bool staged, uint32_t stage_addr,
+                                               long long tile_row0, int warp_row, int lane, uint32_t* masks) {
+    const uint32_t col_s = stage_addr + (uint32_t)f.smem_off;
+    const uint8_t* col_g = f.base + tile_row0 * f.width;
     if (f.kind == kFilterI8Range) {
         const uint32_t lo_b = ((uint32_t)f.lo ^ 0x80u) & 0xFFu;
         const uint32_t hi_b = lo_b + f.span;
         const uint32_t c1 = (0x100u - lo_b) * 0x00010001u;
         const uint32_t c2 = (0x100u | hi_b) * 0x00010001u;
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-            const int q = (c + lane) & 1;  // rotate so the 8 lanes of a quarter-warp hit distinct banks
-            const uint4 v = staged ? lds128(saddr + 16u * q) : ldg128(gptr + 16 * q);
-            mask |= swar_i8_chunk(v, c1, c2) << (16 * q);
+        for (int s = 0; s < W; s++) {
+            const uint32_t off = (uint32_t)(warp_row + s * 1024 + lane * 32);
+            uint32_t mask = 0;
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int q = (c + lane) & 1;  // rotate so the 8 lanes of a quarter-warp hit distinct banks
+                const uint4 v = staged ? lds128(col_s + off + 16u * q) : ldg128(col_g + off + 16 * q);
+                mask |= swar_i8_chunk(v, c1, c2) << (16 * q);
+            }
+            masks[s] &= mask;
         }
     } else if (f.kind == kFilterI32Range) {
         const uint32_t lo = (uint32_t)f.lo, span = f.span;
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-            const int q = (c + lane) & 7;
-            const uint4 v = staged ? lds128(saddr + 16u * q) : ldg128(gptr + 16 * q);
-            mask |= range_i32_chunk(v, lo, span) << (4 * q);
+        for (int s = 0; s < W; s++) {
+            const uint32_t off = (uint32_t)(warp_row + s * 1024 + lane * 32) * 4u;
+            uint32_t mask = 0;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const int q = (c + lane) & 7;
+                const uint4 v = staged ? lds128(col_s + off + 16u * q) : ldg128(col_g + off + 16 * q);
+                mask |= range_i32_chunk(v, lo, span) << (4 * q);
+            }
+            masks[s] &= mask;
         }
     } else if (f.width == 2) {
-        uint32_t acc[4] = {0, 0, 0, 0};  // per chunk: 8 pass bits
-        for (int l = 0; l < f.nlit; l++) {
-            const uint32_t lit = (uint32_t)P.lits[f.lit_off + 2 * l] | ((uint32_t)P.lits[f.lit_off + 2 * l + 1] << 8);
-            const uint32_t ll = lit * 0x00010001u;
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const int q = (c + lane) & 3;
-                const uint4 v = staged ? lds128(saddr + 16u * q) : ldg128(gptr + 16 * q);
-                const uint32_t h0 = zero_halfwords(v.x ^ ll), h1 = zero_halfwords(v.y ^ ll);
-                const uint32_t h2 = zero_halfwords(v.z ^ ll), h3 = zero_halfwords(v.w ^ ll);
-                const uint32_t bits = ((h0 >> 15) & 1u) | ((h0 >> 30) & 2u) | (((h1 >> 15) & 1u) << 2) | (((h1 >> 30) & 2u) << 2) |
-                                      (((h2 >> 15) & 1u) << 4) | (((h2 >> 30) & 2u) << 4) | (((h3 >> 15) & 1u) << 6) |
-                                      (((h3 >> 30) & 2u) << 6);
-                acc[c] |= bits << (8 * q);
+        for (int s = 0; s < W; s++) {
+            const uint32_t off = (uint32_t)(warp_row + s * 1024 + lane * 32) * 2u;
+            uint32_t mask = 0;
+            for (int l = 0; l < f.nlit; l++) {
+                const uint32_t lit = (uint32_t)P.lits[f.lit_off + 2 * l] | ((uint32_t)P.lits[f.lit_off + 2 * l + 1] << 8);
+                const uint32_t ll = lit * 0x00010001u;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int q = (c + lane) & 3;
+                    const uint4 v = staged ? lds128(col_s + off + 16u * q) : ldg128(col_g + off + 16 * q);
+                    const uint32_t h0 = zero_halfwords(v.x ^ ll), h1 = zero_halfwords(v.y ^ ll);
+                    const uint32_t h2 = zero_halfwords(v.z ^ ll), h3 = zero_halfwords(v.w ^ ll);
+                    // bits 15/31 of h* -> two row bits each
+                    const uint32_t b01 = (h0 >> 15) | (h1 >> 13), b23 = (h2 >> 11) | (h3 >> 9);
+                    const uint32_t lo4 = (b01 & 0x5u) | ((b01 >> 15) & 0xAu);
+                    const uint32_t hi4 = ((b23 >> 4) & 0x5u) | ((b23 >> 19) & 0xAu);
+                    mask |= (lo4 | (hi4 << 4)) << (8 * q);
+                }
             }
+            masks[s] &= mask;
         }
-        mask = acc[0] | acc[1] | acc[2] | acc[3];
     } else {
         // Generic k-byte cells: row-per-lane compare, ballot gives the bitmap word of rows 32j..32j+31,
         // which lane j keeps.
         const int k = f.width;
-        const uint32_t wbase_s = stage_addr + (uint32_t)f.smem_off + (uint32_t)(span_row * k);
-        const uint8_t* wbase_g = f.base + (tile_row0 + span_row) * k;
-        for (int j = 0; j < 32; j++) {
-            const int r = j * 32 + lane;
-            bool hit = false;
-            for (int l = 0; l < f.nlit && !hit; l++) {
-                bool eq = true;
-                for (int b = 0; b < k; b++) {
-                    const uint32_t cell = staged ? lds_u8(wbase_s + (uint32_t)(r * k + b)) : (uint32_t)__ldg(wbase_g + r * k + b);
-                    eq = eq && (cell == (uint32_t)P.lits[f.lit_off + l * k + b]);
+        for (int s = 0; s < W; s++) {
+            const uint32_t wbase_s = col_s + (uint32_t)((warp_row + s * 1024) * k);
+            const uint8_t* wbase_g = col_g + (long long)(warp_row + s * 1024) * k;
+            uint32_t mask = 0;
+            for (int j = 0; j < 32; j++) {
+                const int r = j * 32 + lane;
+                bool hit = false;
+                for (int l = 0; l < f.nlit && !hit; l++) {
+                    bool eq = true;
+                    for (int b = 0; b < k; b++) {
+                        const uint32_t cell = staged ? lds_u8(wbase_s + (uint32_t)(r * k + b)) : (uint32_t)__ldg(wbase_g + r * k + b);
+                        eq = eq && (cell == (uint32_t)P.lits[f.lit_off + l * k + b]);
+                    }
+                    hit = eq;
                 }
-                hit = eq;
+                const uint32_t w = __ballot_sync(0xFFFFFFFFu, hit);
+                if (lane == j) mask = w;
             }
-            const uint32_t w = __ballot_sync(0xFFFFFFFFu, hit);
-            if (lane == j) mask = w;
+            masks[s] &= mask;
         }
     }
-    return mask;
 }
 
 // Typed shared-memory loads for the projected cells of staged columns.
@@ -533,14 +556,14 @@ __global__ void __launch_bounds__(kDenseThreads, IMM3_DENSE_MIN_BLOCKS) scan_den
             unsigned lane_total = 0;
 #pragma unroll
             for (int s = 0; s < W; s++) {
-                const int span_row = warp * kWarpSpan + s * 1024;
-                const long long left = P.nrows - (tile_row0 + span_row + lane * 32);
-                uint32_t mask = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
-                for (int i = 0; i < P.nfilter; i++)
-                    mask &= dense_eval_filter(P, P.filter[i], staged, stage_addr, tile_row0, span_row, lane);
-                m_cur[s] = mask;
-                if (P.bitmap) P.bitmap[((tile_row0 + span_row) >> 5) + lane] = mask;
-                lane_total += __popc(mask);
+                const long long left = P.nrows - (tile_row0 + warp * kWarpSpan + s * 1024 + lane * 32);
+                m_cur[s] = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
+            }
+            for (int i = 0; i < P.nfilter; i++) dense_eval_filter<W>(P, P.filter[i], staged, stage_addr, tile_row0, warp * kWarpSpan, lane, m_cur);
+#pragma unroll
+            for (int s = 0; s < W; s++) {
+                if (P.bitmap) P.bitmap[((tile_row0 + warp * kWarpSpan + s * 1024) >> 5) + lane] = m_cur[s];
+                lane_total += __popc(m_cur[s]);
             }
             const unsigned warp_total = __reduce_add_sync(0xFFFFFFFFu, lane_total);
             if (lane == 0) S.warp_cnt[e][warp] = warp_total;
@@ -867,10 +890,11 @@ __global__ void __launch_bounds__(kBlockThreads) scan_blocks_kernel(const __grid
 //                      statically strided over the CTAs: no ordering, no tickets), evaluate the
 //                      conjunction and write the selection BITMAP (one word per lane, coalesced) plus
 //                      the match count of every 1024-row span and of every tile.
-//   K2 scan_kernel   : exclusive prefix sum of the tile counts (device-wide offsets, LIMIT clamp, total).
-//   K3 emit_kernel   : one warp per 1024-row span, no inter-warp dependency at all: span offset =
-//                      tile offset + the counts of the earlier spans of the tile; ballot/popc compaction
-//                      of the bitmap word into a warp-private selection vector; cooperative, coalesced
+//   K2 (tail of K1)  : the last CTA to finish K1 turns the tile counts into device-wide exclusive offsets
+//                      (LIMIT clamp, total) - no separate launch.
+//   K3 emit_kernel   : one warp per group of eight 1024-row spans, no inter-warp dependency at all: offset =
+//                      tile offset + the counts of the earlier spans of the tile; popc/scan compaction of
+//                      the bitmap words into a warp-private selection vector; cooperative, coalesced
 //                      Project gather of the select-list columns.
 // Every stage is embarrassingly parallel, so none of them can be held up by a slow CTA the way a
 // chained single-pass scan is; the price is the bitmap round trip (1 bit/row written + read).
@@ -878,11 +902,48 @@ __global__ void __launch_bounds__(kBlockThreads) scan_blocks_kernel(const __grid
 struct FilterShared {
     unsigned long long mbar_full[kMaxFilterStages];
     unsigned int warp_cnt[2][kComputeWarps];
+    unsigned long long scan_warp[kComputeWarps];
+    unsigned int is_last;
 };
+
+// Exclusive scan of the tile counts by one CTA of kComputeThreads threads (each thread owns a contiguous
+// chunk: two passes over L2-resident counts, one block-wide scan), LIMIT clamp of the total.
+__device__ void scan_tile_counts(FilterShared& S, const uint32_t* tile_cnt, unsigned long long* tile_off, long long ntiles,
+                                 long long limit, ScanCtrl* ctrl) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long chunk = (ntiles + kComputeThreads - 1) / kComputeThreads;
+    const long long i0 = (long long)tid * chunk, i1 = i0 + chunk < ntiles ? i0 + chunk : ntiles;
+    unsigned long long run = 0;
+    for (long long i = i0; i < i1; i++) run += __ldcg(tile_cnt + i);
+    unsigned long long incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += nb;
+    }
+    if (lane == 31) S.scan_warp[warp] = incl;
+    __syncthreads();
+    unsigned long long excl = incl - run, total = 0;
+#pragma unroll
+    for (int w = 0; w < kComputeWarps; w++) {
+        const unsigned long long ws = S.scan_warp[w];
+        if (w < warp) excl += ws;
+        total += ws;
+    }
+    for (long long i = i0; i < i1; i++) {
+        tile_off[i] = excl;
+        excl += __ldcg(tile_cnt + i);
+    }
+    if (tid == 0) {
+        tile_off[ntiles] = total;
+        ctrl->total = total < (unsigned long long)limit ? total : (unsigned long long)limit;
+    }
+}
 
 template <int W>
 __global__ void __launch_bounds__(kComputeThreads) filter_kernel(const __grid_constant__ ScanPlan P, uint32_t* __restrict__ bitmap,
-                                                                   uint32_t* __restrict__ span_cnt, uint32_t* __restrict__ tile_cnt) {
+                                                                   uint32_t* __restrict__ span_cnt, uint32_t* __restrict__ tile_cnt,
+                                                                   unsigned long long* __restrict__ tile_off, ScanCtrl* ctrl) {
     constexpr int kTile = kDenseTileRowsPerWord * W;
     constexpr int kWarpSpan = 1024 * W;
     __shared__ FilterShared S;
@@ -919,17 +980,20 @@ __global__ void __launch_bounds__(kComputeThreads) filter_kernel(const __grid_co
         const long long tile_row0 = tile * kTile;
         const uint32_t stage_addr = ring_addr + (uint32_t)slot * (uint32_t)P.stage_bytes;
         if (staged) mbar_wait(smem_u32(&S.mbar_full[slot]), parity, nullptr);
+        uint32_t m[W];
+#pragma unroll
+        for (int s = 0; s < W; s++) {
+            const long long left = P.nrows - (tile_row0 + warp * kWarpSpan + s * 1024 + lane * 32);
+            m[s] = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
+        }
+        for (int i = 0; i < P.nfilter; i++) dense_eval_filter<W>(P, P.filter[i], staged, stage_addr, tile_row0, warp * kWarpSpan, lane, m);
         unsigned warp_total = 0;
 #pragma unroll
         for (int s = 0; s < W; s++) {
-            const int span_row = warp * kWarpSpan + s * 1024;
-            const long long left = P.nrows - (tile_row0 + span_row + lane * 32);
-            uint32_t mask = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
-            for (int i = 0; i < P.nfilter; i++)
-                mask &= dense_eval_filter(P, P.filter[i], staged, stage_addr, tile_row0, span_row, lane);
-            bitmap[((tile_row0 + span_row) >> 5) + lane] = mask;
-            const unsigned c = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(mask));
-            if (lane == 0) span_cnt[(tile_row0 + span_row) >> 10] = c;
+            const long long span_row0 = tile_row0 + warp * kWarpSpan + s * 1024;
+            bitmap[(span_row0 >> 5) + lane] = m[s];
+            const unsigned c = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(m[s]));
+            if (lane == 0) span_cnt[span_row0 >> 10] = c;
             warp_total += c;
         }
         const int e = (int)(it & 1u);
@@ -945,93 +1009,152 @@ __global__ void __launch_bounds__(kComputeThreads) filter_kernel(const __grid_co
         }
         if (++slot == ring) { slot = 0; parity ^= 1u; }
     }
-}
 
-// Exclusive scan of the tile counts by one CTA (<= a few hundred thousand values), LIMIT clamp of the total.
-__global__ void __launch_bounds__(1024) scan_kernel(const uint32_t* __restrict__ tile_cnt, unsigned long long* __restrict__ tile_off,
-                                                      long long ntiles, long long limit, ScanCtrl* ctrl) {
-    __shared__ unsigned long long warp_sums[32];
-    __shared__ unsigned long long carry_s;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry_s = 0;
+    // The last CTA to finish turns the tile counts into device-wide offsets (saves a launch).
     __syncthreads();
-    for (long long base = 0; base < ntiles; base += 4096) {
-        unsigned long long v[4], run = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const long long i = base + (long long)tid * 4 + k;
-            v[k] = i < ntiles ? tile_cnt[i] : 0u;
-            run += v[k];
-        }
-        unsigned long long incl = run;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += nb;
-        }
-        if (lane == 31) warp_sums[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned long long w = warp_sums[lane], wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long nb = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-                if (lane >= o) wi += nb;
-            }
-            warp_sums[lane] = wi - w;  // exclusive
-        }
-        __syncthreads();
-        unsigned long long excl = carry_s + warp_sums[warp] + incl - run;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const long long i = base + (long long)tid * 4 + k;
-            if (i < ntiles) tile_off[i] = excl;
-            excl += v[k];
-        }
-        __syncthreads();
-        if (tid == 1023) carry_s = excl;
-        __syncthreads();
-    }
     if (tid == 0) {
-        tile_off[ntiles] = carry_s;
-        ctrl->total = carry_s < (unsigned long long)limit ? carry_s : (unsigned long long)limit;
+        __threadfence();
+        const unsigned prev = atomicAdd(&ctrl->exited, 1u);
+        S.is_last = prev == gridDim.x - 1;
+        if (S.is_last) ctrl->exited = 0;
+    }
+    __syncthreads();
+    if (S.is_last) {
+        __threadfence();
+        scan_tile_counts(S, tile_cnt, tile_off, ntiles, P.limit, ctrl);
     }
 }
 
-__global__ void __launch_bounds__(kComputeThreads) emit_kernel(const __grid_constant__ ScanPlan P, const uint32_t* __restrict__ bitmap,
+// A span whose 1024 rows all survive: straight coalesced copy, no selection vector.
+__device__ __noinline__ void emit_span_full(const ScanPlan& P, int lane, long long row0, long long g0) {
+    long long n = P.limit - g0;
+    if (n <= 0) return;
+    if (n > 1024) n = 1024;
+    for (int pc = 0; pc < P.nproj; pc++) {
+        const ProjCol& pj = P.proj[pc];
+        const int w = pj.width;
+        if (w == 4) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(pj.base) + row0;
+            uint32_t* dst = reinterpret_cast<uint32_t*>(pj.out) + g0;
+            for (int i = lane; i < n; i += 32) dst[i] = __ldg(src + i);
+        } else {
+            const uint8_t* src = pj.base + row0 * w;
+            uint8_t* dst = pj.out + g0 * w;
+            for (int i = lane; i < (int)n * w; i += 32) dst[i] = __ldg(src + i);
+        }
+    }
+}
+
+// K3.  Two mappings, chosen on the device from the total match count:
+//  * dense results (>= 32 surviving rows per span on average): one warp per 1024-row span - maximum
+//    parallelism, every span's three metadata loads issued together;
+//  * sparse results: one warp per group of 8 spans - the group's bitmap words are fetched up front, the
+//    surviving rows of consecutive spans are appended to ONE warp-private selection vector and emitted
+//    together, so a group pays one gather latency instead of eight.
+__global__ void __launch_bounds__(kComputeThreads, IMM3_EMIT_MIN_BLOCKS) emit_kernel(const __grid_constant__ ScanPlan P, const uint32_t* __restrict__ bitmap,
                                                                  const uint32_t* __restrict__ span_cnt,
                                                                  const unsigned long long* __restrict__ tile_off, int spans_per_tile,
                                                                  long long nspans) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned short* sel_w = reinterpret_cast<unsigned short*>(dyn_smem) + warp * 1024;
-    for (long long p = (long long)blockIdx.x * kComputeWarps + warp; p < nspans; p += (long long)gridDim.x * kComputeWarps) {
-        const long long t = p / spans_per_tile;
-        const int k = (int)(p - t * spans_per_tile);
-        // counts of the spans of this tile: lane i holds span i (spans_per_tile <= 32)
-        const unsigned c = lane < spans_per_tile && t * spans_per_tile + lane < nspans ? __ldg(span_cnt + t * spans_per_tile + lane) : 0u;
-        const int n = (int)__shfl_sync(0xFFFFFFFFu, c, k);
-        if (n == 0) continue;
-        const unsigned before = __reduce_add_sync(0xFFFFFFFFu, lane < k ? c : 0u);
-        const long long g0 = (long long)__ldg(tile_off + t) + before;
-        if (g0 >= P.limit) continue;
-        uint32_t mm = __ldg(bitmap + p * 32 + lane);
-        const unsigned cnt = (unsigned)__popc(mm);
-        unsigned incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += nb;
-        }
-        unsigned o = incl - cnt;
-        const unsigned iters = __reduce_max_sync(0xFFFFFFFFu, cnt);
-        for (unsigned it = 0; it < iters; it++) {
-            if (mm) {
-                sel_w[o++] = (unsigned short)(lane * 32 + __ffs(mm) - 1);
-                mm &= mm - 1u;
+    const long long ntiles = (nspans + spans_per_tile - 1) / spans_per_tile;
+    const unsigned long long total = __ldg(tile_off + ntiles);
+    const long long warp0 = (long long)blockIdx.x * kComputeWarps + warp, nwarps = (long long)gridDim.x * kComputeWarps;
+
+    if (total >= (unsigned long long)nspans * 32ull) {
+        // ---------------- one warp per span ----------------
+        for (long long p = warp0; p < nspans; p += nwarps) {
+            const long long t = p / spans_per_tile;
+            const int k = (int)(p - t * spans_per_tile);
+            // three independent loads: the tile's span counts (lane i holds span i), its offset, my bitmap word
+            const unsigned c = lane < spans_per_tile && t * spans_per_tile + lane < nspans ? __ldg(span_cnt + t * spans_per_tile + lane) : 0u;
+            const unsigned long long toff = __ldg(tile_off + t);
+            uint32_t mm = __ldg(bitmap + p * 32 + lane);
+            const int n = (int)__shfl_sync(0xFFFFFFFFu, c, k);
+            if (n == 0) continue;
+            const long long g0 = (long long)toff + __reduce_add_sync(0xFFFFFFFFu, lane < k ? c : 0u);
+            if (g0 >= P.limit) continue;
+            if (n == 1024) {
+                emit_span_full(P, lane, p * 1024, g0);
+                continue;
             }
+            const unsigned cnt = (unsigned)__popc(mm);
+            unsigned incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += nb;
+            }
+            unsigned o = incl - cnt;
+            const unsigned iters = __reduce_max_sync(0xFFFFFFFFu, cnt);
+            for (unsigned it = 0; it < iters; it++) {
+                if (mm) {
+                    sel_w[o++] = (unsigned short)(lane * 32 + __ffs(mm) - 1);
+                    mm &= mm - 1u;
+                }
+            }
+            __syncwarp();
+            emit_span_all(P, sel_w, n, lane, false, 0u, 0, p * 1024, g0);
+            __syncwarp();
+        }
+        return;
+    }
+
+    // ---------------- one warp per group of 8 spans ----------------
+    const long long ngroups = (nspans + 7) >> 3;
+    for (long long u = warp0; u < ngroups; u += nwarps) {
+        const long long p0 = u * 8;                   // first span of the group
+        const long long t = p0 / spans_per_tile;      // groups never straddle tiles (spans_per_tile is 8, 16 or 32)
+        const int k0 = (int)(p0 - t * spans_per_tile);
+        const unsigned c = lane < spans_per_tile && t * spans_per_tile + lane < nspans ? __ldg(span_cnt + t * spans_per_tile + lane) : 0u;
+        const unsigned long long toff = __ldg(tile_off + t);
+        const unsigned in_group = __reduce_add_sync(0xFFFFFFFFu, (lane >= k0 && lane < k0 + 8) ? c : 0u);
+        if (in_group == 0) continue;
+        long long g0 = (long long)toff + __reduce_add_sync(0xFFFFFFFFu, lane < k0 ? c : 0u);  // ordinal of the group's first surviving row
+        if (g0 >= P.limit) continue;
+        uint32_t mw[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const unsigned ck = __shfl_sync(0xFFFFFFFFu, c, k0 + k);
+            mw[k] = (ck && ck != 1024u) ? __ldg(bitmap + (p0 + k) * 32 + lane) : 0u;
+        }
+        int fill = 0;          // rows in the selection vector, first of them is global ordinal g0
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int n = (int)__shfl_sync(0xFFFFFFFFu, c, k0 + k);
+            if (n == 0) continue;
+            if (n == 1024 || fill + n > 1024) {  // flush what has been gathered so far
+                __syncwarp();
+                if (fill) emit_span_all(P, sel_w, fill, lane, false, 0u, 0, p0 * 1024, g0);
+                __syncwarp();
+                g0 += fill;
+                fill = 0;
+            }
+            if (n == 1024) {
+                emit_span_full(P, lane, (p0 + k) * 1024, g0);
+                g0 += 1024;
+                continue;
+            }
+            uint32_t mm = mw[k];
+            const unsigned cnt = (unsigned)__popc(mm);
+            unsigned incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += nb;
+            }
+            unsigned o = (unsigned)fill + incl - cnt;
+            const unsigned iters = __reduce_max_sync(0xFFFFFFFFu, cnt);
+            for (unsigned it = 0; it < iters; it++) {
+                if (mm) {
+                    sel_w[o++] = (unsigned short)(k * 1024 + lane * 32 + __ffs(mm) - 1);
+                    mm &= mm - 1u;
+                }
+            }
+            fill += n;
         }
         __syncwarp();
-        emit_span_all(P, sel_w, n, lane, false, 0u, 0, p * 1024, g0);
+        if (fill) emit_span_all(P, sel_w, fill, lane, false, 0u, 0, p0 * 1024, g0);
         __syncwarp();
     }
 }
@@ -1098,18 +1221,13 @@ cudaError_t emit_kernel_occupancy(int* blocks_per_sm) {
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, emit_kernel, kComputeThreads, kComputeWarps * 1024 * 2);
 }
-cudaError_t launch_filter(const ScanPlan& plan, uint32_t* bitmap, uint32_t* span_cnt, uint32_t* tile_cnt, int grid, size_t dyn_smem,
-                          cudaStream_t stream) {
+cudaError_t launch_filter(const ScanPlan& plan, uint32_t* bitmap, uint32_t* span_cnt, uint32_t* tile_cnt, unsigned long long* tile_off,
+                          ScanCtrl* ctrl, int grid, size_t dyn_smem, cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    if (plan.words_per_lane == 4) filter_kernel<4><<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt);
-    else if (plan.words_per_lane == 2) filter_kernel<2><<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt);
-    else filter_kernel<1><<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt);
-    return cudaGetLastError();
-}
-cudaError_t launch_tile_scan(const uint32_t* tile_cnt, unsigned long long* tile_off, long long ntiles, long long limit, ScanCtrl* ctrl,
-                             cudaStream_t stream) {
-    scan_kernel<<<1, 1024, 0, stream>>>(tile_cnt, tile_off, ntiles, limit, ctrl);
+    if (plan.words_per_lane == 4) filter_kernel<4><<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt, tile_off, ctrl);
+    else if (plan.words_per_lane == 2) filter_kernel<2><<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt, tile_off, ctrl);
+    else filter_kernel<1><<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt, tile_off, ctrl);
     return cudaGetLastError();
 }
 cudaError_t launch_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* span_cnt, const unsigned long long* tile_off,

@@ -15,10 +15,8 @@ cudaError_t launch_scan_dense(const ScanPlan& plan, ScanCtrl* ctrl, unsigned lon
                               cudaStream_t stream);
 cudaError_t filter_kernel_occupancy(int words_per_lane, size_t dyn_smem, int* blocks_per_sm);
 cudaError_t emit_kernel_occupancy(int* blocks_per_sm);
-cudaError_t launch_filter(const ScanPlan& plan, uint32_t* bitmap, uint32_t* span_cnt, uint32_t* tile_cnt, int grid, size_t dyn_smem,
-                          cudaStream_t stream);
-cudaError_t launch_tile_scan(const uint32_t* tile_cnt, unsigned long long* tile_off, long long ntiles, long long limit, ScanCtrl* ctrl,
-                             cudaStream_t stream);
+cudaError_t launch_filter(const ScanPlan& plan, uint32_t* bitmap, uint32_t* span_cnt, uint32_t* tile_cnt, unsigned long long* tile_off,
+                          ScanCtrl* ctrl, int grid, size_t dyn_smem, cudaStream_t stream);
 cudaError_t launch_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* span_cnt, const unsigned long long* tile_off,
                         int spans_per_tile, long long nspans, int grid, cudaStream_t stream);
 cudaError_t launch_scan_blocks(const ScanPlan& plan, ScanCtrl* ctrl, unsigned long long* status, int grid, size_t dyn_smem,

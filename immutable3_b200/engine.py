@@ -190,6 +190,9 @@ class Result:
     def kernel_launches(self) -> int:
         return int(self._lib.imm3_result_kernel_launches(self._h))
 
+    def stage_ms(self, stage: int) -> float:
+        return float(self._lib.imm3_result_stage_ms(self._h, stage))
+
     @property
     def algorithmic_bytes(self) -> int:
         return int(self._lib.imm3_result_algorithmic_bytes(self._h))

@@ -159,6 +159,9 @@ const void* imm3_result_col_device(const imm3_result* r, int col); /* device cop
 int imm3_result_format_row(const imm3_result* r, int64_t row, char* buf, size_t buflen);
 double imm3_result_device_ms(const imm3_result* r);         /* CUDA-event time of the kernels of begin  */
 int imm3_result_kernel_launches(const imm3_result* r);      /* kernels launched by begin                */
+/* CUDA-event time of one stage of begin: 0 = filter (+scan) kernel, 1 = emit kernel (multi-pass path);
+ * the fused single-pass kernels report everything as stage 0. */
+double imm3_result_stage_ms(const imm3_result* r, int stage);
 int64_t imm3_result_algorithmic_bytes(const imm3_result* r);/* SURVEY.md §8d formula for this query     */
 int imm3_result_free(imm3_result* r);
 
