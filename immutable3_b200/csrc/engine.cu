@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -113,6 +114,7 @@ struct imm3_db {
     BufPool dev_pool, host_pool;
     Buf d_bitmap, h_bitmap;
     Buf d_span_cnt, d_tile_cnt, d_tile_off;  // multi-pass pipeline scratch (grow-only)
+    Buf d_trace;                             // IMM3_TRACE debugging buffer
     std::string explain_buf;
 };
 
@@ -253,6 +255,7 @@ void free_device_side(imm3_db* db) {
     if (db->d_span_cnt.p) cudaFree(db->d_span_cnt.p);
     if (db->d_tile_cnt.p) cudaFree(db->d_tile_cnt.p);
     if (db->d_tile_off.p) cudaFree(db->d_tile_off.p);
+    if (db->d_trace.p) cudaFree(db->d_trace.p);
     if (db->h_bitmap.p) cudaFreeHost(db->h_bitmap.p);
     if (db->d_status) cudaFree(db->d_status);
     if (db->d_ctrl) cudaFree(db->d_ctrl);
@@ -271,6 +274,8 @@ struct Prepared {
     bool block_mode = false;
     bool multipass = false;   // dense tables: filter -> scan -> emit kernels instead of the fused single pass
     int grid_emit = 0;
+    int grid_emit_stream = 0, emit_stage_bytes = 0, emit_ring = 0;  // streaming emit kernel (dense results); 0 = not usable
+    size_t emit_smem = 0;
     ScanPlan sp;
     size_t dyn_smem = 0;
     int grid = 0;
@@ -382,35 +387,42 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
         pr->dyn_smem = blocks_kernel_smem_bytes(sp.npfor, t.max_block_rows);
         CUDA_TRY(blocks_kernel_occupancy(pr->dyn_smem, &occ));
     } else {
-        // Tile = 8192 * W rows.  W = 2 while one stage (a tile of every filter column) stays within
-        // 32 KiB, else 1: a 3-deep TMA ring then leaves room for 2-3 CTAs (18-27 warps) per SM.  Filter
-        // sets wider than 56 KiB per stage fall back to direct global loads.
         int row_bytes = 0;
         for (int i = 0; i < sp.nfilter; i++) row_bytes += sp.filter[i].width;
-        int W = (kDenseTileRowsPerWord * 2 * row_bytes <= 32 * 1024) ? 2 : 1;
-        if (const char* e = getenv("IMM3_DENSE_W")) {  // tuning / A-B knob
-            int v = atoi(e);
-            if (v == 1 || v == 2 || v == 4) W = v;
-        }
-        const int tile_rows = kDenseTileRowsPerWord * W;
-        sp.words_per_lane = W;
-        sp.ntiles = (t.nrows + tile_rows - 1) / tile_rows;
-        const int stage_bytes = tile_rows * row_bytes;
-        int stages = 0;
-        const bool can_stage = !(db->flags & IMM3_OPEN_NO_TMA) && stage_bytes > 0 && stage_bytes <= 56 * 1024;
+        const int sub_bytes = kDenseTileRowsPerWord * row_bytes;  // one 8192-row sub-tile of every filter column
+        const bool can_stage = !(db->flags & IMM3_OPEN_NO_TMA) && sub_bytes > 0 && sub_bytes <= 56 * 1024;
         if (can_stage) {
             int off = 0;
             for (int i = 0; i < sp.nfilter; i++) {
                 sp.filter[i].smem_off = off;
-                off += tile_rows * sp.filter[i].width;
+                off += kDenseTileRowsPerWord * sp.filter[i].width;
             }
         }
         if (pr->multipass) {
-            // K1 streams: as deep a ring as ~96 KiB allows (tiles are statically strided, so depth is free)
-            if (can_stage) stages = std::max(2, std::min(kMaxFilterStages, (96 * 1024) / stage_bytes));
+            // Multi-pass filter kernel: tile = 8192 * W rows, W = 2 while one stage stays within 16 KiB.
+            int W = (kDenseTileRowsPerWord * 2 * row_bytes <= 16 * 1024) ? 2 : 1;
+            if (const char* e = getenv("IMM3_DENSE_W")) {  // tuning / A-B knob
+                int v = atoi(e);
+                if (v == 1 || v == 2 || v == 4) W = v;
+            }
+            const int tile_rows = kDenseTileRowsPerWord * W;
+            const int stage_bytes = tile_rows * row_bytes;
+            const bool stage_ok = can_stage && stage_bytes <= 56 * 1024;
+            if (stage_ok)
+                for (int i = 0, off = 0; i < sp.nfilter; i++) {
+                    sp.filter[i].smem_off = off;
+                    off += tile_rows * sp.filter[i].width;
+                }
+            else
+                for (int i = 0; i < sp.nfilter; i++) sp.filter[i].smem_off = -1;
+            sp.words_per_lane = W;
+            sp.ntiles = (t.nrows + tile_rows - 1) / tile_rows;
+            int stages = 0;
+            // K1 streams: a ring of ~48 KiB, so that four CTAs (32 warps) share an SM
+            if (stage_ok) stages = std::max(2, std::min(kMaxFilterStages, (48 * 1024) / stage_bytes));
             if (const char* e = getenv("IMM3_FILTER_STAGES")) {
                 int v = atoi(e);
-                if (can_stage && v >= 2 && v <= kMaxFilterStages && (size_t)v * stage_bytes <= 200 * 1024) stages = v;
+                if (stage_ok && v >= 2 && v <= kMaxFilterStages && (size_t)v * stage_bytes <= 200 * 1024) stages = v;
             }
             sp.stages = stages;
             sp.stage_bytes = stage_bytes;
@@ -420,29 +432,74 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
             CUDA_TRY(emit_kernel_occupancy(&occ_emit));
             const int64_t nspans = sp.ntiles * (tile_rows / 1024);
             pr->grid_emit = (int)std::max<int64_t>(1, std::min<int64_t>((nspans + 7) / 8, (int64_t)db->num_sms * std::max(1, occ_emit)));
+            // Streaming emit kernel (dense results): a stage = bitmap words + span counts + one 8192-row tile of every
+            // projected column, if that fits.
+            int pstage = 0;
+            for (int i = 0; i < sp.nproj; i++) {
+                sp.proj[i].stage_off = pstage;
+                pstage += 1024 * sp.proj[i].width;
+            }
+            pr->emit_stage_bytes = 0;
+            if (sp.nproj > 0 && 8 * pstage <= 64 * 1024 && !(db->flags & IMM3_OPEN_NO_TMA) && !getenv("IMM3_NO_EMIT_STREAM")) {
+                pr->emit_stage_bytes = emit_stream_header_bytes() + 8 * pstage;
+                pr->emit_ring = std::max(2, std::min(4, (80 * 1024) / pr->emit_stage_bytes));
+                if (const char* e = getenv("IMM3_EMIT_STAGES")) {
+                    int v = atoi(e);
+                    if (v >= 2 && v <= 4) pr->emit_ring = v;
+                }
+                pr->emit_smem = emit_stream_smem_bytes(pr->emit_stage_bytes, pr->emit_ring);
+                int occ_s = 0;
+                CUDA_TRY(emit_stream_occupancy(pr->emit_smem, &occ_s));
+                if (occ_s < 1) pr->emit_stage_bytes = 0;
+                pr->grid_emit_stream = (int)std::max<int64_t>(1, std::min<int64_t>(sp.ntiles * W, (int64_t)db->num_sms * std::max(1, occ_s)));
+            }
         } else {
+            // Fused kernel: a tile is NS sub-tiles of 8192 rows, NS such that a tile streams ~64 KiB of filter
+            // columns: one offset hand-off per tile, so bigger tiles keep the scanner warp off the critical path.
+            int NS = sub_bytes > 0 ? std::max(1, std::min(4, (64 * 1024) / sub_bytes)) : 4;
+            if (const char* e = getenv("IMM3_DENSE_W")) {  // tuning / A-B knob
+                int v = atoi(e);
+                if (v >= 1 && v <= kMaxSubtiles) NS = v;
+            }
+            sp.subtiles = NS;
+            sp.words_per_lane = 1;
+            const int64_t tile_rows = (int64_t)NS * kDenseTileRowsPerWord;
+            sp.ntiles = (t.nrows + tile_rows - 1) / tile_rows;
+            int stages = 0;
+            // Dense spans stream the projected columns through a warp-private buffer: 1024 rows of every column.
+            int pstage = 0;
+            for (int i = 0; i < sp.nproj; i++) {
+                sp.proj[i].stage_off = pstage;
+                pstage += 1024 * sp.proj[i].width;
+            }
+            if (pstage > 8 * 1024 || (db->flags & IMM3_OPEN_NO_TMA)) pstage = 0;  // too wide (or TMA switched off): always gather
+            sp.proj_stage_bytes = pstage;
+            sp.stream_min_cnt = 64;
+            if (const char* e = getenv("IMM3_STREAM_MIN")) sp.stream_min_cnt = std::max(1, atoi(e));
+            const size_t fixed = 16 * 1024 + (size_t)2 * NS * 1024 + (size_t)8 * pstage;  // selection vectors, bitmap words, staging
             if (can_stage) {
-                stages = 3;  // tile j in E, tile j+1 in F, tile j+2 in flight
+                stages = std::max(2, std::min(kMaxStages, (32 * 1024) / sub_bytes));  // sub-tiles in flight ahead of the filter
                 if (const char* e = getenv("IMM3_DENSE_STAGES")) {
                     int v = atoi(e);
-                    if (v >= 3 && v <= kMaxStages) stages = v;
+                    if (v >= 2 && v <= kMaxStages) stages = v;
                 }
-                while (stages > 3 && 16 * 1024 + (size_t)stages * (size_t)stage_bytes > 200 * 1024) stages--;
+                while (stages > 2 && fixed + (size_t)stages * (size_t)sub_bytes > 200 * 1024) stages--;
             }
             sp.stages = stages;
-            sp.stage_bytes = stage_bytes;
-            pr->dyn_smem = 16 * 1024 + (size_t)stages * (size_t)stage_bytes;  // warp-private selection lists + TMA ring
-            CUDA_TRY(dense_kernel_occupancy(W, pr->dyn_smem, &occ));
+            sp.stage_bytes = sub_bytes;
+            pr->dyn_smem = fixed + (size_t)stages * (size_t)sub_bytes;
+            CUDA_TRY(dense_kernel_occupancy(stages > 0, pr->dyn_smem, &occ));
         }
     }
     if (sp.ntiles >= (int64_t)0x7FFFFFFF) return fail(IMM3_ERR_UNSUPPORTED, "too many tiles (%lld)", (long long)sp.ntiles);
     if (occ < 1) return fail(IMM3_ERR_CUDA, "kernel does not fit on an SM (dynamic shared memory %zu bytes)", pr->dyn_smem);
     const int64_t persistent = (int64_t)db->num_sms * occ;
     pr->grid = (int)std::max<int64_t>(1, std::min<int64_t>(sp.ntiles, persistent));
-    if ((size_t)sp.ntiles > db->status_cap) {
+    const size_t status_need = 2 * (size_t)status_round_up(sp.ntiles);  // tile counts + (dense kernel) tile offsets
+    if (status_need > db->status_cap) {
         if (db->d_status) CUDA_TRY(cudaFree(db->d_status));
         db->d_status = nullptr;
-        size_t cap = (size_t)sp.ntiles + (size_t)sp.ntiles / 4 + 1024;
+        size_t cap = status_need + status_need / 4 + 1024;
         CUDA_TRY(cudaMalloc(&db->d_status, cap * sizeof(unsigned long long)));
         CUDA_TRY(cudaMemsetAsync(db->d_status, 0, cap * sizeof(unsigned long long), db->stream));
         db->status_cap = cap;
@@ -466,14 +523,16 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
     if (pr->multipass) {
         const int64_t tile_rows = (int64_t)kDenseTileRowsPerWord * pr->sp.words_per_lane;
         const int64_t ntiles = pr->sp.ntiles, nspans = ntiles * (tile_rows / 1024);
+        const int64_t nsub = ntiles * pr->sp.words_per_lane;  // 8192-row sub-tiles: the unit of the offset scan
         int rc;
         if (!pr->sp.bitmap) {
             if ((rc = ensure_buf(&db->d_bitmap, (size_t)(ntiles * tile_rows / 32 + 2) * 4))) return rc;
             pr->sp.bitmap = (uint32_t*)db->d_bitmap.p;
         }
         if ((rc = ensure_buf(&db->d_span_cnt, (size_t)nspans * 4))) return rc;
-        if ((rc = ensure_buf(&db->d_tile_cnt, (size_t)ntiles * 4))) return rc;
-        if ((rc = ensure_buf(&db->d_tile_off, (size_t)(ntiles + 1) * 8))) return rc;
+        const size_t nsub_pad = ((size_t)nsub + 4095) / 4096 * 4096 + 16;  // whole rounds of the offset scan
+        if ((rc = ensure_buf(&db->d_tile_cnt, nsub_pad * 4))) return rc;
+        if ((rc = ensure_buf(&db->d_tile_off, nsub_pad * 8))) return rc;
         CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
         CUDA_TRY(launch_filter(pr->sp, pr->sp.bitmap, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
                                (unsigned long long*)db->d_tile_off.p, db->d_ctrl, pr->grid, pr->dyn_smem, db->stream));
@@ -481,12 +540,26 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
         CUDA_TRY(cudaEventRecord(db->ev_mid, db->stream));
         have_mid = true;
         if (pr->sp.nproj > 0) {
-            CUDA_TRY(launch_emit(pr->sp, pr->sp.bitmap, (const uint32_t*)db->d_span_cnt.p, (const unsigned long long*)db->d_tile_off.p,
-                                 (int)(tile_rows / 1024), nspans, pr->grid_emit, db->stream));
-            *launches = 2;
+            // Two emit kernels, one of which does the work: which one is decided on the device from the match count.
+            const int stream_ok = pr->emit_stage_bytes > 0;
+            if (stream_ok) {
+                CUDA_TRY(launch_emit_stream(pr->sp, pr->sp.bitmap, (const uint32_t*)db->d_span_cnt.p, (const uint32_t*)db->d_tile_cnt.p,
+                                            (const unsigned long long*)db->d_tile_off.p, nsub, pr->emit_ring, pr->emit_stage_bytes, 1,
+                                            pr->grid_emit_stream, pr->emit_smem, db->stream));
+                (*launches)++;
+            }
+            CUDA_TRY(launch_emit(pr->sp, pr->sp.bitmap, (const uint32_t*)db->d_span_cnt.p, (const unsigned long long*)db->d_tile_off.p, 8, nspans,
+                                 pr->grid_emit, stream_ok, db->stream));
+            (*launches)++;
         }
         CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
     } else {
+        if (!pr->block_mode && getenv("IMM3_TRACE")) {  // debugging: per-tile globaltimer stamps
+            int rc = ensure_buf(&db->d_trace, (size_t)pr->sp.ntiles * 64);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemsetAsync(db->d_trace.p, 0, (size_t)pr->sp.ntiles * 64, db->stream));
+            pr->sp.trace = (unsigned long long*)db->d_trace.p;
+        }
         CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
         if (pr->block_mode) CUDA_TRY(launch_scan_blocks(pr->sp, db->d_ctrl, db->d_status, pr->grid, pr->dyn_smem, db->stream));
         else CUDA_TRY(launch_scan_dense(pr->sp, db->d_ctrl, db->d_status, pr->grid, pr->dyn_smem, db->stream));
@@ -511,6 +584,14 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
         }
     }
     *total = (int64_t)db->h_ctrl->total;
+    if (pr->sp.trace) {
+        std::vector<unsigned long long> h((size_t)pr->sp.ntiles * 8);
+        CUDA_TRY(cudaMemcpy(h.data(), pr->sp.trace, h.size() * 8, cudaMemcpyDeviceToHost));
+        if (FILE* f = fopen(getenv("IMM3_TRACE"), "wb")) {
+            fwrite(h.data(), 8, h.size(), f);
+            fclose(f);
+        }
+    }
     return 0;
 }
 
@@ -554,6 +635,9 @@ int imm3_open(const char* data_dir, const imm3_open_opts* opts, imm3_db** out) {
             CUDA_TRY(cudaGetDeviceProperties(&prop, db->device));
             if (prop.major < 10) return fail(IMM3_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", db->device, prop.major, prop.minor);
             db->num_sms = prop.multiProcessorCount;
+            if (const char* g = getenv("IMM3_L2_FETCH")) {  // experiment: DRAM->L2 fetch granularity hint (32 / 64 / 128 bytes)
+                CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g)));
+            }
             CUDA_TRY(cudaStreamCreateWithFlags(&db->own_stream, cudaStreamNonBlocking));
             db->stream = db->own_stream;
             CUDA_TRY(cudaEventCreate(&db->ev0));

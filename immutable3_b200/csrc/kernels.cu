@@ -97,12 +97,29 @@ __device__ __noinline__ void watchdog_trap(ScanCtrl* ctrl, unsigned code) {
     __trap();
 }
 
+// try_wait with a suspend-time hint: the hardware parks the warp instead of having it spin through issue slots
+// that the working warps of the SM need.
+__device__ __forceinline__ bool mbar_try_wait_park(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(20000u)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, ScanCtrl* ctrl) {
     if (mbar_try_wait(bar, parity)) return;
-    const uint64_t t0 = globaltimer_ns();
+    uint64_t t0 = 0;
     unsigned spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > kWatchdogNs) watchdog_trap(ctrl, 1);
+    while (!mbar_try_wait_park(bar, parity)) {
+        if ((++spins & 63u) == 0) {  // the watchdog clock is read once per 64 parked waits
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > kWatchdogNs) watchdog_trap(ctrl, 1);
+        }
     }
 }
 
@@ -110,6 +127,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, ScanCtr
 // Tile status words for the decoupled look-back: [63:24] value, [23:2] epoch, [1:0] state
 // =============================================================================================
 constexpr unsigned kStateNone = 0, kStateAggregate = 1, kStatePrefix = 2;
+
 
 __device__ __forceinline__ unsigned long long pack_status(uint32_t epoch, unsigned state, unsigned long long value) {
     return (value << 24) | ((unsigned long long)(epoch & 0x3FFFFFu) << 2) | state;
@@ -203,173 +221,199 @@ __device__ __forceinline__ void cta_exit(ScanCtrl* ctrl) {
             ctrl->ticket = 0;
             ctrl->done = 0;
             ctrl->exited = 0;
+            ctrl->scanner = 0;
         }
     }
 }
 
 // =============================================================================================
-// Dense kernel
+// Dense kernel (fused single pass)
 //
-// CTA = 8 compute warps + 1 control warp.  A tile is 8192*W consecutive rows (W = 1, 2 or 4 bitmap
-// words per lane): warp w owns rows [w*1024*W, (w+1)*1024*W) of the tile, split into W sub-spans of
-// 1024 rows in which lane l owns rows [32*l, 32*l+32) = one 32-bit word of the selection bitmap.
+// CTA = 8 compute warps + a producer warp + a scanner-candidate warp, several CTAs per SM.  A tile is
+// 8192*W consecutive rows (W = 1, 2 or 4 bitmap words per lane): compute warp w owns rows
+// [w*1024*W, (w+1)*1024*W) of the tile, split into W spans of 1024 rows in which lane l owns rows
+// [32*l, 32*l+32) = one 32-bit word of the selection bitmap.
 //
-// The tiles of a CTA are software-pipelined so that nothing waits on the device-wide prefix:
-//
-//   compute warps :  F(0) | F(1) E(0) | F(2) E(1) | ...
-//       F(j) "filter" : wait for tile j's bytes (TMA -> shared memory, mbarrier), evaluate the conjunction
-//                       with SWAR compares, popc + warp/CTA scan -> every lane knows the tile-local rank
-//                       of its first selected row; PUBLISH the tile count.  The lane keeps its bitmap
-//                       words and ranks in registers.
-//       E(j) "emit"   : pick up the tile's global offset (resolved while F(j+1) ran), walk the set bits
-//                       four at a time: gather the projected cells (staged filter columns from shared
-//                       memory, other columns from global memory) and store them at offset + rank.
-//                       Then recycle the tile's ring slot (ticket + TMA bulk copies).
-//   control warp  :  for each tile in order: take its count, publish it, run the decoupled look-back,
-//                    hand the exclusive offset back.  It overlaps F(j+1)/E(j) of the compute warps.
-//
-// Publishing count(j+1) BEFORE emitting tile j matters: tickets are drawn ahead (for the TMA ring), so
-// a CTA busy emitting would otherwise sit on an un-counted earlier tile that every later tile in the
-// grid has to wait for.  Hand-offs are two-entry rings guarded by mbarriers (count_full, excl_full).
+//   producer warp : draws tiles from an atomic ticket `ring` tiles ahead and starts their 1-D TMA bulk
+//                   copies into the CTA's shared-memory ring (full/empty mbarriers per slot).
+//   compute warps : per tile
+//     1. decode + conjunctive filter: 128-bit shared-memory loads, SIMD-within-a-register compares
+//        -> W bitmap words per lane in registers; popc + warp reduce -> tile count, PUBLISHED at once
+//     2. bitmap word -> warp-private selection vector (popc scan), overlapping the offset hand-off
+//     3. Project: entry i of the selection vector is gathered (filter columns from the staged tile,
+//        other columns from global memory, four independent gathers per lane) and stored at
+//        offset + rank: coalesced stores in canonical row order, LIMIT = clamp on the offset.
+//   scanner warp  : ONE warp of the whole grid (elected by an atomic) turns the published tile counts into
+//                   exclusive offsets, 256 tiles per round, and owns the LIMIT cut and the total.
 // =============================================================================================
 #ifndef IMM3_EMIT_MIN_BLOCKS
 #define IMM3_EMIT_MIN_BLOCKS 2
 #endif
 #ifndef IMM3_DENSE_MIN_BLOCKS
-#define IMM3_DENSE_MIN_BLOCKS 3  // register budget: 3 CTAs (27 warps) per SM
+#define IMM3_DENSE_MIN_BLOCKS 3  // register budget: 3 CTAs (24 compute warps) per SM
 #endif
 constexpr int kComputeThreads = 256;
 constexpr int kComputeWarps = kComputeThreads / 32;
 constexpr unsigned kNoMoreTiles = 0xFFFFFFFFu;
+static_assert(kDenseThreads == kComputeThreads + 64, "dense kernel: 8 compute warps + producer warp + scanner warp");
 
 struct DenseShared {
-    unsigned long long mbar_full[kMaxStages];  // TMA bytes of a ring slot have landed
-    unsigned long long mbar_count[2];          // compute -> control: tile_count / tile_id valid
-    unsigned long long mbar_excl[2];           // control -> compute: tile_excl valid
-    unsigned int ticket[kMaxStages];
-    int issued[kMaxStages];
-    unsigned int warp_cnt[2][kComputeWarps];
-    unsigned int tile_count[2];
-    unsigned int tile_id[2];
-    long long tile_excl[2];
+    unsigned long long mbar_full[kMaxStages];   // producer -> compute warps: tile id valid, TMA bytes landed
+    unsigned long long mbar_empty[kMaxStages];  // compute warps -> producer: slot free again
+    unsigned long long mbar_warp[kComputeWarps];  // per compute warp: its projected-column span has landed
+    unsigned int tile[kMaxStages];              // tile held by a ring slot
+    unsigned int span_cnt[2][kMaxSubtiles * kComputeWarps];  // selected rows of every 1024-row span of the tile
+    long long excl[2];
+    unsigned int role;
+    uint8_t lits[kLitPoolBytes];  // MATCH literals of the plan
+    FilterCol filter[kMaxFilterCols];  // the plan's tables (loop-indexed, so not read from the parameter bank)
+    ProjCol proj[kMaxProjCols];
 };
+constexpr unsigned kRoleWorker = 0, kRoleScannerAndWorker = 1, kRoleScannerOnly = 2, kRoleIdle = 3;
 
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// TINYINT range over the lane's 32 consecutive rows (two 16-byte chunks).  Values are biased to
-// unsigned order (x ^ 0x80) and tested in 16-bit SWAR lanes:  bit 8 of (e + 256 - lo) says e >= lo,
-// bit 8 of ((256 | hi) - e) says e <= hi.
-__device__ __forceinline__ uint32_t swar_i8_word(uint32_t x, uint32_t c1, uint32_t c2) {
-    const uint32_t y = x ^ 0x80808080u;
-    const uint32_t e = y & 0x00FF00FFu;
-    const uint32_t o = (y >> 8) & 0x00FF00FFu;
-    const uint32_t pe = (e + c1) & (c2 - e);
-    const uint32_t po = (o + c1) & (c2 - o);
-    const uint32_t z = ((pe >> 8) & 0x00010001u) | ((po >> 7) & 0x00020002u);
-    return (z | (z >> 14)) & 0xFu;
-}
-__device__ __forceinline__ uint32_t swar_i8_chunk(const uint4& v, uint32_t c1, uint32_t c2) {
-    return swar_i8_word(v.x, c1, c2) | (swar_i8_word(v.y, c1, c2) << 4) | (swar_i8_word(v.z, c1, c2) << 8) |
-           (swar_i8_word(v.w, c1, c2) << 12);
+// ---- SIMD-within-a-register predicates ----------------------------------------------------------
+// TINYINT inclusive range [lo, hi] on 16 raw (two's-complement) bytes -> 16 selection bits.  The low
+// seven bits of every byte are range-tested with carry-free byte-wise arithmetic (bit 7 of xl + c1 says
+// xl >= t1, bit 7 of c2 - xl says xl <= t2), the sign bit picks which tests apply:
+//   MODE 0: 0 <= lo        rows must be non-negative, t1 = lo,       t2 = hi
+//   MODE 1: hi < 0         rows must be negative,     t1 = lo + 128, t2 = hi + 128
+//   MODE 2: lo < 0 <= hi   negative rows: xl >= lo + 128; non-negative rows: xl <= hi
+// The four flag bits of a word (bits 7, 15, 23, 31) are gathered into a nibble by one multiply.
+template <int MODE>
+__device__ __forceinline__ uint32_t i8_range16(const uint4& v, uint32_t c1, uint32_t c2) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 3; k >= 0; k--) {
+        const uint32_t x = w[k];
+        const uint32_t xl = x & 0x7F7F7F7Fu;
+        const uint32_t g = xl + c1, l = c2 - xl;
+        uint32_t m;
+        if (MODE == 0) m = (g & l & 0x80808080u) & ~x;
+        else if (MODE == 1) m = (g & l & 0x80808080u) & x;
+        else m = ((x & g) | (~x & l)) & 0x80808080u;
+        r = __funnelshift_l((m >> 7) * 0x10204080u, r, 4);
+    }
+    return r;
 }
 __device__ __forceinline__ uint32_t range_i32_chunk(const uint4& v, uint32_t lo, uint32_t span) {
     return (uint32_t)((v.x - lo) <= span) | ((uint32_t)((v.y - lo) <= span) << 1) | ((uint32_t)((v.z - lo) <= span) << 2) |
            ((uint32_t)((v.w - lo) <= span) << 3);
 }
-// Two 2-byte cells per word; a halfword of t is zero iff bit 15/31 of the result is set.
-__device__ __forceinline__ uint32_t zero_halfwords(uint32_t t) {
-    return ~(((t & 0x7FFF7FFFu) + 0x7FFF7FFFu) | t) & 0x80008000u;
+// Outer perfect shuffle: bit i of the low half goes to bit 2i, bit i of the high half to bit 2i+1.
+__device__ __forceinline__ uint32_t zip16(uint32_t x) {
+    uint32_t t;
+    t = (x ^ (x >> 8)) & 0x0000FF00u; x ^= t ^ (t << 8);
+    t = (x ^ (x >> 4)) & 0x00F000F0u; x ^= t ^ (t << 4);
+    t = (x ^ (x >> 2)) & 0x0C0C0C0Cu; x ^= t ^ (t << 2);
+    t = (x ^ (x >> 1)) & 0x22222222u; x ^= t ^ (t << 1);
+    return x;
+}
+
+template <bool STAGED>
+__device__ __forceinline__ uint4 ld16(uint32_t saddr, const uint8_t* gaddr) {
+    if constexpr (STAGED) return lds128(saddr);
+    else return ldg128(gaddr);
+}
+
+// Selection word of the lane for one filter column: its 32 consecutive rows start at shared address `cell_s`
+// (staged tile) or global address `cell_g` (direct loads).  Out of line, everything passed by value: one copy
+// of every predicate loop per kernel, and its registers are not the caller's problem.
+template <bool STAGED, int MODE>
+__device__ __forceinline__ uint32_t eval_i8(uint32_t cell_s, const uint8_t* cell_g, int lane, int lo, int hi) {
+    const int t1 = MODE == 0 ? lo : lo + 128;
+    const int t2 = MODE == 1 ? hi + 128 : hi;
+    const uint32_t c1 = (uint32_t)(128 - t1) * 0x01010101u;
+    const uint32_t c2 = (uint32_t)(128 + t2) * 0x01010101u;
+    uint32_t mask = 0;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        const int q = (c + lane) & 1;  // rotate so the 8 lanes of a quarter-warp hit distinct banks
+        const uint4 v = ld16<STAGED>(cell_s + 16u * q, cell_g + 16 * q);
+        mask |= i8_range16<MODE>(v, c1, c2) << (16 * q);
+    }
+    return mask;
+}
+
+template <bool STAGED>
+__device__ __noinline__ uint32_t eval_filter_span(uint32_t cell_s, const uint8_t* cell_g, int kind, int width, int lo, uint32_t span,
+                                                  int nlit, const uint8_t* lits, int lane) {
+    if (kind == kFilterI8Range) {
+        const int hi = lo + (int)span;
+        if (lo >= 0) return eval_i8<STAGED, 0>(cell_s, cell_g, lane, lo, hi);
+        if (hi < 0) return eval_i8<STAGED, 1>(cell_s, cell_g, lane, lo, hi);
+        return eval_i8<STAGED, 2>(cell_s, cell_g, lane, lo, hi);
+    }
+    if (kind == kFilterI32Range) {
+        uint32_t mask = 0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int q = (c + lane) & 7;
+            const uint4 v = ld16<STAGED>(cell_s + 16u * q, cell_g + 16 * q);
+            mask |= range_i32_chunk(v, (uint32_t)lo, span) << (4 * q);
+        }
+        return mask;
+    }
+    if (width == 2) {
+        // Two 2-byte cells per word: min(cell ^ literal, 1) is the cell's MISMATCH flag (bits 0 and 16).  The
+        // flags of the 16 words of a lane are accumulated as  even rows -> bits 0..15, odd rows -> bits
+        // 16..31  and interleaved once at the end.
+        uint32_t miss_all = 0xFFFFFFFFu;
+        for (int l = 0; l < nlit; l++) {
+            const uint32_t ll = ((uint32_t)lits[2 * l] | ((uint32_t)lits[2 * l + 1] << 8)) * 0x00010001u;
+            uint32_t miss = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int q = (c + lane) & 3;
+                const uint4 v = ld16<STAGED>(cell_s + 16u * q, cell_g + 16 * q);
+                const uint32_t a = __vminu2(v.x ^ ll, 0x00010001u) + (__vminu2(v.y ^ ll, 0x00010001u) << 1) +
+                                   (__vminu2(v.z ^ ll, 0x00010001u) << 2) + (__vminu2(v.w ^ ll, 0x00010001u) << 3);
+                miss += a << (4 * q);
+            }
+            miss_all &= miss;
+        }
+        return zip16(~miss_all);
+    }
+    // Generic k-byte cells: row-per-lane compare, ballot gives the bitmap word of rows 32j..32j+31, which lane
+    // j keeps.  (cell_s / cell_g are this lane's; the warp's span starts 32*lane rows earlier.)
+    const int k = width;
+    const uint32_t wbase_s = cell_s - (uint32_t)(lane * 32 * k);
+    const uint8_t* wbase_g = cell_g - lane * 32 * k;
+    uint32_t mask = 0;
+    for (int j = 0; j < 32; j++) {
+        const int r = j * 32 + lane;
+        bool hit = false;
+        for (int l = 0; l < nlit && !hit; l++) {
+            bool eq = true;
+            for (int b = 0; b < k; b++) {
+                const uint32_t cell = STAGED ? lds_u8(wbase_s + (uint32_t)(r * k + b)) : (uint32_t)__ldg(wbase_g + r * k + b);
+                eq = eq && (cell == (uint32_t)lits[l * k + b]);
+            }
+            hit = eq;
+        }
+        const uint32_t w = __ballot_sync(0xFFFFFFFFu, hit);
+        if (lane == j) mask = w;
+    }
+    return mask;
 }
 
 // Selection words of the lane for one filter column: word s covers the lane's 32 rows of the 1024-row
-// sub-span starting at tile-relative row `warp_row + s*1024`.  masks[s] is AND-ed in place.  One
-// out-of-line call per (tile, filter column) keeps the kernels small and amortises the setup.
-template <int W>
-__device__ __noinline__ void dense_eval_filter(const ScanPlan& P, const FilterCol& f, bool staged, uint32_t stage_addr,
-                                               long long tile_row0, int warp_row, int lane, uint32_t* masks) {
+// span starting at tile-relative row `warp_row + s*1024`.  masks[s] is AND-ed in place.  `lits` = the plan's
+// literal pool copied to shared memory.
+template <int W, bool STAGED>
+__device__ __forceinline__ void dense_eval_filter(const FilterCol& f, const uint8_t* lits, uint32_t stage_addr, long long tile_row0,
+                                                  int warp_row, int lane, uint32_t* masks) {
     const uint32_t col_s = stage_addr + (uint32_t)f.smem_off;
     const uint8_t* col_g = f.base + tile_row0 * f.width;
-    if (f.kind == kFilterI8Range) {
-        const uint32_t lo_b = ((uint32_t)f.lo ^ 0x80u) & 0xFFu;
-        const uint32_t hi_b = lo_b + f.span;
-        const uint32_t c1 = (0x100u - lo_b) * 0x00010001u;
-        const uint32_t c2 = (0x100u | hi_b) * 0x00010001u;
 #pragma unroll
-        for (int s = 0; s < W; s++) {
-            const uint32_t off = (uint32_t)(warp_row + s * 1024 + lane * 32);
-            uint32_t mask = 0;
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                const int q = (c + lane) & 1;  // rotate so the 8 lanes of a quarter-warp hit distinct banks
-                const uint4 v = staged ? lds128(col_s + off + 16u * q) : ldg128(col_g + off + 16 * q);
-                mask |= swar_i8_chunk(v, c1, c2) << (16 * q);
-            }
-            masks[s] &= mask;
-        }
-    } else if (f.kind == kFilterI32Range) {
-        const uint32_t lo = (uint32_t)f.lo, span = f.span;
-#pragma unroll
-        for (int s = 0; s < W; s++) {
-            const uint32_t off = (uint32_t)(warp_row + s * 1024 + lane * 32) * 4u;
-            uint32_t mask = 0;
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const int q = (c + lane) & 7;
-                const uint4 v = staged ? lds128(col_s + off + 16u * q) : ldg128(col_g + off + 16 * q);
-                mask |= range_i32_chunk(v, lo, span) << (4 * q);
-            }
-            masks[s] &= mask;
-        }
-    } else if (f.width == 2) {
-#pragma unroll
-        for (int s = 0; s < W; s++) {
-            const uint32_t off = (uint32_t)(warp_row + s * 1024 + lane * 32) * 2u;
-            uint32_t mask = 0;
-            for (int l = 0; l < f.nlit; l++) {
-                const uint32_t lit = (uint32_t)P.lits[f.lit_off + 2 * l] | ((uint32_t)P.lits[f.lit_off + 2 * l + 1] << 8);
-                const uint32_t ll = lit * 0x00010001u;
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const int q = (c + lane) & 3;
-                    const uint4 v = staged ? lds128(col_s + off + 16u * q) : ldg128(col_g + off + 16 * q);
-                    const uint32_t h0 = zero_halfwords(v.x ^ ll), h1 = zero_halfwords(v.y ^ ll);
-                    const uint32_t h2 = zero_halfwords(v.z ^ ll), h3 = zero_halfwords(v.w ^ ll);
-                    // bits 15/31 of h* -> two row bits each
-                    const uint32_t b01 = (h0 >> 15) | (h1 >> 13), b23 = (h2 >> 11) | (h3 >> 9);
-                    const uint32_t lo4 = (b01 & 0x5u) | ((b01 >> 15) & 0xAu);
-                    const uint32_t hi4 = ((b23 >> 4) & 0x5u) | ((b23 >> 19) & 0xAu);
-                    mask |= (lo4 | (hi4 << 4)) << (8 * q);
-                }
-            }
-            masks[s] &= mask;
-        }
-    } else {
-        // Generic k-byte cells: row-per-lane compare, ballot gives the bitmap word of rows 32j..32j+31,
-        // which lane j keeps.
-        const int k = f.width;
-        for (int s = 0; s < W; s++) {
-            const uint32_t wbase_s = col_s + (uint32_t)((warp_row + s * 1024) * k);
-            const uint8_t* wbase_g = col_g + (long long)(warp_row + s * 1024) * k;
-            uint32_t mask = 0;
-            for (int j = 0; j < 32; j++) {
-                const int r = j * 32 + lane;
-                bool hit = false;
-                for (int l = 0; l < f.nlit && !hit; l++) {
-                    bool eq = true;
-                    for (int b = 0; b < k; b++) {
-                        const uint32_t cell = staged ? lds_u8(wbase_s + (uint32_t)(r * k + b)) : (uint32_t)__ldg(wbase_g + r * k + b);
-                        eq = eq && (cell == (uint32_t)P.lits[f.lit_off + l * k + b]);
-                    }
-                    hit = eq;
-                }
-                const uint32_t w = __ballot_sync(0xFFFFFFFFu, hit);
-                if (lane == j) mask = w;
-            }
-            masks[s] &= mask;
-        }
+    for (int s = 0; s < W; s++) {
+        const int off = (warp_row + s * 1024 + lane * 32) * f.width;
+        masks[s] &= eval_filter_span<STAGED>(col_s + (uint32_t)off, col_g + off, f.kind, f.width, f.lo, f.span, f.nlit, lits + f.lit_off, lane);
     }
 }
 
@@ -392,19 +436,17 @@ template <> __device__ __forceinline__ unsigned long long lds_cell<unsigned long
     return v;
 }
 
-// Cooperative emission of one 1024-row word-span by one warp: entry i of the warp-private selection
-// list (row index inside the span) goes to out[g0 + i].  Lanes take consecutive entries, so stores are
+// Cooperative emission of one 1024-row span by one warp: entry i of the warp-private selection
+// vector (row index inside the span) goes to out[g0 + i].  Lanes take consecutive entries, so stores are
 // coalesced and every lane carries four independent gathers.
 template <typename T, bool FROM_SMEM>
 __device__ __forceinline__ void emit_span(const unsigned short* sel_w, int n, int lane, uint32_t sbase, const T* __restrict__ gbase,
-                                          T* __restrict__ out, long long g0, long long limit) {
-    const long long room = limit - g0;
-    if (room <= 0) return;
-    if (room < (long long)n) n = (int)room;
-    for (int i0 = 0; i0 < n; i0 += 128) {
-        T v[4];
+                                          T* __restrict__ out) {
+    constexpr int U = FROM_SMEM ? 4 : 8;  // independent gathers per lane
+    for (int i0 = 0; i0 < n; i0 += 32 * U) {
+        T v[U];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < U; k++) {
             const int i = i0 + k * 32 + lane;
             if (i < n) {
                 const uint32_t r = sel_w[i];
@@ -412,235 +454,451 @@ __device__ __forceinline__ void emit_span(const unsigned short* sel_w, int n, in
             }
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < U; k++) {
             const int i = i0 + k * 32 + lane;
-            if (i < n) out[g0 + i] = v[k];
+            if (i < n) out[i] = v[k];
         }
     }
 }
 // Any other cell width: byte-wise.
 __device__ __forceinline__ void emit_span_bytes(const unsigned short* sel_w, int n, int lane, bool from_smem, uint32_t sbase,
-                                                const uint8_t* __restrict__ gbase, uint8_t* __restrict__ out, int w, long long g0,
-                                                long long limit) {
-    const long long room = limit - g0;
-    if (room <= 0) return;
-    if (room < (long long)n) n = (int)room;
+                                                const uint8_t* __restrict__ gbase, uint8_t* __restrict__ out, int w) {
     for (int i = lane; i < n; i += 32) {
         const uint32_t r = sel_w[i];
         for (int b = 0; b < w; b++)
-            out[(g0 + i) * w + b] = (uint8_t)(from_smem ? lds_u8(sbase + r * (uint32_t)w + b) : (uint32_t)__ldg(gbase + (long long)r * w + b));
+            out[(long long)i * w + b] = (uint8_t)(from_smem ? lds_u8(sbase + r * (uint32_t)w + b) : (uint32_t)__ldg(gbase + (long long)r * w + b));
     }
 }
 
-// All projected columns of one span (kept out of line: the kernel body stays small and lean on registers).
-__device__ __noinline__ void emit_span_all(const ScanPlan& P, const unsigned short* sel_w, int n, int lane, bool staged,
-                                           uint32_t stage_addr, int span_row, long long tile_row0, long long g0) {
-    for (int pc = 0; pc < P.nproj; pc++) {
-        const ProjCol& pj = P.proj[pc];
+// One projected column of a selection vector: n selected rows (already clamped to the LIMIT), entry i goes to
+// out[i].  Out of line (one copy of the width dispatch per kernel) with everything passed in registers: the
+// plan lives in the kernel's parameter bank and must not be dereferenced through a pointer here.
+__device__ __noinline__ void emit_col(const unsigned short* sel_w, int n, int lane, int w, bool from_smem, uint32_t sbase,
+                                      const uint8_t* __restrict__ gbase, uint8_t* __restrict__ out) {
+    if (w == 4) {
+        if (from_smem) emit_span<uint32_t, true>(sel_w, n, lane, sbase, nullptr, (uint32_t*)out);
+        else emit_span<uint32_t, false>(sel_w, n, lane, 0u, (const uint32_t*)gbase, (uint32_t*)out);
+    } else if (w == 1) {
+        if (from_smem) emit_span<uint8_t, true>(sel_w, n, lane, sbase, nullptr, out);
+        else emit_span<uint8_t, false>(sel_w, n, lane, 0u, gbase, out);
+    } else if (w == 2) {
+        if (from_smem) emit_span<uint16_t, true>(sel_w, n, lane, sbase, nullptr, (uint16_t*)out);
+        else emit_span<uint16_t, false>(sel_w, n, lane, 0u, (const uint16_t*)gbase, (uint16_t*)out);
+    } else if (w == 8) {
+        if (from_smem) emit_span<unsigned long long, true>(sel_w, n, lane, sbase, nullptr, (unsigned long long*)out);
+        else emit_span<unsigned long long, false>(sel_w, n, lane, 0u, (const unsigned long long*)gbase, (unsigned long long*)out);
+    } else {
+        emit_span_bytes(sel_w, n, lane, from_smem, sbase, gbase, out, w);
+    }
+}
+
+// All projected columns of a selection vector whose rows are relative to tile row `span_row`; the first entry
+// goes to result ordinal g0.
+// (`proj` / `filter` = the plan's tables copied to shared memory: indexing the kernel's parameter bank with a
+// loop variable would make the compiler unroll or spill the whole plan.)
+__device__ __forceinline__ void emit_span_all(const ProjCol* proj, int nproj, const FilterCol* filter, const unsigned short* sel_w, int n,
+                                              int lane, bool staged, uint32_t stage_addr, int span_row, long long tile_row0, long long g0) {
+#pragma unroll 1
+    for (int pc = 0; pc < nproj; pc++) {
+        const ProjCol& pj = proj[pc];
         const int w = pj.width;
         const bool from_smem = staged && pj.filter_idx >= 0;
-        const uint32_t sbase = stage_addr + (from_smem ? (uint32_t)P.filter[pj.filter_idx].smem_off : 0u) + (uint32_t)(span_row * w);
-        const uint8_t* gbase = pj.base + (tile_row0 + span_row) * w;
-        if (w == 4) {
-            if (from_smem) emit_span<uint32_t, true>(sel_w, n, lane, sbase, nullptr, (uint32_t*)pj.out, g0, P.limit);
-            else emit_span<uint32_t, false>(sel_w, n, lane, 0u, (const uint32_t*)gbase, (uint32_t*)pj.out, g0, P.limit);
-        } else if (w == 1) {
-            if (from_smem) emit_span<uint8_t, true>(sel_w, n, lane, sbase, nullptr, pj.out, g0, P.limit);
-            else emit_span<uint8_t, false>(sel_w, n, lane, 0u, gbase, pj.out, g0, P.limit);
-        } else if (w == 2) {
-            if (from_smem) emit_span<uint16_t, true>(sel_w, n, lane, sbase, nullptr, (uint16_t*)pj.out, g0, P.limit);
-            else emit_span<uint16_t, false>(sel_w, n, lane, 0u, (const uint16_t*)gbase, (uint16_t*)pj.out, g0, P.limit);
-        } else if (w == 8) {
-            if (from_smem) emit_span<unsigned long long, true>(sel_w, n, lane, sbase, nullptr, (unsigned long long*)pj.out, g0, P.limit);
-            else emit_span<unsigned long long, false>(sel_w, n, lane, 0u, (const unsigned long long*)gbase, (unsigned long long*)pj.out, g0, P.limit);
-        } else {
-            emit_span_bytes(sel_w, n, lane, from_smem, sbase, gbase, pj.out, w, g0, P.limit);
-        }
+        const uint32_t sbase = stage_addr + (from_smem ? (uint32_t)filter[pj.filter_idx].smem_off : 0u) + (uint32_t)(span_row * w);
+        emit_col(sel_w, n, lane, w, from_smem, sbase, pj.base + (tile_row0 + span_row) * w, pj.out + g0 * w);
+    }
+}
+
+// A span whose 1024 rows all survive: straight coalesced copy of n <= 1024 rows, no selection vector.
+__device__ __noinline__ void copy_rows(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int bytes, int lane) {
+    if ((((uintptr_t)src | (uintptr_t)dst | (uintptr_t)bytes) & 3u) == 0) {
+        const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src);
+        uint32_t* d4 = reinterpret_cast<uint32_t*>(dst);
+        for (int i = lane; i < bytes / 4; i += 32) d4[i] = __ldg(s4 + i);
+    } else {
+        for (int i = lane; i < bytes; i += 32) dst[i] = __ldg(src + i);
+    }
+}
+__device__ __forceinline__ void emit_span_full(const ProjCol* proj, int nproj, int lane, long long row0, long long g0, int n) {
+#pragma unroll 1
+    for (int pc = 0; pc < nproj; pc++) {
+        const ProjCol& pj = proj[pc];
+        const int w = pj.width;
+        copy_rows(pj.base + row0 * w, pj.out + g0 * w, n * w, lane);
+    }
+}
+
+// Bitmap word of the lane -> entries appended to the warp's selection vector (ascending row order): the
+// rows of word `mm` are row_base + 32*lane + bit.
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ void append_selection(uint32_t mm, int lane, unsigned short* sel_at, unsigned row_base) {
+    const unsigned cnt = (unsigned)__popc(mm);
+    unsigned incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += nb;
+    }
+    uint32_t addr = smem_u32(sel_at) + 2u * (incl - cnt);
+    const uint32_t base = row_base + (unsigned)lane * 32u;
+    uint32_t rm = __brev(mm);  // leading zeros of rm = index of the lowest set bit of mm
+    while (rm) {
+        const int b = __clz((int)rm);
+        sts_u16(addr, base + (uint32_t)b);
+        addr += 2u;
+        rm &= ~(0x80000000u >> b);
     }
 }
 
 extern __shared__ __align__(128) uint8_t dyn_smem[];
 
-template <int W>
+// The plan's per-column tables -> shared memory.  Every access to P uses a compile-time index (fully unrolled
+// selects), so the parameter bank is never indexed dynamically.
+__device__ __forceinline__ void copy_plan_tables(const ScanPlan& P, FilterCol* filter, ProjCol* proj, int tid, int nthreads) {
+    (void)nthreads;
+    if (tid < kMaxFilterCols) {
+#pragma unroll
+        for (int i = 0; i < kMaxFilterCols; i++)
+            if (tid == i) filter[i] = P.filter[i];
+    } else if (tid >= 32 && tid < 32 + kMaxProjCols) {
+#pragma unroll
+        for (int i = 0; i < kMaxProjCols; i++)
+            if (tid - 32 == i) proj[i] = P.proj[i];
+    }
+}
+
+// ---- the scanner: one warp of the whole grid turns tile counts into exclusive offsets ----------
+// Workers publish agg[tile] = count as soon as a tile is filtered; the scanner walks the tiles in order,
+// 32*K status words per round (K consecutive tiles per lane, warp scan of the lane sums), and writes
+// pre[tile] = rows selected in all earlier tiles.  A worker therefore waits one hand-off (its own word),
+// however many tiles are in flight - a chained look-back would have every tile of a generation wait for
+// the prefix to ripple through all of them.  The scanner also owns the LIMIT cut (`done`, Project.scala:73-77)
+// and the total.
+constexpr int kScanK = 8;  // tiles per lane per round: one 64-byte aligned group, four 128-bit loads
+
+__device__ __forceinline__ void trace_stamp(const ScanPlan& P, long long tile, int ev) {
+    if (P.trace) P.trace[tile * 8 + ev] = globaltimer_ns();
+}
+__device__ __forceinline__ void ld_relaxed_v2u64(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_v2u64(unsigned long long* p, unsigned long long a, unsigned long long b) {
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+
+// The status arrays are padded to a whole round, so the scanner needs no bounds checks: words past the
+// last tile are never published and are treated as empty tiles.  Loads are 64-byte aligned groups (four
+// 128-bit loads per lane, all issued before the first use); progress is per TILE - a CTA may hold two
+// tiles of one group (one in work, one prefetched), so waiting for whole groups could deadlock.
+__device__ __noinline__ void scanner_loop(const ScanPlan& P, ScanCtrl* ctrl, const unsigned long long* agg, unsigned long long* pre,
+                                          int lane) {
+    const unsigned ep = P.epoch & 0x3FFFFFu;
+    const unsigned long long want = ((unsigned long long)ep << 2) | kStateAggregate;
+    const long long ntiles = P.ntiles;
+    long long pos = 0;  // first tile without an offset yet
+    unsigned long long running = 0;  // rows selected in tiles [0, pos)
+    uint64_t t0 = 0;
+    unsigned spins = 0;
+    while (pos < ntiles) {
+        const long long idx0 = (pos & ~(long long)(kScanK - 1)) + lane * kScanK;
+        unsigned long long st[kScanK];
+#pragma unroll
+        for (int k = 0; k < kScanK; k += 2) ld_relaxed_v2u64(agg + idx0 + k, st[k], st[k + 1]);
+        // leading entries of the lane that are settled: already scanned (< pos), published, or past the end
+        unsigned open = 1, lane_valid = 0, lane_sum = 0;
+        unsigned cnt[kScanK];
+#pragma unroll
+        for (int k = 0; k < kScanK; k++) {
+            const long long idx = idx0 + k;
+            const bool counted = idx >= pos && idx < ntiles;
+            open &= (!counted || (st[k] & 0xFFFFFFull) == want) ? 1u : 0u;
+            cnt[k] = (counted && open) ? (unsigned)(st[k] >> 24) : 0u;
+            lane_valid += open;
+            lane_sum += cnt[k];
+        }
+        const unsigned full = __ballot_sync(0xFFFFFFFFu, lane_valid == (unsigned)kScanK);
+        const int fl = full == 0xFFFFFFFFu ? 32 : __ffs((int)~full) - 1;  // first lane with an unpublished tile
+        const long long new_pos = fl == 32 ? idx0 - lane * kScanK + 32 * kScanK
+                                           : idx0 - lane * kScanK + fl * kScanK + (long long)__shfl_sync(0xFFFFFFFFu, lane_valid, fl & 31);
+        if (new_pos <= pos) {
+            if (spins == 0) t0 = globaltimer_ns();
+            if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > kWatchdogNs) watchdog_trap(ctrl, 2);
+            __nanosleep(20);
+            continue;
+        }
+        spins = 0;
+        if (lane > fl) lane_sum = 0;  // (lane fl: cnt[] is already zero from its first unpublished tile on)
+        unsigned incl = lane_sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        if (lane <= fl) {
+            unsigned long long base = running + (incl - lane_sum);
+#pragma unroll
+            for (int k = 0; k < kScanK; k++) {
+                const long long idx = idx0 + k;
+                if (idx >= pos && idx < new_pos && idx < ntiles) {
+                    st_relaxed_u64(pre + idx, pack_status(ep, kStatePrefix, base));
+                    trace_stamp(P, idx, 5);
+                }
+                base += cnt[k];
+            }
+        }
+        running += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        pos = new_pos;
+        if (running >= (unsigned long long)P.limit) break;  // every tile up to the LIMIT cut has its offset
+    }
+    if (lane == 0) {
+        const bool cut = running >= (unsigned long long)P.limit;
+        ctrl->total = cut ? (unsigned long long)P.limit : running;
+        __threadfence();
+        if (cut) atomicExch(&ctrl->done, 1u);  // after the offsets: a worker that sees `done` and no offset is beyond the cut
+    }
+}
+
+// Exclusive offset of `tile` (one thread).  -1 = the LIMIT was reached before this tile.
+__device__ __forceinline__ long long wait_prefix(const unsigned long long* pre, unsigned tile, uint32_t epoch, ScanCtrl* ctrl) {
+    const unsigned ep = epoch & 0x3FFFFFu;
+    uint64_t t0 = 0;
+    unsigned spins = 0;
+    for (;;) {
+        const unsigned long long s = ld_relaxed_u64(pre + tile);
+        const unsigned d = ld_relaxed_u32(&ctrl->done);
+        if ((((s >> 2) & 0x3FFFFFu) == ep) && ((unsigned)(s & 3u) == kStatePrefix)) return (long long)(s >> 24);
+        if (d) {
+            __threadfence();
+            const unsigned long long s2 = ld_relaxed_u64(pre + tile);
+            if ((((s2 >> 2) & 0x3FFFFFu) == ep) && ((unsigned)(s2 & 3u) == kStatePrefix)) return (long long)(s2 >> 24);
+            return -1;
+        }
+        if (spins == 0) t0 = globaltimer_ns();
+        if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > kWatchdogNs) watchdog_trap(ctrl, 3);
+        __nanosleep(32);
+    }
+}
+
+template <bool STAGED>
 __global__ void __launch_bounds__(kDenseThreads, IMM3_DENSE_MIN_BLOCKS) scan_dense_kernel(const __grid_constant__ ScanPlan P, ScanCtrl* ctrl,
-                                                                     unsigned long long* status) {
-    constexpr int kTile = kDenseTileRowsPerWord * W;  // rows per tile
-    constexpr int kWarpSpan = 1024 * W;               // rows per compute warp
+                                                                                             unsigned long long* status) {
+    constexpr int kSub = kDenseTileRowsPerWord;  // rows per sub-tile (one ring slot): 8 warps x 32 lanes x 32 rows
     __shared__ DenseShared S;
-    // dynamic shared memory: [8 warp-private selection lists of 1024 uint16][TMA ring]
-    const uint32_t ring_addr = smem_u32(dyn_smem) + kComputeWarps * 1024 * 2;
+    // dynamic shared memory: [8 selection vectors of 1024 uint16][2 x NS x 256 bitmap words]
+    //                        [8 warp-private spans of the projected columns][TMA ring of filter-column sub-tiles]
+    const int NS = P.subtiles;          // sub-tiles per tile
+    const int tile_rows = NS * kSub;    // rows per tile
+    unsigned short* const sel_all = reinterpret_cast<unsigned short*>(dyn_smem);
+    uint32_t* const bm_all = reinterpret_cast<uint32_t*>(dyn_smem + kComputeWarps * 1024 * 2);
+    const uint32_t pstage_addr = smem_u32(dyn_smem) + kComputeWarps * 1024 * 2 + 2u * (uint32_t)NS * 256u * 4u;  // 8 x proj_stage_bytes
+    const uint32_t ring_addr = pstage_addr + (uint32_t)kComputeWarps * (uint32_t)P.proj_stage_bytes;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool is_ctrl = warp == kComputeWarps;
-    const bool staged = P.stages > 0;
-    const int ring = staged ? P.stages : 3;
+    const int ring = STAGED ? P.stages : 2;
     const unsigned ntiles = (unsigned)P.ntiles;
+    const unsigned long long* agg = status;
+    unsigned long long* pre = status + status_round_up(P.ntiles);
+    const bool want_offsets = !P.bitmap && P.nproj > 0;
 
+    for (int i = tid; i < kLitPoolBytes; i += kDenseThreads) S.lits[i] = P.lits[i];
+    copy_plan_tables(P, S.filter, S.proj, tid, kDenseThreads);
     if (tid == 0) {
-        for (int s = 0; s < kMaxStages; s++) mbar_init(smem_u32(&S.mbar_full[s]), 1);
-        for (int e = 0; e < 2; e++) {
-            mbar_init(smem_u32(&S.mbar_count[e]), 1);
-            mbar_init(smem_u32(&S.mbar_excl[e]), 1);
+        for (int s = 0; s < kMaxStages; s++) {
+            mbar_init(smem_u32(&S.mbar_full[s]), 1);
+            mbar_init(smem_u32(&S.mbar_empty[s]), kComputeWarps);
         }
+        for (int w = 0; w < kComputeWarps; w++) mbar_init(smem_u32(&S.mbar_warp[w]), 1);
         fence_mbar_init();
+        // Scanner election: the first CTA to get here.  On a full-size grid the scanner gets its SM to itself
+        // (its own compute warps and the other CTAs of that SM retire at once): every tile of the grid waits
+        // on this one warp, so it must not queue for issue slots behind two dozen ALU-bound warps.
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const unsigned old = atomicCAS(&ctrl->scanner, 0u, smid + 1u);
+        const bool dedicate = gridDim.x >= 64u;
+        S.role = old == 0u ? (dedicate ? kRoleScannerOnly : kRoleScannerAndWorker) : ((dedicate && old == smid + 1u) ? kRoleIdle : kRoleWorker);
     }
     __syncthreads();
+    const unsigned role = S.role;
 
-    if (is_ctrl) {
-        // ---------------- control warp: counts in, exclusive offsets out ----------------
-        for (unsigned j = 0;; j++) {
-            const int e = (int)(j & 1u);
-            mbar_wait(smem_u32(&S.mbar_count[e]), (j >> 1) & 1u, ctrl);
-            const unsigned cnt = S.tile_count[e];
-            if (cnt == kNoMoreTiles) break;
-            const long long excl = resolve_tile(P, ctrl, status, S.tile_id[e], cnt, lane);
-            if (lane == 0) {
-                S.tile_excl[e] = excl;
-                mbar_arrive(smem_u32(&S.mbar_excl[e]));
+    if (role == kRoleIdle || (role == kRoleScannerOnly && warp != kComputeWarps + 1)) {
+        // nothing to do: leave the SM to the scanner warp
+    } else if (warp == kComputeWarps) {
+        // ---------------- producer: tickets + TMA, `ring` sub-tiles ahead of the compute warps ----------------
+        if (lane == 0) {
+            unsigned it = 0;
+            for (bool more = true; more;) {
+                unsigned t = kNoMoreTiles;
+                if (!ld_relaxed_u32(&ctrl->done)) t = atomicAdd(&ctrl->ticket, 1u);  // after LIMIT: stop drawing tiles
+                if (t < ntiles) trace_stamp(P, t, 0);
+                for (int sub = 0; sub < NS && more; sub++, it++) {
+                    const int slot = (int)(it % (unsigned)ring);
+                    const unsigned use = it / (unsigned)ring;
+                    if (use > 0) mbar_wait(smem_u32(&S.mbar_empty[slot]), (use - 1) & 1u, ctrl);
+                    S.tile[slot] = t;
+                    const uint32_t bar = smem_u32(&S.mbar_full[slot]);
+                    const long long row0 = (long long)t * tile_rows + (long long)sub * kSub;
+                    if (t >= ntiles) {
+                        mbar_arrive(bar);
+                        more = false;
+                    } else if (STAGED && row0 < P.nrows && !(P.debug & 4u)) {
+                        mbar_arrive_expect_tx(bar, (uint32_t)P.stage_bytes);
+#pragma unroll 1
+                        for (int i = 0; i < P.nfilter; i++) {
+                            const FilterCol& f = S.filter[i];
+                            const uint32_t bytes = (uint32_t)(kSub * f.width);
+                            tma_load_1d(ring_addr + (uint32_t)slot * (uint32_t)P.stage_bytes + (uint32_t)f.smem_off, f.base + row0 * f.width,
+                                        bytes, bar);
+                        }
+                    } else {
+                        mbar_arrive(bar);  // direct loads, or a sub-tile past the last row: nothing to stage
+                    }
+                }
             }
-            __syncwarp();
         }
+    } else if (warp == kComputeWarps + 1) {
+        // ---------------- scanner warp of the elected CTA: serves the whole grid ----------------
+        if (role == kRoleScannerOnly || role == kRoleScannerAndWorker) scanner_loop(P, ctrl, agg, pre, lane);
     } else {
         // ---------------- compute warps ----------------
-        // Hand out the next tile to ring slot `slot` and, if staging, start its bulk copies (thread 0).
-        auto refill = [&](int slot) {
-            unsigned t = kNoMoreTiles;
-            if (!ld_relaxed_u32(&ctrl->done)) t = atomicAdd(&ctrl->ticket, 1u);  // after LIMIT: stop drawing tiles
-            S.ticket[slot] = t;
-            S.issued[slot] = 0;
-            if (staged && t < ntiles) {
-                const uint32_t bar = smem_u32(&S.mbar_full[slot]);
-                mbar_arrive_expect_tx(bar, (uint32_t)P.stage_bytes);
-                for (int i = 0; i < P.nfilter; i++) {
-                    const FilterCol& f = P.filter[i];
-                    const uint32_t bytes = (uint32_t)(kTile * f.width);
-                    tma_load_1d(ring_addr + (uint32_t)slot * (uint32_t)P.stage_bytes + (uint32_t)f.smem_off,
-                                f.base + (long long)t * bytes, bytes, bar);
-                }
-                S.issued[slot] = 1;
-            }
-        };
-        if (tid == 0)
-            for (int s = 0; s < ring; s++) refill(s);
-        bar_sync(1, kComputeThreads);
-
-        // Per-lane state of the tile being filtered (cur) and of the tile waiting to be emitted (prev): the
-        // bitmap words and the tile-local rank of the warp's first selected row.  The in-warp ranks are
-        // recomputed at emit time (a 5-step shuffle scan) rather than carried in registers.
-        uint32_t m_cur[W], m_prev[W];
-        unsigned wbase_cur = 0, wbase_prev = 0;  // tile-local rank of the warp's first selected row
-        long long row0_cur = 0, row0_prev = 0;
-        int slot_cur = 0, slot_prev = 0;
-        int slotF = 0;
-        uint32_t parF = 0;
-        unsigned short* sel_w = reinterpret_cast<unsigned short*>(dyn_smem) + warp * 1024;
-
-        // F(j): returns false when the CTA has run out of tiles.
-        auto filter_tile = [&](unsigned j) -> bool {
+        unsigned short* sel_w = sel_all + warp * 1024;
+        unsigned it = 0;
+        uint32_t wparity = 0;  // phase of this warp's projected-span barrier
+        for (unsigned j = 0;; j++) {
             const int e = (int)(j & 1u);
-            const int slot = slotF;
-            const unsigned tile = S.ticket[slot];
-            if (tile >= ntiles) {
-                if (tid == 0) {
-                    S.tile_count[e] = kNoMoreTiles;
-                    mbar_arrive(smem_u32(&S.mbar_count[e]));
-                }
-                return false;
-            }
-            const long long tile_row0 = (long long)tile * kTile;
-            const uint32_t stage_addr = ring_addr + (uint32_t)slot * (uint32_t)P.stage_bytes;
-            if (S.issued[slot]) mbar_wait(smem_u32(&S.mbar_full[slot]), parF, ctrl);
-            if (++slotF == ring) { slotF = 0; parF ^= 1u; }
+            uint32_t* bm = bm_all + e * NS * 256;
+            unsigned tile = kNoMoreTiles;
 
-            // decode + conjunctive filter: W bitmap words per lane, then ranks
-            unsigned lane_total = 0;
-#pragma unroll
-            for (int s = 0; s < W; s++) {
-                const long long left = P.nrows - (tile_row0 + warp * kWarpSpan + s * 1024 + lane * 32);
-                m_cur[s] = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
+            // ---- phase 1: stream the tile's sub-tiles: decode + conjunctive filter -> bitmap words + span counts ----
+            for (int sub = 0; sub < NS; sub++, it++) {
+                const int slot = (int)(it % (unsigned)ring);
+                mbar_wait(smem_u32(&S.mbar_full[slot]), (it / (unsigned)ring) & 1u, ctrl);
+                tile = S.tile[slot];
+                if (tile >= ntiles) break;  // CTA-uniform; only ever at sub == 0
+                if (tid == 0 && sub == 0) trace_stamp(P, tile, 1);
+                const long long sub_row0 = (long long)tile * tile_rows + (long long)sub * kSub;
+                const uint32_t stage_addr = ring_addr + (uint32_t)slot * (uint32_t)P.stage_bytes;
+                const long long left = P.nrows - (sub_row0 + warp * 1024 + lane * 32);
+                uint32_t m = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
+                if (!(P.debug & 2u) && sub_row0 < P.nrows) {  // (a sub-tile past the last row has nothing staged)
+                    #pragma unroll 1
+                    for (int i = 0; i < P.nfilter; i++) dense_eval_filter<1, STAGED>(S.filter[i], S.lits, stage_addr, sub_row0, warp * 1024, lane, &m);
+                } else if (P.debug & 2u) {
+                    m = 0;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&S.mbar_empty[slot]));  // this warp is done with the slot's bytes
+                if (P.bitmap) P.bitmap[((sub_row0 + warp * 1024) >> 5) + lane] = m;
+                bm[(sub * kComputeWarps + warp) * 32 + lane] = m;  // span sub*8 + warp of the tile
+                const unsigned c = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(m));
+                if (lane == 0) S.span_cnt[e][sub * kComputeWarps + warp] = c;
             }
-            for (int i = 0; i < P.nfilter; i++) dense_eval_filter<W>(P, P.filter[i], staged, stage_addr, tile_row0, warp * kWarpSpan, lane, m_cur);
-#pragma unroll
-            for (int s = 0; s < W; s++) {
-                if (P.bitmap) P.bitmap[((tile_row0 + warp * kWarpSpan + s * 1024) >> 5) + lane] = m_cur[s];
-                lane_total += __popc(m_cur[s]);
-            }
-            const unsigned warp_total = __reduce_add_sync(0xFFFFFFFFu, lane_total);
-            if (lane == 0) S.warp_cnt[e][warp] = warp_total;
+            if (tile >= ntiles) break;
             bar_sync(1, kComputeThreads);
-            unsigned warp_base = 0, tile_count = 0;
-#pragma unroll
-            for (int w = 0; w < kComputeWarps; w++) {
-                const unsigned c = S.warp_cnt[e][w];
-                if (w < warp) warp_base += c;
-                tile_count += c;
-            }
-            if (tid == 0) {  // publish the count as early as possible: the control warp starts the look-back
-                S.tile_count[e] = tile_count;
-                S.tile_id[e] = tile;
-                mbar_arrive(smem_u32(&S.mbar_count[e]));
-            }
-            wbase_cur = warp_base;
-            row0_cur = tile_row0;
-            slot_cur = slot;
-            return true;
-        };
 
-        // E(j): emit the rows of the tile held in *_prev and recycle its ring slot.
-        auto emit_tile = [&](unsigned j) {
-            const int e = (int)(j & 1u);
-            mbar_wait(smem_u32(&S.mbar_excl[e]), (j >> 1) & 1u, ctrl);
-            const long long excl = S.tile_excl[e];
-            const uint32_t stage_addr = ring_addr + (uint32_t)slot_prev * (uint32_t)P.stage_bytes;
-            if (!P.bitmap && excl >= 0 && excl < P.limit) {
-                unsigned wrank = wbase_prev;
-#pragma unroll
-                for (int s = 0; s < W; s++) {
-                    uint32_t mm = m_prev[s];
-                    const unsigned cnt = (unsigned)__popc(mm);
-                    unsigned incl = cnt;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                        if (lane >= o) incl += nb;
-                    }
-                    const int n = (int)__shfl_sync(0xFFFFFFFFu, incl, 31);
-                    const long long g0 = excl + wrank;
-                    wrank += (unsigned)n;
-                    if (n == 0) continue;  // warp-uniform
-                    // warp-private selection list of this 1024-row span, from the register bitmap words
-                    {
-                        unsigned o = incl - cnt;
-                        const unsigned iters = __reduce_max_sync(0xFFFFFFFFu, cnt);
-                        for (unsigned it = 0; it < iters; it++) {
-                            if (mm) {
-                                sel_w[o++] = (unsigned short)(lane * 32 + __ffs(mm) - 1);
-                                mm &= mm - 1u;
+            // Warp w owns the tile's spans [w*NS, (w+1)*NS) = NS*1024 consecutive rows from here on.
+            const int nspans = NS * kComputeWarps;  // <= 64
+            const unsigned c0 = lane < nspans ? S.span_cnt[e][lane] : 0u;
+            const unsigned c1 = lane + 32 < nspans ? S.span_cnt[e][lane + 32] : 0u;
+            const int first = warp * NS;
+            const unsigned tile_count = __reduce_add_sync(0xFFFFFFFFu, c0 + c1);
+            const unsigned warp_base = __reduce_add_sync(0xFFFFFFFFu, (lane < first ? c0 : 0u) + (lane + 32 < first ? c1 : 0u));
+            const bool mine0 = lane >= first && lane < first + NS, mine1 = lane + 32 >= first && lane + 32 < first + NS;
+            const unsigned warp_total = __reduce_add_sync(0xFFFFFFFFu, (mine0 ? c0 : 0u) + (mine1 ? c1 : 0u));
+            const bool any_full = __any_sync(0xFFFFFFFFu, (mine0 && c0 == 1024u) || (mine1 && c1 == 1024u));
+            if (tid == 0) {
+                st_relaxed_u64(status + tile, pack_status(P.epoch, kStateAggregate, tile_count));
+                trace_stamp(P, tile, 2);
+            }
+            if (!want_offsets) continue;
+
+            // ---- phase 2: Project ----
+            // Sparse spans: their selected rows are appended to one selection vector and gathered straight from
+            // global memory.  Dense spans (>= stream_min_cnt rows of 1024): nearly every sector of the span would
+            // be touched anyway, so the span of every projected column is streamed into the warp's shared-memory
+            // buffer with TMA bulk copies (full DRAM pages, no per-row requests) and gathered from there.
+            const long long tile_row0 = (long long)tile * tile_rows;
+            const int warp_row = first * 1024;
+            const bool project = warp_total > 0;  // warp-uniform
+            const unsigned stream_min = P.proj_stage_bytes > 0 ? (unsigned)P.stream_min_cnt : 1024u;
+            const bool any_dense = __any_sync(0xFFFFFFFFu, (mine0 && c0 >= stream_min) || (mine1 && c1 >= stream_min));
+            const bool prebuilt = project && warp_total <= 1024u && !any_dense;  // one vector for the warp's rows, built while the
+            if (prebuilt) {                                                        // scanner resolves the tile's offset
+                unsigned fill = 0;
+                for (int s = 0; s < NS; s++) {
+                    const unsigned cnt = S.span_cnt[e][first + s];
+                    if (cnt) append_selection(bm[(first + s) * 32 + lane], lane, sel_w + fill, (unsigned)(s * 1024));
+                    fill += cnt;
+                }
+                __syncwarp();
+            }
+            if (tid == 0) {
+                S.excl[e] = (P.debug & 1u) ? (long long)tile * 1800 : wait_prefix(pre, tile, P.epoch, ctrl);
+                trace_stamp(P, tile, 3);
+            }
+            bar_sync(1, kComputeThreads);
+            const long long excl = S.excl[e];
+            if (project && excl >= 0 && excl + warp_base < P.limit) {
+                long long g0 = excl + warp_base;  // result ordinal of the first row of the vector
+                auto flush = [&](unsigned fill) {
+                    const long long room = P.limit - g0;
+                    if (fill && room > 0)
+                        emit_span_all(S.proj, P.nproj, S.filter, sel_w, room < (long long)fill ? (int)room : (int)fill, lane, false, 0u, warp_row, tile_row0, g0);
+                    g0 += fill;
+                };
+                if (prebuilt) {
+                    flush(warp_total);
+                } else {
+                    const uint32_t wbuf = pstage_addr + (uint32_t)warp * (uint32_t)P.proj_stage_bytes;
+                    const uint32_t wbar = smem_u32(&S.mbar_warp[warp]);
+                    unsigned fill = 0;
+                    for (int s = 0; s < NS; s++) {
+                        const unsigned cnt = S.span_cnt[e][first + s];
+                        if (cnt == 0) continue;  // warp-uniform
+                        const bool dense = cnt >= stream_min;
+                        if (dense || fill + cnt > 1024u) {
+                            __syncwarp();
+                            flush(fill);
+                            __syncwarp();  // the gathers are done with the vector
+                            fill = 0;
+                        }
+                        const long long room = P.limit - g0;
+                        if (room <= 0) break;
+                        const long long span_row0 = tile_row0 + warp_row + s * 1024;
+                        if (cnt == 1024u) {
+                            emit_span_full(S.proj, P.nproj, lane, span_row0, g0, room < 1024 ? (int)room : 1024);
+                            g0 += 1024;
+                        } else if (dense) {
+                            if (lane == 0) {
+                                mbar_arrive_expect_tx(wbar, (uint32_t)P.proj_stage_bytes);
+#pragma unroll 1
+                                for (int pc = 0; pc < P.nproj; pc++) {
+                                    const ProjCol& pj = S.proj[pc];
+                                    tma_load_1d(wbuf + (uint32_t)pj.stage_off, pj.base + span_row0 * pj.width, (uint32_t)(1024 * pj.width), wbar);
+                                }
                             }
+                            append_selection(bm[(first + s) * 32 + lane], lane, sel_w, 0u);
+                            __syncwarp();
+                            mbar_wait(wbar, wparity, ctrl);
+                            wparity ^= 1u;
+                            const int n = room < (long long)cnt ? (int)room : (int)cnt;
+#pragma unroll 1
+                            for (int pc = 0; pc < P.nproj; pc++) {
+                                const ProjCol& pj = S.proj[pc];
+                                emit_col(sel_w, n, lane, pj.width, true, wbuf + (uint32_t)pj.stage_off, nullptr, pj.out + g0 * pj.width);
+                            }
+                            g0 += cnt;
+                            __syncwarp();  // the gathers are done with the vector and with the buffer
+                        } else {
+                            append_selection(bm[(first + s) * 32 + lane], lane, sel_w + fill, (unsigned)(s * 1024));
+                            fill += cnt;
                         }
                     }
                     __syncwarp();
-                    const int span_row = warp * kWarpSpan + s * 1024;
-                    emit_span_all(P, sel_w, n, lane, staged, stage_addr, span_row, row0_prev, g0);
-                    __syncwarp();  // the list is rebuilt for the next span
+                    flush(fill);
                 }
             }
-            bar_sync(1, kComputeThreads);  // every warp is done with the slot's bytes
-            if (tid == 0) refill(slot_prev);
-        };
-
-        unsigned j = 0;
-        bool more = filter_tile(0);
-        while (more) {
-#pragma unroll
-            for (int s = 0; s < W; s++) m_prev[s] = m_cur[s];
-            wbase_prev = wbase_cur;
-            row0_prev = row0_cur;
-            slot_prev = slot_cur;
-            const bool next = filter_tile(j + 1);
-            emit_tile(j);
-            more = next;
-            j++;
+            __syncwarp();
+            if (tid == 0) trace_stamp(P, tile, 4);
         }
     }
     __syncthreads();
@@ -901,42 +1159,66 @@ __global__ void __launch_bounds__(kBlockThreads) scan_blocks_kernel(const __grid
 // =============================================================================================
 struct FilterShared {
     unsigned long long mbar_full[kMaxFilterStages];
-    unsigned int warp_cnt[2][kComputeWarps];
+    unsigned int span_c[2][4 * kComputeWarps];  // per-span match counts of the tile (W <= 4 spans per warp)
     unsigned long long scan_warp[kComputeWarps];
     unsigned int is_last;
+    uint8_t lits[kLitPoolBytes];  // MATCH literals of the plan
+    FilterCol filter[kMaxFilterCols];
+    ProjCol proj[kMaxProjCols];
 };
 
-// Exclusive scan of the tile counts by one CTA of kComputeThreads threads (each thread owns a contiguous
-// chunk: two passes over L2-resident counts, one block-wide scan), LIMIT clamp of the total.
+// Exclusive scan of the sub-tile counts by one CTA of kComputeThreads threads: 4096 counts per round, every thread
+// loads its 16 consecutive counts with four independent 128-bit loads (the arrays are padded to whole rounds),
+// one block-wide scan per round.  LIMIT clamp of the total.
 __device__ void scan_tile_counts(FilterShared& S, const uint32_t* tile_cnt, unsigned long long* tile_off, long long ntiles,
                                  long long limit, ScanCtrl* ctrl) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long chunk = (ntiles + kComputeThreads - 1) / kComputeThreads;
-    const long long i0 = (long long)tid * chunk, i1 = i0 + chunk < ntiles ? i0 + chunk : ntiles;
-    unsigned long long run = 0;
-    for (long long i = i0; i < i1; i++) run += __ldcg(tile_cnt + i);
-    unsigned long long incl = run;
+    unsigned long long running = 0;
+    for (long long base = 0; base < ntiles; base += kComputeThreads * 16) {
+        const long long i0 = base + tid * 16;
+        uint4 v[4];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= o) incl += nb;
+        for (int k = 0; k < 4; k++) v[k] = __ldcg(reinterpret_cast<const uint4*>(tile_cnt + i0) + k);
+        unsigned c[16] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w,
+                          v[2].x, v[2].y, v[2].z, v[2].w, v[3].x, v[3].y, v[3].z, v[3].w};
+        unsigned sum = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (i0 + k >= ntiles) c[k] = 0;  // padding holds stale counts
+            sum += c[k];
+        }
+        unsigned incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        __syncthreads();  // the previous round's readers are done with scan_warp
+        if (lane == 31) S.scan_warp[warp] = incl;
+        __syncthreads();
+        unsigned long long excl = running + (incl - sum), total = 0;
+#pragma unroll
+        for (int w = 0; w < kComputeWarps; w++) {
+            const unsigned long long ws = S.scan_warp[w];
+            if (w < warp) excl += ws;
+            total += ws;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+            if (i0 + k < ntiles) {  // (pairs: the arrays are padded, the entry after the last sub-tile is rewritten below)
+                ulonglong2 o;
+                o.x = excl;
+                o.y = excl + c[k];
+                *reinterpret_cast<ulonglong2*>(tile_off + i0 + k) = o;
+            }
+            excl += (unsigned long long)c[k] + c[k + 1];
+        }
+        running += total;
     }
-    if (lane == 31) S.scan_warp[warp] = incl;
     __syncthreads();
-    unsigned long long excl = incl - run, total = 0;
-#pragma unroll
-    for (int w = 0; w < kComputeWarps; w++) {
-        const unsigned long long ws = S.scan_warp[w];
-        if (w < warp) excl += ws;
-        total += ws;
-    }
-    for (long long i = i0; i < i1; i++) {
-        tile_off[i] = excl;
-        excl += __ldcg(tile_cnt + i);
-    }
     if (tid == 0) {
-        tile_off[ntiles] = total;
-        ctrl->total = total < (unsigned long long)limit ? total : (unsigned long long)limit;
+        tile_off[ntiles] = running;
+        ctrl->total = running < (unsigned long long)limit ? running : (unsigned long long)limit;
     }
 }
 
@@ -956,12 +1238,16 @@ __global__ void __launch_bounds__(kComputeThreads) filter_kernel(const __grid_co
     auto issue = [&](long long tile, int slot) {  // thread 0
         const uint32_t bar = smem_u32(&S.mbar_full[slot]);
         mbar_arrive_expect_tx(bar, (uint32_t)P.stage_bytes);
+#pragma unroll 1
         for (int i = 0; i < P.nfilter; i++) {
-            const FilterCol& f = P.filter[i];
+            const FilterCol& f = S.filter[i];
             const uint32_t bytes = (uint32_t)(kTile * f.width);
             tma_load_1d(ring_addr + (uint32_t)slot * (uint32_t)P.stage_bytes + (uint32_t)f.smem_off, f.base + tile * bytes, bytes, bar);
         }
     };
+    for (int i = tid; i < kLitPoolBytes; i += kComputeThreads) S.lits[i] = P.lits[i];
+    copy_plan_tables(P, S.filter, S.proj, tid, kComputeThreads);
+    __syncthreads();
     if (tid == 0) {
         for (int s = 0; s < kMaxFilterStages; s++) mbar_init(smem_u32(&S.mbar_full[s]), 1);
         fence_mbar_init();
@@ -986,24 +1272,30 @@ __global__ void __launch_bounds__(kComputeThreads) filter_kernel(const __grid_co
             const long long left = P.nrows - (tile_row0 + warp * kWarpSpan + s * 1024 + lane * 32);
             m[s] = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
         }
-        for (int i = 0; i < P.nfilter; i++) dense_eval_filter<W>(P, P.filter[i], staged, stage_addr, tile_row0, warp * kWarpSpan, lane, m);
-        unsigned warp_total = 0;
+        if (staged) {
+            for (int i = 0; i < P.nfilter; i++) dense_eval_filter<W, true>(S.filter[i], S.lits, stage_addr, tile_row0, warp * kWarpSpan, lane, m);
+        } else {
+            for (int i = 0; i < P.nfilter; i++) dense_eval_filter<W, false>(S.filter[i], S.lits, stage_addr, tile_row0, warp * kWarpSpan, lane, m);
+        }
+        const int e = (int)(it & 1u);
 #pragma unroll
         for (int s = 0; s < W; s++) {
             const long long span_row0 = tile_row0 + warp * kWarpSpan + s * 1024;
             bitmap[(span_row0 >> 5) + lane] = m[s];
             const unsigned c = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(m[s]));
-            if (lane == 0) span_cnt[span_row0 >> 10] = c;
-            warp_total += c;
+            if (lane == 0) {
+                span_cnt[span_row0 >> 10] = c;
+                S.span_c[e][warp * W + s] = c;
+            }
         }
-        const int e = (int)(it & 1u);
-        if (lane == 0) S.warp_cnt[e][warp] = warp_total;
         __syncthreads();  // every warp has consumed the slot's bytes
-        if (tid == 0) {
+        if (tid < W) {  // match count of every 8192-row sub-tile (8 consecutive spans): the unit of the offset scan
             unsigned c = 0;
 #pragma unroll
-            for (int w = 0; w < kComputeWarps; w++) c += S.warp_cnt[e][w];
-            tile_cnt[tile] = c;
+            for (int w = 0; w < kComputeWarps; w++) c += S.span_c[e][tid * kComputeWarps + w];
+            tile_cnt[tile * W + tid] = c;
+        }
+        if (tid == 0) {
             const long long next = tile + (long long)ring * gridDim.x;
             if (staged && next < ntiles) issue(next, slot);
         }
@@ -1021,27 +1313,7 @@ __global__ void __launch_bounds__(kComputeThreads) filter_kernel(const __grid_co
     __syncthreads();
     if (S.is_last) {
         __threadfence();
-        scan_tile_counts(S, tile_cnt, tile_off, ntiles, P.limit, ctrl);
-    }
-}
-
-// A span whose 1024 rows all survive: straight coalesced copy, no selection vector.
-__device__ __noinline__ void emit_span_full(const ScanPlan& P, int lane, long long row0, long long g0) {
-    long long n = P.limit - g0;
-    if (n <= 0) return;
-    if (n > 1024) n = 1024;
-    for (int pc = 0; pc < P.nproj; pc++) {
-        const ProjCol& pj = P.proj[pc];
-        const int w = pj.width;
-        if (w == 4) {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(pj.base) + row0;
-            uint32_t* dst = reinterpret_cast<uint32_t*>(pj.out) + g0;
-            for (int i = lane; i < n; i += 32) dst[i] = __ldg(src + i);
-        } else {
-            const uint8_t* src = pj.base + row0 * w;
-            uint8_t* dst = pj.out + g0 * w;
-            for (int i = lane; i < (int)n * w; i += 32) dst[i] = __ldg(src + i);
-        }
+        scan_tile_counts(S, tile_cnt, tile_off, ntiles * W, P.limit, ctrl);
     }
 }
 
@@ -1054,11 +1326,15 @@ __device__ __noinline__ void emit_span_full(const ScanPlan& P, int lane, long lo
 __global__ void __launch_bounds__(kComputeThreads, IMM3_EMIT_MIN_BLOCKS) emit_kernel(const __grid_constant__ ScanPlan P, const uint32_t* __restrict__ bitmap,
                                                                  const uint32_t* __restrict__ span_cnt,
                                                                  const unsigned long long* __restrict__ tile_off, int spans_per_tile,
-                                                                 long long nspans) {
+                                                                 long long nspans, int dense_off) {
+    __shared__ struct { FilterCol filter[kMaxFilterCols]; ProjCol proj[kMaxProjCols]; } SE;
+    copy_plan_tables(P, SE.filter, SE.proj, threadIdx.x, kComputeThreads);
+    __syncthreads();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned short* sel_w = reinterpret_cast<unsigned short*>(dyn_smem) + warp * 1024;
     const long long ntiles = (nspans + spans_per_tile - 1) / spans_per_tile;
     const unsigned long long total = __ldg(tile_off + ntiles);
+    if (dense_off && total * 32ull >= (unsigned long long)P.nrows) return;  // the streaming emit kernel takes dense results
     const long long warp0 = (long long)blockIdx.x * kComputeWarps + warp, nwarps = (long long)gridDim.x * kComputeWarps;
 
     if (total >= (unsigned long long)nspans * 32ull) {
@@ -1075,7 +1351,7 @@ __global__ void __launch_bounds__(kComputeThreads, IMM3_EMIT_MIN_BLOCKS) emit_ke
             const long long g0 = (long long)toff + __reduce_add_sync(0xFFFFFFFFu, lane < k ? c : 0u);
             if (g0 >= P.limit) continue;
             if (n == 1024) {
-                emit_span_full(P, lane, p * 1024, g0);
+                emit_span_full(SE.proj, P.nproj, lane, p * 1024, g0, (int)(P.limit - g0 < 1024 ? P.limit - g0 : 1024));
                 continue;
             }
             const unsigned cnt = (unsigned)__popc(mm);
@@ -1094,7 +1370,7 @@ __global__ void __launch_bounds__(kComputeThreads, IMM3_EMIT_MIN_BLOCKS) emit_ke
                 }
             }
             __syncwarp();
-            emit_span_all(P, sel_w, n, lane, false, 0u, 0, p * 1024, g0);
+            emit_span_all(SE.proj, P.nproj, nullptr, sel_w, (int)(P.limit - g0 < (long long)n ? P.limit - g0 : (long long)n), lane, false, 0u, 0, p * 1024, g0);
             __syncwarp();
         }
         return;
@@ -1125,13 +1401,13 @@ __global__ void __launch_bounds__(kComputeThreads, IMM3_EMIT_MIN_BLOCKS) emit_ke
             if (n == 0) continue;
             if (n == 1024 || fill + n > 1024) {  // flush what has been gathered so far
                 __syncwarp();
-                if (fill) emit_span_all(P, sel_w, fill, lane, false, 0u, 0, p0 * 1024, g0);
+                if (fill && g0 < P.limit) emit_span_all(SE.proj, P.nproj, nullptr, sel_w, (int)(P.limit - g0 < (long long)fill ? P.limit - g0 : (long long)fill), lane, false, 0u, 0, p0 * 1024, g0);
                 __syncwarp();
                 g0 += fill;
                 fill = 0;
             }
             if (n == 1024) {
-                emit_span_full(P, lane, (p0 + k) * 1024, g0);
+                if (g0 < P.limit) emit_span_full(SE.proj, P.nproj, lane, (p0 + k) * 1024, g0, (int)(P.limit - g0 < 1024 ? P.limit - g0 : 1024));
                 g0 += 1024;
                 continue;
             }
@@ -1154,8 +1430,189 @@ __global__ void __launch_bounds__(kComputeThreads, IMM3_EMIT_MIN_BLOCKS) emit_ke
             fill += n;
         }
         __syncwarp();
-        if (fill) emit_span_all(P, sel_w, fill, lane, false, 0u, 0, p0 * 1024, g0);
+        if (fill && g0 < P.limit) emit_span_all(SE.proj, P.nproj, nullptr, sel_w, (int)(P.limit - g0 < (long long)fill ? P.limit - g0 : (long long)fill), lane, false, 0u, 0, p0 * 1024, g0);
         __syncwarp();
+    }
+}
+
+// K3, dense results: a persistent TMA-ring kernel.  Tile = 8192 rows (8 spans, one per compute warp).  The producer
+// warp knows every tile's match count and offset before it starts (K1 finished), so it prefetches, `ring` tiles
+// ahead, exactly what the tile needs: its 256 bitmap words and 8 span counts, plus - for a tile with at least
+// one selected row in 32 - the tile of every projected column as TMA bulk copies (whole DRAM pages instead
+// of one request per selected row; at >= 3 % selectivity nearly every 128-byte line would be fetched anyway).
+// Sparse tiles gather their few rows straight from global memory.  Empty tiles cost one count load.
+// The compute warps never wait on a global load of their own for a dense tile and never talk to each other.
+// Straight copy of `nbytes` staged bytes (shared address sb, 4-byte aligned) to an arbitrarily aligned global address:
+// the body goes out as aligned 32-bit words, assembled from two shared words when source and destination disagree.
+__device__ __forceinline__ void copy_smem_to_global(uint32_t sb, uint8_t* dst, int nbytes, int lane) {
+    const int head = (int)((4u - ((unsigned)(uintptr_t)dst & 3u)) & 3u);  // bytes before the first aligned word of dst
+    if (lane < head && lane < nbytes) dst[lane] = (uint8_t)lds_u8(sb + (uint32_t)lane);
+    const int nwords = nbytes > head ? (nbytes - head) >> 2 : 0;
+    uint32_t* d4 = reinterpret_cast<uint32_t*>(dst + head);
+    const uint32_t sh = (uint32_t)head * 8u;
+    for (int i = lane; i < nwords; i += 32) {
+        const uint32_t a = sb + (uint32_t)i * 4u;  // source bytes [head + 4i, head + 4i + 4)
+        uint32_t v = lds_cell<uint32_t>(a);
+        if (head) v = __funnelshift_r(v, lds_cell<uint32_t>(a + 4u), sh);
+        d4[i] = v;
+    }
+    const int done = head + nwords * 4;
+    if (lane < nbytes - done) dst[done + lane] = (uint8_t)lds_u8(sb + (uint32_t)(done + lane));
+}
+
+constexpr int kMaxEmitStages = 4;
+constexpr int kEmitHdrBytes = 1024 + 128;  // bitmap words + span counts (padded)
+
+struct EmitShared {
+    unsigned long long mbar_full[kMaxEmitStages];
+    unsigned long long mbar_empty[kMaxEmitStages];
+    long long off[kMaxEmitStages];     // result ordinal of the tile's first selected row
+    unsigned int tile[kMaxEmitStages];
+    unsigned int mode[kMaxEmitStages];  // 0 = no more tiles, 1 = gather from global, 2 = projected columns staged
+    FilterCol filter[kMaxFilterCols];
+    ProjCol proj[kMaxProjCols];
+};
+
+__global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(const __grid_constant__ ScanPlan P, const uint32_t* __restrict__ bitmap,
+                                                                                const uint32_t* __restrict__ span_cnt,
+                                                                                const uint32_t* __restrict__ tile_cnt,
+                                                                                const unsigned long long* __restrict__ tile_off, long long nsub,
+                                                                                int ring, int stage_bytes, int dense_mode) {
+    __shared__ EmitShared S;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // One of the two emit kernels does the work, picked on the device from the match count (no host round trip).
+    const unsigned long long total = __ldcg(tile_off + nsub);
+    if (((total * 32ull >= (unsigned long long)P.nrows) ? 1 : 0) != dense_mode) return;
+
+    const uint32_t ring_addr = smem_u32(dyn_smem) + kComputeWarps * 1024 * 2;  // after the selection vectors
+    copy_plan_tables(P, S.filter, S.proj, tid, kComputeThreads + 32);
+    if (tid == 0) {
+        for (int s = 0; s < kMaxEmitStages; s++) {
+            mbar_init(smem_u32(&S.mbar_full[s]), 1);
+            mbar_init(smem_u32(&S.mbar_empty[s]), kComputeWarps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const bool can_stage = stage_bytes > kEmitHdrBytes;
+
+    if (warp == kComputeWarps) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            unsigned it = 0;
+            for (long long tile = blockIdx.x;; tile += gridDim.x) {
+                unsigned mode = 0, c = 0;
+                long long off = 0;
+                if (tile < nsub) {
+                    c = __ldcg(tile_cnt + tile);
+                    if (c == 0) continue;  // nothing selected: the compute warps never hear of this tile
+                    off = (long long)__ldcg(tile_off + tile);
+                    if (off < P.limit) mode = (can_stage && c * 32u >= (unsigned)kDenseTileRowsPerWord) ? 2u : 1u;  // else: LIMIT reached, stop
+                }
+                const int slot = (int)(it % (unsigned)ring);
+                const unsigned use = it / (unsigned)ring;
+                if (use > 0) mbar_wait(smem_u32(&S.mbar_empty[slot]), (use - 1) & 1u, nullptr);
+                S.off[slot] = off;
+                S.tile[slot] = (unsigned)tile;
+                S.mode[slot] = mode;
+                const uint32_t bar = smem_u32(&S.mbar_full[slot]);
+                if (mode == 0) {
+                    mbar_arrive(bar);
+                    break;
+                }
+                const uint32_t dst = ring_addr + (uint32_t)slot * (uint32_t)stage_bytes;
+                mbar_arrive_expect_tx(bar, mode == 2 ? (uint32_t)(stage_bytes - 96) : 1024u + 32u);
+                tma_load_1d(dst, bitmap + tile * 256, 1024u, bar);
+                tma_load_1d(dst + 1024u, span_cnt + tile * 8, 32u, bar);
+                if (mode == 2) {
+#pragma unroll 1
+                    for (int pc = 0; pc < P.nproj; pc++) {
+                        const ProjCol& pj = S.proj[pc];
+                        const uint32_t bytes = (uint32_t)(kDenseTileRowsPerWord * pj.width);
+                        tma_load_1d(dst + (uint32_t)kEmitHdrBytes + 8u * (uint32_t)pj.stage_off, pj.base + tile * bytes, bytes, bar);
+                    }
+                }
+                it++;
+            }
+        }
+    } else {
+        // ---------------- compute warps: warp w = span w of every tile ----------------
+        unsigned short* sel_w = reinterpret_cast<unsigned short*>(dyn_smem) + warp * 1024;
+        for (unsigned it = 0;; it++) {
+            const int slot = (int)(it % (unsigned)ring);
+            mbar_wait(smem_u32(&S.mbar_full[slot]), (it / (unsigned)ring) & 1u, nullptr);
+            const unsigned mode = S.mode[slot];
+            if (mode == 0) break;
+            const uint32_t stage = ring_addr + (uint32_t)slot * (uint32_t)stage_bytes;
+            const long long tile_row0 = (long long)S.tile[slot] * kDenseTileRowsPerWord;
+            uint32_t m, c;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(stage + (uint32_t)(warp * 32 + lane) * 4u));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c) : "r"(stage + 1024u + (uint32_t)(lane & 7) * 4u));
+            const unsigned n = __shfl_sync(0xFFFFFFFFu, c, warp);
+            const unsigned before = __reduce_add_sync(0xFFFFFFFFu, lane < warp ? c : 0u);
+            const long long g0 = S.off[slot] + before;
+            const long long room = P.limit - g0;
+            if (n > 0 && room > 0) {
+                const int nn = room < (long long)n ? (int)room : (int)n;
+                const int span_row = warp * 1024;
+                if (n == 1024u && mode != 2) {
+                    emit_span_full(S.proj, P.nproj, lane, tile_row0 + span_row, g0, nn);
+                } else if (n == 1024u) {
+#pragma unroll 1
+                    for (int pc = 0; pc < P.nproj; pc++) {
+                        const int w = S.proj[pc].width;
+                        copy_smem_to_global(stage + (uint32_t)kEmitHdrBytes + 8u * (uint32_t)S.proj[pc].stage_off + (uint32_t)(span_row * w),
+                                            S.proj[pc].out + g0 * w, nn * w, lane);
+                    }
+                } else {
+                    append_selection(m, lane, sel_w, 0u);
+                    __syncwarp();
+                    if (mode == 2) {
+                        // staged tile: entry i of the vector -> out[g0 + i], four entries per lane per round, every column in the
+                        // same round (one read of the vector)
+                        const uint32_t sel_addr = smem_u32(sel_w);
+                        const uint32_t cols = stage + (uint32_t)kEmitHdrBytes;
+                        for (int i0 = lane; i0 < nn; i0 += 128) {
+                            uint32_t r[4];
+#pragma unroll
+                            for (int k = 0; k < 4; k++) r[k] = i0 + 32 * k < nn ? lds_cell<uint16_t>(sel_addr + 2u * (uint32_t)(i0 + 32 * k)) : 0xFFFFFFFFu;
+#pragma unroll 1
+                            for (int pc = 0; pc < P.nproj; pc++) {
+                                const int w = S.proj[pc].width;
+                                const uint32_t sb = cols + 8u * (uint32_t)S.proj[pc].stage_off + (uint32_t)(span_row * w);
+                                uint8_t* const ob = S.proj[pc].out + (g0 + i0) * w;
+                                if (w == 4) {
+#pragma unroll
+                                    for (int k = 0; k < 4; k++)
+                                        if (r[k] != 0xFFFFFFFFu) reinterpret_cast<uint32_t*>(ob)[32 * k] = lds_cell<uint32_t>(sb + r[k] * 4u);
+                                } else if (w == 1) {
+#pragma unroll
+                                    for (int k = 0; k < 4; k++)
+                                        if (r[k] != 0xFFFFFFFFu) ob[32 * k] = lds_cell<uint8_t>(sb + r[k]);
+                                } else if (w == 2) {
+#pragma unroll
+                                    for (int k = 0; k < 4; k++)
+                                        if (r[k] != 0xFFFFFFFFu) reinterpret_cast<uint16_t*>(ob)[32 * k] = lds_cell<uint16_t>(sb + r[k] * 2u);
+                                } else {
+                                    for (int k = 0; k < 4; k++)
+                                        if (r[k] != 0xFFFFFFFFu)
+                                            for (int b = 0; b < w; b++) ob[(32 * k) * w + b] = (uint8_t)lds_u8(sb + r[k] * (uint32_t)w + (uint32_t)b);
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int pc = 0; pc < P.nproj; pc++) {
+                            const ProjCol& pj = S.proj[pc];
+                            const int w = pj.width;
+                            emit_col(sel_w, nn, lane, w, false, 0u, pj.base + (tile_row0 + span_row) * w, pj.out + g0 * w);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&S.mbar_empty[slot]));
+        }
     }
 }
 
@@ -1170,12 +1627,12 @@ size_t blocks_kernel_smem_bytes(int npfor, int max_block_rows) {
 
 static cudaError_t configure_once() {
     static cudaError_t rc = [] {
-        cudaError_t e = cudaFuncSetAttribute(scan_dense_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(scan_dense_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(scan_dense_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
+        cudaError_t e = cudaSuccess;
+#define IMM3_SET_SMEM(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e
+        IMM3_SET_SMEM(emit_stream_kernel);
+        IMM3_SET_SMEM((scan_dense_kernel<true>));
+        IMM3_SET_SMEM((scan_dense_kernel<false>));
+#undef IMM3_SET_SMEM
         e = cudaFuncSetAttribute(filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1187,12 +1644,11 @@ static cudaError_t configure_once() {
     return rc;
 }
 
-cudaError_t dense_kernel_occupancy(int words_per_lane, size_t dyn_smem, int* blocks_per_sm) {
+cudaError_t dense_kernel_occupancy(bool staged, size_t dyn_smem, int* blocks_per_sm) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    if (words_per_lane == 4) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, scan_dense_kernel<4>, kDenseThreads, dyn_smem);
-    if (words_per_lane == 2) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, scan_dense_kernel<2>, kDenseThreads, dyn_smem);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, scan_dense_kernel<1>, kDenseThreads, dyn_smem);
+    if (staged) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, scan_dense_kernel<true>, kDenseThreads, dyn_smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, scan_dense_kernel<false>, kDenseThreads, dyn_smem);
 }
 cudaError_t blocks_kernel_occupancy(size_t dyn_smem, int* blocks_per_sm) {
     cudaError_t e = configure_once();
@@ -1204,9 +1660,8 @@ cudaError_t launch_scan_dense(const ScanPlan& plan, ScanCtrl* ctrl, unsigned lon
                               cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    if (plan.words_per_lane == 4) scan_dense_kernel<4><<<grid, kDenseThreads, dyn_smem, stream>>>(plan, ctrl, status);
-    else if (plan.words_per_lane == 2) scan_dense_kernel<2><<<grid, kDenseThreads, dyn_smem, stream>>>(plan, ctrl, status);
-    else scan_dense_kernel<1><<<grid, kDenseThreads, dyn_smem, stream>>>(plan, ctrl, status);
+    if (plan.stages > 0) scan_dense_kernel<true><<<grid, kDenseThreads, dyn_smem, stream>>>(plan, ctrl, status);
+    else scan_dense_kernel<false><<<grid, kDenseThreads, dyn_smem, stream>>>(plan, ctrl, status);
     return cudaGetLastError();
 }
 cudaError_t filter_kernel_occupancy(int words_per_lane, size_t dyn_smem, int* blocks_per_sm) {
@@ -1231,10 +1686,25 @@ cudaError_t launch_filter(const ScanPlan& plan, uint32_t* bitmap, uint32_t* span
     return cudaGetLastError();
 }
 cudaError_t launch_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* span_cnt, const unsigned long long* tile_off,
-                        int spans_per_tile, long long nspans, int grid, cudaStream_t stream) {
+                        int spans_per_tile, long long nspans, int grid, int dense_off, cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    emit_kernel<<<grid, kComputeThreads, kComputeWarps * 1024 * 2, stream>>>(plan, bitmap, span_cnt, tile_off, spans_per_tile, nspans);
+    emit_kernel<<<grid, kComputeThreads, kComputeWarps * 1024 * 2, stream>>>(plan, bitmap, span_cnt, tile_off, spans_per_tile, nspans, dense_off);
+    return cudaGetLastError();
+}
+size_t emit_stream_smem_bytes(int stage_bytes, int ring) { return (size_t)kComputeWarps * 1024 * 2 + (size_t)ring * (size_t)stage_bytes + 16; }
+int emit_stream_header_bytes() { return kEmitHdrBytes; }
+cudaError_t emit_stream_occupancy(size_t dyn_smem, int* blocks_per_sm) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, emit_stream_kernel, kComputeThreads + 32, dyn_smem);
+}
+cudaError_t launch_emit_stream(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* span_cnt, const uint32_t* tile_cnt,
+                               const unsigned long long* tile_off, long long nsub, int ring, int stage_bytes, int dense_mode, int grid,
+                               size_t dyn_smem, cudaStream_t stream) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    emit_stream_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt, tile_off, nsub, ring, stage_bytes, dense_mode);
     return cudaGetLastError();
 }
 

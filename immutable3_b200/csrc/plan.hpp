@@ -17,10 +17,13 @@ constexpr int kMaxPforCols = 4;     // PFOR_INT columns touched by one query
 constexpr int kLitPoolBytes = 512;  // MATCH literals of all filter columns, packed
 constexpr int kDenseTileRowsPerWord = 8192;  // dense kernel: 8 compute warps x 32 lanes x 32 rows per bitmap word
 constexpr int kDenseMaxTileRows = 4 * kDenseTileRowsPerWord;  // tile = 8192 * W rows, W in {1, 2, 4}
-constexpr int kDenseThreads = 288;  // 8 compute warps + 1 control warp (tickets, TMA, look-back)
+constexpr int kDenseThreads = 320;  // 8 compute warps + producer warp (tickets, TMA) + scanner-candidate warp
 constexpr int kBlockThreads = 256;  // block-mode kernel: threads per CTA
 constexpr int kMaxBlockRows = 8192; // block-mode kernel: largest reference block it stages
 constexpr int kMaxStages = 4;
+constexpr int kMaxSubtiles = 8;       // fused dense kernel: a tile is up to 8 sub-tiles of 8192 rows (one scan hand-off per tile)
+// Tile-status arrays of the dense kernel (counts, then offsets) are padded to whole scanner rounds of 256 tiles.
+constexpr long long status_round_up(long long ntiles) { return ((ntiles + 255) & ~255ll) + 256; }
 constexpr int kMaxFilterStages = 8;  // TMA ring depth of the multi-pass filter kernel
 
 enum FilterKind : int32_t {
@@ -47,7 +50,7 @@ struct ProjCol {
     int32_t width;
     int32_t filter_idx;   // >= 0: same column as filter[filter_idx] (its staged tile can be reused)
     int32_t pfor_slot;
-    int32_t pad;
+    int32_t stage_off;    // fused dense kernel: byte offset of this column's 1024-row span in a warp's staging buffer
 };
 
 struct PforCol {
@@ -61,6 +64,7 @@ struct ScanPlan {
     int64_t ntiles;       // dense: ceil(nrows / (8192 * W)); block mode: number of reference blocks
     const uint64_t* row_start;  // block mode: nblocks+1 canonical row ordinals
     uint32_t* bitmap;     // filter-bitmap mode: selection bitmap out (else nullptr)
+    unsigned long long* trace;  // debugging (IMM3_TRACE): 8 globaltimer stamps per tile, else nullptr
     uint32_t epoch;       // tags the tile-status words of this launch
     int32_t nfilter;
     int32_t nproj;
@@ -68,9 +72,11 @@ struct ScanPlan {
     int32_t stages;       // dense: TMA pipeline depth (0 = direct loads, no staging)
     int32_t stage_bytes;  // dense: bytes of one stage
     int32_t max_block_rows;  // block mode: rows of the largest block (shared-memory sizing)
-    int32_t words_per_lane;  // dense: W (tile = 8192 * W rows)
+    int32_t words_per_lane;  // multi-pass filter kernel: W (tile = 8192 * W rows)
+    int32_t subtiles;        // fused dense kernel: NS (tile = NS sub-tiles of 8192 rows)
+    int32_t proj_stage_bytes;  // fused dense kernel: one 1024-row span of every projected column (0 = never staged)
+    int32_t stream_min_cnt;    // fused dense kernel: spans with at least this many selected rows are staged, not gathered
     uint32_t debug;          // IMM3_DEBUG env bits (timing experiments only; bit 0: skip the look-back -> WRONG offsets)
-    uint32_t pad2;
     FilterCol filter[kMaxFilterCols];
     ProjCol proj[kMaxProjCols];
     PforCol pfor[kMaxPforCols];
@@ -84,7 +90,8 @@ struct ScanCtrl {
     unsigned int exited;   // CTAs that have left the kernel
     unsigned int error;    // watchdog: a bounded spin expired (never hang the GPU)
     unsigned long long total;  // rows emitted (min(limit, matches)) or matches in bitmap mode
-    unsigned long long pad;
+    unsigned int scanner;  // dense kernel: the grid's scanner warp has been elected
+    unsigned int pad;
 };
 
 // ---------------------------------------------------------------------------------------------
