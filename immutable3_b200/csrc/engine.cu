@@ -399,27 +399,17 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
             }
         }
         if (pr->multipass) {
-            // Multi-pass filter kernel: tile = 8192 * W rows, W = 2 while one stage stays within 16 KiB.
-            int W = (kDenseTileRowsPerWord * 2 * row_bytes <= 16 * 1024) ? 2 : 1;
-            if (const char* e = getenv("IMM3_DENSE_W")) {  // tuning / A-B knob
-                int v = atoi(e);
-                if (v == 1 || v == 2 || v == 4) W = v;
-            }
-            const int tile_rows = kDenseTileRowsPerWord * W;
-            const int stage_bytes = tile_rows * row_bytes;
-            const bool stage_ok = can_stage && stage_bytes <= 56 * 1024;
-            if (stage_ok)
-                for (int i = 0, off = 0; i < sp.nfilter; i++) {
-                    sp.filter[i].smem_off = off;
-                    off += tile_rows * sp.filter[i].width;
-                }
-            else
+            // Multi-pass filter kernel: tile = 8192 rows; a TMA ring of ~32 KiB, so that four CTAs share an SM.
+            const int W = 1;
+            const int tile_rows = kDenseTileRowsPerWord;
+            const int stage_bytes = sub_bytes;
+            const bool stage_ok = can_stage;
+            if (!stage_ok)
                 for (int i = 0; i < sp.nfilter; i++) sp.filter[i].smem_off = -1;
             sp.words_per_lane = W;
             sp.ntiles = (t.nrows + tile_rows - 1) / tile_rows;
             int stages = 0;
-            // K1 streams: a ring of ~48 KiB, so that four CTAs (32 warps) share an SM
-            if (stage_ok) stages = std::max(2, std::min(kMaxFilterStages, (48 * 1024) / stage_bytes));
+            if (stage_ok) stages = std::max(2, std::min(kMaxFilterStages, (32 * 1024) / stage_bytes));
             if (const char* e = getenv("IMM3_FILTER_STAGES")) {
                 int v = atoi(e);
                 if (stage_ok && v >= 2 && v <= kMaxFilterStages && (size_t)v * stage_bytes <= 200 * 1024) stages = v;
@@ -427,7 +417,7 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
             sp.stages = stages;
             sp.stage_bytes = stage_bytes;
             pr->dyn_smem = (size_t)stages * (size_t)stage_bytes;
-            CUDA_TRY(filter_kernel_occupancy(W, pr->dyn_smem, &occ));
+            CUDA_TRY(filter_kernel_occupancy(pr->dyn_smem, &occ));
             int occ_emit = 0;
             CUDA_TRY(emit_kernel_occupancy(&occ_emit));
             const int64_t nspans = sp.ntiles * (tile_rows / 1024);

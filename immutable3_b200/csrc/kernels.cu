@@ -285,21 +285,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 //   MODE 2: lo < 0 <= hi   negative rows: xl >= lo + 128; non-negative rows: xl <= hi
 // The four flag bits of a word (bits 7, 15, 23, 31) are gathered into a nibble by one multiply.
 template <int MODE>
-__device__ __forceinline__ uint32_t i8_range16(const uint4& v, uint32_t c1, uint32_t c2) {
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t r = 0;
-#pragma unroll
-    for (int k = 3; k >= 0; k--) {
-        const uint32_t x = w[k];
-        const uint32_t xl = x & 0x7F7F7F7Fu;
-        const uint32_t g = xl + c1, l = c2 - xl;
-        uint32_t m;
-        if (MODE == 0) m = (g & l & 0x80808080u) & ~x;
-        else if (MODE == 1) m = (g & l & 0x80808080u) & x;
-        else m = ((x & g) | (~x & l)) & 0x80808080u;
-        r = __funnelshift_l((m >> 7) * 0x10204080u, r, 4);
-    }
-    return r;
+__device__ __forceinline__ uint32_t i8_flags(uint32_t x, uint32_t c1, uint32_t c2) {  // bit 7 of every byte: row selected
+    const uint32_t xl = x & 0x7F7F7F7Fu;
+    const uint32_t g = xl + c1, l = c2 - xl;
+    if (MODE == 0) return (g & l & 0x80808080u) & ~x;
+    if (MODE == 1) return (g & l & 0x80808080u) & x;
+    return ((x & g) | (~x & l)) & 0x80808080u;
+}
+// The flag bytes (0x80 / 0x00) of two words -> one byte of selection bits, scaled by 128: a byte-wise dot product with
+// the weights 1,2,4,8 | 16,32,64,128 (IDP4A accumulates, so a pair costs two instructions off the ALU pipe).
+__device__ __forceinline__ uint32_t flags_pair(uint32_t m_lo, uint32_t m_hi) {
+    return __dp4a(m_lo, 0x08040201u, __dp4a(m_hi, 0x80402010u, 0u));
 }
 __device__ __forceinline__ uint32_t range_i32_chunk(const uint4& v, uint32_t lo, uint32_t span) {
     return (uint32_t)((v.x - lo) <= span) | ((uint32_t)((v.y - lo) <= span) << 1) | ((uint32_t)((v.z - lo) <= span) << 2) |
@@ -330,14 +326,16 @@ __device__ __forceinline__ uint32_t eval_i8(uint32_t cell_s, const uint8_t* cell
     const int t2 = MODE == 1 ? hi + 128 : hi;
     const uint32_t c1 = (uint32_t)(128 - t1) * 0x01010101u;
     const uint32_t c2 = (uint32_t)(128 + t2) * 0x01010101u;
-    uint32_t mask = 0;
-#pragma unroll
-    for (int c = 0; c < 2; c++) {
-        const int q = (c + lane) & 1;  // rotate so the 8 lanes of a quarter-warp hit distinct banks
-        const uint4 v = ld16<STAGED>(cell_s + 16u * q, cell_g + 16 * q);
-        mask |= i8_range16<MODE>(v, c1, c2) << (16 * q);
-    }
-    return mask;
+    // the lane's two 16-byte chunks, fetched in rotated order so that the 8 lanes of a quarter-warp hit distinct banks
+    const int q0 = lane & 1;
+    const uint4 a = ld16<STAGED>(cell_s + 16u * q0, cell_g + 16 * q0);
+    const uint4 b = ld16<STAGED>(cell_s + 16u * (q0 ^ 1), cell_g + 16 * (q0 ^ 1));
+    const uint32_t b0 = flags_pair(i8_flags<MODE>(a.x, c1, c2), i8_flags<MODE>(a.y, c1, c2));
+    const uint32_t b1 = flags_pair(i8_flags<MODE>(a.z, c1, c2), i8_flags<MODE>(a.w, c1, c2));
+    const uint32_t b2 = flags_pair(i8_flags<MODE>(b.x, c1, c2), i8_flags<MODE>(b.y, c1, c2));
+    const uint32_t b3 = flags_pair(i8_flags<MODE>(b.z, c1, c2), i8_flags<MODE>(b.w, c1, c2));
+    const uint32_t r = (b0 >> 7) + b1 * 2u + b2 * 512u + b3 * 131072u;  // chunk a = bits 0..15, chunk b = bits 16..31
+    return __funnelshift_l(r, r, 16 * q0);                              // un-rotate
 }
 
 template <bool STAGED>
@@ -549,6 +547,18 @@ __device__ __forceinline__ void append_selection(uint32_t mm, int lane, unsigned
     }
 }
 
+// Position in a ring of `ring` slots, advanced without integer division.
+struct RingPos {
+    int slot = 0;
+    unsigned use = 0;  // how many times the ring has wrapped
+    __device__ __forceinline__ void advance(int ring) {
+        if (++slot == ring) {
+            slot = 0;
+            use++;
+        }
+    }
+};
+
 extern __shared__ __align__(128) uint8_t dyn_smem[];
 
 // The plan's per-column tables -> shared memory.  Every access to P uses a compile-time index (fully unrolled
@@ -725,14 +735,14 @@ __global__ void __launch_bounds__(kDenseThreads, IMM3_DENSE_MIN_BLOCKS) scan_den
     } else if (warp == kComputeWarps) {
         // ---------------- producer: tickets + TMA, `ring` sub-tiles ahead of the compute warps ----------------
         if (lane == 0) {
-            unsigned it = 0;
+            RingPos rp;
             for (bool more = true; more;) {
                 unsigned t = kNoMoreTiles;
                 if (!ld_relaxed_u32(&ctrl->done)) t = atomicAdd(&ctrl->ticket, 1u);  // after LIMIT: stop drawing tiles
                 if (t < ntiles) trace_stamp(P, t, 0);
-                for (int sub = 0; sub < NS && more; sub++, it++) {
-                    const int slot = (int)(it % (unsigned)ring);
-                    const unsigned use = it / (unsigned)ring;
+                for (int sub = 0; sub < NS && more; sub++, rp.advance(ring)) {
+                    const int slot = rp.slot;
+                    const unsigned use = rp.use;
                     if (use > 0) mbar_wait(smem_u32(&S.mbar_empty[slot]), (use - 1) & 1u, ctrl);
                     S.tile[slot] = t;
                     const uint32_t bar = smem_u32(&S.mbar_full[slot]);
@@ -761,7 +771,7 @@ __global__ void __launch_bounds__(kDenseThreads, IMM3_DENSE_MIN_BLOCKS) scan_den
     } else {
         // ---------------- compute warps ----------------
         unsigned short* sel_w = sel_all + warp * 1024;
-        unsigned it = 0;
+        RingPos rp;
         uint32_t wparity = 0;  // phase of this warp's projected-span barrier
         for (unsigned j = 0;; j++) {
             const int e = (int)(j & 1u);
@@ -769,9 +779,9 @@ __global__ void __launch_bounds__(kDenseThreads, IMM3_DENSE_MIN_BLOCKS) scan_den
             unsigned tile = kNoMoreTiles;
 
             // ---- phase 1: stream the tile's sub-tiles: decode + conjunctive filter -> bitmap words + span counts ----
-            for (int sub = 0; sub < NS; sub++, it++) {
-                const int slot = (int)(it % (unsigned)ring);
-                mbar_wait(smem_u32(&S.mbar_full[slot]), (it / (unsigned)ring) & 1u, ctrl);
+            for (int sub = 0; sub < NS; sub++, rp.advance(ring)) {
+                const int slot = rp.slot;
+                mbar_wait(smem_u32(&S.mbar_full[slot]), rp.use & 1u, ctrl);
                 tile = S.tile[slot];
                 if (tile >= ntiles) break;  // CTA-uniform; only ever at sub == 0
                 if (tid == 0 && sub == 0) trace_stamp(P, tile, 1);
@@ -1159,7 +1169,8 @@ __global__ void __launch_bounds__(kBlockThreads) scan_blocks_kernel(const __grid
 // =============================================================================================
 struct FilterShared {
     unsigned long long mbar_full[kMaxFilterStages];
-    unsigned int span_c[2][4 * kComputeWarps];  // per-span match counts of the tile (W <= 4 spans per warp)
+    unsigned long long mbar_empty[kMaxFilterStages];
+    unsigned int tile_acc[kMaxFilterStages];  // per ring slot: [31:20] warps arrived, [19:0] rows selected
     unsigned long long scan_warp[kComputeWarps];
     unsigned int is_last;
     uint8_t lits[kLitPoolBytes];  // MATCH literals of the plan
@@ -1193,9 +1204,9 @@ __device__ void scan_tile_counts(FilterShared& S, const uint32_t* tile_cnt, unsi
             const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
             if (lane >= o) incl += nb;
         }
-        __syncthreads();  // the previous round's readers are done with scan_warp
+        bar_sync(1, kComputeThreads);  // the previous round's readers are done with scan_warp
         if (lane == 31) S.scan_warp[warp] = incl;
-        __syncthreads();
+        bar_sync(1, kComputeThreads);
         unsigned long long excl = running + (incl - sum), total = 0;
 #pragma unroll
         for (int w = 0; w < kComputeWarps; w++) {
@@ -1215,91 +1226,92 @@ __device__ void scan_tile_counts(FilterShared& S, const uint32_t* tile_cnt, unsi
         }
         running += total;
     }
-    __syncthreads();
+    bar_sync(1, kComputeThreads);
     if (tid == 0) {
         tile_off[ntiles] = running;
         ctrl->total = running < (unsigned long long)limit ? running : (unsigned long long)limit;
     }
 }
 
-template <int W>
-__global__ void __launch_bounds__(kComputeThreads) filter_kernel(const __grid_constant__ ScanPlan P, uint32_t* __restrict__ bitmap,
-                                                                   uint32_t* __restrict__ span_cnt, uint32_t* __restrict__ tile_cnt,
-                                                                   unsigned long long* __restrict__ tile_off, ScanCtrl* ctrl) {
-    constexpr int kTile = kDenseTileRowsPerWord * W;
-    constexpr int kWarpSpan = 1024 * W;
+// K1: tile = 8192 rows = 8 spans, one per compute warp.  A producer warp streams the tiles of this CTA (statically
+// strided: no ordering, no tickets) through a TMA ring `ring` tiles deep; the compute warps never synchronise with each
+// other - each evaluates the conjunction on its span, stores its bitmap word and span count, and adds the count to the
+// tile's total in shared memory; the warp that completes a tile writes the tile count.
+__global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const __grid_constant__ ScanPlan P, uint32_t* __restrict__ bitmap,
+                                                                           uint32_t* __restrict__ span_cnt, uint32_t* __restrict__ tile_cnt,
+                                                                           unsigned long long* __restrict__ tile_off, ScanCtrl* ctrl) {
+    constexpr int kTile = kDenseTileRowsPerWord;
     __shared__ FilterShared S;
     const uint32_t ring_addr = smem_u32(dyn_smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool staged = P.stages > 0;
-    const int ring = staged ? P.stages : 1;
+    const int ring = staged ? P.stages : 2;
     const long long ntiles = P.ntiles;
 
-    auto issue = [&](long long tile, int slot) {  // thread 0
-        const uint32_t bar = smem_u32(&S.mbar_full[slot]);
-        mbar_arrive_expect_tx(bar, (uint32_t)P.stage_bytes);
-#pragma unroll 1
-        for (int i = 0; i < P.nfilter; i++) {
-            const FilterCol& f = S.filter[i];
-            const uint32_t bytes = (uint32_t)(kTile * f.width);
-            tma_load_1d(ring_addr + (uint32_t)slot * (uint32_t)P.stage_bytes + (uint32_t)f.smem_off, f.base + tile * bytes, bytes, bar);
-        }
-    };
-    for (int i = tid; i < kLitPoolBytes; i += kComputeThreads) S.lits[i] = P.lits[i];
-    copy_plan_tables(P, S.filter, S.proj, tid, kComputeThreads);
-    __syncthreads();
+    for (int i = tid; i < kLitPoolBytes; i += kComputeThreads + 32) S.lits[i] = P.lits[i];
+    copy_plan_tables(P, S.filter, S.proj, tid, kComputeThreads + 32);
     if (tid == 0) {
-        for (int s = 0; s < kMaxFilterStages; s++) mbar_init(smem_u32(&S.mbar_full[s]), 1);
+        for (int s = 0; s < kMaxFilterStages; s++) {
+            mbar_init(smem_u32(&S.mbar_full[s]), 1);
+            mbar_init(smem_u32(&S.mbar_empty[s]), kComputeWarps);
+            S.tile_acc[s] = 0;
+        }
         fence_mbar_init();
-        if (staged)
-            for (int s = 0; s < ring; s++) {
-                const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
-                if (t < ntiles) issue(t, s);
-            }
     }
     __syncthreads();
 
-    int slot = 0;
-    uint32_t parity = 0;
-    unsigned it = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-        const long long tile_row0 = tile * kTile;
-        const uint32_t stage_addr = ring_addr + (uint32_t)slot * (uint32_t)P.stage_bytes;
-        if (staged) mbar_wait(smem_u32(&S.mbar_full[slot]), parity, nullptr);
-        uint32_t m[W];
-#pragma unroll
-        for (int s = 0; s < W; s++) {
-            const long long left = P.nrows - (tile_row0 + warp * kWarpSpan + s * 1024 + lane * 32);
-            m[s] = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
-        }
-        if (staged) {
-            for (int i = 0; i < P.nfilter; i++) dense_eval_filter<W, true>(S.filter[i], S.lits, stage_addr, tile_row0, warp * kWarpSpan, lane, m);
-        } else {
-            for (int i = 0; i < P.nfilter; i++) dense_eval_filter<W, false>(S.filter[i], S.lits, stage_addr, tile_row0, warp * kWarpSpan, lane, m);
-        }
-        const int e = (int)(it & 1u);
-#pragma unroll
-        for (int s = 0; s < W; s++) {
-            const long long span_row0 = tile_row0 + warp * kWarpSpan + s * 1024;
-            bitmap[(span_row0 >> 5) + lane] = m[s];
-            const unsigned c = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(m[s]));
-            if (lane == 0) {
-                span_cnt[span_row0 >> 10] = c;
-                S.span_c[e][warp * W + s] = c;
+    if (warp == kComputeWarps) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            RingPos rp;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, rp.advance(ring)) {
+                const int slot = rp.slot;
+                const unsigned use = rp.use;
+                if (use > 0) mbar_wait(smem_u32(&S.mbar_empty[slot]), (use - 1) & 1u, nullptr);
+                const uint32_t bar = smem_u32(&S.mbar_full[slot]);
+                if (staged) {
+                    mbar_arrive_expect_tx(bar, (uint32_t)P.stage_bytes);
+#pragma unroll 1
+                    for (int i = 0; i < P.nfilter; i++) {
+                        const FilterCol& f = S.filter[i];
+                        const uint32_t bytes = (uint32_t)(kTile * f.width);
+                        tma_load_1d(ring_addr + (uint32_t)slot * (uint32_t)P.stage_bytes + (uint32_t)f.smem_off, f.base + tile * bytes, bytes, bar);
+                    }
+                } else {
+                    mbar_arrive(bar);
+                }
             }
         }
-        __syncthreads();  // every warp has consumed the slot's bytes
-        if (tid < W) {  // match count of every 8192-row sub-tile (8 consecutive spans): the unit of the offset scan
-            unsigned c = 0;
-#pragma unroll
-            for (int w = 0; w < kComputeWarps; w++) c += S.span_c[e][tid * kComputeWarps + w];
-            tile_cnt[tile * W + tid] = c;
+    } else {
+        // ---------------- compute warps: warp w = span w of every tile ----------------
+        RingPos rp;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, rp.advance(ring)) {
+            const int slot = rp.slot;
+            mbar_wait(smem_u32(&S.mbar_full[slot]), rp.use & 1u, nullptr);
+            const long long tile_row0 = tile * kTile;
+            const uint32_t stage_addr = ring_addr + (uint32_t)slot * (uint32_t)P.stage_bytes;
+            const long long left = P.nrows - (tile_row0 + warp * 1024 + lane * 32);
+            uint32_t m = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
+#pragma unroll 1
+            for (int i = 0; i < P.nfilter; i++) {
+                if (staged) dense_eval_filter<1, true>(S.filter[i], S.lits, stage_addr, tile_row0, warp * 1024, lane, &m);
+                else dense_eval_filter<1, false>(S.filter[i], S.lits, stage_addr, tile_row0, warp * 1024, lane, &m);
+            }
+            const long long span = tile * kComputeWarps + warp;
+            bitmap[span * 32 + lane] = m;
+            const unsigned c = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(m));
+            if (lane == 0) {
+                span_cnt[span] = c;
+                // tile total: [31:20] warps arrived, [19:0] rows selected; the eighth arrival publishes and clears
+                const unsigned old = atomicAdd(&S.tile_acc[slot], c + (1u << 20));
+                if ((old >> 20) == kComputeWarps - 1) {
+                    tile_cnt[tile] = (old & 0xFFFFFu) + c;
+                    S.tile_acc[slot] = 0;  // (nobody touches it again before this warp's arrival on `empty` below)
+                }
+                mbar_arrive(smem_u32(&S.mbar_empty[slot]));  // this warp is done with the slot's bytes
+            }
+            __syncwarp();
         }
-        if (tid == 0) {
-            const long long next = tile + (long long)ring * gridDim.x;
-            if (staged && next < ntiles) issue(next, slot);
-        }
-        if (++slot == ring) { slot = 0; parity ^= 1u; }
     }
 
     // The last CTA to finish turns the tile counts into device-wide offsets (saves a launch).
@@ -1311,9 +1323,9 @@ __global__ void __launch_bounds__(kComputeThreads) filter_kernel(const __grid_co
         if (S.is_last) ctrl->exited = 0;
     }
     __syncthreads();
-    if (S.is_last) {
+    if (S.is_last && warp < kComputeWarps) {
         __threadfence();
-        scan_tile_counts(S, tile_cnt, tile_off, ntiles * W, P.limit, ctrl);
+        scan_tile_counts(S, tile_cnt, tile_off, ntiles, P.limit, ctrl);
     }
 }
 
@@ -1499,7 +1511,7 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(co
     if (warp == kComputeWarps) {
         // ---------------- producer ----------------
         if (lane == 0) {
-            unsigned it = 0;
+            RingPos rp;
             for (long long tile = blockIdx.x;; tile += gridDim.x) {
                 unsigned mode = 0, c = 0;
                 long long off = 0;
@@ -1509,8 +1521,8 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(co
                     off = (long long)__ldcg(tile_off + tile);
                     if (off < P.limit) mode = (can_stage && c * 32u >= (unsigned)kDenseTileRowsPerWord) ? 2u : 1u;  // else: LIMIT reached, stop
                 }
-                const int slot = (int)(it % (unsigned)ring);
-                const unsigned use = it / (unsigned)ring;
+                const int slot = rp.slot;
+                const unsigned use = rp.use;
                 if (use > 0) mbar_wait(smem_u32(&S.mbar_empty[slot]), (use - 1) & 1u, nullptr);
                 S.off[slot] = off;
                 S.tile[slot] = (unsigned)tile;
@@ -1532,15 +1544,15 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(co
                         tma_load_1d(dst + (uint32_t)kEmitHdrBytes + 8u * (uint32_t)pj.stage_off, pj.base + tile * bytes, bytes, bar);
                     }
                 }
-                it++;
+                rp.advance(ring);
             }
         }
     } else {
         // ---------------- compute warps: warp w = span w of every tile ----------------
         unsigned short* sel_w = reinterpret_cast<unsigned short*>(dyn_smem) + warp * 1024;
-        for (unsigned it = 0;; it++) {
-            const int slot = (int)(it % (unsigned)ring);
-            mbar_wait(smem_u32(&S.mbar_full[slot]), (it / (unsigned)ring) & 1u, nullptr);
+        for (RingPos rp;; rp.advance(ring)) {
+            const int slot = rp.slot;
+            mbar_wait(smem_u32(&S.mbar_full[slot]), rp.use & 1u, nullptr);
             const unsigned mode = S.mode[slot];
             if (mode == 0) break;
             const uint32_t stage = ring_addr + (uint32_t)slot * (uint32_t)stage_bytes;
@@ -1632,13 +1644,8 @@ static cudaError_t configure_once() {
         IMM3_SET_SMEM(emit_stream_kernel);
         IMM3_SET_SMEM((scan_dense_kernel<true>));
         IMM3_SET_SMEM((scan_dense_kernel<false>));
+        IMM3_SET_SMEM(filter_kernel);
 #undef IMM3_SET_SMEM
-        e = cudaFuncSetAttribute(filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(filter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(scan_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     }();
     return rc;
@@ -1664,12 +1671,10 @@ cudaError_t launch_scan_dense(const ScanPlan& plan, ScanCtrl* ctrl, unsigned lon
     else scan_dense_kernel<false><<<grid, kDenseThreads, dyn_smem, stream>>>(plan, ctrl, status);
     return cudaGetLastError();
 }
-cudaError_t filter_kernel_occupancy(int words_per_lane, size_t dyn_smem, int* blocks_per_sm) {
+cudaError_t filter_kernel_occupancy(size_t dyn_smem, int* blocks_per_sm) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    if (words_per_lane == 4) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, filter_kernel<4>, kComputeThreads, dyn_smem);
-    if (words_per_lane == 2) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, filter_kernel<2>, kComputeThreads, dyn_smem);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, filter_kernel<1>, kComputeThreads, dyn_smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, filter_kernel, kComputeThreads + 32, dyn_smem);
 }
 cudaError_t emit_kernel_occupancy(int* blocks_per_sm) {
     cudaError_t e = configure_once();
@@ -1680,9 +1685,7 @@ cudaError_t launch_filter(const ScanPlan& plan, uint32_t* bitmap, uint32_t* span
                           ScanCtrl* ctrl, int grid, size_t dyn_smem, cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    if (plan.words_per_lane == 4) filter_kernel<4><<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt, tile_off, ctrl);
-    else if (plan.words_per_lane == 2) filter_kernel<2><<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt, tile_off, ctrl);
-    else filter_kernel<1><<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt, tile_off, ctrl);
+    filter_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt, tile_off, ctrl);
     return cudaGetLastError();
 }
 cudaError_t launch_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* span_cnt, const unsigned long long* tile_off,
