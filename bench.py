@@ -188,7 +188,7 @@ def measured_peak():
 
 
 def recorded_traffic(workload: str):
-    """dram bytes per launch of the fused kernel from the committed ncu --set full capture, if any."""
+    """dram__bytes_read+write per query (sum over its kernels) from the committed ncu capture, if any."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
@@ -393,10 +393,22 @@ def main():
     peak, peak_src = measured_peak()
     launch_ms = statistics.mean(kernel_ms)
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    st0, st1 = statistics.mean(stage_ms[0]), statistics.mean(stage_ms[1])
+    multi = st1 > 0
+    if args.workload == "c4":
+        kname = "scan_blocks_kernel"
+    elif multi:
+        kname = "filter_kernel -> emit_stream_kernel | emit_kernel (one query = one launch of each; timed together)"
+    else:
+        kname = "scan_dense_kernel"
+    # achieved = algorithmic bytes of the query / CUDA-event time of ALL its kernels (conservative: the numerator is the
+    # SURVEY.md 8d lower bound on traffic, the denominator includes every stage and the gaps between them)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": recorded_traffic(args.workload), "peak_source": peak_src, "kernel": "scan_dense_kernel" if args.workload != "c4" else "scan_blocks_kernel",
+                "traffic": recorded_traffic(args.workload), "peak_source": peak_src, "kernel": kname,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms_mean": launch_ms, "launch_ms_min": min(kernel_ms),
-                "stage_ms_mean": [statistics.mean(stage_ms[0]), statistics.mean(stage_ms[1])]}
+                "stage_ms_mean": [st0, st1],
+                "stages": ({"filter_kernel(+offset scan)": st0, "emit kernels": st1, "dominant": "emit_stream_kernel" if st1 >= st0 else "filter_kernel",
+                            "dominant_share": max(st0, st1) / (st0 + st1)} if multi else None)}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     cpu = None

@@ -532,15 +532,19 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
         if (pr->sp.nproj > 0) {
             // Two emit kernels, one of which does the work: which one is decided on the device from the match count.
             const int stream_ok = pr->emit_stage_bytes > 0;
+            const char* force = getenv("IMM3_EMIT");  // experiment: "stream" = the streaming kernel takes every result
+            const bool only_stream = stream_ok && force && !strcmp(force, "stream");
             if (stream_ok) {
                 CUDA_TRY(launch_emit_stream(pr->sp, pr->sp.bitmap, (const uint32_t*)db->d_span_cnt.p, (const uint32_t*)db->d_tile_cnt.p,
-                                            (const unsigned long long*)db->d_tile_off.p, nsub, pr->emit_ring, pr->emit_stage_bytes, 1,
-                                            pr->grid_emit_stream, pr->emit_smem, db->stream));
+                                            (const unsigned long long*)db->d_tile_off.p, nsub, pr->emit_ring, pr->emit_stage_bytes,
+                                            only_stream ? -1 : 1, pr->grid_emit_stream, pr->emit_smem, db->stream));
                 (*launches)++;
             }
-            CUDA_TRY(launch_emit(pr->sp, pr->sp.bitmap, (const uint32_t*)db->d_span_cnt.p, (const unsigned long long*)db->d_tile_off.p, 8, nspans,
-                                 pr->grid_emit, stream_ok, db->stream));
-            (*launches)++;
+            if (!only_stream) {
+                CUDA_TRY(launch_emit(pr->sp, pr->sp.bitmap, (const uint32_t*)db->d_span_cnt.p, (const unsigned long long*)db->d_tile_off.p, 8,
+                                     nspans, pr->grid_emit, stream_ok, db->stream));
+                (*launches)++;
+            }
         }
         CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
     } else {

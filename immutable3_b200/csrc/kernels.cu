@@ -1494,7 +1494,7 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(co
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // One of the two emit kernels does the work, picked on the device from the match count (no host round trip).
     const unsigned long long total = __ldcg(tile_off + nsub);
-    if (((total * 32ull >= (unsigned long long)P.nrows) ? 1 : 0) != dense_mode) return;
+    if (dense_mode >= 0 && ((total * 32ull >= (unsigned long long)P.nrows) ? 1 : 0) != dense_mode) return;  // (-1: take every result)
 
     const uint32_t ring_addr = smem_u32(dyn_smem) + kComputeWarps * 1024 * 2;  // after the selection vectors
     copy_plan_tables(P, S.filter, S.proj, tid, kComputeThreads + 32);
