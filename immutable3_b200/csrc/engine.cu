@@ -365,6 +365,15 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
         for (int k = 0; k < sp.nfilter; k++)
             if (lp.filters[(size_t)k].col_idx == ci) p.filter_idx = k;
     }
+    // A filter column that is also projected is read again by the emit kernel: ask L2 to keep it if all such
+    // columns together fit in ~2/3 of the 126 MB L2.
+    {
+        int64_t again = 0;
+        for (int i = 0; i < sp.nproj; i++)
+            if (sp.proj[i].filter_idx >= 0) again += t.nrows * sp.filter[sp.proj[i].filter_idx].width;
+        for (int i = 0; i < sp.nproj; i++)
+            if (sp.proj[i].filter_idx >= 0) sp.filter[sp.proj[i].filter_idx].keep_l2 = (again > 0 && again <= (int64_t)84 << 20) ? 1 : 0;
+    }
     sp.npfor = (int)pfor_cols.size();
     for (int i = 0; i < sp.npfor; i++) {
         const ColumnStore& c = t.cols[(size_t)pfor_cols[(size_t)i]];

@@ -59,6 +59,23 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// L2 cache policies for bulk copies: a column that a later kernel reads again is kept (evict_last), a column that
+// is streamed exactly once goes first (evict_first) so that it does not push the former out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_1d_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ uint64_t globaltimer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -1236,7 +1253,10 @@ __device__ void scan_tile_counts(FilterShared& S, const uint32_t* tile_cnt, unsi
 // K1: tile = 8192 rows = 8 spans, one per compute warp.  A producer warp streams the tiles of this CTA (statically
 // strided: no ordering, no tickets) through a TMA ring `ring` tiles deep; the compute warps never synchronise with each
 // other - each evaluates the conjunction on its span, stores its bitmap word and span count, and adds the count to the
-// tile's total in shared memory; the warp that completes a tile writes the tile count.
+// tile's total in shared memory; the warp that completes a tile writes the tile count.  The kernel is issue-bound, so
+// everything that does not depend on the tile is hoisted out of the loop (the single-filter-column case keeps the
+// whole predicate descriptor in registers) and the row-count mask is only built for the table's last tile.
+template <bool STAGED>
 __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const __grid_constant__ ScanPlan P, uint32_t* __restrict__ bitmap,
                                                                            uint32_t* __restrict__ span_cnt, uint32_t* __restrict__ tile_cnt,
                                                                            unsigned long long* __restrict__ tile_off, ScanCtrl* ctrl) {
@@ -1244,8 +1264,7 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
     __shared__ FilterShared S;
     const uint32_t ring_addr = smem_u32(dyn_smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool staged = P.stages > 0;
-    const int ring = staged ? P.stages : 2;
+    const int ring = STAGED ? P.stages : 2;
     const long long ntiles = P.ntiles;
 
     for (int i = tid; i < kLitPoolBytes; i += kComputeThreads + 32) S.lits[i] = P.lits[i];
@@ -1263,19 +1282,22 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
     if (warp == kComputeWarps) {
         // ---------------- producer ----------------
         if (lane == 0) {
+            const uint64_t pol_keep = l2_policy_evict_last();
             RingPos rp;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, rp.advance(ring)) {
                 const int slot = rp.slot;
                 const unsigned use = rp.use;
                 if (use > 0) mbar_wait(smem_u32(&S.mbar_empty[slot]), (use - 1) & 1u, nullptr);
                 const uint32_t bar = smem_u32(&S.mbar_full[slot]);
-                if (staged) {
+                if (STAGED) {
                     mbar_arrive_expect_tx(bar, (uint32_t)P.stage_bytes);
 #pragma unroll 1
                     for (int i = 0; i < P.nfilter; i++) {
                         const FilterCol& f = S.filter[i];
                         const uint32_t bytes = (uint32_t)(kTile * f.width);
-                        tma_load_1d(ring_addr + (uint32_t)slot * (uint32_t)P.stage_bytes + (uint32_t)f.smem_off, f.base + tile * bytes, bytes, bar);
+                        const uint32_t dst = ring_addr + (uint32_t)slot * (uint32_t)P.stage_bytes + (uint32_t)f.smem_off;
+                        if ((P.debug & 8u) || !f.keep_l2) tma_load_1d(dst, f.base + tile * bytes, bytes, bar);
+                        else tma_load_1d_hint(dst, f.base + tile * bytes, bytes, bar, pol_keep);
                     }
                 } else {
                     mbar_arrive(bar);
@@ -1284,24 +1306,35 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
         }
     } else {
         // ---------------- compute warps: warp w = span w of every tile ----------------
+        const int nf = P.nfilter;
+        const FilterCol f0 = S.filter[0];                          // the (very common) single-column predicate lives in registers
+        const int cell = (warp * 1024 + lane * 32) * f0.width;     // this lane's 32 rows inside a tile of column 0
+        const uint8_t* const lits0 = S.lits + f0.lit_off;
+        const long long full_tiles = P.nrows / kTile;              // tiles below this index have no rows past the end
+        uint32_t* bm_w = bitmap + ((long long)blockIdx.x * kComputeWarps + warp) * 32 + lane;
+        uint32_t* sc_w = span_cnt + (long long)blockIdx.x * kComputeWarps + warp;
+        const long long bm_step = (long long)gridDim.x * kComputeWarps * 32, sc_step = (long long)gridDim.x * kComputeWarps;
         RingPos rp;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, rp.advance(ring)) {
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, rp.advance(ring), bm_w += bm_step, sc_w += sc_step) {
             const int slot = rp.slot;
             mbar_wait(smem_u32(&S.mbar_full[slot]), rp.use & 1u, nullptr);
-            const long long tile_row0 = tile * kTile;
             const uint32_t stage_addr = ring_addr + (uint32_t)slot * (uint32_t)P.stage_bytes;
-            const long long left = P.nrows - (tile_row0 + warp * 1024 + lane * 32);
-            uint32_t m = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
-#pragma unroll 1
-            for (int i = 0; i < P.nfilter; i++) {
-                if (staged) dense_eval_filter<1, true>(S.filter[i], S.lits, stage_addr, tile_row0, warp * 1024, lane, &m);
-                else dense_eval_filter<1, false>(S.filter[i], S.lits, stage_addr, tile_row0, warp * 1024, lane, &m);
+            uint32_t m = 0xFFFFFFFFu;
+            if (tile >= full_tiles) {
+                const long long left = P.nrows - (tile * kTile + warp * 1024 + lane * 32);
+                m = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
             }
-            const long long span = tile * kComputeWarps + warp;
-            bitmap[span * 32 + lane] = m;
+            if (nf == 1) {
+                m &= eval_filter_span<STAGED>(stage_addr + (uint32_t)f0.smem_off + (uint32_t)cell, f0.base + tile * (kTile * f0.width) + cell, f0.kind,
+                                              f0.width, f0.lo, f0.span, f0.nlit, lits0, lane);
+            } else {
+#pragma unroll 1
+                for (int i = 0; i < nf; i++) dense_eval_filter<1, STAGED>(S.filter[i], S.lits, stage_addr, tile * kTile, warp * 1024, lane, &m);
+            }
+            *bm_w = m;
             const unsigned c = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(m));
             if (lane == 0) {
-                span_cnt[span] = c;
+                *sc_w = c;
                 // tile total: [31:20] warps arrived, [19:0] rows selected; the eighth arrival publishes and clears
                 const unsigned old = atomicAdd(&S.tile_acc[slot], c + (1u << 20));
                 if ((old >> 20) == kComputeWarps - 1) {
@@ -1511,6 +1544,7 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(co
     if (warp == kComputeWarps) {
         // ---------------- producer ----------------
         if (lane == 0) {
+            const uint64_t pol_stream = l2_policy_evict_first();
             RingPos rp;
             for (long long tile = blockIdx.x;; tile += gridDim.x) {
                 unsigned mode = 0, c = 0;
@@ -1541,7 +1575,10 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(co
                     for (int pc = 0; pc < P.nproj; pc++) {
                         const ProjCol& pj = S.proj[pc];
                         const uint32_t bytes = (uint32_t)(kDenseTileRowsPerWord * pj.width);
-                        tma_load_1d(dst + (uint32_t)kEmitHdrBytes + 8u * (uint32_t)pj.stage_off, pj.base + tile * bytes, bytes, bar);
+                        if ((P.debug & 8u) || pj.filter_idx >= 0)
+                            tma_load_1d(dst + (uint32_t)kEmitHdrBytes + 8u * (uint32_t)pj.stage_off, pj.base + tile * bytes, bytes, bar);
+                        else
+                            tma_load_1d_hint(dst + (uint32_t)kEmitHdrBytes + 8u * (uint32_t)pj.stage_off, pj.base + tile * bytes, bytes, bar, pol_stream);
                     }
                 }
                 rp.advance(ring);
@@ -1644,7 +1681,8 @@ static cudaError_t configure_once() {
         IMM3_SET_SMEM(emit_stream_kernel);
         IMM3_SET_SMEM((scan_dense_kernel<true>));
         IMM3_SET_SMEM((scan_dense_kernel<false>));
-        IMM3_SET_SMEM(filter_kernel);
+        IMM3_SET_SMEM(filter_kernel<true>);
+        IMM3_SET_SMEM(filter_kernel<false>);
 #undef IMM3_SET_SMEM
         return cudaFuncSetAttribute(scan_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     }();
@@ -1674,7 +1712,8 @@ cudaError_t launch_scan_dense(const ScanPlan& plan, ScanCtrl* ctrl, unsigned lon
 cudaError_t filter_kernel_occupancy(size_t dyn_smem, int* blocks_per_sm) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, filter_kernel, kComputeThreads + 32, dyn_smem);
+    if (dyn_smem > 0) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, filter_kernel<true>, kComputeThreads + 32, dyn_smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, filter_kernel<false>, kComputeThreads + 32, dyn_smem);
 }
 cudaError_t emit_kernel_occupancy(int* blocks_per_sm) {
     cudaError_t e = configure_once();
@@ -1685,7 +1724,8 @@ cudaError_t launch_filter(const ScanPlan& plan, uint32_t* bitmap, uint32_t* span
                           ScanCtrl* ctrl, int grid, size_t dyn_smem, cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    filter_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt, tile_off, ctrl);
+    if (plan.stages > 0) filter_kernel<true><<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt, tile_off, ctrl);
+    else filter_kernel<false><<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt, tile_off, ctrl);
     return cudaGetLastError();
 }
 cudaError_t launch_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* span_cnt, const unsigned long long* tile_off,

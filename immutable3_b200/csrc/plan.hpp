@@ -42,6 +42,8 @@ struct FilterCol {
     int32_t lit_off;      // ... at lits[lit_off]
     int32_t smem_off;     // dense kernel: byte offset of this column's tile inside a stage, -1 = read from global
     int32_t pfor_slot;    // block kernel: index into ScanPlan::pfor, -1 = dense column
+    int32_t keep_l2;      // multi-pass: the column is projected too and small enough to stay in L2 until the emit kernel
+    int32_t pad;
 };
 
 struct ProjCol {
