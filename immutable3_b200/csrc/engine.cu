@@ -273,6 +273,9 @@ struct Prepared {
     LogicalPlan lp;
     bool block_mode = false;
     bool multipass = false;   // dense tables: filter -> scan -> emit kernels instead of the fused single pass
+    bool blocks_multi = false;  // block mode: warp-per-block filter kernel -> offset scan -> emit kernel (no look-back chain)
+    bool for_bitmap = false;    // imm3_filter_bitmap: the canonical-row bitmap comes from the single-pass kernels
+    int grid_blocks_emit = 0;
     int grid_emit = 0;
     int grid_emit_stream = 0, emit_stage_bytes = 0, emit_ring = 0;  // streaming emit kernel (dense results); 0 = not usable
     size_t emit_smem = 0;
@@ -392,9 +395,23 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
         if (t.max_block_rows > kMaxBlockRows)
             return fail(IMM3_ERR_UNSUPPORTED, "block-mode kernel stages blocks of at most %d rows, table %s has a block of %d",
                         kMaxBlockRows, t.meta.name.c_str(), t.max_block_rows);
-        sp.ntiles = t.nblocks;
-        pr->dyn_smem = blocks_kernel_smem_bytes(sp.npfor, t.max_block_rows);
-        CUDA_TRY(blocks_kernel_occupancy(pr->dyn_smem, &occ));
+        const char* path = getenv("IMM3_PATH");
+        pr->blocks_multi = !pr->for_bitmap && t.max_block_rows <= 1024 && (lp.limit <= 0 || lp.limit > (1 << 20)) &&
+                           !(path && !strcmp(path, "fused"));
+        if (pr->blocks_multi) {
+            sp.ntiles = (t.nblocks + 7) / 8;  // the offset scan works on tiles of 8 blocks
+            int64_t cap = 0;  // per-warp scratch for the byte-swapped words of one encoded block
+            for (int ci : pfor_cols) cap = std::max<int64_t>(cap, t.cols[(size_t)ci].max_block_words);
+            sp.blk_words_cap = (int)std::min<int64_t>(1120, ((cap + 4 + 31) / 32) * 32);
+            pr->dyn_smem = blocks_multi_smem_bytes(sp.npfor, sp.blk_words_cap);
+            int occ_e = 0;
+            CUDA_TRY(blocks_multi_occupancy(pr->dyn_smem, &occ, &occ_e));
+            pr->grid_blocks_emit = (int)std::max<int64_t>(1, std::min<int64_t>(sp.ntiles, (int64_t)db->num_sms * std::max(1, occ_e)));
+        } else {
+            sp.ntiles = t.nblocks;
+            pr->dyn_smem = blocks_kernel_smem_bytes(sp.npfor, t.max_block_rows);
+            CUDA_TRY(blocks_kernel_occupancy(pr->dyn_smem, &occ));
+        }
     } else {
         int row_bytes = 0;
         for (int i = 0; i < sp.nfilter; i++) row_bytes += sp.filter[i].width;
@@ -519,7 +536,29 @@ int ensure_buf(Buf* b, size_t bytes) {
 // Launch the kernels of one query and wait for the match count.
 int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launches, double* stage_ms = nullptr) {
     bool have_mid = false;
-    if (pr->multipass) {
+    if (pr->block_mode && pr->blocks_multi) {
+        TableStore& t = *pr->table;
+        const int64_t nblocks = t.nblocks, ntiles = pr->sp.ntiles;
+        int rc;
+        if ((rc = ensure_buf(&db->d_bitmap, (size_t)(nblocks * 32 + 2) * 4))) return rc;
+        if ((rc = ensure_buf(&db->d_span_cnt, (size_t)(nblocks + 8) * 4))) return rc;
+        const size_t ntiles_pad = ((size_t)ntiles + 4095) / 4096 * 4096 + 16;  // whole rounds of the offset scan
+        if ((rc = ensure_buf(&db->d_tile_cnt, ntiles_pad * 4))) return rc;
+        if ((rc = ensure_buf(&db->d_tile_off, ntiles_pad * 8))) return rc;
+        CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
+        CUDA_TRY(cudaMemsetAsync(db->d_tile_cnt.p, 0, (size_t)ntiles * 4, db->stream));  // K1b accumulates the tile counts with atomics
+        CUDA_TRY(launch_blocks_filter(pr->sp, (uint32_t*)db->d_bitmap.p, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
+                                      (unsigned long long*)db->d_tile_off.p, db->d_ctrl, nblocks, pr->grid, pr->dyn_smem, db->stream));
+        *launches = 1;
+        CUDA_TRY(cudaEventRecord(db->ev_mid, db->stream));
+        have_mid = true;
+        if (pr->sp.nproj > 0) {
+            CUDA_TRY(launch_blocks_emit(pr->sp, (const uint32_t*)db->d_bitmap.p, (const uint32_t*)db->d_span_cnt.p,
+                                        (const unsigned long long*)db->d_tile_off.p, nblocks, pr->grid_blocks_emit, pr->dyn_smem, db->stream));
+            (*launches)++;
+        }
+        CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
+    } else if (pr->multipass) {
         const int64_t tile_rows = (int64_t)kDenseTileRowsPerWord * pr->sp.words_per_lane;
         const int64_t ntiles = pr->sp.ntiles, nspans = ntiles * (tile_rows / 1024);
         const int64_t nsub = ntiles * pr->sp.words_per_lane;  // 8192-row sub-tiles: the unit of the offset scan
@@ -933,6 +972,7 @@ int imm3_filter_bitmap(imm3_db* db, const char* table, const imm3_pred* preds, i
     CUDA_TRY(cudaMemsetAsync(db->d_bitmap.p, 0, need_words * 4, db->stream));
     int64_t total = 0;
     if (!pr.lp.always_empty && t.nrows > 0) {
+        pr.for_bitmap = true;
         if ((rc = fill_scan_plan(db, &pr))) return rc;
         pr.sp.bitmap = (uint32_t*)db->d_bitmap.p;
         pr.sp.limit = INT64_MAX;

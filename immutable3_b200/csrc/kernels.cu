@@ -1480,6 +1480,308 @@ __global__ void __launch_bounds__(kComputeThreads, IMM3_EMIT_MIN_BLOCKS) emit_ke
     }
 }
 
+// =============================================================================================
+// Block-mode multi-pass pipeline (tables with blocks of <= 1024 rows; the sorted-integer codec's normal case)
+//
+//   K1b blocks_filter_kernel : one WARP per reference block (tile = 8 consecutive blocks = one CTA iteration).  The warp
+//                              decodes the block of every PFOR_INT filter column in shared memory (lane m unpacks
+//                              mini-block m: 32 funnel-shift extractions with a running delta sum; a segmented warp scan
+//                              chains the mini-blocks, b = 32 mini-blocks restart the chain), evaluates the conjunction
+//                              row-per-lane (ballot = one bitmap word per 32 rows) and stores the block's 32 bitmap
+//                              words (block-local alignment), its match count, and the tile count.  The last CTA turns
+//                              tile counts into offsets (same scan as the dense pipeline).
+//   K3b blocks_emit_kernel   : one warp per NON-EMPTY block: offset = tile offset + counts of the tile's earlier blocks;
+//                              PFOR columns of the select list are decoded again (only for blocks with matches - 1 % of
+//                              them for C4), rows are emitted word by word: rank = popc(word & lanemask_lt).
+// No look-back chain: the old single-pass block kernel spent 13 ns per block on it (97.6 K blocks per 100 M rows).
+// =============================================================================================
+constexpr int kBlkRows = 1024;        // largest block this pipeline takes
+constexpr int kBlkWordsCap = 1120;    // byte-swapped words of one encoded block: count + 8 headers + 1024 + var-byte tail
+__host__ __device__ constexpr int blk_warp_smem_words(int npfor, int words_cap) { return words_cap + npfor * kBlkRows; }
+
+__device__ __forceinline__ int sw_idx(int m, int j) { return m * 32 + ((j + m) & 31); }  // bank-conflict-free either way
+
+// Decode one PFOR_INT block (n <= 1024 values) by one warp.  vals[sw_idx(m, j)] + base(m) = value 32m+j,
+// where base(m) is returned in lane m (mini-block-local prefix sums are stored; raw b = 32 mini-blocks and the
+// var-byte tail store absolute values with base 0).
+__device__ __forceinline__ uint32_t pfor_decode_warp(const uint32_t* __restrict__ words, uint32_t w0, uint32_t w1, int n, uint32_t* Wb,
+                                                     int words_cap, uint32_t* vals, int lane) {
+    int nw = (int)(w1 - w0) - 2;  // PFORCodecInt.encode appends 8 zero bytes (PFORCodec.scala:20)
+    if (nw > words_cap - 2) nw = words_cap - 2;
+    for (int i = lane; i < nw; i += 32) Wb[i] = __byte_perm(__ldg(words + w0 + i), 0, 0x0123);  // putInt is big-endian
+    __syncwarp();
+    const int packed = n & ~31, nmini = packed >> 5;
+    // header walk (every lane, uniformly): one word per 128-value super-block, then one per left-over mini-block
+    int ip = 1, mypos = 0, mybits = 0, m = 0, s = 0;
+    for (; s + 128 <= packed; s += 128) {
+        const uint32_t h = Wb[ip++];
+#pragma unroll
+        for (int q = 0; q < 4; q++, m++) {
+            const int b = (int)((h >> (24 - 8 * q)) & 0xFFu);
+            if (m == lane) { mypos = ip; mybits = b; }
+            ip += b;
+        }
+    }
+    for (; s < packed; s += 32, m++) {
+        const int b = (int)Wb[ip++];
+        if (m == lane) { mypos = ip; mybits = b; }
+        ip += b;
+    }
+    // mini-block `lane`: 32 values
+    uint32_t total = 0;
+    const bool raw = mybits >= 32;
+    if (lane < nmini) {
+        if (raw) {
+            for (int j = 0; j < 32; j++) vals[sw_idx(lane, j)] = total = Wb[mypos + j];
+        } else {
+            const uint32_t mask = (1u << mybits) - 1u;
+            int off = 0;
+            for (int j = 0; j < 32; j++, off += mybits) {
+                const int wi = mypos + (off >> 5), sh = off & 31;
+                const uint32_t d = __funnelshift_r(Wb[wi], Wb[wi + 1], sh) & mask;
+                total += d;
+                vals[sw_idx(lane, j)] = total;
+            }
+        }
+    }
+    // chain the mini-blocks: carry(m) = raw ? last raw value : carry(m-1) + total   (segmented inclusive scan)
+    uint32_t v = lane < nmini ? total : 0u;
+    unsigned f = (lane < nmini && raw) ? 1u : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t pv = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        const unsigned pf = __shfl_up_sync(0xFFFFFFFFu, f, o);
+        if (lane >= o) {
+            if (!f) v += pv;
+            f |= pf;
+        }
+    }
+    uint32_t base = __shfl_up_sync(0xFFFFFFFFu, v, 1);  // carry after the previous mini-block
+    if (lane == 0) base = 0;                             // initvalue = 0 at every block
+    uint32_t carry_tail = __shfl_sync(0xFFFFFFFFu, v, (nmini + 31) & 31);  // carry after the last packed mini-block
+    if (nmini == 0) carry_tail = 0;
+    if (raw || lane >= nmini) base = 0;
+    // var-byte remainder (n % 32 values): 7-bit groups, low first, the last byte of a value has bit 7 set
+    if (n > packed && lane == 0) {
+        int wp = ip, shb = 0, shift = 0;
+        uint32_t acc = 0, cur = carry_tail;
+        for (int k = packed; k < n;) {
+            const uint32_t c = Wb[wp] >> shb;
+            shb += 8;
+            wp += shb >> 5;
+            shb &= 31;
+            acc += (c & 127u) << shift;
+            if (c & 128u) {
+                cur += acc;
+                vals[sw_idx(nmini, k - packed)] = cur;
+                k++;
+                acc = 0;
+                shift = 0;
+            } else {
+                shift += 7;
+            }
+        }
+    }
+    __syncwarp();
+    return base;
+}
+
+__global__ void __launch_bounds__(kComputeThreads, 3) blocks_filter_kernel(const __grid_constant__ ScanPlan P, uint32_t* __restrict__ bitmapB,
+                                                                             uint32_t* __restrict__ blk_cnt, uint32_t* __restrict__ tile_cnt,
+                                                                             unsigned long long* __restrict__ tile_off, ScanCtrl* ctrl,
+                                                                             long long nblocks) {
+    __shared__ FilterShared S;
+    __shared__ PforCol s_pfor[kMaxPforCols];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < kLitPoolBytes; i += kComputeThreads) S.lits[i] = P.lits[i];
+    copy_plan_tables(P, S.filter, S.proj, tid, kComputeThreads);
+    if (tid < kMaxPforCols) {
+#pragma unroll
+        for (int i = 0; i < kMaxPforCols; i++)
+            if (tid == i) s_pfor[i] = P.pfor[i];
+    }
+    __syncthreads();
+    uint32_t* const Wb = reinterpret_cast<uint32_t*>(dyn_smem) + warp * blk_warp_smem_words(P.npfor, P.blk_words_cap);
+    uint32_t* const vals0 = Wb + P.blk_words_cap;
+    const long long ntiles = P.ntiles;  // tiles of 8 blocks
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long blk = tile * kComputeWarps + warp;
+        uint32_t myword = 0;  // lane w keeps bitmap word w of the block
+        unsigned cnt = 0;
+        if (blk < nblocks) {
+            // block metadata in ONE round trip: lanes 0,1 = row ordinals, lanes 2+2s, 3+2s = word offsets of PFOR slot s
+            unsigned long long meta = 0;
+            if (lane < 2) meta = P.row_start[blk + lane];
+            else if (lane < 2 + 2 * P.npfor) meta = s_pfor[(lane - 2) >> 1].word_off[blk + (lane & 1)];
+            const long long R0 = (long long)__shfl_sync(0xFFFFFFFFu, meta, 0);
+            const int n = (int)((long long)__shfl_sync(0xFFFFFFFFu, meta, 1) - R0);
+            uint32_t wo0[kMaxPforCols], wo1[kMaxPforCols];
+#pragma unroll
+            for (int s = 0; s < kMaxPforCols; s++) {
+                wo0[s] = (uint32_t)__shfl_sync(0xFFFFFFFFu, meta, 2 + 2 * s);
+                wo1[s] = (uint32_t)__shfl_sync(0xFFFFFFFFu, meta, 3 + 2 * s);
+            }
+            uint32_t base[kMaxPforCols];
+#pragma unroll
+            for (int s = 0; s < kMaxPforCols; s++) {
+                base[s] = 0;
+                if (s < P.npfor) {
+                    bool used = false;
+                    for (int fi = 0; fi < P.nfilter; fi++) used = used || S.filter[fi].pfor_slot == s;
+                    if (used) base[s] = pfor_decode_warp(s_pfor[s].words, wo0[s], wo1[s], n, Wb, P.blk_words_cap, vals0 + s * kBlkRows, lane);
+                }
+            }
+            const int nwords = (n + 31) >> 5;
+            {   // rows of the block that exist: lane w owns word w = rows [32w, 32w+32)
+                const int left = n - lane * 32;
+                myword = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+            }
+#pragma unroll 1
+            for (int fi = 0; fi < P.nfilter; fi++) {
+                const FilterCol f = S.filter[fi];
+                if (f.kind == kFilterI32Range && f.pfor_slot >= 0) {
+                    // decoded column: lane m tests its own mini-block (the values it just unpacked) - no ballots
+                    uint32_t b = 0;
+#pragma unroll
+                    for (int s = 0; s < kMaxPforCols; s++)
+                        if (s == f.pfor_slot) b = base[s];
+                    const uint32_t* vp = vals0 + f.pfor_slot * kBlkRows + lane * 32;
+                    const uint32_t lo = (uint32_t)f.lo - b;
+                    uint32_t word = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) word |= (uint32_t)((vp[(j + lane) & 31] - lo) <= f.span) << j;
+                    myword &= word;
+                } else {
+                    // dense column: row per lane (coalesced), one ballot per 32 rows
+                    for (int w = 0; w < nwords; w++) {
+                        const int i = w * 32 + lane;
+                        bool pass = i < n;
+                        if (f.kind == kFilterI32Range) {
+                            const uint32_t v = pass ? __ldg(reinterpret_cast<const uint32_t*>(f.base) + R0 + i) : 0u;
+                            pass = pass && ((v - (uint32_t)f.lo) <= f.span);
+                        } else if (f.kind == kFilterI8Range) {
+                            const int v = pass ? (int)(signed char)__ldg(f.base + R0 + i) : 0;
+                            pass = pass && ((uint32_t)(v - f.lo) <= f.span);
+                        } else {
+                            bool hit = false;
+                            if (pass) {
+                                const uint8_t* cell = f.base + (R0 + i) * f.width;
+                                for (int l = 0; l < f.nlit && !hit; l++) {
+                                    bool eq = true;
+                                    for (int bb = 0; bb < f.width; bb++) eq = eq && (__ldg(cell + bb) == S.lits[f.lit_off + l * f.width + bb]);
+                                    hit = eq;
+                                }
+                            }
+                            pass = hit;
+                        }
+                        const uint32_t word = __ballot_sync(0xFFFFFFFFu, pass);
+                        if (lane == w) myword &= word;
+                    }
+                }
+            }
+            bitmapB[blk * 32 + lane] = myword;
+            cnt = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(myword));
+            if (lane == 0) blk_cnt[blk] = cnt;
+        }
+        if (lane == 0 && cnt) atomicAdd(tile_cnt + tile, cnt);  // (the host zeroes the tile counts before the launch)
+    }
+
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(&ctrl->exited, 1u);
+        S.is_last = prev == gridDim.x - 1;
+        if (S.is_last) ctrl->exited = 0;
+    }
+    __syncthreads();
+    if (S.is_last) {
+        __threadfence();
+        scan_tile_counts(S, tile_cnt, tile_off, ntiles, P.limit, ctrl);
+    }
+}
+
+__global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const __grid_constant__ ScanPlan P, const uint32_t* __restrict__ bitmapB,
+                                                                           const uint32_t* __restrict__ blk_cnt,
+                                                                           const unsigned long long* __restrict__ tile_off, long long nblocks) {
+    __shared__ ProjCol s_proj[kMaxProjCols];
+    __shared__ FilterCol s_filter[kMaxFilterCols];
+    __shared__ PforCol s_pfor[kMaxPforCols];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    copy_plan_tables(P, s_filter, s_proj, tid, kComputeThreads);
+    if (tid < kMaxPforCols) {
+#pragma unroll
+        for (int i = 0; i < kMaxPforCols; i++)
+            if (tid == i) s_pfor[i] = P.pfor[i];
+    }
+    __syncthreads();
+    uint32_t* const Wb = reinterpret_cast<uint32_t*>(dyn_smem) + warp * blk_warp_smem_words(P.npfor, P.blk_words_cap);
+    uint32_t* const vals0 = Wb + P.blk_words_cap;
+    const long long warp0 = (long long)blockIdx.x * kComputeWarps + warp, nwarps = (long long)gridDim.x * kComputeWarps;
+    for (long long blk = warp0; blk < nblocks; blk += nwarps) {
+        const long long t8 = blk & ~7ll;
+        const unsigned c = (lane < 8 && t8 + lane < nblocks) ? __ldg(blk_cnt + t8 + lane) : 0u;  // the tile's block counts
+        const unsigned mine = __shfl_sync(0xFFFFFFFFu, c, (int)(blk & 7));
+        if (mine == 0) continue;
+        long long g = (long long)__ldg(tile_off + (blk >> 3)) + __reduce_add_sync(0xFFFFFFFFu, lane < (int)(blk & 7) ? c : 0u);
+        if (g >= P.limit) continue;
+        const uint32_t myword = __ldg(bitmapB + blk * 32 + lane);
+        unsigned long long meta = 0;
+        if (lane < 2) meta = P.row_start[blk + lane];
+        else if (lane < 2 + 2 * P.npfor) meta = s_pfor[(lane - 2) >> 1].word_off[blk + (lane & 1)];
+        const long long R0 = (long long)__shfl_sync(0xFFFFFFFFu, meta, 0);
+        const int n = (int)((long long)__shfl_sync(0xFFFFFFFFu, meta, 1) - R0);
+        uint32_t wo0[kMaxPforCols], wo1[kMaxPforCols];
+#pragma unroll
+        for (int s = 0; s < kMaxPforCols; s++) {
+            wo0[s] = (uint32_t)__shfl_sync(0xFFFFFFFFu, meta, 2 + 2 * s);
+            wo1[s] = (uint32_t)__shfl_sync(0xFFFFFFFFu, meta, 3 + 2 * s);
+        }
+        uint32_t base[kMaxPforCols];
+#pragma unroll
+        for (int s = 0; s < kMaxPforCols; s++) {
+            base[s] = 0;
+            if (s < P.npfor) {
+                bool used = false;
+                for (int pc = 0; pc < P.nproj; pc++) used = used || s_proj[pc].pfor_slot == s;
+                if (used) base[s] = pfor_decode_warp(s_pfor[s].words, wo0[s], wo1[s], n, Wb, P.blk_words_cap, vals0 + s * kBlkRows, lane);
+            }
+        }
+        const int nwords = (n + 31) >> 5;
+        for (int w = 0; w < nwords; w++) {
+            const uint32_t word = __shfl_sync(0xFFFFFFFFu, myword, w);
+            if (word == 0) continue;  // warp-uniform
+            const bool sel = (word >> lane) & 1u;
+            const long long dst = g + __popc(word & ((1u << lane) - 1u));
+            const int i = w * 32 + lane;
+#pragma unroll 1
+            for (int pc = 0; pc < P.nproj; pc++) {
+                const ProjCol& pj = s_proj[pc];
+                if (pj.pfor_slot >= 0) {
+                    uint32_t b = 0;
+#pragma unroll
+                    for (int s = 0; s < kMaxPforCols; s++)
+                        if (s == pj.pfor_slot) b = base[s];
+                    const uint32_t v = vals0[pj.pfor_slot * kBlkRows + sw_idx(w, lane)] + __shfl_sync(0xFFFFFFFFu, b, w);
+                    if (sel && dst < P.limit) reinterpret_cast<uint32_t*>(pj.out)[dst] = v;
+                } else if (sel && dst < P.limit) {
+                    if (pj.width == 4) {
+                        reinterpret_cast<uint32_t*>(pj.out)[dst] = __ldg(reinterpret_cast<const uint32_t*>(pj.base) + R0 + i);
+                    } else if (pj.width == 1) {
+                        pj.out[dst] = __ldg(pj.base + R0 + i);
+                    } else {
+                        const uint8_t* src = pj.base + (R0 + i) * pj.width;
+                        uint8_t* o = pj.out + dst * pj.width;
+                        for (int b = 0; b < pj.width; b++) o[b] = __ldg(src + b);
+                    }
+                }
+            }
+            g += __popc(word);
+        }
+        __syncwarp();  // the next block reuses the warp's shared-memory scratch
+    }
+}
+
 // K3, dense results: a persistent TMA-ring kernel.  Tile = 8192 rows (8 spans, one per compute warp).  The producer
 // warp knows every tile's match count and offset before it starts (K1 finished), so it prefetches, `ring` tiles
 // ahead, exactly what the tile needs: its 256 bitmap words and 8 span counts, plus - for a tile with at least
@@ -1679,6 +1981,8 @@ static cudaError_t configure_once() {
         cudaError_t e = cudaSuccess;
 #define IMM3_SET_SMEM(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e
         IMM3_SET_SMEM(emit_stream_kernel);
+        IMM3_SET_SMEM(blocks_filter_kernel);
+        IMM3_SET_SMEM(blocks_emit_kernel);
         IMM3_SET_SMEM((scan_dense_kernel<true>));
         IMM3_SET_SMEM((scan_dense_kernel<false>));
         IMM3_SET_SMEM(filter_kernel<true>);
@@ -1748,6 +2052,29 @@ cudaError_t launch_emit_stream(const ScanPlan& plan, const uint32_t* bitmap, con
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
     emit_stream_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt, tile_off, nsub, ring, stage_bytes, dense_mode);
+    return cudaGetLastError();
+}
+
+size_t blocks_multi_smem_bytes(int npfor, int words_cap) { return (size_t)kComputeWarps * blk_warp_smem_words(npfor, words_cap) * 4; }
+cudaError_t blocks_multi_occupancy(size_t dyn_smem, int* filter_blocks_per_sm, int* emit_blocks_per_sm) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(filter_blocks_per_sm, blocks_filter_kernel, kComputeThreads, dyn_smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(emit_blocks_per_sm, blocks_emit_kernel, kComputeThreads, dyn_smem);
+}
+cudaError_t launch_blocks_filter(const ScanPlan& plan, uint32_t* bitmapB, uint32_t* blk_cnt, uint32_t* tile_cnt, unsigned long long* tile_off,
+                                 ScanCtrl* ctrl, long long nblocks, int grid, size_t dyn_smem, cudaStream_t stream) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    blocks_filter_kernel<<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks);
+    return cudaGetLastError();
+}
+cudaError_t launch_blocks_emit(const ScanPlan& plan, const uint32_t* bitmapB, const uint32_t* blk_cnt, const unsigned long long* tile_off,
+                               long long nblocks, int grid, size_t dyn_smem, cudaStream_t stream) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    blocks_emit_kernel<<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_off, nblocks);
     return cudaGetLastError();
 }
 

@@ -200,6 +200,9 @@ static int load_table(const std::string& data_dir, const std::string& dir_name, 
             base += sf.nbytes;
         }
         col.word_off.push_back((uint32_t)(base / 4));
+        col.max_block_words = 0;
+        for (size_t b = 0; b + 1 < col.word_off.size(); b++)
+            col.max_block_words = std::max<int64_t>(col.max_block_words, (int64_t)col.word_off[b + 1] - (int64_t)col.word_off[b]);
         if (base / 4 > 0xFFFFFFFFll) return fail(IMM3_ERR_UNSUPPORTED, "PFOR_INT column %s exceeds 16 GiB per GPU", col.meta.name.c_str());
     }
     return 0;

@@ -19,6 +19,7 @@ struct ColumnStore {
     uint8_t* h_mirror = nullptr;     // pinned copy of the slice (IMM3_OPEN_KEEP_HOST)
     std::vector<uint32_t> word_off;  // PFOR_INT: nblocks+1 offsets in 32-bit words into the arena
     uint32_t* d_word_off = nullptr;
+    int64_t max_block_words = 0;     // PFOR_INT: largest encoded block, in 32-bit words
 };
 
 struct TableStore {
