@@ -22,6 +22,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "kernels.hpp"
@@ -115,6 +116,10 @@ struct imm3_db {
     Buf d_bitmap, h_bitmap;
     Buf d_span_cnt, d_tile_cnt, d_tile_off;  // multi-pass pipeline scratch (grow-only)
     Buf d_trace;                             // IMM3_TRACE debugging buffer
+    // Emit-kernel feedback: result density class (1 dense, 0 sparse) last seen for a query shape (table, filter
+    // columns and kinds, select list).  A known class launches only the matching emit kernel; both kernels are correct
+    // for any result, so a stale hint costs time, never rows.
+    std::unordered_map<std::string, int> emit_hint;
     std::string explain_buf;
 };
 
@@ -278,6 +283,7 @@ struct Prepared {
     int grid_blocks_emit = 0;
     int grid_emit = 0;
     int grid_emit_stream = 0, emit_stage_bytes = 0, emit_ring = 0;  // streaming emit kernel (dense results); 0 = not usable
+    std::string shape_key;    // key of imm3_db::emit_hint
     size_t emit_smem = 0;
     ScanPlan sp;
     size_t dyn_smem = 0;
@@ -312,6 +318,10 @@ int prepare(imm3_db* db, const char* table, const imm3_pred* preds, int npreds, 
     if (rc) return rc;
     kernel_name(db, *pr->table, pr->lp, &pr->block_mode);
     pr->multipass = choose_multipass(pr->lp, pr->block_mode);
+    pr->shape_key = pr->table->meta.name + "|";
+    for (auto& f : pr->lp.filters) pr->shape_key += std::to_string(f.col_idx) + ":" + std::to_string(f.kind) + ",";
+    pr->shape_key += "|";
+    for (int c : pr->lp.proj) pr->shape_key += std::to_string(c) + ",";
     return 0;
 }
 
@@ -580,17 +590,24 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
         if (pr->sp.nproj > 0) {
             // Two emit kernels, one of which does the work: which one is decided on the device from the match count.
             const int stream_ok = pr->emit_stage_bytes > 0;
-            const char* force = getenv("IMM3_EMIT");  // experiment: "stream" = the streaming kernel takes every result
-            const bool only_stream = stream_ok && force && !strcmp(force, "stream");
-            if (stream_ok) {
+            const char* force = getenv("IMM3_EMIT");  // experiment: "stream" / "gather" = that kernel takes every result, "both" = no feedback
+            int hint = -1;
+            if (stream_ok && !(force && !strcmp(force, "both"))) {
+                auto it = db->emit_hint.find(pr->shape_key);
+                if (it != db->emit_hint.end()) hint = it->second;
+                if (force && !strcmp(force, "stream")) hint = 1;
+                if (force && !strcmp(force, "gather")) hint = 0;
+            }
+            const bool only_stream = stream_ok && hint == 1, only_gather = stream_ok && hint == 0;
+            if (stream_ok && !only_gather) {
                 CUDA_TRY(launch_emit_stream(pr->sp, pr->sp.bitmap, (const uint32_t*)db->d_span_cnt.p, (const uint32_t*)db->d_tile_cnt.p,
                                             (const unsigned long long*)db->d_tile_off.p, nsub, pr->emit_ring, pr->emit_stage_bytes,
-                                            only_stream ? -1 : 1, pr->grid_emit_stream, pr->emit_smem, db->stream));
+                                            only_stream ? -1 : 1, pr->grid_emit_stream, pr->emit_smem, db->d_ctrl, db->stream));
                 (*launches)++;
             }
             if (!only_stream) {
                 CUDA_TRY(launch_emit(pr->sp, pr->sp.bitmap, (const uint32_t*)db->d_span_cnt.p, (const unsigned long long*)db->d_tile_off.p, 8,
-                                     nspans, pr->grid_emit, stream_ok, db->stream));
+                                     nspans, pr->grid_emit, stream_ok && !only_gather, db->d_ctrl, db->stream));
                 (*launches)++;
             }
         }
@@ -626,6 +643,8 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
         }
     }
     *total = (int64_t)db->h_ctrl->total;
+    if (pr->multipass && pr->sp.nproj > 0 && pr->emit_stage_bytes > 0)  // feedback for the next query of this shape
+        db->emit_hint[pr->shape_key] = (db->h_ctrl->total > 0 && db->h_ctrl->dense_rows * 2 >= db->h_ctrl->total) ? 1 : 0;
     if (pr->sp.trace) {
         std::vector<unsigned long long> h((size_t)pr->sp.ntiles * 8);
         CUDA_TRY(cudaMemcpy(h.data(), pr->sp.trace, h.size() * 8, cudaMemcpyDeviceToHost));

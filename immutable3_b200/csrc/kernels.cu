@@ -1199,9 +1199,10 @@ struct FilterShared {
 // loads its 16 consecutive counts with four independent 128-bit loads (the arrays are padded to whole rounds),
 // one block-wide scan per round.  LIMIT clamp of the total.
 __device__ void scan_tile_counts(FilterShared& S, const uint32_t* tile_cnt, unsigned long long* tile_off, long long ntiles,
-                                 long long limit, ScanCtrl* ctrl) {
+                                 long long limit, ScanCtrl* ctrl, int dense_tile_rows = kDenseTileRowsPerWord) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long running = 0;
+    unsigned long long dense = 0;  // rows selected in tiles with at least one selected row in 32 (this thread's share)
     for (long long base = 0; base < ntiles; base += kComputeThreads * 16) {
         const long long i0 = base + tid * 16;
         uint4 v[4];
@@ -1214,6 +1215,7 @@ __device__ void scan_tile_counts(FilterShared& S, const uint32_t* tile_cnt, unsi
         for (int k = 0; k < 16; k++) {
             if (i0 + k >= ntiles) c[k] = 0;  // padding holds stale counts
             sum += c[k];
+            dense += c[k] * 32u >= (unsigned)dense_tile_rows ? c[k] : 0u;
         }
         unsigned incl = sum;
 #pragma unroll
@@ -1243,7 +1245,9 @@ __device__ void scan_tile_counts(FilterShared& S, const uint32_t* tile_cnt, unsi
         }
         running += total;
     }
+    if (tid == 0) ctrl->dense_rows = 0;
     bar_sync(1, kComputeThreads);
+    if (dense) atomicAdd(&ctrl->dense_rows, dense);
     if (tid == 0) {
         tile_off[ntiles] = running;
         ctrl->total = running < (unsigned long long)limit ? running : (unsigned long long)limit;
@@ -1362,6 +1366,13 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
     }
 }
 
+// Result class decided by K1's offset scan: dense = at least half of the selected rows live in tiles with >= 1 selected
+// row in 32 (those tiles are streamed); otherwise the rows are thinly spread and the gather kernel is the better fit.
+__device__ __forceinline__ int emit_class_dense(const ScanCtrl* ctrl) {
+    const unsigned long long total = __ldcg(&ctrl->total), dense = __ldcg(&ctrl->dense_rows);
+    return (total > 0 && dense * 2ull >= total) ? 1 : 0;
+}
+
 // K3.  Two mappings, chosen on the device from the total match count:
 //  * dense results (>= 32 surviving rows per span on average): one warp per 1024-row span - maximum
 //    parallelism, every span's three metadata loads issued together;
@@ -1371,7 +1382,7 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
 __global__ void __launch_bounds__(kComputeThreads, IMM3_EMIT_MIN_BLOCKS) emit_kernel(const __grid_constant__ ScanPlan P, const uint32_t* __restrict__ bitmap,
                                                                  const uint32_t* __restrict__ span_cnt,
                                                                  const unsigned long long* __restrict__ tile_off, int spans_per_tile,
-                                                                 long long nspans, int dense_off) {
+                                                                 long long nspans, int dense_off, const ScanCtrl* ctrl) {
     __shared__ struct { FilterCol filter[kMaxFilterCols]; ProjCol proj[kMaxProjCols]; } SE;
     copy_plan_tables(P, SE.filter, SE.proj, threadIdx.x, kComputeThreads);
     __syncthreads();
@@ -1379,7 +1390,7 @@ __global__ void __launch_bounds__(kComputeThreads, IMM3_EMIT_MIN_BLOCKS) emit_ke
     unsigned short* sel_w = reinterpret_cast<unsigned short*>(dyn_smem) + warp * 1024;
     const long long ntiles = (nspans + spans_per_tile - 1) / spans_per_tile;
     const unsigned long long total = __ldg(tile_off + ntiles);
-    if (dense_off && total * 32ull >= (unsigned long long)P.nrows) return;  // the streaming emit kernel takes dense results
+    if (dense_off && emit_class_dense(ctrl)) return;  // the streaming emit kernel takes dense results
     const long long warp0 = (long long)blockIdx.x * kComputeWarps + warp, nwarps = (long long)gridDim.x * kComputeWarps;
 
     if (total >= (unsigned long long)nspans * 32ull) {
@@ -1824,12 +1835,11 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(co
                                                                                 const uint32_t* __restrict__ span_cnt,
                                                                                 const uint32_t* __restrict__ tile_cnt,
                                                                                 const unsigned long long* __restrict__ tile_off, long long nsub,
-                                                                                int ring, int stage_bytes, int dense_mode) {
+                                                                                int ring, int stage_bytes, int dense_mode, const ScanCtrl* ctrl) {
     __shared__ EmitShared S;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // One of the two emit kernels does the work, picked on the device from the match count (no host round trip).
-    const unsigned long long total = __ldcg(tile_off + nsub);
-    if (dense_mode >= 0 && ((total * 32ull >= (unsigned long long)P.nrows) ? 1 : 0) != dense_mode) return;  // (-1: take every result)
+    if (dense_mode >= 0 && emit_class_dense(ctrl) != dense_mode) return;  // (-1: take every result)
 
     const uint32_t ring_addr = smem_u32(dyn_smem) + kComputeWarps * 1024 * 2;  // after the selection vectors
     copy_plan_tables(P, S.filter, S.proj, tid, kComputeThreads + 32);
@@ -1889,6 +1899,8 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(co
     } else {
         // ---------------- compute warps: warp w = span w of every tile ----------------
         unsigned short* sel_w = reinterpret_cast<unsigned short*>(dyn_smem) + warp * 1024;
+        bool fast_sparse = P.nproj <= 4;  // sparse tiles: fused multi-column gather (widths 1, 2, 4)
+        for (int pc = 0; pc < P.nproj && pc < 4; pc++) fast_sparse = fast_sparse && (S.proj[pc].width == 4 || S.proj[pc].width == 2 || S.proj[pc].width == 1);
         for (RingPos rp;; rp.advance(ring)) {
             const int slot = rp.slot;
             mbar_wait(smem_u32(&S.mbar_full[slot]), rp.use & 1u, nullptr);
@@ -1948,6 +1960,33 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(co
                                     for (int k = 0; k < 4; k++)
                                         if (r[k] != 0xFFFFFFFFu)
                                             for (int b = 0; b < w; b++) ob[(32 * k) * w + b] = (uint8_t)lds_u8(sb + r[k] * (uint32_t)w + (uint32_t)b);
+                                }
+                            }
+                        }
+                    } else if (fast_sparse) {
+                        // sparse tile: a few rows per span.  Every lane fetches ALL columns of its row before the first store,
+                        // so the span costs one global round trip instead of one per column.
+                        const uint32_t sel_addr = smem_u32(sel_w);
+                        for (int i0 = lane; i0 < nn; i0 += 32) {
+                            const long long row = tile_row0 + span_row + lds_cell<uint16_t>(sel_addr + 2u * (uint32_t)i0);
+                            uint32_t v[4];
+#pragma unroll
+                            for (int pc = 0; pc < 4; pc++) {
+                                if (pc < P.nproj) {
+                                    const int w = S.proj[pc].width;
+                                    const uint8_t* src = S.proj[pc].base + row * w;
+                                    v[pc] = w == 4 ? __ldg(reinterpret_cast<const uint32_t*>(src))
+                                                   : (w == 2 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(src)) : (uint32_t)__ldg(src));
+                                }
+                            }
+#pragma unroll
+                            for (int pc = 0; pc < 4; pc++) {
+                                if (pc < P.nproj) {
+                                    const int w = S.proj[pc].width;
+                                    uint8_t* dst = S.proj[pc].out + (g0 + i0) * w;
+                                    if (w == 4) *reinterpret_cast<uint32_t*>(dst) = v[pc];
+                                    else if (w == 2) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)v[pc];
+                                    else *dst = (uint8_t)v[pc];
                                 }
                             }
                         }
@@ -2033,10 +2072,10 @@ cudaError_t launch_filter(const ScanPlan& plan, uint32_t* bitmap, uint32_t* span
     return cudaGetLastError();
 }
 cudaError_t launch_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* span_cnt, const unsigned long long* tile_off,
-                        int spans_per_tile, long long nspans, int grid, int dense_off, cudaStream_t stream) {
+                        int spans_per_tile, long long nspans, int grid, int dense_off, const ScanCtrl* ctrl, cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    emit_kernel<<<grid, kComputeThreads, kComputeWarps * 1024 * 2, stream>>>(plan, bitmap, span_cnt, tile_off, spans_per_tile, nspans, dense_off);
+    emit_kernel<<<grid, kComputeThreads, kComputeWarps * 1024 * 2, stream>>>(plan, bitmap, span_cnt, tile_off, spans_per_tile, nspans, dense_off, ctrl);
     return cudaGetLastError();
 }
 size_t emit_stream_smem_bytes(int stage_bytes, int ring) { return (size_t)kComputeWarps * 1024 * 2 + (size_t)ring * (size_t)stage_bytes + 16; }
@@ -2048,10 +2087,10 @@ cudaError_t emit_stream_occupancy(size_t dyn_smem, int* blocks_per_sm) {
 }
 cudaError_t launch_emit_stream(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* span_cnt, const uint32_t* tile_cnt,
                                const unsigned long long* tile_off, long long nsub, int ring, int stage_bytes, int dense_mode, int grid,
-                               size_t dyn_smem, cudaStream_t stream) {
+                               size_t dyn_smem, const ScanCtrl* ctrl, cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    emit_stream_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt, tile_off, nsub, ring, stage_bytes, dense_mode);
+    emit_stream_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt, tile_off, nsub, ring, stage_bytes, dense_mode, ctrl);
     return cudaGetLastError();
 }
 

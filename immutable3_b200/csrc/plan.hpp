@@ -95,6 +95,7 @@ struct ScanCtrl {
     unsigned long long total;  // rows emitted (min(limit, matches)) or matches in bitmap mode
     unsigned int scanner;  // dense kernel: the grid's scanner warp has been elected
     unsigned int pad;
+    unsigned long long dense_rows;  // multi-pass: selected rows living in tiles with >= 1 selected row in 32 (emit-kernel choice)
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -291,7 +291,7 @@ def test_full_size_synthetic_properties(tmp_path_factory):
             m = (age > 18) & (age < 30)
             with eng.execute(Query("syn", conj(Select("age", GT(18)), Select("age", LT(30))), Project(["id", "age"]))) as r:     # C2
                 assert r.nrows == int(m.sum()) and np.array_equal(r.column(0), ids[m]) and np.array_equal(r.column(1), age[m])
-                assert r.algorithmic_bytes == n + r.nrows * 9 and r.kernel_launches == (1 if path == "fused" else 3)
+                assert r.algorithmic_bytes == n + r.nrows * 9 and r.kernel_launches in ((1,) if path == "fused" else (2, 3))
             m3 = m & (st == b"CA")
             with eng.execute(Query("syn", conj(Select("state", Match(["CA"])), Select("age", GT(18)), Select("age", LT(30))), Project(["id", "state", "age"]))) as r:  # C3
                 assert r.nrows == int(m3.sum()) and np.array_equal(r.column(0), ids[m3]) and np.all(r.column(1) == b"CA")
