@@ -367,6 +367,7 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
             f.span = (uint32_t)(lf.hi - lf.lo);
         }
     }
+    sp.lit_bytes = lit_at;
     for (int i = 0; i < sp.nproj; i++) {
         const int ci = lp.proj[(size_t)i];
         const ColumnStore& c = t.cols[(size_t)ci];

@@ -582,11 +582,11 @@ extern __shared__ __align__(128) uint8_t dyn_smem[];
 // selects), so the parameter bank is never indexed dynamically.
 __device__ __forceinline__ void copy_plan_tables(const ScanPlan& P, FilterCol* filter, ProjCol* proj, int tid, int nthreads) {
     (void)nthreads;
-    if (tid < kMaxFilterCols) {
+    if (tid < P.nfilter) {
 #pragma unroll
         for (int i = 0; i < kMaxFilterCols; i++)
             if (tid == i) filter[i] = P.filter[i];
-    } else if (tid >= 32 && tid < 32 + kMaxProjCols) {
+    } else if (tid >= 32 && tid < 32 + P.nproj) {
 #pragma unroll
         for (int i = 0; i < kMaxProjCols; i++)
             if (tid - 32 == i) proj[i] = P.proj[i];
@@ -726,7 +726,7 @@ __global__ void __launch_bounds__(kDenseThreads, IMM3_DENSE_MIN_BLOCKS) scan_den
     unsigned long long* pre = status + status_round_up(P.ntiles);
     const bool want_offsets = !P.bitmap && P.nproj > 0;
 
-    for (int i = tid; i < kLitPoolBytes; i += kDenseThreads) S.lits[i] = P.lits[i];
+    for (int i = tid; i < P.lit_bytes; i += kDenseThreads) S.lits[i] = P.lits[i];  // (nothing to copy unless a MATCH predicate exists)
     copy_plan_tables(P, S.filter, S.proj, tid, kDenseThreads);
     if (tid == 0) {
         for (int s = 0; s < kMaxStages; s++) {
@@ -1271,7 +1271,7 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
     const int ring = STAGED ? P.stages : 2;
     const long long ntiles = P.ntiles;
 
-    for (int i = tid; i < kLitPoolBytes; i += kComputeThreads + 32) S.lits[i] = P.lits[i];
+    for (int i = tid; i < P.lit_bytes; i += kComputeThreads + 32) S.lits[i] = P.lits[i];  // (nothing to copy unless a MATCH predicate exists)
     copy_plan_tables(P, S.filter, S.proj, tid, kComputeThreads + 32);
     if (tid == 0) {
         for (int s = 0; s < kMaxFilterStages; s++) {
@@ -1604,7 +1604,7 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_filter_kernel(const
     __shared__ FilterShared S;
     __shared__ PforCol s_pfor[kMaxPforCols];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < kLitPoolBytes; i += kComputeThreads) S.lits[i] = P.lits[i];
+    for (int i = tid; i < P.lit_bytes; i += kComputeThreads) S.lits[i] = P.lits[i];  // (nothing to copy unless a MATCH predicate exists)
     copy_plan_tables(P, S.filter, S.proj, tid, kComputeThreads);
     if (tid < kMaxPforCols) {
 #pragma unroll

@@ -74,6 +74,7 @@ struct ScanPlan {
     int32_t stages;       // dense: TMA pipeline depth (0 = direct loads, no staging)
     int32_t stage_bytes;  // dense: bytes of one stage
     int32_t max_block_rows;  // block mode: rows of the largest block (shared-memory sizing)
+    int32_t lit_bytes;       // bytes of `lits` in use
     int32_t blk_words_cap;   // block-mode multi-pass: 32-bit words of the largest encoded PFOR block (+ slack), per-warp scratch
     int32_t words_per_lane;  // multi-pass filter kernel: W (tile = 8192 * W rows)
     int32_t subtiles;        // fused dense kernel: NS (tile = NS sub-tiles of 8192 rows)

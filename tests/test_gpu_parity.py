@@ -325,3 +325,30 @@ def test_full_size_sorted_int_codec_properties(tmp_path_factory):
             assert np.array_equal(r.column(0), ids[age == 7]) and np.all(r.column(1) == 7)
         with eng.execute(Query("synp", NoSelect, Project(["id"]))) as r:
             assert np.array_equal(r.column(0), ids)
+
+
+def test_multipass_large_limit_and_mixed_density(tmp_path_factory):
+    """LIMIT > 2^20 keeps the multi-pass pipelines (dense and block mode) and must cut exactly; results whose density varies
+    along the table (clustered id window = full and empty tiles, a rare age value = sparse tiles, a dense age range = streamed
+    tiles) exercise every per-tile mode of the streaming emit kernel, both emit kernels and the per-shape feedback."""
+    d = tmp_path_factory.mktemp("big")
+    n = 2_600_000
+    make_table(d, "big", n, 1024, 100, seed=12)                                             # 26 segments, dense id
+    make_table(d, "bigp", n, 1024, 100, seed=12, id_codec="PFOR_INT")                     # same rows, sorted-int codec id
+    os.environ.pop("IMM3_PATH", None)
+    with O.Oracle(d) as orc, SegmentManager(d) as sm:
+        eng = Engine(sm)
+        cases = [(NoSelect, ["id", "state", "age"]),
+                 (conj(Select("age", GT(10)), Select("age", LT(60))), ["age", "id"]),
+                 (conj(Select("id", GT(3_000_000)), Select("id", LT(6_500_000))), ["id", "age", "state"]),
+                 (Select("age", EQ(7)), ["id", "state"]),
+                 (conj(Select("state", Match(["CA", "NY"])), Select("age", GT(90))), ["state", "id"])]
+        for table in ("big", "bigp"):
+            for sel, proj in cases:
+                for limit in (0, (1 << 20) + 1, (1 << 20) + 4099, 2_500_000):
+                    for _rep in range(2):  # second run: only the emit kernel remembered for this shape is launched
+                        exp = orc.query(table, oracle_preds(sel), proj, limit=limit)
+                        with eng.execute(Query(table, sel, Project(proj, limit))) as got:
+                            assert got.nrows == exp.nrows, (table, sel, limit, got.nrows, exp.nrows)
+                            for c in range(len(proj)):
+                                assert np.array_equal(got.column(c), exp.columns[c]), (table, sel, proj[c], limit)
