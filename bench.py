@@ -394,7 +394,7 @@ def main():
     launch_ms = statistics.mean(kernel_ms)
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
     st0, st1 = statistics.mean(stage_ms[0]), statistics.mean(stage_ms[1])
-    multi = st1 > 0
+    multi = launches >= 2 * args.steps  # filter kernel + emit kernel(s) per query
     if args.workload == "c4":
         kname = "scan_blocks_kernel"
     elif multi:
@@ -407,8 +407,9 @@ def main():
                 "traffic": recorded_traffic(args.workload), "peak_source": peak_src, "kernel": kname,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms_mean": launch_ms, "launch_ms_min": min(kernel_ms),
                 "stage_ms_mean": [st0, st1],
-                "stages": ({"filter_kernel(+offset scan)": st0, "emit kernels": st1, "dominant": "emit_stream_kernel" if st1 >= st0 else "filter_kernel",
-                            "dominant_share": max(st0, st1) / (st0 + st1)} if multi else None)}
+                "stages": ({"note": "per-stage CUDA-event times need IMM3_NO_PDL=1 (the emit kernel is a programmatic dependent launch of the filter "
+                                    "kernel, no event may sit between them); ncu shares are in profiles/",
+                            "filter_kernel(+offset scan)": st0 if st1 > 0 else None, "emit kernels": st1 if st1 > 0 else None} if multi else None)}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     cpu = None

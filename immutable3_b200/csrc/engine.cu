@@ -570,6 +570,15 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
         }
         CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
     } else if (pr->multipass) {
+        if ((pr->sp.debug & 16u) && getenv("IMM3_TRACE")) {  // debugging: phase stamps (min / max over CTAs)
+            int rc0 = ensure_buf(&db->d_trace, 64 * 8);
+            if (rc0) return rc0;
+            std::vector<unsigned long long> init(64);
+            for (int i = 0; i < 64; i++) init[(size_t)i] = (i & 1) ? 0ull : ~0ull;
+            CUDA_TRY(cudaMemcpyAsync(db->d_trace.p, init.data(), 64 * 8, cudaMemcpyHostToDevice, db->stream));
+            CUDA_TRY(cudaStreamSynchronize(db->stream));
+            pr->sp.trace = (unsigned long long*)db->d_trace.p;
+        }
         const int64_t tile_rows = (int64_t)kDenseTileRowsPerWord * pr->sp.words_per_lane;
         const int64_t ntiles = pr->sp.ntiles, nspans = ntiles * (tile_rows / 1024);
         const int64_t nsub = ntiles * pr->sp.words_per_lane;  // 8192-row sub-tiles: the unit of the offset scan
@@ -582,28 +591,34 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
         const size_t nsub_pad = ((size_t)nsub + 4095) / 4096 * 4096 + 16;  // whole rounds of the offset scan
         if ((rc = ensure_buf(&db->d_tile_cnt, nsub_pad * 4))) return rc;
         if ((rc = ensure_buf(&db->d_tile_off, nsub_pad * 8))) return rc;
+        // Emit-kernel choice known from an earlier query of this shape (see emit_hint).
+        const int stream_ok = pr->emit_stage_bytes > 0 && pr->sp.nproj > 0;
+        const char* force = getenv("IMM3_EMIT");  // experiment: "stream" / "gather" = that kernel takes every result, "both" = no feedback
+        int hint = -1;
+        if (stream_ok && !(force && !strcmp(force, "both"))) {
+            auto it = db->emit_hint.find(pr->shape_key);
+            if (it != db->emit_hint.end()) hint = it->second;
+            if (force && !strcmp(force, "stream")) hint = 1;
+            if (force && !strcmp(force, "gather")) hint = 0;
+        }
+        const bool only_stream = stream_ok && hint == 1, only_gather = stream_ok && hint == 0;
+        const bool pdl = stream_ok && !only_gather && !getenv("IMM3_NO_PDL");
         CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
         CUDA_TRY(launch_filter(pr->sp, pr->sp.bitmap, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
                                (unsigned long long*)db->d_tile_off.p, db->d_ctrl, pr->grid, pr->dyn_smem, db->stream));
         *launches = 1;
-        CUDA_TRY(cudaEventRecord(db->ev_mid, db->stream));
-        have_mid = true;
+        // The streaming emit kernel is launched as a programmatic dependent of the filter kernel (its prologue overlaps the
+        // filter kernel's tail), so no event may sit between the two; IMM3_NO_PDL=1 restores per-stage timing.
+        if (!pdl) {
+            CUDA_TRY(cudaEventRecord(db->ev_mid, db->stream));
+            have_mid = true;
+        }
         if (pr->sp.nproj > 0) {
             // Two emit kernels, one of which does the work: which one is decided on the device from the match count.
-            const int stream_ok = pr->emit_stage_bytes > 0;
-            const char* force = getenv("IMM3_EMIT");  // experiment: "stream" / "gather" = that kernel takes every result, "both" = no feedback
-            int hint = -1;
-            if (stream_ok && !(force && !strcmp(force, "both"))) {
-                auto it = db->emit_hint.find(pr->shape_key);
-                if (it != db->emit_hint.end()) hint = it->second;
-                if (force && !strcmp(force, "stream")) hint = 1;
-                if (force && !strcmp(force, "gather")) hint = 0;
-            }
-            const bool only_stream = stream_ok && hint == 1, only_gather = stream_ok && hint == 0;
             if (stream_ok && !only_gather) {
                 CUDA_TRY(launch_emit_stream(pr->sp, pr->sp.bitmap, (const uint32_t*)db->d_span_cnt.p, (const uint32_t*)db->d_tile_cnt.p,
                                             (const unsigned long long*)db->d_tile_off.p, nsub, pr->emit_ring, pr->emit_stage_bytes,
-                                            only_stream ? -1 : 1, pr->grid_emit_stream, pr->emit_smem, db->d_ctrl, db->stream));
+                                            only_stream ? -1 : 1, pr->grid_emit_stream, pr->emit_smem, db->d_ctrl, pdl, db->stream));
                 (*launches)++;
             }
             if (!only_stream) {
@@ -646,7 +661,18 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
     *total = (int64_t)db->h_ctrl->total;
     if (pr->multipass && pr->sp.nproj > 0 && pr->emit_stage_bytes > 0)  // feedback for the next query of this shape
         db->emit_hint[pr->shape_key] = (db->h_ctrl->total > 0 && db->h_ctrl->dense_rows * 2 >= db->h_ctrl->total) ? 1 : 0;
-    if (pr->sp.trace) {
+    if (pr->sp.trace && (pr->sp.debug & 16u)) {
+        unsigned long long h[64];
+        CUDA_TRY(cudaMemcpy(h, pr->sp.trace, sizeof h, cudaMemcpyDeviceToHost));
+        if (FILE* f = fopen(getenv("IMM3_TRACE"), "w")) {
+            const char* names[] = {"K1 entry", "K1 cta done", "K1 scan start", "K1 scan end", "K3s entry", "K3s first tile", "K3s cta done"};
+            for (int i = 0; i < 7; i++)
+                fprintf(f, "%-16s min %9.2f us  max %9.2f us\n", names[i], (double)(h[2 * i] - h[0]) / 1e3, (double)(h[2 * i + 1] - h[0]) / 1e3);
+            for (int i = 0; i < 8; i++)
+                if (h[32 + i] != ~0ull && h[32 + i] != 0) fprintf(f, "scan round %d after block scan: %9.2f us\n", i, (double)(h[32 + i] - h[0]) / 1e3);
+            fclose(f);
+        }
+    } else if (pr->sp.trace) {
         std::vector<unsigned long long> h((size_t)pr->sp.ntiles * 8);
         CUDA_TRY(cudaMemcpy(h.data(), pr->sp.trace, h.size() * 8, cudaMemcpyDeviceToHost));
         if (FILE* f = fopen(getenv("IMM3_TRACE"), "wb")) {

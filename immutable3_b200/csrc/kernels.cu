@@ -59,6 +59,16 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// Debugging (IMM3_DEBUG bit 4 + IMM3_TRACE): phase stamps of the multi-pass kernels, min and max over CTAs per event.
+__device__ __forceinline__ void phase_stamp(const ScanPlan& P, int ev) {
+    if ((P.debug & 16u) && P.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMin(P.trace + 2 * ev, t);
+        atomicMax(P.trace + 2 * ev + 1, t);
+    }
+}
+
 // L2 cache policies for bulk copies: a column that a later kernel reads again is kept (evict_last), a column that
 // is streamed exactly once goes first (evict_first) so that it does not push the former out of the 126 MB L2.
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
@@ -1198,16 +1208,31 @@ struct FilterShared {
 // Exclusive scan of the sub-tile counts by one CTA of kComputeThreads threads: 4096 counts per round, every thread
 // loads its 16 consecutive counts with four independent 128-bit loads (the arrays are padded to whole rounds),
 // one block-wide scan per round.  LIMIT clamp of the total.
+// 128-bit L2 load that stays where it is written (the compiler sinks a plain __ldcg to its first use, which defeats a prefetch).
+__device__ __forceinline__ uint4 ldcg_v4_here(const uint32_t* p) {
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ void scan_tile_counts(FilterShared& S, const uint32_t* tile_cnt, unsigned long long* tile_off, long long ntiles,
-                                 long long limit, ScanCtrl* ctrl, int dense_tile_rows = kDenseTileRowsPerWord) {
+                                 long long limit, ScanCtrl* ctrl, int dense_tile_rows = kDenseTileRowsPerWord,
+                                 unsigned long long* dbg = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long running = 0;
     unsigned long long dense = 0;  // rows selected in tiles with at least one selected row in 32 (this thread's share)
+    uint4 nx[4];  // the next round's counts, in flight while this round is scanned
+#pragma unroll
+    for (int k = 0; k < 4; k++) nx[k] = ldcg_v4_here(tile_cnt + tid * 16 + 4 * k);
     for (long long base = 0; base < ntiles; base += kComputeThreads * 16) {
         const long long i0 = base + tid * 16;
         uint4 v[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = __ldcg(reinterpret_cast<const uint4*>(tile_cnt + i0) + k);
+        for (int k = 0; k < 4; k++) v[k] = nx[k];
+        if (base + kComputeThreads * 16 < ntiles) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) nx[k] = ldcg_v4_here(tile_cnt + i0 + kComputeThreads * 16 + 4 * k);
+        }
         unsigned c[16] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w,
                           v[2].x, v[2].y, v[2].z, v[2].w, v[3].x, v[3].y, v[3].z, v[3].w};
         unsigned sum = 0;
@@ -1226,6 +1251,7 @@ __device__ void scan_tile_counts(FilterShared& S, const uint32_t* tile_cnt, unsi
         bar_sync(1, kComputeThreads);  // the previous round's readers are done with scan_warp
         if (lane == 31) S.scan_warp[warp] = incl;
         bar_sync(1, kComputeThreads);
+        if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[(base / (kComputeThreads * 16)) & 7] = t; }
         unsigned long long excl = running + (incl - sum), total = 0;
 #pragma unroll
         for (int w = 0; w < kComputeWarps; w++) {
@@ -1247,7 +1273,9 @@ __device__ void scan_tile_counts(FilterShared& S, const uint32_t* tile_cnt, unsi
     }
     if (tid == 0) ctrl->dense_rows = 0;
     bar_sync(1, kComputeThreads);
-    if (dense) atomicAdd(&ctrl->dense_rows, dense);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dense += __shfl_xor_sync(0xFFFFFFFFu, dense, o);  // one atomic per warp, not per thread
+    if (lane == 0 && dense) atomicAdd(&ctrl->dense_rows, dense);
     if (tid == 0) {
         tile_off[ntiles] = running;
         ctrl->total = running < (unsigned long long)limit ? running : (unsigned long long)limit;
@@ -1270,6 +1298,10 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ring = STAGED ? P.stages : 2;
     const long long ntiles = P.ntiles;
+    if (tid == 0) phase_stamp(P, 0);
+    // Programmatic dependent launch: the emit kernel's CTAs may take over SMs as this grid's CTAs retire and run their
+    // prologue; they block in griddepcontrol.wait until this whole grid (including the offset scan) has completed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     for (int i = tid; i < P.lit_bytes; i += kComputeThreads + 32) S.lits[i] = P.lits[i];  // (nothing to copy unless a MATCH predicate exists)
     copy_plan_tables(P, S.filter, S.proj, tid, kComputeThreads + 32);
@@ -1328,7 +1360,9 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
                 const long long left = P.nrows - (tile * kTile + warp * 1024 + lane * 32);
                 m = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
             }
-            if (nf == 1) {
+            if (P.debug & 2u) {
+                m = 0;  // timing experiment: stream the tiles, skip the predicate
+            } else if (nf == 1) {
                 m &= eval_filter_span<STAGED>(stage_addr + (uint32_t)f0.smem_off + (uint32_t)cell, f0.base + tile * (kTile * f0.width) + cell, f0.kind,
                                               f0.width, f0.lo, f0.span, f0.nlit, lits0, lane);
             } else {
@@ -1351,9 +1385,11 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
         }
     }
 
-    // The last CTA to finish turns the tile counts into device-wide offsets (saves a launch).
+    // The last CTA to finish turns the tile counts into device-wide offsets (saves a launch).  (Letting every emit CTA
+    // derive the offsets of its own tiles instead was measured: slower, 12-18 us of dependent L2 round trips per CTA.)
     __syncthreads();
     if (tid == 0) {
+        phase_stamp(P, 1);
         __threadfence();
         const unsigned prev = atomicAdd(&ctrl->exited, 1u);
         S.is_last = prev == gridDim.x - 1;
@@ -1362,7 +1398,9 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
     __syncthreads();
     if (S.is_last && warp < kComputeWarps) {
         __threadfence();
-        scan_tile_counts(S, tile_cnt, tile_off, ntiles, P.limit, ctrl);
+        if (tid == 0) phase_stamp(P, 2);
+        scan_tile_counts(S, tile_cnt, tile_off, ntiles, P.limit, ctrl, kDenseTileRowsPerWord, ((P.debug & 16u) && P.trace) ? P.trace + 32 : nullptr);
+        if (tid == 0) phase_stamp(P, 3);
     }
 }
 
@@ -1839,8 +1877,7 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(co
     __shared__ EmitShared S;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // One of the two emit kernels does the work, picked on the device from the match count (no host round trip).
-    if (dense_mode >= 0 && emit_class_dense(ctrl) != dense_mode) return;  // (-1: take every result)
-
+    if (tid == 0) phase_stamp(P, 4);
     const uint32_t ring_addr = smem_u32(dyn_smem) + kComputeWarps * 1024 * 2;  // after the selection vectors
     copy_plan_tables(P, S.filter, S.proj, tid, kComputeThreads + 32);
     if (tid == 0) {
@@ -1851,6 +1888,10 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(co
         fence_mbar_init();
     }
     __syncthreads();
+    // Everything above overlapped the tail of the filter kernel (programmatic dependent launch); its outputs - counts,
+    // offsets, bitmap, result class - may only be read from here on.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (dense_mode >= 0 && emit_class_dense(ctrl) != dense_mode) return;  // (-1: take every result)
     const bool can_stage = stage_bytes > kEmitHdrBytes;
 
     if (warp == kComputeWarps) {
@@ -1905,6 +1946,7 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(co
             const int slot = rp.slot;
             mbar_wait(smem_u32(&S.mbar_full[slot]), rp.use & 1u, nullptr);
             const unsigned mode = S.mode[slot];
+            if (tid == 0 && rp.use == 0 && rp.slot == 0) phase_stamp(P, 5);
             if (mode == 0) break;
             const uint32_t stage = ring_addr + (uint32_t)slot * (uint32_t)stage_bytes;
             const long long tile_row0 = (long long)S.tile[slot] * kDenseTileRowsPerWord;
@@ -2003,6 +2045,7 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(co
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&S.mbar_empty[slot]));
         }
+        if (tid == 0) phase_stamp(P, 6);
     }
 }
 
@@ -2087,11 +2130,20 @@ cudaError_t emit_stream_occupancy(size_t dyn_smem, int* blocks_per_sm) {
 }
 cudaError_t launch_emit_stream(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* span_cnt, const uint32_t* tile_cnt,
                                const unsigned long long* tile_off, long long nsub, int ring, int stage_bytes, int dense_mode, int grid,
-                               size_t dyn_smem, const ScanCtrl* ctrl, cudaStream_t stream) {
+                               size_t dyn_smem, const ScanCtrl* ctrl, bool pdl, cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    emit_stream_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt, tile_off, nsub, ring, stage_bytes, dense_mode, ctrl);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kComputeThreads + 32);
+    cfg.dynamicSmemBytes = dyn_smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, emit_stream_kernel, plan, bitmap, span_cnt, tile_cnt, tile_off, nsub, ring, stage_bytes, dense_mode, ctrl);
 }
 
 size_t blocks_multi_smem_bytes(int npfor, int words_cap) { return (size_t)kComputeWarps * blk_warp_smem_words(npfor, words_cap) * 4; }
