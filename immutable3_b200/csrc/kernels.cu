@@ -1198,6 +1198,7 @@ struct FilterShared {
     unsigned long long mbar_full[kMaxFilterStages];
     unsigned long long mbar_empty[kMaxFilterStages];
     unsigned int tile_acc[kMaxFilterStages];  // per ring slot: [31:20] warps arrived, [19:0] rows selected
+    unsigned int tile_id[kMaxFilterStages];   // tile held by a ring slot (kNoMoreTiles = the CTA is done)
     unsigned long long scan_warp[kComputeWarps];
     unsigned int is_last;
     uint8_t lits[kLitPoolBytes];  // MATCH literals of the plan
@@ -1319,12 +1320,22 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
         // ---------------- producer ----------------
         if (lane == 0) {
             const uint64_t pol_keep = l2_policy_evict_last();
+            // Tiles are drawn from an atomic ticket (the CTAs finish within one tile of each other instead of one in twenty);
+            // the next ticket is already in flight while this tile's copies are issued.
+            unsigned t_next = atomicAdd(&ctrl->ticket, 1u);
             RingPos rp;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, rp.advance(ring)) {
+            for (;; rp.advance(ring)) {
+                const long long tile = t_next;
+                if (tile < ntiles) t_next = atomicAdd(&ctrl->ticket, 1u);
                 const int slot = rp.slot;
                 const unsigned use = rp.use;
                 if (use > 0) mbar_wait(smem_u32(&S.mbar_empty[slot]), (use - 1) & 1u, nullptr);
                 const uint32_t bar = smem_u32(&S.mbar_full[slot]);
+                S.tile_id[slot] = tile < ntiles ? (unsigned)tile : kNoMoreTiles;
+                if (tile >= ntiles) {
+                    mbar_arrive(bar);
+                    break;
+                }
                 if (STAGED) {
                     mbar_arrive_expect_tx(bar, (uint32_t)P.stage_bytes);
 #pragma unroll 1
@@ -1347,13 +1358,16 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
         const int cell = (warp * 1024 + lane * 32) * f0.width;     // this lane's 32 rows inside a tile of column 0
         const uint8_t* const lits0 = S.lits + f0.lit_off;
         const long long full_tiles = P.nrows / kTile;              // tiles below this index have no rows past the end
-        uint32_t* bm_w = bitmap + ((long long)blockIdx.x * kComputeWarps + warp) * 32 + lane;
-        uint32_t* sc_w = span_cnt + (long long)blockIdx.x * kComputeWarps + warp;
-        const long long bm_step = (long long)gridDim.x * kComputeWarps * 32, sc_step = (long long)gridDim.x * kComputeWarps;
-        RingPos rp;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, rp.advance(ring), bm_w += bm_step, sc_w += sc_step) {
+        uint32_t* const bm_w0 = bitmap + warp * 32 + lane;
+        uint32_t* const sc_w0 = span_cnt + warp;
+        for (RingPos rp;; rp.advance(ring)) {
             const int slot = rp.slot;
             mbar_wait(smem_u32(&S.mbar_full[slot]), rp.use & 1u, nullptr);
+            const unsigned tile_u = S.tile_id[slot];
+            if (tile_u == kNoMoreTiles) break;
+            const long long tile = tile_u;
+            uint32_t* const bm_w = bm_w0 + tile * (kComputeWarps * 32);
+            uint32_t* const sc_w = sc_w0 + tile * kComputeWarps;
             const uint32_t stage_addr = ring_addr + (uint32_t)slot * (uint32_t)P.stage_bytes;
             uint32_t m = 0xFFFFFFFFu;
             if (tile >= full_tiles) {
@@ -1393,7 +1407,11 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
         __threadfence();
         const unsigned prev = atomicAdd(&ctrl->exited, 1u);
         S.is_last = prev == gridDim.x - 1;
-        if (S.is_last) ctrl->exited = 0;
+        if (S.is_last) {  // everybody has drawn its last ticket: reset the counters for the emit kernel and the next query
+            ctrl->exited = 0;
+            ctrl->ticket = 0;
+            ctrl->ticket2 = 0;
+        }
     }
     __syncthreads();
     if (S.is_last && warp < kComputeWarps) {
@@ -1873,7 +1891,7 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(co
                                                                                 const uint32_t* __restrict__ span_cnt,
                                                                                 const uint32_t* __restrict__ tile_cnt,
                                                                                 const unsigned long long* __restrict__ tile_off, long long nsub,
-                                                                                int ring, int stage_bytes, int dense_mode, const ScanCtrl* ctrl) {
+                                                                                int ring, int stage_bytes, int dense_mode, ScanCtrl* ctrl) {
     __shared__ EmitShared S;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // One of the two emit kernels does the work, picked on the device from the match count (no host round trip).
@@ -1899,13 +1917,16 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(co
         if (lane == 0) {
             const uint64_t pol_stream = l2_policy_evict_first();
             RingPos rp;
-            for (long long tile = blockIdx.x;; tile += gridDim.x) {
+            unsigned t_next = atomicAdd(&ctrl->ticket2, 1u);  // dynamic tile assignment; the next ticket is always in flight
+            for (;;) {
+                const long long tile = t_next;
+                if (tile < nsub) t_next = atomicAdd(&ctrl->ticket2, 1u);
                 unsigned mode = 0, c = 0;
                 long long off = 0;
                 if (tile < nsub) {
                     c = __ldcg(tile_cnt + tile);
-                    if (c == 0) continue;  // nothing selected: the compute warps never hear of this tile
                     off = (long long)__ldcg(tile_off + tile);
+                    if (c == 0) continue;  // nothing selected: the compute warps never hear of this tile
                     if (off < P.limit) mode = (can_stage && c * 32u >= (unsigned)kDenseTileRowsPerWord) ? 2u : 1u;  // else: LIMIT reached, stop
                 }
                 const int slot = rp.slot;
@@ -2130,7 +2151,7 @@ cudaError_t emit_stream_occupancy(size_t dyn_smem, int* blocks_per_sm) {
 }
 cudaError_t launch_emit_stream(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* span_cnt, const uint32_t* tile_cnt,
                                const unsigned long long* tile_off, long long nsub, int ring, int stage_bytes, int dense_mode, int grid,
-                               size_t dyn_smem, const ScanCtrl* ctrl, bool pdl, cudaStream_t stream) {
+                               size_t dyn_smem, ScanCtrl* ctrl, bool pdl, cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};

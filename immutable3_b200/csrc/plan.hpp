@@ -95,7 +95,7 @@ struct ScanCtrl {
     unsigned int error;    // watchdog: a bounded spin expired (never hang the GPU)
     unsigned long long total;  // rows emitted (min(limit, matches)) or matches in bitmap mode
     unsigned int scanner;  // dense kernel: the grid's scanner warp has been elected
-    unsigned int pad;
+    unsigned int ticket2;  // multi-pass: next tile of the streaming emit kernel (reset by the filter kernel's last CTA)
     unsigned long long dense_rows;  // multi-pass: selected rows living in tiles with >= 1 selected row in 32 (emit-kernel choice)
 };
 
