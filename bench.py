@@ -300,10 +300,18 @@ def main():
     used_cols = sorted({l.col for l in flatten_select(query.select)} | set(query.project.cols))
     used_bytes = sum(c.encoded_bytes for c in tinfo.columns if c.name in used_cols)
 
-    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    flush_buf = torch.zeros(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    flush_sink = torch.zeros((), dtype=torch.int64, device="cuda")
+
+    flush_mode = os.environ.get("IMM3_BENCH_FLUSH", "read")
 
     def flush_l2(i):
-        flush_buf.fill_(i & 0xFF)
+        # Evict the table from the 126 MB L2 between steps.  A READ pass over 512 MiB leaves clean lines behind; a write
+        # pass (fill_) would leave ~126 MB of dirty lines whose write-back is then charged to the next query.
+        if flush_mode == "write":
+            flush_buf.fill_(i & 0xFF)
+        elif flush_mode == "read":
+            flush_sink.copy_(flush_buf.view(torch.int64).sum())
         torch.cuda.synchronize()
 
     def exchange(count):
@@ -426,7 +434,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload][0], "rows_per_gpu": args.rows, "rows_total": total, "block_size": BLOCK,
-                       "segment_size": SEGMENT, "segments": tinfo.nsegments, "l2": "flushed between steps (512 MiB write)",
+                       "segment_size": SEGMENT, "segments": tinfo.nsegments, "l2": "flushed between steps (512 MiB %s pass)" % os.environ.get("IMM3_BENCH_FLUSH", "read"),
                        "kernel_variant": "direct" if args.no_tma else "tma", "result_rows_rank0": local_rows},
             "clocks": clocks, "e2e": e2e, "e2e_resident": e2e_res, "gpu_launches": launches_all, "roofline": roofline,
             "cpu_baseline": cpu, "wall_s_timed_region": wall, "open_s": open_s, "upload_gbs": tinfo.resident_bytes / open_s / 1e9,
