@@ -1422,6 +1422,41 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
     }
 }
 
+// A short selection vector (a few rows): every lane fetches ALL columns of its row before the first store, so the rows
+// cost one global round trip instead of one per column.  Up to 4 columns of width 1, 2 or 4 (the caller checks).
+__device__ __noinline__ void emit_rows_fused(const ProjCol* proj, int nproj, const unsigned short* sel_w, int n, int lane, long long row0,
+                                                long long g0) {
+    const uint32_t sel_addr = smem_u32(sel_w);
+    for (int i0 = lane; i0 < n; i0 += 32) {
+        const long long row = row0 + lds_cell<uint16_t>(sel_addr + 2u * (uint32_t)i0);
+        uint32_t v[4];
+#pragma unroll
+        for (int pc = 0; pc < 4; pc++) {
+            if (pc < nproj) {
+                const int w = proj[pc].width;
+                const uint8_t* src = proj[pc].base + row * w;
+                v[pc] = w == 4 ? __ldg(reinterpret_cast<const uint32_t*>(src))
+                               : (w == 2 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(src)) : (uint32_t)__ldg(src));
+            }
+        }
+#pragma unroll
+        for (int pc = 0; pc < 4; pc++) {
+            if (pc < nproj) {
+                const int w = proj[pc].width;
+                uint8_t* dst = proj[pc].out + (g0 + i0) * w;
+                if (w == 4) *reinterpret_cast<uint32_t*>(dst) = v[pc];
+                else if (w == 2) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)v[pc];
+                else *dst = (uint8_t)v[pc];
+            }
+        }
+    }
+}
+__device__ __forceinline__ bool can_emit_fused(const ProjCol* proj, int nproj) {
+    bool ok = nproj <= 4;
+    for (int pc = 0; pc < nproj && pc < 4; pc++) ok = ok && (proj[pc].width == 4 || proj[pc].width == 2 || proj[pc].width == 1);
+    return ok;
+}
+
 // Result class decided by K1's offset scan: dense = at least half of the selected rows live in tiles with >= 1 selected
 // row in 32 (those tiles are streamed); otherwise the rows are thinly spread and the gather kernel is the better fit.
 __device__ __forceinline__ int emit_class_dense(const ScanCtrl* ctrl) {
@@ -1429,12 +1464,11 @@ __device__ __forceinline__ int emit_class_dense(const ScanCtrl* ctrl) {
     return (total > 0 && dense * 2ull >= total) ? 1 : 0;
 }
 
-// K3.  Two mappings, chosen on the device from the total match count:
-//  * dense results (>= 32 surviving rows per span on average): one warp per 1024-row span - maximum
-//    parallelism, every span's three metadata loads issued together;
-//  * sparse results: one warp per group of 8 spans - the group's bitmap words are fetched up front, the
-//    surviving rows of consecutive spans are appended to ONE warp-private selection vector and emitted
-//    together, so a group pays one gather latency instead of eight.
+// K3, sparse results (and the fallback when the projected columns are too wide to stage): one warp per group of 8
+// spans = one 8192-row tile.  The group's bitmap words are fetched up front, the surviving rows of consecutive spans
+// are appended to ONE warp-private selection vector and emitted together - a short vector through the fused
+// multi-column gather (one global round trip for all columns), a long one column by column; spans with all 1024 rows
+// selected are copied straight.
 __global__ void __launch_bounds__(kComputeThreads, IMM3_EMIT_MIN_BLOCKS) emit_kernel(const __grid_constant__ ScanPlan P, const uint32_t* __restrict__ bitmap,
                                                                  const uint32_t* __restrict__ span_cnt,
                                                                  const unsigned long long* __restrict__ tile_off, int spans_per_tile,
@@ -1449,46 +1483,8 @@ __global__ void __launch_bounds__(kComputeThreads, IMM3_EMIT_MIN_BLOCKS) emit_ke
     if (dense_off && emit_class_dense(ctrl)) return;  // the streaming emit kernel takes dense results
     const long long warp0 = (long long)blockIdx.x * kComputeWarps + warp, nwarps = (long long)gridDim.x * kComputeWarps;
 
-    if (total >= (unsigned long long)nspans * 32ull) {
-        // ---------------- one warp per span ----------------
-        for (long long p = warp0; p < nspans; p += nwarps) {
-            const long long t = p / spans_per_tile;
-            const int k = (int)(p - t * spans_per_tile);
-            // three independent loads: the tile's span counts (lane i holds span i), its offset, my bitmap word
-            const unsigned c = lane < spans_per_tile && t * spans_per_tile + lane < nspans ? __ldg(span_cnt + t * spans_per_tile + lane) : 0u;
-            const unsigned long long toff = __ldg(tile_off + t);
-            uint32_t mm = __ldg(bitmap + p * 32 + lane);
-            const int n = (int)__shfl_sync(0xFFFFFFFFu, c, k);
-            if (n == 0) continue;
-            const long long g0 = (long long)toff + __reduce_add_sync(0xFFFFFFFFu, lane < k ? c : 0u);
-            if (g0 >= P.limit) continue;
-            if (n == 1024) {
-                emit_span_full(SE.proj, P.nproj, lane, p * 1024, g0, (int)(P.limit - g0 < 1024 ? P.limit - g0 : 1024));
-                continue;
-            }
-            const unsigned cnt = (unsigned)__popc(mm);
-            unsigned incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += nb;
-            }
-            unsigned o = incl - cnt;
-            const unsigned iters = __reduce_max_sync(0xFFFFFFFFu, cnt);
-            for (unsigned it = 0; it < iters; it++) {
-                if (mm) {
-                    sel_w[o++] = (unsigned short)(lane * 32 + __ffs(mm) - 1);
-                    mm &= mm - 1u;
-                }
-            }
-            __syncwarp();
-            emit_span_all(SE.proj, P.nproj, nullptr, sel_w, (int)(P.limit - g0 < (long long)n ? P.limit - g0 : (long long)n), lane, false, 0u, 0, p * 1024, g0);
-            __syncwarp();
-        }
-        return;
-    }
-
     // ---------------- one warp per group of 8 spans ----------------
+    const bool fused_ok = can_emit_fused(SE.proj, P.nproj);
     const long long ngroups = (nspans + 7) >> 3;
     for (long long u = warp0; u < ngroups; u += nwarps) {
         const long long p0 = u * 8;                   // first span of the group
@@ -1507,13 +1503,18 @@ __global__ void __launch_bounds__(kComputeThreads, IMM3_EMIT_MIN_BLOCKS) emit_ke
             mw[k] = (ck && ck != 1024u) ? __ldg(bitmap + (p0 + k) * 32 + lane) : 0u;
         }
         int fill = 0;          // rows in the selection vector, first of them is global ordinal g0
+        auto emit_group = [&](int nfill) {
+            const int nn = (int)(P.limit - g0 < (long long)nfill ? P.limit - g0 : (long long)nfill);
+            if (fused_ok && nn <= 128) emit_rows_fused(SE.proj, P.nproj, sel_w, nn, lane, p0 * 1024, g0);
+            else emit_span_all(SE.proj, P.nproj, nullptr, sel_w, nn, lane, false, 0u, 0, p0 * 1024, g0);
+        };
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const int n = (int)__shfl_sync(0xFFFFFFFFu, c, k0 + k);
             if (n == 0) continue;
             if (n == 1024 || fill + n > 1024) {  // flush what has been gathered so far
                 __syncwarp();
-                if (fill && g0 < P.limit) emit_span_all(SE.proj, P.nproj, nullptr, sel_w, (int)(P.limit - g0 < (long long)fill ? P.limit - g0 : (long long)fill), lane, false, 0u, 0, p0 * 1024, g0);
+                if (fill && g0 < P.limit) emit_group(fill);
                 __syncwarp();
                 g0 += fill;
                 fill = 0;
@@ -1542,7 +1543,7 @@ __global__ void __launch_bounds__(kComputeThreads, IMM3_EMIT_MIN_BLOCKS) emit_ke
             fill += n;
         }
         __syncwarp();
-        if (fill && g0 < P.limit) emit_span_all(SE.proj, P.nproj, nullptr, sel_w, (int)(P.limit - g0 < (long long)fill ? P.limit - g0 : (long long)fill), lane, false, 0u, 0, p0 * 1024, g0);
+        if (fill && g0 < P.limit) emit_group(fill);
         __syncwarp();
     }
 }
@@ -1961,8 +1962,7 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(co
     } else {
         // ---------------- compute warps: warp w = span w of every tile ----------------
         unsigned short* sel_w = reinterpret_cast<unsigned short*>(dyn_smem) + warp * 1024;
-        bool fast_sparse = P.nproj <= 4;  // sparse tiles: fused multi-column gather (widths 1, 2, 4)
-        for (int pc = 0; pc < P.nproj && pc < 4; pc++) fast_sparse = fast_sparse && (S.proj[pc].width == 4 || S.proj[pc].width == 2 || S.proj[pc].width == 1);
+        const bool fast_sparse = can_emit_fused(S.proj, P.nproj);  // sparse tiles: fused multi-column gather
         for (RingPos rp;; rp.advance(ring)) {
             const int slot = rp.slot;
             mbar_wait(smem_u32(&S.mbar_full[slot]), rp.use & 1u, nullptr);
@@ -2027,32 +2027,7 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(co
                             }
                         }
                     } else if (fast_sparse) {
-                        // sparse tile: a few rows per span.  Every lane fetches ALL columns of its row before the first store,
-                        // so the span costs one global round trip instead of one per column.
-                        const uint32_t sel_addr = smem_u32(sel_w);
-                        for (int i0 = lane; i0 < nn; i0 += 32) {
-                            const long long row = tile_row0 + span_row + lds_cell<uint16_t>(sel_addr + 2u * (uint32_t)i0);
-                            uint32_t v[4];
-#pragma unroll
-                            for (int pc = 0; pc < 4; pc++) {
-                                if (pc < P.nproj) {
-                                    const int w = S.proj[pc].width;
-                                    const uint8_t* src = S.proj[pc].base + row * w;
-                                    v[pc] = w == 4 ? __ldg(reinterpret_cast<const uint32_t*>(src))
-                                                   : (w == 2 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(src)) : (uint32_t)__ldg(src));
-                                }
-                            }
-#pragma unroll
-                            for (int pc = 0; pc < 4; pc++) {
-                                if (pc < P.nproj) {
-                                    const int w = S.proj[pc].width;
-                                    uint8_t* dst = S.proj[pc].out + (g0 + i0) * w;
-                                    if (w == 4) *reinterpret_cast<uint32_t*>(dst) = v[pc];
-                                    else if (w == 2) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)v[pc];
-                                    else *dst = (uint8_t)v[pc];
-                                }
-                            }
-                        }
+                        emit_rows_fused(S.proj, P.nproj, sel_w, nn, lane, tile_row0 + span_row, g0);  // sparse tile: one round trip for all columns
                     } else {
 #pragma unroll 1
                         for (int pc = 0; pc < P.nproj; pc++) {
