@@ -602,7 +602,7 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
             if (force && !strcmp(force, "gather")) hint = 0;
         }
         const bool only_stream = stream_ok && hint == 1, only_gather = stream_ok && hint == 0;
-        const bool pdl = stream_ok && !only_gather && !getenv("IMM3_NO_PDL");
+        const bool pdl = pr->sp.nproj > 0 && !getenv("IMM3_NO_PDL");  // the first emit kernel launched is a programmatic dependent
         CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
         CUDA_TRY(launch_filter(pr->sp, pr->sp.bitmap, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
                                (unsigned long long*)db->d_tile_off.p, db->d_ctrl, pr->grid, pr->dyn_smem, db->stream));
@@ -623,7 +623,7 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
             }
             if (!only_stream) {
                 CUDA_TRY(launch_emit(pr->sp, pr->sp.bitmap, (const uint32_t*)db->d_span_cnt.p, (const unsigned long long*)db->d_tile_off.p, 8,
-                                     nspans, pr->grid_emit, stream_ok && !only_gather, db->d_ctrl, db->stream));
+                                     nspans, pr->grid_emit, stream_ok && !only_gather, db->d_ctrl, pdl && (only_gather || !stream_ok), db->stream));
                 (*launches)++;
             }
         }

@@ -1478,30 +1478,45 @@ __global__ void __launch_bounds__(kComputeThreads, IMM3_EMIT_MIN_BLOCKS) emit_ke
     __syncthreads();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned short* sel_w = reinterpret_cast<unsigned short*>(dyn_smem) + warp * 1024;
-    const long long ntiles = (nspans + spans_per_tile - 1) / spans_per_tile;
-    const unsigned long long total = __ldg(tile_off + ntiles);
+    (void)spans_per_tile;
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // (a programmatic dependent of the filter kernel when it is the only emit kernel)
     if (dense_off && emit_class_dense(ctrl)) return;  // the streaming emit kernel takes dense results
     const long long warp0 = (long long)blockIdx.x * kComputeWarps + warp, nwarps = (long long)gridDim.x * kComputeWarps;
 
     // ---------------- one warp per group of 8 spans ----------------
     const bool fused_ok = can_emit_fused(SE.proj, P.nproj);
     const long long ngroups = (nspans + 7) >> 3;
+    // The next group's metadata (8 span counts, tile offset, 8 bitmap words per lane - all independent loads, pinned in
+    // place) is in flight while this group is emitted: a group costs one exposed round trip (its gathers), not three.
+    auto load_u32 = [](const uint32_t* p) {
+        uint32_t v;
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        return v;
+    };
+    unsigned c_n = 0;
+    unsigned long long toff_n = 0;
+    uint32_t mw_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    auto load_group = [&](long long u) {
+        const long long p0 = u * 8;
+        c_n = (lane < 8 && p0 + lane < nspans) ? load_u32(span_cnt + p0 + lane) : 0u;
+        asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(toff_n) : "l"(tile_off + u) : "memory");
+#pragma unroll
+        for (int k = 0; k < 8; k++) mw_n[k] = p0 + k < nspans ? load_u32(bitmap + (p0 + k) * 32 + lane) : 0u;
+    };
+    if (warp0 < ngroups) load_group(warp0);
     for (long long u = warp0; u < ngroups; u += nwarps) {
-        const long long p0 = u * 8;                   // first span of the group
-        const long long t = p0 / spans_per_tile;      // groups never straddle tiles (spans_per_tile is 8, 16 or 32)
-        const int k0 = (int)(p0 - t * spans_per_tile);
-        const unsigned c = lane < spans_per_tile && t * spans_per_tile + lane < nspans ? __ldg(span_cnt + t * spans_per_tile + lane) : 0u;
-        const unsigned long long toff = __ldg(tile_off + t);
-        const unsigned in_group = __reduce_add_sync(0xFFFFFFFFu, (lane >= k0 && lane < k0 + 8) ? c : 0u);
-        if (in_group == 0) continue;
-        long long g0 = (long long)toff + __reduce_add_sync(0xFFFFFFFFu, lane < k0 ? c : 0u);  // ordinal of the group's first surviving row
-        if (g0 >= P.limit) continue;
+        const long long p0 = u * 8;  // first span of the group (a group = one 8192-row tile; spans_per_tile is 8)
+        const int k0 = 0;
+        const unsigned c = c_n;
+        const unsigned long long toff = toff_n;
         uint32_t mw[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const unsigned ck = __shfl_sync(0xFFFFFFFFu, c, k0 + k);
-            mw[k] = (ck && ck != 1024u) ? __ldg(bitmap + (p0 + k) * 32 + lane) : 0u;
-        }
+        for (int k = 0; k < 8; k++) mw[k] = mw_n[k];
+        if (u + nwarps < ngroups) load_group(u + nwarps);
+        const unsigned in_group = __reduce_add_sync(0xFFFFFFFFu, lane < 8 ? c : 0u);
+        if (in_group == 0) continue;
+        long long g0 = (long long)toff;  // ordinal of the group's first surviving row
+        if (g0 >= P.limit) continue;
         int fill = 0;          // rows in the selection vector, first of them is global ordinal g0
         auto emit_group = [&](int nfill) {
             const int nn = (int)(P.limit - g0 < (long long)nfill ? P.limit - g0 : (long long)nfill);
@@ -2111,11 +2126,20 @@ cudaError_t launch_filter(const ScanPlan& plan, uint32_t* bitmap, uint32_t* span
     return cudaGetLastError();
 }
 cudaError_t launch_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* span_cnt, const unsigned long long* tile_off,
-                        int spans_per_tile, long long nspans, int grid, int dense_off, const ScanCtrl* ctrl, cudaStream_t stream) {
+                        int spans_per_tile, long long nspans, int grid, int dense_off, const ScanCtrl* ctrl, bool pdl, cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    emit_kernel<<<grid, kComputeThreads, kComputeWarps * 1024 * 2, stream>>>(plan, bitmap, span_cnt, tile_off, spans_per_tile, nspans, dense_off, ctrl);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kComputeThreads);
+    cfg.dynamicSmemBytes = kComputeWarps * 1024 * 2;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, emit_kernel, plan, bitmap, span_cnt, tile_off, spans_per_tile, nspans, dense_off, ctrl);
 }
 size_t emit_stream_smem_bytes(int stage_bytes, int ring) { return (size_t)kComputeWarps * 1024 * 2 + (size_t)ring * (size_t)stage_bytes + 16; }
 int emit_stream_header_bytes() { return kEmitHdrBytes; }
