@@ -50,6 +50,8 @@ WORKLOADS = {
     "x_none": ("X select id, age where age = 127 (no match)", "DENSE_INT"),
     "x_all": ("X select id, age (no predicate)", "DENSE_INT"),
     "x_1pct": ("X select id, age where age = 7", "DENSE_INT"),
+    "c5_limit10": ("C5 select id, age where (age > 18 and age < 30) limit 10", "DENSE_INT"),
+    "c5_rare_limit10": ("C5 select id, state, age where (state = 'CA' and age = 7) limit 10", "DENSE_INT"),
 }
 
 
@@ -69,6 +71,11 @@ def build_query(workload: str, table: str, total_rows: int):
         if workload == "x_1pct":
             sel = Select("age", EQ(7))
         return Query(table, sel, Project(proj))
+    if workload == "c5_limit10":
+        return Query(table, And(Select("age", GT(18)), Select("age", LT(30))), Project(["id", "age"], 10))
+    if workload == "c5_rare_limit10":
+        from immutable3_b200 import EQ
+        return Query(table, And(Select("state", Match(["CA"])), Select("age", EQ(7))), Project(["id", "state", "age"], 10))
     if workload == "c3":
         return Query(table, And(And(Select("state", Match(["CA"])), Select("age", GT(18))), Select("age", LT(30))),
                      Project(["id", "state", "age"]))
@@ -100,7 +107,7 @@ def canonical_ids(nseg: int):
 
 def data_dir_for(args, world: int) -> str:
     base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
-    kind = "c2" if args.workload in ("c2", "c3") or args.workload.startswith("x_") else args.workload
+    kind = "c2" if args.workload in ("c2", "c3") or args.workload.startswith("x_") or args.workload.startswith("c5_") else args.workload
     return os.path.join(base, f"imm3_bench_{kind}_{args.rows}x{world}")
 
 
@@ -113,7 +120,7 @@ def ensure_table(args, rank: int, world: int, barrier):
 
     total = args.rows * world
     d = data_dir_for(args, world)
-    table = "test_100m" if args.workload in ("c2", "c3") or args.workload.startswith("x_") else "test_ids"
+    table = "test_100m" if args.workload in ("c2", "c3") or args.workload.startswith("x_") or args.workload.startswith("c5_") else "test_ids"
     marker = os.path.join(d, table, f".complete_{rank}_{world}")
     codec = L.CODEC_PFOR_INT if WORKLOADS[args.workload][1] == "PFOR_INT" else L.CODEC_DENSE_INT
     nseg = synth_segments(total, BLOCK, SEGMENT)
