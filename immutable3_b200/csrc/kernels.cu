@@ -1199,76 +1199,84 @@ struct FilterShared {
     unsigned long long mbar_empty[kMaxFilterStages];
     unsigned int tile_acc[kMaxFilterStages];  // per ring slot: [31:20] warps arrived, [19:0] rows selected
     unsigned int tile_id[kMaxFilterStages];   // tile held by a ring slot (kNoMoreTiles = the CTA is done)
-    unsigned long long scan_warp[kComputeWarps];
+    unsigned long long scan_warp[2 * kComputeWarps];  // double-buffered per scan round
     unsigned int is_last;
     uint8_t lits[kLitPoolBytes];  // MATCH literals of the plan
     FilterCol filter[kMaxFilterCols];
     ProjCol proj[kMaxProjCols];
 };
 
-// Exclusive scan of the sub-tile counts by one CTA of kComputeThreads threads: 4096 counts per round, every thread
-// loads its 16 consecutive counts with four independent 128-bit loads (the arrays are padded to whole rounds),
-// one block-wide scan per round.  LIMIT clamp of the total.
-// 128-bit L2 load that stays where it is written (the compiler sinks a plain __ldcg to its first use, which defeats a prefetch).
-__device__ __forceinline__ uint4 ldcg_v4_here(const uint32_t* p) {
-    uint4 v;
-    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+// Exclusive scan of the tile counts by one CTA of kComputeThreads threads, 4096 counts per round.  Warp w owns 512
+// consecutive counts of the round; lane l handles the count PAIRS l, l+32, ..., l+224 of them, so every load and every
+// offset store of a warp is one fully coalesced access (256 B / 512 B) - with 16 consecutive counts per thread the
+// 128-byte-strided stores cost ~1 us of LSU wavefronts per round.  Eight warp scans chain the pairs, one block-level
+// exchange per round (double-buffered, one barrier) chains the warps; the next round's counts are in flight meanwhile.
+// Also applies the LIMIT clamp to the total and sums the rows that live in dense tiles (emit-kernel choice).
+__device__ __forceinline__ uint2 ldcg_v2_here(const uint32_t* p) {
+    uint2 v;
+    asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
 
 __device__ void scan_tile_counts(FilterShared& S, const uint32_t* tile_cnt, unsigned long long* tile_off, long long ntiles,
                                  long long limit, ScanCtrl* ctrl, int dense_tile_rows = kDenseTileRowsPerWord,
                                  unsigned long long* dbg = nullptr) {
+    constexpr int kRound = kComputeThreads * 16;  // counts per round
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long running = 0;
     unsigned long long dense = 0;  // rows selected in tiles with at least one selected row in 32 (this thread's share)
-    uint4 nx[4];  // the next round's counts, in flight while this round is scanned
+    const unsigned dense_min = ((unsigned)dense_tile_rows + 31u) / 32u;
+    const int my0 = warp * 512 + lane * 2;  // first count of this lane's pair 0 inside a round; pair j is 64 counts further
+    uint2 nx[8];                            // the next round's counts, in flight while this round is scanned
 #pragma unroll
-    for (int k = 0; k < 4; k++) nx[k] = ldcg_v4_here(tile_cnt + tid * 16 + 4 * k);
-    for (long long base = 0; base < ntiles; base += kComputeThreads * 16) {
-        const long long i0 = base + tid * 16;
-        uint4 v[4];
+    for (int j = 0; j < 8; j++) nx[j] = ldcg_v2_here(tile_cnt + my0 + 64 * j);
+    unsigned round = 0;
+    for (long long base = 0; base < ntiles; base += kRound, round++) {
+        uint2 c[8];
 #pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = nx[k];
-        if (base + kComputeThreads * 16 < ntiles) {
+        for (int j = 0; j < 8; j++) c[j] = nx[j];
+        if (base + kRound < ntiles) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) nx[k] = ldcg_v4_here(tile_cnt + i0 + kComputeThreads * 16 + 4 * k);
+            for (int j = 0; j < 8; j++) nx[j] = ldcg_v2_here(tile_cnt + base + kRound + my0 + 64 * j);
         }
-        unsigned c[16] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w,
-                          v[2].x, v[2].y, v[2].z, v[2].w, v[3].x, v[3].y, v[3].z, v[3].w};
-        unsigned sum = 0;
+        // pair sums -> exclusive position of every pair inside the warp's 512 counts
+        unsigned excl_pair[8], carry = 0, dsum = 0;
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            if (i0 + k >= ntiles) c[k] = 0;  // padding holds stale counts
-            sum += c[k];
-            dense += c[k] * 32u >= (unsigned)dense_tile_rows ? c[k] : 0u;
-        }
-        unsigned incl = sum;
+        for (int j = 0; j < 8; j++) {
+            const long long i = base + my0 + 64 * j;  // padding holds stale counts
+            if (i >= ntiles) c[j].x = 0;
+            if (i + 1 >= ntiles) c[j].y = 0;
+            dsum += (c[j].x >= dense_min ? c[j].x : 0u) + (c[j].y >= dense_min ? c[j].y : 0u);
+            const unsigned ps = c[j].x + c[j].y;
+            unsigned incl = ps;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += nb;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += nb;
+            }
+            excl_pair[j] = carry + incl - ps;
+            carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
-        bar_sync(1, kComputeThreads);  // the previous round's readers are done with scan_warp
-        if (lane == 31) S.scan_warp[warp] = incl;
+        dense += dsum;
+        if (lane == 0) S.scan_warp[warp + 8 * (round & 1u)] = carry;  // the warp's 512 counts; double-buffered: one barrier per round
         bar_sync(1, kComputeThreads);
-        if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[(base / (kComputeThreads * 16)) & 7] = t; }
-        unsigned long long excl = running + (incl - sum), total = 0;
+        if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[round & 7] = t; }
+        unsigned long long wbase = running, total = 0;
 #pragma unroll
         for (int w = 0; w < kComputeWarps; w++) {
-            const unsigned long long ws = S.scan_warp[w];
-            if (w < warp) excl += ws;
+            const unsigned long long ws = S.scan_warp[w + 8 * (round & 1u)];
+            if (w < warp) wbase += ws;
             total += ws;
         }
 #pragma unroll
-        for (int k = 0; k < 16; k += 2) {
-            if (i0 + k < ntiles) {  // (pairs: the arrays are padded, the entry after the last sub-tile is rewritten below)
+        for (int j = 0; j < 8; j++) {
+            const long long i = base + my0 + 64 * j;
+            if (i < ntiles) {  // (pairs: the arrays are padded, the entry after the last tile is rewritten below)
                 ulonglong2 o;
-                o.x = excl;
-                o.y = excl + c[k];
-                *reinterpret_cast<ulonglong2*>(tile_off + i0 + k) = o;
+                o.x = wbase + excl_pair[j];
+                o.y = o.x + c[j].x;
+                *reinterpret_cast<ulonglong2*>(tile_off + i) = o;
             }
-            excl += (unsigned long long)c[k] + c[k + 1];
         }
         running += total;
     }
@@ -1579,7 +1587,6 @@ __global__ void __launch_bounds__(kComputeThreads, IMM3_EMIT_MIN_BLOCKS) emit_ke
 // No look-back chain: the old single-pass block kernel spent 13 ns per block on it (97.6 K blocks per 100 M rows).
 // =============================================================================================
 constexpr int kBlkRows = 1024;        // largest block this pipeline takes
-constexpr int kBlkWordsCap = 1120;    // byte-swapped words of one encoded block: count + 8 headers + 1024 + var-byte tail
 __host__ __device__ constexpr int blk_warp_smem_words(int npfor, int words_cap) { return words_cap + npfor * kBlkRows; }
 
 __device__ __forceinline__ int sw_idx(int m, int j) { return m * 32 + ((j + m) & 31); }  // bank-conflict-free either way
