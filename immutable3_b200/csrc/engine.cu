@@ -386,7 +386,7 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
         for (int i = 0; i < sp.nproj; i++)
             if (sp.proj[i].filter_idx >= 0) again += t.nrows * sp.filter[sp.proj[i].filter_idx].width;
         for (int i = 0; i < sp.nproj; i++)
-            if (sp.proj[i].filter_idx >= 0) sp.filter[sp.proj[i].filter_idx].keep_l2 = (again > 0 && again <= (int64_t)84 << 20) ? 1 : 0;
+            if (sp.proj[i].filter_idx >= 0) sp.filter[sp.proj[i].filter_idx].keep_l2 = (again > 0 && again <= (int64_t)(getenv("IMM3_KEEP_L2_MB") ? atoi(getenv("IMM3_KEEP_L2_MB")) : 84) << 20) ? 1 : 0;
     }
     sp.npfor = (int)pfor_cols.size();
     for (int i = 0; i < sp.npfor; i++) {

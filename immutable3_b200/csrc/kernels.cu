@@ -1587,11 +1587,33 @@ __global__ void __launch_bounds__(kComputeThreads, IMM3_EMIT_MIN_BLOCKS) emit_ke
 // No look-back chain: the old single-pass block kernel spent 13 ns per block on it (97.6 K blocks per 100 M rows).
 // =============================================================================================
 constexpr int kBlkRows = 1024;        // largest block this pipeline takes
-__host__ __device__ constexpr int blk_warp_smem_words(int npfor, int words_cap) { return words_cap + npfor * kBlkRows; }
+constexpr int kBlkLane = 33;          // decoded values: mini-block m lives at vals[33 m .. 33 m + 32) - odd stride, so both the
+constexpr int kBlkVals = 32 * kBlkLane;  // lane-per-mini-block and the row-per-lane access patterns are bank-conflict-free
+__host__ __device__ constexpr int blk_warp_smem_words(int npfor, int words_cap) { return words_cap + npfor * kBlkVals; }
 
-__device__ __forceinline__ int sw_idx(int m, int j) { return m * 32 + ((j + m) & 31); }  // bank-conflict-free either way
+// One mini-block of 32 B-bit deltas, B known at compile time: every word index and shift folds to an immediate.
+template <int B>
+__device__ __forceinline__ uint32_t unpack_fixed(const uint32_t* __restrict__ wp, uint32_t* __restrict__ vp) {
+    uint32_t w[B > 0 ? B : 1];
+#pragma unroll
+    for (int i = 0; i < B; i++) w[i] = wp[i];
+    uint32_t total = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        if (B > 0) {
+            const int bit = j * B, wi = bit >> 5, sh = bit & 31;
+            uint32_t d;
+            if (sh + B <= 32) d = w[wi] >> sh;
+            else d = __funnelshift_r(w[wi], w[wi + 1 < B ? wi + 1 : wi], sh);
+            if (sh + B != 32) d &= (1u << B) - 1u;
+            total += d;
+        }
+        vp[j] = total;
+    }
+    return total;
+}
 
-// Decode one PFOR_INT block (n <= 1024 values) by one warp.  vals[sw_idx(m, j)] + base(m) = value 32m+j,
+// Decode one PFOR_INT block (n <= 1024 values) by one warp.  vals[33 m + j] + base(m) = value 32m+j,
 // where base(m) is returned in lane m (mini-block-local prefix sums are stored; raw b = 32 mini-blocks and the
 // var-byte tail store absolute values with base 0).
 __device__ __forceinline__ uint32_t pfor_decode_warp(const uint32_t* __restrict__ words, uint32_t w0, uint32_t w1, int n, uint32_t* Wb,
@@ -1600,37 +1622,59 @@ __device__ __forceinline__ uint32_t pfor_decode_warp(const uint32_t* __restrict_
     if (nw > words_cap - 2) nw = words_cap - 2;
     for (int i = lane; i < nw; i += 32) Wb[i] = __byte_perm(__ldg(words + w0 + i), 0, 0x0123);  // putInt is big-endian
     __syncwarp();
-    const int packed = n & ~31, nmini = packed >> 5;
-    // header walk (every lane, uniformly): one word per 128-value super-block, then one per left-over mini-block
-    int ip = 1, mypos = 0, mybits = 0, m = 0, s = 0;
-    for (; s + 128 <= packed; s += 128) {
-        const uint32_t h = Wb[ip++];
-#pragma unroll
-        for (int q = 0; q < 4; q++, m++) {
-            const int b = (int)((h >> (24 - 8 * q)) & 0xFFu);
+    const int packed = n & ~31, nmini = packed >> 5, nsuper = packed >> 7;
+    // header walk: one word per 128-value super-block (four 8-bit widths, first mini-block in the top byte), then one word
+    // per left-over mini-block.  Lane m picks up mini-block m: its width and where its words start (byte sums by IDP.4A).
+    int ip = 1, mypos = 0, mybits = 0;
+    {
+        const int q = lane & 3, k = lane >> 2;
+        const uint32_t before = q == 0 ? 0u : (0x01010100u << (8 * (3 - q)));  // selects the widths of the mini-blocks ahead of q
+#pragma unroll 1
+        for (int s = 0; s < nsuper; s++) {
+            const uint32_t h = Wb[ip];
+            if (k == s) {
+                mybits = (int)((h >> (24 - 8 * q)) & 0xFFu);
+                mypos = ip + 1 + (int)__dp4a(h, before, 0u);
+            }
+            ip += 1 + (int)__dp4a(h, 0x01010101u, 0u);
+        }
+        for (int m = nsuper * 4; m < nmini; m++) {
+            const int b = (int)Wb[ip++];
             if (m == lane) { mypos = ip; mybits = b; }
             ip += b;
         }
     }
-    for (; s < packed; s += 32, m++) {
-        const int b = (int)Wb[ip++];
-        if (m == lane) { mypos = ip; mybits = b; }
-        ip += b;
-    }
     // mini-block `lane`: 32 values
     uint32_t total = 0;
     const bool raw = mybits >= 32;
-    if (lane < nmini) {
+    const uint32_t* wp = Wb + mypos;
+    uint32_t* vp = vals + lane * kBlkLane;
+    const int b0 = __shfl_sync(0xFFFFFFFFu, mybits, 0);
+    if (b0 <= 16 && __all_sync(0xFFFFFFFFu, lane >= nmini || mybits == b0)) {
+        // the usual case of a sorted column: one width for the whole block -> the fully specialised unpack
+        if (lane < nmini) {
+            switch (b0) {
+#define IMM3_UNPACK_CASE(B) case B: total = unpack_fixed<B>(wp, vp); break;
+                IMM3_UNPACK_CASE(0) IMM3_UNPACK_CASE(1) IMM3_UNPACK_CASE(2) IMM3_UNPACK_CASE(3) IMM3_UNPACK_CASE(4)
+                IMM3_UNPACK_CASE(5) IMM3_UNPACK_CASE(6) IMM3_UNPACK_CASE(7) IMM3_UNPACK_CASE(8) IMM3_UNPACK_CASE(9)
+                IMM3_UNPACK_CASE(10) IMM3_UNPACK_CASE(11) IMM3_UNPACK_CASE(12) IMM3_UNPACK_CASE(13) IMM3_UNPACK_CASE(14)
+                IMM3_UNPACK_CASE(15) IMM3_UNPACK_CASE(16)
+#undef IMM3_UNPACK_CASE
+                default: break;
+            }
+        }
+    } else if (lane < nmini) {
         if (raw) {
-            for (int j = 0; j < 32; j++) vals[sw_idx(lane, j)] = total = Wb[mypos + j];
+#pragma unroll
+            for (int j = 0; j < 32; j++) vp[j] = total = wp[j];
         } else {
             const uint32_t mask = (1u << mybits) - 1u;
-            int off = 0;
-            for (int j = 0; j < 32; j++, off += mybits) {
-                const int wi = mypos + (off >> 5), sh = off & 31;
-                const uint32_t d = __funnelshift_r(Wb[wi], Wb[wi + 1], sh) & mask;
-                total += d;
-                vals[sw_idx(lane, j)] = total;
+            uint32_t off = 0;
+#pragma unroll
+            for (int j = 0; j < 32; j++, off += (uint32_t)mybits) {
+                const uint32_t* p = wp + (off >> 5);
+                total += __funnelshift_r(p[0], p[1], off) & mask;  // (the shift amount is taken mod 32)
+                vp[j] = total;
             }
         }
     }
@@ -1653,17 +1697,17 @@ __device__ __forceinline__ uint32_t pfor_decode_warp(const uint32_t* __restrict_
     if (raw || lane >= nmini) base = 0;
     // var-byte remainder (n % 32 values): 7-bit groups, low first, the last byte of a value has bit 7 set
     if (n > packed && lane == 0) {
-        int wp = ip, shb = 0, shift = 0;
+        int wpos = ip, shb = 0, shift = 0;
         uint32_t acc = 0, cur = carry_tail;
         for (int k = packed; k < n;) {
-            const uint32_t c = Wb[wp] >> shb;
+            const uint32_t c = Wb[wpos] >> shb;
             shb += 8;
-            wp += shb >> 5;
+            wpos += shb >> 5;
             shb &= 31;
             acc += (c & 127u) << shift;
             if (c & 128u) {
                 cur += acc;
-                vals[sw_idx(nmini, k - packed)] = cur;
+                vals[nmini * kBlkLane + (k - packed)] = cur;
                 k++;
                 acc = 0;
                 shift = 0;
@@ -1719,7 +1763,7 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_filter_kernel(const
                 if (s < P.npfor) {
                     bool used = false;
                     for (int fi = 0; fi < P.nfilter; fi++) used = used || S.filter[fi].pfor_slot == s;
-                    if (used) base[s] = pfor_decode_warp(s_pfor[s].words, wo0[s], wo1[s], n, Wb, P.blk_words_cap, vals0 + s * kBlkRows, lane);
+                    if (used) base[s] = pfor_decode_warp(s_pfor[s].words, wo0[s], wo1[s], n, Wb, P.blk_words_cap, vals0 + s * kBlkVals, lane);
                 }
             }
             const int nwords = (n + 31) >> 5;
@@ -1736,11 +1780,11 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_filter_kernel(const
 #pragma unroll
                     for (int s = 0; s < kMaxPforCols; s++)
                         if (s == f.pfor_slot) b = base[s];
-                    const uint32_t* vp = vals0 + f.pfor_slot * kBlkRows + lane * 32;
+                    const uint32_t* vp = vals0 + f.pfor_slot * kBlkVals + lane * kBlkLane;
                     const uint32_t lo = (uint32_t)f.lo - b;
                     uint32_t word = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) word |= (uint32_t)((vp[(j + lane) & 31] - lo) <= f.span) << j;
+                    for (int j = 0; j < 32; j++) word |= (uint32_t)((vp[j] - lo) <= f.span) << j;
                     myword &= word;
                 } else {
                     // dense column: row per lane (coalesced), one ballot per 32 rows
@@ -1834,7 +1878,7 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const _
             if (s < P.npfor) {
                 bool used = false;
                 for (int pc = 0; pc < P.nproj; pc++) used = used || s_proj[pc].pfor_slot == s;
-                if (used) base[s] = pfor_decode_warp(s_pfor[s].words, wo0[s], wo1[s], n, Wb, P.blk_words_cap, vals0 + s * kBlkRows, lane);
+                if (used) base[s] = pfor_decode_warp(s_pfor[s].words, wo0[s], wo1[s], n, Wb, P.blk_words_cap, vals0 + s * kBlkVals, lane);
             }
         }
         const int nwords = (n + 31) >> 5;
@@ -1852,7 +1896,7 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const _
 #pragma unroll
                     for (int s = 0; s < kMaxPforCols; s++)
                         if (s == pj.pfor_slot) b = base[s];
-                    const uint32_t v = vals0[pj.pfor_slot * kBlkRows + sw_idx(w, lane)] + __shfl_sync(0xFFFFFFFFu, b, w);
+                    const uint32_t v = vals0[pj.pfor_slot * kBlkVals + w * kBlkLane + lane] + __shfl_sync(0xFFFFFFFFu, b, w);
                     if (sel && dst < P.limit) reinterpret_cast<uint32_t*>(pj.out)[dst] = v;
                 } else if (sel && dst < P.limit) {
                     if (pj.width == 4) {
