@@ -1629,15 +1629,16 @@ __device__ __forceinline__ uint32_t pfor_decode_warp(const uint32_t* __restrict_
     {
         const int q = lane & 3, k = lane >> 2;
         const uint32_t before = q == 0 ? 0u : (0x01010100u << (8 * (3 - q)));  // selects the widths of the mini-blocks ahead of q
+        uint32_t myh = 0;
 #pragma unroll 1
         for (int s = 0; s < nsuper; s++) {
             const uint32_t h = Wb[ip];
-            if (k == s) {
-                mybits = (int)((h >> (24 - 8 * q)) & 0xFFu);
-                mypos = ip + 1 + (int)__dp4a(h, before, 0u);
-            }
+            const int pos = ip + 1 + (int)__dp4a(h, before, 0u);
+            mypos = k == s ? pos : mypos;  // (selects, not branches)
+            myh = k == s ? h : myh;
             ip += 1 + (int)__dp4a(h, 0x01010101u, 0u);
         }
+        mybits = (int)((myh >> (24 - 8 * q)) & 0xFFu);
         for (int m = nsuper * 4; m < nmini; m++) {
             const int b = (int)Wb[ip++];
             if (m == lane) { mypos = ip; mybits = b; }
@@ -1750,38 +1751,26 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_filter_kernel(const
             else if (lane < 2 + 2 * P.npfor) meta = s_pfor[(lane - 2) >> 1].word_off[blk + (lane & 1)];
             const long long R0 = (long long)__shfl_sync(0xFFFFFFFFu, meta, 0);
             const int n = (int)((long long)__shfl_sync(0xFFFFFFFFu, meta, 1) - R0);
-            uint32_t wo0[kMaxPforCols], wo1[kMaxPforCols];
-#pragma unroll
-            for (int s = 0; s < kMaxPforCols; s++) {
-                wo0[s] = (uint32_t)__shfl_sync(0xFFFFFFFFu, meta, 2 + 2 * s);
-                wo1[s] = (uint32_t)__shfl_sync(0xFFFFFFFFu, meta, 3 + 2 * s);
-            }
-            uint32_t base[kMaxPforCols];
-#pragma unroll
-            for (int s = 0; s < kMaxPforCols; s++) {
-                base[s] = 0;
-                if (s < P.npfor) {
-                    bool used = false;
-                    for (int fi = 0; fi < P.nfilter; fi++) used = used || S.filter[fi].pfor_slot == s;
-                    if (used) base[s] = pfor_decode_warp(s_pfor[s].words, wo0[s], wo1[s], n, Wb, P.blk_words_cap, vals0 + s * kBlkVals, lane);
-                }
-            }
             const int nwords = (n + 31) >> 5;
             {   // rows of the block that exist: lane w owns word w = rows [32w, 32w+32)
                 const int left = n - lane * 32;
                 myword = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
             }
+            int decoded = -1;   // PFOR slot whose block sits in vals0 (one buffer: the filter kernel keeps no decoded column)
+            uint32_t base = 0;
 #pragma unroll 1
             for (int fi = 0; fi < P.nfilter; fi++) {
                 const FilterCol f = S.filter[fi];
                 if (f.kind == kFilterI32Range && f.pfor_slot >= 0) {
                     // decoded column: lane m tests its own mini-block (the values it just unpacked) - no ballots
-                    uint32_t b = 0;
-#pragma unroll
-                    for (int s = 0; s < kMaxPforCols; s++)
-                        if (s == f.pfor_slot) b = base[s];
-                    const uint32_t* vp = vals0 + f.pfor_slot * kBlkVals + lane * kBlkLane;
-                    const uint32_t lo = (uint32_t)f.lo - b;
+                    if (f.pfor_slot != decoded) {  // (two predicates on one column share the decode)
+                        const uint32_t wo0 = (uint32_t)__shfl_sync(0xFFFFFFFFu, meta, 2 + 2 * f.pfor_slot);
+                        const uint32_t wo1 = (uint32_t)__shfl_sync(0xFFFFFFFFu, meta, 3 + 2 * f.pfor_slot);
+                        base = pfor_decode_warp(s_pfor[f.pfor_slot].words, wo0, wo1, n, Wb, P.blk_words_cap, vals0, lane);
+                        decoded = f.pfor_slot;
+                    }
+                    const uint32_t* vp = vals0 + lane * kBlkLane;
+                    const uint32_t lo = (uint32_t)f.lo - base;
                     uint32_t word = 0;
 #pragma unroll
                     for (int j = 0; j < 32; j++) word |= (uint32_t)((vp[j] - lo) <= f.span) << j;
@@ -1852,6 +1841,9 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const _
     uint32_t* const Wb = reinterpret_cast<uint32_t*>(dyn_smem) + warp * blk_warp_smem_words(P.npfor, P.blk_words_cap);
     uint32_t* const vals0 = Wb + P.blk_words_cap;
     const long long warp0 = (long long)blockIdx.x * kComputeWarps + warp, nwarps = (long long)gridDim.x * kComputeWarps;
+    unsigned used_slots = 0;  // PFOR columns of the select list
+    for (int pc = 0; pc < P.nproj; pc++)
+        if (s_proj[pc].pfor_slot >= 0) used_slots |= 1u << s_proj[pc].pfor_slot;
     for (long long blk = warp0; blk < nblocks; blk += nwarps) {
         const long long t8 = blk & ~7ll;
         const unsigned c = (lane < 8 && t8 + lane < nblocks) ? __ldg(blk_cnt + t8 + lane) : 0u;  // the tile's block counts
@@ -1876,9 +1868,7 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const _
         for (int s = 0; s < kMaxPforCols; s++) {
             base[s] = 0;
             if (s < P.npfor) {
-                bool used = false;
-                for (int pc = 0; pc < P.nproj; pc++) used = used || s_proj[pc].pfor_slot == s;
-                if (used) base[s] = pfor_decode_warp(s_pfor[s].words, wo0[s], wo1[s], n, Wb, P.blk_words_cap, vals0 + s * kBlkVals, lane);
+                if ((used_slots >> s) & 1u) base[s] = pfor_decode_warp(s_pfor[s].words, wo0[s], wo1[s], n, Wb, P.blk_words_cap, vals0 + s * kBlkVals, lane);
             }
         }
         const int nwords = (n + 31) >> 5;
