@@ -282,6 +282,7 @@ struct Prepared {
     bool for_bitmap = false;    // imm3_filter_bitmap: the canonical-row bitmap comes from the single-pass kernels
     int grid_blocks_emit = 0;
     int grid_emit = 0;
+    bool emit_general = false;  // select list needs the general gather kernel (> 4 columns or a width other than 1/2/4)
     int grid_emit_stream = 0, emit_stage_bytes = 0, emit_ring = 0;  // streaming emit kernel (dense results); 0 = not usable
     std::string shape_key;    // key of imm3_db::emit_hint
     size_t emit_smem = 0;
@@ -456,7 +457,9 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
             pr->dyn_smem = (size_t)stages * (size_t)stage_bytes;
             CUDA_TRY(filter_kernel_occupancy(pr->dyn_smem, &occ));
             int occ_emit = 0;
-            CUDA_TRY(emit_kernel_occupancy(&occ_emit));
+            pr->emit_general = sp.nproj > 4 || getenv("IMM3_EMIT_GENERAL");
+            for (int i = 0; i < sp.nproj; i++) pr->emit_general = pr->emit_general || !(sp.proj[i].width == 1 || sp.proj[i].width == 2 || sp.proj[i].width == 4);
+            CUDA_TRY(emit_kernel_occupancy(pr->emit_general, &occ_emit));
             const int64_t nspans = sp.ntiles * (tile_rows / 1024);
             pr->grid_emit = (int)std::max<int64_t>(1, std::min<int64_t>((nspans + 7) / 8, (int64_t)db->num_sms * std::max(1, occ_emit)));
             // Streaming emit kernel (dense results): a stage = bitmap words + span counts + one 8192-row tile of every
@@ -623,7 +626,8 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
             }
             if (!only_stream) {
                 CUDA_TRY(launch_emit(pr->sp, pr->sp.bitmap, (const uint32_t*)db->d_span_cnt.p, (const unsigned long long*)db->d_tile_off.p, 8,
-                                     nspans, pr->grid_emit, stream_ok && !only_gather, db->d_ctrl, pdl && (only_gather || !stream_ok), db->stream));
+                                     nspans, pr->grid_emit, stream_ok && !only_gather, db->d_ctrl, pr->emit_general, pdl && (only_gather || !stream_ok),
+                                     db->stream));
                 (*launches)++;
             }
         }

@@ -1472,12 +1472,162 @@ __device__ __forceinline__ int emit_class_dense(const ScanCtrl* ctrl) {
     return (total > 0 && dense * 2ull >= total) ? 1 : 0;
 }
 
-// K3, sparse results (and the fallback when the projected columns are too wide to stage): one warp per group of 8
-// spans = one 8192-row tile.  The group's bitmap words are fetched up front, the surviving rows of consecutive spans
-// are appended to ONE warp-private selection vector and emitted together - a short vector through the fused
-// multi-column gather (one global round trip for all columns), a long one column by column; spans with all 1024 rows
-// selected are copied straight.
+// K3, sparse results: one warp per group of 8 spans = one 8192-row tile.  Two kernels, chosen on the host by the select
+// list:
+//   emit_kernel          up to 4 columns of width 1/2/4 (can_emit_fused).
+//     * The next group's metadata is always in flight: its span counts and tile offset in registers, its 256 bitmap
+//       words on their way into a warp-private shared-memory buffer (LDGSTS, double-buffered), so a group exposes ONE
+//       global round trip - its gathers.
+//     * The eight spans' lane counts are scanned together (two 16-bit counts per register: 20 shuffles per group, not
+//       40); surviving rows are appended span by span to one warp-private selection vector (flushed when the next span
+//       would not fit) and gathered 128 at a time - each lane issues the loads of 4 rows x all columns before its first
+//       store.
+//   emit_general_kernel  any select list: span by span, full spans copied straight, long vectors column by column.
+constexpr int kEmitWarpSmemBytes = 2048 + 2 * 1024;  // selection vector (1024 x u16) + two buffers of 256 bitmap words
+
 __global__ void __launch_bounds__(kComputeThreads, IMM3_EMIT_MIN_BLOCKS) emit_kernel(const __grid_constant__ ScanPlan P, const uint32_t* __restrict__ bitmap,
+                                                                 const uint32_t* __restrict__ span_cnt,
+                                                                 const unsigned long long* __restrict__ tile_off, int spans_per_tile,
+                                                                 long long nspans, int dense_off, const ScanCtrl* ctrl) {
+    __shared__ struct { FilterCol filter[kMaxFilterCols]; ProjCol proj[kMaxProjCols]; } SE;
+    copy_plan_tables(P, SE.filter, SE.proj, threadIdx.x, kComputeThreads);
+    __syncthreads();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    (void)spans_per_tile;
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // (a programmatic dependent of the filter kernel when it is the only emit kernel)
+    if (__ldcg(&ctrl->total) == 0ull) return;            // nothing survived the predicates
+    if (dense_off && emit_class_dense(ctrl)) return;     // the streaming emit kernel takes dense results
+    const long long warp0 = (long long)blockIdx.x * kComputeWarps + warp, nwarps = (long long)gridDim.x * kComputeWarps;
+    const long long ngroups = (nspans + 7) >> 3;
+    const uint32_t sel_addr = smem_u32(dyn_smem + warp * kEmitWarpSmemBytes), bm_addr = sel_addr + 2048u;
+
+    unsigned c_n = 0;
+    unsigned long long toff_n = 0;
+    auto load_group = [&](long long u, int buf) {  // independent loads, pinned in place
+        const long long p0 = u * 8;
+        c_n = 0;
+        if (lane < 8 && p0 + lane < nspans) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(c_n) : "l"(span_cnt + p0 + lane) : "memory");
+        asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(toff_n) : "l"(tile_off + u) : "memory");
+        // lane l copies words [8l, 8l+8) of the group = a quarter of span l/4
+        const uint32_t dst = bm_addr + (uint32_t)buf * 1024u + (uint32_t)lane * 32u;
+        if (p0 + (lane >> 2) < nspans) {
+            const uint32_t* src = bitmap + p0 * 32 + lane * 8;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u), "l"(src + 4) : "memory");
+        } else {
+            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst + 16u), "r"(0u) : "memory");
+        }
+    };
+    int buf = 0;
+    if (warp0 < ngroups) load_group(warp0, 0);
+#pragma unroll 1
+    for (long long u = warp0; u < ngroups; u += nwarps, buf ^= 1) {
+        const long long p0 = u * 8;  // first span of the group (a group = one 8192-row tile; spans_per_tile is 8)
+        const unsigned c = c_n;
+        const unsigned long long toff = toff_n;
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        const uint32_t bm_cur = bm_addr + (uint32_t)buf * 1024u + (uint32_t)lane * 4u;  // word k of this lane: + 128 k
+        if (u + nwarps < ngroups) load_group(u + nwarps, buf ^ 1);
+        const unsigned in_group = __reduce_add_sync(0xFFFFFFFFu, lane < 8 ? c : 0u);
+        if (in_group == 0) continue;
+        long long g0 = (long long)toff;  // ordinal of the first surviving row not emitted yet
+        if (g0 >= P.limit) continue;
+        // ---- lane offsets of all eight spans in one go ----
+        uint32_t pk[4], inc[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            inc[q] = pk[q] = (uint32_t)__popc(lds_cell<uint32_t>(bm_cur + 256u * q)) | ((uint32_t)__popc(lds_cell<uint32_t>(bm_cur + 256u * q + 128u)) << 16);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc[q], o);
+                if (lane >= o) inc[q] += t;
+            }
+        }
+        const long long row0 = p0 * 1024;
+        uint32_t fill = 0;  // rows in the selection vector; the first of them is global ordinal g0
+#pragma unroll 1
+        for (int k = 0; k <= 8; k++) {
+            uint32_t excl = 0, n_k = 0;
+            if (k < 8) {
+                const int q = k >> 1, sh = 16 * (k & 1);
+                const uint32_t iq = q == 0 ? inc[0] : (q == 1 ? inc[1] : (q == 2 ? inc[2] : inc[3]));
+                const uint32_t pq = q == 0 ? pk[0] : (q == 1 ? pk[1] : (q == 2 ? pk[2] : pk[3]));
+                excl = ((iq - pq) >> sh) & 0xFFFFu;
+                n_k = (__shfl_sync(0xFFFFFFFFu, iq, 31) >> sh) & 0xFFFFu;
+                if (n_k == 0) continue;
+            }
+            if (k == 8 || fill + n_k > 1024u) {
+                // ---- gather what the vector holds: 128 rows per round, all loads of a round before its first store ----
+                __syncwarp();
+                const int nn = (int)(P.limit - g0 < (long long)fill ? P.limit - g0 : (long long)fill);
+#pragma unroll 1
+                for (int b0 = 0; b0 < nn; b0 += 128) {
+                    int idx[4];  // row within the group, -1 = no row
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const int i = b0 + lane + 32 * r;
+                        idx[r] = i < nn ? (int)lds_cell<uint16_t>(sel_addr + 2u * (uint32_t)i) : -1;
+                    }
+                    uint32_t v[4][4];
+#pragma unroll
+                    for (int pc = 0; pc < 4; pc++) {
+                        if (pc < P.nproj) {
+                            const int w = SE.proj[pc].width;
+                            const uint8_t* cbase = SE.proj[pc].base + row0 * w;
+                            if (w == 4) {
+#pragma unroll
+                                for (int r = 0; r < 4; r++) v[r][pc] = idx[r] >= 0 ? __ldg(reinterpret_cast<const uint32_t*>(cbase) + idx[r]) : 0u;
+                            } else if (w == 1) {
+#pragma unroll
+                                for (int r = 0; r < 4; r++) v[r][pc] = idx[r] >= 0 ? (uint32_t)__ldg(cbase + idx[r]) : 0u;
+                            } else {
+#pragma unroll
+                                for (int r = 0; r < 4; r++)
+                                    v[r][pc] = idx[r] >= 0 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(cbase) + idx[r]) : 0u;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int pc = 0; pc < 4; pc++) {
+                        if (pc < P.nproj) {
+                            const int w = SE.proj[pc].width;
+                            uint8_t* obase = SE.proj[pc].out + (g0 + b0 + lane) * w;
+#pragma unroll
+                            for (int r = 0; r < 4; r++) {
+                                if (idx[r] >= 0) {
+                                    if (w == 4) reinterpret_cast<uint32_t*>(obase)[32 * r] = v[r][pc];
+                                    else if (w == 1) obase[32 * r] = (uint8_t)v[r][pc];
+                                    else reinterpret_cast<uint16_t*>(obase)[32 * r] = (uint16_t)v[r][pc];
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                g0 += fill;
+                fill = 0;
+                if (k == 8 || g0 >= P.limit) break;
+            }
+            // ---- append span k ----
+            uint32_t addr = sel_addr + 2u * (fill + excl);
+            const uint32_t base = (uint32_t)k * 1024u + (uint32_t)lane * 32u;
+            uint32_t rm = __brev(lds_cell<uint32_t>(bm_cur + 128u * (uint32_t)k));  // leading zeros = index of the lowest set bit of the word
+            while (rm) {
+                const int b = __clz((int)rm);
+                sts_u16(addr, base + (uint32_t)b);
+                addr += 2u;
+                rm &= ~(0x80000000u >> b);
+            }
+            fill += n_k;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kComputeThreads, 2) emit_general_kernel(const __grid_constant__ ScanPlan P, const uint32_t* __restrict__ bitmap,
                                                                  const uint32_t* __restrict__ span_cnt,
                                                                  const unsigned long long* __restrict__ tile_off, int spans_per_tile,
                                                                  long long nspans, int dense_off, const ScanCtrl* ctrl) {
@@ -1488,6 +1638,7 @@ __global__ void __launch_bounds__(kComputeThreads, IMM3_EMIT_MIN_BLOCKS) emit_ke
     unsigned short* sel_w = reinterpret_cast<unsigned short*>(dyn_smem) + warp * 1024;
     (void)spans_per_tile;
     asm volatile("griddepcontrol.wait;" ::: "memory");  // (a programmatic dependent of the filter kernel when it is the only emit kernel)
+    if (__ldcg(&ctrl->total) == 0ull) return;            // nothing survived the predicates
     if (dense_off && emit_class_dense(ctrl)) return;  // the streaming emit kernel takes dense results
     const long long warp0 = (long long)blockIdx.x * kComputeWarps + warp, nwarps = (long long)gridDim.x * kComputeWarps;
 
@@ -2117,6 +2268,7 @@ static cudaError_t configure_once() {
         IMM3_SET_SMEM(emit_stream_kernel);
         IMM3_SET_SMEM(blocks_filter_kernel);
         IMM3_SET_SMEM(blocks_emit_kernel);
+        IMM3_SET_SMEM(emit_general_kernel);
         IMM3_SET_SMEM((scan_dense_kernel<true>));
         IMM3_SET_SMEM((scan_dense_kernel<false>));
         IMM3_SET_SMEM(filter_kernel<true>);
@@ -2153,10 +2305,11 @@ cudaError_t filter_kernel_occupancy(size_t dyn_smem, int* blocks_per_sm) {
     if (dyn_smem > 0) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, filter_kernel<true>, kComputeThreads + 32, dyn_smem);
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, filter_kernel<false>, kComputeThreads + 32, dyn_smem);
 }
-cudaError_t emit_kernel_occupancy(int* blocks_per_sm) {
+cudaError_t emit_kernel_occupancy(bool general, int* blocks_per_sm) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, emit_kernel, kComputeThreads, kComputeWarps * 1024 * 2);
+    if (general) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, emit_general_kernel, kComputeThreads, kComputeWarps * 1024 * 2);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, emit_kernel, kComputeThreads, kComputeWarps * kEmitWarpSmemBytes);
 }
 cudaError_t launch_filter(const ScanPlan& plan, uint32_t* bitmap, uint32_t* span_cnt, uint32_t* tile_cnt, unsigned long long* tile_off,
                           ScanCtrl* ctrl, int grid, size_t dyn_smem, cudaStream_t stream) {
@@ -2167,19 +2320,24 @@ cudaError_t launch_filter(const ScanPlan& plan, uint32_t* bitmap, uint32_t* span
     return cudaGetLastError();
 }
 cudaError_t launch_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* span_cnt, const unsigned long long* tile_off,
-                        int spans_per_tile, long long nspans, int grid, int dense_off, const ScanCtrl* ctrl, bool pdl, cudaStream_t stream) {
+                        int spans_per_tile, long long nspans, int grid, int dense_off, const ScanCtrl* ctrl, bool general, bool pdl,
+                        cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kComputeThreads);
-    cfg.dynamicSmemBytes = kComputeWarps * 1024 * 2;
+    cfg.dynamicSmemBytes = kComputeWarps * kEmitWarpSmemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (general) {
+        cfg.dynamicSmemBytes = kComputeWarps * 1024 * 2;
+        return cudaLaunchKernelEx(&cfg, emit_general_kernel, plan, bitmap, span_cnt, tile_off, spans_per_tile, nspans, dense_off, ctrl);
+    }
     return cudaLaunchKernelEx(&cfg, emit_kernel, plan, bitmap, span_cnt, tile_off, spans_per_tile, nspans, dense_off, ctrl);
 }
 size_t emit_stream_smem_bytes(int stage_bytes, int ring) { return (size_t)kComputeWarps * 1024 * 2 + (size_t)ring * (size_t)stage_bytes + 16; }

@@ -14,11 +14,12 @@ cudaError_t blocks_kernel_occupancy(size_t dyn_smem, int* blocks_per_sm);
 cudaError_t launch_scan_dense(const ScanPlan& plan, ScanCtrl* ctrl, unsigned long long* status, int grid, size_t dyn_smem,
                               cudaStream_t stream);
 cudaError_t filter_kernel_occupancy(size_t dyn_smem, int* blocks_per_sm);
-cudaError_t emit_kernel_occupancy(int* blocks_per_sm);
+cudaError_t emit_kernel_occupancy(bool general, int* blocks_per_sm);
 cudaError_t launch_filter(const ScanPlan& plan, uint32_t* bitmap, uint32_t* span_cnt, uint32_t* tile_cnt, unsigned long long* tile_off,
                           ScanCtrl* ctrl, int grid, size_t dyn_smem, cudaStream_t stream);
 cudaError_t launch_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* span_cnt, const unsigned long long* tile_off,
-                        int spans_per_tile, long long nspans, int grid, int dense_off, const ScanCtrl* ctrl, bool pdl, cudaStream_t stream);
+                        int spans_per_tile, long long nspans, int grid, int dense_off, const ScanCtrl* ctrl, bool general, bool pdl,
+                        cudaStream_t stream);
 size_t emit_stream_smem_bytes(int stage_bytes, int ring);
 int emit_stream_header_bytes();
 cudaError_t emit_stream_occupancy(size_t dyn_smem, int* blocks_per_sm);
