@@ -50,6 +50,7 @@ WORKLOADS = {
     "x_none": ("X select id, age where age = 127 (no match)", "DENSE_INT"),
     "x_all": ("X select id, age (no predicate)", "DENSE_INT"),
     "x_1pct": ("X select id, age where age = 7", "DENSE_INT"),
+    **{f"x_lt{t}": (f"C5 scattered: select id, age where age < {t} ({t} %)", "DENSE_INT") for t in (2, 3, 4, 5, 6, 8, 10, 25, 50)},
     "c5_limit10": ("C5 select id, age where (age > 18 and age < 30) limit 10", "DENSE_INT"),
     "c5_rare_limit10": ("C5 select id, state, age where (state = 'CA' and age = 7) limit 10", "DENSE_INT"),
 }
@@ -70,6 +71,8 @@ def build_query(workload: str, table: str, total_rows: int):
             sel = NoSelect
         if workload == "x_1pct":
             sel = Select("age", EQ(7))
+        if workload.startswith("x_lt"):
+            sel = Select("age", LT(int(workload[4:])))
         return Query(table, sel, Project(proj))
     if workload == "c5_limit10":
         return Query(table, And(Select("age", GT(18)), Select("age", LT(30))), Project(["id", "age"], 10))

@@ -1224,8 +1224,8 @@ __device__ void scan_tile_counts(FilterShared& S, const uint32_t* tile_cnt, unsi
     constexpr int kRound = kComputeThreads * 16;  // counts per round
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long running = 0;
-    unsigned long long dense = 0;  // rows selected in tiles with at least one selected row in 32 (this thread's share)
-    const unsigned dense_min = ((unsigned)dense_tile_rows + 31u) / 32u;
+    unsigned long long dense = 0;  // rows selected in dense tiles (>= kDenseTileMinRows of 8192; this thread's share)
+    const unsigned dense_min = dense_tile_rows == kDenseTileRowsPerWord ? (unsigned)kDenseTileMinRows : ((unsigned)dense_tile_rows + 31u) / 32u;
     const int my0 = warp * 512 + lane * 2;  // first count of this lane's pair 0 inside a round; pair j is 64 counts further
     uint2 nx[8];                            // the next round's counts, in flight while this round is scanned
 #pragma unroll
@@ -1465,8 +1465,8 @@ __device__ __forceinline__ bool can_emit_fused(const ProjCol* proj, int nproj) {
     return ok;
 }
 
-// Result class decided by K1's offset scan: dense = at least half of the selected rows live in tiles with >= 1 selected
-// row in 32 (those tiles are streamed); otherwise the rows are thinly spread and the gather kernel is the better fit.
+// Result class decided by K1's offset scan: dense = at least half of the selected rows live in tiles with at least
+// kDenseTileMinRows selected rows (those tiles are streamed); otherwise the rows are thinly spread and the gather kernel is the better fit.
 __device__ __forceinline__ int emit_class_dense(const ScanCtrl* ctrl) {
     const unsigned long long total = __ldcg(&ctrl->total), dense = __ldcg(&ctrl->dense_rows);
     return (total > 0 && dense * 2ull >= total) ? 1 : 0;
@@ -2060,8 +2060,8 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const _
 // K3, dense results: a persistent TMA-ring kernel.  Tile = 8192 rows (8 spans, one per compute warp).  The producer
 // warp knows every tile's match count and offset before it starts (K1 finished), so it prefetches, `ring` tiles
 // ahead, exactly what the tile needs: its 256 bitmap words and 8 span counts, plus - for a tile with at least
-// one selected row in 32 - the tile of every projected column as TMA bulk copies (whole DRAM pages instead
-// of one request per selected row; at >= 3 % selectivity nearly every 128-byte line would be fetched anyway).
+// kDenseTileMinRows (4.9 %) selected rows - the tile of every projected column as TMA bulk copies (whole DRAM pages
+// instead of one request per selected row; at that density most 128-byte lines would be fetched anyway).
 // Sparse tiles gather their few rows straight from global memory.  Empty tiles cost one count load.
 // The compute warps never wait on a global load of their own for a dense tile and never talk to each other.
 // Straight copy of `nbytes` staged bytes (shared address sb, 4-byte aligned) to an arbitrarily aligned global address:
@@ -2135,7 +2135,7 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 2) emit_stream_kernel(co
                     c = __ldcg(tile_cnt + tile);
                     off = (long long)__ldcg(tile_off + tile);
                     if (c == 0) continue;  // nothing selected: the compute warps never hear of this tile
-                    if (off < P.limit) mode = (can_stage && c * 32u >= (unsigned)kDenseTileRowsPerWord) ? 2u : 1u;  // else: LIMIT reached, stop
+                    if (off < P.limit) mode = (can_stage && c >= (unsigned)kDenseTileMinRows) ? 2u : 1u;  // else: LIMIT reached, stop
                 }
                 const int slot = rp.slot;
                 const unsigned use = rp.use;

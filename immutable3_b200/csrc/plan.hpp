@@ -16,6 +16,8 @@ constexpr int kMaxProjCols = 16;    // select-list length (duplicates allowed, P
 constexpr int kMaxPforCols = 4;     // PFOR_INT columns touched by one query
 constexpr int kLitPoolBytes = 512;  // MATCH literals of all filter columns, packed
 constexpr int kDenseTileRowsPerWord = 8192;  // dense kernel: 8 compute warps x 32 lanes x 32 rows per bitmap word
+constexpr int kDenseTileMinRows = 400;  // an 8192-row tile with at least this many selected rows (4.9 %) is streamed, not gathered:
+                                        // measured crossover of the two emit kernels (age < t sweep, 100 M rows: equal at 5 %)
 constexpr int kDenseMaxTileRows = 4 * kDenseTileRowsPerWord;  // tile = 8192 * W rows, W in {1, 2, 4}
 constexpr int kDenseThreads = 320;  // 8 compute warps + producer warp (tickets, TMA) + scanner-candidate warp
 constexpr int kBlockThreads = 256;  // block-mode kernel: threads per CTA
