@@ -414,15 +414,21 @@ def main():
     st0, st1 = statistics.mean(stage_ms[0]), statistics.mean(stage_ms[1])
     multi = launches >= 2 * args.steps  # filter kernel + emit kernel(s) per query
     if args.workload == "c4":
-        kname = "scan_blocks_kernel"
+        kname = ("blocks_filter_kernel -> blocks_emit_kernel (sorted-integer codec decoded warp-per-block; timed together)" if multi
+                 else "scan_blocks_kernel")
     elif multi:
         kname = "filter_kernel -> emit_stream_kernel | emit_kernel (one query = one launch of each; timed together)"
     else:
         kname = "scan_dense_kernel"
     # achieved = algorithmic bytes of the query / CUDA-event time of ALL its kernels (conservative: the numerator is the
     # SURVEY.md 8d lower bound on traffic, the denominator includes every stage and the gaps between them)
+    traffic = recorded_traffic(args.workload) if args.rows == 100_000_000 else None  # (the capture is of the 100 M-row table)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": recorded_traffic(args.workload), "peak_source": peak_src, "kernel": kname,
+                "traffic": traffic, "peak_source": peak_src, "kernel": kname,
+                # the DRAM bytes the query really moves (ncu) over the same time: how close the kernels run to the HBM
+                # roofline of their actual traffic (128-byte line fills make it ~3x the algorithmic bytes on C2)
+                "traffic_gbs": (traffic / (launch_ms * 1e-3) / 1e9) if traffic else None,
+                "traffic_frac": (traffic / (launch_ms * 1e-3) / 1e9 / peak) if traffic else None,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms_mean": launch_ms, "launch_ms_min": min(kernel_ms),
                 "stage_ms_mean": [st0, st1],
                 "stages": ({"note": "per-stage CUDA-event times need IMM3_NO_PDL=1 (the emit kernel is a programmatic dependent launch of the filter "
