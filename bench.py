@@ -53,6 +53,9 @@ WORKLOADS = {
     **{f"x_lt{t}": (f"C5 scattered: select id, age where age < {t} ({t} %)", "DENSE_INT") for t in (2, 3, 4, 5, 6, 8, 10, 25, 50)},
     "c5_limit10": ("C5 select id, age where (age > 18 and age < 30) limit 10", "DENSE_INT"),
     "c5_rare_limit10": ("C5 select id, state, age where (state = 'CA' and age = 7) limit 10", "DENSE_INT"),
+    "c5p_limit10": ("C5 sorted-int-codec id: select id, age where age < 10 limit 10", "PFOR_INT"),
+    "c5p_nolimit": ("C5 sorted-int-codec id: select id, age where age < 10", "PFOR_INT"),
+    "c5p_window_limit10": ("C5 sorted-int-codec id: select id where (id > L and id < H) limit 10, 1% window", "PFOR_INT"),
 }
 
 
@@ -76,6 +79,11 @@ def build_query(workload: str, table: str, total_rows: int):
         return Query(table, sel, Project(proj))
     if workload == "c5_limit10":
         return Query(table, And(Select("age", GT(18)), Select("age", LT(30))), Project(["id", "age"], 10))
+    if workload in ("c5p_limit10", "c5p_nolimit"):
+        return Query(table, Select("age", LT(10)), Project(["id", "age"], 10 if workload == "c5p_limit10" else 0))
+    if workload == "c5p_window_limit10":
+        lo, hi = total_rows // 2 - total_rows // 200, total_rows // 2 + total_rows // 200
+        return Query(table, And(Select("id", GT(lo)), Select("id", LT(hi))), Project(["id"], 10))
     if workload == "c5_rare_limit10":
         from immutable3_b200 import EQ
         return Query(table, And(Select("state", Match(["CA"])), Select("age", EQ(7))), Project(["id", "state", "age"], 10))
@@ -413,7 +421,7 @@ def main():
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
     st0, st1 = statistics.mean(stage_ms[0]), statistics.mean(stage_ms[1])
     multi = launches >= 2 * args.steps  # filter kernel + emit kernel(s) per query
-    if args.workload == "c4":
+    if WORKLOADS[args.workload][1] == "PFOR_INT":
         kname = ("blocks_filter_kernel -> blocks_emit_kernel (sorted-integer codec decoded warp-per-block; timed together)" if multi
                  else "scan_blocks_kernel")
     elif multi:

@@ -280,6 +280,8 @@ struct Prepared {
     bool multipass = false;   // dense tables: filter -> scan -> emit kernels instead of the fused single pass
     bool blocks_multi = false;  // block mode: warp-per-block filter kernel -> offset scan -> emit kernel (no look-back chain)
     bool for_bitmap = false;    // imm3_filter_bitmap: the canonical-row bitmap comes from the single-pass kernels
+    bool hybrid = false;        // block mode, no predicate on an encoded column: DENSE filter kernel (row space) -> block emit kernel
+    size_t blocks_emit_smem = 0;
     int grid_blocks_emit = 0;
     int grid_emit = 0;
     bool emit_general = false;  // select list needs the general gather kernel (> 4 columns or a width other than 1/2/4)
@@ -403,6 +405,38 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
     if (const char* e = getenv("IMM3_DEBUG")) sp.debug = (uint32_t)atoi(e);
 
     int occ = 0;
+    // one 8192-row sub-tile of every (dense) filter column, and where each column sits inside a TMA stage
+    auto dense_sub_bytes = [&]() {
+        int row_bytes = 0;
+        for (int i = 0; i < sp.nfilter; i++) row_bytes += sp.filter[i].width;
+        return kDenseTileRowsPerWord * row_bytes;
+    };
+    auto dense_stage_offsets = [&](int sub_bytes) {
+        const bool can_stage = !(db->flags & IMM3_OPEN_NO_TMA) && sub_bytes > 0 && sub_bytes <= 56 * 1024;
+        int off = 0;
+        for (int i = 0; i < sp.nfilter; i++) {
+            sp.filter[i].smem_off = can_stage ? off : -1;
+            off += kDenseTileRowsPerWord * sp.filter[i].width;
+        }
+        return can_stage;
+    };
+    // Multi-pass filter kernel (K1): tile = 8192 rows; a TMA ring of ~32 KiB, so that four CTAs share an SM.
+    auto config_dense_filter = [&]() -> cudaError_t {
+        const int stage_bytes = dense_sub_bytes();
+        const bool stage_ok = dense_stage_offsets(stage_bytes);
+        sp.words_per_lane = 1;
+        sp.ntiles = (t.nrows + kDenseTileRowsPerWord - 1) / kDenseTileRowsPerWord;
+        int stages = 0;
+        if (stage_ok) stages = std::max(2, std::min(kMaxFilterStages, (32 * 1024) / stage_bytes));
+        if (const char* e = getenv("IMM3_FILTER_STAGES")) {
+            int v = atoi(e);
+            if (stage_ok && v >= 2 && v <= kMaxFilterStages && (size_t)v * stage_bytes <= 200 * 1024) stages = v;
+        }
+        sp.stages = stages;
+        sp.stage_bytes = stage_bytes;
+        pr->dyn_smem = (size_t)stages * (size_t)stage_bytes;
+        return filter_kernel_occupancy(pr->dyn_smem, &occ);
+    };
     if (pr->block_mode) {
         if (t.max_block_rows > kMaxBlockRows)
             return fail(IMM3_ERR_UNSUPPORTED, "block-mode kernel stages blocks of at most %d rows, table %s has a block of %d",
@@ -411,51 +445,34 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
         pr->blocks_multi = !pr->for_bitmap && t.max_block_rows <= 1024 && (lp.limit <= 0 || lp.limit > (1 << 20)) &&
                            !(path && !strcmp(path, "fused"));
         if (pr->blocks_multi) {
+            bool filters_dense = true;
+            for (int i = 0; i < sp.nfilter; i++) filters_dense = filters_dense && sp.filter[i].pfor_slot < 0;
+            pr->hybrid = filters_dense && !getenv("IMM3_NO_HYBRID");
             sp.ntiles = (t.nblocks + 7) / 8;  // the offset scan works on tiles of 8 blocks
             int64_t cap = 0;  // per-warp scratch for the byte-swapped words of one encoded block
             for (int ci : pfor_cols) cap = std::max<int64_t>(cap, t.cols[(size_t)ci].max_block_words);
             sp.blk_words_cap = (int)std::min<int64_t>(1120, ((cap + 4 + 31) / 32) * 32);
             pr->dyn_smem = blocks_multi_smem_bytes(sp.npfor, sp.blk_words_cap);
+            pr->blocks_emit_smem = blocks_emit_smem_bytes(sp.npfor, sp.blk_words_cap);
             int occ_e = 0;
-            CUDA_TRY(blocks_multi_occupancy(pr->dyn_smem, &occ, &occ_e));
-            pr->grid_blocks_emit = (int)std::max<int64_t>(1, std::min<int64_t>(sp.ntiles, (int64_t)db->num_sms * std::max(1, occ_e)));
+            CUDA_TRY(blocks_multi_occupancy(pr->dyn_smem, pr->blocks_emit_smem, pr->hybrid ? nullptr : &occ, &occ_e));
+            if (occ_e < 1) return fail(IMM3_ERR_CUDA, "block emit kernel does not fit on an SM (dynamic shared memory %zu bytes)", pr->blocks_emit_smem);
+            pr->grid_blocks_emit = (int)std::max<int64_t>(1, std::min<int64_t>((t.nblocks + 7) / 8, (int64_t)db->num_sms * std::max(1, occ_e)));
+            if (pr->hybrid) {
+                // No predicate touches an encoded column: the dense filter kernel runs over the table's row space (dense
+                // columns are contiguous in HBM whatever the block framing) and only the emit kernel works per block.
+                CUDA_TRY(config_dense_filter());
+            }
         } else {
             sp.ntiles = t.nblocks;
             pr->dyn_smem = blocks_kernel_smem_bytes(sp.npfor, t.max_block_rows);
             CUDA_TRY(blocks_kernel_occupancy(pr->dyn_smem, &occ));
         }
     } else {
-        int row_bytes = 0;
-        for (int i = 0; i < sp.nfilter; i++) row_bytes += sp.filter[i].width;
-        const int sub_bytes = kDenseTileRowsPerWord * row_bytes;  // one 8192-row sub-tile of every filter column
-        const bool can_stage = !(db->flags & IMM3_OPEN_NO_TMA) && sub_bytes > 0 && sub_bytes <= 56 * 1024;
-        if (can_stage) {
-            int off = 0;
-            for (int i = 0; i < sp.nfilter; i++) {
-                sp.filter[i].smem_off = off;
-                off += kDenseTileRowsPerWord * sp.filter[i].width;
-            }
-        }
         if (pr->multipass) {
-            // Multi-pass filter kernel: tile = 8192 rows; a TMA ring of ~32 KiB, so that four CTAs share an SM.
+            CUDA_TRY(config_dense_filter());
             const int W = 1;
             const int tile_rows = kDenseTileRowsPerWord;
-            const int stage_bytes = sub_bytes;
-            const bool stage_ok = can_stage;
-            if (!stage_ok)
-                for (int i = 0; i < sp.nfilter; i++) sp.filter[i].smem_off = -1;
-            sp.words_per_lane = W;
-            sp.ntiles = (t.nrows + tile_rows - 1) / tile_rows;
-            int stages = 0;
-            if (stage_ok) stages = std::max(2, std::min(kMaxFilterStages, (32 * 1024) / stage_bytes));
-            if (const char* e = getenv("IMM3_FILTER_STAGES")) {
-                int v = atoi(e);
-                if (stage_ok && v >= 2 && v <= kMaxFilterStages && (size_t)v * stage_bytes <= 200 * 1024) stages = v;
-            }
-            sp.stages = stages;
-            sp.stage_bytes = stage_bytes;
-            pr->dyn_smem = (size_t)stages * (size_t)stage_bytes;
-            CUDA_TRY(filter_kernel_occupancy(pr->dyn_smem, &occ));
             int occ_emit = 0;
             pr->emit_general = sp.nproj > 4 || getenv("IMM3_EMIT_GENERAL");
             for (int i = 0; i < sp.nproj; i++) pr->emit_general = pr->emit_general || !(sp.proj[i].width == 1 || sp.proj[i].width == 2 || sp.proj[i].width == 4);
@@ -484,6 +501,8 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
                 pr->grid_emit_stream = (int)std::max<int64_t>(1, std::min<int64_t>(sp.ntiles * W, (int64_t)db->num_sms * std::max(1, occ_s)));
             }
         } else {
+            const int sub_bytes = dense_sub_bytes();
+            const bool can_stage = dense_stage_offsets(sub_bytes);
             // Fused kernel: a tile is NS sub-tiles of 8192 rows, NS such that a tile streams ~64 KiB of filter
             // columns: one offset hand-off per tile, so bigger tiles keep the scanner warp off the critical path.
             int NS = sub_bytes > 0 ? std::max(1, std::min(4, (64 * 1024) / sub_bytes)) : 4;
@@ -550,7 +569,30 @@ int ensure_buf(Buf* b, size_t bytes) {
 // Launch the kernels of one query and wait for the match count.
 int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launches, double* stage_ms = nullptr) {
     bool have_mid = false;
-    if (pr->block_mode && pr->blocks_multi) {
+    if (pr->block_mode && pr->hybrid) {
+        // dense filter kernel over the row space -> block emit kernel (decodes only blocks with surviving rows)
+        TableStore& t = *pr->table;
+        const int64_t ntiles = pr->sp.ntiles, nspans = ntiles * 8;
+        int rc;
+        if ((rc = ensure_buf(&db->d_bitmap, (size_t)(ntiles * kDenseTileRowsPerWord / 32 + 2) * 4))) return rc;
+        pr->sp.bitmap = (uint32_t*)db->d_bitmap.p;
+        if ((rc = ensure_buf(&db->d_span_cnt, (size_t)(nspans + 8) * 4))) return rc;
+        const size_t ntiles_pad = ((size_t)ntiles + 4095) / 4096 * 4096 + 16;  // whole rounds of the offset scan
+        if ((rc = ensure_buf(&db->d_tile_cnt, ntiles_pad * 4))) return rc;
+        if ((rc = ensure_buf(&db->d_tile_off, ntiles_pad * 8))) return rc;
+        CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
+        CUDA_TRY(launch_filter(pr->sp, pr->sp.bitmap, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
+                               (unsigned long long*)db->d_tile_off.p, db->d_ctrl, pr->grid, pr->dyn_smem, db->stream));
+        *launches = 1;
+        CUDA_TRY(cudaEventRecord(db->ev_mid, db->stream));
+        have_mid = true;
+        if (pr->sp.nproj > 0) {
+            CUDA_TRY(launch_blocks_emit(pr->sp, pr->sp.bitmap, (const uint32_t*)db->d_span_cnt.p, (const unsigned long long*)db->d_tile_off.p,
+                                        t.nblocks, db->d_ctrl, true, pr->grid_blocks_emit, pr->blocks_emit_smem, db->stream));
+            (*launches)++;
+        }
+        CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
+    } else if (pr->block_mode && pr->blocks_multi) {
         TableStore& t = *pr->table;
         const int64_t nblocks = t.nblocks, ntiles = pr->sp.ntiles;
         int rc;
@@ -568,7 +610,8 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
         have_mid = true;
         if (pr->sp.nproj > 0) {
             CUDA_TRY(launch_blocks_emit(pr->sp, (const uint32_t*)db->d_bitmap.p, (const uint32_t*)db->d_span_cnt.p,
-                                        (const unsigned long long*)db->d_tile_off.p, nblocks, pr->grid_blocks_emit, pr->dyn_smem, db->stream));
+                                        (const unsigned long long*)db->d_tile_off.p, nblocks, db->d_ctrl, false, pr->grid_blocks_emit,
+                                        pr->blocks_emit_smem, db->stream));
             (*launches)++;
         }
         CUDA_TRY(cudaEventRecord(db->ev1, db->stream));

@@ -1740,7 +1740,10 @@ __global__ void __launch_bounds__(kComputeThreads, 2) emit_general_kernel(const 
 constexpr int kBlkRows = 1024;        // largest block this pipeline takes
 constexpr int kBlkLane = 33;          // decoded values: mini-block m lives at vals[33 m .. 33 m + 32) - odd stride, so both the
 constexpr int kBlkVals = 32 * kBlkLane;  // lane-per-mini-block and the row-per-lane access patterns are bank-conflict-free
-__host__ __device__ constexpr int blk_warp_smem_words(int npfor, int words_cap) { return words_cap + npfor * kBlkVals; }
+// per warp, in words: the filter kernel keeps the block's byte-swapped words and ONE decoded column; the emit kernel keeps
+// the words, every decoded column of the select list, their mini-block bases and a 1024-entry selection vector
+__host__ __device__ constexpr int blk_warp_smem_words(int npfor, int words_cap) { return words_cap + (npfor > 0 ? kBlkVals : 0); }
+__host__ __device__ constexpr int blk_emit_warp_words(int npfor, int words_cap) { return words_cap + npfor * (kBlkVals + 32) + 512; }
 
 // One mini-block of 32 B-bit deltas, B known at compile time: every word index and shift folds to an immediate.
 template <int B>
@@ -1975,9 +1978,20 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_filter_kernel(const
     }
 }
 
-__global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const __grid_constant__ ScanPlan P, const uint32_t* __restrict__ bitmapB,
-                                                                           const uint32_t* __restrict__ blk_cnt,
-                                                                           const unsigned long long* __restrict__ tile_off, long long nblocks) {
+// Emit kernel of the block pipelines: one warp per reference block with at least one surviving row.
+//   ROWSPACE = false : bitmap written by blocks_filter_kernel (32 words per block, block-local alignment); a block's first
+//                      ordinal = tile offset + counts of the tile's earlier blocks.
+//   ROWSPACE = true  : bitmap written by the DENSE filter kernel over the table's row space (no predicate touches an
+//                      encoded column, so K1 never decodes anything): the block's bits start at bit R0 of that bitmap
+//                      (funnel shift of two words per lane); first ordinal = tile offset + span counts + popc of the
+//                      words of R0's span below R0.
+// The block's surviving rows go to a warp-private selection vector; encoded columns of the select list are decoded once
+// into shared memory; rows are emitted 128 per round, each lane fetching 4 rows x all columns before its first store.
+template <bool ROWSPACE>
+__global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const __grid_constant__ ScanPlan P, const uint32_t* __restrict__ bitmap,
+                                                                           const uint32_t* __restrict__ cnts,
+                                                                           const unsigned long long* __restrict__ tile_off, long long nblocks,
+                                                                           const ScanCtrl* ctrl) {
     __shared__ ProjCol s_proj[kMaxProjCols];
     __shared__ FilterCol s_filter[kMaxFilterCols];
     __shared__ PforCol s_pfor[kMaxPforCols];
@@ -1989,71 +2003,143 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const _
             if (tid == i) s_pfor[i] = P.pfor[i];
     }
     __syncthreads();
-    uint32_t* const Wb = reinterpret_cast<uint32_t*>(dyn_smem) + warp * blk_warp_smem_words(P.npfor, P.blk_words_cap);
+    if (__ldcg(&ctrl->total) == 0ull) return;  // nothing survived the predicates
+    uint32_t* const Wb = reinterpret_cast<uint32_t*>(dyn_smem) + warp * blk_emit_warp_words(P.npfor, P.blk_words_cap);
     uint32_t* const vals0 = Wb + P.blk_words_cap;
+    uint32_t* const bases = vals0 + P.npfor * kBlkVals;  // [slot][mini-block]: what to add to the stored prefix sums
+    unsigned short* const sel_w = reinterpret_cast<unsigned short*>(bases + P.npfor * 32);
+    const uint32_t sel_addr = smem_u32(sel_w);
     const long long warp0 = (long long)blockIdx.x * kComputeWarps + warp, nwarps = (long long)gridDim.x * kComputeWarps;
-    unsigned used_slots = 0;  // PFOR columns of the select list
-    for (int pc = 0; pc < P.nproj; pc++)
+    unsigned used_slots = 0;  // encoded columns of the select list
+    bool fused_ok = P.nproj <= 4;
+    for (int pc = 0; pc < P.nproj; pc++) {
         if (s_proj[pc].pfor_slot >= 0) used_slots |= 1u << s_proj[pc].pfor_slot;
+        fused_ok = fused_ok && (s_proj[pc].width == 4 || s_proj[pc].width == 2 || s_proj[pc].width == 1);
+    }
+    // block metadata in ONE round trip: lanes 0,1 = row ordinals, lanes 2+2s, 3+2s = word offsets of encoded column s
+    auto load_meta = [&](long long b) -> unsigned long long {
+        unsigned long long m = 0;
+        if (b < nblocks) {
+            if (lane < 2) m = P.row_start[b + lane];
+            else if (lane < 2 + 2 * P.npfor) m = s_pfor[(lane - 2) >> 1].word_off[b + (lane & 1)];
+        }
+        return m;
+    };
+    unsigned long long meta_n = load_meta(warp0);
+#pragma unroll 1
     for (long long blk = warp0; blk < nblocks; blk += nwarps) {
-        const long long t8 = blk & ~7ll;
-        const unsigned c = (lane < 8 && t8 + lane < nblocks) ? __ldg(blk_cnt + t8 + lane) : 0u;  // the tile's block counts
-        const unsigned mine = __shfl_sync(0xFFFFFFFFu, c, (int)(blk & 7));
-        if (mine == 0) continue;
-        long long g = (long long)__ldg(tile_off + (blk >> 3)) + __reduce_add_sync(0xFFFFFFFFu, lane < (int)(blk & 7) ? c : 0u);
-        if (g >= P.limit) continue;
-        const uint32_t myword = __ldg(bitmapB + blk * 32 + lane);
-        unsigned long long meta = 0;
-        if (lane < 2) meta = P.row_start[blk + lane];
-        else if (lane < 2 + 2 * P.npfor) meta = s_pfor[(lane - 2) >> 1].word_off[blk + (lane & 1)];
+        const unsigned long long meta = meta_n;
+        meta_n = load_meta(blk + nwarps);  // (in flight while this block is handled)
         const long long R0 = (long long)__shfl_sync(0xFFFFFFFFu, meta, 0);
         const int n = (int)((long long)__shfl_sync(0xFFFFFFFFu, meta, 1) - R0);
-        uint32_t wo0[kMaxPforCols], wo1[kMaxPforCols];
-#pragma unroll
-        for (int s = 0; s < kMaxPforCols; s++) {
-            wo0[s] = (uint32_t)__shfl_sync(0xFFFFFFFFu, meta, 2 + 2 * s);
-            wo1[s] = (uint32_t)__shfl_sync(0xFFFFFFFFu, meta, 3 + 2 * s);
+        uint32_t myword;  // lane w: rows [32w, 32w+32) of the block
+        long long g;      // ordinal of the block's first surviving row
+        if (ROWSPACE) {
+            const long long bit0 = R0 + 32 * lane;
+            const uint32_t lo = __ldg(bitmap + (bit0 >> 5)), hi = __ldg(bitmap + (bit0 >> 5) + 1);
+            const long long span = R0 >> 10;
+            const uint32_t sw = __ldg(bitmap + span * 32 + lane);                        // R0's span, word `lane`
+            const unsigned sc = lane < (int)(span & 7) ? __ldg(cnts + (span & ~7ll) + lane) : 0u;  // earlier spans of the tile
+            const unsigned long long toff = __ldg(tile_off + (span >> 3));
+            myword = __funnelshift_r(lo, hi, (uint32_t)(bit0 & 31));
+            const int left = n - lane * 32;
+            myword &= left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+            if (__ballot_sync(0xFFFFFFFFu, myword != 0u) == 0u) continue;
+            const long long wrow0 = (span << 10) + 32 * lane;  // first row of span word `lane`
+            const unsigned below = wrow0 + 32 <= R0 ? (unsigned)__popc(sw) : (wrow0 < R0 ? (unsigned)__popc(sw & ((1u << (int)(R0 - wrow0)) - 1u)) : 0u);
+            g = (long long)toff + __reduce_add_sync(0xFFFFFFFFu, sc + below);
+        } else {
+            const long long t8 = blk & ~7ll;
+            const unsigned c = (lane < 8 && t8 + lane < nblocks) ? __ldg(cnts + t8 + lane) : 0u;  // the tile's block counts
+            if (__shfl_sync(0xFFFFFFFFu, c, (int)(blk & 7)) == 0u) continue;
+            g = (long long)__ldg(tile_off + (blk >> 3)) + __reduce_add_sync(0xFFFFFFFFu, lane < (int)(blk & 7) ? c : 0u);
+            myword = __ldg(bitmap + blk * 32 + lane);
         }
-        uint32_t base[kMaxPforCols];
-#pragma unroll
-        for (int s = 0; s < kMaxPforCols; s++) {
-            base[s] = 0;
-            if (s < P.npfor) {
-                if ((used_slots >> s) & 1u) base[s] = pfor_decode_warp(s_pfor[s].words, wo0[s], wo1[s], n, Wb, P.blk_words_cap, vals0 + s * kBlkVals, lane);
-            }
-        }
-        const int nwords = (n + 31) >> 5;
-        for (int w = 0; w < nwords; w++) {
-            const uint32_t word = __shfl_sync(0xFFFFFFFFu, myword, w);
-            if (word == 0) continue;  // warp-uniform
-            const bool sel = (word >> lane) & 1u;
-            const long long dst = g + __popc(word & ((1u << lane) - 1u));
-            const int i = w * 32 + lane;
+        if (g >= P.limit) continue;
+        __syncwarp();  // (the previous block's readers are done with the scratch)
+        // decode the encoded columns of the select list
 #pragma unroll 1
-            for (int pc = 0; pc < P.nproj; pc++) {
-                const ProjCol& pj = s_proj[pc];
-                if (pj.pfor_slot >= 0) {
-                    uint32_t b = 0;
+        for (int s = 0; s < P.npfor; s++) {
+            if (!((used_slots >> s) & 1u)) continue;
+            const uint32_t wo0 = (uint32_t)__shfl_sync(0xFFFFFFFFu, meta, 2 + 2 * s);
+            const uint32_t wo1 = (uint32_t)__shfl_sync(0xFFFFFFFFu, meta, 3 + 2 * s);
+            const uint32_t b = pfor_decode_warp(s_pfor[s].words, wo0, wo1, n, Wb, P.blk_words_cap, vals0 + s * kBlkVals, lane);
+            bases[s * 32 + lane] = b;
+            __syncwarp();
+        }
+        // selection vector of the block (ascending rows)
+        const int cnt = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(myword));
+        append_selection(myword, lane, sel_w, 0u);
+        __syncwarp();
+        const int nn = (int)(P.limit - g < (long long)cnt ? P.limit - g : (long long)cnt);
+        if (fused_ok) {
+#pragma unroll 1
+            for (int b0 = 0; b0 < nn; b0 += 128) {
+                int idx[4];  // row within the block, -1 = no row
 #pragma unroll
-                    for (int s = 0; s < kMaxPforCols; s++)
-                        if (s == pj.pfor_slot) b = base[s];
-                    const uint32_t v = vals0[pj.pfor_slot * kBlkVals + w * kBlkLane + lane] + __shfl_sync(0xFFFFFFFFu, b, w);
-                    if (sel && dst < P.limit) reinterpret_cast<uint32_t*>(pj.out)[dst] = v;
-                } else if (sel && dst < P.limit) {
-                    if (pj.width == 4) {
-                        reinterpret_cast<uint32_t*>(pj.out)[dst] = __ldg(reinterpret_cast<const uint32_t*>(pj.base) + R0 + i);
-                    } else if (pj.width == 1) {
-                        pj.out[dst] = __ldg(pj.base + R0 + i);
-                    } else {
-                        const uint8_t* src = pj.base + (R0 + i) * pj.width;
-                        uint8_t* o = pj.out + dst * pj.width;
-                        for (int b = 0; b < pj.width; b++) o[b] = __ldg(src + b);
+                for (int r = 0; r < 4; r++) {
+                    const int i = b0 + lane + 32 * r;
+                    idx[r] = i < nn ? (int)lds_cell<uint16_t>(sel_addr + 2u * (uint32_t)i) : -1;
+                }
+                uint32_t v[4][4];
+#pragma unroll
+                for (int pc = 0; pc < 4; pc++) {
+                    if (pc < P.nproj) {
+                        const int w = s_proj[pc].width, slot = s_proj[pc].pfor_slot;
+                        if (slot >= 0) {
+                            const uint32_t* vs = vals0 + slot * kBlkVals;
+                            const uint32_t* bs = bases + slot * 32;
+#pragma unroll
+                            for (int r = 0; r < 4; r++) v[r][pc] = idx[r] >= 0 ? vs[(idx[r] >> 5) * kBlkLane + (idx[r] & 31)] + bs[idx[r] >> 5] : 0u;
+                        } else {
+                            const uint8_t* cbase = s_proj[pc].base + R0 * w;
+                            if (w == 4) {
+#pragma unroll
+                                for (int r = 0; r < 4; r++) v[r][pc] = idx[r] >= 0 ? __ldg(reinterpret_cast<const uint32_t*>(cbase) + idx[r]) : 0u;
+                            } else if (w == 1) {
+#pragma unroll
+                                for (int r = 0; r < 4; r++) v[r][pc] = idx[r] >= 0 ? (uint32_t)__ldg(cbase + idx[r]) : 0u;
+                            } else {
+#pragma unroll
+                                for (int r = 0; r < 4; r++)
+                                    v[r][pc] = idx[r] >= 0 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(cbase) + idx[r]) : 0u;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int pc = 0; pc < 4; pc++) {
+                    if (pc < P.nproj) {
+                        const int w = s_proj[pc].width;
+                        uint8_t* obase = s_proj[pc].out + (g + b0 + lane) * w;
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            if (idx[r] >= 0) {
+                                if (w == 4) reinterpret_cast<uint32_t*>(obase)[32 * r] = v[r][pc];
+                                else if (w == 1) obase[32 * r] = (uint8_t)v[r][pc];
+                                else reinterpret_cast<uint16_t*>(obase)[32 * r] = (uint16_t)v[r][pc];
+                            }
+                        }
                     }
                 }
             }
-            g += __popc(word);
+        } else {
+            // any select list: column by column, a row per lane
+#pragma unroll 1
+            for (int pc = 0; pc < P.nproj; pc++) {
+                const int w = s_proj[pc].width, slot = s_proj[pc].pfor_slot;
+                for (int i = lane; i < nn; i += 32) {
+                    const int row = (int)lds_cell<uint16_t>(sel_addr + 2u * (uint32_t)i);
+                    uint8_t* o = s_proj[pc].out + (g + i) * w;
+                    if (slot >= 0) {
+                        *reinterpret_cast<uint32_t*>(o) = vals0[slot * kBlkVals + (row >> 5) * kBlkLane + (row & 31)] + bases[slot * 32 + (row >> 5)];
+                    } else {
+                        const uint8_t* src = s_proj[pc].base + (R0 + row) * w;
+                        for (int b = 0; b < w; b++) o[b] = __ldg(src + b);
+                    }
+                }
+            }
         }
-        __syncwarp();  // the next block reuses the warp's shared-memory scratch
     }
 }
 
@@ -2267,7 +2353,8 @@ static cudaError_t configure_once() {
 #define IMM3_SET_SMEM(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e
         IMM3_SET_SMEM(emit_stream_kernel);
         IMM3_SET_SMEM(blocks_filter_kernel);
-        IMM3_SET_SMEM(blocks_emit_kernel);
+        IMM3_SET_SMEM(blocks_emit_kernel<true>);
+        IMM3_SET_SMEM(blocks_emit_kernel<false>);
         IMM3_SET_SMEM(emit_general_kernel);
         IMM3_SET_SMEM((scan_dense_kernel<true>));
         IMM3_SET_SMEM((scan_dense_kernel<false>));
@@ -2366,12 +2453,15 @@ cudaError_t launch_emit_stream(const ScanPlan& plan, const uint32_t* bitmap, con
 }
 
 size_t blocks_multi_smem_bytes(int npfor, int words_cap) { return (size_t)kComputeWarps * blk_warp_smem_words(npfor, words_cap) * 4; }
-cudaError_t blocks_multi_occupancy(size_t dyn_smem, int* filter_blocks_per_sm, int* emit_blocks_per_sm) {
+size_t blocks_emit_smem_bytes(int npfor, int words_cap) { return (size_t)kComputeWarps * blk_emit_warp_words(npfor, words_cap) * 4; }
+cudaError_t blocks_multi_occupancy(size_t filter_smem, size_t emit_smem, int* filter_blocks_per_sm, int* emit_blocks_per_sm) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(filter_blocks_per_sm, blocks_filter_kernel, kComputeThreads, dyn_smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(emit_blocks_per_sm, blocks_emit_kernel, kComputeThreads, dyn_smem);
+    if (filter_blocks_per_sm) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(filter_blocks_per_sm, blocks_filter_kernel, kComputeThreads, filter_smem);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(emit_blocks_per_sm, blocks_emit_kernel<true>, kComputeThreads, emit_smem);
 }
 cudaError_t launch_blocks_filter(const ScanPlan& plan, uint32_t* bitmapB, uint32_t* blk_cnt, uint32_t* tile_cnt, unsigned long long* tile_off,
                                  ScanCtrl* ctrl, long long nblocks, int grid, size_t dyn_smem, cudaStream_t stream) {
@@ -2380,11 +2470,12 @@ cudaError_t launch_blocks_filter(const ScanPlan& plan, uint32_t* bitmapB, uint32
     blocks_filter_kernel<<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks);
     return cudaGetLastError();
 }
-cudaError_t launch_blocks_emit(const ScanPlan& plan, const uint32_t* bitmapB, const uint32_t* blk_cnt, const unsigned long long* tile_off,
-                               long long nblocks, int grid, size_t dyn_smem, cudaStream_t stream) {
+cudaError_t launch_blocks_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* cnts, const unsigned long long* tile_off,
+                               long long nblocks, const ScanCtrl* ctrl, bool rowspace, int grid, size_t dyn_smem, cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    blocks_emit_kernel<<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_off, nblocks);
+    if (rowspace) blocks_emit_kernel<true><<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmap, cnts, tile_off, nblocks, ctrl);
+    else blocks_emit_kernel<false><<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmap, cnts, tile_off, nblocks, ctrl);
     return cudaGetLastError();
 }
 

@@ -27,11 +27,13 @@ cudaError_t launch_emit_stream(const ScanPlan& plan, const uint32_t* bitmap, con
                                const unsigned long long* tile_off, long long nsub, int ring, int stage_bytes, int dense_mode, int grid,
                                size_t dyn_smem, ScanCtrl* ctrl, bool pdl, cudaStream_t stream);
 size_t blocks_multi_smem_bytes(int npfor, int words_cap);
-cudaError_t blocks_multi_occupancy(size_t dyn_smem, int* filter_blocks_per_sm, int* emit_blocks_per_sm);
+size_t blocks_emit_smem_bytes(int npfor, int words_cap);
+cudaError_t blocks_multi_occupancy(size_t filter_smem, size_t emit_smem, int* filter_blocks_per_sm, int* emit_blocks_per_sm);
 cudaError_t launch_blocks_filter(const ScanPlan& plan, uint32_t* bitmapB, uint32_t* blk_cnt, uint32_t* tile_cnt, unsigned long long* tile_off,
                                  ScanCtrl* ctrl, long long nblocks, int grid, size_t dyn_smem, cudaStream_t stream);
-cudaError_t launch_blocks_emit(const ScanPlan& plan, const uint32_t* bitmapB, const uint32_t* blk_cnt, const unsigned long long* tile_off,
-                               long long nblocks, int grid, size_t dyn_smem, cudaStream_t stream);
+// rowspace: the bitmap / counts come from the dense filter kernel (row space), not from blocks_filter_kernel (block-local)
+cudaError_t launch_blocks_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* cnts, const unsigned long long* tile_off,
+                               long long nblocks, const ScanCtrl* ctrl, bool rowspace, int grid, size_t dyn_smem, cudaStream_t stream);
 cudaError_t launch_scan_blocks(const ScanPlan& plan, ScanCtrl* ctrl, unsigned long long* status, int grid, size_t dyn_smem,
                                cudaStream_t stream);
 
