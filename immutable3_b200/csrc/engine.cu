@@ -282,6 +282,7 @@ struct Prepared {
     bool for_bitmap = false;    // imm3_filter_bitmap: the canonical-row bitmap comes from the single-pass kernels
     bool hybrid = false;        // block mode, no predicate on an encoded column: DENSE filter kernel (row space) -> block emit kernel
     size_t blocks_emit_smem = 0;
+    int64_t prefix_blocks = 0;  // small LIMIT on a block table: the pipeline first runs over this many leading blocks (0 = no prefix)
     int grid_blocks_emit = 0;
     int grid_emit = 0;
     bool emit_general = false;  // select list needs the general gather kernel (> 4 columns or a width other than 1/2/4)
@@ -442,8 +443,16 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
             return fail(IMM3_ERR_UNSUPPORTED, "block-mode kernel stages blocks of at most %d rows, table %s has a block of %d",
                         kMaxBlockRows, t.meta.name.c_str(), t.max_block_rows);
         const char* path = getenv("IMM3_PATH");
-        pr->blocks_multi = !pr->for_bitmap && t.max_block_rows <= 1024 && (lp.limit <= 0 || lp.limit > (1 << 20)) &&
-                           !(path && !strcmp(path, "fused"));
+        pr->blocks_multi = !pr->for_bitmap && t.max_block_rows <= 1024 && !(path && !strcmp(path, "fused"));
+        // Small LIMIT: the multi-pass pipeline has no early exit, so it first runs over a prefix of the table (64 rows per
+        // requested row, at least 4 M rows); only if that does not fill the LIMIT is the whole table scanned.  (The
+        // single-pass kernel does stop early, but its look-back chain costs 13 ns per block when the rows come late.)
+        if (pr->blocks_multi && lp.limit > 0 && lp.limit <= (1 << 20) && !getenv("IMM3_NO_PREFIX")) {
+            const int64_t min_rows = getenv("IMM3_PREFIX_ROWS") ? std::max(1024, atoi(getenv("IMM3_PREFIX_ROWS"))) : (4 << 20);  // (tests shrink it)
+            const int64_t want_rows = std::max<int64_t>(min_rows, lp.limit * 64);
+            const int64_t nb = (want_rows + 1023) / 1024;
+            if (nb * 2 <= t.nblocks) pr->prefix_blocks = nb;
+        }
         if (pr->blocks_multi) {
             bool filters_dense = true;
             for (int i = 0; i < sp.nfilter; i++) filters_dense = filters_dense && sp.filter[i].pfor_slot < 0;
@@ -567,7 +576,7 @@ int ensure_buf(Buf* b, size_t bytes) {
 }
 
 // Launch the kernels of one query and wait for the match count.
-int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launches, double* stage_ms = nullptr) {
+int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launches, double* stage_ms, int64_t nblocks_use) {
     bool have_mid = false;
     if (pr->block_mode && pr->hybrid) {
         // dense filter kernel over the row space -> block emit kernel (decodes only blocks with surviving rows)
@@ -588,13 +597,14 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
         have_mid = true;
         if (pr->sp.nproj > 0) {
             CUDA_TRY(launch_blocks_emit(pr->sp, pr->sp.bitmap, (const uint32_t*)db->d_span_cnt.p, (const unsigned long long*)db->d_tile_off.p,
-                                        t.nblocks, db->d_ctrl, true, pr->grid_blocks_emit, pr->blocks_emit_smem, db->stream));
+                                        nblocks_use, db->d_ctrl, true, (int)std::min<int64_t>(pr->grid_blocks_emit, (nblocks_use + 7) / 8),
+                                        pr->blocks_emit_smem, db->stream));
             (*launches)++;
         }
         CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
     } else if (pr->block_mode && pr->blocks_multi) {
         TableStore& t = *pr->table;
-        const int64_t nblocks = t.nblocks, ntiles = pr->sp.ntiles;
+        const int64_t nblocks = nblocks_use, ntiles = pr->sp.ntiles;
         int rc;
         if ((rc = ensure_buf(&db->d_bitmap, (size_t)(nblocks * 32 + 2) * 4))) return rc;
         if ((rc = ensure_buf(&db->d_span_cnt, (size_t)(nblocks + 8) * 4))) return rc;
@@ -610,8 +620,8 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
         have_mid = true;
         if (pr->sp.nproj > 0) {
             CUDA_TRY(launch_blocks_emit(pr->sp, (const uint32_t*)db->d_bitmap.p, (const uint32_t*)db->d_span_cnt.p,
-                                        (const unsigned long long*)db->d_tile_off.p, nblocks, db->d_ctrl, false, pr->grid_blocks_emit,
-                                        pr->blocks_emit_smem, db->stream));
+                                        (const unsigned long long*)db->d_tile_off.p, nblocks, db->d_ctrl, false,
+                                        (int)std::min<int64_t>(pr->grid_blocks_emit, (nblocks + 7) / 8), pr->blocks_emit_smem, db->stream));
             (*launches)++;
         }
         CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
@@ -727,6 +737,41 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
             fclose(f);
         }
     }
+    return 0;
+}
+
+// Launch the kernels of one query and wait for the match count (see Prepared::prefix_blocks for the two-phase LIMIT).
+int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launches, double* stage_ms = nullptr) {
+    TableStore& t = *pr->table;
+    if (!(pr->block_mode && pr->blocks_multi && pr->prefix_blocks > 0)) return run_scan_once(db, pr, ms, total, launches, stage_ms, t.nblocks);
+    // phase A: the leading blocks only
+    const ScanPlan full = pr->sp;
+    const int grid_full = pr->grid;
+    const int64_t nb = pr->prefix_blocks;
+    if (pr->hybrid) {
+        pr->sp.nrows = (int64_t)t.row_start[(size_t)nb];
+        pr->sp.ntiles = (pr->sp.nrows + kDenseTileRowsPerWord - 1) / kDenseTileRowsPerWord;
+    } else {
+        pr->sp.ntiles = (nb + 7) / 8;
+    }
+    pr->grid = (int)std::max<int64_t>(1, std::min<int64_t>(pr->sp.ntiles, grid_full));
+    double ms_a = 0, st_a[2] = {0, 0};
+    int launches_a = 0;
+    int rc = run_scan_once(db, pr, &ms_a, total, &launches_a, st_a, nb);
+    pr->sp = full;
+    pr->grid = grid_full;
+    if (rc) return rc;
+    *ms = ms_a;
+    *launches = launches_a;
+    if (stage_ms) stage_ms[0] = st_a[0], stage_ms[1] = st_a[1];
+    if (*total >= pr->lp.limit) return 0;
+    // phase B: the prefix did not fill the LIMIT - the whole table
+    double ms_b = 0, st_b[2] = {0, 0};
+    int launches_b = 0;
+    if ((rc = run_scan_once(db, pr, &ms_b, total, &launches_b, st_b, t.nblocks))) return rc;
+    *ms += ms_b;
+    *launches += launches_b;
+    if (stage_ms) stage_ms[0] += st_b[0], stage_ms[1] += st_b[1];
     return 0;
 }
 

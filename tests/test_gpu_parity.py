@@ -354,6 +354,32 @@ def test_multipass_large_limit_and_mixed_density(tmp_path_factory):
                                 assert np.array_equal(got.column(c), exp.columns[c]), (table, sel, proj[c], limit)
 
 
+def test_small_limit_on_block_tables_runs_prefix_first(tmp_path_factory, monkeypatch):
+    """Small LIMIT on a table with a sorted-int-codec column: the pipeline first covers a prefix of the blocks and only
+    scans the whole table when the prefix does not fill the LIMIT.  Rows found early, late (id window at the end), never,
+    and a LIMIT that the prefix fills only partly must all give the oracle's exact cut."""
+    d = tmp_path_factory.mktemp("pfx")
+    n = 300_000
+    make_table(d, "pp", n, 1024, 40, seed=5, id_codec="PFOR_INT")
+    monkeypatch.setenv("IMM3_PREFIX_ROWS", "8192")
+    os.environ.pop("IMM3_PATH", None)
+    with O.Oracle(d) as orc, SegmentManager(d) as sm:
+        eng = Engine(sm)
+        cases = [(Select("age", LT(10)), ["id", "age"]),                                             # early, dense filter (row-space path)
+                 (conj(Select("id", GT(250_000)), Select("id", LT(260_000))), ["id", "state"]),       # late, filter on the encoded column
+                 (conj(Select("id", GT(4_000)), Select("age", EQ(7))), ["age", "id"]),                # straddles the prefix
+                 (conj(Select("state", Match(["CA"])), Select("age", EQ(3))), ["id", "state", "age"]),  # rare rows
+                 (Select("age", EQ(127)), ["id"]),                                                     # no rows at all
+                 (NoSelect, ["id"])]
+        for sel, proj in cases:
+            for limit in (1, 10, 100, 5000):
+                exp = orc.query("pp", oracle_preds(sel), proj, limit=limit)
+                with eng.execute(Query("pp", sel, Project(proj, limit))) as got:
+                    assert got.nrows == exp.nrows, (sel, limit, got.nrows, exp.nrows)
+                    for c in range(len(proj)):
+                        assert np.array_equal(got.column(c), exp.columns[c]), (sel, proj[c], limit)
+
+
 @pytest.mark.parametrize("seed", range(10))
 def test_random_tables_and_queries(tmp_path_factory, seed):
     """Randomised end-to-end parity: table shape (rows, block size, segment size, id codec and order), predicate set, select
