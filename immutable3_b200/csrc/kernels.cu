@@ -22,6 +22,7 @@
 // running (forward progress without relying on block scheduling order).  No spin is unbounded: a
 // watchdog traps instead of hanging the GPU.
 #include <cuda_runtime.h>
+#include <type_traits>
 
 #include <cstdint>
 
@@ -1368,6 +1369,12 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
         const long long full_tiles = P.nrows / kTile;              // tiles below this index have no rows past the end
         uint32_t* const bm_w0 = bitmap + warp * 32 + lane;
         uint32_t* const sc_w0 = span_cnt + warp;
+        // The loop is instantiated once per "filter program": the single-predicate forms that dominate in practice (range
+        // on a TINYINT column in its three sign modes, range on an INT column) have the predicate inlined - no call, no
+        // dispatch on kind per span; everything else takes the general body.
+        auto consume = [&](auto prog_tag) {
+        constexpr int PROG = decltype(prog_tag)::value;
+        const int hi0 = f0.lo + (int)f0.span;
         for (RingPos rp;; rp.advance(ring)) {
             const int slot = rp.slot;
             mbar_wait(smem_u32(&S.mbar_full[slot]), rp.use & 1u, nullptr);
@@ -1382,7 +1389,21 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
                 const long long left = P.nrows - (tile * kTile + warp * 1024 + lane * 32);
                 m = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
             }
-            if (P.debug & 2u) {
+            if (PROG >= 1 && PROG <= 3) {
+                m &= eval_i8<STAGED, PROG - 1>(stage_addr + (uint32_t)f0.smem_off + (uint32_t)cell, f0.base + tile * (kTile * f0.width) + cell, lane,
+                                               f0.lo, hi0);
+            } else if (PROG == 4) {
+                const uint32_t cs = stage_addr + (uint32_t)f0.smem_off + (uint32_t)cell;
+                const uint8_t* cg = f0.base + tile * (kTile * f0.width) + cell;
+                uint32_t mask = 0;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const int q = (c + lane) & 7;
+                    const uint4 v = ld16<STAGED>(cs + 16u * q, cg + 16 * q);
+                    mask |= range_i32_chunk(v, (uint32_t)f0.lo, f0.span) << (4 * q);
+                }
+                m &= mask;
+            } else if (P.debug & 2u) {
                 m = 0;  // timing experiment: stream the tiles, skip the predicate
             } else if (nf == 1) {
                 m &= eval_filter_span<STAGED>(stage_addr + (uint32_t)f0.smem_off + (uint32_t)cell, f0.base + tile * (kTile * f0.width) + cell, f0.kind,
@@ -1404,6 +1425,19 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
                 mbar_arrive(smem_u32(&S.mbar_empty[slot]));  // this warp is done with the slot's bytes
             }
             __syncwarp();
+        }
+        };
+        int prog = 0;
+        if (nf == 1 && !(P.debug & 2u)) {
+            if (f0.kind == kFilterI8Range) prog = f0.lo >= 0 ? 1 : (f0.lo + (int)f0.span < 0 ? 2 : 3);
+            else if (f0.kind == kFilterI32Range) prog = 4;
+        }
+        switch (prog) {
+            case 1: consume(std::integral_constant<int, 1>{}); break;
+            case 2: consume(std::integral_constant<int, 2>{}); break;
+            case 3: consume(std::integral_constant<int, 3>{}); break;
+            case 4: consume(std::integral_constant<int, 4>{}); break;
+            default: consume(std::integral_constant<int, 0>{}); break;
         }
     }
 
