@@ -2059,11 +2059,24 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const _
         }
         return m;
     };
-    unsigned long long meta_n = load_meta(warp0);
+    // What decides whether a block has work is in flight one block ahead: its metadata (row space: the block's bits are
+    // found through R0) or the block counts of its tile (block-local bitmap: only non-empty blocks fetch their metadata).
+    auto load_counts = [&](long long b) -> unsigned {
+        const long long t8 = b & ~7ll;
+        return (b < nblocks && lane < 8 && t8 + lane < nblocks) ? __ldg(cnts + t8 + lane) : 0u;
+    };
+    unsigned long long meta_n = ROWSPACE ? load_meta(warp0) : 0ull;
+    unsigned c_n = ROWSPACE ? 0u : load_counts(warp0);
 #pragma unroll 1
     for (long long blk = warp0; blk < nblocks; blk += nwarps) {
-        const unsigned long long meta = meta_n;
-        meta_n = load_meta(blk + nwarps);  // (in flight while this block is handled)
+        unsigned long long meta = meta_n;
+        const unsigned c = c_n;
+        if (ROWSPACE) meta_n = load_meta(blk + nwarps);
+        else c_n = load_counts(blk + nwarps);
+        if (!ROWSPACE) {
+            if (__shfl_sync(0xFFFFFFFFu, c, (int)(blk & 7)) == 0u) continue;
+            meta = load_meta(blk);
+        }
         const long long R0 = (long long)__shfl_sync(0xFFFFFFFFu, meta, 0);
         const int n = (int)((long long)__shfl_sync(0xFFFFFFFFu, meta, 1) - R0);
         uint32_t myword;  // lane w: rows [32w, 32w+32) of the block
@@ -2083,9 +2096,6 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const _
             const unsigned below = wrow0 + 32 <= R0 ? (unsigned)__popc(sw) : (wrow0 < R0 ? (unsigned)__popc(sw & ((1u << (int)(R0 - wrow0)) - 1u)) : 0u);
             g = (long long)toff + __reduce_add_sync(0xFFFFFFFFu, sc + below);
         } else {
-            const long long t8 = blk & ~7ll;
-            const unsigned c = (lane < 8 && t8 + lane < nblocks) ? __ldg(cnts + t8 + lane) : 0u;  // the tile's block counts
-            if (__shfl_sync(0xFFFFFFFFu, c, (int)(blk & 7)) == 0u) continue;
             g = (long long)__ldg(tile_off + (blk >> 3)) + __reduce_add_sync(0xFFFFFFFFu, lane < (int)(blk & 7) ? c : 0u);
             myword = __ldg(bitmap + blk * 32 + lane);
         }
