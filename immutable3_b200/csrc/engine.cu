@@ -105,6 +105,7 @@ struct imm3_db {
     bool host_only = false;
     std::vector<TableStore> tables;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // imm3_result_fetch_async: device->host copies overlap the next query's staging
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
     ScanCtrl* d_ctrl = nullptr;
     ScanCtrl* h_ctrl = nullptr;
@@ -131,6 +132,8 @@ struct imm3_result {
     std::vector<Buf> d_cols, h_cols;
     int64_t local_count = 0;
     int64_t fetched = 0;
+    int64_t pending = -1;        // rows of an imm3_result_fetch_async still in flight (-1 = none)
+    cudaEvent_t copied = nullptr;  // recorded on the copy stream after the last device->host copy
     double device_ms = 0;
     double stage_ms[2] = {0, 0};
     int launches = 0;
@@ -268,6 +271,7 @@ void free_device_side(imm3_db* db) {
     if (db->ev0) cudaEventDestroy(db->ev0);
     if (db->ev1) cudaEventDestroy(db->ev1);
     if (db->ev_mid) cudaEventDestroy(db->ev_mid);
+    if (db->copy_stream) cudaStreamDestroy(db->copy_stream);
     if (db->own_stream) cudaStreamDestroy(db->own_stream);
     cudaGetLastError();
 }
@@ -1024,6 +1028,40 @@ int imm3_result_fetch(imm3_result* r, int64_t nrows) {
     return 0;
 }
 
+int imm3_result_fetch_async(imm3_result* r, int64_t nrows) {
+    if (!r) return fail(IMM3_ERR_INVALID_ARG, "imm3_result_fetch_async: result is NULL");
+    if (nrows < 0 || nrows > r->local_count) return fail(IMM3_ERR_INVALID_ARG, "imm3_result_fetch_async: %lld rows of %lld", (long long)nrows, (long long)r->local_count);
+    imm3_db* db = r->db;
+    int rc = use_device(db);
+    if (rc) return rc;
+    if (!db->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&db->copy_stream, cudaStreamNonBlocking));
+    // (imm3_query_begin returned after the kernels had finished: the rows are final, the copy stream needs no event)
+    for (int i = 0; i < r->ncols; i++) {
+        const size_t bytes = (size_t)nrows * (size_t)r->widths[(size_t)i];
+        if (r->h_cols[(size_t)i].cap < bytes || !r->h_cols[(size_t)i].p) {
+            db->host_pool.release(r->h_cols[(size_t)i]);
+            r->h_cols[(size_t)i] = Buf();
+            if ((rc = db->host_pool.acquire(bytes, &r->h_cols[(size_t)i]))) return rc;
+        }
+        if (bytes) CUDA_TRY(cudaMemcpyAsync(r->h_cols[(size_t)i].p, r->d_cols[(size_t)i].p, bytes, cudaMemcpyDeviceToHost, db->copy_stream));
+    }
+    if (!r->copied) CUDA_TRY(cudaEventCreateWithFlags(&r->copied, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(r->copied, db->copy_stream));
+    r->pending = nrows;
+    return 0;
+}
+
+int imm3_result_wait(imm3_result* r) {
+    if (!r) return fail(IMM3_ERR_INVALID_ARG, "imm3_result_wait: result is NULL");
+    if (r->pending < 0) return 0;  // nothing in flight
+    int rc = use_device(r->db);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventSynchronize(r->copied));
+    r->fetched = r->pending;
+    r->pending = -1;
+    return 0;
+}
+
 int imm3_query(imm3_db* db, const char* table, const imm3_pred* preds, int npreds, const char* const* proj_cols,
                int nproj, int64_t limit, imm3_result** out) {
     imm3_result* r = nullptr;
@@ -1085,6 +1123,8 @@ int imm3_result_format_row(const imm3_result* r, int64_t row, char* buf, size_t 
 
 int imm3_result_free(imm3_result* r) {
     if (!r) return 0;
+    if (r->pending >= 0) cudaEventSynchronize(r->copied);  // never hand buffers back while a copy is reading them
+    if (r->copied) cudaEventDestroy(r->copied);
     for (auto& b : r->d_cols) r->db->dev_pool.release(b);
     for (auto& b : r->h_cols) r->db->host_pool.release(b);
     delete r;

@@ -173,6 +173,15 @@ class Result:
         L.check(self._lib.imm3_result_fetch(self._h, int(nrows)))
         return self
 
+    def fetch_async(self, nrows: int) -> "Result":
+        """Queue the device->host copies of the first `nrows` rows and return; `wait()` makes them readable."""
+        L.check(self._lib.imm3_result_fetch_async(self._h, int(nrows)))
+        return self
+
+    def wait(self) -> "Result":
+        L.check(self._lib.imm3_result_wait(self._h))
+        return self
+
     # -- accessors --
     @property
     def nrows(self) -> int:

@@ -144,6 +144,14 @@ int imm3_query_begin(imm3_db* db, const char* table, const imm3_pred* preds, int
                      const char* const* proj_cols, int nproj, int64_t limit, imm3_result** out);
 int64_t imm3_result_local_count(const imm3_result* r);
 int imm3_result_fetch(imm3_result* r, int64_t nrows);
+/* Asynchronous form of fetch: the device->host copies are queued on the handle's copy stream and
+ * the call returns; imm3_result_wait blocks until the rows are in host memory.  The consumer of
+ * the reference is lazy too - ProjectOp.ProjectIterator materialises rows as they are pulled
+ * (Project.scala:22-81) - so a caller can overlap the read-back of one query with staging the
+ * next one's inputs (imm3_reupload) over the full-duplex PCIe link.  The result (and its device
+ * buffers) must stay open until the wait has returned. */
+int imm3_result_fetch_async(imm3_result* r, int64_t nrows);
+int imm3_result_wait(imm3_result* r);
 
 /* Same query text the reference CLI takes (SQLParser.scala:8-129; SqlCli.scala:60). */
 int imm3_query_sql(imm3_db* db, const char* sql, imm3_result** out);

@@ -267,6 +267,34 @@ def test_reupload_from_pinned_host_mirror(world):
         check(orc, sm, "p", Select("id", GT(100)), ["id"])
 
 
+def test_async_fetch_overlaps_restaging_and_matches_sync(world):
+    """imm3_result_fetch_async / imm3_result_wait: the read-back of query i runs on the copy stream while the inputs of
+    query i+1 are re-staged and its kernels run; rows are identical to the synchronous fetch and to the oracle."""
+    d, tables, orc, sms = world
+    with SegmentManager(d, flags=OPEN_KEEP_HOST) as sm:
+        eng = Engine(sm)
+        sel = conj(Select("age", GT(18)), Select("age", LT(30)))
+        exp = orc.query("t", oracle_preds(sel), ["id", "age"], limit=0)
+        q = Query("t", sel, Project(["id", "age"]))
+        prev = None
+        for _ in range(4):
+            sm.reupload("t", ["age", "id"])
+            r = eng.begin(q)
+            assert r.local_count == exp.nrows
+            r.fetch_async(r.local_count)
+            if prev is not None:
+                prev.wait()
+                assert np.array_equal(prev.column(0), exp.columns[0]) and np.array_equal(prev.column(1), exp.columns[1])
+                prev.close()
+            prev = r
+        prev.wait().wait()  # a second wait is a no-op
+        assert prev.nrows == exp.nrows and np.array_equal(prev.column(0), exp.columns[0])
+        prev.close()
+        r = eng.begin(q)
+        r.fetch_async(10)
+        r.close()  # closing with a copy in flight waits for it
+
+
 def test_repeated_queries_reuse_buffers_and_epochs(world):
     d, tables, orc, sms = world
     sel = conj(Select("age", GT(18)), Select("age", LT(30)))
@@ -308,9 +336,9 @@ def test_full_size_synthetic_properties(tmp_path_factory):
 
 def test_full_size_sorted_int_codec_properties(tmp_path_factory):
     d = tmp_path_factory.mktemp("synp")
-    n = 6_000_000
+    n = 12_000_000  # large enough for the prefix-first LIMIT (4 M-row prefix) to be taken at its default size
     synth_write(d, "synp", n, id_codec=L.CODEC_PFOR_INT)
-    order = sorted(range(6), key=lambda i: f"id_{i}.dat")
+    order = sorted(range(12), key=lambda i: f"id_{i}.dat")
     age = np.concatenate([np.fromfile(d / "synp" / f"age_{i}.dat", np.int8) for i in order])
     per = 1024 * 1000 + 1
     ids = np.concatenate([np.arange(i * per, min(n, (i + 1) * per), dtype=np.int32) for i in order])
@@ -325,6 +353,14 @@ def test_full_size_sorted_int_codec_properties(tmp_path_factory):
             assert np.array_equal(r.column(0), ids[age == 7]) and np.all(r.column(1) == 7)
         with eng.execute(Query("synp", NoSelect, Project(["id"]))) as r:
             assert np.array_equal(r.column(0), ids)
+        # small LIMIT: filled by the prefix / only by the whole table (id window past the prefix) / never filled
+        with eng.execute(Query("synp", Select("age", LT(10)), Project(["id", "age"], 10))) as r:
+            assert r.nrows == 10 and np.array_equal(r.column(0), ids[age < 10][:10])
+        with eng.execute(Query("synp", conj(Select("id", GT(lo)), Select("id", LT(hi))), Project(["id"], 1000))) as r:
+            assert r.nrows == 1000 and np.array_equal(r.column(0), ids[mm][:1000])
+        with eng.execute(Query("synp", conj(Select("id", GT(n - 5)), Select("age", LT(100))), Project(["id", "age"], 100))) as r:
+            tail = (ids > n - 5)
+            assert r.nrows == int(tail.sum()) and np.array_equal(r.column(0), ids[tail])
 
 
 def test_multipass_large_limit_and_mixed_density(tmp_path_factory):
