@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libimm3gpu.so")
 
-SOURCES = ["meta.cpp", "writer.cpp", "plan.cpp", "sql.cpp", "store.cpp", "kernels.cu", "engine.cu"]
+SOURCES = ["meta.cpp", "writer.cpp", "plan.cpp", "sql.cpp", "store.cpp", "kernels.cu", "engine.cu", "encode.cu"]
 HEADERS = ["common.hpp", "json_min.hpp", "plan.hpp", "store.hpp", "kernels.hpp", "../../include/imm3.h"]
 
 NVCC_FLAGS = [

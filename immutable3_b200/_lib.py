@@ -82,6 +82,8 @@ SIGNATURES = {
     "imm3_writer_close": (C.c_int, [_P]),
     "imm3_load_csv": (C.c_int, [C.c_char_p, C.c_char_p, _STRS, C.c_int, C.c_int32, C.c_int32, C.c_char_p]),
     "imm3_pfor_encode": (C.c_int64, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_uint8), C.c_int64]),
+    "imm3_pfor_encode_blocks_gpu": (C.c_int64, [C.c_int, C.POINTER(C.c_int32), C.c_int64, C.c_int32, C.POINTER(C.c_uint8), C.c_int64,
+                                    C.POINTER(C.c_int64)]),
     "imm3_synth_write": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int]),
     "imm3_synth_row": (None, [C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int8), C.c_char_p]),
     "imm3_last_error": (C.c_char_p, []),

@@ -66,6 +66,20 @@ def pfor_encode(values) -> bytes:
     return bytes(out)
 
 
+def pfor_encode_blocks_gpu(values, block_rows: int = 1024, device: int = 0):
+    """PFORCodecInt.encode of a whole column on the GPU: (bytes of all blocks back to back, int64 block offsets)."""
+    lib = L.lib()
+    v = np.ascontiguousarray(values, dtype=np.int32)
+    p = v.ctypes.data_as(C.POINTER(C.c_int32))
+    nblocks = (len(v) + block_rows - 1) // block_rows
+    off = np.zeros(nblocks + 1, dtype=np.int64)
+    po = off.ctypes.data_as(C.POINTER(C.c_int64))
+    n = L.check(lib.imm3_pfor_encode_blocks_gpu(device, p, len(v), block_rows, None, 0, po))
+    out = np.zeros(max(n, 1), dtype=np.uint8)
+    L.check(lib.imm3_pfor_encode_blocks_gpu(device, p, len(v), block_rows, out.ctypes.data_as(C.POINTER(C.c_uint8)), n, po))
+    return out[:n].tobytes(), off
+
+
 def synth_segments(nrows: int, block_size: int, segment_size: int) -> int:
     rows_per_seg = block_size * segment_size + 1
     return (nrows + rows_per_seg - 1) // rows_per_seg

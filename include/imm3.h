@@ -204,6 +204,14 @@ int imm3_load_csv(const char* data_dir, const char* table, const char* const* co
 /* PFORCodecInt.encode (PFORCodec.scala:17-28): n int32 -> big-endian words + 8 zero bytes.
  * Returns bytes written or <0; call with out==NULL to size. */
 int64_t imm3_pfor_encode(const int32_t* values, int32_t n, uint8_t* out, int64_t out_cap);
+/* The same encoder on the GPU for a whole column: `n` values are cut into blocks of
+ * `block_rows` values (the SegmentWriter's blocks, Segment.scala:99-151: every block restarts the
+ * delta chain at 0), every block is encoded exactly as imm3_pfor_encode encodes it and the blocks are
+ * written back to back; block_off (nblocks+1 entries, may be NULL) receives their byte offsets -
+ * SegmentMeta.blockOffsets (Segment.scala:33).  block_rows: a multiple of 32, at most 1024.
+ * Returns the bytes written, or the bytes needed when out == NULL, or <0. */
+int64_t imm3_pfor_encode_blocks_gpu(int device, const int32_t* values, int64_t n, int32_t block_rows,
+                                    uint8_t* out, int64_t out_cap, int64_t* block_off);
 
 /* Deterministic synthetic tables of BASELINE.md (id=row index, age uniform [0,100), state uniform
  * over 51 two-letter codes; counter-based PRNG, seed 42).  Writes the canonical segments

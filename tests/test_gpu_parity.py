@@ -390,6 +390,32 @@ def test_multipass_large_limit_and_mixed_density(tmp_path_factory):
                                 assert np.array_equal(got.column(c), exp.columns[c]), (table, sel, proj[c], limit)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("block_rows", [1024, 256, 32])
+def test_gpu_sorted_int_encoder_is_bit_exact(block_rows):
+    """imm3_pfor_encode_blocks_gpu == the host encoder (== the oracle's, tests/test_oracle_kat.py) block by block: sorted
+    ids, equal values (width 0), wide and negative deltas (width 32, raw mini-blocks), every tail length, one short block."""
+    from immutable3_b200.loader import pfor_encode, pfor_encode_blocks_gpu
+    rng = np.random.default_rng(7 + block_rows)
+    cols = {
+        "row index": np.arange(10 * block_rows + 17, dtype=np.int64),
+        "steps": np.cumsum(rng.integers(0, 1000, 7 * block_rows + 5)),
+        "constant": np.full(3 * block_rows, 12345, dtype=np.int64),
+        "mixed widths": np.cumsum(np.where(rng.random(9 * block_rows + 31) < 0.02, rng.integers(0, 1 << 20, 9 * block_rows + 31), rng.integers(0, 4, 9 * block_rows + 31))),
+        "unsorted": rng.integers(-2**31, 2**31 - 1, 5 * block_rows + 1),
+        "short": np.arange(7, dtype=np.int64) * 300,
+        "one": np.array([300], dtype=np.int64),
+    }
+    for tail in range(0, 33, 5):
+        cols[f"tail {tail}"] = np.cumsum(rng.integers(0, 70000, 2 * block_rows + tail))
+    for name, v in cols.items():
+        v = v.astype(np.int64).astype(np.int32) if v.dtype != np.int32 else v
+        got, off = pfor_encode_blocks_gpu(v, block_rows)
+        exp = [pfor_encode(v[i:i + block_rows]) for i in range(0, len(v), block_rows)]
+        assert list(np.diff(off)) == [len(e) for e in exp], name
+        assert got == b"".join(exp), name
+
+
 def test_small_limit_on_block_tables_runs_prefix_first(tmp_path_factory, monkeypatch):
     """Small LIMIT on a table with a sorted-int-codec column: the pipeline first covers a prefix of the blocks and only
     scans the whole table when the prefix does not fill the LIMIT.  Rows found early, late (id window at the end), never,
