@@ -192,20 +192,36 @@ extern "C" int64_t imm3_pfor_encode_blocks_gpu(int device, const int32_t* values
     int* d_nwords = nullptr;
     long long* d_off = nullptr;
     uint8_t* d_out = nullptr;
+    bool own_values = false, own_out = false;
     auto release = [&]() {
-        cudaFree(d_values);
+        if (own_values) cudaFree(d_values);
         cudaFree(d_nwords);
         cudaFree(d_off);
-        cudaFree(d_out);
+        if (own_out) cudaFree(d_out);
         d_values = nullptr, d_nwords = nullptr, d_off = nullptr, d_out = nullptr;
     };
     CUDA_TRY(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    CUDA_TRY(cudaMalloc(&d_values, (size_t)(n + 32) * 4));  // (the width pass reads whole 16-byte groups)
-    CUDA_TRY(cudaMemcpy(d_values, values, (size_t)n * 4, cudaMemcpyHostToDevice));
+    int num_sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+    // `values` / `out` may live in device memory (tables generated or loaded on the device): then nothing is staged.
+    auto on_device = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+    };
+    if (on_device(values)) {
+        if ((reinterpret_cast<uintptr_t>(values) & 15u) != 0) return fail(IMM3_ERR_INVALID_ARG, "imm3_pfor_encode_blocks_gpu: device values must be 16-byte aligned");
+        d_values = const_cast<int32_t*>(values);
+    } else {
+        own_values = true;
+        CUDA_TRY(cudaMalloc(&d_values, (size_t)(n + 32) * 4));
+        CUDA_TRY(cudaMemcpy(d_values, values, (size_t)n * 4, cudaMemcpyHostToDevice));
+    }
     CUDA_TRY(cudaMalloc(&d_nwords, (size_t)nblocks * sizeof(int)));
-    const int grid = (int)std::min<int64_t>((nblocks + kEncWarps - 1) / kEncWarps, (int64_t)prop.multiProcessorCount * 8);
+    const int grid = (int)std::min<int64_t>((nblocks + kEncWarps - 1) / kEncWarps, (int64_t)num_sms * 8);
     pfor_block_sizes_kernel<<<grid, kEncWarps * 32>>>(d_values, n, block_rows, nblocks, d_nwords);
     CUDA_TRY(cudaGetLastError());
     std::vector<int> nwords((size_t)nblocks);
@@ -226,10 +242,17 @@ extern "C" int64_t imm3_pfor_encode_blocks_gpu(int device, const int32_t* values
     }
     CUDA_TRY(cudaMalloc(&d_off, ((size_t)nblocks + 1) * sizeof(long long)));
     CUDA_TRY(cudaMemcpy(d_off, off.data(), ((size_t)nblocks + 1) * sizeof(long long), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc(&d_out, (size_t)total));
+    if (on_device(out)) {
+        if ((reinterpret_cast<uintptr_t>(out) & 3u) != 0) { release(); return fail(IMM3_ERR_INVALID_ARG, "imm3_pfor_encode_blocks_gpu: device out must be 4-byte aligned"); }
+        d_out = out;
+    } else {
+        own_out = true;
+        CUDA_TRY(cudaMalloc(&d_out, (size_t)total));
+    }
     pfor_encode_blocks_kernel<<<grid, kEncWarps * 32>>>(d_values, n, block_rows, nblocks, d_off, d_out);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpy(out, d_out, (size_t)total, cudaMemcpyDeviceToHost));
+    if (own_out) CUDA_TRY(cudaMemcpy(out, d_out, (size_t)total, cudaMemcpyDeviceToHost));
+    else CUDA_TRY(cudaDeviceSynchronize());
     release();
     return total;
 }
