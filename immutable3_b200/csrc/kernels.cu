@@ -2059,23 +2059,37 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const _
         }
         return m;
     };
-    // What decides whether a block has work is in flight one block ahead: its metadata (row space: the block's bits are
-    // found through R0) or the block counts of its tile (block-local bitmap: only non-empty blocks fetch their metadata).
-    auto load_counts = [&](long long b) -> unsigned {
-        const long long t8 = b & ~7ll;
-        return (b < nblocks && lane < 8 && t8 + lane < nblocks) ? __ldg(cnts + t8 + lane) : 0u;
-    };
+    // A warp visits blocks warp0, warp0 + nwarps, ... (round robin, so that a clustered result spreads over all warps).
+    // Row space: the next block's metadata (its bits are found through R0) is in flight while this one is handled.
+    // Block-local bitmap: the counts of the warp's next 32 blocks are fetched in ONE round trip (a lane each) and only the
+    // non-empty ones (1 % of them for C4) are visited; those alone fetch their metadata and their tile's counts.
     unsigned long long meta_n = ROWSPACE ? load_meta(warp0) : 0ull;
-    unsigned c_n = ROWSPACE ? 0u : load_counts(warp0);
 #pragma unroll 1
-    for (long long blk = warp0; blk < nblocks; blk += nwarps) {
-        unsigned long long meta = meta_n;
-        const unsigned c = c_n;
-        if (ROWSPACE) meta_n = load_meta(blk + nwarps);
-        else c_n = load_counts(blk + nwarps);
+    for (long long it = 0;; it++) {
+        unsigned todo;  // blocks of this iteration still to handle (row space: bit 0)
+        const long long first = ROWSPACE ? warp0 + it * nwarps : warp0 + it * 32 * nwarps;  // block of lane 0 / of bit 0
+        if (first >= nblocks) break;
+        unsigned long long meta_it = 0;
+        if (ROWSPACE) {
+            meta_it = meta_n;
+            meta_n = load_meta(first + nwarps);
+            todo = 1u;
+        } else {
+            const long long b = first + lane * nwarps;
+            todo = __ballot_sync(0xFFFFFFFFu, b < nblocks && __ldg(cnts + b) != 0u);
+        }
+#pragma unroll 1
+        while (todo) {
+        const int src = __ffs((int)todo) - 1;
+        todo &= todo - 1u;
+        const long long blk = first + src * nwarps;
+        const unsigned long long meta = ROWSPACE ? meta_it : load_meta(blk);
+        unsigned tile_c = 0;                 // block-local: counts of the tile's blocks (lanes 0-7)
+        unsigned long long tile_o = 0;
         if (!ROWSPACE) {
-            if (__shfl_sync(0xFFFFFFFFu, c, (int)(blk & 7)) == 0u) continue;
-            meta = load_meta(blk);
+            const long long t8 = blk & ~7ll;
+            tile_c = (lane < 8 && t8 + lane < nblocks) ? __ldg(cnts + t8 + lane) : 0u;
+            tile_o = __ldg(tile_off + (blk >> 3));
         }
         const long long R0 = (long long)__shfl_sync(0xFFFFFFFFu, meta, 0);
         const int n = (int)((long long)__shfl_sync(0xFFFFFFFFu, meta, 1) - R0);
@@ -2096,7 +2110,7 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const _
             const unsigned below = wrow0 + 32 <= R0 ? (unsigned)__popc(sw) : (wrow0 < R0 ? (unsigned)__popc(sw & ((1u << (int)(R0 - wrow0)) - 1u)) : 0u);
             g = (long long)toff + __reduce_add_sync(0xFFFFFFFFu, sc + below);
         } else {
-            g = (long long)__ldg(tile_off + (blk >> 3)) + __reduce_add_sync(0xFFFFFFFFu, lane < (int)(blk & 7) ? c : 0u);
+            g = (long long)tile_o + __reduce_add_sync(0xFFFFFFFFu, lane < (int)(blk & 7) ? tile_c : 0u);
             myword = __ldg(bitmap + blk * 32 + lane);
         }
         if (g >= P.limit) continue;
@@ -2183,6 +2197,7 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const _
                     }
                 }
             }
+        }
         }
     }
 }
