@@ -1838,11 +1838,37 @@ __device__ __forceinline__ uint32_t pfor_decode_warp(const uint32_t* __restrict_
     const bool raw = mybits >= 32;
     const uint32_t* wp = Wb + mypos;
     uint32_t* vp = vals + lane * kBlkLane;
-    const int b0 = __shfl_sync(0xFFFFFFFFu, mybits, 0);
-    if (b0 <= 16 && __all_sync(0xFFFFFFFFu, lane >= nmini || mybits == b0)) {
-        // the usual case of a sorted column: one width for the whole block -> the fully specialised unpack
-        if (lane < nmini) {
-            switch (b0) {
+    // The usual shape of a sorted column's block: one width for (nearly) every mini-block, except the first one, whose
+    // first delta carries the block's absolute start value.  The mini-blocks of the majority width (<= 16 bits) take the
+    // fully specialised unpack; the few odd ones are decoded cooperatively first (a value per lane + a warp scan);
+    // anything less regular takes the generic per-lane loop.
+    const unsigned same = __match_any_sync(0xFFFFFFFFu, lane < nmini ? mybits : -1 - lane);
+    const unsigned vote = __reduce_max_sync(0xFFFFFFFFu, lane < nmini ? ((unsigned)__popc(same) << 8) | (unsigned)mybits : 0u);
+    const int bmode = (int)(vote & 0xFFu);
+    const unsigned odd = __ballot_sync(0xFFFFFFFFu, lane < nmini && mybits != bmode);
+    if (nmini > 0 && bmode <= 16 && __popc(odd) <= 4) {
+        for (unsigned rest = odd; rest; rest &= rest - 1u) {
+            const int m = __ffs((int)rest) - 1;
+            const int bm = __shfl_sync(0xFFFFFFFFu, mybits, m), pm = __shfl_sync(0xFFFFFFFFu, mypos, m);
+            uint32_t v;
+            if (bm >= 32) {
+                v = Wb[pm + lane];  // raw: the values themselves
+            } else {
+                const uint32_t off = (uint32_t)(lane * bm);
+                const uint32_t* p = Wb + pm + (off >> 5);
+                v = __funnelshift_r(p[0], p[1], off) & ((1u << bm) - 1u);
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+                    if (lane >= o) v += t;
+                }
+            }
+            vals[m * kBlkLane + lane] = v;
+            const uint32_t last = __shfl_sync(0xFFFFFFFFu, v, 31);
+            if (lane == m) total = last;
+        }
+        if (lane < nmini && mybits == bmode) {
+            switch (bmode) {
 #define IMM3_UNPACK_CASE(B) case B: total = unpack_fixed<B>(wp, vp); break;
                 IMM3_UNPACK_CASE(0) IMM3_UNPACK_CASE(1) IMM3_UNPACK_CASE(2) IMM3_UNPACK_CASE(3) IMM3_UNPACK_CASE(4)
                 IMM3_UNPACK_CASE(5) IMM3_UNPACK_CASE(6) IMM3_UNPACK_CASE(7) IMM3_UNPACK_CASE(8) IMM3_UNPACK_CASE(9)
