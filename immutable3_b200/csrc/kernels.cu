@@ -1772,8 +1772,9 @@ __global__ void __launch_bounds__(kComputeThreads, 2) emit_general_kernel(const 
 // No look-back chain: the old single-pass block kernel spent 13 ns per block on it (97.6 K blocks per 100 M rows).
 // =============================================================================================
 constexpr int kBlkRows = 1024;        // largest block this pipeline takes
-constexpr int kBlkLane = 33;          // decoded values: mini-block m lives at vals[33 m .. 33 m + 32) - odd stride, so both the
-constexpr int kBlkVals = 32 * kBlkLane;  // lane-per-mini-block and the row-per-lane access patterns are bank-conflict-free
+constexpr int kBlkLane = 36;          // decoded values: mini-block m lives at vals[36 m .. 36 m + 32): 16-byte aligned rows, so a lane
+constexpr int kBlkVals = 32 * kBlkLane;  // moves its mini-block with 128-bit accesses (conflict-free per quarter warp), and the
+                                      // row-per-lane view (emit) reads consecutive words
 // per warp, in words: the filter kernel keeps the block's byte-swapped words and ONE decoded column; the emit kernel keeps
 // the words, every decoded column of the select list, their mini-block bases and a 1024-entry selection vector
 __host__ __device__ constexpr int blk_warp_smem_words(int npfor, int words_cap) { return words_cap + (npfor > 0 ? kBlkVals : 0); }
@@ -1786,6 +1787,7 @@ __device__ __forceinline__ uint32_t unpack_fixed(const uint32_t* __restrict__ wp
 #pragma unroll
     for (int i = 0; i < B; i++) w[i] = wp[i];
     uint32_t total = 0;
+    uint32_t t4[4];
 #pragma unroll
     for (int j = 0; j < 32; j++) {
         if (B > 0) {
@@ -1796,12 +1798,13 @@ __device__ __forceinline__ uint32_t unpack_fixed(const uint32_t* __restrict__ wp
             if (sh + B != 32) d &= (1u << B) - 1u;
             total += d;
         }
-        vp[j] = total;
+        t4[j & 3] = total;
+        if ((j & 3) == 3) reinterpret_cast<uint4*>(vp)[j >> 2] = make_uint4(t4[0], t4[1], t4[2], t4[3]);  // (rows are 16-byte aligned)
     }
     return total;
 }
 
-// Decode one PFOR_INT block (n <= 1024 values) by one warp.  vals[33 m + j] + base(m) = value 32m+j,
+// Decode one PFOR_INT block (n <= 1024 values) by one warp.  vals[kBlkLane m + j] + base(m) = value 32m+j,
 // where base(m) is returned in lane m (mini-block-local prefix sums are stored; raw b = 32 mini-blocks and the
 // var-byte tail store absolute values with base 0).
 __device__ __forceinline__ uint32_t pfor_decode_warp(const uint32_t* __restrict__ words, uint32_t w0, uint32_t w1, int n, uint32_t* Wb,
@@ -1987,7 +1990,12 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_filter_kernel(const
                     const uint32_t lo = (uint32_t)f.lo - base;
                     uint32_t word = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) word |= (uint32_t)((vp[j] - lo) <= f.span) << j;
+                    for (int q = 0; q < 8; q++) {
+                        const uint4 v = reinterpret_cast<const uint4*>(vp)[q];
+                        word |= ((uint32_t)((v.x - lo) <= f.span) | ((uint32_t)((v.y - lo) <= f.span) << 1) | ((uint32_t)((v.z - lo) <= f.span) << 2) |
+                                 ((uint32_t)((v.w - lo) <= f.span) << 3))
+                                << (4 * q);
+                    }
                     myword &= word;
                 } else {
                     // dense column: row per lane (coalesced), one ballot per 32 rows
