@@ -275,7 +275,7 @@ __device__ __forceinline__ void cta_exit(ScanCtrl* ctrl) {
 //                   exclusive offsets, 256 tiles per round, and owns the LIMIT cut and the total.
 // =============================================================================================
 #ifndef IMM3_EMIT_MIN_BLOCKS
-#define IMM3_EMIT_MIN_BLOCKS 2
+#define IMM3_EMIT_MIN_BLOCKS 4
 #endif
 #ifndef IMM3_DENSE_MIN_BLOCKS
 #define IMM3_DENSE_MIN_BLOCKS 3  // register budget: 3 CTAs (24 compute warps) per SM
