@@ -1938,7 +1938,7 @@ __device__ __forceinline__ uint32_t pfor_decode_warp(const uint32_t* __restrict_
     return base;
 }
 
-__global__ void __launch_bounds__(kComputeThreads, 3) blocks_filter_kernel(const __grid_constant__ ScanPlan P, uint32_t* __restrict__ bitmapB,
+__global__ void __launch_bounds__(kComputeThreads, 4) blocks_filter_kernel(const __grid_constant__ ScanPlan P, uint32_t* __restrict__ bitmapB,
                                                                              uint32_t* __restrict__ blk_cnt, uint32_t* __restrict__ tile_cnt,
                                                                              unsigned long long* __restrict__ tile_off, ScanCtrl* ctrl,
                                                                              long long nblocks) {
