@@ -416,13 +416,14 @@ def test_gpu_sorted_int_encoder_is_bit_exact(block_rows):
         assert got == b"".join(exp), name
 
 
-def test_small_limit_on_block_tables_runs_prefix_first(tmp_path_factory, monkeypatch):
-    """Small LIMIT on a table with a sorted-int-codec column: the pipeline first covers a prefix of the blocks and only
+def test_small_limit_runs_prefix_first(tmp_path_factory, monkeypatch):
+    """Small LIMIT (here on a table with a sorted-int-codec column and on its dense twin): the pipeline first covers a prefix of the blocks and only
     scans the whole table when the prefix does not fill the LIMIT.  Rows found early, late (id window at the end), never,
     and a LIMIT that the prefix fills only partly must all give the oracle's exact cut."""
     d = tmp_path_factory.mktemp("pfx")
     n = 300_000
     make_table(d, "pp", n, 1024, 40, seed=5, id_codec="PFOR_INT")
+    make_table(d, "pd", n, 1024, 40, seed=5)  # dense twin: the same policy on the dense multi-pass pipeline
     monkeypatch.setenv("IMM3_PREFIX_ROWS", "8192")
     os.environ.pop("IMM3_PATH", None)
     with O.Oracle(d) as orc, SegmentManager(d) as sm:
@@ -433,13 +434,14 @@ def test_small_limit_on_block_tables_runs_prefix_first(tmp_path_factory, monkeyp
                  (conj(Select("state", Match(["CA"])), Select("age", EQ(3))), ["id", "state", "age"]),  # rare rows
                  (Select("age", EQ(127)), ["id"]),                                                     # no rows at all
                  (NoSelect, ["id"])]
-        for sel, proj in cases:
-            for limit in (1, 10, 100, 5000):
-                exp = orc.query("pp", oracle_preds(sel), proj, limit=limit)
-                with eng.execute(Query("pp", sel, Project(proj, limit))) as got:
-                    assert got.nrows == exp.nrows, (sel, limit, got.nrows, exp.nrows)
-                    for c in range(len(proj)):
-                        assert np.array_equal(got.column(c), exp.columns[c]), (sel, proj[c], limit)
+        for table in ("pp", "pd"):
+            for sel, proj in cases:
+                for limit in (1, 10, 100, 5000):
+                    exp = orc.query(table, oracle_preds(sel), proj, limit=limit)
+                    with eng.execute(Query(table, sel, Project(proj, limit))) as got:
+                        assert got.nrows == exp.nrows, (table, sel, limit, got.nrows, exp.nrows)
+                        for c in range(len(proj)):
+                            assert np.array_equal(got.column(c), exp.columns[c]), (table, sel, proj[c], limit)
 
 
 @pytest.mark.parametrize("seed", range(10))
