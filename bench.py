@@ -12,12 +12,12 @@ Weak scaling: every rank owns a 100 M-row canonical slice of an (N x 100 M)-row 
 no collective, only the per-rank match counts are all-gathered (NCCL).
 
 Printed keys (one JSON line on rank 0):
-  value        rows/s, table resident in HBM, CUDA-event time of the fused kernel (max over ranks)
+  value        rows/s, table resident in HBM, CUDA-event time of the query's kernels (filter -> offset scan -> emit) (max over ranks)
   e2e          rows/s through the C ABI from PINNED HOST buffers: per step the used columns are re-staged
                host->HBM, the query runs, counts are exchanged and the result rows are copied to host
   e2e_resident rows/s through the C ABI with the table resident (the steady state of the drop-in:
                SegmentManager loads once, Engine.execute per query): query + count exchange + result D2H
-  roofline     achieved algorithmic GB/s of the fused kernel against the measured HBM peak
+  roofline     achieved algorithmic GB/s of the query's kernels against the measured HBM peak
   cpu_baseline the oracle (CPU restatement, kind "port") timed on this box's host cores
 """
 from __future__ import annotations
@@ -43,7 +43,7 @@ WORKLOADS = {
     "c3": ("C3 test_100m: select id, state, age from test_100m where (state = 'CA' and age > 18 and age < 30)", "DENSE_INT"),
     "c4": ("C4 sorted-int-codec id: select id from t where (id > L and id < H), 1% window", "PFOR_INT"),
     "c4dense": ("C4 dense-id twin: select id from t where (id > L and id < H), 1% window", "DENSE_INT"),
-    # experiments (same test_100m table as c2): isolate the cost of each stage of the fused kernel
+    # experiments (same test_100m table as c2): isolate the cost of each stage of the pipeline
     "x_age": ("X select age where (age > 18 and age < 30)", "DENSE_INT"),
     "x_id": ("X select id where (age > 18 and age < 30)", "DENSE_INT"),
     "x_count": ("X select <nothing> where (age > 18 and age < 30)", "DENSE_INT"),
@@ -340,7 +340,7 @@ def main():
         dist.all_gather(allc, mine)  # the only exchange on the path: 8 bytes per rank over NVLink
         return [int(t.item()) for t in allc]
 
-    # ---- value: table resident, CUDA-event time of the fused kernel ----
+    # ---- value: table resident, CUDA-event time of the query's kernels ----
     sampler = ClockSampler(local_rank)
     kernel_ms, alg_bytes, launches, local_rows = [], 0, 0, 0
     stage_ms = [[], []]
@@ -428,7 +428,7 @@ def main():
                "what": "per step: re-stage the query's columns host(pinned)->HBM, kernels, count exchange, result rows -> host (read-back of step i overlaps the staging of step i+1; K steps timed as a whole)"}
         e2e_res = {"value": total / sec_res, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h_b,
                    "ms_per_step": sec_res * 1e3,
-                   "what": "table resident in HBM (SegmentManager loads once): fused kernel, count exchange, result rows -> host"}
+                   "what": "table resident in HBM (SegmentManager loads once): kernels, count exchange, result rows -> host"}
 
     # ---- roofline of the dominant (only) kernel ----
     peak, peak_src = measured_peak()
