@@ -2485,6 +2485,34 @@ cudaError_t filter_kernel_occupancy(size_t dyn_smem, int* blocks_per_sm) {
     if (dyn_smem > 0) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, filter_kernel<true>, kComputeThreads + 32, dyn_smem);
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, filter_kernel<false>, kComputeThreads + 32, dyn_smem);
 }
+// K1 of a query without predicates: every row is selected, so the bitmap (ones, masked past the last row), the span and
+// tile counts and the tile offsets are known without reading a byte of the table.
+__global__ void __launch_bounds__(kComputeThreads) select_all_kernel(const __grid_constant__ ScanPlan P, uint32_t* __restrict__ bitmap,
+                                                                    uint32_t* __restrict__ span_cnt, uint32_t* __restrict__ tile_cnt,
+                                                                    unsigned long long* __restrict__ tile_off, ScanCtrl* ctrl) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int tid = threadIdx.x;
+    constexpr int kTile = kDenseTileRowsPerWord;
+    for (long long tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        const long long row0 = tile * kTile + (long long)tid * 32;
+        const long long left = P.nrows - row0;
+        bitmap[tile * (kTile / 32) + tid] = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
+        const long long in_tile = P.nrows - tile * kTile < kTile ? P.nrows - tile * kTile : kTile;
+        if (tid < 8) {
+            const long long s = in_tile - tid * 1024;
+            span_cnt[tile * 8 + tid] = (uint32_t)(s >= 1024 ? 1024 : (s <= 0 ? 0 : s));
+        }
+        if (tid == 8) tile_cnt[tile] = (uint32_t)in_tile;
+        if (tid == 9) tile_off[tile] = (unsigned long long)(tile * kTile);
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        ctrl->total = (unsigned long long)(P.nrows < P.limit ? P.nrows : P.limit);
+        ctrl->dense_rows = (unsigned long long)P.nrows;
+        ctrl->ticket = 0;
+        ctrl->ticket2 = 0;
+    }
+}
+
 cudaError_t emit_kernel_occupancy(bool general, int* blocks_per_sm) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
@@ -2495,6 +2523,10 @@ cudaError_t launch_filter(const ScanPlan& plan, uint32_t* bitmap, uint32_t* span
                           ScanCtrl* ctrl, int grid, size_t dyn_smem, cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
+    if (plan.nfilter == 0) {  // no predicate: nothing to read - the selection metadata is written analytically
+        select_all_kernel<<<grid, kComputeThreads, 0, stream>>>(plan, bitmap, span_cnt, tile_cnt, tile_off, ctrl);
+        return cudaGetLastError();
+    }
     if (plan.stages > 0) filter_kernel<true><<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt, tile_off, ctrl);
     else filter_kernel<false><<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmap, span_cnt, tile_cnt, tile_off, ctrl);
     return cudaGetLastError();
