@@ -16,7 +16,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libimm3gpu.so")
 
 SOURCES = ["meta.cpp", "writer.cpp", "plan.cpp", "sql.cpp", "store.cpp", "kernels.cu", "engine.cu", "encode.cu"]
-HEADERS = ["common.hpp", "json_min.hpp", "plan.hpp", "store.hpp", "kernels.hpp", "../../include/imm3.h"]
+HEADERS = ["common.hpp", "json_min.hpp", "plan.hpp", "store.hpp", "kernels.hpp", "../../include/imm3.h",
+           "k_ptx.cuh", "k_rowspace.cuh", "k_fused.cuh", "k_blocks_single.cuh", "k_multipass.cuh", "k_blocks_multi.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
