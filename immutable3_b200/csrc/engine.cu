@@ -605,11 +605,14 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         CUDA_TRY(launch_filter(pr->sp, pr->sp.bitmap, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
                                (unsigned long long*)db->d_tile_off.p, db->d_ctrl, pr->grid, pr->dyn_smem, db->stream));
         *launches = 1;
-        CUDA_TRY(cudaEventRecord(db->ev_mid, db->stream));
-        have_mid = true;
+        const bool pdl = pr->sp.nproj > 0 && !getenv("IMM3_NO_PDL");  // (no event may sit between a kernel and its programmatic dependent)
+        if (!pdl) {
+            CUDA_TRY(cudaEventRecord(db->ev_mid, db->stream));
+            have_mid = true;
+        }
         if (pr->sp.nproj > 0) {
             CUDA_TRY(launch_blocks_emit(pr->sp, pr->sp.bitmap, (const uint32_t*)db->d_span_cnt.p, (const unsigned long long*)db->d_tile_off.p,
-                                        nblocks_use, db->d_ctrl, true, (int)std::min<int64_t>(pr->grid_blocks_emit, (nblocks_use + 7) / 8),
+                                        nblocks_use, db->d_ctrl, true, pdl, (int)std::min<int64_t>(pr->grid_blocks_emit, (nblocks_use + 7) / 8),
                                         pr->blocks_emit_smem, db->stream));
             (*launches)++;
         }
@@ -628,11 +631,14 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         CUDA_TRY(launch_blocks_filter(pr->sp, (uint32_t*)db->d_bitmap.p, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
                                       (unsigned long long*)db->d_tile_off.p, db->d_ctrl, nblocks, pr->grid, pr->dyn_smem, db->stream));
         *launches = 1;
-        CUDA_TRY(cudaEventRecord(db->ev_mid, db->stream));
-        have_mid = true;
+        const bool pdl = pr->sp.nproj > 0 && !getenv("IMM3_NO_PDL");
+        if (!pdl) {
+            CUDA_TRY(cudaEventRecord(db->ev_mid, db->stream));
+            have_mid = true;
+        }
         if (pr->sp.nproj > 0) {
             CUDA_TRY(launch_blocks_emit(pr->sp, (const uint32_t*)db->d_bitmap.p, (const uint32_t*)db->d_span_cnt.p,
-                                        (const unsigned long long*)db->d_tile_off.p, nblocks, db->d_ctrl, false,
+                                        (const unsigned long long*)db->d_tile_off.p, nblocks, db->d_ctrl, false, pdl,
                                         (int)std::min<int64_t>(pr->grid_blocks_emit, (nblocks + 7) / 8), pr->blocks_emit_smem, db->stream));
             (*launches)++;
         }

@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(kComputeThreads, 4) blocks_filter_kernel(const
                                                                              long long nblocks) {
     __shared__ FilterShared S;
     __shared__ PforCol s_pfor[kMaxPforCols];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the emit kernel may become resident and set itself up
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < P.lit_bytes; i += kComputeThreads) S.lits[i] = P.lits[i];  // (nothing to copy unless a MATCH predicate exists)
     copy_plan_tables(P, S.filter, S.proj, tid, kComputeThreads);
@@ -317,6 +318,7 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const _
             if (tid == i) s_pfor[i] = P.pfor[i];
     }
     __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // launched as a programmatic dependent of the filter kernel: its results are final now
     if (__ldcg(&ctrl->total) == 0ull) return;  // nothing survived the predicates
     uint32_t* const Wb = reinterpret_cast<uint32_t*>(dyn_smem) + warp * blk_emit_warp_words(P.npfor, P.blk_words_cap);
     uint32_t* const vals0 = Wb + P.blk_words_cap;

@@ -170,12 +170,22 @@ cudaError_t launch_blocks_filter(const ScanPlan& plan, uint32_t* bitmapB, uint32
     return cudaGetLastError();
 }
 cudaError_t launch_blocks_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* cnts, const unsigned long long* tile_off,
-                               long long nblocks, const ScanCtrl* ctrl, bool rowspace, int grid, size_t dyn_smem, cudaStream_t stream) {
+                               long long nblocks, const ScanCtrl* ctrl, bool rowspace, bool pdl, int grid, size_t dyn_smem, cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    if (rowspace) blocks_emit_kernel<true><<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmap, cnts, tile_off, nblocks, ctrl);
-    else blocks_emit_kernel<false><<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmap, cnts, tile_off, nblocks, ctrl);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kComputeThreads);
+    cfg.dynamicSmemBytes = dyn_smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const long long nb = nblocks;
+    if (rowspace) return cudaLaunchKernelEx(&cfg, blocks_emit_kernel<true>, plan, bitmap, cnts, tile_off, nb, ctrl);
+    return cudaLaunchKernelEx(&cfg, blocks_emit_kernel<false>, plan, bitmap, cnts, tile_off, nb, ctrl);
 }
 
 cudaError_t launch_scan_blocks(const ScanPlan& plan, ScanCtrl* ctrl, unsigned long long* status, int grid, size_t dyn_smem,

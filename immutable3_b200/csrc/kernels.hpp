@@ -33,7 +33,8 @@ cudaError_t launch_blocks_filter(const ScanPlan& plan, uint32_t* bitmapB, uint32
                                  ScanCtrl* ctrl, long long nblocks, int grid, size_t dyn_smem, cudaStream_t stream);
 // rowspace: the bitmap / counts come from the dense filter kernel (row space), not from blocks_filter_kernel (block-local)
 cudaError_t launch_blocks_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* cnts, const unsigned long long* tile_off,
-                               long long nblocks, const ScanCtrl* ctrl, bool rowspace, int grid, size_t dyn_smem, cudaStream_t stream);
+                               long long nblocks, const ScanCtrl* ctrl, bool rowspace, bool pdl, int grid, size_t dyn_smem,
+                               cudaStream_t stream);
 cudaError_t launch_scan_blocks(const ScanPlan& plan, ScanCtrl* ctrl, unsigned long long* status, int grid, size_t dyn_smem,
                                cudaStream_t stream);
 
