@@ -416,6 +416,33 @@ def test_gpu_sorted_int_encoder_is_bit_exact(block_rows):
         assert got == b"".join(exp), name
 
 
+def test_several_sorted_int_codec_columns(tmp_path_factory):
+    """Three encoded columns in one table: predicates on one or two of them (one decode per predicate column in the
+    filter kernel), all of them in the select list (several decoded columns side by side in the emit kernel), a select
+    list of more than four columns (the column-by-column emit path), with and without LIMIT."""
+    d = tmp_path_factory.mktemp("multi_pfor")
+    n = 70_000
+    rng = np.random.default_rng(21)
+    ts = np.cumsum(rng.integers(0, 50, n)).astype(np.int32)
+    k2 = np.cumsum(rng.choice([0, 1, 70000], size=n, p=[0.5, 0.49, 0.01])).astype(np.int32)
+    make_table(d, "mp", n, 1024, 20, seed=3, id_codec="PFOR_INT", extra_cols=[("ts:PFOR_INT", ts), ("k2:PFOR_INT", k2), ("v:DENSE_INT", (ts // 7).astype(np.int32))])
+    os.environ.pop("IMM3_PATH", None)
+    with O.Oracle(d) as orc, SegmentManager(d) as sm:
+        eng = Engine(sm)
+        cases = [(conj(Select("ts", GT(int(ts[n // 3]))), Select("ts", LT(int(ts[n // 2])))), ["id", "ts", "k2"]),
+                 (conj(Select("ts", GT(int(ts[n // 4]))), Select("k2", LT(int(k2[3 * n // 4]))), Select("age", LT(40))), ["k2", "age", "ts"]),
+                 (Select("age", EQ(7)), ["ts", "id", "k2", "v"]),
+                 (conj(Select("id", GT(30_000)), Select("v", LT(int(ts[n // 2]) // 7))), ["id", "state", "age", "ts", "k2", "v"]),
+                 (NoSelect, ["k2", "ts"])]
+        for sel, proj in cases:
+            for limit in (0, 10, 3000):
+                exp = orc.query("mp", oracle_preds(sel), proj, limit=limit)
+                with eng.execute(Query("mp", sel, Project(proj, limit))) as got:
+                    assert got.nrows == exp.nrows, (sel, limit, got.nrows, exp.nrows)
+                    for c in range(len(proj)):
+                        assert np.array_equal(got.column(c), exp.columns[c]), (sel, proj[c], limit)
+
+
 def test_small_limit_runs_prefix_first(tmp_path_factory, monkeypatch):
     """Small LIMIT (here on a table with a sorted-int-codec column and on its dense twin): the pipeline first covers a prefix of the blocks and only
     scans the whole table when the prefix does not fill the LIMIT.  Rows found early, late (id window at the end), never,
