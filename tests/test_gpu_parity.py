@@ -405,6 +405,7 @@ def test_gpu_sorted_int_encoder_is_bit_exact(block_rows):
         "unsorted": rng.integers(-2**31, 2**31 - 1, 5 * block_rows + 1),
         "short": np.arange(7, dtype=np.int64) * 300,
         "one": np.array([300], dtype=np.int64),
+        "worksheet": np.array([1, 2, 3, 4, 5, 100, 120, 123, 150, 121, 122, 123, 125, 1000, 1100], dtype=np.int64),  # exploration/compression.sc:6
     }
     for tail in range(0, 33, 5):
         cols[f"tail {tail}"] = np.cumsum(rng.integers(0, 70000, 2 * block_rows + tail))
