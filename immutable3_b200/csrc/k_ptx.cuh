@@ -143,6 +143,7 @@ __device__ long long lookback_exclusive(const unsigned long long* status, long l
     long long pos = tile - 1;
     uint64_t t0 = 0;
     unsigned spins = 0;
+    bool saw_done = false;
     const unsigned ep = epoch & 0x3FFFFFu;
     for (;;) {
         unsigned long long st[4];
@@ -170,7 +171,17 @@ __device__ long long lookback_exclusive(const unsigned long long* status, long l
         const int p = pre ? (__ffs(pre) - 1) : 32;
         const unsigned need = (p >= 31) ? 0xFFFFFFFFu : ((2u << p) - 1u);  // lanes 0..p
         if (inv & need) {
-            if (__any_sync(0xFFFFFFFFu, ld_relaxed_u32(&ctrl->done) != 0u)) return -1;
+            // LIMIT reached somewhere.  The tile that crossed it had every predecessor's status in hand before it raised
+            // `done`, so a tile BEFORE it finds all of its own predecessors published once it re-reads them behind a fence
+            // (it must go on and emit its rows); only a tile AFTER the crossing can still see an unpublished predecessor
+            // (a CTA that drew its ticket and left): that one gives up.  (Giving up at the first sight of `done` dropped
+            // the rows of earlier tiles whose status reads were a moment older than the flag.)
+            if (__any_sync(0xFFFFFFFFu, ld_relaxed_u32(&ctrl->done) != 0u)) {
+                if (saw_done) return -1;
+                saw_done = true;
+                __threadfence();
+                continue;
+            }
             if (spins == 0) t0 = globaltimer_ns();
             if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > kWatchdogNs) watchdog_trap(ctrl, 2);
             __nanosleep(20);

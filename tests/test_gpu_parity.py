@@ -472,11 +472,12 @@ def test_small_limit_runs_prefix_first(tmp_path_factory, monkeypatch):
                             assert np.array_equal(got.column(c), exp.columns[c]), (table, sel, proj[c], limit)
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", list(range(10)) + [118])  # 118: LIMIT == number of matches on 1500 small blocks (look-back abort race)
 def test_random_tables_and_queries(tmp_path_factory, seed):
     """Randomised end-to-end parity: table shape (rows, block size, segment size, id codec and order), predicate set, select
     list and LIMIT are drawn from a seeded generator; the default kernel choice and the forced single-pass kernels must both
     reproduce the oracle's rows, values and order."""
+    seed += int(os.environ.get("IMM3_TEST_SEED_BASE", "0"))  # (stress runs: other seeds without editing the file)
     rng = np.random.default_rng(1000 + seed)
     d = tmp_path_factory.mktemp(f"rnd{seed}")
     nrows = int(rng.choice([1, 31, 1000, 8191, 8193, 40_000, 150_000]))
