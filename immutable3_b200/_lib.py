@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("IMM3_LIB") or os.path.join(HERE, "libimm3gpu.so")  # IMM3_LIB: experiment builds
 
 OK = 0
-ERR_NOT_FOUND, ERR_UNSUPPORTED, ERR_BAD_FORMAT, ERR_CUDA, ERR_OOM, ERR_INVALID_ARG, ERR_IO, ERR_STATE = range(-1, -9, -1)
+ERR_NOT_FOUND, ERR_UNSUPPORTED, ERR_BAD_FORMAT, ERR_CUDA, ERR_OOM, ERR_INVALID_ARG, ERR_IO, ERR_STATE, ERR_COMM = range(-1, -10, -1)
+COMM_HANDLE_BYTES = 64
 COL_INT, COL_TINYINT, COL_STRING = 0, 1, 2
 CODEC_PFOR_INT, CODEC_DENSE_INT, CODEC_DENSE_TINYINT, CODEC_DENSE_STRING = 0, 1, 2, 3
 OP_GT, OP_LT, OP_EQ, OP_MATCH, OP_NOTMATCH, OP_NOOP = 1, 2, 3, 4, 5, 6
@@ -56,6 +57,12 @@ SIGNATURES = {
     "imm3_query": (C.c_int, [_P, C.c_char_p, C.POINTER(Pred), C.c_int, _STRS, C.c_int, C.c_int64, _PP]),
     "imm3_query_begin": (C.c_int, [_P, C.c_char_p, C.POINTER(Pred), C.c_int, _STRS, C.c_int, C.c_int64, _PP]),
     "imm3_result_local_count": (C.c_int64, [_P]),
+    "imm3_comm_local_handle": (C.c_int, [_P, _P]),
+    "imm3_comm_connect": (C.c_int, [_P, _P, C.c_int]),
+    "imm3_result_global_offset": (C.c_int64, [_P]),
+    "imm3_result_take": (C.c_int64, [_P]),
+    "imm3_result_global_count": (C.c_int64, [_P]),
+    "imm3_result_rank_counts": (C.c_int, [_P, C.POINTER(C.c_int64), C.c_int]),
     "imm3_result_fetch": (C.c_int, [_P, C.c_int64]),
     "imm3_result_fetch_async": (C.c_int, [_P, C.c_int64]),
     "imm3_result_wait": (C.c_int, [_P]),

@@ -107,8 +107,15 @@ struct imm3_db {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_stream = nullptr;      // imm3_result_fetch_async: device->host copies overlap the next query's staging
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
-    ScanCtrl* d_ctrl = nullptr;
-    ScanCtrl* h_ctrl = nullptr;
+    ScanCtrl* d_ctrl = nullptr;   // first member of a device CtrlBlock (ScanCtrl + CommOut)
+    CtrlBlock* h_ctrl = nullptr;  // pinned copy, refreshed once per launch sequence
+    int live_results = 0;         // imm3_result objects that still point at this db (imm3_close refuses while > 0)
+    // Count exchange over NVLink peer memory (imm3_comm_*): the local mailbox, every rank's mailbox as mapped here.
+    unsigned long long* d_mailbox = nullptr;
+    unsigned long long* comm_peer[kMaxWorld] = {};
+    bool comm_on = false;
+    uint32_t comm_epoch = 0;
+    unsigned long long comm_timeout_ns = 30000000000ull;
     unsigned long long* d_status = nullptr;
     size_t status_cap = 0;
     uint32_t epoch = 0;
@@ -131,6 +138,9 @@ struct imm3_result {
     std::vector<int> types, widths;
     std::vector<Buf> d_cols, h_cols;
     int64_t local_count = 0;
+    int64_t g_offset = 0, g_take = 0, g_total = 0;  // after the count exchange (single handle: 0, local_count, local_count)
+    int world = 1;
+    int64_t rank_counts[kMaxWorld] = {};
     int64_t fetched = 0;
     int64_t pending = -1;        // rows of an imm3_result_fetch_async still in flight (-1 = none)
     cudaEvent_t copied = nullptr;  // recorded on the copy stream after the last device->host copy
@@ -268,6 +278,9 @@ void free_device_side(imm3_db* db) {
     if (db->d_status) cudaFree(db->d_status);
     if (db->d_ctrl) cudaFree(db->d_ctrl);
     if (db->h_ctrl) cudaFreeHost(db->h_ctrl);
+    for (int i = 0; i < kMaxWorld; i++)
+        if (db->comm_peer[i] && db->comm_peer[i] != db->d_mailbox) cudaIpcCloseMemHandle(db->comm_peer[i]);
+    if (db->d_mailbox) cudaFree(db->d_mailbox);
     if (db->ev0) cudaEventDestroy(db->ev0);
     if (db->ev1) cudaEventDestroy(db->ev1);
     if (db->ev_mid) cudaEventDestroy(db->ev_mid);
@@ -588,14 +601,46 @@ int ensure_buf(Buf* b, size_t bytes) {
 }
 
 // Launch the kernels of one query and wait for the match count.
-int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launches, double* stage_ms, int64_t nblocks_use) {
+// Launch the count-exchange kernel of one round (every rank of the communicator must launch the same rounds in the same
+// order).  has_count = 0: this rank ran no kernel in this query (empty slice) and contributes 0.
+int launch_exchange(imm3_db* db, int64_t limit, int has_count) {
+    CommPlan cp;
+    std::memset(&cp, 0, sizeof cp);
+    for (int i = 0; i < db->world; i++) cp.peer[i] = db->comm_peer[i];
+    cp.rank = db->rank;
+    cp.world = db->world;
+    if (((++db->comm_epoch) & 0xFFFFFFu) == 0) ++db->comm_epoch;  // tag 0 is what an untouched mailbox holds
+    cp.epoch = db->comm_epoch;
+    cp.has_count = has_count;
+    cp.limit = limit;
+    cp.timeout_ns = db->comm_timeout_ns;
+    CUDA_TRY(launch_count_exchange(cp, db->d_ctrl, &reinterpret_cast<CtrlBlock*>(db->d_ctrl)->x, db->stream));
+    return 0;
+}
+
+// A round of the exchange without a scan of this rank's own: its slice is empty (has_count = 0) or its previous phase
+// already covered the whole slice (has_count = 1: ctrl->total still holds that count).
+int exchange_only(imm3_db* db, int64_t limit, int has_count) {
+    int rc = launch_exchange(db, limit, has_count);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(db->h_ctrl, db->d_ctrl, sizeof(CtrlBlock), cudaMemcpyDeviceToHost, db->stream));
+    CUDA_TRY(cudaStreamSynchronize(db->stream));
+    if (db->h_ctrl->x.error)
+        return fail(IMM3_ERR_COMM, "count exchange: a peer's count did not arrive within %llu ms (ranks must issue the same queries in the same order)",
+                    db->comm_timeout_ns / 1000000ull);
+    return 0;
+}
+
+int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launches, double* stage_ms, int64_t nblocks_use, bool exchange) {
     bool have_mid = false;
     if (pr->block_mode && pr->hybrid) {
         // dense filter kernel over the row space -> block emit kernel (decodes only blocks with surviving rows)
         TableStore& t = *pr->table;
         const int64_t ntiles = pr->sp.ntiles, nspans = ntiles * 8;
         int rc;
-        if ((rc = ensure_buf(&db->d_bitmap, (size_t)(ntiles * kDenseTileRowsPerWord / 32 + 2) * 4))) return rc;
+        // (+64 words: the row-space emit kernel reads, for every lane of a block's warp, the word holding bit R0 + 32*lane
+        // and the one after it - up to 33 words past the last row's word for a 1-row tail block at the end of the slice)
+        if ((rc = ensure_buf(&db->d_bitmap, (size_t)(ntiles * kDenseTileRowsPerWord / 32 + 64) * 4))) return rc;
         pr->sp.bitmap = (uint32_t*)db->d_bitmap.p;
         if ((rc = ensure_buf(&db->d_span_cnt, (size_t)(nspans + 8) * 4))) return rc;
         const size_t ntiles_pad = ((size_t)ntiles + 4095) / 4096 * 4096 + 16;  // whole rounds of the offset scan
@@ -716,9 +761,20 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
         *launches = 1;
     }
-    CUDA_TRY(cudaMemcpyAsync(db->h_ctrl, db->d_ctrl, sizeof(ScanCtrl), cudaMemcpyDeviceToHost, db->stream));
+    if (exchange && db->comm_on) {
+        // The per-rank counts are exchanged by the GPUs themselves (k_comm.cuh), behind the query's last kernel: no host
+        // round trip between the kernels and the exchange, one synchronisation per query.
+        int rc = launch_exchange(db, pr->sp.limit, 1);
+        if (rc) return rc;
+        (*launches)++;
+        CUDA_TRY(cudaEventRecord(db->ev1, db->stream));  // (re-recorded: the timed span now ends behind the exchange)
+    }
+    CUDA_TRY(cudaMemcpyAsync(db->h_ctrl, db->d_ctrl, sizeof(CtrlBlock), cudaMemcpyDeviceToHost, db->stream));
     CUDA_TRY(cudaStreamSynchronize(db->stream));
-    if (db->h_ctrl->error) return fail(IMM3_ERR_CUDA, "kernel watchdog fired (code %u)", db->h_ctrl->error);
+    if (db->h_ctrl->c.error) return fail(IMM3_ERR_CUDA, "kernel watchdog fired (code %u)", db->h_ctrl->c.error);
+    if (exchange && db->comm_on && db->h_ctrl->x.error)
+        return fail(IMM3_ERR_COMM, "count exchange: a peer's count did not arrive within %llu ms (ranks must issue the same queries in the same order)",
+                    db->comm_timeout_ns / 1000000ull);
     float f = 0;
     CUDA_TRY(cudaEventElapsedTime(&f, db->ev0, db->ev1));
     *ms = f;
@@ -733,9 +789,9 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
             stage_ms[1] = b;
         }
     }
-    *total = (int64_t)db->h_ctrl->total;
+    *total = (int64_t)db->h_ctrl->c.total;
     if (pr->multipass && pr->sp.nproj > 0 && pr->emit_stage_bytes > 0)  // feedback for the next query of this shape
-        db->emit_hint[pr->shape_key] = (db->h_ctrl->total > 0 && db->h_ctrl->dense_rows * 2 >= db->h_ctrl->total) ? 1 : 0;
+        db->emit_hint[pr->shape_key] = (db->h_ctrl->c.total > 0 && db->h_ctrl->c.dense_rows * 2 >= db->h_ctrl->c.total) ? 1 : 0;
     if (pr->sp.trace && (pr->sp.debug & 16u)) {
         unsigned long long h[64];
         CUDA_TRY(cudaMemcpy(h, pr->sp.trace, sizeof h, cudaMemcpyDeviceToHost));
@@ -758,40 +814,53 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
     return 0;
 }
 
+// A small LIMIT is served "prefix first": phase A scans a leading part of the slice, phase B the whole slice if that did
+// not fill the LIMIT.  With a communicator every rank must run the same rounds, so the policy depends only on the query:
+// phase A everywhere (a rank whose slice is too small for a prefix scans all of it), then - unless RANK 0's phase A alone
+// fills the LIMIT, in which case the global result is its first `limit` rows - phase B everywhere.
+bool small_limit_policy(const LogicalPlan& lp) { return lp.limit > 0 && lp.limit <= (1 << 20) && !getenv("IMM3_NO_PREFIX"); }
+
 // Launch the kernels of one query and wait for the match count (see Prepared::prefix_blocks for the two-phase LIMIT).
 int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launches, double* stage_ms = nullptr) {
     TableStore& t = *pr->table;
+    const bool comm = db->comm_on && !pr->for_bitmap;
     const bool block_prefix = pr->block_mode && pr->blocks_multi && pr->prefix_blocks > 0;
     const bool dense_prefix = !pr->block_mode && pr->multipass && pr->prefix_rows > 0;
-    if (!block_prefix && !dense_prefix) return run_scan_once(db, pr, ms, total, launches, stage_ms, t.nblocks);
+    const bool two_phase = comm ? small_limit_policy(pr->lp) : (block_prefix || dense_prefix);
+    if (!two_phase) return run_scan_once(db, pr, ms, total, launches, stage_ms, t.nblocks, comm);
     // phase A: the leading blocks / rows only
     const ScanPlan full = pr->sp;
     const int grid_full = pr->grid;
-    const int64_t nb = pr->prefix_blocks;
-    if (dense_prefix) {
-        pr->sp.nrows = pr->prefix_rows;
-        pr->sp.ntiles = pr->prefix_rows / kDenseTileRowsPerWord;
-    } else if (pr->hybrid) {
-        pr->sp.nrows = (int64_t)t.row_start[(size_t)nb];
-        pr->sp.ntiles = (pr->sp.nrows + kDenseTileRowsPerWord - 1) / kDenseTileRowsPerWord;
-    } else {
-        pr->sp.ntiles = (nb + 7) / 8;
+    const bool local_prefix = block_prefix || dense_prefix;
+    int64_t nb = t.nblocks;
+    if (local_prefix) {
+        nb = pr->prefix_blocks;
+        if (dense_prefix) {
+            pr->sp.nrows = pr->prefix_rows;
+            pr->sp.ntiles = pr->prefix_rows / kDenseTileRowsPerWord;
+        } else if (pr->hybrid) {
+            pr->sp.nrows = (int64_t)t.row_start[(size_t)nb];
+            pr->sp.ntiles = (pr->sp.nrows + kDenseTileRowsPerWord - 1) / kDenseTileRowsPerWord;
+        } else {
+            pr->sp.ntiles = (nb + 7) / 8;
+        }
+        pr->grid = (int)std::max<int64_t>(1, std::min<int64_t>(pr->sp.ntiles, grid_full));
     }
-    pr->grid = (int)std::max<int64_t>(1, std::min<int64_t>(pr->sp.ntiles, grid_full));
     double ms_a = 0, st_a[2] = {0, 0};
     int launches_a = 0;
-    int rc = run_scan_once(db, pr, &ms_a, total, &launches_a, st_a, nb);
+    int rc = run_scan_once(db, pr, &ms_a, total, &launches_a, st_a, nb, comm);
     pr->sp = full;
     pr->grid = grid_full;
     if (rc) return rc;
     *ms = ms_a;
     *launches = launches_a;
     if (stage_ms) stage_ms[0] = st_a[0], stage_ms[1] = st_a[1];
-    if (*total >= pr->lp.limit) return 0;
+    if (comm ? (int64_t)db->h_ctrl->x.counts[0] >= pr->lp.limit : *total >= pr->lp.limit) return 0;
     // phase B: the prefix did not fill the LIMIT - the whole table
+    if (!local_prefix) return exchange_only(db, pr->sp.limit, 1);  // (comm only: phase A was this rank's whole slice already)
     double ms_b = 0, st_b[2] = {0, 0};
     int launches_b = 0;
-    if ((rc = run_scan_once(db, pr, &ms_b, total, &launches_b, st_b, t.nblocks))) return rc;
+    if ((rc = run_scan_once(db, pr, &ms_b, total, &launches_b, st_b, t.nblocks, comm))) return rc;
     *ms += ms_b;
     *launches += launches_b;
     if (stage_ms) stage_ms[0] += st_b[0], stage_ms[1] += st_b[1];
@@ -846,9 +915,11 @@ int imm3_open(const char* data_dir, const imm3_open_opts* opts, imm3_db** out) {
             CUDA_TRY(cudaEventCreate(&db->ev0));
             CUDA_TRY(cudaEventCreate(&db->ev1));
             CUDA_TRY(cudaEventCreate(&db->ev_mid));
-            CUDA_TRY(cudaMalloc(&db->d_ctrl, sizeof(ScanCtrl)));
-            CUDA_TRY(cudaMemsetAsync(db->d_ctrl, 0, sizeof(ScanCtrl), db->stream));
-            CUDA_TRY(cudaMallocHost(&db->h_ctrl, sizeof(ScanCtrl)));
+            CUDA_TRY(cudaMalloc(&db->d_ctrl, sizeof(CtrlBlock)));
+            CUDA_TRY(cudaMemsetAsync(db->d_ctrl, 0, sizeof(CtrlBlock), db->stream));
+            CUDA_TRY(cudaMallocHost(&db->h_ctrl, sizeof(CtrlBlock)));
+            std::memset(db->h_ctrl, 0, sizeof(CtrlBlock));
+            if (const char* e = getenv("IMM3_COMM_TIMEOUT_MS")) db->comm_timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
             return upload_all(db.get());
         };
         rc = body();
@@ -864,8 +935,61 @@ int imm3_open(const char* data_dir, const imm3_open_opts* opts, imm3_db** out) {
 
 int imm3_close(imm3_db* db) {
     if (!db) return 0;
+    // Results borrow buffers from the db's pools and dereference it in fetch / wait / free: closing under them would be a
+    // use-after-free.  The caller frees its results first (the Python mirror does so in SegmentManager.close).
+    if (db->live_results > 0)
+        return fail(IMM3_ERR_STATE, "imm3_close: %d result(s) of this handle are still open (imm3_result_free them first)", db->live_results);
     free_device_side(db);
     delete db;
+    return 0;
+}
+
+// ---- count exchange over NVLink peer memory -----------------------------------------------------
+int imm3_comm_local_handle(imm3_db* db, void* handle_out) {
+    if (!db || !handle_out) return fail(IMM3_ERR_INVALID_ARG, "imm3_comm_local_handle: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == IMM3_COMM_HANDLE_BYTES, "IMM3_COMM_HANDLE_BYTES must be sizeof(cudaIpcMemHandle_t)");
+    int rc = use_device(db);
+    if (rc) return rc;
+    if (db->world > kMaxWorld) return fail(IMM3_ERR_UNSUPPORTED, "count exchange supports at most %d ranks (world = %d)", kMaxWorld, db->world);
+    if (!db->d_mailbox) {
+        CUDA_TRY(cudaMalloc(&db->d_mailbox, kMailboxBytes));
+        CUDA_TRY(cudaMemset(db->d_mailbox, 0, kMailboxBytes));
+    }
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, db->d_mailbox));
+    std::memcpy(handle_out, &h, sizeof h);
+    return 0;
+}
+
+int imm3_comm_connect(imm3_db* db, const void* handles, int nhandles) {
+    if (!db || !handles) return fail(IMM3_ERR_INVALID_ARG, "imm3_comm_connect: NULL argument");
+    int rc = use_device(db);
+    if (rc) return rc;
+    if (nhandles != db->world) return fail(IMM3_ERR_INVALID_ARG, "imm3_comm_connect: %d handles for a world of %d", nhandles, db->world);
+    if (!db->d_mailbox) return fail(IMM3_ERR_STATE, "imm3_comm_connect: call imm3_comm_local_handle first");
+    if (db->comm_on) return fail(IMM3_ERR_STATE, "imm3_comm_connect: already connected");
+    for (int i = 0; i < db->world; i++) {
+        if (i == db->rank) {
+            db->comm_peer[i] = db->d_mailbox;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const uint8_t*)handles + (size_t)i * sizeof h, sizeof h);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int k = 0; k < i; k++) {
+                if (db->comm_peer[k] && db->comm_peer[k] != db->d_mailbox) cudaIpcCloseMemHandle(db->comm_peer[k]);
+                db->comm_peer[k] = nullptr;
+            }
+            return fail(IMM3_ERR_COMM, "imm3_comm_connect: cannot map the mailbox of rank %d (%s); the ranks must be processes on one NVLink-connected node", i,
+                        cudaGetErrorString(e));
+        }
+        db->comm_peer[i] = (unsigned long long*)p;
+    }
+    db->comm_on = db->world > 1;
+    db->comm_epoch = 0;
     return 0;
 }
 
@@ -1001,6 +1125,28 @@ int imm3_query_begin(imm3_db* db, const char* table, const imm3_pred* preds, int
         for (int i = 0; i < r->ncols; i++) pr.sp.proj[i].out = (uint8_t*)r->d_cols[(size_t)i].p;
         pr.sp.bitmap = nullptr;
         if ((rc = run_scan(db, &pr, &r->device_ms, &r->local_count, &r->launches, r->stage_ms))) { give_back(); return rc; }
+    } else if (db->comm_on && !pr.lp.always_empty) {
+        // Empty slice (more ranks than segments): this rank still takes part in every round of the exchange.  (A predicate
+        // that can never hold is a property of the query, known to every rank: nobody exchanges anything.)
+        const int64_t lim = limit > 0 ? limit : INT64_MAX;
+        if ((rc = exchange_only(db, lim, 0))) { give_back(); return rc; }
+        if (small_limit_policy(pr.lp) && (int64_t)db->h_ctrl->x.counts[0] < pr.lp.limit && (rc = exchange_only(db, lim, 0))) { give_back(); return rc; }
+        r->launches = 1;
+    }
+    // Global placement of this rank's rows: from the on-device exchange, or trivially for a single handle.
+    r->world = 1;
+    r->g_offset = 0;
+    r->g_take = r->g_total = r->local_count;
+    r->rank_counts[0] = r->local_count;
+    if (db->comm_on && !pr.lp.always_empty) {
+        const CommOut& x = db->h_ctrl->x;
+        r->world = db->world;
+        r->g_offset = (int64_t)x.g_offset;
+        r->g_take = (int64_t)x.g_take;
+        r->g_total = (int64_t)x.g_total;
+        for (int i = 0; i < db->world; i++) r->rank_counts[i] = (int64_t)x.counts[i];
+    } else if (db->comm_on) {
+        r->world = db->world;
     }
     // Algorithmic bytes: filter columns' encoded bytes once + per surviving row the
     // project-only widths read and every projected width written (+ 4 B/block for PFOR offsets).
@@ -1021,11 +1167,20 @@ int imm3_query_begin(imm3_db* db, const char* table, const imm3_pred* preds, int
         }
         r->alg_bytes = a + per_row * r->local_count;
     }
+    db->live_results++;
     *out = r.release();
     return 0;
 }
 
 int64_t imm3_result_local_count(const imm3_result* r) { return r ? r->local_count : IMM3_ERR_INVALID_ARG; }
+int64_t imm3_result_global_offset(const imm3_result* r) { return r ? r->g_offset : IMM3_ERR_INVALID_ARG; }
+int64_t imm3_result_take(const imm3_result* r) { return r ? r->g_take : IMM3_ERR_INVALID_ARG; }
+int64_t imm3_result_global_count(const imm3_result* r) { return r ? r->g_total : IMM3_ERR_INVALID_ARG; }
+int imm3_result_rank_counts(const imm3_result* r, int64_t* counts, int cap) {
+    if (!r || !counts || cap < r->world) return fail(IMM3_ERR_INVALID_ARG, "imm3_result_rank_counts: need room for %d counts", r ? r->world : 0);
+    for (int i = 0; i < r->world; i++) counts[i] = r->rank_counts[i];
+    return r->world;
+}
 
 int imm3_result_fetch(imm3_result* r, int64_t nrows) {
     if (!r) return fail(IMM3_ERR_INVALID_ARG, "imm3_result_fetch: result is NULL");
@@ -1086,7 +1241,7 @@ int imm3_query(imm3_db* db, const char* table, const imm3_pred* preds, int npred
     imm3_result* r = nullptr;
     int rc = imm3_query_begin(db, table, preds, npreds, proj_cols, nproj, limit, &r);
     if (rc) return rc;
-    if ((rc = imm3_result_fetch(r, r->local_count))) {
+    if ((rc = imm3_result_fetch(r, r->g_take))) {  // (a single handle: all local rows; with a communicator: this rank's share)
         std::string why = last_error();
         imm3_result_free(r);
         return fail(rc, "%s", why.c_str());
@@ -1146,6 +1301,7 @@ int imm3_result_free(imm3_result* r) {
     if (r->copied) cudaEventDestroy(r->copied);
     for (auto& b : r->d_cols) r->db->dev_pool.release(b);
     for (auto& b : r->h_cols) r->db->host_pool.release(b);
+    r->db->live_results--;
     delete r;
     return 0;
 }

@@ -20,6 +20,7 @@
 #include <type_traits>
 
 #include <cstdint>
+#include <mutex>
 
 #include "kernels.hpp"
 #include "plan.hpp"
@@ -32,6 +33,7 @@ namespace imm3 {
 #include "k_blocks_single.cuh"
 #include "k_multipass.cuh"
 #include "k_blocks_multi.cuh"
+#include "k_comm.cuh"
 
 // =============================================================================================
 // Launchers
@@ -42,8 +44,24 @@ size_t blocks_kernel_smem_bytes(int npfor, int max_block_rows) {
     return words * 4 + nmb * 2 + nmb + 64;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: one process may hold handles on several GPUs
+// (one GpuEngine per GPU), so the kernels are configured once per device ordinal, for the device that is
+// current on the calling thread (every entry point of engine.cu has called cudaSetDevice(db->device) by now).
+static cudaError_t configure_device();
 static cudaError_t configure_once() {
-    static cudaError_t rc = [] {
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    e = configure_device();
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    return e;
+}
+static cudaError_t configure_device() {
+    {
         cudaError_t e = cudaSuccess;
 #define IMM3_SET_SMEM(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e
         IMM3_SET_SMEM(emit_stream_kernel);
@@ -57,8 +75,7 @@ static cudaError_t configure_once() {
         IMM3_SET_SMEM(filter_kernel<false>);
 #undef IMM3_SET_SMEM
         return cudaFuncSetAttribute(scan_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    }();
-    return rc;
+    }
 }
 
 cudaError_t dense_kernel_occupancy(bool staged, size_t dyn_smem, int* blocks_per_sm) {
@@ -186,6 +203,20 @@ cudaError_t launch_blocks_emit(const ScanPlan& plan, const uint32_t* bitmap, con
     const long long nb = nblocks;
     if (rowspace) return cudaLaunchKernelEx(&cfg, blocks_emit_kernel<true>, plan, bitmap, cnts, tile_off, nb, ctrl);
     return cudaLaunchKernelEx(&cfg, blocks_emit_kernel<false>, plan, bitmap, cnts, tile_off, nb, ctrl);
+}
+
+// The count exchange rides behind the query's last kernel as a programmatic dependent (its launch overlaps that kernel).
+cudaError_t launch_count_exchange(const CommPlan& plan, const ScanCtrl* ctrl, CommOut* out, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(32);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, count_exchange_kernel, plan, ctrl, out);
 }
 
 cudaError_t launch_scan_blocks(const ScanPlan& plan, ScanCtrl* ctrl, unsigned long long* status, int grid, size_t dyn_smem,

@@ -102,6 +102,41 @@ struct ScanCtrl {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Multi-GPU count exchange over NVLink peer memory (k_comm.cuh).  Every rank owns a MAILBOX in its HBM:
+// kCommRing rounds x kMaxWorld senders of one 64-bit word  [63:40] exchange epoch, [39:0] match count.
+// Rank r stores its word into slot [epoch % ring][r] of EVERY rank's mailbox (peer stores through NVLink,
+// the pointers come from cudaIpcOpenMemHandle) and then polls its own mailbox until all `world` words of the
+// epoch have arrived.  Replaces the fan-in of ResultQueue.scala:7-56 / Engine.scala:166,190-196.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxWorld = 16;
+constexpr int kCommRing = 4;
+constexpr size_t kMailboxBytes = (size_t)kCommRing * kMaxWorld * sizeof(unsigned long long);
+
+struct CommPlan {
+    unsigned long long* peer[kMaxWorld];  // mailbox of every rank as mapped in THIS process (peer[rank] = the local one)
+    int32_t rank, world;
+    uint32_t epoch;                       // exchange sequence number of this db (identical on all ranks)
+    int32_t has_count;                    // 0: this rank ran no kernel (empty slice) - it contributes 0
+    long long limit;                      // INT64_MAX = unlimited
+    unsigned long long timeout_ns;
+};
+
+// What the exchange kernel leaves behind for the host (copied back together with ScanCtrl).
+struct CommOut {
+    unsigned long long g_offset;  // global ordinal of this rank's first row = sum of the counts of the ranks before it
+    unsigned long long g_take;    // rows of this rank that survive the global LIMIT cut
+    unsigned long long g_total;   // rows of the whole result (min(limit, sum of counts))
+    unsigned int error;           // 1 = a peer's count did not arrive before the timeout
+    unsigned int world;
+    unsigned long long counts[kMaxWorld];  // local count of every rank (each capped at LIMIT)
+};
+
+struct CtrlBlock {
+    ScanCtrl c;
+    CommOut x;
+};
+
+// ---------------------------------------------------------------------------------------------
 // Host-side logical plan (independent of device pointers; testable on CPU through imm3_explain).
 // ---------------------------------------------------------------------------------------------
 struct LogicalFilter {

@@ -14,8 +14,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <atomic>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.hpp"
@@ -486,22 +489,52 @@ int imm3_synth_write(const char* data_dir, const char* table, int64_t nrows, int
             remove((base + c + "_0.meta").c_str());
         }
     }
-    const int64_t chunk = 1 << 20;
-    std::vector<int32_t> ids((size_t)chunk);
-    std::vector<int8_t> ages((size_t)chunk);
-    std::vector<char> states((size_t)chunk * 2);
-    for (int32_t seg = seg_id_begin; seg < seg_id_end; seg++) {
-        imm3_writer* w = nullptr;
-        int rc = imm3_writer_open(data_dir, table, specs, 3, block_size, segment_size, seg, 0, &w);
-        if (rc) return rc;
-        int64_t r0 = seg * rows_per_seg, r1 = r0 + rows_per_seg < nrows ? r0 + rows_per_seg : nrows;
-        for (int64_t r = r0; r < r1; r += chunk) {
-            int64_t n = r1 - r < chunk ? r1 - r : chunk;
-            for (int64_t i = 0; i < n; i++) synth_row(r + i, &ids[(size_t)i], &ages[(size_t)i], &states[(size_t)i * 2]);
-            const void* cols[3] = {ids.data(), states.data(), ages.data()};
-            if ((rc = imm3_writer_append(w, cols, n))) { imm3_writer_close(w); return rc; }
+    // Segments are independent files: written by a small pool of threads (a 1 B-row table is 977 segments).
+    const int nsegs = seg_id_end - seg_id_begin;
+    if (nsegs <= 0) return 0;
+    int nthreads = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("IMM3_WRITER_THREADS")) nthreads = atoi(e);
+    nthreads = std::max(1, std::min(nthreads, nsegs));
+    std::atomic<int> next(seg_id_begin);
+    std::atomic<int> first_rc(0);
+    std::vector<std::string> errors((size_t)nthreads);
+    auto work = [&](int tid) {
+        const int64_t chunk = 1 << 18;
+        std::vector<int32_t> ids((size_t)chunk);
+        std::vector<int8_t> ages((size_t)chunk);
+        std::vector<char> states((size_t)chunk * 2);
+        for (;;) {
+            const int seg = next.fetch_add(1);
+            if (seg >= seg_id_end || first_rc.load()) return;
+            imm3_writer* w = nullptr;
+            int rc = imm3_writer_open(data_dir, table, specs, 3, block_size, segment_size, seg, 0, &w);
+            int64_t r0 = seg * rows_per_seg, r1 = r0 + rows_per_seg < nrows ? r0 + rows_per_seg : nrows;
+            for (int64_t r = r0; !rc && r < r1; r += chunk) {
+                int64_t n = r1 - r < chunk ? r1 - r : chunk;
+                for (int64_t i = 0; i < n; i++) synth_row(r + i, &ids[(size_t)i], &ages[(size_t)i], &states[(size_t)i * 2]);
+                const void* cols[3] = {ids.data(), states.data(), ages.data()};
+                rc = imm3_writer_append(w, cols, n);
+            }
+            if (w) {
+                int rc2 = imm3_writer_close(w);
+                if (!rc) rc = rc2;
+            }
+            if (rc) {
+                errors[(size_t)tid] = last_error();  // (the message is thread-local)
+                int zero = 0;
+                first_rc.compare_exchange_strong(zero, rc);
+                return;
+            }
         }
-        if ((rc = imm3_writer_close(w))) return rc;
+    };
+    std::vector<std::thread> pool;
+    for (int i = 1; i < nthreads; i++) pool.emplace_back(work, i);
+    work(0);
+    for (auto& th : pool) th.join();
+    if (int rc = first_rc.load()) {
+        for (auto& e : errors)
+            if (!e.empty()) return fail(rc, "%s", e.c_str());
+        return fail(rc, "imm3_synth_write failed");
     }
     return 0;
 }

@@ -1,8 +1,10 @@
 """Segment-sharded execution: one process (rank) per GPU, contiguous canonical segment slices
 (SURVEY.md §8e).  The data path has no collective: every rank scans its own slice.  The only
-exchange is one int64 per rank — its local match count (already capped at LIMIT) — through
-`torch.distributed.all_gather` (NCCL over NVLink on GPUs; gloo in the CPU tests), after which each
-rank knows its global output offset and how many of its leading rows survive the LIMIT cut.
+exchange is one int64 per rank — its local match count (already capped at LIMIT).  On GPUs the
+library does it itself, on the device (peer stores over NVLink behind the query's last kernel,
+`SegmentManager.comm_connect`, include/imm3.h imm3_comm_*); without a connected communicator (the
+gloo CPU tests, which exercise the host arithmetic) it is a `torch.distributed.all_gather`.  Either
+way each rank then knows its global output offset and how many of its leading rows survive the LIMIT cut.
 
 The local executor is any object with `begin(query) -> handle` (handle.local_count) and
 `finish(handle, take) -> list of numpy columns`.  The product executor is `CudaExecutor`
@@ -77,6 +79,11 @@ class ShardedEngine:
         import torch
 
         h = self.executor.begin(query)
+        if getattr(getattr(self.executor, "engine", None), "sm", None) is not None and self.executor.engine.sm.comm_connected:
+            # the GPUs exchanged the counts themselves (imm3_comm_*): nothing to gather here
+            counts = h.rank_counts
+            cols = self.executor.finish(h, h.take)
+            return ShardResult(self.rank, self.world, counts, h.global_offset, h.take, h.global_count, cols, float(h.device_ms))
         mine = torch.tensor([int(h.local_count)], dtype=torch.int64, device=self.collective_device)
         everyone = [torch.zeros_like(mine) for _ in range(self.world)]
         self.dist.all_gather(everyone, mine, group=self.group)  # the only exchange on the path

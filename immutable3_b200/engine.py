@@ -16,6 +16,7 @@ the CUDA library.  There is no compute and no fallback on this side.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass, field
 from typing import Iterator, List, Optional, Sequence, Union
 
@@ -160,14 +161,36 @@ _NP = {L.COL_INT: np.dtype("<i4"), L.COL_TINYINT: np.dtype("i1")}
 class Result:
     """Rows of one query in canonical order, column-major (owns an imm3_result)."""
 
-    def __init__(self, handle: int, lib):
+    def __init__(self, handle: int, lib, sm=None):
         self._h = handle
         self._lib = lib
+        self._sm = sm  # keeps the SegmentManager (and its imm3_db) alive for as long as this result is open
+        if sm is not None:
+            sm._results.add(self)
 
     # -- two-phase API (sharded execution) --
     @property
     def local_count(self) -> int:
         return int(self._lib.imm3_result_local_count(self._h))
+
+    # -- placement in the global result after the on-device count exchange (single handle: 0 / all / all) --
+    @property
+    def global_offset(self) -> int:
+        return int(self._lib.imm3_result_global_offset(self._h))
+
+    @property
+    def take(self) -> int:
+        return int(self._lib.imm3_result_take(self._h))
+
+    @property
+    def global_count(self) -> int:
+        return int(self._lib.imm3_result_global_count(self._h))
+
+    @property
+    def rank_counts(self) -> List[int]:
+        buf = (C.c_int64 * 16)()
+        n = L.check(self._lib.imm3_result_rank_counts(self._h, buf, 16))
+        return [int(buf[i]) for i in range(n)]
 
     def fetch(self, nrows: int) -> "Result":
         L.check(self._lib.imm3_result_fetch(self._h, int(nrows)))
@@ -308,9 +331,28 @@ class SegmentManager:
         self._lib = L.lib()
         self._h = C.c_void_p()
         opts = L.OpenOpts(device, rank, world, flags)
+        self._results = weakref.WeakSet()  # open results of this handle: closed before the handle is
+        self.comm_connected = False
         L.check(self._lib.imm3_open(str(dataDir).encode(), C.byref(opts), C.byref(self._h)))
         self.dataDir = str(dataDir)
         self.rank, self.world, self.flags = rank, world, flags
+
+    def comm_connect(self, group=None) -> "SegmentManager":
+        """Connect the ranks' count mailboxes (imm3_comm_*): after this, every query exchanges the per-rank match counts
+        on the GPUs over NVLink.  The 64-byte IPC handles travel once through torch.distributed (bootstrap only)."""
+        if self.world == 1:
+            return self
+        import torch.distributed as dist
+
+        mine = (C.c_uint8 * L.COMM_HANDLE_BYTES)()
+        L.check(self._lib.imm3_comm_local_handle(self._h, mine))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, bytes(mine), group=group)
+        blob = C.create_string_buffer(b"".join(everyone), self.world * L.COMM_HANDLE_BYTES)
+        L.check(self._lib.imm3_comm_connect(self._h, blob, self.world))
+        self.comm_connected = True
+        dist.barrier(group=group)  # nobody queries before every rank has mapped every mailbox
+        return self
 
     @property
     def handle(self):
@@ -360,7 +402,9 @@ class SegmentManager:
 
     def close(self):
         if self._h:
-            self._lib.imm3_close(self._h)
+            for r in list(self._results):
+                r.close()
+            L.check(self._lib.imm3_close(self._h))
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -395,7 +439,7 @@ class Engine:
         L.check(fn(self.sm.handle, query.table.encode(), preds, npreds, C.cast(proj, C.POINTER(C.c_char_p)),
                    len(query.project.cols), int(query.project.limit), C.byref(out)))
         del keep
-        return Result(out, self._lib)
+        return Result(out, self._lib, self.sm)
 
     def execute(self, query: Query) -> Result:
         """Engine.execute: the rows of the query in canonical order (iterate for Row objects)."""
@@ -409,7 +453,7 @@ class Engine:
         """Same text as `SqlCli -q` (SQLParser.scala)."""
         out = C.c_void_p()
         L.check(self._lib.imm3_query_sql(self.sm.handle, sql.encode(), C.byref(out)))
-        return Result(out, self._lib)
+        return Result(out, self._lib, self.sm)
 
     def filter_bitmap(self, table: str, select: SelectADT):
         """Selection bitmap of the conjunction (uint32 words, bit i of word w = canonical row 32w+i)."""

@@ -45,7 +45,8 @@ typedef enum imm3_status {
     IMM3_ERR_OOM = -5,
     IMM3_ERR_INVALID_ARG = -6,
     IMM3_ERR_IO = -7,
-    IMM3_ERR_STATE = -8        /* call sequence error (e.g. fetch before begin) */
+    IMM3_ERR_STATE = -8,       /* call sequence error (e.g. fetch before begin, close with open results) */
+    IMM3_ERR_COMM = -9         /* count exchange between the GPUs failed (peer mailbox unmappable, a peer's count late) */
 } imm3_status;
 
 /* ColumnType enumeration, Column.scala:13-16 */
@@ -143,6 +144,25 @@ int imm3_query(imm3_db* db, const char* table, const imm3_pred* preds, int npred
 int imm3_query_begin(imm3_db* db, const char* table, const imm3_pred* preds, int npreds,
                      const char* const* proj_cols, int nproj, int64_t limit, imm3_result** out);
 int64_t imm3_result_local_count(const imm3_result* r);
+
+/* ---- The fan-in across GPUs: ResultQueueOp (ResultQueue.scala:7-56) + the queue of Engine.scala:166,190-196 ----
+ * The reference funnels every worker's batches through one queue; across segment-sharded GPUs the ordered
+ * concatenation and the LIMIT cut need only the match count of every rank (global order = rank order).  The GPUs
+ * exchange those counts THEMSELVES: each rank owns a small mailbox in its HBM, exported as an IPC handle; once every
+ * rank has mapped every mailbox (imm3_comm_connect), imm3_query_begin appends a one-warp kernel to the query that
+ * stores the local count into every peer's mailbox over NVLink and waits for the peers' counts - no host round trip,
+ * no collective library.  Bootstrap: each rank calls imm3_comm_local_handle, the IMM3_COMM_HANDLE_BYTES-byte handles
+ * are all-gathered by whatever channel the host processes share (the JVM shim: its own RPC; bench/tests:
+ * torch.distributed), rank order = imm3_open_opts.rank, then each rank calls imm3_comm_connect with all of them.
+ * One process per GPU on one NVLink-connected node; every rank must issue the same queries in the same order. */
+#define IMM3_COMM_HANDLE_BYTES 64
+int imm3_comm_local_handle(imm3_db* db, void* handle_out /* IMM3_COMM_HANDLE_BYTES */);
+int imm3_comm_connect(imm3_db* db, const void* handles /* world x IMM3_COMM_HANDLE_BYTES, rank order */, int nhandles);
+/* After imm3_query_begin on a connected handle (a single handle reports offset 0, take = count = local count): */
+int64_t imm3_result_global_offset(const imm3_result* r); /* ordinal of this rank's first row in the global result  */
+int64_t imm3_result_take(const imm3_result* r);          /* leading local rows that survive the global LIMIT cut    */
+int64_t imm3_result_global_count(const imm3_result* r);  /* rows of the whole result: min(limit, sum of counts)     */
+int imm3_result_rank_counts(const imm3_result* r, int64_t* counts, int cap); /* local count of every rank; returns world */
 int imm3_result_fetch(imm3_result* r, int64_t nrows);
 /* Asynchronous form of fetch: the device->host copies are queued on the handle's copy stream and
  * the call returns; imm3_result_wait blocks until the rows are in host memory.  The consumer of

@@ -1165,3 +1165,212 @@ int64_t orc_table_nrows(orc_db* db, const char* table, int seg_begin, int seg_en
     }
     return rows;
 }
+
+/* ===================================================================================== */
+/* Writer side (test fixtures and the reference arm's tables need no product code)         */
+/*   SegmentWriter      Segment.scala:70-152   lazy block flush: a block is written when the */
+/*                      (blockSize+1)-th value arrives, close() writes what is buffered      */
+/*   LoaderCli loop     LoaderCli.scala:142-148 roll to a new segment when remaining == 0    */
+/*                      BEFORE a write => a full segment holds S*B + 1 rows = S full blocks  */
+/*                      + one 1-row tail block                               */
+/*   TableIO.store      Table.scala:27-35,50-59 compact JSON                                 */
+/* ===================================================================================== */
+static int mkdir_p(const char* path) {
+    char tmp[4096];
+    snprintf(tmp, sizeof tmp, "%s", path);
+    for (char* q = tmp + 1; *q; q++)
+        if (*q == '/') {
+            *q = 0;
+            if (mkdir(tmp, 0777) && errno != EEXIST) return fail(ORC_ERR_IO, "mkdir %s: %s", tmp, strerror(errno));
+            *q = '/';
+        }
+    if (mkdir(tmp, 0777) && errno != EEXIST) return fail(ORC_ERR_IO, "mkdir %s: %s", tmp, strerror(errno));
+    return 0;
+}
+
+/* One segment of one column: `nrows` cells (little-endian, `width` bytes each) cut into blocks of block_size rows (the
+ * last one shorter), each block encoded by the column's codec; <col>_<id>.dat + <col>_<id>.meta (Segment.scala:75-76,
+ * 41-45, 120-121, 144-151). */
+static int write_segment(const char* tdir, const char* col, int codec, int width, int seg_id, const uint8_t* cells,
+                         int64_t nrows, int block_size) {
+    char path[4096];
+    snprintf(path, sizeof path, "%s/%s_%d.dat", tdir, col, seg_id);
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(ORC_ERR_IO, "open %s: %s", path, strerror(errno));
+    const int64_t nblocks = (nrows + block_size - 1) / block_size;
+    int32_t* offs = (int32_t*)malloc((size_t)(nblocks + 1) * 4);
+    uint8_t* enc = (uint8_t*)malloc((size_t)block_size * 4 + (size_t)block_size / 8 + 512);
+    int32_t* vals = (int32_t*)malloc((size_t)block_size * 4);
+    int rc = 0;
+    int64_t at = 0;
+    if (!offs || !enc || !vals) rc = fail(ORC_ERR_OOM, "out of memory");
+    if (!rc) offs[0] = 0;
+    for (int64_t b = 0; !rc && b < nblocks; b++) {
+        const int64_t r0 = b * block_size, n = nrows - r0 < block_size ? nrows - r0 : block_size;
+        const uint8_t* src = cells + r0 * width;
+        int64_t len = n * width;
+        if (codec == ORC_CODEC_PFOR_INT) { /* SegmentWriter.flush: codec.encode(buffer), Segment.scala:120 */
+            for (int64_t i = 0; i < n; i++) vals[i] = orc_bytes_to_int(src + 4 * i);
+            len = orc_pfor_encode_block(vals, (int32_t)n, enc, (int64_t)block_size * 4 + block_size / 8 + 512);
+            if (len < 0) { rc = fail(ORC_ERR_OOM, "sorted-int encode failed"); break; }
+            src = enc;
+        }
+        if (fwrite(src, 1, (size_t)len, f) != (size_t)len) rc = fail(ORC_ERR_IO, "short write on %s", path);
+        at += len;
+        if (at > INT32_MAX) rc = fail(ORC_ERR_UNSUPPORTED, "segment %s exceeds 2 GiB (block offsets are Int, Segment.scala:33)", path);
+        offs[b + 1] = (int32_t)at;
+    }
+    fclose(f);
+    if (!rc) {
+        snprintf(path, sizeof path, "%s/%s_%d.meta", tdir, col, seg_id);
+        FILE* m = fopen(path, "wb");
+        if (!m) rc = fail(ORC_ERR_IO, "open %s: %s", path, strerror(errno));
+        else {
+            fputs("{\"blockOffset\":[", m);
+            for (int64_t b = 0; b <= nblocks; b++) fprintf(m, b ? ",%d" : "%d", offs[b]);
+            fputs("]}", m);
+            fclose(m);
+        }
+    }
+    free(offs);
+    free(enc);
+    free(vals);
+    return rc;
+}
+
+/* TableIO.clear + store: remove the regular files of the table directory, write _table.meta. */
+int orc_write_table_meta(const char* data_dir, const char* table, const char* meta_json) {
+    char tdir[4096], path[4400];
+    snprintf(tdir, sizeof tdir, "%s/%s", data_dir, table);
+    int rc = mkdir_p(tdir);
+    if (rc) return rc;
+    DIR* d = opendir(tdir);
+    if (d) {
+        struct dirent* e;
+        while ((e = readdir(d))) {
+            if (e->d_name[0] == '.' && (!e->d_name[1] || (e->d_name[1] == '.' && !e->d_name[2]))) continue;
+            snprintf(path, sizeof path, "%s/%s", tdir, e->d_name);
+            struct stat st;
+            if (!stat(path, &st) && S_ISREG(st.st_mode)) remove(path);
+        }
+        closedir(d);
+    }
+    snprintf(path, sizeof path, "%s/_table.meta", tdir);
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(ORC_ERR_IO, "open %s: %s", path, strerror(errno));
+    fputs(meta_json, f);
+    fclose(f);
+    return 0;
+}
+
+/* A whole column given as one array of cells: segments 0, 1, ... in the loader's layout. */
+int orc_write_column(const char* data_dir, const char* table, const char* col, int codec, int width, const void* cells,
+                     int64_t nrows, int block_size, int segment_size) {
+    if (block_size <= 0 || segment_size <= 0 || width <= 0 || nrows < 0) return fail(ORC_ERR_INVALID_ARG, "orc_write_column: bad sizes");
+    char tdir[4096];
+    snprintf(tdir, sizeof tdir, "%s/%s", data_dir, table);
+    const int64_t per_seg = (int64_t)block_size * segment_size + 1;
+    int64_t nseg = (nrows + per_seg - 1) / per_seg;
+    if (nseg == 0) nseg = 1; /* the writer of segment 0 exists before the first row arrives (LoaderCli.scala:118-127) */
+    for (int64_t s = 0; s < nseg; s++) {
+        const int64_t r0 = s * per_seg, n = nrows - r0 < per_seg ? nrows - r0 : per_seg;
+        int rc = write_segment(tdir, col, codec, width, (int)s, (const uint8_t*)cells + r0 * width, n > 0 ? n : 0, block_size);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+/* The synthetic tables of BASELINE.md: id = row index, age uniform [0,100), state uniform over 51 two-letter codes;
+ * counter-based PRNG (splitmix64 of (seed ^ column) << 32 ^ row), seed 42.  Numeric segment ids [seg_begin, seg_end). */
+static const char kStates[51][3] = {
+    "AL", "AK", "AZ", "AR", "CA", "CO", "CT", "DE", "FL", "GA", "HI", "ID", "IL", "IN", "IA", "KS", "KY",
+    "LA", "ME", "MD", "MA", "MI", "MN", "MS", "MO", "MT", "NE", "NV", "NH", "NJ", "NM", "NY", "NC", "ND",
+    "OH", "OK", "OR", "PA", "RI", "SC", "SD", "TN", "TX", "UT", "VT", "VA", "WA", "WV", "WI", "WY", "DC"};
+static inline uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+void orc_synth_row(int64_t row, int32_t* id, int8_t* age, char state[2]) {
+    *id = (int32_t)row;
+    *age = (int8_t)((splitmix64(((42ull ^ 1) << 32) ^ (uint64_t)row) >> 32) % 100u);
+    const char* s = kStates[(splitmix64(((42ull ^ 2) << 32) ^ (uint64_t)row) >> 32) % 51u];
+    state[0] = s[0];
+    state[1] = s[1];
+}
+
+typedef struct {
+    const char* tdir;
+    int64_t nrows, per_seg;
+    int block_size, id_codec, seg_end;
+    int* next;
+    int* rc;
+    pthread_mutex_t* mu;
+} synth_job_t;
+
+static void* synth_worker(void* arg) {
+    synth_job_t* j = (synth_job_t*)arg;
+    uint8_t* ids = (uint8_t*)malloc((size_t)j->per_seg * 4);
+    uint8_t* ages = (uint8_t*)malloc((size_t)j->per_seg);
+    uint8_t* states = (uint8_t*)malloc((size_t)j->per_seg * 2);
+    for (;;) {
+        pthread_mutex_lock(j->mu);
+        const int seg = (*j->next)++;
+        const int stop = *j->rc != 0;
+        pthread_mutex_unlock(j->mu);
+        if (seg >= j->seg_end || stop) break;
+        int rc = (!ids || !ages || !states) ? ORC_ERR_OOM : 0;
+        const int64_t r0 = (int64_t)seg * j->per_seg, n = j->nrows - r0 < j->per_seg ? j->nrows - r0 : j->per_seg;
+        for (int64_t i = 0; !rc && i < n; i++) {
+            int32_t id;
+            orc_synth_row(r0 + i, &id, (int8_t*)&ages[i], (char*)&states[2 * i]);
+            orc_int_to_bytes(id, ids + 4 * i);
+        }
+        if (!rc) rc = write_segment(j->tdir, "id", j->id_codec, 4, seg, ids, n, j->block_size);
+        if (!rc) rc = write_segment(j->tdir, "state", ORC_CODEC_DENSE_STRING, 2, seg, states, n, j->block_size);
+        if (!rc) rc = write_segment(j->tdir, "age", ORC_CODEC_DENSE_TINYINT, 1, seg, ages, n, j->block_size);
+        if (rc) {
+            pthread_mutex_lock(j->mu);
+            if (!*j->rc) *j->rc = rc;
+            pthread_mutex_unlock(j->mu);
+        }
+    }
+    free(ids);
+    free(ages);
+    free(states);
+    return NULL;
+}
+
+int orc_synth_write(const char* data_dir, const char* table, int64_t nrows, int32_t block_size, int32_t segment_size,
+                    int32_t id_codec, int32_t seg_begin, int32_t seg_end, int write_table_meta, int nthreads) {
+    if (nrows < 0 || block_size <= 0 || segment_size <= 0) return fail(ORC_ERR_INVALID_ARG, "orc_synth_write: bad sizes");
+    char tdir[4096];
+    snprintf(tdir, sizeof tdir, "%s/%s", data_dir, table);
+    if (write_table_meta) {
+        char meta[1024];
+        snprintf(meta, sizeof meta,
+                 "{\"name\":\"%s\",\"columns\":[{\"name\":\"id\",\"columnType\":\"INT\",\"codec\":\"%s\",\"dtypeAttrs\":{}},"
+                 "{\"name\":\"state\",\"columnType\":\"STRING\",\"codec\":\"DENSE_STRING\",\"dtypeAttrs\":{\"size\":\"2\"}},"
+                 "{\"name\":\"age\",\"columnType\":\"TINYINT\",\"codec\":\"DENSE_TINYINT\",\"dtypeAttrs\":{}}],\"blockSize\":%d}",
+                 table, id_codec == ORC_CODEC_PFOR_INT ? "PFOR_INT" : "DENSE_INT", block_size);
+        int rc = orc_write_table_meta(data_dir, table, meta);
+        if (rc) return rc;
+    }
+    const int64_t per_seg = (int64_t)block_size * segment_size + 1;
+    const int64_t nseg = (nrows + per_seg - 1) / per_seg;
+    if (seg_end < 0 || seg_end > nseg) seg_end = (int32_t)nseg;
+    if (seg_begin < 0) seg_begin = 0;
+    if (seg_end <= seg_begin) return 0;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > seg_end - seg_begin) nthreads = seg_end - seg_begin;
+    if (nthreads > 256) nthreads = 256;
+    pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+    int next = seg_begin, rc = 0;
+    synth_job_t job = {tdir, nrows, per_seg, block_size, id_codec, seg_end, &next, &rc, &mu};
+    pthread_t th[256];
+    for (int i = 1; i < nthreads; i++) pthread_create(&th[i], NULL, synth_worker, &job);
+    synth_worker(&job);
+    for (int i = 1; i < nthreads; i++) pthread_join(th[i], NULL);
+    return rc ? fail(rc, "orc_synth_write failed (status %d)", rc) : 0;
+}

@@ -94,6 +94,17 @@ int orc_filter_bitmap(orc_db* db, const char* table, const orc_pred* preds, int 
                       int seg_begin, int seg_end, uint32_t** words, int64_t* nwords, int64_t* nselected);
 void orc_free(void* p);
 
+/* ---- Writer side: SegmentWriter (Segment.scala:70-152) + the LoaderCli roll (LoaderCli.scala:142-148) +
+ *      TableIO.store (Table.scala:27-35,50-59), so that fixtures and the reference arm's tables are made without any
+ *      product code.  Cells are little-endian, `width` bytes each (DataType.scala:40-47, 60, 69). ---- */
+int orc_write_table_meta(const char* data_dir, const char* table, const char* meta_json); /* clears the table dir */
+int orc_write_column(const char* data_dir, const char* table, const char* col, int codec, int width, const void* cells,
+                     int64_t nrows, int block_size, int segment_size);
+/* BASELINE.md's synthetic tables (id:DENSE_INT|PFOR_INT, state:DENSE_STRING size=2, age:DENSE_TINYINT). */
+void orc_synth_row(int64_t row, int32_t* id, int8_t* age, char state[2]);
+int orc_synth_write(const char* data_dir, const char* table, int64_t nrows, int32_t block_size, int32_t segment_size,
+                    int32_t id_codec, int32_t seg_begin, int32_t seg_end, int write_table_meta, int nthreads);
+
 const char* orc_last_error(void);
 
 #ifdef __cplusplus

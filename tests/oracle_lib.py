@@ -56,6 +56,10 @@ def lib():
             "orc_result_free": (None, [P]),
             "orc_filter_bitmap": (C.c_int, [P, C.c_char_p, C.POINTER(OrcPred), C.c_int, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
             "orc_free": (None, [P]),
+            "orc_write_table_meta": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p]),
+            "orc_write_column": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, P, C.c_int64, C.c_int, C.c_int]),
+            "orc_synth_row": (None, [C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int8), C.c_char_p]),
+            "orc_synth_write": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int, C.c_int]),
             "orc_last_error": (C.c_char_p, []),
         }
         for n, (r, a) in sig.items():
@@ -209,3 +213,38 @@ def dense_decode(data: bytes, width: int) -> bytes:
     out = C.create_string_buffer((len(data) // width + 2) * width)
     n = lib().orc_dense_decode(data, len(data), width, out)
     return out.raw[: n * width]
+
+
+# writer side (fixtures / reference-arm tables without product code) ---------------------------------
+CODEC_PFOR_INT, CODEC_DENSE_INT, CODEC_DENSE_TINYINT, CODEC_DENSE_STRING = 0, 1, 2, 3
+_CODECS = {"PFOR_INT": (CODEC_PFOR_INT, "INT", 4), "DENSE_INT": (CODEC_DENSE_INT, "INT", 4), "DENSE_TINYINT": (CODEC_DENSE_TINYINT, "TINYINT", 1),
+           "DENSE_STRING": (CODEC_DENSE_STRING, "STRING", 0)}
+
+
+def write_table(data_dir, name, specs, cols, block_size, segment_size):
+    """Oracle-side SegmentWriter + LoaderCli layout: specs use the loader's "name:CODEC[:k=v;k=v]" syntax
+    (LoaderCli.scala:66-80), cols = {name: numpy array (int32 / int8 / S<k>)}."""
+    import json
+
+    metas, jobs = [], []
+    for spec in specs:
+        parts = spec.split(":")
+        cname, codec = parts[0], parts[1]
+        attrs = dict(kv.split("=") for kv in parts[2].split(";")) if len(parts) > 2 else {}
+        cid, ctype, width = _CODECS[codec]
+        if codec == "DENSE_STRING":
+            width = int(attrs["size"])
+        metas.append({"name": cname, "columnType": ctype, "codec": codec, "dtypeAttrs": attrs})
+        arr = cols[cname]
+        dt = {4: np.dtype("<i4"), 1: np.dtype("i1")}.get(width) if ctype != "STRING" else np.dtype(f"S{width}")
+        jobs.append((cname, cid, width, np.ascontiguousarray(arr, dtype=dt)))
+    meta = json.dumps({"name": name, "columns": metas, "blockSize": block_size}, separators=(",", ":"))
+    _check(lib().orc_write_table_meta(str(data_dir).encode(), name.encode(), meta.encode()))
+    for cname, cid, width, arr in jobs:
+        _check(lib().orc_write_column(str(data_dir).encode(), name.encode(), cname.encode(), cid, width, arr.ctypes.data, len(arr), block_size, segment_size))
+
+
+def synth_write(data_dir, table, nrows, block_size=1024, segment_size=1000, id_codec=CODEC_DENSE_INT, seg_begin=0, seg_end=-1,
+                write_table_meta=True, nthreads=1):
+    _check(lib().orc_synth_write(str(data_dir).encode(), table.encode(), nrows, block_size, segment_size, id_codec, seg_begin, seg_end,
+                                 1 if write_table_meta else 0, nthreads))
