@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -14,6 +15,13 @@ namespace imm3 {
 void set_error(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
 int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
 const char* last_error();
+
+// Host threads for the embarrassingly parallel parts of imm3_open (one .meta / .dat file per task): hardware
+// concurrency capped at 16, IMM3_IO_THREADS overrides.
+int io_threads();
+// fn(i) for i in [0, n) on up to `nthreads` threads (dynamic assignment); returns the first non-zero status, with that
+// thread's error message re-published on the calling thread.
+int parallel_for(int64_t n, int nthreads, const std::function<int(int64_t)>& fn);
 
 // JVM narrowing used by the predicate constants (Select.scala:65,73,103,111,141,149).
 int32_t d2i(double d);  // Scala Double.toInt

@@ -4,9 +4,13 @@
 #include <dirent.h>
 
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <mutex>
 #include <sstream>
+#include <thread>
 
 #include "common.hpp"
 #include "json_min.hpp"
@@ -29,6 +33,48 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 const char* last_error() { return g_err; }
+
+int io_threads() {
+    int n = (int)std::thread::hardware_concurrency();
+    if (n < 1) n = 1;
+    if (n > 16) n = 16;
+    if (const char* e = getenv("IMM3_IO_THREADS")) n = std::max(1, atoi(e));
+    return n;
+}
+
+int parallel_for(int64_t n, int nthreads, const std::function<int(int64_t)>& fn) {
+    if (n <= 0) return 0;
+    if (nthreads > n) nthreads = (int)n;
+    if (nthreads <= 1) {
+        for (int64_t i = 0; i < n; i++)
+            if (int rc = fn(i)) return rc;
+        return 0;
+    }
+    std::atomic<int64_t> next(0);
+    std::atomic<int> first(0);
+    std::mutex mu;
+    std::string why;
+    auto work = [&]() {
+        for (;;) {
+            const int64_t i = next.fetch_add(1);
+            if (i >= n || first.load()) return;
+            if (int rc = fn(i)) {
+                std::lock_guard<std::mutex> lock(mu);
+                if (!first.load()) {
+                    why = last_error();  // (the message is thread-local: carry it over to the caller)
+                    first.store(rc);
+                }
+                return;
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; t++) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    if (int rc = first.load()) return fail(rc, "%s", why.c_str());
+    return 0;
+}
 
 // Scala Double.toInt == JVM d2i: NaN -> 0, saturating, else truncation toward zero.
 int32_t d2i(double d) {

@@ -132,50 +132,70 @@ static int load_table(const std::string& data_dir, const std::string& dir_name, 
     for (auto& f : dats[0]) t->file_ids.push_back(parse_file_id(f, t->cols[0].meta.name));
     shard_range(t->nsegments, rank, world, &t->seg_begin, &t->seg_end);
 
-    // Per column: offsets of the owned segments, block row counts.
-    std::vector<std::vector<int32_t>> block_rows(t->cols.size());
-    for (size_t c = 0; c < t->cols.size(); c++) {
-        ColumnStore& col = t->cols[c];
-        for (int s = t->seg_begin; s < t->seg_end; s++) {
-            SegmentFile sf;
-            sf.path = t->dir + "/" + dats[c][(size_t)s];
-            sf.file_id = parse_file_id(dats[c][(size_t)s], col.meta.name);
-            std::string mpath = t->dir + "/" + metas[c][(size_t)s], mtxt;  // i-th sorted .meta pairs with i-th sorted .dat
-            if ((rc = read_text_file(mpath, &mtxt))) return rc;
-            if ((rc = parse_segment_meta(mtxt, mpath, &sf.offsets))) return rc;
-            if (sf.offsets.empty()) return fail(IMM3_ERR_BAD_FORMAT, "%s: empty blockOffset array", mpath.c_str());
-            if (sf.offsets[0] != 0) return fail(IMM3_ERR_BAD_FORMAT, "%s: blockOffset must start at 0", mpath.c_str());
-            for (size_t b = 1; b < sf.offsets.size(); b++)
-                if (sf.offsets[b] < sf.offsets[b - 1]) return fail(IMM3_ERR_BAD_FORMAT, "%s: blockOffset decreases", mpath.c_str());
-            sf.nbytes = sf.offsets.back();
-            struct stat st;
-            if (stat(sf.path.c_str(), &st)) return fail(IMM3_ERR_IO, "stat %s: %s", sf.path.c_str(), strerror(errno));
-            if (st.st_size < sf.nbytes)
-                return fail(IMM3_ERR_BAD_FORMAT, "%s: %lld bytes on disk, block offsets need %lld", sf.path.c_str(),
-                            (long long)st.st_size, (long long)sf.nbytes);
-            const size_t nb = sf.offsets.size() - 1;
-            if (col.meta.codec == IMM3_CODEC_PFOR_INT) {
-                FileMap fm;
-                if ((rc = fm.open(sf.path, (size_t)sf.nbytes))) return rc;
-                for (size_t b = 0; b < nb; b++) {
-                    int32_t n = 0;
-                    if ((rc = pfor_validate_block(fm.data + sf.offsets[b], sf.offsets[b + 1] - sf.offsets[b], &n))) {
-                        std::string why = last_error();
-                        return fail(rc, "%s block %zu: %s", sf.path.c_str(), b, why.c_str());
-                    }
-                    block_rows[c].push_back(n);
+    // Per column: offsets of the owned segments, block row counts.  One task per (column, segment) file pair on the I/O
+    // thread pool (a 1 B-row table is 2931 .meta files and 277 MB of sorted-int blocks to validate); merged in order below.
+    const int nown = t->seg_end - t->seg_begin;
+    const size_t ncols = t->cols.size();
+    struct SegTask {
+        SegmentFile sf;
+        std::vector<int32_t> rows;
+    };
+    std::vector<SegTask> tasks(ncols * (size_t)nown);
+    rc = parallel_for((int64_t)tasks.size(), io_threads(), [&](int64_t ti) -> int {
+        const size_t c = (size_t)ti / (size_t)nown;
+        const int s = t->seg_begin + (int)((size_t)ti % (size_t)nown);
+        const ColumnStore& col = t->cols[c];
+        SegTask& task = tasks[(size_t)ti];
+        SegmentFile& sf = task.sf;
+        int rc = 0;
+        sf.path = t->dir + "/" + dats[c][(size_t)s];
+        sf.file_id = parse_file_id(dats[c][(size_t)s], col.meta.name);
+        std::string mpath = t->dir + "/" + metas[c][(size_t)s], mtxt;  // i-th sorted .meta pairs with i-th sorted .dat
+        if ((rc = read_text_file(mpath, &mtxt))) return rc;
+        if ((rc = parse_segment_meta(mtxt, mpath, &sf.offsets))) return rc;
+        if (sf.offsets.empty()) return fail(IMM3_ERR_BAD_FORMAT, "%s: empty blockOffset array", mpath.c_str());
+        if (sf.offsets[0] != 0) return fail(IMM3_ERR_BAD_FORMAT, "%s: blockOffset must start at 0", mpath.c_str());
+        for (size_t b = 1; b < sf.offsets.size(); b++)
+            if (sf.offsets[b] < sf.offsets[b - 1]) return fail(IMM3_ERR_BAD_FORMAT, "%s: blockOffset decreases", mpath.c_str());
+        sf.nbytes = sf.offsets.back();
+        struct stat st;
+        if (stat(sf.path.c_str(), &st)) return fail(IMM3_ERR_IO, "stat %s: %s", sf.path.c_str(), strerror(errno));
+        if (st.st_size < sf.nbytes)
+            return fail(IMM3_ERR_BAD_FORMAT, "%s: %lld bytes on disk, block offsets need %lld", sf.path.c_str(),
+                        (long long)st.st_size, (long long)sf.nbytes);
+        const size_t nb = sf.offsets.size() - 1;
+        task.rows.reserve(nb);
+        if (col.meta.codec == IMM3_CODEC_PFOR_INT) {
+            FileMap fm;
+            if ((rc = fm.open(sf.path, (size_t)sf.nbytes))) return rc;
+            for (size_t b = 0; b < nb; b++) {
+                int32_t n = 0;
+                if ((rc = pfor_validate_block(fm.data + sf.offsets[b], sf.offsets[b + 1] - sf.offsets[b], &n))) {
+                    std::string why = last_error();
+                    return fail(rc, "%s block %zu: %s", sf.path.c_str(), b, why.c_str());
                 }
-            } else {
-                for (size_t b = 0; b < nb; b++) {
-                    int64_t len = (int64_t)sf.offsets[b + 1] - sf.offsets[b];
-                    if (len % col.meta.width)
-                        return fail(IMM3_ERR_BAD_FORMAT, "%s block %zu: %lld bytes is not a multiple of the value width %d",
-                                    sf.path.c_str(), b, (long long)len, col.meta.width);
-                    block_rows[c].push_back((int32_t)(len / col.meta.width));
-                }
+                task.rows.push_back(n);
             }
-            col.encoded_bytes += sf.nbytes;
-            col.segs.push_back(std::move(sf));
+        } else {
+            for (size_t b = 0; b < nb; b++) {
+                int64_t len = (int64_t)sf.offsets[b + 1] - sf.offsets[b];
+                if (len % col.meta.width)
+                    return fail(IMM3_ERR_BAD_FORMAT, "%s block %zu: %lld bytes is not a multiple of the value width %d",
+                                sf.path.c_str(), b, (long long)len, col.meta.width);
+                task.rows.push_back((int32_t)(len / col.meta.width));
+            }
+        }
+        return 0;
+    });
+    if (rc) return rc;
+    std::vector<std::vector<int32_t>> block_rows(ncols);
+    for (size_t c = 0; c < ncols; c++) {
+        ColumnStore& col = t->cols[c];
+        for (int s = 0; s < nown; s++) {
+            SegTask& task = tasks[c * (size_t)nown + (size_t)s];
+            block_rows[c].insert(block_rows[c].end(), task.rows.begin(), task.rows.end());
+            col.encoded_bytes += task.sf.nbytes;
+            col.segs.push_back(std::move(task.sf));
         }
         if (block_rows[c] != block_rows[0])
             return fail(IMM3_ERR_BAD_FORMAT, "table %s: columns %s and %s do not hold the same rows per block",

@@ -441,6 +441,21 @@ class Engine:
         del keep
         return Result(out, self._lib, self.sm)
 
+    def prepare(self, query: Query):
+        """The argument marshalling of `begin`, done once: `begin_prepared(p)` then costs one foreign call per query (a
+        caller that repeats a query - the benchmark, a dashboard - keeps Python out of the measured path)."""
+        if not isinstance(query.project, Project):
+            raise L.Imm3Error(L.ERR_UNSUPPORTED, "only Project queries are on the scan/filter/project path")
+        preds, npreds, keep = _pred_array(flatten_select(query.select))
+        proj = L.cstr_array(list(query.project.cols))
+        return (query.table.encode(), preds, npreds, C.cast(proj, C.POINTER(C.c_char_p)), len(query.project.cols),
+                int(query.project.limit), (keep, proj))
+
+    def begin_prepared(self, p) -> Result:
+        out = C.c_void_p()
+        L.check(self._lib.imm3_query_begin(self.sm.handle, p[0], p[1], p[2], p[3], p[4], p[5], C.byref(out)))
+        return Result(out, self._lib, self.sm)
+
     def execute(self, query: Query) -> Result:
         """Engine.execute: the rows of the query in canonical order (iterate for Row objects)."""
         return self._call(self._lib.imm3_query, query)
