@@ -315,13 +315,13 @@ int upload_all(imm3_db* db) {
             col.arena_bytes = arena;
             CUDA_TRY(cudaMemsetAsync(col.d_arena + payload, 0, arena - payload, db->stream));  // zero padding up to a whole tile
             if (!dense) {
-                CUDA_TRY(cudaMalloc(&col.d_word_off, col.word_off.size() * sizeof(uint32_t)));
+                CUDA_TRY(cudaMalloc(&col.d_word_off, col.word_off.size() * sizeof(uint32_t) + 128));  // (+128: the filter kernel's TMA reads 12 entries per tile)
                 CUDA_TRY(cudaMemcpyAsync(col.d_word_off, col.word_off.data(), col.word_off.size() * sizeof(uint32_t),
                                          cudaMemcpyHostToDevice, db->stream));
             }
             cut_pieces(col, &pieces);
         }
-        CUDA_TRY(cudaMalloc(&t.d_row_start, t.row_start.size() * sizeof(uint64_t)));
+        CUDA_TRY(cudaMalloc(&t.d_row_start, t.row_start.size() * sizeof(uint64_t) + 128));  // (+128: ... and 10 row ordinals)
         CUDA_TRY(cudaMemcpyAsync(t.d_row_start, t.row_start.data(), t.row_start.size() * sizeof(uint64_t),
                                  cudaMemcpyHostToDevice, db->stream));
     }
@@ -567,7 +567,25 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
             int64_t cap = 0;  // per-warp scratch for the byte-swapped words of one encoded block
             for (int ci : pfor_cols) cap = std::max<int64_t>(cap, t.cols[(size_t)ci].max_block_words);
             sp.blk_words_cap = (int)std::min<int64_t>(1120, ((cap + 4 + 31) / 32) * 32);
-            pr->dyn_smem = blocks_multi_smem_bytes(sp.npfor, sp.blk_words_cap);
+            // Filter kernel: a TMA ring of raw tiles (8 blocks of every encoded column that carries a predicate + metadata).
+            int64_t tile_cap = 0;
+            int nstaged = 0;
+            sp.pfor_filter_mask = 0;
+            for (int i = 0; i < sp.nfilter; i++)
+                if (sp.filter[i].pfor_slot >= 0) sp.pfor_filter_mask |= 1u << sp.filter[i].pfor_slot;
+            for (int s = 0; s < sp.npfor; s++)
+                if ((sp.pfor_filter_mask >> s) & 1u) {
+                    tile_cap = std::max<int64_t>(tile_cap, t.cols[(size_t)pfor_cols[(size_t)s]].max_tile_bytes);
+                    nstaged++;
+                }
+            sp.blk_tile_bytes = (int)((tile_cap + 16 + 15) & ~15ll);
+            const int slot_bytes = blocks_filter_slot_bytes(nstaged, sp.blk_tile_bytes);
+            int ring = std::max(2, std::min(kMaxFilterStages, (48 * 1024) / slot_bytes));
+            if (const char* e = getenv("IMM3_BLOCKS_STAGES")) ring = std::max(2, std::min(kMaxFilterStages, atoi(e)));
+            while (ring > 2 && (size_t)ring * slot_bytes > 200 * 1024) ring--;
+            sp.stages = ring;  // (the row-space variant below re-plans these two for the dense filter kernel)
+            sp.stage_bytes = slot_bytes;
+            pr->dyn_smem = blocks_filter_smem_bytes(nstaged, sp.blk_tile_bytes, ring);
             pr->blocks_emit_smem = blocks_emit_smem_bytes(sp.npfor, sp.blk_words_cap);
             int occ_e = 0;
             CUDA_TRY(blocks_multi_occupancy(pr->dyn_smem, pr->blocks_emit_smem, pr->hybrid ? nullptr : &occ, &occ_e));
@@ -758,7 +776,6 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         if ((rc = ensure_buf(&db->d_tile_cnt, ntiles_pad * 4))) return rc;
         if ((rc = ensure_buf(&db->d_tile_off, ntiles_pad * 8))) return rc;
         CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
-        CUDA_TRY(cudaMemsetAsync(db->d_tile_cnt.p, 0, (size_t)ntiles * 4, db->stream));  // K1b accumulates the tile counts with atomics
         CUDA_TRY(launch_blocks_filter(pr->sp, (uint32_t*)db->d_bitmap.p, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
                                       (unsigned long long*)db->d_tile_off.p, db->d_ctrl, nblocks, pr->grid, pr->dyn_smem, db->stream));
         *launches = 1;

@@ -1,4 +1,4 @@
-// k_blocks_multi.cuh - the block pipeline of the sorted-integer codec: warp-per-block decode, blocks_filter_kernel (K1b), blocks_emit_kernel (K3b)
+// k_blocks_multi.cuh - the block pipeline of the sorted-integer codec: warp-per-block decode (pfor_decode_warp), blocks_emit_kernel (K3b)
 // Fragment of kernels.cu (one translation unit, included inside namespace imm3 in the order listed there).
 #pragma once
 
@@ -21,9 +21,8 @@ constexpr int kBlkRows = 1024;        // largest block this pipeline takes
 constexpr int kBlkLane = 36;          // decoded values: mini-block m lives at vals[36 m .. 36 m + 32): 16-byte aligned rows, so a lane
 constexpr int kBlkVals = 32 * kBlkLane;  // moves its mini-block with 128-bit accesses (conflict-free per quarter warp), and the
                                       // row-per-lane view (emit) reads consecutive words
-// per warp, in words: the filter kernel keeps the block's byte-swapped words and ONE decoded column; the emit kernel keeps
-// the words, every decoded column of the select list, their mini-block bases and a 1024-entry selection vector
-__host__ __device__ constexpr int blk_warp_smem_words(int npfor, int words_cap) { return words_cap + (npfor > 0 ? kBlkVals : 0); }
+// per warp, in words: the emit kernel keeps the block's byte-swapped words, every decoded column of the select list, their
+// mini-block bases and a 1024-entry selection vector  (the filter kernel, k_blocks_filter.cuh, stages raw tiles instead)
 __host__ __device__ constexpr int blk_emit_warp_words(int npfor, int words_cap) { return words_cap + npfor * (kBlkVals + 32) + 512; }
 
 // One mini-block of 32 B-bit deltas, B known at compile time: every word index and shift folds to an immediate.
@@ -184,115 +183,6 @@ __device__ __forceinline__ uint32_t pfor_decode_warp(const uint32_t* __restrict_
     return base;
 }
 
-__global__ void __launch_bounds__(kComputeThreads, 4) blocks_filter_kernel(const __grid_constant__ ScanPlan P, uint32_t* __restrict__ bitmapB,
-                                                                             uint32_t* __restrict__ blk_cnt, uint32_t* __restrict__ tile_cnt,
-                                                                             unsigned long long* __restrict__ tile_off, ScanCtrl* ctrl,
-                                                                             long long nblocks) {
-    __shared__ FilterShared S;
-    __shared__ PforCol s_pfor[kMaxPforCols];
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the emit kernel may become resident and set itself up
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < P.lit_bytes; i += kComputeThreads) S.lits[i] = P.lits[i];  // (nothing to copy unless a MATCH predicate exists)
-    copy_plan_tables(P, S.filter, S.proj, tid, kComputeThreads);
-    if (tid < kMaxPforCols) {
-#pragma unroll
-        for (int i = 0; i < kMaxPforCols; i++)
-            if (tid == i) s_pfor[i] = P.pfor[i];
-    }
-    __syncthreads();
-    uint32_t* const Wb = reinterpret_cast<uint32_t*>(dyn_smem) + warp * blk_warp_smem_words(P.npfor, P.blk_words_cap);
-    uint32_t* const vals0 = Wb + P.blk_words_cap;
-    const long long ntiles = P.ntiles;  // tiles of 8 blocks
-
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long blk = tile * kComputeWarps + warp;
-        uint32_t myword = 0;  // lane w keeps bitmap word w of the block
-        unsigned cnt = 0;
-        if (blk < nblocks) {
-            // block metadata in ONE round trip: lanes 0,1 = row ordinals, lanes 2+2s, 3+2s = word offsets of PFOR slot s
-            unsigned long long meta = 0;
-            if (lane < 2) meta = P.row_start[blk + lane];
-            else if (lane < 2 + 2 * P.npfor) meta = s_pfor[(lane - 2) >> 1].word_off[blk + (lane & 1)];
-            const long long R0 = (long long)__shfl_sync(0xFFFFFFFFu, meta, 0);
-            const int n = (int)((long long)__shfl_sync(0xFFFFFFFFu, meta, 1) - R0);
-            const int nwords = (n + 31) >> 5;
-            {   // rows of the block that exist: lane w owns word w = rows [32w, 32w+32)
-                const int left = n - lane * 32;
-                myword = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
-            }
-            int decoded = -1;   // PFOR slot whose block sits in vals0 (one buffer: the filter kernel keeps no decoded column)
-            uint32_t base = 0;
-#pragma unroll 1
-            for (int fi = 0; fi < P.nfilter; fi++) {
-                const FilterCol f = S.filter[fi];
-                if (f.kind == kFilterI32Range && f.pfor_slot >= 0) {
-                    // decoded column: lane m tests its own mini-block (the values it just unpacked) - no ballots
-                    if (f.pfor_slot != decoded) {  // (two predicates on one column share the decode)
-                        const uint32_t wo0 = (uint32_t)__shfl_sync(0xFFFFFFFFu, meta, 2 + 2 * f.pfor_slot);
-                        const uint32_t wo1 = (uint32_t)__shfl_sync(0xFFFFFFFFu, meta, 3 + 2 * f.pfor_slot);
-                        base = pfor_decode_warp(s_pfor[f.pfor_slot].words, wo0, wo1, n, Wb, P.blk_words_cap, vals0, lane);
-                        decoded = f.pfor_slot;
-                    }
-                    const uint32_t* vp = vals0 + lane * kBlkLane;
-                    const uint32_t lo = (uint32_t)f.lo - base;
-                    uint32_t word = 0;
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const uint4 v = reinterpret_cast<const uint4*>(vp)[q];
-                        word |= ((uint32_t)((v.x - lo) <= f.span) | ((uint32_t)((v.y - lo) <= f.span) << 1) | ((uint32_t)((v.z - lo) <= f.span) << 2) |
-                                 ((uint32_t)((v.w - lo) <= f.span) << 3))
-                                << (4 * q);
-                    }
-                    myword &= word;
-                } else {
-                    // dense column: row per lane (coalesced), one ballot per 32 rows
-                    for (int w = 0; w < nwords; w++) {
-                        const int i = w * 32 + lane;
-                        bool pass = i < n;
-                        if (f.kind == kFilterI32Range) {
-                            const uint32_t v = pass ? __ldg(reinterpret_cast<const uint32_t*>(f.base) + R0 + i) : 0u;
-                            pass = pass && ((v - (uint32_t)f.lo) <= f.span);
-                        } else if (f.kind == kFilterI8Range) {
-                            const int v = pass ? (int)(signed char)__ldg(f.base + R0 + i) : 0;
-                            pass = pass && ((uint32_t)(v - f.lo) <= f.span);
-                        } else {
-                            bool hit = false;
-                            if (pass) {
-                                const uint8_t* cell = f.base + (R0 + i) * f.width;
-                                for (int l = 0; l < f.nlit && !hit; l++) {
-                                    bool eq = true;
-                                    for (int bb = 0; bb < f.width; bb++) eq = eq && (__ldg(cell + bb) == S.lits[f.lit_off + l * f.width + bb]);
-                                    hit = eq;
-                                }
-                            }
-                            pass = hit;
-                        }
-                        const uint32_t word = __ballot_sync(0xFFFFFFFFu, pass);
-                        if (lane == w) myword &= word;
-                    }
-                }
-            }
-            bitmapB[blk * 32 + lane] = myword;
-            cnt = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(myword));
-            if (lane == 0) blk_cnt[blk] = cnt;
-        }
-        if (lane == 0 && cnt) atomicAdd(tile_cnt + tile, cnt);  // (the host zeroes the tile counts before the launch)
-    }
-
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        const unsigned prev = atomicAdd(&ctrl->exited, 1u);
-        S.is_last = prev == gridDim.x - 1;
-        if (S.is_last) ctrl->exited = 0;
-    }
-    __syncthreads();
-    if (S.is_last) {
-        __threadfence();
-        scan_tile_counts(S, tile_cnt, tile_off, ntiles, P.limit, ctrl);
-    }
-}
-
 // Emit kernel of the block pipelines: one warp per reference block with at least one surviving row.
 //   ROWSPACE = false : bitmap written by blocks_filter_kernel (32 words per block, block-local alignment); a block's first
 //                      ordinal = tile offset + counts of the tile's earlier blocks.
@@ -393,7 +283,14 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const _
             g = (long long)toff + __reduce_add_sync(0xFFFFFFFFu, sc + below);
         } else {
             g = (long long)tile_o + __reduce_add_sync(0xFFFFFFFFu, lane < (int)(blk & 7) ? tile_c : 0u);
-            myword = __ldg(bitmap + blk * 32 + lane);
+            // the filter kernel stores the 32 words of a block only if SOME of its rows survive; all of them: the count says so
+            const unsigned mycnt = __shfl_sync(0xFFFFFFFFu, tile_c, (int)(blk & 7));
+            if (mycnt == (unsigned)n) {
+                const int left = n - lane * 32;
+                myword = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+            } else {
+                myword = __ldg(bitmap + blk * 32 + lane);
+            }
         }
         if (g >= P.limit) continue;
         __syncwarp();  // (the previous block's readers are done with the scratch)

@@ -33,6 +33,7 @@ namespace imm3 {
 #include "k_blocks_single.cuh"
 #include "k_multipass.cuh"
 #include "k_blocks_multi.cuh"
+#include "k_blocks_filter.cuh"
 #include "k_comm.cuh"
 
 // =============================================================================================
@@ -168,13 +169,14 @@ cudaError_t launch_emit_stream(const ScanPlan& plan, const uint32_t* bitmap, con
     return cudaLaunchKernelEx(&cfg, emit_stream_kernel, plan, bitmap, span_cnt, tile_cnt, tile_off, nsub, ring, stage_bytes, dense_mode, ctrl);
 }
 
-size_t blocks_multi_smem_bytes(int npfor, int words_cap) { return (size_t)kComputeWarps * blk_warp_smem_words(npfor, words_cap) * 4; }
+size_t blocks_filter_smem_bytes(int nstaged, int tile_cap_bytes, int ring) { return (size_t)ring * (size_t)blk_filter_slot_bytes(nstaged, tile_cap_bytes); }
+int blocks_filter_slot_bytes(int nstaged, int tile_cap_bytes) { return blk_filter_slot_bytes(nstaged, tile_cap_bytes); }
 size_t blocks_emit_smem_bytes(int npfor, int words_cap) { return (size_t)kComputeWarps * blk_emit_warp_words(npfor, words_cap) * 4; }
 cudaError_t blocks_multi_occupancy(size_t filter_smem, size_t emit_smem, int* filter_blocks_per_sm, int* emit_blocks_per_sm) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
     if (filter_blocks_per_sm) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(filter_blocks_per_sm, blocks_filter_kernel, kComputeThreads, filter_smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(filter_blocks_per_sm, blocks_filter_kernel, kComputeThreads + 32, filter_smem);
         if (e != cudaSuccess) return e;
     }
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(emit_blocks_per_sm, blocks_emit_kernel<true>, kComputeThreads, emit_smem);
@@ -183,7 +185,7 @@ cudaError_t launch_blocks_filter(const ScanPlan& plan, uint32_t* bitmapB, uint32
                                  ScanCtrl* ctrl, long long nblocks, int grid, size_t dyn_smem, cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    blocks_filter_kernel<<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks);
+    blocks_filter_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks);
     return cudaGetLastError();
 }
 cudaError_t launch_blocks_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* cnts, const unsigned long long* tile_off,

@@ -26,7 +26,8 @@ cudaError_t emit_stream_occupancy(size_t dyn_smem, int* blocks_per_sm);
 cudaError_t launch_emit_stream(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* span_cnt, const uint32_t* tile_cnt,
                                const unsigned long long* tile_off, long long nsub, int ring, int stage_bytes, int dense_mode, int grid,
                                size_t dyn_smem, ScanCtrl* ctrl, bool pdl, cudaStream_t stream);
-size_t blocks_multi_smem_bytes(int npfor, int words_cap);
+size_t blocks_filter_smem_bytes(int nstaged, int tile_cap_bytes, int ring);
+int blocks_filter_slot_bytes(int nstaged, int tile_cap_bytes);
 size_t blocks_emit_smem_bytes(int npfor, int words_cap);
 cudaError_t blocks_multi_occupancy(size_t filter_smem, size_t emit_smem, int* filter_blocks_per_sm, int* emit_blocks_per_sm);
 cudaError_t launch_blocks_filter(const ScanPlan& plan, uint32_t* bitmapB, uint32_t* blk_cnt, uint32_t* tile_cnt, unsigned long long* tile_off,

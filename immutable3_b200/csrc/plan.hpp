@@ -78,6 +78,8 @@ struct ScanPlan {
     int32_t max_block_rows;  // block mode: rows of the largest block (shared-memory sizing)
     int32_t lit_bytes;       // bytes of `lits` in use
     int32_t blk_words_cap;   // block-mode multi-pass: 32-bit words of the largest encoded PFOR block (+ slack), per-warp scratch
+    int32_t blk_tile_bytes;  // blocks_filter_kernel: bytes reserved per staged encoded column in a ring slot (largest 8-block tile)
+    uint32_t pfor_filter_mask;  // blocks_filter_kernel: PFOR slots that carry a predicate (their tiles are staged)
     int32_t words_per_lane;  // multi-pass filter kernel: W (tile = 8192 * W rows)
     int32_t subtiles;        // fused dense kernel: NS (tile = NS sub-tiles of 8192 rows)
     int32_t proj_stage_bytes;  // fused dense kernel: one 1024-row span of every projected column (0 = never staged)

@@ -18,6 +18,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cerrno>
 #include <cstring>
 
@@ -223,6 +224,12 @@ static int load_table(const std::string& data_dir, const std::string& dir_name, 
         col.max_block_words = 0;
         for (size_t b = 0; b + 1 < col.word_off.size(); b++)
             col.max_block_words = std::max<int64_t>(col.max_block_words, (int64_t)col.word_off[b + 1] - (int64_t)col.word_off[b]);
+        col.max_tile_bytes = 0;
+        const size_t nb = col.word_off.size() - 1;
+        for (size_t b = 0; b < nb; b += 8) {
+            const uint64_t w0 = col.word_off[b] & ~3u, w8 = col.word_off[std::min(b + 8, nb)];
+            col.max_tile_bytes = std::max<int64_t>(col.max_tile_bytes, (int64_t)(((w8 - w0) * 4 + 15) & ~15ull));
+        }
         if (base / 4 > 0xFFFFFFFFll) return fail(IMM3_ERR_UNSUPPORTED, "PFOR_INT column %s exceeds 16 GiB per GPU", col.meta.name.c_str());
     }
     return 0;

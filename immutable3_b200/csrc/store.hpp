@@ -20,6 +20,7 @@ struct ColumnStore {
     std::vector<uint32_t> word_off;  // PFOR_INT: nblocks+1 offsets in 32-bit words into the arena
     uint32_t* d_word_off = nullptr;
     int64_t max_block_words = 0;     // PFOR_INT: largest encoded block, in 32-bit words
+    int64_t max_tile_bytes = 0;      // PFOR_INT: largest 8-block tile as the filter kernel stages it (16-byte aligned start and size)
 };
 
 struct TableStore {

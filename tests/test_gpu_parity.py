@@ -523,3 +523,64 @@ def test_random_tables_and_queries(tmp_path_factory, seed):
                         for c in range(len(proj)):
                             assert np.array_equal(got.column(c), exp.columns[c]), (seed, path, sel, proj[c], limit)
     os.environ.pop("IMM3_PATH", None)
+
+
+def _shape_ids(shape, n, rng):
+    """int32 id columns that walk the sorted-integer codec's block shapes (widths, raw mini-blocks, wrap-around)."""
+    kind, arg = shape
+    if kind == "const":      # constant delta: every mini-block has the same width
+        start, d = arg
+        v = start + d * np.arange(n, dtype=np.int64)
+    elif kind == "bits":     # random deltas below 2^b (cumulative sum wraps mod 2^32 for large b)
+        v = np.cumsum(rng.integers(0, 1 << arg, size=n, dtype=np.int64)) + int(rng.integers(-2**31, 2**31))
+    elif kind == "mixed":    # mostly width 1-2, a few wide jumps, a few repeats, a run of unsorted values (raw mini-blocks)
+        d = rng.choice([0, 1, 1, 1, 2, 3, 1 << arg], size=n, p=[0.1, 0.3, 0.2, 0.2, 0.1, 0.09, 0.01]).astype(np.int64)
+        v = np.cumsum(d) - 2**31 + 17
+        if n > 300:
+            a = int(rng.integers(0, n - 200))
+            v[a:a + 150] = rng.integers(-2**31, 2**31, size=150)
+    else:                    # unsorted: every mini-block raw
+        v = rng.integers(-2**31, 2**31, size=n, dtype=np.int64)
+    return ((v + 2**31) % 2**32 - 2**31).astype(np.int32)
+
+
+SHAPES = [("const", (0, 0)), ("const", (5, 1)), ("const", (-2**31, 2)), ("const", (7, 3)), ("const", (100, 15)), ("const", (0, 16)),
+          ("const", (-1000, 255)), ("const", (3, 256)), ("const", (2**31 - 70_000 * 4 - 2, 4)), ("const", (0, 65535)), ("const", (-2**31, 30000)),
+          ("bits", 1), ("bits", 2), ("bits", 3), ("bits", 4), ("bits", 7), ("bits", 8), ("bits", 9), ("bits", 13), ("bits", 16), ("bits", 20),
+          ("bits", 26), ("bits", 27), ("bits", 30), ("mixed", 10), ("mixed", 24), ("mixed", 29), ("random", 0)]
+
+
+@pytest.mark.parametrize("block", [1024, 1000, 160, 32])
+def test_sorted_int_codec_range_predicates_over_block_shapes(tmp_path_factory, block):
+    """The filter kernel of the sorted-integer codec classifies whole mini-blocks from their packed words (k_blocks_filter.cuh):
+    every width class, raw mini-blocks, wrap-around past 2^31 / 2^32, window edges on and next to mini-block boundaries."""
+    from immutable3_b200.loader import SegmentWriter
+
+    d = tmp_path_factory.mktemp(f"shapes{block}")
+    rng = np.random.default_rng(block)
+    n = 70_000 if block >= 1000 else 9_000
+    cols = {}
+    for i, shape in enumerate(SHAPES):
+        ids = _shape_ids(shape, n, rng)
+        ages = rng.integers(0, 100, size=n).astype(np.int8)
+        with SegmentWriter(d, f"s{i}", ["id:PFOR_INT", "age:DENSE_TINYINT"], block, 11) as w:
+            w.append(ids, ages)
+        cols[f"s{i}"] = ids
+    os.environ.pop("IMM3_PATH", None)
+    with O.Oracle(d) as orc, SegmentManager(d) as sm:
+        eng = Engine(sm)
+        for name, ids in cols.items():
+            picks = [int(ids[int(j)]) for j in rng.integers(0, n, size=6)] + [int(ids[0]), int(ids[31]), int(ids[32]), int(ids[-1]), int(ids.min()), int(ids.max())]
+            sels = []
+            for a in picks[:6]:
+                b = picks[int(rng.integers(0, len(picks)))]
+                lo, hi = min(a, b), max(a, b)
+                sels += [conj(Select("id", GT(lo)), Select("id", LT(hi))), conj(Select("id", GT(lo - 1)), Select("id", LT(hi + 1)))]
+            sels += [Select("id", EQ(picks[1])), Select("id", GT(picks[8])), Select("id", LT(picks[7])), Select("id", GT(-3e9)), Select("id", LT(-3e9)),
+                     conj(Select("id", GT(picks[2])), Select("age", LT(50))), Select("id", EQ(int(ids.min()))), Select("id", GT(int(ids.max()) - 1))]
+            for sel in sels:
+                for limit in (0, 33):
+                    exp = orc.query(name, oracle_preds(sel), ["id"], limit=limit)
+                    with eng.execute(Query(name, sel, Project(["id"], limit))) as got:
+                        assert got.nrows == exp.nrows, (name, SHAPES[int(name[1:])], sel, limit, got.nrows, exp.nrows)
+                        assert np.array_equal(got.column(0), exp.columns[0]), (name, SHAPES[int(name[1:])], sel, limit)
