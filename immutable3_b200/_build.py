@@ -16,8 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libimm3gpu.so")
 
 SOURCES = ["meta.cpp", "writer.cpp", "plan.cpp", "sql.cpp", "store.cpp", "kernels.cu", "engine.cu", "encode.cu"]
-HEADERS = ["common.hpp", "json_min.hpp", "plan.hpp", "store.hpp", "kernels.hpp", "../../include/imm3.h",
-           "k_ptx.cuh", "k_rowspace.cuh", "k_fused.cuh", "k_blocks_single.cuh", "k_multipass.cuh", "k_blocks_multi.cuh"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".hpp", ".cuh", ".h"))) + ["../../include/imm3.h"]  # every header is a dependency
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -315,13 +315,13 @@ int upload_all(imm3_db* db) {
             col.arena_bytes = arena;
             CUDA_TRY(cudaMemsetAsync(col.d_arena + payload, 0, arena - payload, db->stream));  // zero padding up to a whole tile
             if (!dense) {
-                CUDA_TRY(cudaMalloc(&col.d_word_off, col.word_off.size() * sizeof(uint32_t) + 128));  // (+128: the filter kernel's TMA reads 12 entries per tile)
+                CUDA_TRY(cudaMalloc(&col.d_word_off, col.word_off.size() * sizeof(uint32_t) + 256));  // (+256: the filter kernels' TMA reads up to 36 entries per tile)
                 CUDA_TRY(cudaMemcpyAsync(col.d_word_off, col.word_off.data(), col.word_off.size() * sizeof(uint32_t),
                                          cudaMemcpyHostToDevice, db->stream));
             }
             cut_pieces(col, &pieces);
         }
-        CUDA_TRY(cudaMalloc(&t.d_row_start, t.row_start.size() * sizeof(uint64_t) + 128));  // (+128: ... and 10 row ordinals)
+        CUDA_TRY(cudaMalloc(&t.d_row_start, t.row_start.size() * sizeof(uint64_t) + 512));  // (+512: ... and up to 34 row ordinals)
         CUDA_TRY(cudaMemcpyAsync(t.d_row_start, t.row_start.data(), t.row_start.size() * sizeof(uint64_t),
                                  cudaMemcpyHostToDevice, db->stream));
     }
@@ -383,6 +383,7 @@ struct Prepared {
     bool multipass = false;   // dense tables: filter -> scan -> emit kernels instead of the fused single pass
     bool blocks_multi = false;  // block mode: warp-per-block filter kernel -> offset scan -> emit kernel (no look-back chain)
     bool for_bitmap = false;    // imm3_filter_bitmap: the canonical-row bitmap comes from the single-pass kernels
+    bool quad = false;          // block mode: the single-range-predicate filter kernel (lane = block x super-block)
     bool hybrid = false;        // block mode, no predicate on an encoded column: DENSE filter kernel (row space) -> block emit kernel
     size_t blocks_emit_smem = 0;
     int64_t prefix_blocks = 0;  // small LIMIT on a block table: the pipeline first runs over this many leading blocks (0 = no prefix)
@@ -586,9 +587,25 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
             sp.stages = ring;  // (the row-space variant below re-plans these two for the dense filter kernel)
             sp.stage_bytes = slot_bytes;
             pr->dyn_smem = blocks_filter_smem_bytes(nstaged, sp.blk_tile_bytes, ring);
+            // The only predicate is a range on one encoded column (C4): the quad kernel - lane = (block, super-block), CTA tile
+            // of 32 blocks - if such a tile of this column fits a ring slot (i.e. the column actually compresses).
+            pr->quad = false;
+            if (sp.nfilter == 1 && sp.filter[0].pfor_slot >= 0 && sp.filter[0].kind == kFilterI32Range && !getenv("IMM3_NO_QUAD")) {
+                const int64_t cap32 = (t.cols[(size_t)pfor_cols[(size_t)sp.filter[0].pfor_slot]].max_tile32_bytes + 16 + 15) & ~15ll;
+                const int qslot = blocks_filter_quad_slot_bytes((int)cap32);
+                if (qslot <= 40 * 1024) {
+                    pr->quad = true;
+                    int qring = std::max(2, std::min(4, (40 * 1024) / qslot));
+                    if (const char* e = getenv("IMM3_BLOCKS_STAGES")) qring = std::max(2, std::min(kMaxFilterStages, atoi(e)));
+                    sp.blk_tile_bytes = (int)cap32;
+                    sp.stages = qring;
+                    sp.stage_bytes = qslot;
+                    pr->dyn_smem = (size_t)qring * (size_t)qslot;
+                }
+            }
             pr->blocks_emit_smem = blocks_emit_smem_bytes(sp.npfor, sp.blk_words_cap);
             int occ_e = 0;
-            CUDA_TRY(blocks_multi_occupancy(pr->dyn_smem, pr->blocks_emit_smem, pr->hybrid ? nullptr : &occ, &occ_e));
+            CUDA_TRY(blocks_multi_occupancy(pr->dyn_smem, pr->blocks_emit_smem, pr->hybrid ? nullptr : &occ, &occ_e, pr->quad));
             if (occ_e < 1) return fail(IMM3_ERR_CUDA, "block emit kernel does not fit on an SM (dynamic shared memory %zu bytes)", pr->blocks_emit_smem);
             pr->grid_blocks_emit = (int)std::max<int64_t>(1, std::min<int64_t>((t.nblocks + 7) / 8, (int64_t)db->num_sms * std::max(1, occ_e)));
             if (pr->hybrid) {
@@ -777,7 +794,8 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         if ((rc = ensure_buf(&db->d_tile_off, ntiles_pad * 8))) return rc;
         CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
         CUDA_TRY(launch_blocks_filter(pr->sp, (uint32_t*)db->d_bitmap.p, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
-                                      (unsigned long long*)db->d_tile_off.p, db->d_ctrl, nblocks, pr->grid, pr->dyn_smem, db->stream));
+                                      (unsigned long long*)db->d_tile_off.p, db->d_ctrl, nblocks,
+                                      pr->quad ? (int)std::max<int64_t>(1, std::min<int64_t>(pr->grid, (nblocks + 31) / 32)) : pr->grid, pr->dyn_smem, pr->quad, db->stream));
         *launches = 1;
         const bool pdl = pr->sp.nproj > 0 && !getenv("IMM3_NO_PDL");
         if (!pdl) {

@@ -407,3 +407,362 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) blocks_filter_kernel(
         scan_tile_counts(S, tile_cnt, tile_off, ntiles, P.limit, ctrl);
     }
 }
+
+// =============================================================================================
+// blocks_filter_quad_kernel: the same decision procedure, mapped  lane = (block g of 4, super-block s of 8).
+//
+// A query whose only predicate is a range on ONE encoded column (C4) spends most of blocks_filter_kernel's ~350
+// warp-instructions per block on work that is uniform across the warp (header walk, votes, scans, bookkeeping).  Here a warp
+// takes FOUR blocks at a time: lane (g, s) owns super-block s (128 values = 4 mini-blocks) of block g, so every uniform step
+// serves four blocks, each lane reads its own super-block header (no broadcast), the carry chain is a 3-step scan over 8
+// lanes, and a lane leaves with four selection words = one 16-byte store.  Mini-blocks whose width is not 0/1/2/4/8 (the
+// first one of every block of a sorted column: its first delta is the block's absolute start value) are summed by the 8
+// lanes of their block together, 4 fields each; straddling / raw / possibly-wrapping mini-blocks are unpacked by the
+// whole warp (rare).  A quad in which any block is irregular (rows not a multiple of 128: the 1-row tail block of a
+// segment, odd block sizes) or whose header speculation fails is handed, block by block, to pfor_range_word above.
+// CTA tile = 32 blocks (8 warps x 4); the 8-block tile counts of the offset scan are summed by warp pairs in shared memory.
+// =============================================================================================
+#ifndef IMM3_QUAD_MIN_BLOCKS
+#define IMM3_QUAD_MIN_BLOCKS 4
+#endif
+constexpr int kQuadTileBlocks = 4 * kComputeWarps;           // blocks per CTA tile
+constexpr int kQuadHdrBytes = 272 + 16 + 144 + 16;           // 34 row ordinals, 36 word offsets (both padded to 16 bytes)
+constexpr int kQuadWoOff = 288;
+
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
+// Selection words of lane (g, s): word[q] = rows of mini-block 4s+q of block g.  wa: shared address of the block's word 0,
+// nw: its words without the pad, nsuper: its super-blocks (rows / 128, >= 1).  Returns false (nothing decided) if the
+// header speculation fails in any of the four blocks.
+__device__ __forceinline__ uint32_t widths_before(int q) { return q == 0 ? 0u : (0x01010100u << (8 * (3 - q))); }  // IDP4A selector: widths of the mini-blocks ahead of q
+
+__device__ __forceinline__ bool pfor_range_quad(uint32_t wa, int nw, int nsuper, uint32_t lo, uint32_t span, int lane, uint32_t (&word)[4]) {
+    const int s = lane & 7;
+    // ---------------- headers: lane s reads header s where it sits if super-blocks 1 .. s-1 have the shape of super-block 1 ----------------
+    const uint32_t h0 = bswap32(lds32(wa + 4u));
+    const int p1 = 2 + (int)__dp4a(h0, 0x01010101u, 0u);
+    const uint32_t h1 = bswap32(lds32(wa + 4u * (uint32_t)(p1 < nw ? p1 : nw)));
+    const int S1 = (int)__dp4a(h1, 0x01010101u, 0u);
+    int ps = s == 0 ? 1 : p1 + (s - 1) * (1 + S1);
+    const bool inside = ps < nw;
+    ps = inside ? ps : nw;
+    uint32_t hs = bswap32(lds32(wa + 4u * (uint32_t)ps));
+    const int Ss = (int)__dp4a(hs, 0x01010101u, 0u);
+    if (!__all_sync(0xFFFFFFFFu, s >= nsuper || (inside && (s == 0 || s == nsuper - 1 || Ss == S1)))) return false;
+    const bool active = s < nsuper;
+    if (!active) hs = 0;  // (lanes past the block's last super-block: no widths, no rows)
+    // ---------------- d0 / rest of the lane's four mini-blocks.  Widths 0 and 1 - a sorted, dense column - inline and branch-free ----------------
+    uint32_t d0[4], rest[4];
+    unsigned slow = 0;
+    {
+        uint32_t a = wa + 4u * (uint32_t)(ps + 1);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t b = (hs >> (24 - 8 * q)) & 0xFFu;
+            const uint32_t w = lds32(a);  // (read even when unused: the address stays inside the staged tile)
+            const bool one = b == 1u;
+            d0[q] = one ? ((w >> 24) & 1u) : 0u;
+            rest[q] = one ? (uint32_t)__popc(w) - d0[q] : 0u;
+            if (b > 1u) slow |= 1u << q;
+            a += 4u * b;
+        }
+    }
+    // ---------------- any other width: per lane (2, 4, 8: SWAR; 32: raw) or left to the block's 8 lanes together ----------------
+    unsigned rawm = 0, pend = 0, unsafe = 0;  // bit q: raw (d0 = last value) / needs the cooperative sum / sum may not fit 32 bits
+    while (slow) {
+        const int q = __ffs((int)slow) - 1;
+        slow &= slow - 1u;
+        const int b = (int)((hs >> (24 - 8 * q)) & 0xFFu);
+        if (b > 8 && b < 32) { pend |= 1u << q; continue; }
+        const uint32_t a = wa + 4u * (uint32_t)(ps + 1 + (int)__dp4a(hs, widths_before(q), 0u));
+        uint32_t x0 = 0, xr = 0;
+        if (b >= 32) {
+            x0 = bswap32(lds32(a + 4u * 31u));
+            rawm |= 1u << q;
+        } else if (b == 2) {  // fields of width 2, 4, 8 never straddle a byte: no byte swap needed for sums
+            const uint32_t w0 = lds32(a), w1 = lds32(a + 4u);
+            x0 = (w0 >> 24) & 3u;
+            xr = (uint32_t)(__popc(w0 & 0x55555555u) + __popc(w1 & 0x55555555u)) + 2u * (uint32_t)(__popc(w0 & 0xAAAAAAAAu) + __popc(w1 & 0xAAAAAAAAu)) - x0;
+        } else if (b == 4) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t w = lds32(a + 4u * i);
+                acc = __dp4a((w & 0x0F0F0F0Fu) + ((w >> 4) & 0x0F0F0F0Fu), 0x01010101u, acc);
+            }
+            x0 = (lds32(a) >> 24) & 15u;
+            xr = acc - x0;
+        } else if (b == 8) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc = __dp4a(lds32(a + 4u * i), 0x01010101u, acc);
+            x0 = lds32(a) >> 24;
+            xr = acc - x0;
+        } else {
+            pend |= 1u << q;  // 3, 5, 6, 7
+            continue;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k == q) { d0[k] = x0; rest[k] = xr; }
+    }
+    // ---------------- the 8 lanes of a block sum one such mini-block together, 4 fields each ----------------
+    const unsigned gmask = 0xFFu << (lane & 24);
+    for (;;) {
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, pend != 0u);
+        if (!bal) break;
+        const unsigned mine = bal & gmask;
+        const int m = mine ? __ffs((int)mine) - 1 : lane;  // the lane of this block that is served in this round
+        const int myq = pend ? __ffs((int)pend) - 1 : 0;   // every lane offers its lowest pending mini-block
+        const int ob = (int)((hs >> (24 - 8 * myq)) & 0xFFu), op = ps + 1 + (int)__dp4a(hs, widths_before(myq), 0u);
+        const int bm = __shfl_sync(0xFFFFFFFFu, ob, m), pm = __shfl_sync(0xFFFFFFFFu, op, m);
+        uint32_t sum = 0, f0 = 0;
+        bool big = false;
+        if (mine) {
+            const uint32_t mask = (1u << bm) - 1u;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t off = (uint32_t)((4 * s + i) * bm);
+                const uint32_t a = wa + 4u * ((uint32_t)pm + (off >> 5));
+                const uint32_t f = __funnelshift_r(bswap32(lds32(a)), bswap32(lds32(a + 4u)), off) & mask;
+                if (i == 0) f0 = f;
+                if (i == 0 && s == 0) continue;  // the first delta is not part of `rest`
+                sum += f;
+                big = big || f >= (1u << 26);
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+        f0 = __shfl_sync(0xFFFFFFFFu, f0, lane & 24);  // field 0 sits in the block's first lane
+        const unsigned bigs = __ballot_sync(0xFFFFFFFFu, big) & gmask;
+        if (mine && lane == m) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (k == myq) { d0[k] = f0; rest[k] = sum; }
+            if (bigs) unsafe |= 1u << myq;
+            pend &= pend - 1u;
+        }
+    }
+    // ---------------- carry chain: within the lane, then a segmented scan over the 8 lanes of the block ----------------
+    uint32_t c = 0;
+    unsigned absf = 0;  // the lane's span contains a raw mini-block: its outgoing carry does not depend on the incoming one
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const bool r = (rawm >> q) & 1u;
+        c = r ? d0[q] : c + d0[q] + rest[q];
+        absf |= r ? 1u : 0u;
+    }
+    if (__any_sync(0xFFFFFFFFu, rawm != 0u)) {
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const uint32_t pc = __shfl_up_sync(0xFFFFFFFFu, c, o, 8);
+            const unsigned pa = __shfl_up_sync(0xFFFFFFFFu, absf, o, 8);
+            if (s >= o) {
+                if (!absf) c += pc;
+                absf |= pa;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const uint32_t pc = __shfl_up_sync(0xFFFFFFFFu, c, o, 8);
+            if (s >= o) c += pc;
+        }
+    }
+    uint32_t base = __shfl_up_sync(0xFFFFFFFFu, c, 1, 8);
+    if (s == 0) base = 0;  // initvalue = 0 at every block
+    // ---------------- classify (branch-free): all rows / no row / has to be unpacked ----------------
+    unsigned need = 0;
+    const unsigned hard = rawm | unsafe;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t uf = base + d0[q] - lo, ul = uf + rest[q];  // first / last value of the run in the window's frame
+        const bool mono = ul >= uf && !((hard >> q) & 1u);         // (no wrap past 2^32 in that frame)
+        const bool all = mono && ul <= span, none = mono && uf > span;
+        word[q] = all ? 0xFFFFFFFFu : 0u;
+        if (!all && !none) need |= 1u << q;
+        base = ((rawm >> q) & 1u) ? d0[q] : base + d0[q] + rest[q];
+    }
+    if (!active) {
+        need = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) word[q] = 0;
+    }
+    // ---------------- the few mini-blocks that have to be unpacked: the whole warp, a value per lane ----------------
+    for (;;) {
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, need != 0u);
+        if (!bal) break;
+        const int m = __ffs((int)bal) - 1;
+        const int myq = need ? __ffs((int)need) - 1 : 0;
+        const int ob = (int)((hs >> (24 - 8 * myq)) & 0xFFu), op = ps + 1 + (int)__dp4a(hs, widths_before(myq), 0u);
+        // carry handed to mini-block myq: the lane's incoming carry plus its earlier mini-blocks (a raw one restarts the chain)
+        uint32_t ocarry = __shfl_up_sync(0xFFFFFFFFu, c, 1, 8);
+        if (s == 0) ocarry = 0;
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+            if (q < myq) ocarry = ((rawm >> q) & 1u) ? d0[q] : ocarry + d0[q] + rest[q];
+        const int bm = __shfl_sync(0xFFFFFFFFu, ob, m), pm = __shfl_sync(0xFFFFFFFFu, op, m);
+        const uint32_t cm = __shfl_sync(0xFFFFFFFFu, ocarry, m), wam = __shfl_sync(0xFFFFFFFFu, wa, m);
+        uint32_t val;
+        if (bm >= 32) {
+            val = bswap32(lds32(wam + 4u * (uint32_t)(pm + lane)));
+        } else {
+            const uint32_t off = (uint32_t)(lane * bm);
+            const uint32_t a = wam + 4u * ((uint32_t)pm + (off >> 5));
+            val = __funnelshift_r(bswap32(lds32(a)), bswap32(lds32(a + 4u)), off) & ((1u << bm) - 1u);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, val, o);
+                if (lane >= o) val += t;
+            }
+            val += cm;
+        }
+        const uint32_t wd = __ballot_sync(0xFFFFFFFFu, (val - lo) <= span);
+        if (lane == m) {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (q == myq) word[q] = wd;
+            need &= need - 1u;
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(kComputeThreads + 32, IMM3_QUAD_MIN_BLOCKS) blocks_filter_quad_kernel(const __grid_constant__ ScanPlan P, uint32_t* __restrict__ bitmapB,
+                                                                                       uint32_t* __restrict__ blk_cnt, uint32_t* __restrict__ tile_cnt,
+                                                                                       unsigned long long* __restrict__ tile_off, ScanCtrl* ctrl,
+                                                                                       long long nblocks) {
+    __shared__ FilterShared S;
+    __shared__ uint32_t s_base[kMaxFilterStages];       // per ring slot: arena word that sits at the slot's data offset
+    __shared__ unsigned int s_tacc[kMaxFilterStages][4];  // per ring slot: the four 8-block tile counts ([31:20] warps arrived)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ring = P.stages;
+    if (tid == 0) {
+        for (int s = 0; s < kMaxFilterStages; s++) {
+            mbar_init(smem_u32(&S.mbar_full[s]), 1);
+            mbar_init(smem_u32(&S.mbar_empty[s]), kComputeWarps);
+            for (int k = 0; k < 4; k++) s_tacc[s][k] = 0;
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const long long ntiles8 = P.ntiles;                                         // 8-block tiles (offset scan, emit kernel)
+    const long long nct = (nblocks + kQuadTileBlocks - 1) / kQuadTileBlocks;     // CTA tiles of 32 blocks
+    const int slot_bytes = P.stage_bytes;
+    const FilterCol f0 = P.filter[0];
+    const PforCol pc = P.pfor[f0.pfor_slot < 0 ? 0 : (f0.pfor_slot == 0 ? 0 : (f0.pfor_slot == 1 ? 1 : (f0.pfor_slot == 2 ? 2 : 3)))];
+    const uint32_t ring_addr = smem_u32(dyn_smem);
+
+    if (warp == kComputeWarps) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            RingPos rp;
+            for (long long ct = blockIdx.x;; ct += gridDim.x, rp.advance(ring)) {
+                const int slot = rp.slot;
+                if (rp.use > 0) mbar_wait(smem_u32(&S.mbar_empty[slot]), (rp.use - 1) & 1u, nullptr);
+                const uint32_t bar = smem_u32(&S.mbar_full[slot]);
+                if (ct >= nct) {
+                    S.tile_id[slot] = kNoMoreTiles;
+                    mbar_arrive(bar);
+                    break;
+                }
+                S.tile_id[slot] = (unsigned)ct;
+                const uint32_t dst = ring_addr + (uint32_t)slot * (uint32_t)slot_bytes;
+                const long long b0 = ct * kQuadTileBlocks;
+                const long long b1 = b0 + kQuadTileBlocks < nblocks ? b0 + kQuadTileBlocks : nblocks;
+                const uint32_t wo0 = __ldg(pc.word_off + b0), wo1 = __ldg(pc.word_off + b1);
+                const uint32_t base_w = wo0 & ~3u;  // 16-byte aligned source
+                uint32_t nb = ((wo1 - base_w) * 4u + 15u) & ~15u;
+                if (nb > (uint32_t)P.blk_tile_bytes) nb = (uint32_t)P.blk_tile_bytes;
+                s_base[slot] = base_w;
+                mbar_arrive_expect_tx(bar, 272u + 144u + nb);
+                tma_load_1d(dst, P.row_start + b0, 272u, bar);
+                tma_load_1d(dst + (uint32_t)kQuadWoOff, pc.word_off + b0, 144u, bar);
+                tma_load_1d(dst + (uint32_t)kQuadHdrBytes, pc.words + base_w, nb, bar);
+            }
+        }
+    } else {
+        // ---------------- compute warps: warp w = blocks 32 * ct + 4 w .. + 3 ----------------
+        const int g = lane >> 3, s = lane & 7;
+        const uint32_t lo = (uint32_t)f0.lo, span = f0.span;
+        for (RingPos rp;; rp.advance(ring)) {
+            const int slot = rp.slot;
+            mbar_wait(smem_u32(&S.mbar_full[slot]), rp.use & 1u, nullptr);
+            const unsigned ct_u = S.tile_id[slot];
+            if (ct_u == kNoMoreTiles) break;
+            const long long blk0 = (long long)ct_u * kQuadTileBlocks + 4 * warp;  // first block of this warp's quad
+            const uint32_t sl = ring_addr + (uint32_t)slot * (uint32_t)slot_bytes;
+            const int bi = 4 * warp + g;                                          // my block inside the CTA tile
+            const long long blk = blk0 + g;
+            const bool exists = blk < nblocks;
+            int n = 0, nw = 0;
+            uint32_t wa = sl + (uint32_t)kQuadHdrBytes;
+            if (exists) {
+                const unsigned long long r0 = lds_cell<unsigned long long>(sl + 8u * (uint32_t)bi), r1 = lds_cell<unsigned long long>(sl + 8u * (uint32_t)bi + 8u);
+                const uint32_t w0 = lds32(sl + (uint32_t)kQuadWoOff + 4u * (uint32_t)bi), w1 = lds32(sl + (uint32_t)kQuadWoOff + 4u * (uint32_t)bi + 4u);
+                n = (int)(r1 - r0);
+                nw = (int)(w1 - w0) - 2;
+                wa += 4u * (w0 - s_base[slot]);
+            }
+            unsigned quad_cnt = 0;  // rows selected in the quad (lane 0)
+            uint32_t word[4];
+            bool fast = __all_sync(0xFFFFFFFFu, exists && n > 0 && (n & 127) == 0);
+            if (fast) fast = pfor_range_quad(wa, nw, n >> 7, lo, span, lane, word);
+            if (fast) {
+                unsigned c = (unsigned)(__popc(word[0]) + __popc(word[1]) + __popc(word[2]) + __popc(word[3]));
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);  // rows selected in my block
+                if (c != 0u && c != (unsigned)n)  // (lanes past the block's last super-block write zeros: the emit kernel reads all 32 words)
+                    *reinterpret_cast<uint4*>(bitmapB + blk * 32 + 4 * s) = make_uint4(word[0], word[1], word[2], word[3]);
+                if (s == 0) blk_cnt[blk] = c;
+                quad_cnt = c + __shfl_xor_sync(0xFFFFFFFFu, c, 8);
+                quad_cnt += __shfl_xor_sync(0xFFFFFFFFu, quad_cnt, 16);
+            } else {
+                // irregular quad: block by block, lane m = mini-block m (pfor_range_word)
+#pragma unroll 1
+                for (int k = 0; k < 4; k++) {
+                    const int nk = __shfl_sync(0xFFFFFFFFu, n, 8 * k), nwk = __shfl_sync(0xFFFFFFFFu, nw, 8 * k);
+                    const uint32_t wak = __shfl_sync(0xFFFFFFFFu, wa, 8 * k);
+                    if (blk0 + k >= nblocks) break;
+                    const uint32_t* W = reinterpret_cast<const uint32_t*>(dyn_smem + (wak - ring_addr));
+                    const int left = nk - lane * 32;
+                    uint32_t mw = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+                    mw &= pfor_range_word(W, nwk, nk, lo, span, lane);
+                    const unsigned c = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(mw));
+                    if (c != 0u && c != (unsigned)nk) bitmapB[(blk0 + k) * 32 + lane] = mw;
+                    if (lane == 0) blk_cnt[blk0 + k] = c;
+                    quad_cnt += c;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                // 8-block tile = this warp's quad + its neighbour's: the second arrival publishes and clears
+                const long long t8 = blk0 >> 3;
+                const unsigned old = atomicAdd(&s_tacc[slot][warp >> 1], quad_cnt + (1u << 20));
+                if ((old >> 20) == 1u) {
+                    if (t8 < ntiles8) tile_cnt[t8] = (old & 0xFFFFFu) + quad_cnt;
+                    s_tacc[slot][warp >> 1] = 0;
+                }
+                mbar_arrive(smem_u32(&S.mbar_empty[slot]));
+            }
+        }
+    }
+
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(&ctrl->exited, 1u);
+        S.is_last = prev == gridDim.x - 1;
+        if (S.is_last) ctrl->exited = 0;
+    }
+    __syncthreads();
+    if (S.is_last && warp < kComputeWarps) {
+        __threadfence();
+        scan_tile_counts(S, tile_cnt, tile_off, ntiles8, P.limit, ctrl);
+    }
+}

@@ -230,6 +230,11 @@ static int load_table(const std::string& data_dir, const std::string& dir_name, 
             const uint64_t w0 = col.word_off[b] & ~3u, w8 = col.word_off[std::min(b + 8, nb)];
             col.max_tile_bytes = std::max<int64_t>(col.max_tile_bytes, (int64_t)(((w8 - w0) * 4 + 15) & ~15ull));
         }
+        col.max_tile32_bytes = 0;
+        for (size_t b = 0; b < nb; b += 32) {
+            const uint64_t w0 = col.word_off[b] & ~3u, w1 = col.word_off[std::min(b + 32, nb)];
+            col.max_tile32_bytes = std::max<int64_t>(col.max_tile32_bytes, (int64_t)(((w1 - w0) * 4 + 15) & ~15ull));
+        }
         if (base / 4 > 0xFFFFFFFFll) return fail(IMM3_ERR_UNSUPPORTED, "PFOR_INT column %s exceeds 16 GiB per GPU", col.meta.name.c_str());
     }
     return 0;
