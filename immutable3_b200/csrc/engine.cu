@@ -130,6 +130,8 @@ struct imm3_db {
     BufPool dev_pool, host_pool;
     Buf d_bitmap, h_bitmap;
     Buf d_span_cnt, d_tile_cnt, d_tile_off;  // multi-pass pipeline scratch (grow-only)
+    Buf d_scan_part;                         // offset_scan_kernel: epoch-tagged chunk sums (zeroed when (re)allocated)
+    uint32_t scan_epoch = 0;
     Buf d_trace;                             // IMM3_TRACE debugging buffer
     // Emit-kernel feedback: result density class (1 dense, 0 sparse) last seen for a query shape (table, filter
     // columns and kinds, select list).  A known class launches only the matching emit kernel; both kernels are correct
@@ -360,6 +362,7 @@ void free_device_side(imm3_db* db) {
     if (db->d_tile_cnt.p) cudaFree(db->d_tile_cnt.p);
     if (db->d_tile_off.p) cudaFree(db->d_tile_off.p);
     if (db->d_trace.p) cudaFree(db->d_trace.p);
+    if (db->d_scan_part.p) cudaFree(db->d_scan_part.p);
     if (db->h_bitmap.p) cudaFreeHost(db->h_bitmap.p);
     if (db->d_status) cudaFree(db->d_status);
     if (db->d_ctrl) cudaFree(db->d_ctrl);
@@ -752,8 +755,35 @@ int exchange_only(imm3_db* db, int64_t limit, int has_count) {
     return 0;
 }
 
+// Who turns the tile counts into offsets: the filter kernel's last CTA (small tables), or offset_scan_kernel - one CTA per
+// 4096 counts, launched behind the filter kernel (large tables: 122 K counts at 1 B rows take one SM ~50 us).
+bool scan_inline_for(int64_t ntiles) {
+    if (const char* e = getenv("IMM3_SCAN")) {
+        if (!strcmp(e, "inline")) return true;
+        if (!strcmp(e, "kernel")) return false;
+    }
+    return ntiles <= scan_inline_max_tiles();
+}
+int launch_scan_kernel(imm3_db* db, const ScanPlan& sp, int64_t ntiles, int* launches) {
+    const size_t nchunks = (size_t)((ntiles + 4095) / 4096);
+    if (db->d_scan_part.cap < nchunks * 16) {
+        if (db->d_scan_part.p) cudaFree(db->d_scan_part.p);
+        db->d_scan_part = Buf();
+        const size_t cap = nchunks * 16 + 4096;
+        CUDA_TRY(cudaMalloc(&db->d_scan_part.p, cap));
+        CUDA_TRY(cudaMemsetAsync(db->d_scan_part.p, 0, cap, db->stream));
+        db->d_scan_part.cap = cap;
+    }
+    if (((++db->scan_epoch) & 0xFFFFFFu) == 0) ++db->scan_epoch;  // (tag 0 = never written)
+    CUDA_TRY(launch_offset_scan((const uint32_t*)db->d_tile_cnt.p, (unsigned long long*)db->d_tile_off.p, ntiles, sp.limit, db->scan_epoch,
+                                (unsigned long long*)db->d_scan_part.p, db->d_ctrl, db->stream));
+    (*launches)++;
+    return 0;
+}
+
 int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launches, double* stage_ms, int64_t nblocks_use, bool exchange) {
     bool have_mid = false;
+    pr->sp.scan_inline = 1;
     if (pr->block_mode && pr->hybrid) {
         // dense filter kernel over the row space -> block emit kernel (decodes only blocks with surviving rows)
         TableStore& t = *pr->table;
@@ -767,10 +797,12 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         const size_t ntiles_pad = ((size_t)ntiles + 4095) / 4096 * 4096 + 16;  // whole rounds of the offset scan
         if ((rc = ensure_buf(&db->d_tile_cnt, ntiles_pad * 4))) return rc;
         if ((rc = ensure_buf(&db->d_tile_off, ntiles_pad * 8))) return rc;
+        pr->sp.scan_inline = (pr->sp.nfilter == 0 || scan_inline_for(ntiles)) ? 1 : 0;
         CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
         CUDA_TRY(launch_filter(pr->sp, pr->sp.bitmap, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
                                (unsigned long long*)db->d_tile_off.p, db->d_ctrl, pr->grid, pr->dyn_smem, db->stream));
         *launches = 1;
+        if (!pr->sp.scan_inline && (rc = launch_scan_kernel(db, pr->sp, ntiles, launches))) return rc;
         const bool pdl = pr->sp.nproj > 0 && !getenv("IMM3_NO_PDL");  // (no event may sit between a kernel and its programmatic dependent)
         if (!pdl) {
             CUDA_TRY(cudaEventRecord(db->ev_mid, db->stream));
@@ -792,11 +824,13 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         const size_t ntiles_pad = ((size_t)ntiles + 4095) / 4096 * 4096 + 16;  // whole rounds of the offset scan
         if ((rc = ensure_buf(&db->d_tile_cnt, ntiles_pad * 4))) return rc;
         if ((rc = ensure_buf(&db->d_tile_off, ntiles_pad * 8))) return rc;
+        pr->sp.scan_inline = scan_inline_for(ntiles) ? 1 : 0;
         CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
         CUDA_TRY(launch_blocks_filter(pr->sp, (uint32_t*)db->d_bitmap.p, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
                                       (unsigned long long*)db->d_tile_off.p, db->d_ctrl, nblocks,
                                       pr->quad ? (int)std::max<int64_t>(1, std::min<int64_t>(pr->grid, (nblocks + 31) / 32)) : pr->grid, pr->dyn_smem, pr->quad, db->stream));
         *launches = 1;
+        if (!pr->sp.scan_inline && (rc = launch_scan_kernel(db, pr->sp, ntiles, launches))) return rc;
         const bool pdl = pr->sp.nproj > 0 && !getenv("IMM3_NO_PDL");
         if (!pdl) {
             CUDA_TRY(cudaEventRecord(db->ev_mid, db->stream));
@@ -843,10 +877,12 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         }
         const bool only_stream = stream_ok && hint == 1, only_gather = stream_ok && hint == 0;
         const bool pdl = pr->sp.nproj > 0 && !getenv("IMM3_NO_PDL");  // the first emit kernel launched is a programmatic dependent
+        pr->sp.scan_inline = (pr->sp.nfilter == 0 || scan_inline_for(nsub)) ? 1 : 0;
         CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
         CUDA_TRY(launch_filter(pr->sp, pr->sp.bitmap, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
                                (unsigned long long*)db->d_tile_off.p, db->d_ctrl, pr->grid, pr->dyn_smem, db->stream));
         *launches = 1;
+        if (!pr->sp.scan_inline && (rc = launch_scan_kernel(db, pr->sp, nsub, launches))) return rc;
         // The streaming emit kernel is launched as a programmatic dependent of the filter kernel (its prologue overlaps the
         // filter kernel's tail), so no event may sit between the two; IMM3_NO_PDL=1 restores per-stage timing.
         if (!pdl) {

@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) blocks_filter_kernel(
         if (S.is_last) ctrl->exited = 0;
     }
     __syncthreads();
-    if (S.is_last && warp < kComputeWarps) {
+    if (S.is_last && warp < kComputeWarps && P.scan_inline) {
         __threadfence();
         scan_tile_counts(S, tile_cnt, tile_off, ntiles, P.limit, ctrl);
     }
@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(kComputeThreads + 32, IMM3_QUAD_MIN_BLOCKS) bl
         if (S.is_last) ctrl->exited = 0;
     }
     __syncthreads();
-    if (S.is_last && warp < kComputeWarps) {
+    if (S.is_last && warp < kComputeWarps && P.scan_inline) {
         __threadfence();
         scan_tile_counts(S, tile_cnt, tile_off, ntiles8, P.limit, ctrl);
     }

@@ -115,6 +115,127 @@ __device__ void scan_tile_counts(FilterShared& S, const uint32_t* tile_cnt, unsi
     }
 }
 
+// The same exclusive scan as a kernel of its own, one CTA per 4096 counts: at 1 B rows there are 122 K tile counts and the
+// last CTA of the filter kernel needs ~50 us for them (30 serial rounds on one SM) - a quarter of a C4 query.  Here every
+// CTA scans one round's worth, publishes its sum as an epoch-tagged word and adds up the sums of the chunks before it
+// (chunks are handed out by an atomic ticket, so a CTA only ever waits for CTAs that are already running).  ~5 us.
+// Launched between the filter and the emit kernel as a programmatic dependent of the former when the table has more than
+// kScanInlineMaxTiles tiles; the CTA of the last chunk writes the total, the LIMIT clamp and the dense-tile row count.
+constexpr long long kScanInlineMaxTiles = 4 * kComputeThreads * 16;
+
+__global__ void __launch_bounds__(kComputeThreads) offset_scan_kernel(const uint32_t* __restrict__ tile_cnt, unsigned long long* __restrict__ tile_off,
+                                                                     long long ntiles, long long limit, uint32_t epoch,
+                                                                     unsigned long long* __restrict__ partials, ScanCtrl* ctrl) {
+    constexpr int kRound = kComputeThreads * 16;
+    __shared__ unsigned long long s_sum[kComputeWarps], s_dense[kComputeWarps], s_prev[kComputeWarps], s_prevd[kComputeWarps];
+    __shared__ unsigned int s_chunk;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the filter kernel's tile counts are final
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_chunk = atomicAdd(&ctrl->ticket, 1u);
+    __syncthreads();
+    const long long chunk = s_chunk, nchunks = (ntiles + kRound - 1) / kRound, base_i = chunk * kRound;
+    const int my0 = warp * 512 + lane * 2;  // (same pair layout as scan_tile_counts: every access of a warp is coalesced)
+    uint2 c[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) c[j] = ldcg_v2_here(tile_cnt + base_i + my0 + 64 * j);  // (the arrays are padded to whole rounds)
+    unsigned excl_pair[8], carry = 0, dsum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const long long i = base_i + my0 + 64 * j;
+        if (i >= ntiles) c[j].x = 0;
+        if (i + 1 >= ntiles) c[j].y = 0;
+        dsum += (c[j].x >= (unsigned)kDenseTileMinRows ? c[j].x : 0u) + (c[j].y >= (unsigned)kDenseTileMinRows ? c[j].y : 0u);
+        const unsigned ps = c[j].x + c[j].y;
+        unsigned incl = ps;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        excl_pair[j] = carry + incl - ps;
+        carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    dsum = __reduce_add_sync(0xFFFFFFFFu, dsum);
+    if (lane == 0) {
+        s_sum[warp] = carry;
+        s_dense[warp] = dsum;
+    }
+    __syncthreads();
+    unsigned long long wbase = 0, chunk_total = 0, chunk_dense = 0;
+#pragma unroll
+    for (int w = 0; w < kComputeWarps; w++) {
+        if (w < warp) wbase += s_sum[w];
+        chunk_total += s_sum[w];
+        chunk_dense += s_dense[w];
+    }
+    constexpr unsigned long long kVal = (1ull << 40) - 1ull;
+    const unsigned long long tag = (unsigned long long)(epoch & 0xFFFFFFu) << 40;
+    if (tid == 0) {
+        st_relaxed_u64(partials + 2 * chunk, tag | (chunk_total & kVal));
+        st_relaxed_u64(partials + 2 * chunk + 1, tag | (chunk_dense & kVal));
+    }
+    // sums of the chunks before this one (tickets: they are all running or done); the final chunk also needs their dense rows
+    const bool is_final = chunk == nchunks - 1;
+    unsigned long long prev = 0, prevd = 0;
+    for (int word = 0; word < (is_final ? 2 : 1); word++) {
+        for (long long p = tid; p < chunk; p += kComputeThreads) {
+            unsigned long long v = ld_relaxed_u64(partials + 2 * p + word);
+            if ((v >> 40) != (tag >> 40)) {
+                const uint64_t t0 = globaltimer_ns();
+                unsigned spins = 0;
+                while (((v = ld_relaxed_u64(partials + 2 * p + word)) >> 40) != (tag >> 40)) {
+                    __nanosleep(20);
+                    if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > kWatchdogNs) watchdog_trap(ctrl, 3);
+                }
+            }
+            if (word == 0) prev += v & kVal;
+            else prevd += v & kVal;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        prev += __shfl_xor_sync(0xFFFFFFFFu, prev, o);
+        prevd += __shfl_xor_sync(0xFFFFFFFFu, prevd, o);
+    }
+    if (lane == 0) {
+        s_prev[warp] = prev;
+        s_prevd[warp] = prevd;
+    }
+    __syncthreads();
+    unsigned long long base = 0, based = 0;
+#pragma unroll
+    for (int w = 0; w < kComputeWarps; w++) {
+        base += s_prev[w];
+        based += s_prevd[w];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const long long i = base_i + my0 + 64 * j;
+        if (i < ntiles) {
+            ulonglong2 o;
+            o.x = base + wbase + excl_pair[j];
+            o.y = o.x + c[j].x;
+            *reinterpret_cast<ulonglong2*>(tile_off + i) = o;
+        }
+    }
+    __syncthreads();
+    if (is_final && tid == 0) {
+        const unsigned long long total = base + chunk_total;
+        tile_off[ntiles] = total;
+        ctrl->total = total < (unsigned long long)limit ? total : (unsigned long long)limit;
+        ctrl->dense_rows = based + chunk_dense;
+    }
+    if (tid == 0) {
+        __threadfence();
+        const unsigned done = atomicAdd(&ctrl->exited, 1u);
+        if (done == gridDim.x - 1) {  // last CTA out: the counters are the next query's again
+            ctrl->exited = 0;
+            ctrl->ticket = 0;
+        }
+    }
+}
+
 // K1: tile = 8192 rows = 8 spans, one per compute warp.  A producer warp streams the tiles of this CTA (statically
 // strided: no ordering, no tickets) through a TMA ring `ring` tiles deep; the compute warps never synchronise with each
 // other - each evaluates the conjunction on its span, stores its bitmap word and span count, and adds the count to the
@@ -279,7 +400,7 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
         }
     }
     __syncthreads();
-    if (S.is_last && warp < kComputeWarps) {
+    if (S.is_last && warp < kComputeWarps && P.scan_inline) {  // (large tables: offset_scan_kernel takes over)
         __threadfence();
         if (tid == 0) phase_stamp(P, 2);
         scan_tile_counts(S, tile_cnt, tile_off, ntiles, P.limit, ctrl, kDenseTileRowsPerWord, ((P.debug & 16u) && P.trace) ? P.trace + 32 : nullptr);

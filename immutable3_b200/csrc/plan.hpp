@@ -79,6 +79,7 @@ struct ScanPlan {
     int32_t lit_bytes;       // bytes of `lits` in use
     int32_t blk_words_cap;   // block-mode multi-pass: 32-bit words of the largest encoded PFOR block (+ slack), per-warp scratch
     int32_t blk_tile_bytes;  // blocks_filter_kernel: bytes reserved per staged encoded column in a ring slot (largest 8-block tile)
+    int32_t scan_inline;     // 1: the filter kernel's last CTA turns the tile counts into offsets; 0: offset_scan_kernel does (large tables)
     uint32_t pfor_filter_mask;  // blocks_filter_kernel: PFOR slots that carry a predicate (their tiles are staged)
     int32_t words_per_lane;  // multi-pass filter kernel: W (tile = 8192 * W rows)
     int32_t subtiles;        // fused dense kernel: NS (tile = NS sub-tiles of 8192 rows)

@@ -584,3 +584,48 @@ def test_sorted_int_codec_range_predicates_over_block_shapes(tmp_path_factory, b
                     with eng.execute(Query(name, sel, Project(["id"], limit))) as got:
                         assert got.nrows == exp.nrows, (name, SHAPES[int(name[1:])], sel, limit, got.nrows, exp.nrows)
                         assert np.array_equal(got.column(0), exp.columns[0]), (name, SHAPES[int(name[1:])], sel, limit)
+
+
+def test_offset_scan_kernel_on_large_and_small_tables(tmp_path_factory, world, monkeypatch):
+    """Tables with more than 16 K tiles hand the tile-count scan to offset_scan_kernel (one CTA per 4096 counts, chained sums);
+    IMM3_SCAN=kernel forces it everywhere: multi-chunk dense and block tables, the small fixtures, LIMIT cuts."""
+    monkeypatch.setenv("IMM3_SCAN", "kernel")
+    os.environ.pop("IMM3_PATH", None)
+    d, tables, orc, sms = world
+    for table, sel, proj in [("t", conj(Select("age", GT(18)), Select("age", LT(30))), ["id", "age"]), ("t", NoSelect, ["id"]),
+                             ("p", conj(Select("id", GT(2000)), Select("id", LT(900000))), ["id", "age"]), ("p", Select("age", LT(10)), ["id"]),
+                             ("wide", Select("name", Match(["carol"])), ["id", "name", "zip"]), ("one", NoSelect, ["id"])]:
+        for limit in (0, 1, 100, 5000):
+            check(orc, sms["auto"], table, sel, proj, limit, "auto")
+    # 40 M rows: 4883 dense tiles -> 2 chunks; checked with numpy from the files
+    d2 = tmp_path_factory.mktemp("scan")
+    n = 40_000_000
+    synth_write(d2, "syn", n)
+    order = sorted(range(40), key=lambda i: f"id_{i}.dat")
+    age = np.concatenate([np.fromfile(d2 / "syn" / f"age_{i}.dat", np.int8) for i in order])
+    ids = np.concatenate([np.fromfile(d2 / "syn" / f"id_{i}.dat", "<i4") for i in order])
+    # a block table with small blocks: 3 M rows in blocks of 32 -> 11.7 K tiles of 8 blocks -> 3 chunks
+    rng = np.random.default_rng(5)
+    nb = 3_000_000
+    bid = np.cumsum(rng.integers(0, 4, size=nb)).astype(np.int32)
+    bage = rng.integers(0, 100, size=nb).astype(np.int8)
+    from immutable3_b200.loader import SegmentWriter
+    with SegmentWriter(d2, "b32", ["id:PFOR_INT", "age:DENSE_TINYINT"], 32, 1000) as w:
+        w.append(bid, bage)
+    border = np.concatenate([np.arange(i * 32001, min(nb, (i + 1) * 32001)) for i in sorted(range((nb + 32000) // 32001), key=lambda i: f"id_{i}.dat")])
+    with SegmentManager(d2) as sm:
+        eng = Engine(sm)
+        for lim in (0, 1000, 3_000_000):
+            m = (age > 18) & (age < 30)
+            with eng.execute(Query("syn", conj(Select("age", GT(18)), Select("age", LT(30))), Project(["id", "age"], lim))) as r:
+                want = ids[m][:lim] if lim else ids[m]
+                assert r.nrows == len(want) and np.array_equal(r.column(0), want) and r.kernel_launches >= 3
+            lo, hi = int(bid[nb // 3]), int(bid[2 * nb // 3])
+            cb, ca = bid[border], bage[border]
+            mb = (cb > lo) & (cb < hi)
+            with eng.execute(Query("b32", conj(Select("id", GT(lo)), Select("id", LT(hi))), Project(["id", "age"], lim))) as r:
+                want = cb[mb][:lim] if lim else cb[mb]
+                assert r.nrows == len(want) and np.array_equal(r.column(0), want) and np.array_equal(r.column(1), (ca[mb][:lim] if lim else ca[mb]))
+            with eng.execute(Query("b32", Select("age", LT(3)), Project(["id"], lim))) as r:     # row-space filter + block emit
+                want = cb[ca < 3][:lim] if lim else cb[ca < 3]
+                assert r.nrows == len(want) and np.array_equal(r.column(0), want)
