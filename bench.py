@@ -67,7 +67,7 @@ WORKLOADS = {
        for n, p in (("001", "0.01%"), ("01", "0.1%"), ("1", "1%"), ("10", "10%"), ("50", "50%"), ("100", "100%"))},
 }
 # what the default run measures besides the headline: (record name, workload, table rows)
-SECONDARY = [("c2_100m", "c2", 100_000_000), ("c3_100m", "c3", 100_000_000), ("c4_limit10_1b", "c4_limit10", None),
+SECONDARY = [("c4_pruned_1b", "c4", None), ("c2_100m", "c2", 100_000_000), ("c3_100m", "c3", 100_000_000), ("c4_limit10_1b", "c4_limit10", None),
              ("c5_rare_1b", "c5_rare", None), ("c5p_lt10_1b", "c5p_lt10", None)]
 WINDOW_FRAC = {"c5w_001": 1e-4, "c5w_01": 1e-3, "c5w_1": 1e-2, "c5w_10": 0.1, "c5w_50": 0.5, "c5w_100": 1.0}
 
@@ -391,13 +391,22 @@ def main():
             opened[key] = (sm, Engine(sm), d, table, sm.getTable(table), open_s, gen_s)
         return opened[key]
 
-    def measure(workload, rows_total, steps, warmup, sample_clocks=False):
+    def measure(workload, rows_total, steps, warmup, sample_clocks=False, prune=False):
         """K timed steps of one query.  Per step: L2 flush + barrier (untimed), then the wall time of imm3_query_begin -
         launch of every kernel of the query, the on-device count exchange, one synchronisation, counts on the host."""
         sm, eng, d, table, tinfo, open_s, gen_s = open_table(WORKLOADS[workload][1], rows_total)
         query = build_query(workload, table, rows_total)
         prep = eng.prepare(query)
+        # Block pruning (per-block min/max, SURVEY.md 8f-4) changes the bytes a range query on the encoded column has to read:
+        # the headline is the plain scan (every block decided from its encoded bytes); the pruned figure is a secondary record.
+        if os.environ.get("IMM3_BENCH_KEEP_PRUNE_ENV"):
+            pass  # (profiling scripts choose the mode themselves)
+        elif prune:
+            os.environ.pop("IMM3_NO_PRUNE", None)
+        else:
+            os.environ["IMM3_NO_PRUNE"] = "1"
         wall, dev, launches, alg, local_rows, take, gcount = [], [], 0, 0, 0, 0, 0
+        phases = []
         for i in range(warmup):
             flush_l2(i)
             barrier()
@@ -413,6 +422,7 @@ def main():
             t1 = time.perf_counter()
             wall.append((t1 - t0) * 1e3)
             dev.append(r.device_ms)
+            phases.append(r.host_us())
             launches += r.kernel_launches
             alg, local_rows, take, gcount = r.algorithmic_bytes, r.local_count, r.take, r.global_count
             r.close()
@@ -424,7 +434,9 @@ def main():
                "ms_per_step": ms, "wall_ms": {"median": ms, "mean": statistics.mean(wall_max), "min": min(wall_max), "max": max(wall_max)},
                "device_ms": {"median": statistics.median(dev_max), "mean": statistics.mean(dev_max), "min": min(dev_max)},
                "host_overhead_us": (ms - statistics.median(dev_max)) * 1e3, "result_rows": gcount,
-               "gpu_launches": allsum(launches), "steps": steps}
+               "host_phase_us_rank0": dict(zip(("plan", "buffers+device_plan", "launches", "wait_gpu", "epilogue"),
+                                               [statistics.median(p[i] for p in phases) for i in range(5)])),
+               "gpu_launches": allsum(launches), "steps": steps, "block_pruning": bool(prune)}
         # roofline of the query's kernels (rank 0's slice: its algorithmic bytes / its CUDA-event time)
         peak, peak_src = measured_peak()
         my_ms = statistics.mean(dev)
@@ -554,7 +566,7 @@ def main():
         for name, wl, rows in SECONDARY:
             rows_total = (rows if rows is not None else args.rows) * (world if args.scaling == "weak" else 1)
             try:
-                rec, _, sctx = measure(wl, rows_total, max(5, args.steps // 2), 3)
+                rec, _, sctx = measure(wl, rows_total, max(5, args.steps // 2), 3, prune=True)  # (secondary records: the library's defaults)
                 if not args.no_verify and rec["result_rows"] <= 50_000_000:
                     ok = verify(load_oracle(), wl, rows_total, sctx, max(1, cores // world))
                     if world > 1:
@@ -573,9 +585,9 @@ def main():
             "data": "synthetic",
             "config": config_dict(args, args.workload, total, world, {
                 "l2": "flushed between steps (512 MiB %s pass)" % flush_mode, "kernel_variant": "direct" if args.no_tma else "tma",
-                "timed": "wall: host barrier -> imm3_query_begin returns (all kernels + on-device count exchange + one sync); median of K steps of the max over ranks",
+                "block_pruning": False, "timed": "wall: host barrier -> imm3_query_begin returns (all kernels + on-device count exchange + one sync); median of K steps of the max over ranks",
                 "result_rows": head["result_rows"]}),
-            "clocks": clocks, "timing": {k: head[k] for k in ("wall_ms", "device_ms", "host_overhead_us")},
+            "clocks": clocks, "timing": {k: head[k] for k in ("wall_ms", "device_ms", "host_overhead_us", "host_phase_us_rank0")},
             "e2e": e2e, "e2e_resident": e2e_res, "gpu_launches": head["gpu_launches"], "roofline": roofline, "cpu_baseline": cpu,
             "result_equal": result_equal, "workloads": secondary, "open_s": open_s,
             "upload_gbs": tinfo.resident_bytes / open_s / 1e9, "resident_bytes_rank0": tinfo.resident_bytes, "table_gen_s": gen_s,

@@ -4,6 +4,6 @@ library lazily on first use and fails loudly if it is missing (there is no CPU f
 from .engine import (And, Column, EQ, Engine, GT, LT, Match, NoOp, NoSelect, NotMatch, Or, Project, Query, Result, Row,
                      SegmentManager, Select, Table, flatten_select)
 from ._lib import (CODEC_DENSE_INT, CODEC_DENSE_STRING, CODEC_DENSE_TINYINT, CODEC_PFOR_INT, Imm3Error, OPEN_FORCE_BLOCKS,
-                   OPEN_HOST_ONLY, OPEN_KEEP_HOST, OPEN_NO_TMA)
+                   OPEN_HOST_ONLY, OPEN_KEEP_HOST, OPEN_NO_STATS, OPEN_NO_TMA)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -17,7 +17,7 @@ COMM_HANDLE_BYTES = 64
 COL_INT, COL_TINYINT, COL_STRING = 0, 1, 2
 CODEC_PFOR_INT, CODEC_DENSE_INT, CODEC_DENSE_TINYINT, CODEC_DENSE_STRING = 0, 1, 2, 3
 OP_GT, OP_LT, OP_EQ, OP_MATCH, OP_NOTMATCH, OP_NOOP = 1, 2, 3, 4, 5, 6
-OPEN_HOST_ONLY, OPEN_KEEP_HOST, OPEN_NO_TMA, OPEN_FORCE_BLOCKS = 1, 2, 4, 8
+OPEN_HOST_ONLY, OPEN_KEEP_HOST, OPEN_NO_TMA, OPEN_FORCE_BLOCKS, OPEN_NO_STATS = 1, 2, 4, 8, 16
 
 
 class Pred(C.Structure):
@@ -78,6 +78,7 @@ SIGNATURES = {
     "imm3_result_device_ms": (C.c_double, [_P]),
     "imm3_result_kernel_launches": (C.c_int, [_P]),
     "imm3_result_stage_ms": (C.c_double, [_P, C.c_int]),
+    "imm3_result_host_us": (C.c_double, [_P, C.c_int]),
     "imm3_result_algorithmic_bytes": (C.c_int64, [_P]),
     "imm3_result_free": (C.c_int, [_P]),
     "imm3_filter_bitmap": (C.c_int, [_P, C.c_char_p, C.POINTER(Pred), C.c_int, C.POINTER(C.POINTER(C.c_uint32)),

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fcntl.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <atomic>
@@ -52,6 +53,13 @@ struct Buf {
     void* p = nullptr;
     size_t cap = 0;
 };
+
+inline double now_us() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec * 1e6 + (double)ts.tv_nsec * 1e-3;
+}
+thread_local double g_t_launched = 0, g_t_synced = 0;  // stamps taken inside run_scan_once (last launch queued / GPU done)
 
 // Grow-only cache of device / pinned-host buffers: result columns are handed back on
 // imm3_result_free and reused by the next query (cudaMalloc / cudaMallocHost cost milliseconds).
@@ -130,6 +138,7 @@ struct imm3_db {
     BufPool dev_pool, host_pool;
     Buf d_bitmap, h_bitmap;
     Buf d_span_cnt, d_tile_cnt, d_tile_off;  // multi-pass pipeline scratch (grow-only)
+    Buf d_work;                              // blocks_prune_kernel: work list of tiles for the filter kernel ([0] = count)
     Buf d_scan_part;                         // offset_scan_kernel: epoch-tagged chunk sums (zeroed when (re)allocated)
     uint32_t scan_epoch = 0;
     Buf d_trace;                             // IMM3_TRACE debugging buffer
@@ -155,6 +164,7 @@ struct imm3_result {
     cudaEvent_t copied = nullptr;  // recorded on the copy stream after the last device->host copy
     double device_ms = 0;
     double stage_ms[2] = {0, 0};
+    double host_us[5] = {0, 0, 0, 0, 0};  // wall clock inside imm3_query_begin: plan, buffers + device plan, launches, wait for the GPU, epilogue
     int launches = 0;
     int64_t alg_bytes = 0;
 };
@@ -331,6 +341,23 @@ int upload_all(imm3_db* db) {
     cudaError_t e = cudaStreamSynchronize(db->stream);
     if (rc) return rc;
     if (e != cudaSuccess) return fail(IMM3_ERR_CUDA, "upload: %s", cudaGetErrorString(e));
+    // Block statistics of the encoded INT columns (exact min / max per block, one decode pass on the GPU): what the stubs
+    // SegmentStats / check() of the reference (Segment.scala:18-30) were meant to hold.  Range queries prune with them.
+    if (!(db->flags & IMM3_OPEN_NO_STATS)) {
+        for (auto& t : db->tables) {
+            if (t.max_block_rows > 1024 || t.nblocks == 0) continue;  // (the warp-per-block decoder takes blocks of <= 1024 rows)
+            for (auto& col : t.cols) {
+                if (col.meta.codec != IMM3_CODEC_PFOR_INT) continue;
+                CUDA_TRY(cudaMalloc(&col.d_stats, (size_t)t.nblocks * sizeof(BlockStat)));
+                PforCol pc;
+                pc.words = reinterpret_cast<const uint32_t*>(col.d_arena);
+                pc.word_off = col.d_word_off;
+                const int cap = (int)std::min<int64_t>(1120, ((col.max_block_words + 4 + 31) / 32) * 32);
+                CUDA_TRY(launch_block_stats(pc, t.d_row_start, t.nblocks, cap, db->num_sms, (BlockStat*)col.d_stats, db->stream));
+            }
+        }
+        CUDA_TRY(cudaStreamSynchronize(db->stream));
+    }
     return 0;
 }
 
@@ -351,6 +378,7 @@ void free_device_side(imm3_db* db) {
         for (auto& c : t.cols) {
             if (c.d_arena) cudaFree(c.d_arena);
             if (c.d_word_off) cudaFree(c.d_word_off);
+            if (c.d_stats) cudaFree(c.d_stats);
             if (c.h_mirror) cudaFreeHost(c.h_mirror);
         }
         if (t.d_row_start) cudaFree(t.d_row_start);
@@ -363,6 +391,7 @@ void free_device_side(imm3_db* db) {
     if (db->d_tile_off.p) cudaFree(db->d_tile_off.p);
     if (db->d_trace.p) cudaFree(db->d_trace.p);
     if (db->d_scan_part.p) cudaFree(db->d_scan_part.p);
+    if (db->d_work.p) cudaFree(db->d_work.p);
     if (db->h_bitmap.p) cudaFreeHost(db->h_bitmap.p);
     if (db->d_status) cudaFree(db->d_status);
     if (db->d_ctrl) cudaFree(db->d_ctrl);
@@ -387,6 +416,8 @@ struct Prepared {
     bool blocks_multi = false;  // block mode: warp-per-block filter kernel -> offset scan -> emit kernel (no look-back chain)
     bool for_bitmap = false;    // imm3_filter_bitmap: the canonical-row bitmap comes from the single-pass kernels
     bool quad = false;          // block mode: the single-range-predicate filter kernel (lane = block x super-block)
+    bool prune = false;         // block mode: every predicate is a range on an encoded column with block statistics: blocks_prune_kernel first
+    PrunePlan pp;
     bool hybrid = false;        // block mode, no predicate on an encoded column: DENSE filter kernel (row space) -> block emit kernel
     size_t blocks_emit_smem = 0;
     int64_t prefix_blocks = 0;  // small LIMIT on a block table: the pipeline first runs over this many leading blocks (0 = no prefix)
@@ -606,6 +637,24 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
                     pr->dyn_smem = (size_t)qring * (size_t)qslot;
                 }
             }
+            // Pruning: every predicate is a range on an encoded column that has block statistics.
+            pr->prune = false;
+            if (sp.nfilter > 0 && !pr->hybrid && !getenv("IMM3_NO_PRUNE")) {
+                bool ok = true;
+                std::memset(&pr->pp, 0, sizeof pr->pp);
+                for (int i = 0; i < sp.nfilter && ok; i++) {
+                    const FilterCol& f = sp.filter[i];
+                    ok = f.pfor_slot >= 0 && f.kind == kFilterI32Range && t.cols[(size_t)pfor_cols[(size_t)f.pfor_slot]].d_stats != nullptr;
+                    if (ok) {
+                        pr->pp.stats[i] = (const BlockStat*)t.cols[(size_t)pfor_cols[(size_t)f.pfor_slot]].d_stats;
+                        pr->pp.lo[i] = f.lo;
+                        pr->pp.hi[i] = (int32_t)((int64_t)f.lo + (int64_t)f.span);
+                    }
+                }
+                pr->pp.nfilter = sp.nfilter;
+                pr->pp.group_shift = pr->quad ? 5 : 3;
+                pr->prune = ok;
+            }
             pr->blocks_emit_smem = blocks_emit_smem_bytes(sp.npfor, sp.blk_words_cap);
             int occ_e = 0;
             CUDA_TRY(blocks_multi_occupancy(pr->dyn_smem, pr->blocks_emit_smem, pr->hybrid ? nullptr : &occ, &occ_e, pr->quad));
@@ -784,6 +833,7 @@ int launch_scan_kernel(imm3_db* db, const ScanPlan& sp, int64_t ntiles, int* lau
 int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launches, double* stage_ms, int64_t nblocks_use, bool exchange) {
     bool have_mid = false;
     pr->sp.scan_inline = 1;
+    *launches = 0;
     if (pr->block_mode && pr->hybrid) {
         // dense filter kernel over the row space -> block emit kernel (decodes only blocks with surviving rows)
         TableStore& t = *pr->table;
@@ -825,11 +875,23 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         if ((rc = ensure_buf(&db->d_tile_cnt, ntiles_pad * 4))) return rc;
         if ((rc = ensure_buf(&db->d_tile_off, ntiles_pad * 8))) return rc;
         pr->sp.scan_inline = scan_inline_for(ntiles) ? 1 : 0;
+        const unsigned int* work = nullptr;
+        if (pr->prune) {
+            if ((rc = ensure_buf(&db->d_work, (size_t)((nblocks + 7) / 8 + 2) * 4))) return rc;
+            work = (const unsigned int*)db->d_work.p;
+        }
         CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
+        if (pr->prune) {
+            // whole blocks decided from their min / max; only the tiles a window edge cuts through reach the filter kernel
+            CUDA_TRY(cudaMemsetAsync(db->d_work.p, 0, 4, db->stream));
+            CUDA_TRY(launch_blocks_prune(pr->pp, t.d_row_start, nblocks, ntiles, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
+                                         (unsigned int*)db->d_work.p, db->num_sms, db->stream));
+            (*launches)++;
+        }
         CUDA_TRY(launch_blocks_filter(pr->sp, (uint32_t*)db->d_bitmap.p, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
                                       (unsigned long long*)db->d_tile_off.p, db->d_ctrl, nblocks,
-                                      pr->quad ? (int)std::max<int64_t>(1, std::min<int64_t>(pr->grid, (nblocks + 31) / 32)) : pr->grid, pr->dyn_smem, pr->quad, db->stream));
-        *launches = 1;
+                                      pr->quad ? (int)std::max<int64_t>(1, std::min<int64_t>(pr->grid, (nblocks + 31) / 32)) : pr->grid, pr->dyn_smem, pr->quad, work, db->stream));
+        (*launches)++;
         if (!pr->sp.scan_inline && (rc = launch_scan_kernel(db, pr->sp, ntiles, launches))) return rc;
         const bool pdl = pr->sp.nproj > 0 && !getenv("IMM3_NO_PDL");
         if (!pdl) {
@@ -927,7 +989,9 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         CUDA_TRY(cudaEventRecord(db->ev1, db->stream));  // (re-recorded: the timed span now ends behind the exchange)
     }
     CUDA_TRY(cudaMemcpyAsync(db->h_ctrl, db->d_ctrl, sizeof(CtrlBlock), cudaMemcpyDeviceToHost, db->stream));
+    g_t_launched = now_us();
     CUDA_TRY(cudaStreamSynchronize(db->stream));
+    g_t_synced = now_us();
     if (db->h_ctrl->c.error) return fail(IMM3_ERR_CUDA, "kernel watchdog fired (code %u)", db->h_ctrl->c.error);
     if (exchange && db->comm_on && db->h_ctrl->x.error)
         return fail(IMM3_ERR_COMM, "count exchange: a peer's count did not arrive within %llu ms (ranks must issue the same queries in the same order)",
@@ -1255,10 +1319,14 @@ int imm3_explain(imm3_db* db, const char* table, const imm3_pred* preds, int npr
 int imm3_query_begin(imm3_db* db, const char* table, const imm3_pred* preds, int npreds, const char* const* proj_cols,
                      int nproj, int64_t limit, imm3_result** out) {
     if (!db || !out) return fail(IMM3_ERR_INVALID_ARG, "imm3_query_begin: NULL argument");
+    const double t_in = now_us();
     Prepared pr;
     int rc = prepare(db, table, preds, npreds, proj_cols, nproj, limit, &pr);  // validation before any device work
     if (rc) return rc;
     if ((rc = use_device(db))) return rc;
+    const double t_plan = now_us();
+    double t_dev = t_plan;
+    g_t_launched = g_t_synced = 0;
     TableStore& t = *pr.table;
     std::unique_ptr<imm3_result> r(new imm3_result());
     r->db = db;
@@ -1282,6 +1350,7 @@ int imm3_query_begin(imm3_db* db, const char* table, const imm3_pred* preds, int
         if ((rc = fill_scan_plan(db, &pr))) { give_back(); return rc; }
         for (int i = 0; i < r->ncols; i++) pr.sp.proj[i].out = (uint8_t*)r->d_cols[(size_t)i].p;
         pr.sp.bitmap = nullptr;
+        t_dev = now_us();
         if ((rc = run_scan(db, &pr, &r->device_ms, &r->local_count, &r->launches, r->stage_ms))) { give_back(); return rc; }
     } else if (db->comm_on && !pr.lp.always_empty) {
         // Empty slice (more ranks than segments): this rank still takes part in every round of the exchange.  (A predicate
@@ -1326,6 +1395,16 @@ int imm3_query_begin(imm3_db* db, const char* table, const imm3_pred* preds, int
         r->alg_bytes = a + per_row * r->local_count;
     }
     db->live_results++;
+    {
+        const double t_out = now_us();
+        r->host_us[0] = t_plan - t_in;
+        r->host_us[1] = t_dev - t_plan;
+        if (g_t_launched > 0) {
+            r->host_us[2] = g_t_launched - t_dev;     // (two-phase LIMIT queries: the last phase's stamps)
+            r->host_us[3] = g_t_synced - g_t_launched;
+            r->host_us[4] = t_out - g_t_synced;
+        }
+    }
     *out = r.release();
     return 0;
 }
@@ -1427,6 +1506,7 @@ const void* imm3_result_col_data(const imm3_result* r, int c) { return (r && c >
 const void* imm3_result_col_device(const imm3_result* r, int c) { return (r && c >= 0 && c < r->ncols) ? r->d_cols[(size_t)c].p : nullptr; }
 double imm3_result_device_ms(const imm3_result* r) { return r ? r->device_ms : -1.0; }
 int imm3_result_kernel_launches(const imm3_result* r) { return r ? r->launches : IMM3_ERR_INVALID_ARG; }
+double imm3_result_host_us(const imm3_result* r, int phase) { return (r && phase >= 0 && phase < 5) ? r->host_us[phase] : -1.0; }
 double imm3_result_stage_ms(const imm3_result* r, int stage) { return (r && stage >= 0 && stage < 2) ? r->stage_ms[stage] : -1.0; }
 int64_t imm3_result_algorithmic_bytes(const imm3_result* r) { return r ? r->alg_bytes : IMM3_ERR_INVALID_ARG; }
 

@@ -245,7 +245,7 @@ __host__ __device__ constexpr int blk_filter_slot_bytes(int nstaged, int tile_ca
 __global__ void __launch_bounds__(kComputeThreads + 32, 4) blocks_filter_kernel(const __grid_constant__ ScanPlan P, uint32_t* __restrict__ bitmapB,
                                                                                   uint32_t* __restrict__ blk_cnt, uint32_t* __restrict__ tile_cnt,
                                                                                   unsigned long long* __restrict__ tile_off, ScanCtrl* ctrl,
-                                                                                  long long nblocks) {
+                                                                                  long long nblocks, const unsigned int* __restrict__ work) {
     __shared__ FilterShared S;
     __shared__ PforCol s_pfor[kMaxPforCols];
     __shared__ uint32_t s_base[kMaxFilterStages][kMaxPforCols];  // per ring slot and encoded column: arena word that sits at the slot's data offset
@@ -278,10 +278,12 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) blocks_filter_kernel(
         // ---------------- producer ----------------
         if (lane == 0) {
             RingPos rp;
-            for (long long tile = blockIdx.x;; tile += gridDim.x, rp.advance(ring)) {
+            const long long nwork = work ? (long long)work[0] : ntiles;  // pruned query: only the tiles blocks_prune_kernel listed
+            for (long long k = blockIdx.x;; k += gridDim.x, rp.advance(ring)) {
                 const int slot = rp.slot;
                 if (rp.use > 0) mbar_wait(smem_u32(&S.mbar_empty[slot]), (rp.use - 1) & 1u, nullptr);
                 const uint32_t bar = smem_u32(&S.mbar_full[slot]);
+                const long long tile = k < nwork ? (work ? (long long)work[1 + k] : k) : ntiles;
                 if (tile >= ntiles) {
                     S.tile_id[slot] = kNoMoreTiles;
                     mbar_arrive(bar);
@@ -635,7 +637,7 @@ __device__ __forceinline__ bool pfor_range_quad(uint32_t wa, int nw, int nsuper,
 __global__ void __launch_bounds__(kComputeThreads + 32, IMM3_QUAD_MIN_BLOCKS) blocks_filter_quad_kernel(const __grid_constant__ ScanPlan P, uint32_t* __restrict__ bitmapB,
                                                                                        uint32_t* __restrict__ blk_cnt, uint32_t* __restrict__ tile_cnt,
                                                                                        unsigned long long* __restrict__ tile_off, ScanCtrl* ctrl,
-                                                                                       long long nblocks) {
+                                                                                       long long nblocks, const unsigned int* __restrict__ work) {
     __shared__ FilterShared S;
     __shared__ uint32_t s_base[kMaxFilterStages];       // per ring slot: arena word that sits at the slot's data offset
     __shared__ unsigned int s_tacc[kMaxFilterStages][4];  // per ring slot: the four 8-block tile counts ([31:20] warps arrived)
@@ -662,10 +664,12 @@ __global__ void __launch_bounds__(kComputeThreads + 32, IMM3_QUAD_MIN_BLOCKS) bl
         // ---------------- producer ----------------
         if (lane == 0) {
             RingPos rp;
-            for (long long ct = blockIdx.x;; ct += gridDim.x, rp.advance(ring)) {
+            const long long nwork = work ? (long long)work[0] : nct;  // pruned query: only the tiles blocks_prune_kernel listed
+            for (long long k = blockIdx.x;; k += gridDim.x, rp.advance(ring)) {
                 const int slot = rp.slot;
                 if (rp.use > 0) mbar_wait(smem_u32(&S.mbar_empty[slot]), (rp.use - 1) & 1u, nullptr);
                 const uint32_t bar = smem_u32(&S.mbar_full[slot]);
+                const long long ct = k < nwork ? (work ? (long long)work[1 + k] : k) : nct;
                 if (ct >= nct) {
                     S.tile_id[slot] = kNoMoreTiles;
                     mbar_arrive(bar);

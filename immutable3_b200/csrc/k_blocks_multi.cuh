@@ -306,9 +306,27 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const _
         }
         // selection vector of the block (ascending rows)
         const int cnt = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(myword));
+        const int nn = (int)(P.limit - g < (long long)cnt ? P.limit - g : (long long)cnt);
+        if (cnt == n) {
+            // every row of the block survives (the inside of a window on a sorted column): no selection vector - decoded
+            // columns go out row by row (a coalesced store per 32 rows), dense columns are copied straight
+#pragma unroll 1
+            for (int pc = 0; pc < P.nproj; pc++) {
+                const int w = s_proj[pc].width, slot = s_proj[pc].pfor_slot;
+                if (slot >= 0) {
+                    const uint32_t* vs = vals0 + slot * kBlkVals;
+                    const uint32_t* bs = bases + slot * 32;
+                    uint32_t* o = reinterpret_cast<uint32_t*>(s_proj[pc].out) + g;
+#pragma unroll 4
+                    for (int i = lane; i < nn; i += 32) o[i] = vs[(i >> 5) * kBlkLane + lane] + bs[i >> 5];
+                } else {
+                    copy_rows(s_proj[pc].base + R0 * w, s_proj[pc].out + g * w, nn * w, lane);
+                }
+            }
+            continue;
+        }
         append_selection(myword, lane, sel_w, 0u);
         __syncwarp();
-        const int nn = (int)(P.limit - g < (long long)cnt ? P.limit - g : (long long)cnt);
         if (fused_ok) {
 #pragma unroll 1
             for (int b0 = 0; b0 < nn; b0 += 128) {

@@ -17,8 +17,10 @@
 // Tiles are handed out by atomic tickets, so a tile only ever waits on tiles that are already running (forward progress
 // without relying on block scheduling order).  No spin is unbounded: a watchdog traps instead of hanging the GPU.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <type_traits>
 
+#include <climits>
 #include <cstdint>
 #include <mutex>
 
@@ -34,6 +36,7 @@ namespace imm3 {
 #include "k_multipass.cuh"
 #include "k_blocks_multi.cuh"
 #include "k_blocks_filter.cuh"
+#include "k_blocks_prune.cuh"
 #include "k_comm.cuh"
 
 // =============================================================================================
@@ -68,6 +71,7 @@ static cudaError_t configure_device() {
         IMM3_SET_SMEM(emit_stream_kernel);
         IMM3_SET_SMEM(blocks_filter_kernel);
         IMM3_SET_SMEM(blocks_filter_quad_kernel);
+        IMM3_SET_SMEM(block_stats_kernel);
         IMM3_SET_SMEM(blocks_emit_kernel<true>);
         IMM3_SET_SMEM(blocks_emit_kernel<false>);
         IMM3_SET_SMEM(emit_general_kernel);
@@ -170,6 +174,28 @@ cudaError_t launch_emit_stream(const ScanPlan& plan, const uint32_t* bitmap, con
     return cudaLaunchKernelEx(&cfg, emit_stream_kernel, plan, bitmap, span_cnt, tile_cnt, tile_off, nsub, ring, stage_bytes, dense_mode, ctrl);
 }
 
+// Exact signed min / max of every block of an encoded INT column (imm3_open).
+cudaError_t launch_block_stats(const PforCol& pc, const uint64_t* row_start, long long nblocks, int words_cap, int num_sms, BlockStat* stats,
+                               cudaStream_t stream) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    const size_t smem = (size_t)kComputeWarps * (size_t)(words_cap + kBlkVals) * 4;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, block_stats_kernel, kComputeThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorInvalidConfiguration;
+    const long long grid = std::max<long long>(1, std::min<long long>((nblocks + kComputeWarps - 1) / kComputeWarps, (long long)num_sms * occ));
+    block_stats_kernel<<<(unsigned)grid, kComputeThreads, smem, stream>>>(pc, row_start, nblocks, words_cap, stats);
+    return cudaGetLastError();
+}
+cudaError_t launch_blocks_prune(const PrunePlan& q, const uint64_t* row_start, long long nblocks, long long ntiles8, uint32_t* blk_cnt,
+                                uint32_t* tile_cnt, unsigned int* work, int num_sms, cudaStream_t stream) {
+    const long long groups = (nblocks + 31) / 32;
+    const long long grid = std::max<long long>(1, std::min<long long>((groups + kComputeWarps - 1) / kComputeWarps, (long long)num_sms * 8));
+    blocks_prune_kernel<<<(unsigned)grid, kComputeThreads, 0, stream>>>(q, row_start, nblocks, ntiles8, blk_cnt, tile_cnt, work);
+    return cudaGetLastError();
+}
+
 long long scan_inline_max_tiles() { return kScanInlineMaxTiles; }
 cudaError_t launch_offset_scan(const uint32_t* tile_cnt, unsigned long long* tile_off, long long ntiles, long long limit, uint32_t epoch,
                                unsigned long long* partials, ScanCtrl* ctrl, cudaStream_t stream) {
@@ -200,11 +226,12 @@ cudaError_t blocks_multi_occupancy(size_t filter_smem, size_t emit_smem, int* fi
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(emit_blocks_per_sm, blocks_emit_kernel<true>, kComputeThreads, emit_smem);
 }
 cudaError_t launch_blocks_filter(const ScanPlan& plan, uint32_t* bitmapB, uint32_t* blk_cnt, uint32_t* tile_cnt, unsigned long long* tile_off,
-                                 ScanCtrl* ctrl, long long nblocks, int grid, size_t dyn_smem, bool quad, cudaStream_t stream) {
+                                 ScanCtrl* ctrl, long long nblocks, int grid, size_t dyn_smem, bool quad, const unsigned int* work,
+                                 cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    if (quad) blocks_filter_quad_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks);
-    else blocks_filter_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks);
+    if (quad) blocks_filter_quad_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks, work);
+    else blocks_filter_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks, work);
     return cudaGetLastError();
 }
 cudaError_t launch_blocks_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* cnts, const unsigned long long* tile_off,

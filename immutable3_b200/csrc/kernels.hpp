@@ -35,7 +35,12 @@ size_t blocks_emit_smem_bytes(int npfor, int words_cap);
 int blocks_filter_quad_slot_bytes(int tile_cap_bytes);
 cudaError_t blocks_multi_occupancy(size_t filter_smem, size_t emit_smem, int* filter_blocks_per_sm, int* emit_blocks_per_sm, bool quad);
 cudaError_t launch_blocks_filter(const ScanPlan& plan, uint32_t* bitmapB, uint32_t* blk_cnt, uint32_t* tile_cnt, unsigned long long* tile_off,
-                                 ScanCtrl* ctrl, long long nblocks, int grid, size_t dyn_smem, bool quad, cudaStream_t stream);
+                                 ScanCtrl* ctrl, long long nblocks, int grid, size_t dyn_smem, bool quad, const unsigned int* work,
+                                 cudaStream_t stream);
+cudaError_t launch_block_stats(const PforCol& pc, const uint64_t* row_start, long long nblocks, int words_cap, int num_sms, BlockStat* stats,
+                               cudaStream_t stream);
+cudaError_t launch_blocks_prune(const PrunePlan& q, const uint64_t* row_start, long long nblocks, long long ntiles8, uint32_t* blk_cnt,
+                                uint32_t* tile_cnt, unsigned int* work, int num_sms, cudaStream_t stream);
 // rowspace: the bitmap / counts come from the dense filter kernel (row space), not from blocks_filter_kernel (block-local)
 cudaError_t launch_blocks_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* cnts, const unsigned long long* tile_off,
                                long long nblocks, const ScanCtrl* ctrl, bool rowspace, bool pdl, int grid, size_t dyn_smem,

@@ -92,6 +92,18 @@ struct ScanPlan {
     uint8_t lits[kLitPoolBytes];
 };
 
+// Block pruning (k_blocks_prune.cuh): exact signed min / max of every block of an encoded INT column, computed on the GPU
+// when the table is opened, and the plan of the kernel that decides whole blocks from them.
+struct alignas(8) BlockStat {
+    int32_t mn, mx;
+};
+struct PrunePlan {
+    const BlockStat* stats[kMaxFilterCols];  // per predicate: the block statistics of its column
+    int32_t lo[kMaxFilterCols], hi[kMaxFilterCols];  // inclusive signed window
+    int32_t nfilter;
+    int32_t group_shift;  // work-list granularity: tiles of 1 << group_shift blocks (5: quad filter kernel, 3: blocks_filter_kernel)
+};
+
 // Device-resident control block of one db (reset by the last CTA of every launch).
 struct ScanCtrl {
     unsigned int ticket;   // next tile to hand out

@@ -21,6 +21,7 @@ struct ColumnStore {
     uint32_t* d_word_off = nullptr;
     int64_t max_block_words = 0;     // PFOR_INT: largest encoded block, in 32-bit words
     int64_t max_tile_bytes = 0;      // PFOR_INT: largest 8-block tile as the filter kernel stages it (16-byte aligned start and size)
+    void* d_stats = nullptr;         // PFOR_INT: BlockStat per block (exact min / max), computed on the GPU at open
     int64_t max_tile32_bytes = 0;    // PFOR_INT: largest 32-block tile (the quad filter kernel's CTA tile)
 };
 

@@ -225,6 +225,10 @@ class Result:
     def stage_ms(self, stage: int) -> float:
         return float(self._lib.imm3_result_stage_ms(self._h, stage))
 
+    def host_us(self):
+        """Wall clock inside imm3_query_begin by phase: [plan, buffers + device plan, launches, wait for the GPU, epilogue]."""
+        return [float(self._lib.imm3_result_host_us(self._h, i)) for i in range(5)]
+
     @property
     def algorithmic_bytes(self) -> int:
         return int(self._lib.imm3_result_algorithmic_bytes(self._h))

@@ -86,6 +86,7 @@ typedef struct imm3_pred {
 #define IMM3_OPEN_KEEP_HOST 0x2u  /* keep a pinned host mirror so imm3_reupload can re-stage  */
 #define IMM3_OPEN_NO_TMA    0x4u  /* force the direct-load variant of the dense kernel (A/B)  */
 #define IMM3_OPEN_FORCE_BLOCKS 0x8u /* run every query through the block-mode kernel (cross-check) */
+#define IMM3_OPEN_NO_STATS  0x10u /* do not compute per-block min/max of the encoded INT columns (no block pruning) */
 
 typedef struct imm3_open_opts {
     int32_t device;  /* CUDA ordinal */
@@ -190,6 +191,9 @@ int imm3_result_kernel_launches(const imm3_result* r);      /* kernels launched 
 /* CUDA-event time of one stage of begin: 0 = filter (+scan) kernel, 1 = emit kernel (multi-pass path);
  * the fused single-pass kernels report everything as stage 0. */
 double imm3_result_stage_ms(const imm3_result* r, int stage);
+/* Wall clock (microseconds) spent inside imm3_query_begin, by phase: 0 = validation + logical plan, 1 = result buffers + device
+ * plan, 2 = queueing the launches, 3 = waiting for the GPU (kernels + count exchange + the 200-byte read-back), 4 = epilogue. */
+double imm3_result_host_us(const imm3_result* r, int phase);
 int64_t imm3_result_algorithmic_bytes(const imm3_result* r);/* SURVEY.md §8d formula for this query     */
 int imm3_result_free(imm3_result* r);
 

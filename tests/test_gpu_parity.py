@@ -550,12 +550,15 @@ SHAPES = [("const", (0, 0)), ("const", (5, 1)), ("const", (-2**31, 2)), ("const"
           ("bits", 26), ("bits", 27), ("bits", 30), ("mixed", 10), ("mixed", 24), ("mixed", 29), ("random", 0)]
 
 
+@pytest.mark.parametrize("prune", [True, False])
 @pytest.mark.parametrize("block", [1024, 1000, 640, 256, 160, 128, 32])
-def test_sorted_int_codec_range_predicates_over_block_shapes(tmp_path_factory, block):
+def test_sorted_int_codec_range_predicates_over_block_shapes(tmp_path_factory, block, prune, monkeypatch):
     """The filter kernel of the sorted-integer codec classifies whole mini-blocks from their packed words (k_blocks_filter.cuh):
     every width class, raw mini-blocks, wrap-around past 2^31 / 2^32, window edges on and next to mini-block boundaries."""
     from immutable3_b200.loader import SegmentWriter
 
+    if not prune:
+        monkeypatch.setenv("IMM3_NO_PRUNE", "1")  # (default: whole blocks are decided from their min / max first, k_blocks_prune.cuh)
     d = tmp_path_factory.mktemp(f"shapes{block}")
     rng = np.random.default_rng(block)
     n = 70_000 if block >= 1000 else 9_000
