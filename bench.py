@@ -361,6 +361,20 @@ def main():
             flush_sink.copy_(flush_buf.view(torch.int64).sum())
         torch.cuda.synchronize()
 
+    def aligned_start():
+        """Host barrier, then every rank spins to the same instant of the host's monotonic clock (all ranks are processes on
+        one host): the ranks leave a collective barrier tens of microseconds apart, which a 0.1 ms query would be charged
+        as waiting time in the count exchange."""
+        barrier()
+        if world > 1:
+            t = torch.tensor([time.monotonic_ns() + 300_000], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            target = int(t.item())
+        else:
+            target = time.monotonic_ns() + 20_000
+        while time.monotonic_ns() < target:
+            pass
+
     def allmax(values):
         if world == 1:
             return list(values)
@@ -409,14 +423,14 @@ def main():
         phases = []
         for i in range(warmup):
             flush_l2(i)
-            barrier()
+            aligned_start()
             eng.begin_prepared(prep).close()
         sampler = ClockSampler(local_rank) if sample_clocks else None
         if sampler:
             sampler.start()
         for i in range(steps):
             flush_l2(i)
-            barrier()
+            aligned_start()
             t0 = time.perf_counter()
             r = eng.begin_prepared(prep)
             t1 = time.perf_counter()
@@ -585,7 +599,7 @@ def main():
             "data": "synthetic",
             "config": config_dict(args, args.workload, total, world, {
                 "l2": "flushed between steps (512 MiB %s pass)" % flush_mode, "kernel_variant": "direct" if args.no_tma else "tma",
-                "block_pruning": False, "timed": "wall: host barrier -> imm3_query_begin returns (all kernels + on-device count exchange + one sync); median of K steps of the max over ranks",
+                "block_pruning": False, "timed": "wall: host barrier (ranks released at one instant of the host clock) -> imm3_query_begin returns (all kernels + on-device count exchange + one sync); median of K steps of the max over ranks",
                 "result_rows": head["result_rows"]}),
             "clocks": clocks, "timing": {k: head[k] for k in ("wall_ms", "device_ms", "host_overhead_us", "host_phase_us_rank0")},
             "e2e": e2e, "e2e_resident": e2e_res, "gpu_launches": head["gpu_launches"], "roofline": roofline, "cpu_baseline": cpu,

@@ -193,7 +193,8 @@ int use_device(imm3_db* db) {
 // no intermediate copy - and queues the host->device copy on its own stream, so file reads, PCIe copies of different
 // threads and the refill of the other buffer all overlap.  (Round 1: one thread memcpy-ing mmap pages into a 2 x 32 MiB
 // ring - 1.4 GB/s.)  The same piece reader fills the pinned host mirror that imm3_reupload re-stages from.
-constexpr size_t kStageBytes = 8u << 20;
+constexpr size_t kStageBytes = 4u << 20;
+constexpr int kMaxStageThreads = 12;
 
 struct Piece {
     ColumnStore* col;
@@ -251,9 +252,23 @@ int read_piece(const Piece& pc, uint8_t* dst) {
 // the columns' pinned host mirrors.
 int run_pieces(imm3_db* db, const std::vector<Piece>& pieces, bool to_device) {
     if (pieces.empty()) return 0;
-    const int nthreads = std::max(1, std::min<int>(io_threads(), (int)pieces.size()));
+    const int nthreads = std::max(1, std::min<int>(std::min(io_threads(), kMaxStageThreads), (int)pieces.size()));
+    // Pinning memory is the slow part of a staged upload (tens of ms per 16 MiB, serialised inside the driver): ONE pinned
+    // block for all staging threads, allocated on first use and kept for the life of the process.
+    uint8_t* pool_base = nullptr;
+    if (to_device) {
+        static std::mutex pin_mu;
+        static uint8_t* pin_block = nullptr;
+        std::lock_guard<std::mutex> lock(pin_mu);
+        if (!pin_block) CUDA_TRY(cudaHostAlloc(&pin_block, (size_t)kMaxStageThreads * 2 * kStageBytes, cudaHostAllocPortable));
+        pool_base = pin_block;
+    }
+    static std::mutex run_mu;  // (one staged upload at a time per process: the pinned block is shared)
+    std::unique_lock<std::mutex> run_lock(run_mu, std::defer_lock);
+    if (to_device) run_lock.lock();
     std::atomic<size_t> next(0);
     std::atomic<int> first_rc(0);
+    std::atomic<long long> us_alloc(0), us_read(0), us_wait(0);  // summed over the threads (IMM3_OPEN_TRACE)
     std::mutex mu;
     std::string why;
     auto report = [&](int rc) {
@@ -263,18 +278,20 @@ int run_pieces(imm3_db* db, const std::vector<Piece>& pieces, bool to_device) {
             first_rc.store(rc);
         }
     };
-    auto work = [&]() {
+    auto work = [&](int tid) {
         uint8_t* stage[2] = {nullptr, nullptr};
         cudaEvent_t ev[2] = {nullptr, nullptr};
         cudaStream_t st = nullptr;
         auto body = [&]() -> int {
             if (to_device) {
+                const double ta = now_us();
                 CUDA_TRY(cudaSetDevice(db->device));
                 CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
                 for (int i = 0; i < 2; i++) {
-                    CUDA_TRY(cudaMallocHost(&stage[i], kStageBytes));
+                    stage[i] = pool_base + ((size_t)tid * 2 + (size_t)i) * kStageBytes;  // (carved out of the process-wide pinned block)
                     CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
                 }
+                us_alloc += (long long)(now_us() - ta);
             }
             int cur = 0;
             bool used[2] = {false, false};
@@ -287,9 +304,13 @@ int run_pieces(imm3_db* db, const std::vector<Piece>& pieces, bool to_device) {
                     if (rc) return rc;
                     continue;
                 }
+                const double tw = now_us();
                 if (used[cur]) CUDA_TRY(cudaEventSynchronize(ev[cur]));  // the buffer's previous copy has retired
+                const double tr = now_us();
                 int rc = read_piece(pc, stage[cur]);
                 if (rc) return rc;
+                us_wait += (long long)(tr - tw);
+                us_read += (long long)(now_us() - tr);
                 CUDA_TRY(cudaMemcpyAsync(pc.col->d_arena + pc.off, stage[cur], pc.bytes, cudaMemcpyHostToDevice, st));
                 CUDA_TRY(cudaEventRecord(ev[cur], st));
                 used[cur] = true;
@@ -301,21 +322,24 @@ int run_pieces(imm3_db* db, const std::vector<Piece>& pieces, bool to_device) {
         const int rc = body();
         if (rc) report(rc);
         if (st) cudaStreamSynchronize(st);
-        for (int i = 0; i < 2; i++) {
-            if (stage[i]) cudaFreeHost(stage[i]);
+        for (int i = 0; i < 2; i++)
             if (ev[i]) cudaEventDestroy(ev[i]);
-        }
         if (st) cudaStreamDestroy(st);
     };
     std::vector<std::thread> pool;
-    for (int t = 1; t < nthreads; t++) pool.emplace_back(work);
-    work();
+    for (int t = 1; t < nthreads; t++) pool.emplace_back(work, t);
+    work(0);
     for (auto& th : pool) th.join();
     if (int rc = first_rc.load()) return fail(rc, "%s", why.c_str());
+    if (getenv("IMM3_OPEN_TRACE") && to_device)
+        fprintf(stderr, "[imm3_open] %d staging threads; per thread: pinned buffers %.1f ms, file reads %.1f ms, waiting for copies %.1f ms\n", nthreads,
+                us_alloc.load() * 1e-3 / nthreads, us_read.load() * 1e-3 / nthreads, us_wait.load() * 1e-3 / nthreads);
     return 0;
 }
 
 int upload_all(imm3_db* db) {
+    const bool otrace = getenv("IMM3_OPEN_TRACE") != nullptr;
+    const double t0 = now_us();
     std::vector<Piece> pieces;
     for (auto& t : db->tables) {
         for (auto& col : t.cols) {
@@ -337,10 +361,18 @@ int upload_all(imm3_db* db) {
         CUDA_TRY(cudaMemcpyAsync(t.d_row_start, t.row_start.data(), t.row_start.size() * sizeof(uint64_t),
                                  cudaMemcpyHostToDevice, db->stream));
     }
+    const double t1 = now_us();
     int rc = run_pieces(db, pieces, true);
     cudaError_t e = cudaStreamSynchronize(db->stream);
     if (rc) return rc;
     if (e != cudaSuccess) return fail(IMM3_ERR_CUDA, "upload: %s", cudaGetErrorString(e));
+    if (otrace) {
+        size_t bytes = 0;
+        for (auto& pc : pieces) bytes += pc.bytes;
+        fprintf(stderr, "[imm3_open] arenas allocated in %.1f ms; %zu pieces, %.1f MB staged in %.1f ms = %.1f GB/s\n", (t1 - t0) * 1e-3, pieces.size(),
+                bytes * 1e-6, (now_us() - t1) * 1e-3, bytes * 1e-3 / (now_us() - t1));
+    }
+    const double t2 = now_us();
     // Block statistics of the encoded INT columns (exact min / max per block, one decode pass on the GPU): what the stubs
     // SegmentStats / check() of the reference (Segment.scala:18-30) were meant to hold.  Range queries prune with them.
     if (!(db->flags & IMM3_OPEN_NO_STATS)) {
@@ -357,6 +389,7 @@ int upload_all(imm3_db* db) {
             }
         }
         CUDA_TRY(cudaStreamSynchronize(db->stream));
+        if (otrace) fprintf(stderr, "[imm3_open] block statistics in %.1f ms\n", (now_us() - t2) * 1e-3);
     }
     return 0;
 }
@@ -1111,8 +1144,11 @@ int imm3_open(const char* data_dir, const imm3_open_opts* opts, imm3_db** out) {
     db->flags = o.flags;
     db->host_only = (o.flags & IMM3_OPEN_HOST_ONLY) != 0;
     db->host_pool.pinned_host = true;
+    const bool otrace = getenv("IMM3_OPEN_TRACE") != nullptr;  // phase times of the open path on stderr
+    const double t_open0 = now_us();
     int rc = load_tables(db->dir, o.rank, o.world, &db->tables);
     if (rc) return rc;
+    if (otrace) fprintf(stderr, "[imm3_open] metadata + validation %.1f ms (%d I/O threads)\n", (now_us() - t_open0) * 1e-3, io_threads());
     if (!db->host_only) {
         int ndev = 0;
         cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1141,6 +1177,7 @@ int imm3_open(const char* data_dir, const imm3_open_opts* opts, imm3_db** out) {
             CUDA_TRY(cudaMallocHost(&db->h_ctrl, sizeof(CtrlBlock)));
             std::memset(db->h_ctrl, 0, sizeof(CtrlBlock));
             if (const char* e = getenv("IMM3_COMM_TIMEOUT_MS")) db->comm_timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
+            if (otrace) fprintf(stderr, "[imm3_open] device + stream setup at %.1f ms\n", (now_us() - t_open0) * 1e-3);
             return upload_all(db.get());
         };
         rc = body();
