@@ -393,7 +393,7 @@ def test_multipass_large_limit_and_mixed_density(tmp_path_factory):
 @pytest.mark.gpu
 @pytest.mark.parametrize("block_rows", [1024, 256, 32])
 def test_gpu_sorted_int_encoder_is_bit_exact(block_rows):
-    """imm3_pfor_encode_blocks_gpu == the host encoder (== the oracle's, tests/test_oracle_kat.py) block by block: sorted
+    """imm3_pfor_encode_blocks_gpu == the ORACLE's PFORCodecInt.encode (and the product's host encoder) block by block: sorted
     ids, equal values (width 0), wide and negative deltas (width 32, raw mini-blocks), every tail length, one short block."""
     from immutable3_b200.loader import pfor_encode, pfor_encode_blocks_gpu
     rng = np.random.default_rng(7 + block_rows)
@@ -412,9 +412,10 @@ def test_gpu_sorted_int_encoder_is_bit_exact(block_rows):
     for name, v in cols.items():
         v = v.astype(np.int64).astype(np.int32) if v.dtype != np.int32 else v
         got, off = pfor_encode_blocks_gpu(v, block_rows)
-        exp = [pfor_encode(v[i:i + block_rows]) for i in range(0, len(v), block_rows)]
+        exp = [O.pfor_encode(v[i:i + block_rows]) for i in range(0, len(v), block_rows)]   # the checker, directly
         assert list(np.diff(off)) == [len(e) for e in exp], name
         assert got == b"".join(exp), name
+        assert exp == [pfor_encode(v[i:i + block_rows]) for i in range(0, len(v), block_rows)], name
 
 
 def test_several_sorted_int_codec_columns(tmp_path_factory):
