@@ -54,6 +54,8 @@ WORKLOADS = {
     "c5_rare": ("C5 test_1b: select id, state, age from test_1b where (state = 'CA' and age = 7)", "pfor"),
     "c5_rare_limit10": ("C5 test_1b: select id, state, age from test_1b where (state = 'CA' and age = 7) limit 10", "pfor"),
     "c5_limit10": ("C5 select id, age where (age > 18 and age < 30) limit 10", "dense"),
+    "agg": ("Engine.scala:66-78 example: select min(age), max(age) from test_100m where age > 18 group by state", "dense"),
+    "agg_count": ("select count(id), max(id) from test_100m where (age > 18 and age < 30) group by state, age", "dense"),
     "x_age": ("X select age where (age > 18 and age < 30)", "dense"),
     "x_id": ("X select id where (age > 18 and age < 30)", "dense"),
     "x_count": ("X select <nothing> where (age > 18 and age < 30)", "dense"),
@@ -67,7 +69,11 @@ WORKLOADS = {
        for n, p in (("001", "0.01%"), ("01", "0.1%"), ("1", "1%"), ("10", "10%"), ("50", "50%"), ("100", "100%"))},
 }
 # what the default run measures besides the headline: (record name, workload, table rows)
-SECONDARY = [("c4_pruned_1b", "c4", None), ("c2_100m", "c2", 100_000_000), ("c3_100m", "c3", 100_000_000), ("c4_limit10_1b", "c4_limit10", None),
+AGG_SPECS = {  # workload -> (predicates, aggregates as (op, col) with op 0 = count, 1 = min, 2 = max, group-by columns)
+    "agg": ([("age", 1, 18)], [(1, "age"), (2, "age")], ["state"]),
+    "agg_count": ([("age", 1, 18), ("age", 2, 30)], [(0, "id"), (2, "id")], ["state", "age"]),
+}
+SECONDARY = [("c4_pruned_1b", "c4", None), ("agg_100m", "agg", 100_000_000), ("c2_100m", "c2", 100_000_000), ("c3_100m", "c3", 100_000_000), ("c4_limit10_1b", "c4_limit10", None),
              ("c5_rare_1b", "c5_rare", None), ("c5p_lt10_1b", "c5p_lt10", None)]
 WINDOW_FRAC = {"c5w_001": 1e-4, "c5w_01": 1e-3, "c5w_1": 1e-2, "c5w_10": 0.1, "c5w_50": 0.5, "c5w_100": 1.0}
 
@@ -102,13 +108,19 @@ def query_spec(workload: str, total_rows: int):
 
 
 def build_query(workload: str, table: str, total_rows: int):
-    from immutable3_b200 import EQ, GT, LT, And, Match, NoSelect, Project, Query, Select
+    from immutable3_b200 import EQ, GT, LT, And, Count, Match, Max, Min, NoSelect, Project, ProjectAgg, Query, Select
 
-    preds, proj, limit = query_spec(workload, total_rows)
+    if workload in AGG_SPECS:
+        preds, aggs, group_by = AGG_SPECS[workload]
+        proj, limit = None, 0
+    else:
+        preds, proj, limit = query_spec(workload, total_rows)
     leaves = [Select(c, {1: GT, 2: LT, 3: EQ}[op](v)) if op != 4 else Select(c, Match(v)) for c, op, v in preds]
     sel = NoSelect
     for i, leaf in enumerate(leaves):
         sel = leaf if i == 0 else And(sel, leaf)
+    if proj is None:
+        return Query(table, sel, ProjectAgg([{0: Count, 1: Min, 2: Max}[op](col) for op, col in aggs], group_by))
     return Query(table, sel, Project(proj, limit))
 
 
@@ -254,13 +266,17 @@ def load_oracle():
 
 
 def run_cpu(O, d, table, workload, total_rows, nthreads, steps, warmup, seg_begin=0, seg_end=-1):
-    preds, proj, limit = query_spec(workload, total_rows)
+    agg = AGG_SPECS.get(workload)
+    preds, proj, limit = (agg[0], None, 0) if agg else query_spec(workload, total_rows)
     times, res = [], None
     with O.Oracle(d) as orc:
         rows_scanned = orc.nrows(table, seg_begin, seg_end)
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            res = orc.query(table, preds, proj, limit=limit, nthreads=nthreads, seg_begin=seg_begin, seg_end=seg_end)
+            if agg:
+                res = orc.query_agg(table, preds, agg[1], agg[2], nthreads=nthreads, seg_begin=seg_begin, seg_end=seg_end)
+            else:
+                res = orc.query(table, preds, proj, limit=limit, nthreads=nthreads, seg_begin=seg_begin, seg_end=seg_end)
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
@@ -410,7 +426,9 @@ def main():
         launch of every kernel of the query, the on-device count exchange, one synchronisation, counts on the host."""
         sm, eng, d, table, tinfo, open_s, gen_s = open_table(WORKLOADS[workload][1], rows_total)
         query = build_query(workload, table, rows_total)
-        prep = eng.prepare(query)
+        is_agg = workload in AGG_SPECS
+        prep = None if is_agg else eng.prepare(query)
+        run = (lambda: eng.execute(query)) if is_agg else (lambda: eng.begin_prepared(prep))
         # Block pruning (per-block min/max, SURVEY.md 8f-4) changes the bytes a range query on the encoded column has to read:
         # the headline is the plain scan (every block decided from its encoded bytes); the pruned figure is a secondary record.
         if os.environ.get("IMM3_BENCH_KEEP_PRUNE_ENV"):
@@ -424,7 +442,7 @@ def main():
         for i in range(warmup):
             flush_l2(i)
             aligned_start()
-            eng.begin_prepared(prep).close()
+            run().close()
         sampler = ClockSampler(local_rank) if sample_clocks else None
         if sampler:
             sampler.start()
@@ -432,7 +450,7 @@ def main():
             flush_l2(i)
             aligned_start()
             t0 = time.perf_counter()
-            r = eng.begin_prepared(prep)
+            r = run()
             t1 = time.perf_counter()
             wall.append((t1 - t0) * 1e3)
             dev.append(r.device_ms)
@@ -479,6 +497,12 @@ def main():
     def verify(O, workload, rows_total, ctx, nthreads, oracle_result=None):
         """Content parity at full size: this rank's fetched rows vs the oracle over this rank's slice (CRC-32 per column)."""
         sm, eng, d, table, tinfo, query, prep, _, _ = ctx
+        if workload in AGG_SPECS:
+            # per-rank partial aggregates vs the oracle over this rank's slice (groups, order and values)
+            with eng.execute(query) as r:
+                got = crc_columns(r.columns())
+            _, ores, _ = run_cpu(O, d, table, workload, rows_total, nthreads, 1, 0, tinfo.seg_begin, tinfo.seg_end)
+            return got == crc_columns(ores.columns)
         with eng.begin_prepared(prep) as r:
             r.fetch(r.take)
             got = crc_columns(r.columns())

@@ -138,6 +138,8 @@ struct imm3_db {
     BufPool dev_pool, host_pool;
     Buf d_bitmap, h_bitmap;
     Buf d_span_cnt, d_tile_cnt, d_tile_off;  // multi-pass pipeline scratch (grow-only)
+    Buf d_agg_table, d_agg_out, d_agg_cnt;   // aggregation: global hash table, compacted groups, [groups, overflow] counters
+    Buf h_agg_out;                           // pinned read-back of the compacted groups
     Buf d_work;                              // blocks_prune_kernel: work list of tiles for the filter kernel ([0] = count)
     Buf d_scan_part;                         // offset_scan_kernel: epoch-tagged chunk sums (zeroed when (re)allocated)
     uint32_t scan_epoch = 0;
@@ -159,6 +161,7 @@ struct imm3_result {
     int64_t g_offset = 0, g_take = 0, g_total = 0;  // after the count exchange (single handle: 0, local_count, local_count)
     int world = 1;
     int64_t rank_counts[kMaxWorld] = {};
+    int agg_first_col = -1;  // aggregate result: index of the first aggregate column (rows live in host buffers only)
     int64_t fetched = 0;
     int64_t pending = -1;        // rows of an imm3_result_fetch_async still in flight (-1 = none)
     cudaEvent_t copied = nullptr;  // recorded on the copy stream after the last device->host copy
@@ -425,6 +428,10 @@ void free_device_side(imm3_db* db) {
     if (db->d_trace.p) cudaFree(db->d_trace.p);
     if (db->d_scan_part.p) cudaFree(db->d_scan_part.p);
     if (db->d_work.p) cudaFree(db->d_work.p);
+    if (db->d_agg_table.p) cudaFree(db->d_agg_table.p);
+    if (db->d_agg_out.p) cudaFree(db->d_agg_out.p);
+    if (db->d_agg_cnt.p) cudaFree(db->d_agg_cnt.p);
+    if (db->h_agg_out.p) cudaFreeHost(db->h_agg_out.p);
     if (db->h_bitmap.p) cudaFreeHost(db->h_bitmap.p);
     if (db->d_status) cudaFree(db->d_status);
     if (db->d_ctrl) cudaFree(db->d_ctrl);
@@ -1121,6 +1128,21 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
     return 0;
 }
 
+// java.lang.Double.toString for an integral value of int32 magnitude (all Min/MaxDoubleAggr ever hold here): "18.0",
+// "-128.0", and computerized scientific notation from 10^7 on ("1.0E7", "2.147483647E9").
+std::string java_double_to_string_integral(double v) {
+    if (v == 0) return "0.0";
+    const bool neg = v < 0;
+    long long a = (long long)(neg ? -v : v);
+    std::string digits = std::to_string(a);
+    std::string out = neg ? "-" : "";
+    if (a < 10000000ll) return out + digits + ".0";
+    const int exp10 = (int)digits.size() - 1;
+    std::string frac = digits.substr(1);
+    while (frac.size() > 1 && frac.back() == '0') frac.pop_back();
+    return out + digits.substr(0, 1) + "." + frac + "E" + std::to_string(exp10);
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -1459,6 +1481,7 @@ int imm3_result_rank_counts(const imm3_result* r, int64_t* counts, int cap) {
 int imm3_result_fetch(imm3_result* r, int64_t nrows) {
     if (!r) return fail(IMM3_ERR_INVALID_ARG, "imm3_result_fetch: result is NULL");
     if (nrows < 0 || nrows > r->local_count) return fail(IMM3_ERR_INVALID_ARG, "imm3_result_fetch: %lld rows of %lld", (long long)nrows, (long long)r->local_count);
+    if (r->agg_first_col >= 0) return 0;  // (aggregate results are materialised on the host by imm3_query_agg)
     imm3_db* db = r->db;
     int rc = use_device(db);
     if (rc) return rc;
@@ -1479,6 +1502,7 @@ int imm3_result_fetch(imm3_result* r, int64_t nrows) {
 int imm3_result_fetch_async(imm3_result* r, int64_t nrows) {
     if (!r) return fail(IMM3_ERR_INVALID_ARG, "imm3_result_fetch_async: result is NULL");
     if (nrows < 0 || nrows > r->local_count) return fail(IMM3_ERR_INVALID_ARG, "imm3_result_fetch_async: %lld rows of %lld", (long long)nrows, (long long)r->local_count);
+    if (r->agg_first_col >= 0) return 0;
     imm3_db* db = r->db;
     int rc = use_device(db);
     if (rc) return rc;
@@ -1524,6 +1548,171 @@ int imm3_query(imm3_db* db, const char* table, const imm3_pred* preds, int npred
     return 0;
 }
 
+int imm3_query_agg(imm3_db* db, const char* table, const imm3_pred* preds, int npreds, const imm3_agg* aggs, int naggs,
+                   const char* const* group_cols, int ngroup, imm3_result** out) {
+    if (!db || !out || (naggs > 0 && !aggs) || (ngroup > 0 && !group_cols)) return fail(IMM3_ERR_INVALID_ARG, "imm3_query_agg: NULL argument");
+    if (naggs < 1) return fail(IMM3_ERR_INVALID_ARG, "imm3_query_agg: no aggregates");
+    if (naggs > kMaxAggs) return fail(IMM3_ERR_UNSUPPORTED, "imm3_query_agg: at most %d aggregates", kMaxAggs);
+    if (ngroup > kMaxGroupCols) return fail(IMM3_ERR_UNSUPPORTED, "imm3_query_agg: at most %d group-by columns", kMaxGroupCols);
+    Prepared pr;
+    int rc = prepare(db, table, preds, npreds, nullptr, 0, 0, &pr);  // validation before any device work
+    if (rc) return rc;
+    TableStore& t = *pr.table;
+    auto find_col = [&](const char* name) -> int {
+        if (!name) return -1;
+        for (size_t i = 0; i < t.cols.size(); i++)
+            if (t.cols[i].meta.name == name) return (int)i;
+        return -1;
+    };
+    AggPlan ap;
+    std::memset(&ap, 0, sizeof ap);
+    std::unique_ptr<imm3_result> r(new imm3_result());
+    r->db = db;
+    std::vector<int> gidx, aidx;
+    int key_bits = 0;
+    for (int g = 0; g < ngroup; g++) {
+        const int ci = find_col(group_cols[g]);
+        if (ci < 0) return fail(IMM3_ERR_NOT_FOUND, "Column %s does not exist in table %s", group_cols[g] ? group_cols[g] : "(null)", t.meta.name.c_str());
+        const ColumnStore& c = t.cols[(size_t)ci];
+        if (c.meta.codec == IMM3_CODEC_PFOR_INT) return fail(IMM3_ERR_UNSUPPORTED, "group by a sorted-int-codec column (%s) is not supported", c.meta.name.c_str());
+        if (key_bits + 8 * c.meta.width > 56) return fail(IMM3_ERR_UNSUPPORTED, "group-by cells must pack into 7 bytes");
+        ap.group[g].width = c.meta.width;
+        ap.group[g].key_shift = key_bits;
+        key_bits += 8 * c.meta.width;
+        gidx.push_back(ci);
+        r->names.push_back(c.meta.name);
+        r->types.push_back(c.meta.ctype);
+        r->widths.push_back(c.meta.width);
+    }
+    for (int a = 0; a < naggs; a++) {
+        const int ci = find_col(aggs[a].col);
+        if (ci < 0) return fail(IMM3_ERR_NOT_FOUND, "Column %s does not exist in table %s", aggs[a].col ? aggs[a].col : "(null)", t.meta.name.c_str());
+        const ColumnStore& c = t.cols[(size_t)ci];
+        const char* suffix = "_count";
+        if (aggs[a].op == IMM3_AGG_COUNT) {
+            ap.agg[a].op = kAggCount;
+        } else if (aggs[a].op == IMM3_AGG_MIN || aggs[a].op == IMM3_AGG_MAX) {
+            if (c.meta.ctype == IMM3_COL_STRING)
+                return fail(IMM3_ERR_UNSUPPORTED, "min / max on a STRING column (the reference maps both to MaxStringAggr, Engine.scala:137,147)");
+            if (c.meta.codec == IMM3_CODEC_PFOR_INT) return fail(IMM3_ERR_UNSUPPORTED, "min / max on a sorted-int-codec column (%s) is not supported", c.meta.name.c_str());
+            ap.agg[a].op = aggs[a].op == IMM3_AGG_MIN ? kAggMin : kAggMax;
+            suffix = aggs[a].op == IMM3_AGG_MIN ? "_min" : "_max";
+        } else {
+            return fail(IMM3_ERR_UNSUPPORTED, "Unknown Aggregate type (Engine.scala:153: only Min, Max and Count are resolved)");
+        }
+        ap.agg[a].width = c.meta.width;
+        aidx.push_back(ci);
+        r->names.push_back(c.meta.name + suffix);  // alias.getOrElse(col + "_max"), Engine.scala:136-152
+        r->types.push_back(ap.agg[a].op == kAggCount ? IMM3_COL_COUNT : IMM3_COL_DOUBLE);
+        r->widths.push_back(8);
+    }
+    r->ncols = ngroup + naggs;
+    r->agg_first_col = ngroup;
+    r->h_cols.resize((size_t)r->ncols);
+    ap.naggs = naggs;
+    ap.ngroup = ngroup;
+    if (pr.block_mode && !pr.lp.filters.empty()) {
+        for (auto& f : pr.lp.filters)
+            if (t.cols[(size_t)f.col_idx].meta.codec == IMM3_CODEC_PFOR_INT)
+                return fail(IMM3_ERR_UNSUPPORTED, "aggregation with a predicate on a sorted-int-codec column (%s) is not supported yet", t.cols[(size_t)f.col_idx].meta.name.c_str());
+    }
+    if ((rc = use_device(db))) return rc;
+    int64_t ngroups_out = 0;
+    std::vector<AggEntry> groups;
+    if (!pr.lp.always_empty && t.nrows > 0) {
+        // The filter runs in row space exactly as for a Project query without a select list (dense filter kernel: bitmap,
+        // span counts, total); the aggregation kernel is queued behind it, one synchronisation for the whole query.
+        const bool was_block = pr.block_mode;
+        pr.block_mode = false;
+        pr.multipass = true;
+        pr.for_bitmap = false;
+        if ((rc = fill_scan_plan(db, &pr))) return rc;
+        pr.block_mode = was_block;
+        ScanPlan& sp = pr.sp;
+        sp.bitmap = nullptr;
+        const int64_t ntiles = sp.ntiles, nspans = ntiles * 8;
+        if ((rc = ensure_buf(&db->d_bitmap, (size_t)(ntiles * kDenseTileRowsPerWord / 32 + 64) * 4))) return rc;
+        if ((rc = ensure_buf(&db->d_span_cnt, (size_t)(nspans + 8) * 4))) return rc;
+        const size_t ntiles_pad = ((size_t)ntiles + 4095) / 4096 * 4096 + 16;
+        if ((rc = ensure_buf(&db->d_tile_cnt, ntiles_pad * 4))) return rc;
+        if ((rc = ensure_buf(&db->d_tile_off, ntiles_pad * 8))) return rc;
+        ap.table_slots = 1u << 16;
+        if (const char* e = getenv("IMM3_AGG_SLOTS")) {  // (tests shrink it to exercise the overflow report)
+            uint32_t v = (uint32_t)atoi(e);
+            if (v >= 64 && (v & (v - 1)) == 0) ap.table_slots = v;
+        }
+        if ((rc = ensure_buf(&db->d_agg_table, (size_t)ap.table_slots * sizeof(AggEntry)))) return rc;
+        if ((rc = ensure_buf(&db->d_agg_out, (size_t)ap.table_slots * sizeof(AggEntry)))) return rc;
+        if ((rc = ensure_buf(&db->d_agg_cnt, 64))) return rc;
+        ap.nrows = t.nrows;
+        ap.ntiles = ntiles;
+        for (int g = 0; g < ngroup; g++) ap.group[g].base = t.cols[(size_t)gidx[(size_t)g]].d_arena;
+        for (int a = 0; a < naggs; a++) ap.agg[a].base = t.cols[(size_t)aidx[(size_t)a]].d_arena;
+        sp.scan_inline = 1;  // (only the total matters here; the last CTA's scan provides it)
+        CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
+        CUDA_TRY(launch_agg_init((AggEntry*)db->d_agg_table.p, ap.table_slots, ap, (unsigned int*)db->d_agg_cnt.p, db->stream));
+        CUDA_TRY(launch_filter(sp, (uint32_t*)db->d_bitmap.p, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
+                               (unsigned long long*)db->d_tile_off.p, db->d_ctrl, pr.grid, pr.dyn_smem, db->stream));
+        CUDA_TRY(launch_agg(ap, (const uint32_t*)db->d_bitmap.p, (const uint32_t*)db->d_span_cnt.p, (AggEntry*)db->d_agg_table.p,
+                            (AggEntry*)db->d_agg_out.p, (unsigned int*)db->d_agg_cnt.p, db->d_ctrl, db->num_sms, db->stream));
+        CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
+        r->launches = 4;
+        unsigned int counters[2] = {0, 0};
+        CUDA_TRY(cudaMemcpyAsync(db->h_ctrl, db->d_ctrl, sizeof(CtrlBlock), cudaMemcpyDeviceToHost, db->stream));
+        CUDA_TRY(cudaMemcpyAsync(counters, db->d_agg_cnt.p, sizeof counters, cudaMemcpyDeviceToHost, db->stream));
+        CUDA_TRY(cudaStreamSynchronize(db->stream));
+        if (db->h_ctrl->c.error) return fail(IMM3_ERR_CUDA, "kernel watchdog fired (code %u)", db->h_ctrl->c.error);
+        if (counters[1]) return fail(IMM3_ERR_UNSUPPORTED, "aggregation: more than %u groups", ap.table_slots);
+        float f = 0;
+        CUDA_TRY(cudaEventElapsedTime(&f, db->ev0, db->ev1));
+        r->device_ms = f;
+        r->stage_ms[0] = f;
+        ngroups_out = counters[0];
+        groups.resize((size_t)ngroups_out);
+        if (ngroups_out) CUDA_TRY(cudaMemcpy(groups.data(), db->d_agg_out.p, (size_t)ngroups_out * sizeof(AggEntry), cudaMemcpyDeviceToHost));
+        std::sort(groups.begin(), groups.end(), [](const AggEntry& x, const AggEntry& y) { return x.first_row < y.first_row; });
+        // algorithmic bytes: filter columns once + per selected row the cells of the group and aggregate columns
+        int64_t bytes = 0, per_row = 0;
+        for (auto& f2 : pr.lp.filters) bytes += t.cols[(size_t)f2.col_idx].encoded_bytes;
+        for (int ci : gidx) per_row += t.cols[(size_t)ci].meta.width;
+        for (int a = 0; a < naggs; a++)
+            if (ap.agg[a].op != kAggCount) per_row += ap.agg[a].width;
+        r->alg_bytes = bytes + per_row * (int64_t)db->h_ctrl->c.total;
+    }
+    // rows of the result: group cells, then the aggregates (COUNT: int64, MIN / MAX: double)
+    for (int c = 0; c < r->ncols; c++) {
+        const size_t w = (size_t)r->widths[(size_t)c];
+        if ((rc = db->host_pool.acquire(std::max<size_t>(1, (size_t)ngroups_out * w), &r->h_cols[(size_t)c]))) {
+            for (auto& b : r->h_cols) db->host_pool.release(b);
+            return rc;
+        }
+        uint8_t* dst = (uint8_t*)r->h_cols[(size_t)c].p;
+        for (int64_t i = 0; i < ngroups_out; i++) {
+            const AggEntry& e = groups[(size_t)i];
+            if (c < ngroup) {
+                const unsigned long long cell = e.key >> ap.group[c].key_shift;
+                for (size_t b = 0; b < w; b++) dst[(size_t)i * w + b] = (uint8_t)(cell >> (8 * b));
+            } else {
+                const int a = c - ngroup;
+                if (ap.agg[a].op == kAggCount) {
+                    const int64_t v = e.val[a];
+                    std::memcpy(dst + (size_t)i * 8, &v, 8);
+                } else {
+                    const double v = (double)e.val[a];  // value.toDouble, ProjectAggregate.scala:176-178
+                    std::memcpy(dst + (size_t)i * 8, &v, 8);
+                }
+            }
+        }
+    }
+    r->local_count = r->fetched = ngroups_out;
+    r->g_offset = 0;
+    r->g_take = r->g_total = ngroups_out;
+    r->world = 1;
+    db->live_results++;
+    *out = r.release();
+    return 0;
+}
+
 int imm3_query_sql(imm3_db* db, const char* sql, imm3_result** out) {
     if (!db || !out) return fail(IMM3_ERR_INVALID_ARG, "imm3_query_sql: NULL argument");
     ParsedQuery q;
@@ -1540,7 +1729,7 @@ int imm3_result_col_type(const imm3_result* r, int c) { return (r && c >= 0 && c
 int imm3_result_col_width(const imm3_result* r, int c) { return (r && c >= 0 && c < r->ncols) ? r->widths[(size_t)c] : IMM3_ERR_INVALID_ARG; }
 const char* imm3_result_col_name(const imm3_result* r, int c) { return (r && c >= 0 && c < r->ncols) ? r->names[(size_t)c].c_str() : nullptr; }
 const void* imm3_result_col_data(const imm3_result* r, int c) { return (r && c >= 0 && c < r->ncols) ? r->h_cols[(size_t)c].p : nullptr; }
-const void* imm3_result_col_device(const imm3_result* r, int c) { return (r && c >= 0 && c < r->ncols) ? r->d_cols[(size_t)c].p : nullptr; }
+const void* imm3_result_col_device(const imm3_result* r, int c) { return (r && c >= 0 && c < r->ncols && (size_t)c < r->d_cols.size()) ? r->d_cols[(size_t)c].p : nullptr; }
 double imm3_result_device_ms(const imm3_result* r) { return r ? r->device_ms : -1.0; }
 int imm3_result_kernel_launches(const imm3_result* r) { return r ? r->launches : IMM3_ERR_INVALID_ARG; }
 double imm3_result_host_us(const imm3_result* r, int phase) { return (r && phase >= 0 && phase < 5) ? r->host_us[phase] : -1.0; }
@@ -1551,10 +1740,19 @@ int64_t imm3_result_algorithmic_bytes(const imm3_result* r) { return r ? r->alg_
 int imm3_result_format_row(const imm3_result* r, int64_t row, char* buf, size_t buflen) {
     if (!r || !buf || row < 0 || row >= r->fetched) return fail(IMM3_ERR_INVALID_ARG, "imm3_result_format_row: bad arguments");
     std::string s = "Row(";
-    for (int c = 0; c < r->ncols; c++) {
-        if (c) s += ",";
+    const int c0 = r->agg_first_col >= 0 ? r->agg_first_col : 0;  // aggregate rows print the aggregators' repr only (ProjectAggregateQueue.scala:48-50)
+    for (int c = c0; c < r->ncols; c++) {
+        if (c > c0) s += ",";
         const uint8_t* p = (const uint8_t*)r->h_cols[(size_t)c].p + (size_t)row * (size_t)r->widths[(size_t)c];
-        if (r->types[(size_t)c] == IMM3_COL_INT) {
+        if (r->types[(size_t)c] == IMM3_COL_COUNT) {
+            int64_t v;
+            std::memcpy(&v, p, 8);
+            s += std::to_string(v);  // Long.toString
+        } else if (r->types[(size_t)c] == IMM3_COL_DOUBLE) {
+            double v;
+            std::memcpy(&v, p, 8);
+            s += java_double_to_string_integral(v);
+        } else if (r->types[(size_t)c] == IMM3_COL_INT) {
             int32_t v;
             std::memcpy(&v, p, 4);
             s += std::to_string(v);

@@ -38,6 +38,7 @@ namespace imm3 {
 #include "k_blocks_filter.cuh"
 #include "k_blocks_prune.cuh"
 #include "k_comm.cuh"
+#include "k_agg.cuh"
 
 // =============================================================================================
 // Launchers
@@ -72,6 +73,7 @@ static cudaError_t configure_device() {
         IMM3_SET_SMEM(blocks_filter_kernel);
         IMM3_SET_SMEM(blocks_filter_quad_kernel);
         IMM3_SET_SMEM(block_stats_kernel);
+        IMM3_SET_SMEM(agg_kernel);
         IMM3_SET_SMEM(blocks_emit_kernel<true>);
         IMM3_SET_SMEM(blocks_emit_kernel<false>);
         IMM3_SET_SMEM(emit_general_kernel);
@@ -193,6 +195,33 @@ cudaError_t launch_blocks_prune(const PrunePlan& q, const uint64_t* row_start, l
     const long long groups = (nblocks + 31) / 32;
     const long long grid = std::max<long long>(1, std::min<long long>((groups + kComputeWarps - 1) / kComputeWarps, (long long)num_sms * 8));
     blocks_prune_kernel<<<(unsigned)grid, kComputeThreads, 0, stream>>>(q, row_start, nblocks, ntiles8, blk_cnt, tile_cnt, work);
+    return cudaGetLastError();
+}
+
+// count / min / max ... group by: empty table -> (filter kernel, launched by the caller) -> agg_kernel -> compaction.
+cudaError_t launch_agg_init(AggEntry* table, uint32_t slots, const AggPlan& a, unsigned int* counters, cudaStream_t stream) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    AggOps ops;
+    for (int i = 0; i < kMaxAggs; i++) ops.op[i] = i < a.naggs ? a.agg[i].op : 0;
+    ops.naggs = a.naggs;
+    agg_init_kernel<<<(slots + kComputeThreads - 1) / kComputeThreads, kComputeThreads, 0, stream>>>(table, slots, ops, counters);
+    return cudaGetLastError();
+}
+cudaError_t launch_agg(const AggPlan& a, const uint32_t* bitmap, const uint32_t* span_cnt, AggEntry* table, AggEntry* out, unsigned int* counters,
+                       const ScanCtrl* ctrl, int num_sms, cudaStream_t stream) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    const size_t smem = sizeof(AggShared) + (size_t)kComputeWarps * 1024 * 2;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, agg_kernel, kComputeThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorInvalidConfiguration;
+    const long long nspans = a.ntiles * 8;
+    const long long grid = std::max<long long>(1, std::min<long long>((nspans + kComputeWarps - 1) / kComputeWarps, (long long)num_sms * occ));
+    agg_kernel<<<(unsigned)grid, kComputeThreads, smem, stream>>>(a, bitmap, span_cnt, table, counters + 1, ctrl);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    agg_compact_kernel<<<(a.table_slots + kComputeThreads - 1) / kComputeThreads, kComputeThreads, 0, stream>>>(table, a.table_slots, out, counters);
     return cudaGetLastError();
 }
 

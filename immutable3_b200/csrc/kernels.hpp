@@ -26,6 +26,9 @@ cudaError_t emit_stream_occupancy(size_t dyn_smem, int* blocks_per_sm);
 cudaError_t launch_emit_stream(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* span_cnt, const uint32_t* tile_cnt,
                                const unsigned long long* tile_off, long long nsub, int ring, int stage_bytes, int dense_mode, int grid,
                                size_t dyn_smem, ScanCtrl* ctrl, bool pdl, cudaStream_t stream);
+cudaError_t launch_agg_init(AggEntry* table, uint32_t slots, const AggPlan& a, unsigned int* counters, cudaStream_t stream);
+cudaError_t launch_agg(const AggPlan& a, const uint32_t* bitmap, const uint32_t* span_cnt, AggEntry* table, AggEntry* out, unsigned int* counters,
+                       const ScanCtrl* ctrl, int num_sms, cudaStream_t stream);
 long long scan_inline_max_tiles();
 cudaError_t launch_offset_scan(const uint32_t* tile_cnt, unsigned long long* tile_off, long long ntiles, long long limit, uint32_t epoch,
                                unsigned long long* partials, ScanCtrl* ctrl, cudaStream_t stream);

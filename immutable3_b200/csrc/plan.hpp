@@ -104,6 +104,38 @@ struct PrunePlan {
     int32_t group_shift;  // work-list granularity: tiles of 1 << group_shift blocks (5: quad filter kernel, 3: blocks_filter_kernel)
 };
 
+// Aggregation (k_agg.cuh; ProjectAggOp, ProjectAggregate.scala:115-226): count / min / max over the rows the filter
+// kernel selected, grouped by up to kMaxGroupCols dense columns whose cells pack into at most 7 key bytes.
+constexpr int kMaxAggs = 8;
+constexpr int kMaxGroupCols = 4;
+constexpr int kAggSmemSlots = 1024;       // per-CTA hash table (groups are merged into the global table when the CTA is done)
+enum AggOp : int32_t { kAggCount = 0, kAggMin = 1, kAggMax = 2 };
+struct AggCol {
+    const uint8_t* base;  // device arena of the aggregated column (dense INT / TINYINT; unused for COUNT)
+    int32_t width;        // 4 or 1
+    int32_t op;           // AggOp
+};
+struct GroupCol {
+    const uint8_t* base;
+    int32_t width;        // bytes per cell
+    int32_t key_shift;    // bit position of this column's cell inside the packed 64-bit key
+};
+struct AggPlan {
+    int64_t nrows;
+    int64_t ntiles;        // 8192-row tiles of the row-space bitmap
+    int32_t naggs, ngroup;
+    uint32_t table_slots;  // global hash table size (power of two)
+    int32_t pad;
+    AggCol agg[kMaxAggs];
+    GroupCol group[kMaxGroupCols];
+};
+// One group in the global table / in the compacted result.  val[i]: COUNT -> the count, MIN / MAX -> the extreme as int64.
+struct AggEntry {
+    unsigned long long key;        // packed group cells, ~0 = empty slot
+    unsigned long long first_row;  // canonical ordinal of the group's first selected row (groups are reported in that order)
+    long long val[kMaxAggs];
+};
+
 // Device-resident control block of one db (reset by the last CTA of every launch).
 struct ScanCtrl {
     unsigned int ticket;   // next tile to hand out

@@ -98,6 +98,44 @@ class Project:
     limit: int = 0
 
 
+# Aggregates (Query.scala:17-27).  Sum / Avg exist in the ADT and the parser, but Engine.resolveProjectOp throws on them
+# (Engine.scala:153); they are accepted here only to come back as IMM3_ERR_UNSUPPORTED.
+@dataclass(frozen=True)
+class Sum:
+    col: str
+    alias: Optional[str] = None
+
+
+@dataclass(frozen=True)
+class Avg:
+    col: str
+    alias: Optional[str] = None
+
+
+@dataclass(frozen=True)
+class Min:
+    col: str
+    alias: Optional[str] = None
+
+
+@dataclass(frozen=True)
+class Max:
+    col: str
+    alias: Optional[str] = None
+
+
+@dataclass(frozen=True)
+class Count:
+    col: str
+    alias: Optional[str] = None
+
+
+@dataclass(frozen=True)
+class ProjectAgg:
+    aggs: Sequence
+    groupBy: Sequence[str] = ()
+
+
 @dataclass(frozen=True)
 class Query:
     table: str
@@ -155,7 +193,8 @@ class Row(tuple):
     __str__ = __repr__
 
 
-_NP = {L.COL_INT: np.dtype("<i4"), L.COL_TINYINT: np.dtype("i1")}
+_NP = {L.COL_INT: np.dtype("<i4"), L.COL_TINYINT: np.dtype("i1"), L.COL_COUNT: np.dtype("<i8"), L.COL_DOUBLE: np.dtype("<f8")}
+_AGG_OPS = {"Count": L.AGG_COUNT, "Min": L.AGG_MIN, "Max": L.AGG_MAX, "Sum": L.AGG_SUM, "Avg": L.AGG_AVG}
 
 
 class Result:
@@ -265,7 +304,7 @@ class Result:
         types = [self.col_type(c) for c in range(self.ncols)]
         for i in range(self.nrows):
             yield Row(
-                cols[c][i].decode("utf-8", "replace") if types[c] == L.COL_STRING else int(cols[c][i])
+                cols[c][i].decode("utf-8", "replace") if types[c] == L.COL_STRING else (float(cols[c][i]) if types[c] == L.COL_DOUBLE else int(cols[c][i]))
                 for c in range(len(cols))
             )
 
@@ -462,11 +501,30 @@ class Engine:
 
     def execute(self, query: Query) -> Result:
         """Engine.execute: the rows of the query in canonical order (iterate for Row objects)."""
+        if isinstance(query.project, ProjectAgg):
+            return self._call_agg(query)
         return self._call(self._lib.imm3_query, query)
 
     def begin(self, query: Query) -> Result:
         """First phase of a sharded query: kernels done, local match count known, nothing fetched."""
+        if isinstance(query.project, ProjectAgg):
+            return self._call_agg(query)
         return self._call(self._lib.imm3_query_begin, query)
+
+    def _call_agg(self, query: Query) -> Result:
+        """Engine.execute, ProjectAgg branch (Engine.scala:200-232): one row per group, group columns then aggregates."""
+        preds, npreds, keep = _pred_array(flatten_select(query.select))
+        aggs = list(query.project.aggs)
+        arr = (L.Agg * max(1, len(aggs)))()
+        for i, a in enumerate(aggs):
+            arr[i].col = a.col.encode()
+            arr[i].op = _AGG_OPS[type(a).__name__]
+        groups = L.cstr_array(list(query.project.groupBy))
+        out = C.c_void_p()
+        L.check(self._lib.imm3_query_agg(self.sm.handle, query.table.encode(), preds, npreds, arr, len(aggs),
+                                         C.cast(groups, C.POINTER(C.c_char_p)), len(query.project.groupBy), C.byref(out)))
+        del keep
+        return Result(out, self._lib, self.sm)
 
     def execute_sql(self, sql: str) -> Result:
         """Same text as `SqlCli -q` (SQLParser.scala)."""

@@ -50,7 +50,11 @@ typedef enum imm3_status {
 } imm3_status;
 
 /* ColumnType enumeration, Column.scala:13-16 */
-typedef enum imm3_column_type { IMM3_COL_INT = 0, IMM3_COL_TINYINT = 1, IMM3_COL_STRING = 2 } imm3_column_type;
+typedef enum imm3_column_type {
+    IMM3_COL_INT = 0, IMM3_COL_TINYINT = 1, IMM3_COL_STRING = 2,
+    IMM3_COL_COUNT = 3,   /* aggregate results only: int64 (CountAggr, ProjectAggregate.scala:21-35)                 */
+    IMM3_COL_DOUBLE = 4   /* aggregate results only: IEEE double (Min/MaxDoubleAggr, ProjectAggregate.scala:37-59)    */
+} imm3_column_type;
 
 /* CodecType enumeration (same order), Codec.scala:20-23 */
 typedef enum imm3_codec {
@@ -173,6 +177,28 @@ int imm3_result_fetch(imm3_result* r, int64_t nrows);
  * buffers) must stay open until the wait has returned. */
 int imm3_result_fetch_async(imm3_result* r, int64_t nrows);
 int imm3_result_wait(imm3_result* r);
+
+/* ---- Scan -> Select* -> ProjectAgg: Engine.execute ProjectAgg branch (Engine.scala:200-232), ProjectAggOp
+ *      (ProjectAggregate.scala:115-226), ProjectAggregateQueueOp (ProjectAggregateQueue.scala:9-54) -------------------
+ * count / min / max over the selected rows, grouped by `group_cols` (none = one group, reported only if a row was
+ * selected).  The aggregate kinds are the ones Engine.resolveProjectOp accepts (Engine.scala:130-156): Min / Max on INT
+ * and TINYINT columns (the reference widens to Double: results are IMM3_COL_DOUBLE), Count on any column
+ * (IMM3_COL_COUNT); Sum / Avg throw there ("Unknown Aggregate type") and return IMM3_ERR_UNSUPPORTED here, as do Min / Max
+ * on STRING columns (the reference maps both to MaxStringAggr, Engine.scala:137,147).
+ * Result: one row per group, in the order the groups first appear in canonical row order (what the reference's
+ * LinkedHashMaps produce with one worker); columns = the group columns (their own types), then one column per aggregate in
+ * select-list order, named <col>_count / <col>_min / <col>_max (Engine.scala:136-152).  imm3_result_format_row prints the
+ * aggregates only, as the reference does (Row of the aggregators' repr, ProjectAggregateQueue.scala:48-50).
+ * Library limits (IMM3_ERR_UNSUPPORTED): group cells must pack into 7 bytes; aggregate and group columns must be dense;
+ * predicates on a sorted-int-codec column cannot be combined with aggregation yet.  On a sharded handle the result holds
+ * this rank's groups (partials); the caller merges ranks in rank order (count: sum, min / max: min / max). */
+typedef enum imm3_agg_op { IMM3_AGG_COUNT = 0, IMM3_AGG_MIN = 1, IMM3_AGG_MAX = 2, IMM3_AGG_SUM = 3, IMM3_AGG_AVG = 4 } imm3_agg_op;
+typedef struct imm3_agg {
+    const char* col;
+    int32_t op;  /* imm3_agg_op */
+} imm3_agg;
+int imm3_query_agg(imm3_db* db, const char* table, const imm3_pred* preds, int npreds, const imm3_agg* aggs, int naggs,
+                   const char* const* group_cols, int ngroup, imm3_result** out);
 
 /* Same query text the reference CLI takes (SQLParser.scala:8-129; SqlCli.scala:60). */
 int imm3_query_sql(imm3_db* db, const char* sql, imm3_result** out);

@@ -1374,3 +1374,132 @@ int orc_synth_write(const char* data_dir, const char* table, int64_t nrows, int3
     for (int i = 1; i < nthreads; i++) pthread_join(th[i], NULL);
     return rc ? fail(rc, "orc_synth_write failed (status %d)", rc) : 0;
 }
+
+/* ===================================================================================== */
+/* Engine.execute, ProjectAgg branch (Engine.scala:130-156, 200-232)                        */
+/*   ProjectAggOp.ProjectAggIterator.runAggs   ProjectAggregate.scala:160-222                */
+/*     per batch, per SELECTED row: key = group values joined by "_" (:152,166-170);        */
+/*     resultMap.getOrElseUpdate(key, fresh aggregators) - a LinkedHashMap, so groups keep  */
+/*     the order of their first row (:128,178); CountAggr.add counts the row (:21-24),      */
+/*     Min/MaxDoubleAggr.add(value.toDouble) (:37-59,176-178,190-192)                       */
+/*   ProjectAggregateQueueOp.init              ProjectAggregateQueue.scala:21-45            */
+/*     merges the per-segment maps in arrival order (one worker: segment order) with        */
+/*     combine(): counts add, min/max of min/max                                            */
+/* Net effect with one worker: one group per distinct key in order of first appearance in   */
+/* canonical row order.  Output row of the reference = the aggregators' repr only           */
+/* (ProjectAggregateQueue.scala:48-50) - in the iteration order of a mutable.HashMap keyed  */
+/* by alias; INTENDED order (used here): the select list's.  Min on a STRING column is      */
+/* resolved to MaxStringAggr (Engine.scala:147) and Min/MaxStringAggr are not what this     */
+/* restatement covers: ORC_ERR_UNSUPPORTED, as are Sum / Avg (Engine.scala:153).            */
+/* Result columns: the group columns, then per aggregate COUNT -> int64, MIN/MAX -> double. */
+/* ===================================================================================== */
+enum { ORC_COL_COUNT = 3, ORC_COL_DOUBLE = 4 };
+
+int orc_query_agg(orc_db* db, const char* table, const orc_pred* preds, int npreds, const orc_agg* aggs, int naggs,
+                  const char* const* group_cols, int ngroup, int nthreads, int seg_begin, int seg_end, orc_result** out) {
+    if (naggs < 1 || naggs > 16 || ngroup < 0 || ngroup > 8) return fail(ORC_ERR_INVALID_ARG, "orc_query_agg: bad counts");
+    table_t* t = get_table(db, table);
+    if (!t) return fail(ORC_ERR_NOT_FOUND, "Table %s does not exist in SegmentManager", table);
+    /* usedColumns = aggs' columns ++ group columns (Engine.scala:97-101): project them all, unlimited */
+    const char* proj[24];
+    for (int g = 0; g < ngroup; g++) proj[g] = group_cols[g];
+    for (int a = 0; a < naggs; a++) {
+        proj[ngroup + a] = aggs[a].col;
+        if (aggs[a].op != ORC_AGG_COUNT && aggs[a].op != ORC_AGG_MIN && aggs[a].op != ORC_AGG_MAX)
+            return fail(ORC_ERR_UNSUPPORTED, "Unknown Aggregate type");
+        col_t* c = get_column(t, aggs[a].col);
+        if (c && c->ctype == ORC_COL_STRING && aggs[a].op != ORC_AGG_COUNT) return fail(ORC_ERR_UNSUPPORTED, "min / max on a STRING column");
+    }
+    orc_result* rows = NULL;
+    int rc = orc_query(db, table, preds, npreds, proj, ngroup + naggs, 0, nthreads, seg_begin, seg_end, &rows);
+    if (rc) return rc;
+    const int64_t n = rows->nrows;
+    int keyw = 0;
+    for (int g = 0; g < ngroup; g++) keyw += rows->width[g];
+    /* open-addressing map: key bytes -> group index, groups appended in first-appearance order */
+    int64_t cap = 1024, ngroups = 0;
+    int64_t* slot = (int64_t*)malloc((size_t)cap * 8);
+    for (int64_t i = 0; i < cap; i++) slot[i] = -1;
+    uint8_t* gkeys = NULL;
+    int64_t* cnt = NULL;
+    double* val = NULL; /* [group][agg] */
+    int64_t gcap = 0;
+    uint8_t key[256];
+    for (int64_t r = 0; r < n; r++) {
+        int at = 0;
+        for (int g = 0; g < ngroup; g++) {
+            memcpy(key + at, rows->cols[g] + r * rows->width[g], (size_t)rows->width[g]);
+            at += rows->width[g];
+        }
+        uint64_t h = 1469598103934665603ull;
+        for (int i = 0; i < keyw; i++) h = (h ^ key[i]) * 1099511628211ull;
+        int64_t gi = -1;
+        for (int64_t p = (int64_t)(h & (uint64_t)(cap - 1));; p = (p + 1) & (cap - 1)) {
+            if (slot[p] < 0) {
+                if (ngroups == gcap) {
+                    gcap = gcap ? gcap * 2 : 256;
+                    gkeys = (uint8_t*)realloc(gkeys, (size_t)gcap * (size_t)(keyw ? keyw : 1));
+                    cnt = (int64_t*)realloc(cnt, (size_t)gcap * (size_t)naggs * 8);
+                    val = (double*)realloc(val, (size_t)gcap * (size_t)naggs * 8);
+                }
+                gi = ngroups++;
+                slot[p] = gi;
+                memcpy(gkeys + gi * keyw, key, (size_t)keyw);
+                for (int a = 0; a < naggs; a++) { /* aggregator.make: fresh state (ProjectAggregate.scala:21,38,50) */
+                    cnt[gi * naggs + a] = 0;
+                    val[gi * naggs + a] = aggs[a].op == ORC_AGG_MAX ? -1.7976931348623157e308 : 1.7976931348623157e308; /* Double.MinValue / MaxValue */
+                }
+                break;
+            }
+            if (!memcmp(gkeys + slot[p] * keyw, key, (size_t)keyw)) { gi = slot[p]; break; }
+        }
+        for (int a = 0; a < naggs; a++) {
+            const int c = ngroup + a;
+            if (aggs[a].op == ORC_AGG_COUNT) { cnt[gi * naggs + a]++; continue; }
+            const double v = rows->ctype[c] == ORC_COL_INT ? (double)orc_bytes_to_int(rows->cols[c] + r * 4) : (double)(int8_t)rows->cols[c][r];
+            double* m = &val[gi * naggs + a];
+            if (aggs[a].op == ORC_AGG_MAX ? v > *m : v < *m) *m = v;
+        }
+        if (ngroups * 2 > cap) { /* grow the index */
+            cap *= 2;
+            slot = (int64_t*)realloc(slot, (size_t)cap * 8);
+            for (int64_t i = 0; i < cap; i++) slot[i] = -1;
+            for (int64_t g2 = 0; g2 < ngroups; g2++) {
+                uint64_t h2 = 1469598103934665603ull;
+                for (int i = 0; i < keyw; i++) h2 = (h2 ^ gkeys[g2 * keyw + i]) * 1099511628211ull;
+                int64_t p = (int64_t)(h2 & (uint64_t)(cap - 1));
+                while (slot[p] >= 0) p = (p + 1) & (cap - 1);
+                slot[p] = g2;
+            }
+        }
+    }
+    orc_result* res = (orc_result*)calloc(1, sizeof *res);
+    res->ncols = ngroup + naggs;
+    res->nrows = ngroups;
+    res->nmatched = n;
+    int at = 0;
+    for (int g = 0; g < ngroup; g++) {
+        res->ctype[g] = rows->ctype[g];
+        res->width[g] = rows->width[g];
+        res->cols[g] = (uint8_t*)malloc((size_t)(ngroups ? ngroups : 1) * (size_t)rows->width[g]);
+        for (int64_t i = 0; i < ngroups; i++) memcpy(res->cols[g] + i * rows->width[g], gkeys + i * keyw + at, (size_t)rows->width[g]);
+        at += rows->width[g];
+    }
+    for (int a = 0; a < naggs; a++) {
+        const int c = ngroup + a;
+        res->ctype[c] = aggs[a].op == ORC_AGG_COUNT ? ORC_COL_COUNT : ORC_COL_DOUBLE;
+        res->width[c] = 8;
+        res->cols[c] = (uint8_t*)malloc((size_t)(ngroups ? ngroups : 1) * 8);
+        for (int64_t i = 0; i < ngroups; i++) {
+            if (aggs[a].op == ORC_AGG_COUNT) memcpy(res->cols[c] + i * 8, &cnt[i * naggs + a], 8);
+            else memcpy(res->cols[c] + i * 8, &val[i * naggs + a], 8);
+        }
+    }
+    free(slot);
+    free(gkeys);
+    free(cnt);
+    free(val);
+    orc_result_free(rows);
+    *out = res;
+    return 0;
+}

@@ -89,6 +89,17 @@ int orc_result_ref_throw(const orc_result* r, int64_t* rows_before);
 int orc_result_format_row(const orc_result* r, int64_t row, char* buf, size_t buflen); /* Record.scala:13 */
 void orc_result_free(orc_result* r);
 
+/* ---- Engine.execute, ProjectAgg branch: count / min / max ... group by (ProjectAggregate.scala:115-226,
+ *      ProjectAggregateQueue.scala:9-54).  One row per group in first-appearance canonical order; columns = the group
+ *      columns, then per aggregate COUNT -> int64 (column type 3), MIN / MAX -> double (column type 4). ---- */
+enum { ORC_AGG_COUNT = 0, ORC_AGG_MIN = 1, ORC_AGG_MAX = 2 };
+typedef struct orc_agg {
+    const char* col;
+    int32_t op;
+} orc_agg;
+int orc_query_agg(orc_db* db, const char* table, const orc_pred* preds, int npreds, const orc_agg* aggs, int naggs,
+                  const char* const* group_cols, int ngroup, int nthreads, int seg_begin, int seg_end, orc_result** out);
+
 /* Selection bitmap of the conjunction alone, canonical row order, bit i of word w = row 32w+i. */
 int orc_filter_bitmap(orc_db* db, const char* table, const orc_pred* preds, int npreds,
                       int seg_begin, int seg_end, uint32_t** words, int64_t* nwords, int64_t* nselected);

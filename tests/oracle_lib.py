@@ -15,6 +15,14 @@ OP_GT, OP_LT, OP_EQ, OP_MATCH, OP_NOTMATCH, OP_NOOP = 1, 2, 3, 4, 5, 6
 COL_INT, COL_TINYINT, COL_STRING = 0, 1, 2
 
 
+class OrcAgg(C.Structure):
+    _fields_ = [("col", C.c_char_p), ("op", C.c_int32)]
+
+
+AGG_COUNT, AGG_MIN, AGG_MAX = 0, 1, 2
+COL_COUNT, COL_DOUBLE = 3, 4
+
+
 class OrcPred(C.Structure):
     _fields_ = [("col", C.c_char_p), ("op", C.c_int32), ("num", C.c_double), ("strs", C.POINTER(C.c_char_p)), ("nstrs", C.c_int32)]
 
@@ -45,6 +53,8 @@ def lib():
             "orc_segment_file_id": (C.c_int, [P, C.c_char_p, C.c_int]),
             "orc_table_nrows": (C.c_int64, [P, C.c_char_p, C.c_int, C.c_int]),
             "orc_query": (C.c_int, [P, C.c_char_p, C.POINTER(OrcPred), C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(P)]),
+            "orc_query_agg": (C.c_int, [P, C.c_char_p, C.POINTER(OrcPred), C.c_int, C.POINTER(OrcAgg), C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.POINTER(P)]),
             "orc_result_nrows": (C.c_int64, [P]),
             "orc_result_nmatched": (C.c_int64, [P]),
             "orc_result_ncols": (C.c_int, [P]),
@@ -99,7 +109,7 @@ def _preds(preds):
     return arr, n, keep
 
 
-_NP = {COL_INT: np.dtype("<i4"), COL_TINYINT: np.dtype("i1")}
+_NP = {COL_INT: np.dtype("<i4"), COL_TINYINT: np.dtype("i1"), COL_COUNT: np.dtype("<i8"), COL_DOUBLE: np.dtype("<f8")}
 
 
 class OracleResult:
@@ -168,6 +178,36 @@ class Oracle:
             res = OracleResult(cols, types, widths, self._l.orc_result_nmatched(out), thr, rb.value, text)
             if not cols:
                 res.nrows = nrows
+            return res
+        finally:
+            self._l.orc_result_free(out)
+
+    def query_agg(self, table, preds, aggs, group_by=(), nthreads=1, seg_begin=0, seg_end=-1) -> OracleResult:
+        """aggs: list of (op, col) with op in AGG_COUNT / AGG_MIN / AGG_MAX.  Columns of the result: the group columns, then
+        one per aggregate (count: int64, min / max: float64), one row per group in first-appearance order."""
+        arr, n, keep = _preds(preds)
+        ag = (OrcAgg * max(1, len(aggs)))()
+        for i, (op, col) in enumerate(aggs):
+            ag[i].op, ag[i].col = op, col.encode()
+        gb = (C.c_char_p * max(1, len(group_by)))(*[g.encode() for g in group_by])
+        out = C.c_void_p()
+        _check(self._l.orc_query_agg(self._h, table.encode(), arr, n, ag, len(aggs), C.cast(gb, C.POINTER(C.c_char_p)), len(group_by), nthreads,
+                                     seg_begin, seg_end, C.byref(out)))
+        try:
+            nrows = self._l.orc_result_nrows(out)
+            cols, types, widths = [], [], []
+            for c in range(self._l.orc_result_ncols(out)):
+                t, w = self._l.orc_result_col_type(out, c), self._l.orc_result_col_width(out, c)
+                dt = _NP.get(t, np.dtype(f"S{w}"))
+                if nrows:
+                    raw = (C.c_uint8 * (nrows * w)).from_address(self._l.orc_result_col_data(out, c))
+                    cols.append(np.frombuffer(raw, dtype=dt, count=nrows).copy())
+                else:
+                    cols.append(np.empty(0, dt))
+                types.append(t)
+                widths.append(w)
+            res = OracleResult(cols, types, widths, self._l.orc_result_nmatched(out), 0, 0, [])
+            res.nrows = nrows
             return res
         finally:
             self._l.orc_result_free(out)
