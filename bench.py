@@ -520,10 +520,12 @@ def main():
     head, clocks, ctx = measure(args.workload, total, args.steps, args.warmup, sample_clocks=True)
     sm, eng, d, table, tinfo, query, prep, local_rows, take = ctx
     open_s, gen_s = opened[(WORKLOADS[args.workload][1], total)][5:7]
-    st0, st1 = stage_times(eng, prep)
+    agg_head = args.workload in AGG_SPECS
+    st0, st1 = (None, None) if agg_head else stage_times(eng, prep)
     kind = WORKLOADS[args.workload][1]
     on_pfor_filter = kind == "pfor" and any(l.col == "id" for l in flatten_select(query.select))
-    kname = ("blocks_filter_kernel (sorted-int codec, warp per block) -> blocks_emit_kernel" if on_pfor_filter else
+    kname = ("filter_kernel -> agg_kernel -> agg_compact_kernel" if agg_head else
+             "blocks_filter_quad_kernel (sorted-int codec, lane = block x super-block) [-> offset_scan_kernel] -> blocks_emit_kernel" if on_pfor_filter else
              "filter_kernel (row space) -> blocks_emit_kernel" if kind == "pfor" else "filter_kernel -> emit_stream_kernel | emit_kernel")
     roofline = head.pop("roofline")
     tr = recorded_traffic(f"{args.workload}_{total}") if world == 1 else None
@@ -532,7 +534,7 @@ def main():
                      "traffic": tr["bytes"] if tr else None, "traffic_source": ("ncu capture " + tr["source"]) if tr else None})
 
     # ---- e2e through the C ABI ----
-    used_cols = sorted({l.col for l in flatten_select(query.select)} | set(query.project.cols))
+    used_cols = sorted({l.col for l in flatten_select(query.select)} | (set() if agg_head else set(query.project.cols)))
     used_bytes = allsum(sum(c.encoded_bytes for c in tinfo.columns if c.name in used_cols))
 
     def e2e_pass(reupload: bool):
@@ -567,7 +569,7 @@ def main():
         return allmax([dt])[0] / args.steps, allsum(d2h)
 
     e2e = e2e_res = None
-    if not args.no_e2e:
+    if not args.no_e2e and not agg_head:
         sec_res, d2h_b = e2e_pass(False)
         sec_cold, _ = e2e_pass(True)
         e2e = {"value": total / sec_cold, "unit": "rows/s", "h2d_bytes_per_step": used_bytes, "d2h_bytes_per_step": d2h_b,

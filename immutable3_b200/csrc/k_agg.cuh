@@ -26,24 +26,27 @@ __device__ __forceinline__ uint32_t agg_hash(unsigned long long k) {
     return (uint32_t)k;
 }
 
-struct AggShared {
-    unsigned long long key[kAggSmemSlots];
-    unsigned long long first_row[kAggSmemSlots];
-    long long val[kMaxAggs][kAggSmemSlots];
+// Per-WARP hash tables in shared memory: a group is updated by one lane per 32-row step (the leader of the lanes that hold
+// its key), so inside a warp's own table the values need no atomics at all - only claiming a fresh slot does (two new keys
+// may want the same slot in one step).  With one table per CTA, a low-cardinality group-by (51 states) serialised every
+// warp of the SM on the same few shared-memory words: 5.2 ms for the reference's example on 100 M rows.
+constexpr int kAggWarpSlots = 128;
+struct AggWarpTable {
+    unsigned long long key[kAggWarpSlots];
+    unsigned long long first_row[kAggWarpSlots];
+    int val[kMaxAggs][kAggWarpSlots];  // 32-bit: native shared-memory atomics (a warp counts far fewer than 2^32 rows; min / max inputs are int32 / int8)
 };
 
-// Find or claim the slot of `key` in a table of `slots` entries (power of two).  Returns the slot, or -1 if the probe
-// sequence is exhausted (shared table full: the caller goes to the global table).
-template <typename KeyPtr>
-__device__ __forceinline__ int agg_find_slot(KeyPtr keys, uint32_t slots, unsigned long long key, int max_probe) {
-    uint32_t h = agg_hash(key) & (slots - 1);
-    for (int p = 0; p < max_probe; p++, h = (h + 1) & (slots - 1)) {
+// Slot of `key` in a shared-memory table (claimed if new), -1 if `max_probe` slots in a row are taken by other keys.
+__device__ __forceinline__ int agg_smem_slot(unsigned long long* keys, unsigned long long key, int max_probe) {
+    uint32_t h = agg_hash(key) & (kAggWarpSlots - 1);
+    for (int p = 0; p < max_probe; p++, h = (h + 1) & (kAggWarpSlots - 1)) {
         unsigned long long cur = keys[h];
-        if (cur == key) return (int)h;
         if (cur == kAggEmpty) {
-            cur = atomicCAS(&keys[h], kAggEmpty, key);
-            if (cur == kAggEmpty || cur == key) return (int)h;
+            const unsigned long long old = atomicCAS(&keys[h], kAggEmpty, key);
+            cur = old == kAggEmpty ? key : old;
         }
+        if (cur == key) return (int)h;
     }
     return -1;
 }
@@ -70,12 +73,23 @@ __device__ __forceinline__ void agg_update(long long* v, int op, long long x) {
 }
 __device__ __forceinline__ long long agg_identity(int op) { return op == kAggCount ? 0ll : (op == kAggMin ? LLONG_MAX : LLONG_MIN); }
 
+__device__ __forceinline__ void agg_to_global(AggEntry* table, uint32_t slots, unsigned int* overflow, unsigned long long key, unsigned long long fr,
+                                              const long long* x, const AggCol* aggs, int naggs) {
+    const int gs = agg_global_slot(table, slots, key);
+    if (gs < 0) {
+        atomicExch(overflow, 1u);
+        return;
+    }
+    atomicMin(&table[gs].first_row, fr);
+    for (int a = 0; a < naggs; a++) agg_update(&table[gs].val[a], aggs[a].op, x[a]);
+}
+
 __global__ void __launch_bounds__(kComputeThreads, 2) agg_kernel(const __grid_constant__ AggPlan A, const uint32_t* __restrict__ bitmap,
                                                                   const uint32_t* __restrict__ span_cnt, AggEntry* __restrict__ table,
                                                                   unsigned int* __restrict__ overflow, const ScanCtrl* ctrl) {
     extern __shared__ __align__(128) uint8_t agg_smem[];
-    AggShared& S = *reinterpret_cast<AggShared*>(agg_smem);
-    unsigned short* const sel_all = reinterpret_cast<unsigned short*>(agg_smem + sizeof(AggShared));
+    AggWarpTable* const tables = reinterpret_cast<AggWarpTable*>(agg_smem);
+    unsigned short* const sel_all = reinterpret_cast<unsigned short*>(agg_smem + kComputeWarps * sizeof(AggWarpTable));
     __shared__ AggCol s_agg[kMaxAggs];
     __shared__ GroupCol s_group[kMaxGroupCols];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -86,12 +100,13 @@ __global__ void __launch_bounds__(kComputeThreads, 2) agg_kernel(const __grid_co
     for (int i = 0; i < kMaxGroupCols; i++)
         if (tid == 32 + i) s_group[i] = A.group[i];
     __syncthreads();
-    for (int i = tid; i < kAggSmemSlots; i += kComputeThreads) {
-        S.key[i] = kAggEmpty;
-        S.first_row[i] = ~0ull;
-        for (int a = 0; a < A.naggs; a++) S.val[a][i] = agg_identity(s_agg[a].op);
+    AggWarpTable& T = tables[warp];
+    for (int i = lane; i < kAggWarpSlots; i += 32) {
+        T.key[i] = kAggEmpty;
+        T.first_row[i] = ~0ull;
+        for (int a = 0; a < A.naggs; a++) T.val[a][i] = s_agg[a].op == kAggCount ? 0 : (s_agg[a].op == kAggMin ? INT_MAX : INT_MIN);
     }
-    __syncthreads();
+    __syncwarp();
     asm volatile("griddepcontrol.wait;" ::: "memory");  // the filter kernel's bitmap and counts are final
     if (__ldcg(&ctrl->total) != 0ull) {
         unsigned short* const sel_w = sel_all + warp * 1024;
@@ -112,7 +127,10 @@ __global__ void __launch_bounds__(kComputeThreads, 2) agg_kernel(const __grid_co
                     const GroupCol gc = s_group[gcol];
                     unsigned long long cell = 0;
                     const uint8_t* src = gc.base + row * gc.width;
-                    for (int b = 0; b < gc.width; b++) cell |= (unsigned long long)__ldg(src + b) << (8 * b);
+                    if (gc.width == 2) cell = __ldg(reinterpret_cast<const unsigned short*>(src));
+                    else if (gc.width == 4) cell = __ldg(reinterpret_cast<const uint32_t*>(src));
+                    else
+                        for (int b = 0; b < gc.width; b++) cell |= (unsigned long long)__ldg(src + b) << (8 * b);
                     key |= cell << gc.key_shift;
                 }
                 long long x[kMaxAggs];
@@ -125,53 +143,60 @@ __global__ void __launch_bounds__(kComputeThreads, 2) agg_kernel(const __grid_co
                         else x[a] = ac.width == 4 ? (long long)(int)__ldg(reinterpret_cast<const uint32_t*>(ac.base) + row) : (long long)(signed char)__ldg(ac.base + row);
                     }
                 }
-                // lanes with the same key combine first: one table update per distinct key of the 32 rows
-                const unsigned active = __ballot_sync(0xFFFFFFFFu, live);
+                // every lane updates its group in the warp's table with native 32-bit shared-memory atomics.  (Combining the lanes
+                // of a key first - MATCH.ANY + REDUX per distinct key - was 10x slower: with ~20 distinct keys per 32 rows the
+                // partial-mask reductions run one after the other.)
                 if (live) {
-                    const unsigned peers = __match_any_sync(active, key);
-                    const int leader = __ffs((int)peers) - 1;
-                    unsigned long long fr = (unsigned long long)row;
-                    // (rows of a selection vector ascend with the lane: the leader - lowest lane - holds the smallest row)
+                    const int slot = agg_smem_slot(T.key, key, 16);
+                    if (slot >= 0) {
+                        // rows reach a warp in ascending order: only the step that creates the group can lower first_row
+                        if ((unsigned long long)row < *reinterpret_cast<volatile unsigned long long*>(&T.first_row[slot])) atomicMin(&T.first_row[slot], (unsigned long long)row);
 #pragma unroll
-                    for (int a = 0; a < kMaxAggs; a++) {
-                        if (a < A.naggs) {
-                            const int op = s_agg[a].op;
-                            if (op == kAggCount) x[a] = (long long)__popc(peers);
-                            else {
-                                // 64-bit values: reduce the (int32-range) payload as 32-bit
-                                const int v32 = (int)x[a];
-                                x[a] = op == kAggMin ? (long long)__reduce_min_sync(peers, v32) : (long long)__reduce_max_sync(peers, v32);
+                        for (int a = 0; a < kMaxAggs; a++) {
+                            if (a < A.naggs) {
+                                const int op = s_agg[a].op;
+                                if (op == kAggCount) atomicAdd(reinterpret_cast<unsigned int*>(&T.val[a][slot]), 1u);
+                                else if (op == kAggMin) atomicMin(&T.val[a][slot], (int)x[a]);
+                                else atomicMax(&T.val[a][slot], (int)x[a]);
                             }
                         }
-                    }
-                    if (lane == leader) {
-                        int slot = agg_find_slot(S.key, kAggSmemSlots, key, 64);
-                        if (slot >= 0) {
-                            atomicMin(&S.first_row[slot], fr);
-                            for (int a = 0; a < A.naggs; a++) agg_update(&S.val[a][slot], s_agg[a].op, x[a]);
-                        } else {
-                            // the CTA's table is full: straight to the global table
-                            const int gs = agg_global_slot(table, A.table_slots, key);
-                            if (gs < 0) atomicExch(overflow, 1u);
-                            else {
-                                atomicMin(&table[gs].first_row, fr);
-                                for (int a = 0; a < A.naggs; a++) agg_update(&table[gs].val[a], s_agg[a].op, x[a]);
-                            }
-                        }
+                    } else {
+                        agg_to_global(table, A.table_slots, overflow, key, (unsigned long long)row, x, s_agg, A.naggs);  // the warp's table is full
                     }
                 }
             }
         }
     }
-    // merge the CTA's groups into the global table
+    // the CTA's warps fold their tables into warp 0's (shared-memory atomics now: several writers), which goes to the global table
     __syncthreads();
-    for (int i = tid; i < kAggSmemSlots; i += kComputeThreads) {
-        const unsigned long long key = S.key[i];
+    AggWarpTable& T0 = tables[0];
+    if (warp > 0) {
+        for (int i = lane; i < kAggWarpSlots; i += 32) {
+            const unsigned long long key = T.key[i];
+            if (key == kAggEmpty) continue;
+            long long x[kMaxAggs];
+            for (int a = 0; a < A.naggs; a++) x[a] = s_agg[a].op == kAggCount ? (long long)(unsigned int)T.val[a][i] : (long long)T.val[a][i];
+            const int slot = agg_smem_slot(T0.key, key, kAggWarpSlots);
+            if (slot >= 0) {
+                atomicMin(&T0.first_row[slot], T.first_row[i]);
+                for (int a = 0; a < A.naggs; a++) {
+                    const int op = s_agg[a].op;
+                    if (op == kAggCount) atomicAdd(reinterpret_cast<unsigned int*>(&T0.val[a][slot]), (unsigned int)T.val[a][i]);  // (a CTA counts < 2^32 rows)
+                    else if (op == kAggMin) atomicMin(&T0.val[a][slot], T.val[a][i]);
+                    else atomicMax(&T0.val[a][slot], T.val[a][i]);
+                }
+            } else {
+                agg_to_global(table, A.table_slots, overflow, key, T.first_row[i], x, s_agg, A.naggs);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < kAggWarpSlots; i += kComputeThreads) {
+        const unsigned long long key = T0.key[i];
         if (key == kAggEmpty) continue;
-        const int gs = agg_global_slot(table, A.table_slots, key);
-        if (gs < 0) { atomicExch(overflow, 1u); continue; }
-        atomicMin(&table[gs].first_row, S.first_row[i]);
-        for (int a = 0; a < A.naggs; a++) agg_update(&table[gs].val[a], s_agg[a].op, S.val[a][i]);
+        long long x[kMaxAggs];
+        for (int a = 0; a < A.naggs; a++) x[a] = s_agg[a].op == kAggCount ? (long long)(unsigned int)T0.val[a][i] : (long long)T0.val[a][i];
+        agg_to_global(table, A.table_slots, overflow, key, T0.first_row[i], x, s_agg, A.naggs);
     }
 }
 

@@ -212,7 +212,7 @@ cudaError_t launch_agg(const AggPlan& a, const uint32_t* bitmap, const uint32_t*
                        const ScanCtrl* ctrl, int num_sms, cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    const size_t smem = sizeof(AggShared) + (size_t)kComputeWarps * 1024 * 2;
+    const size_t smem = (size_t)kComputeWarps * sizeof(AggWarpTable) + (size_t)kComputeWarps * 1024 * 2;
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, agg_kernel, kComputeThreads, smem);
     if (e != cudaSuccess) return e;

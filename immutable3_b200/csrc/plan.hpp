@@ -108,7 +108,6 @@ struct PrunePlan {
 // kernel selected, grouped by up to kMaxGroupCols dense columns whose cells pack into at most 7 key bytes.
 constexpr int kMaxAggs = 8;
 constexpr int kMaxGroupCols = 4;
-constexpr int kAggSmemSlots = 1024;       // per-CTA hash table (groups are merged into the global table when the CTA is done)
 enum AggOp : int32_t { kAggCount = 0, kAggMin = 1, kAggMax = 2 };
 struct AggCol {
     const uint8_t* base;  // device arena of the aggregated column (dense INT / TINYINT; unused for COUNT)
