@@ -478,21 +478,15 @@ const char* kernel_name(const imm3_db* db, const TableStore& t, const LogicalPla
     (void)t;
     *block_mode = blocks;
     if (lp.always_empty) return "none(always_empty)";
-    return blocks ? "scan_blocks" : ((db->flags & IMM3_OPEN_NO_TMA) ? "scan_dense(direct)" : "scan_dense(tma)");
+    return blocks ? "blocks_filter -> blocks_emit" : ((db->flags & IMM3_OPEN_NO_TMA) ? "filter(direct) -> emit" : "filter(tma) -> emit");
 }
 
-// Dense tables have two execution paths.  The three-kernel pipeline (filter -> scan -> emit) has no cross-CTA
-// dependencies and is the default; a small LIMIT makes it run over a prefix of the table first (Prepared::prefix_rows).
-// The fused single-pass kernel (one launch, stops early once a LIMIT is satisfied) is kept behind IMM3_PATH=fused: it
-// needs 38 us for a LIMIT 10 that the prefix pipeline serves in 26 us, and scans a whole table at 0.7x the pipeline's rate
-// when the LIMIT is never filled.
+// Dense tables run the three-kernel pipeline (filter -> offset scan -> emit: no cross-CTA dependency); a small LIMIT makes it
+// run over a prefix of the table first (Prepared::prefix_rows).  (Round 1 also carried a fused single-pass kernel behind
+// IMM3_PATH=fused - 0.7x the pipeline's rate, never the default, and the home of that round's one wrong result; deleted.)
 bool choose_multipass(const LogicalPlan& lp, bool block_mode) {
     (void)lp;
-    if (block_mode) return false;
-    if (const char* e = getenv("IMM3_PATH")) {
-        if (!strcmp(e, "fused")) return false;
-    }
-    return true;
+    return !block_mode;
 }
 
 int prepare(imm3_db* db, const char* table, const imm3_pred* preds, int npreds, const char* const* proj, int nproj,
@@ -747,44 +741,6 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
                 if (occ_s < 1) pr->emit_stage_bytes = 0;
                 pr->grid_emit_stream = (int)std::max<int64_t>(1, std::min<int64_t>(sp.ntiles * W, (int64_t)db->num_sms * std::max(1, occ_s)));
             }
-        } else {
-            const int sub_bytes = dense_sub_bytes();
-            const bool can_stage = dense_stage_offsets(sub_bytes);
-            // Fused kernel: a tile is NS sub-tiles of 8192 rows, NS such that a tile streams ~64 KiB of filter
-            // columns: one offset hand-off per tile, so bigger tiles keep the scanner warp off the critical path.
-            int NS = sub_bytes > 0 ? std::max(1, std::min(4, (64 * 1024) / sub_bytes)) : 4;
-            if (const char* e = getenv("IMM3_DENSE_W")) {  // tuning / A-B knob
-                int v = atoi(e);
-                if (v >= 1 && v <= kMaxSubtiles) NS = v;
-            }
-            sp.subtiles = NS;
-            sp.words_per_lane = 1;
-            const int64_t tile_rows = (int64_t)NS * kDenseTileRowsPerWord;
-            sp.ntiles = (t.nrows + tile_rows - 1) / tile_rows;
-            int stages = 0;
-            // Dense spans stream the projected columns through a warp-private buffer: 1024 rows of every column.
-            int pstage = 0;
-            for (int i = 0; i < sp.nproj; i++) {
-                sp.proj[i].stage_off = pstage;
-                pstage += 1024 * sp.proj[i].width;
-            }
-            if (pstage > 8 * 1024 || (db->flags & IMM3_OPEN_NO_TMA)) pstage = 0;  // too wide (or TMA switched off): always gather
-            sp.proj_stage_bytes = pstage;
-            sp.stream_min_cnt = 64;
-            if (const char* e = getenv("IMM3_STREAM_MIN")) sp.stream_min_cnt = std::max(1, atoi(e));
-            const size_t fixed = 16 * 1024 + (size_t)2 * NS * 1024 + (size_t)8 * pstage;  // selection vectors, bitmap words, staging
-            if (can_stage) {
-                stages = std::max(2, std::min(kMaxStages, (32 * 1024) / sub_bytes));  // sub-tiles in flight ahead of the filter
-                if (const char* e = getenv("IMM3_DENSE_STAGES")) {
-                    int v = atoi(e);
-                    if (v >= 2 && v <= kMaxStages) stages = v;
-                }
-                while (stages > 2 && fixed + (size_t)stages * (size_t)sub_bytes > 200 * 1024) stages--;
-            }
-            sp.stages = stages;
-            sp.stage_bytes = sub_bytes;
-            pr->dyn_smem = fixed + (size_t)stages * (size_t)sub_bytes;
-            CUDA_TRY(dense_kernel_occupancy(stages > 0, pr->dyn_smem, &occ));
         }
     }
     if (sp.ntiles >= (int64_t)0x7FFFFFFF) return fail(IMM3_ERR_UNSUPPORTED, "too many tiles (%lld)", (long long)sp.ntiles);
@@ -1015,8 +971,7 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
             pr->sp.trace = (unsigned long long*)db->d_trace.p;
         }
         CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
-        if (pr->block_mode) CUDA_TRY(launch_scan_blocks(pr->sp, db->d_ctrl, db->d_status, pr->grid, pr->dyn_smem, db->stream));
-        else CUDA_TRY(launch_scan_dense(pr->sp, db->d_ctrl, db->d_status, pr->grid, pr->dyn_smem, db->stream));
+        CUDA_TRY(launch_scan_blocks(pr->sp, db->d_ctrl, db->d_status, pr->grid, pr->dyn_smem, db->stream));  // (single-pass block kernel: blocks > 1024 rows, bitmaps)
         CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
         *launches = 1;
     }

@@ -71,6 +71,16 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// Tile status words of the single-pass look-back are published with release and polled with acquire semantics: a tile
+// that reads a predecessor's Prefix also observes everything that predecessor had read before publishing it.
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -150,7 +160,7 @@ __device__ long long lookback_exclusive(const unsigned long long* status, long l
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const long long idx = pos - 4 * lane - k;  // lane 0 / k 0 is the nearest predecessor
-            st[k] = idx >= 0 ? ld_relaxed_u64(status + idx) : pack_status(epoch, kStatePrefix, 0);  // virtual tile -1: prefix 0
+            st[k] = idx >= 0 ? ld_acquire_u64(status + idx) : pack_status(epoch, kStatePrefix, 0);  // virtual tile -1: prefix 0
         }
         unsigned long long lsum = 0;
         bool lpre = false, linv = false;
@@ -202,12 +212,12 @@ __device__ long long resolve_tile(const ScanPlan& P, ScanCtrl* ctrl, unsigned lo
                                   unsigned tile_count, int lane) {
     long long excl = 0;
     if (tile == 0) {
-        if (lane == 0) st_relaxed_u64(status + tile, pack_status(P.epoch, kStatePrefix, tile_count));
+        if (lane == 0) st_release_u64(status + tile, pack_status(P.epoch, kStatePrefix, tile_count));
     } else {
-        if (lane == 0) st_relaxed_u64(status + tile, pack_status(P.epoch, kStateAggregate, tile_count));
+        if (lane == 0) st_release_u64(status + tile, pack_status(P.epoch, kStateAggregate, tile_count));
         excl = (P.debug & 1u) ? (long long)tile * 1800 : lookback_exclusive(status, tile, P.epoch, ctrl, lane);
         if (excl < 0) return -1;
-        if (lane == 0) st_relaxed_u64(status + tile, pack_status(P.epoch, kStatePrefix, (unsigned long long)excl + tile_count));
+        if (lane == 0) st_release_u64(status + tile, pack_status(P.epoch, kStatePrefix, (unsigned long long)excl + tile_count));
     }
     if (lane == 0) {
         const long long incl = excl + (long long)tile_count;

@@ -5,28 +5,9 @@
 #ifndef IMM3_EMIT_MIN_BLOCKS
 #define IMM3_EMIT_MIN_BLOCKS 4
 #endif
-#ifndef IMM3_DENSE_MIN_BLOCKS
-#define IMM3_DENSE_MIN_BLOCKS 3  // register budget: 3 CTAs (24 compute warps) per SM
-#endif
 constexpr int kComputeThreads = 256;
 constexpr int kComputeWarps = kComputeThreads / 32;
 constexpr unsigned kNoMoreTiles = 0xFFFFFFFFu;
-static_assert(kDenseThreads == kComputeThreads + 64, "dense kernel: 8 compute warps + producer warp + scanner warp");
-
-struct DenseShared {
-    unsigned long long mbar_full[kMaxStages];   // producer -> compute warps: tile id valid, TMA bytes landed
-    unsigned long long mbar_empty[kMaxStages];  // compute warps -> producer: slot free again
-    unsigned long long mbar_warp[kComputeWarps];  // per compute warp: its projected-column span has landed
-    unsigned int tile[kMaxStages];              // tile held by a ring slot
-    unsigned int span_cnt[2][kMaxSubtiles * kComputeWarps];  // selected rows of every 1024-row span of the tile
-    long long excl[2];
-    unsigned int role;
-    uint8_t lits[kLitPoolBytes];  // MATCH literals of the plan
-    FilterCol filter[kMaxFilterCols];  // the plan's tables (loop-indexed, so not read from the parameter bank)
-    ProjCol proj[kMaxProjCols];
-};
-constexpr unsigned kRoleWorker = 0, kRoleScannerAndWorker = 1, kRoleScannerOnly = 2, kRoleIdle = 3;
-
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");

@@ -9,7 +9,6 @@
 //                        results, TMA-streamed) or emit_kernel / emit_general_kernel (sparse results, gathers)
 //   k_blocks_multi.cuh   any query touching a sorted-int-codec column: blocks_filter_kernel (or the dense filter kernel in
 //                        row space when no predicate touches an encoded column) -> blocks_emit_kernel, one warp per block
-//   k_fused.cuh          scan_dense_kernel: the one-launch dense kernel with a scanner warp (IMM3_PATH=fused)
 //   k_blocks_single.cuh  scan_blocks_kernel: single-pass block kernel with decoupled look-back (blocks > 1024 rows, bitmaps)
 //   k_rowspace.cuh       predicates (SIMD within a register), selection vectors, gathers, plan tables in shared memory
 //   k_ptx.cuh            mbarrier / TMA / L2-policy / relaxed-load helpers
@@ -31,7 +30,6 @@ namespace imm3 {
 
 #include "k_ptx.cuh"
 #include "k_rowspace.cuh"
-#include "k_fused.cuh"
 #include "k_blocks_single.cuh"
 #include "k_multipass.cuh"
 #include "k_blocks_multi.cuh"
@@ -77,8 +75,6 @@ static cudaError_t configure_device() {
         IMM3_SET_SMEM(blocks_emit_kernel<true>);
         IMM3_SET_SMEM(blocks_emit_kernel<false>);
         IMM3_SET_SMEM(emit_general_kernel);
-        IMM3_SET_SMEM((scan_dense_kernel<true>));
-        IMM3_SET_SMEM((scan_dense_kernel<false>));
         IMM3_SET_SMEM(filter_kernel<true>);
         IMM3_SET_SMEM(filter_kernel<false>);
 #undef IMM3_SET_SMEM
@@ -86,26 +82,12 @@ static cudaError_t configure_device() {
     }
 }
 
-cudaError_t dense_kernel_occupancy(bool staged, size_t dyn_smem, int* blocks_per_sm) {
-    cudaError_t e = configure_once();
-    if (e != cudaSuccess) return e;
-    if (staged) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, scan_dense_kernel<true>, kDenseThreads, dyn_smem);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, scan_dense_kernel<false>, kDenseThreads, dyn_smem);
-}
 cudaError_t blocks_kernel_occupancy(size_t dyn_smem, int* blocks_per_sm) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, scan_blocks_kernel, kBlockThreads, dyn_smem);
 }
 
-cudaError_t launch_scan_dense(const ScanPlan& plan, ScanCtrl* ctrl, unsigned long long* status, int grid, size_t dyn_smem,
-                              cudaStream_t stream) {
-    cudaError_t e = configure_once();
-    if (e != cudaSuccess) return e;
-    if (plan.stages > 0) scan_dense_kernel<true><<<grid, kDenseThreads, dyn_smem, stream>>>(plan, ctrl, status);
-    else scan_dense_kernel<false><<<grid, kDenseThreads, dyn_smem, stream>>>(plan, ctrl, status);
-    return cudaGetLastError();
-}
 cudaError_t filter_kernel_occupancy(size_t dyn_smem, int* blocks_per_sm) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;

@@ -9,10 +9,7 @@
 namespace imm3 {
 
 size_t blocks_kernel_smem_bytes(int npfor, int max_block_rows);
-cudaError_t dense_kernel_occupancy(bool staged, size_t dyn_smem, int* blocks_per_sm);
 cudaError_t blocks_kernel_occupancy(size_t dyn_smem, int* blocks_per_sm);
-cudaError_t launch_scan_dense(const ScanPlan& plan, ScanCtrl* ctrl, unsigned long long* status, int grid, size_t dyn_smem,
-                              cudaStream_t stream);
 cudaError_t filter_kernel_occupancy(size_t dyn_smem, int* blocks_per_sm);
 cudaError_t emit_kernel_occupancy(bool general, int* blocks_per_sm);
 cudaError_t launch_filter(const ScanPlan& plan, uint32_t* bitmap, uint32_t* span_cnt, uint32_t* tile_cnt, unsigned long long* tile_off,

@@ -19,11 +19,8 @@ constexpr int kDenseTileRowsPerWord = 8192;  // dense kernel: 8 compute warps x 
 constexpr int kDenseTileMinRows = 400;  // an 8192-row tile with at least this many selected rows (4.9 %) is streamed, not gathered:
                                         // measured crossover of the two emit kernels (age < t sweep, 100 M rows: equal at 5 %)
 constexpr int kDenseMaxTileRows = 4 * kDenseTileRowsPerWord;  // tile = 8192 * W rows, W in {1, 2, 4}
-constexpr int kDenseThreads = 320;  // 8 compute warps + producer warp (tickets, TMA) + scanner-candidate warp
 constexpr int kBlockThreads = 256;  // block-mode kernel: threads per CTA
 constexpr int kMaxBlockRows = 8192; // block-mode kernel: largest reference block it stages
-constexpr int kMaxStages = 4;
-constexpr int kMaxSubtiles = 8;       // fused dense kernel: a tile is up to 8 sub-tiles of 8192 rows (one scan hand-off per tile)
 // Tile-status arrays of the dense kernel (counts, then offsets) are padded to whole scanner rounds of 256 tiles.
 constexpr long long status_round_up(long long ntiles) { return ((ntiles + 255) & ~255ll) + 256; }
 constexpr int kMaxFilterStages = 8;  // TMA ring depth of the multi-pass filter kernel
@@ -82,9 +79,6 @@ struct ScanPlan {
     int32_t scan_inline;     // 1: the filter kernel's last CTA turns the tile counts into offsets; 0: offset_scan_kernel does (large tables)
     uint32_t pfor_filter_mask;  // blocks_filter_kernel: PFOR slots that carry a predicate (their tiles are staged)
     int32_t words_per_lane;  // multi-pass filter kernel: W (tile = 8192 * W rows)
-    int32_t subtiles;        // fused dense kernel: NS (tile = NS sub-tiles of 8192 rows)
-    int32_t proj_stage_bytes;  // fused dense kernel: one 1024-row span of every projected column (0 = never staged)
-    int32_t stream_min_cnt;    // fused dense kernel: spans with at least this many selected rows are staged, not gathered
     uint32_t debug;          // IMM3_DEBUG env bits (timing experiments only; bit 0: skip the look-back -> WRONG offsets)
     FilterCol filter[kMaxFilterCols];
     ProjCol proj[kMaxProjCols];

@@ -15,9 +15,9 @@ from immutable3_b200.loader import synth_write
 
 pytestmark = pytest.mark.gpu
 
-# variant -> (imm3_open flags, IMM3_PATH): the fused single-pass kernel with TMA staging / direct loads, the
-# block-mode kernel forced onto dense tables, and the three-kernel filter->scan->emit pipeline.
-VARIANT_DEFS = {"tma": (0, "fused"), "direct": (OPEN_NO_TMA, "fused"), "blocks": (OPEN_FORCE_BLOCKS, "fused"),
+# variant -> (imm3_open flags, IMM3_PATH): the filter -> offset scan -> emit pipeline with TMA staging / direct loads, the
+# single-pass block kernel forced onto dense tables (IMM3_PATH=fused selects it on block tables), and the library's own choice.
+VARIANT_DEFS = {"blocks": (OPEN_FORCE_BLOCKS, "fused"), "blocks_multi": (OPEN_FORCE_BLOCKS, ""),
                 "multi": (0, "multi"), "multi_direct": (OPEN_NO_TMA, "multi"), "auto": (0, "")}
 VARIANTS = {k: v[0] for k, v in VARIANT_DEFS.items()}
 
@@ -157,7 +157,7 @@ def test_dense_tile_shapes(world, w, stages, monkeypatch):
     d, tables, orc, sms = world
     monkeypatch.setenv("IMM3_DENSE_W", str(w))
     monkeypatch.setenv("IMM3_DENSE_STAGES", str(stages))
-    for variant in ("tma", "direct", "multi", "multi_direct"):
+    for variant in ("multi", "multi_direct"):
         for sel, proj in QUERIES_T[:5] + [(NoSelect, ["id", "state", "age"])]:
             for limit in (0, 10, 8191, 8193, 20_000):
                 check(orc, sms[variant], "t", sel, proj, limit, f"{variant}/W{w}/S{stages}")
@@ -177,7 +177,7 @@ def test_readme_cli_query_and_row_format(world):
         with Engine(sm).execute_sql(sql) as got:
             assert [got.format_row(i) for i in range(got.nrows)] == exp.format_rows(), variant
             assert [str(r) for r in got] == exp.format_rows()
-    with Engine(sms["tma"]).execute_sql("select state, id from t where (state = 'CA' and age > 18 and age < 30) limit 3") as got:
+    with Engine(sms["auto"]).execute_sql("select state, id from t where (state = 'CA' and age > 18 and age < 30) limit 3") as got:
         e2 = orc.query("t", [("state", O.OP_MATCH, ["CA"]), ("age", O.OP_GT, 18), ("age", O.OP_LT, 30)], ["state", "id"], limit=3, fmt_rows=3)
         assert [got.format_row(i) for i in range(got.nrows)] == e2.format_rows()
 
@@ -185,7 +185,7 @@ def test_readme_cli_query_and_row_format(world):
 @pytest.mark.parametrize("table", ["p", "pr", "ps"])
 def test_sorted_int_codec_tables(world, table):
     d, tables, orc, sms = world
-    sm = sms["tma"]  # PFOR columns always take the block-mode kernel
+    sm = sms["auto"]  # PFOR columns always take the block-mode kernel
     ids = tables[table]["id"]
     lo, hi = int(np.percentile(ids, 40)), int(np.percentile(ids, 60))
     for sel, proj in [
@@ -216,7 +216,7 @@ def test_selection_bitmap(world, variant):
 
 def test_errors_come_back_as_status_codes_not_hangs(world):
     d, tables, orc, sms = world
-    eng = Engine(sms["tma"])
+    eng = Engine(sms["auto"])
     for q, status in [(Query("t", Select("state", GT(1)), Project(["id"])), L.ERR_UNSUPPORTED),
                       (Query("t", Select("age", Match(["x"])), Project(["id"])), L.ERR_UNSUPPORTED),
                       (Query("t", NoSelect, Project(["nope"])), L.ERR_NOT_FOUND),
@@ -224,7 +224,7 @@ def test_errors_come_back_as_status_codes_not_hangs(world):
         with pytest.raises(Imm3Error) as e:
             eng.execute(q)
         assert e.value.status == status
-    check(orc, sms["tma"], "t", Select("age", GT(18)), ["id"], 10)  # the handle is still usable afterwards
+    check(orc, sms["auto"], "t", Select("age", GT(18)), ["id"], 10)  # the handle is still usable afterwards
 
 
 @pytest.mark.parametrize("nshards", [2, 3, 8])
@@ -299,7 +299,7 @@ def test_repeated_queries_reuse_buffers_and_epochs(world):
     d, tables, orc, sms = world
     sel = conj(Select("age", GT(18)), Select("age", LT(30)))
     for i in range(40):
-        check(orc, sms["tma"], "t", sel, ["id", "age"], [0, 7, 5000][i % 3])
+        check(orc, sms["auto"], "t", sel, ["id", "age"], [0, 7, 5000][i % 3])
 
 
 def test_full_size_synthetic_properties(tmp_path_factory):
@@ -312,14 +312,14 @@ def test_full_size_synthetic_properties(tmp_path_factory):
     age = np.concatenate([np.fromfile(d / "syn" / f"age_{i}.dat", np.int8) for i in order])
     ids = np.concatenate([np.fromfile(d / "syn" / f"id_{i}.dat", "<i4") for i in order])
     st = np.concatenate([np.fromfile(d / "syn" / f"state_{i}.dat", "S2") for i in order])
-    for flags, path in ((0, "fused"), (OPEN_NO_TMA, "fused"), (0, "multi"), (0, "")):
-        set_path({"fused": "tma", "multi": "multi", "": "auto"}[path])
+    for flags, path in ((0, "multi"), (OPEN_NO_TMA, "multi"), (0, "")):
+        set_path({"multi": "multi", "": "auto"}[path])
         with SegmentManager(d, flags=flags) as sm:
             eng = Engine(sm)
             m = (age > 18) & (age < 30)
             with eng.execute(Query("syn", conj(Select("age", GT(18)), Select("age", LT(30))), Project(["id", "age"]))) as r:     # C2
                 assert r.nrows == int(m.sum()) and np.array_equal(r.column(0), ids[m]) and np.array_equal(r.column(1), age[m])
-                assert r.algorithmic_bytes == n + r.nrows * 9 and r.kernel_launches in ((1,) if path == "fused" else (2, 3))
+                assert r.algorithmic_bytes == n + r.nrows * 9 and r.kernel_launches in (2, 3)
             m3 = m & (st == b"CA")
             with eng.execute(Query("syn", conj(Select("state", Match(["CA"])), Select("age", GT(18)), Select("age", LT(30))), Project(["id", "state", "age"]))) as r:  # C3
                 assert r.nrows == int(m3.sum()) and np.array_equal(r.column(0), ids[m3]) and np.all(r.column(1) == b"CA")
