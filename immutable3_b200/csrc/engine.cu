@@ -456,6 +456,7 @@ struct Prepared {
     bool blocks_multi = false;  // block mode: warp-per-block filter kernel -> offset scan -> emit kernel (no look-back chain)
     bool for_bitmap = false;    // imm3_filter_bitmap: the canonical-row bitmap comes from the single-pass kernels
     bool quad = false;          // block mode: the single-range-predicate filter kernel (lane = block x super-block)
+    bool lane = false;          // block mode: ... its lane-per-block successor (every warp its own TMA ring)
     bool prune = false;         // block mode: every predicate is a range on an encoded column with block statistics: blocks_prune_kernel first
     PrunePlan pp;
     bool hybrid = false;        // block mode, no predicate on an encoded column: DENSE filter kernel (row space) -> block emit kernel
@@ -658,6 +659,7 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
             // The only predicate is a range on one encoded column (C4): the quad kernel - lane = (block, super-block), CTA tile
             // of 32 blocks - if such a tile of this column fits a ring slot (i.e. the column actually compresses).
             pr->quad = false;
+            pr->lane = false;
             if (sp.nfilter == 1 && sp.filter[0].pfor_slot >= 0 && sp.filter[0].kind == kFilterI32Range && !getenv("IMM3_NO_QUAD")) {
                 const int64_t cap32 = (t.cols[(size_t)pfor_cols[(size_t)sp.filter[0].pfor_slot]].max_tile32_bytes + 16 + 15) & ~15ll;
                 const int qslot = blocks_filter_quad_slot_bytes((int)cap32);
@@ -669,6 +671,14 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
                     sp.stages = qring;
                     sp.stage_bytes = qslot;
                     pr->dyn_smem = (size_t)qring * (size_t)qslot;
+                }
+                // lane = block: every one of the CTA's 8 warps runs its own ring of 2 .. 4 such slots (one CTA per SM)
+                if (pr->quad && 2 * 8 * (size_t)qslot <= 220 * 1024 && !getenv("IMM3_NO_LANE")) {
+                    pr->lane = true;
+                    int lring = (int)std::min<size_t>(4, (220 * 1024) / (8 * (size_t)qslot));
+                    if (const char* e = getenv("IMM3_LANE_STAGES")) lring = std::max(2, std::min(lring, atoi(e)));
+                    sp.stages = lring;
+                    pr->dyn_smem = (size_t)lring * 8 * (size_t)qslot;
                 }
             }
             // Pruning: every predicate is a range on an encoded column that has block statistics.
@@ -691,7 +701,7 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
             }
             pr->blocks_emit_smem = blocks_emit_smem_bytes(sp.npfor, sp.blk_words_cap);
             int occ_e = 0;
-            CUDA_TRY(blocks_multi_occupancy(pr->dyn_smem, pr->blocks_emit_smem, pr->hybrid ? nullptr : &occ, &occ_e, pr->quad));
+            CUDA_TRY(blocks_multi_occupancy(pr->dyn_smem, pr->blocks_emit_smem, pr->hybrid ? nullptr : &occ, &occ_e, pr->lane ? 2 : (pr->quad ? 1 : 0)));
             if (occ_e < 1) return fail(IMM3_ERR_CUDA, "block emit kernel does not fit on an SM (dynamic shared memory %zu bytes)", pr->blocks_emit_smem);
             pr->grid_blocks_emit = (int)std::max<int64_t>(1, std::min<int64_t>((t.nblocks + 7) / 8, (int64_t)db->num_sms * std::max(1, occ_e)));
             if (pr->hybrid) {
@@ -886,7 +896,9 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         }
         CUDA_TRY(launch_blocks_filter(pr->sp, (uint32_t*)db->d_bitmap.p, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
                                       (unsigned long long*)db->d_tile_off.p, db->d_ctrl, nblocks,
-                                      pr->quad ? (int)std::max<int64_t>(1, std::min<int64_t>(pr->grid, (nblocks + 31) / 32)) : pr->grid, pr->dyn_smem, pr->quad, work, db->stream));
+                                      pr->lane ? (int)std::max<int64_t>(1, std::min<int64_t>(pr->grid, (nblocks + 255) / 256))
+                                               : (pr->quad ? (int)std::max<int64_t>(1, std::min<int64_t>(pr->grid, (nblocks + 31) / 32)) : pr->grid),
+                                      pr->dyn_smem, pr->lane ? 2 : (pr->quad ? 1 : 0), work, db->stream));
         (*launches)++;
         if (!pr->sp.scan_inline && (rc = launch_scan_kernel(db, pr->sp, ntiles, launches))) return rc;
         const bool pdl = pr->sp.nproj > 0 && !getenv("IMM3_NO_PDL");

@@ -634,6 +634,57 @@ __device__ __forceinline__ bool pfor_range_quad(uint32_t wa, int nw, int nsuper,
     return true;
 }
 
+// The four blocks bi0 .. bi0 + 3 of the staged 32-block tile at shared address sl (global blocks blk0 ..): lane (g, s) decides
+// super-block s of block g with pfor_range_quad; an irregular quad goes block by block through pfor_range_word.  Writes the
+// blocks' counts and - for partially selected blocks - bitmap words; returns the rows selected in the quad (every lane).
+__device__ __forceinline__ unsigned quad_decide(uint32_t sl, uint32_t ring_addr, uint32_t base_w, int bi0, long long blk0, long long nblocks,
+                                                uint32_t lo, uint32_t span, int lane, uint32_t* __restrict__ bitmapB, uint32_t* __restrict__ blk_cnt) {
+    const int g = lane >> 3, s = lane & 7;
+    const int bi = bi0 + g;  // my block inside the staged tile
+    const long long blk = blk0 + g;
+    const bool exists = blk < nblocks;
+    int n = 0, nw = 0;
+    uint32_t wa = sl + (uint32_t)kQuadHdrBytes;
+    if (exists) {
+        const unsigned long long r0 = lds_cell<unsigned long long>(sl + 8u * (uint32_t)bi), r1 = lds_cell<unsigned long long>(sl + 8u * (uint32_t)bi + 8u);
+        const uint32_t w0 = lds32(sl + (uint32_t)kQuadWoOff + 4u * (uint32_t)bi), w1 = lds32(sl + (uint32_t)kQuadWoOff + 4u * (uint32_t)bi + 4u);
+        n = (int)(r1 - r0);
+        nw = (int)(w1 - w0) - 2;
+        wa += 4u * (w0 - base_w);
+    }
+    unsigned quad_cnt = 0;
+    uint32_t word[4];
+    bool fast = __all_sync(0xFFFFFFFFu, exists && n > 0 && (n & 127) == 0);
+    if (fast) fast = pfor_range_quad(wa, nw, n >> 7, lo, span, lane, word);
+    if (fast) {
+        unsigned c = (unsigned)(__popc(word[0]) + __popc(word[1]) + __popc(word[2]) + __popc(word[3]));
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);  // rows selected in my block
+        if (c != 0u && c != (unsigned)n)  // (lanes past the block's last super-block write zeros: the emit kernel reads all 32 words)
+            *reinterpret_cast<uint4*>(bitmapB + blk * 32 + 4 * s) = make_uint4(word[0], word[1], word[2], word[3]);
+        if (s == 0) blk_cnt[blk] = c;
+        quad_cnt = c + __shfl_xor_sync(0xFFFFFFFFu, c, 8);
+        quad_cnt += __shfl_xor_sync(0xFFFFFFFFu, quad_cnt, 16);
+    } else {
+        // irregular quad: block by block, lane m = mini-block m (pfor_range_word)
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) {
+            const int nk = __shfl_sync(0xFFFFFFFFu, n, 8 * k), nwk = __shfl_sync(0xFFFFFFFFu, nw, 8 * k);
+            const uint32_t wak = __shfl_sync(0xFFFFFFFFu, wa, 8 * k);
+            if (blk0 + k >= nblocks) break;
+            const uint32_t* W = reinterpret_cast<const uint32_t*>(dyn_smem + (wak - ring_addr));
+            const int left = nk - lane * 32;
+            uint32_t mw = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+            mw &= pfor_range_word(W, nwk, nk, lo, span, lane);
+            const unsigned c = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(mw));
+            if (c != 0u && c != (unsigned)nk) bitmapB[(blk0 + k) * 32 + lane] = mw;
+            if (lane == 0) blk_cnt[blk0 + k] = c;
+            quad_cnt += c;
+        }
+    }
+    return quad_cnt;
+}
+
 __global__ void __launch_bounds__(kComputeThreads + 32, IMM3_QUAD_MIN_BLOCKS) blocks_filter_quad_kernel(const __grid_constant__ ScanPlan P, uint32_t* __restrict__ bitmapB,
                                                                                        uint32_t* __restrict__ blk_cnt, uint32_t* __restrict__ tile_cnt,
                                                                                        unsigned long long* __restrict__ tile_off, ScanCtrl* ctrl,
@@ -692,7 +743,6 @@ __global__ void __launch_bounds__(kComputeThreads + 32, IMM3_QUAD_MIN_BLOCKS) bl
         }
     } else {
         // ---------------- compute warps: warp w = blocks 32 * ct + 4 w .. + 3 ----------------
-        const int g = lane >> 3, s = lane & 7;
         const uint32_t lo = (uint32_t)f0.lo, span = f0.span;
         for (RingPos rp;; rp.advance(ring)) {
             const int slot = rp.slot;
@@ -701,48 +751,7 @@ __global__ void __launch_bounds__(kComputeThreads + 32, IMM3_QUAD_MIN_BLOCKS) bl
             if (ct_u == kNoMoreTiles) break;
             const long long blk0 = (long long)ct_u * kQuadTileBlocks + 4 * warp;  // first block of this warp's quad
             const uint32_t sl = ring_addr + (uint32_t)slot * (uint32_t)slot_bytes;
-            const int bi = 4 * warp + g;                                          // my block inside the CTA tile
-            const long long blk = blk0 + g;
-            const bool exists = blk < nblocks;
-            int n = 0, nw = 0;
-            uint32_t wa = sl + (uint32_t)kQuadHdrBytes;
-            if (exists) {
-                const unsigned long long r0 = lds_cell<unsigned long long>(sl + 8u * (uint32_t)bi), r1 = lds_cell<unsigned long long>(sl + 8u * (uint32_t)bi + 8u);
-                const uint32_t w0 = lds32(sl + (uint32_t)kQuadWoOff + 4u * (uint32_t)bi), w1 = lds32(sl + (uint32_t)kQuadWoOff + 4u * (uint32_t)bi + 4u);
-                n = (int)(r1 - r0);
-                nw = (int)(w1 - w0) - 2;
-                wa += 4u * (w0 - s_base[slot]);
-            }
-            unsigned quad_cnt = 0;  // rows selected in the quad (lane 0)
-            uint32_t word[4];
-            bool fast = __all_sync(0xFFFFFFFFu, exists && n > 0 && (n & 127) == 0);
-            if (fast) fast = pfor_range_quad(wa, nw, n >> 7, lo, span, lane, word);
-            if (fast) {
-                unsigned c = (unsigned)(__popc(word[0]) + __popc(word[1]) + __popc(word[2]) + __popc(word[3]));
-#pragma unroll
-                for (int o = 1; o < 8; o <<= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);  // rows selected in my block
-                if (c != 0u && c != (unsigned)n)  // (lanes past the block's last super-block write zeros: the emit kernel reads all 32 words)
-                    *reinterpret_cast<uint4*>(bitmapB + blk * 32 + 4 * s) = make_uint4(word[0], word[1], word[2], word[3]);
-                if (s == 0) blk_cnt[blk] = c;
-                quad_cnt = c + __shfl_xor_sync(0xFFFFFFFFu, c, 8);
-                quad_cnt += __shfl_xor_sync(0xFFFFFFFFu, quad_cnt, 16);
-            } else {
-                // irregular quad: block by block, lane m = mini-block m (pfor_range_word)
-#pragma unroll 1
-                for (int k = 0; k < 4; k++) {
-                    const int nk = __shfl_sync(0xFFFFFFFFu, n, 8 * k), nwk = __shfl_sync(0xFFFFFFFFu, nw, 8 * k);
-                    const uint32_t wak = __shfl_sync(0xFFFFFFFFu, wa, 8 * k);
-                    if (blk0 + k >= nblocks) break;
-                    const uint32_t* W = reinterpret_cast<const uint32_t*>(dyn_smem + (wak - ring_addr));
-                    const int left = nk - lane * 32;
-                    uint32_t mw = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
-                    mw &= pfor_range_word(W, nwk, nk, lo, span, lane);
-                    const unsigned c = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(mw));
-                    if (c != 0u && c != (unsigned)nk) bitmapB[(blk0 + k) * 32 + lane] = mw;
-                    if (lane == 0) blk_cnt[blk0 + k] = c;
-                    quad_cnt += c;
-                }
-            }
+            const unsigned quad_cnt = quad_decide(sl, ring_addr, s_base[slot], 4 * warp, blk0, nblocks, lo, span, lane, bitmapB, blk_cnt);
             __syncwarp();
             if (lane == 0) {
                 // 8-block tile = this warp's quad + its neighbour's: the second arrival publishes and clears

@@ -34,6 +34,7 @@ namespace imm3 {
 #include "k_multipass.cuh"
 #include "k_blocks_multi.cuh"
 #include "k_blocks_filter.cuh"
+#include "k_blocks_lane.cuh"
 #include "k_blocks_prune.cuh"
 #include "k_comm.cuh"
 #include "k_agg.cuh"
@@ -70,6 +71,7 @@ static cudaError_t configure_device() {
         IMM3_SET_SMEM(emit_stream_kernel);
         IMM3_SET_SMEM(blocks_filter_kernel);
         IMM3_SET_SMEM(blocks_filter_quad_kernel);
+        if ((e = cudaFuncSetAttribute(blocks_filter_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)) != cudaSuccess) return e;
         IMM3_SET_SMEM(block_stats_kernel);
         IMM3_SET_SMEM(agg_kernel);
         IMM3_SET_SMEM(blocks_emit_kernel<true>);
@@ -226,22 +228,24 @@ size_t blocks_filter_smem_bytes(int nstaged, int tile_cap_bytes, int ring) { ret
 int blocks_filter_slot_bytes(int nstaged, int tile_cap_bytes) { return blk_filter_slot_bytes(nstaged, tile_cap_bytes); }
 size_t blocks_emit_smem_bytes(int npfor, int words_cap) { return (size_t)kComputeWarps * blk_emit_warp_words(npfor, words_cap) * 4; }
 int blocks_filter_quad_slot_bytes(int tile_cap_bytes) { return kQuadHdrBytes + tile_cap_bytes; }
-cudaError_t blocks_multi_occupancy(size_t filter_smem, size_t emit_smem, int* filter_blocks_per_sm, int* emit_blocks_per_sm, bool quad) {
+cudaError_t blocks_multi_occupancy(size_t filter_smem, size_t emit_smem, int* filter_blocks_per_sm, int* emit_blocks_per_sm, int mode) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
     if (filter_blocks_per_sm) {
-        e = quad ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(filter_blocks_per_sm, blocks_filter_quad_kernel, kComputeThreads + 32, filter_smem)
-                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(filter_blocks_per_sm, blocks_filter_kernel, kComputeThreads + 32, filter_smem);
+        e = mode == 2   ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(filter_blocks_per_sm, blocks_filter_lane_kernel, kComputeThreads, filter_smem)
+            : mode == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(filter_blocks_per_sm, blocks_filter_quad_kernel, kComputeThreads + 32, filter_smem)
+                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(filter_blocks_per_sm, blocks_filter_kernel, kComputeThreads + 32, filter_smem);
         if (e != cudaSuccess) return e;
     }
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(emit_blocks_per_sm, blocks_emit_kernel<true>, kComputeThreads, emit_smem);
 }
 cudaError_t launch_blocks_filter(const ScanPlan& plan, uint32_t* bitmapB, uint32_t* blk_cnt, uint32_t* tile_cnt, unsigned long long* tile_off,
-                                 ScanCtrl* ctrl, long long nblocks, int grid, size_t dyn_smem, bool quad, const unsigned int* work,
+                                 ScanCtrl* ctrl, long long nblocks, int grid, size_t dyn_smem, int mode, const unsigned int* work,
                                  cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    if (quad) blocks_filter_quad_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks, work);
+    if (mode == 2) blocks_filter_lane_kernel<<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks, work);
+    else if (mode == 1) blocks_filter_quad_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks, work);
     else blocks_filter_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks, work);
     return cudaGetLastError();
 }
