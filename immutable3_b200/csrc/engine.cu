@@ -457,6 +457,7 @@ struct Prepared {
     bool for_bitmap = false;    // imm3_filter_bitmap: the canonical-row bitmap comes from the single-pass kernels
     bool quad = false;          // block mode: the single-range-predicate filter kernel (lane = block x super-block)
     bool lane = false;          // block mode: ... its lane-per-block successor (every warp its own TMA ring)
+    int lane_warps = 8;         // ... warps per CTA of that kernel
     bool prune = false;         // block mode: every predicate is a range on an encoded column with block statistics: blocks_prune_kernel first
     PrunePlan pp;
     bool hybrid = false;        // block mode, no predicate on an encoded column: DENSE filter kernel (row space) -> block emit kernel
@@ -672,13 +673,19 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
                     sp.stage_bytes = qslot;
                     pr->dyn_smem = (size_t)qring * (size_t)qslot;
                 }
-                // lane = block: every one of the CTA's 8 warps runs its own ring of 2 .. 4 such slots (one CTA per SM)
-                if (pr->quad && 2 * 8 * (size_t)qslot <= 220 * 1024 && !getenv("IMM3_NO_LANE")) {
+                // lane = block: every warp of the CTA runs its own ring of 2 .. 4 such slots; one CTA per SM with as many warps
+                // (8 .. 16) as its shared memory holds two-slot rings for
+                const size_t lane_smem_cap = 222 * 1024;
+                if (pr->quad && 2 * 8 * (size_t)qslot <= lane_smem_cap && !getenv("IMM3_NO_LANE")) {
                     pr->lane = true;
-                    int lring = (int)std::min<size_t>(4, (220 * 1024) / (8 * (size_t)qslot));
-                    if (const char* e = getenv("IMM3_LANE_STAGES")) lring = std::max(2, std::min(lring, atoi(e)));
+                    int lring = 2;
+                    if (const char* e = getenv("IMM3_LANE_STAGES")) lring = std::max(2, std::min(4, atoi(e)));
+                    while (lring > 2 && (size_t)lring * 4 * (size_t)qslot > lane_smem_cap) lring--;
+                    int lw = (int)std::min<size_t>(16, lane_smem_cap / ((size_t)lring * (size_t)qslot));
+                    if (const char* e = getenv("IMM3_LANE_WARPS")) lw = std::max(4, std::min(lw, atoi(e)));
+                    pr->lane_warps = lw;
                     sp.stages = lring;
-                    pr->dyn_smem = (size_t)lring * 8 * (size_t)qslot;
+                    pr->dyn_smem = (size_t)lring * (size_t)lw * (size_t)qslot;
                 }
             }
             // Pruning: every predicate is a range on an encoded column that has block statistics.
@@ -701,7 +708,7 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
             }
             pr->blocks_emit_smem = blocks_emit_smem_bytes(sp.npfor, sp.blk_words_cap);
             int occ_e = 0;
-            CUDA_TRY(blocks_multi_occupancy(pr->dyn_smem, pr->blocks_emit_smem, pr->hybrid ? nullptr : &occ, &occ_e, pr->lane ? 2 : (pr->quad ? 1 : 0)));
+            CUDA_TRY(blocks_multi_occupancy(pr->dyn_smem, pr->blocks_emit_smem, pr->hybrid ? nullptr : &occ, &occ_e, pr->lane ? (2 | (pr->lane_warps << 8)) : (pr->quad ? 1 : 0)));
             if (occ_e < 1) return fail(IMM3_ERR_CUDA, "block emit kernel does not fit on an SM (dynamic shared memory %zu bytes)", pr->blocks_emit_smem);
             pr->grid_blocks_emit = (int)std::max<int64_t>(1, std::min<int64_t>((t.nblocks + 7) / 8, (int64_t)db->num_sms * std::max(1, occ_e)));
             if (pr->hybrid) {
@@ -880,7 +887,7 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         const size_t ntiles_pad = ((size_t)ntiles + 4095) / 4096 * 4096 + 16;  // whole rounds of the offset scan
         if ((rc = ensure_buf(&db->d_tile_cnt, ntiles_pad * 4))) return rc;
         if ((rc = ensure_buf(&db->d_tile_off, ntiles_pad * 8))) return rc;
-        pr->sp.scan_inline = scan_inline_for(ntiles) ? 1 : 0;
+        pr->sp.scan_inline = (scan_inline_for(ntiles) && !(pr->lane && pr->lane_warps < 8)) ? 1 : 0;  // (the inline scan is written for 8 warps)
         const unsigned int* work = nullptr;
         if (pr->prune) {
             if ((rc = ensure_buf(&db->d_work, (size_t)((nblocks + 7) / 8 + 2) * 4))) return rc;
@@ -896,9 +903,9 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         }
         CUDA_TRY(launch_blocks_filter(pr->sp, (uint32_t*)db->d_bitmap.p, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
                                       (unsigned long long*)db->d_tile_off.p, db->d_ctrl, nblocks,
-                                      pr->lane ? (int)std::max<int64_t>(1, std::min<int64_t>(pr->grid, (nblocks + 255) / 256))
+                                      pr->lane ? (int)std::max<int64_t>(1, std::min<int64_t>(pr->grid, (nblocks + 32 * pr->lane_warps - 1) / (32 * pr->lane_warps)))
                                                : (pr->quad ? (int)std::max<int64_t>(1, std::min<int64_t>(pr->grid, (nblocks + 31) / 32)) : pr->grid),
-                                      pr->dyn_smem, pr->lane ? 2 : (pr->quad ? 1 : 0), work, db->stream));
+                                      pr->dyn_smem, pr->lane ? (2 | (pr->lane_warps << 8)) : (pr->quad ? 1 : 0), work, db->stream));
         (*launches)++;
         if (!pr->sp.scan_inline && (rc = launch_scan_kernel(db, pr->sp, ntiles, launches))) return rc;
         const bool pdl = pr->sp.nproj > 0 && !getenv("IMM3_NO_PDL");

@@ -30,6 +30,7 @@
 //   * Every warp runs its own TMA ring (lane 0 issues the bulk copies of the tile after next, the warp waits on its own
 //     mbarriers): no producer warp, no CTA-wide synchronisation, no shared counters; tile counts leave from registers.
 // =============================================================================================
+constexpr int kLaneWarpsMax = 16;  // warps of a CTA (blockDim.x / 32 says how many it has)
 constexpr int kLaneStages = 4;  // most ring slots a warp can have (ScanPlan::stages says how many it has: 2 .. 4)
 
 template <int K>
@@ -81,17 +82,98 @@ __device__ __forceinline__ uint32_t lane_narrow(uint32_t wa, int nsuper, uint32_
     return sum;
 }
 
-__global__ void __launch_bounds__(kComputeThreads, 1) blocks_filter_lane_kernel(const __grid_constant__ ScanPlan P, uint32_t* __restrict__ bitmapB,
+// The dense sorted column's block - 1024 rows, widths (B, 1, 1, 1), (1, 1, 1, 1) x 7 - with B known at compile time.
+// lane_wide: the B words of the wide mini-block go to registers and every field's word index, shift and mask folds to an
+// immediate (3 instructions per field instead of 12).
+//   M < 0  : LDS.32 at the lane's own word addresses (block sizes B + 42 that are not a multiple of 4 words put the lanes'
+//            blocks in different banks: at most a 2-way conflict)
+//   M 0..3 : blocks of B + 42 = 0 mod 4 words all start at the same word M of a 16-byte chunk (and would meet in one bank
+//            eight at a time): LDS.128 of whole chunks, block word j = chunk word j + M
+// Returns d0; wsum / wor = sum / OR of the other 31 fields.
+template <int B, int M>
+__device__ __forceinline__ uint32_t lane_wide(uint32_t ww, uint32_t& wsum, uint32_t& wor) {
+    uint32_t y[B];  // the mini-block's words (block words 2 .. B + 1), byte-swapped
+    if (M < 0) {
+#pragma unroll
+        for (int j = 0; j < B; j++) y[j] = bswap32(lds32(ww + 4u * (2 + j)));
+    } else {
+        constexpr int MM = M < 0 ? 0 : M;
+        constexpr int C0 = (2 + MM) / 4, C1 = (B + 1 + MM) / 4;  // first / last chunk that holds a word of the mini-block
+        const uint32_t cb = ww - 4u * MM;
+#pragma unroll
+        for (int c = C0; c <= C1; c++) {
+            const uint4 v = lds128(cb + 16u * c);
+            if (4 * c + 0 - MM - 2 >= 0 && 4 * c + 0 - MM - 2 < B) y[4 * c + 0 - MM - 2 < 0 ? 0 : 4 * c + 0 - MM - 2] = bswap32(v.x);
+            if (4 * c + 1 - MM - 2 >= 0 && 4 * c + 1 - MM - 2 < B) y[4 * c + 1 - MM - 2 < 0 ? 0 : 4 * c + 1 - MM - 2] = bswap32(v.y);
+            if (4 * c + 2 - MM - 2 >= 0 && 4 * c + 2 - MM - 2 < B) y[4 * c + 2 - MM - 2 < 0 ? 0 : 4 * c + 2 - MM - 2] = bswap32(v.z);
+            if (4 * c + 3 - MM - 2 >= 0 && 4 * c + 3 - MM - 2 < B) y[4 * c + 3 - MM - 2 < 0 ? 0 : 4 * c + 3 - MM - 2] = bswap32(v.w);
+        }
+    }
+    constexpr uint32_t mask = (1u << B) - 1u;
+    uint32_t sum = 0, orv = 0;
+#pragma unroll
+    for (int i = 1; i < 32; i++) {
+        const int bit = i * B, wi = bit >> 5, sh = bit & 31;
+        uint32_t f;
+        if (sh + B <= 32) f = y[wi] >> sh;
+        else f = __funnelshift_r(y[wi], y[wi + 1 < B ? wi + 1 : wi], sh);
+        if (sh + B != 32) f &= mask;
+        sum += f;
+        orv |= f;
+    }
+    wsum = sum;
+    wor = orv;
+    return y[0] & mask;
+}
+
+// ... and its 31 one-bit mini-blocks: a POPC each.  The seven regular super-blocks (header + 4 words) are walked in a
+// loop that starts rho7 super-blocks further on in lane l (bank conflicts, see above).  bad != 0: a header is not (1, 1, 1, 1).
+__device__ __forceinline__ uint32_t lane_narrow_dense(uint32_t ww, uint32_t B, int rho7, uint32_t& bad) {
+    const uint32_t n0a = ww + 4u * (2u + B);  // the three narrow mini-blocks of super-block 0
+    uint32_t sum = (uint32_t)(__popc(lds32(n0a)) + __popc(lds32(n0a + 4u)) + __popc(lds32(n0a + 8u)));
+    const uint32_t p0 = n0a + 12u, pend = p0 + 140u;  // header 1 .. behind super-block 7
+    uint32_t p = p0 + 20u * (uint32_t)rho7, hb = 0;
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        const uint32_t h = lds32(p), a = lds32(p + 4u), b = lds32(p + 8u), c = lds32(p + 12u), d = lds32(p + 16u);
+        hb |= h ^ 0x01010101u;
+        sum += (uint32_t)(__popc(a) + __popc(b)) + (uint32_t)(__popc(c) + __popc(d));
+        p += 20u;
+        p = p == pend ? p0 : p;
+    }
+    bad = hb;
+    return sum;
+}
+
+#define IMM3_LANE_WIDE_CASE(BB, MMODE) case BB: d0 = lane_wide<BB, MMODE>(ww, wsum, wor); break;
+#define IMM3_LANE_WIDE_ALL(MMODE)                                                                                                   \
+    IMM3_LANE_WIDE_CASE(17, MMODE) IMM3_LANE_WIDE_CASE(18, MMODE) IMM3_LANE_WIDE_CASE(19, MMODE) IMM3_LANE_WIDE_CASE(20, MMODE) \
+    IMM3_LANE_WIDE_CASE(21, MMODE) IMM3_LANE_WIDE_CASE(22, MMODE) IMM3_LANE_WIDE_CASE(23, MMODE) IMM3_LANE_WIDE_CASE(24, MMODE) \
+    IMM3_LANE_WIDE_CASE(25, MMODE) IMM3_LANE_WIDE_CASE(26, MMODE) IMM3_LANE_WIDE_CASE(27, MMODE) IMM3_LANE_WIDE_CASE(28, MMODE) \
+    IMM3_LANE_WIDE_CASE(29, MMODE) IMM3_LANE_WIDE_CASE(30, MMODE) IMM3_LANE_WIDE_CASE(31, MMODE)
+#define IMM3_LANE_WIDE_CHUNKS(MMODE) \
+    IMM3_LANE_WIDE_CASE(18, MMODE) IMM3_LANE_WIDE_CASE(22, MMODE) IMM3_LANE_WIDE_CASE(26, MMODE) IMM3_LANE_WIDE_CASE(30, MMODE)
+constexpr int kLaneFixedMinB = 17;
+
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kLaneWarpsMax * 32, 1) blocks_filter_lane_kernel(const __grid_constant__ ScanPlan P, uint32_t* __restrict__ bitmapB,
                                                                                 uint32_t* __restrict__ blk_cnt, uint32_t* __restrict__ tile_cnt,
                                                                                 unsigned long long* __restrict__ tile_off, ScanCtrl* ctrl,
                                                                                 long long nblocks, const unsigned int* __restrict__ work) {
     __shared__ FilterShared S;
-    __shared__ unsigned long long s_bar[kComputeWarps][kLaneStages];
-    __shared__ uint32_t s_basew[kComputeWarps][kLaneStages];  // arena word that sits at the slot's data offset
-    __shared__ int s_tile[kComputeWarps][kLaneStages];        // 32-block tile held by the slot (-1: no more work)
+    __shared__ unsigned long long s_bar[kLaneWarpsMax][kLaneStages];
+    __shared__ __align__(16) int s_meta[kLaneWarpsMax][8][4];  // per warp, a ring of work items: {32-block tile (-1: none), its first word offset, its end, -}
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid < kComputeWarps * kLaneStages) mbar_init(smem_u32(&s_bar[0][0]) + 8u * (uint32_t)tid, 1);
+    if (tid < kLaneWarpsMax * kLaneStages) mbar_init(smem_u32(&s_bar[0][0]) + 8u * (uint32_t)tid, 1);
     if (tid == 0) fence_mbar_init();
     __syncthreads();
     const long long ntiles8 = P.ntiles;           // 8-block tiles (offset scan, emit kernel)
@@ -103,66 +185,84 @@ __global__ void __launch_bounds__(kComputeThreads, 1) blocks_filter_lane_kernel(
     const int nstages = P.stages;
     const uint32_t my_ring = ring_addr + (uint32_t)(warp * nstages) * (uint32_t)slot_bytes;
     const uint32_t lo = (uint32_t)f0.lo, span = f0.span;
-    const long long nwork = work ? (long long)__ldg(work) : nct;  // pruned query: only the tiles blocks_prune_kernel listed
-    const long long gw = (long long)blockIdx.x * kComputeWarps + warp, nwarps = (long long)gridDim.x * kComputeWarps;
+    const int nwork = work ? (int)__ldg(work) : (int)nct;  // pruned query: only the tiles blocks_prune_kernel listed
+    const int cta_warps = (int)(blockDim.x >> 5);
+    const int gw = (int)blockIdx.x * cta_warps + warp, nwarps = (int)gridDim.x * cta_warps;
+    const uint32_t meta_addr = smem_u32(&s_meta[warp][0][0]);
 
-    // Work items gw, gw + nwarps, ...; the copies of item i + stages - 1 are issued while item i is decided.  The tile id of an item is
-    // fetched two steps, its first / last word offset one step before its copies are issued (no global load is waited for).
-    auto tile_of = [&](long long k) -> long long { return k < nwork ? (work ? (long long)__ldg(work + 1 + k) : k) : -1ll; };
-    long long kq = gw;           // next item whose tile id gets fetched
-    long long tA = tile_of(kq);  // tile id fetched, word offsets not yet
-    kq += nwarps;
-    long long tB = -1;           // tile id + word offsets fetched: ready to issue
-    uint32_t woB0 = 0, woB1 = 0;
-    auto advance = [&]() {
-        tB = tA;
-        if (tB >= 0) {
-            const long long b0 = tB * 32, b1 = b0 + 32 < nblocks ? b0 + 32 : nblocks;
-            woB0 = __ldg(pc.word_off + b0);
-            woB1 = __ldg(pc.word_off + b1);
-        }
-        tA = tile_of(kq);
-        kq += nwarps;
-    };
-    auto issue = [&](int slot) {  // copies of item (tB, woB0, woB1) into `slot`
-        if (lane == 0) {
-            s_tile[warp][slot] = (int)tB;
-            if (tB >= 0) {
-                const uint32_t bar = smem_u32(&s_bar[warp][slot]);
-                const uint32_t dst = my_ring + (uint32_t)slot * (uint32_t)slot_bytes;
-                const long long b0 = tB * 32;
-                const uint32_t base_w = woB0 & ~3u;  // 16-byte aligned source
-                uint32_t nb = ((woB1 - base_w) * 4u + 15u) & ~15u;
-                if (nb > (uint32_t)P.blk_tile_bytes) nb = (uint32_t)P.blk_tile_bytes;
-                s_basew[warp][slot] = base_w;
-                mbar_arrive_expect_tx(bar, 272u + 144u + nb);
-                tma_load_1d(dst, P.row_start + b0, 272u, bar);
-                tma_load_1d(dst + (uint32_t)kQuadWoOff, pc.word_off + b0, 144u, bar);
-                tma_load_1d(dst + (uint32_t)kQuadHdrBytes, pc.words + base_w, nb, bar);
-            }
+    // Work items q = 0, 1, ... of this warp are the work-list entries (or tiles) gw + q nwarps.  Lane 0 keeps three things going
+    // for the items ahead, one step each per tile decided, none of which it ever waits for: S1 fetch the item's tile id
+    // (pruned queries: from the work list), S2 fetch the tile's first / end word offset, S3 issue its bulk copies.  The
+    // fetches are 4-byte cp.async into s_meta - a plain load would stall the warp at the first touch of its register.
+    auto S1 = [&](int q) {
+        const long long k = (long long)gw + (long long)q * nwarps;
+        const uint32_t e = meta_addr + 16u * (uint32_t)(q & 7);
+        if (k < nwork) {
+            if (work) cp_async4(e, work + 1 + k);
+            else s_meta[warp][q & 7][0] = (int)k;
+        } else {
+            s_meta[warp][q & 7][0] = -1;
         }
     };
-    advance();
-#pragma unroll 1
-    for (int j = 0; j < nstages - 1; j++) {
-        issue(j);
-        advance();
+    auto S2 = [&](int q) {
+        const int t = *reinterpret_cast<volatile int*>(&s_meta[warp][q & 7][0]);
+        if (t >= 0) {
+            const long long b0 = (long long)t * 32, b1 = b0 + 32 < nblocks ? b0 + 32 : nblocks;
+            const uint32_t e = meta_addr + 16u * (uint32_t)(q & 7);
+            cp_async4(e + 4u, pc.word_off + b0);
+            cp_async4(e + 8u, pc.word_off + b1);
+        }
+    };
+    auto S3 = [&](int q, int slot) {
+        const int t = *reinterpret_cast<volatile int*>(&s_meta[warp][q & 7][0]);
+        if (t >= 0) {
+            const uint32_t wo0 = *reinterpret_cast<volatile uint32_t*>(&s_meta[warp][q & 7][1]);
+            const uint32_t wo1 = *reinterpret_cast<volatile uint32_t*>(&s_meta[warp][q & 7][2]);
+            const uint32_t bar = smem_u32(&s_bar[warp][slot]);
+            const uint32_t dst = my_ring + (uint32_t)slot * (uint32_t)slot_bytes;
+            const long long b0 = (long long)t * 32;
+            const uint32_t base_w = wo0 & ~3u;  // 16-byte aligned source
+            uint32_t nb = ((wo1 - base_w) * 4u + 15u) & ~15u;
+            if (nb > (uint32_t)P.blk_tile_bytes) nb = (uint32_t)P.blk_tile_bytes;
+            mbar_arrive_expect_tx(bar, 272u + 144u + nb);
+            tma_load_1d(dst, P.row_start + b0, 272u, bar);
+            tma_load_1d(dst + (uint32_t)kQuadWoOff, pc.word_off + b0, 144u, bar);
+            tma_load_1d(dst + (uint32_t)kQuadHdrBytes, pc.words + base_w, nb, bar);
+        }
+    };
+    if (lane == 0) {
+        for (int q = 0; q <= nstages; q++) S1(q);
+        cp_async_commit_wait_all();
+        for (int q = 0; q < nstages; q++) S2(q);
+        cp_async_commit_wait_all();
+        for (int q = 0; q < nstages - 1; q++) S3(q, q);
     }
     __syncwarp();
 
     int slot = 0, pslot = nstages - 1;
     unsigned use = 0;
 #pragma unroll 1
-    for (;;) {
-        issue(pslot);  // (the slot decided in the previous step: every lane is past its last read of it)
-        advance();
+    for (int it = 0;; it++) {
+        if (lane == 0) {
+            cp_async_wait_all();           // (issued one step ago)
+            S3(it + nstages - 1, pslot);   // into the slot decided in the previous step: every lane is past its last read of it
+            S2(it + nstages);
+            S1(it + nstages + 1);
+            cp_async_commit();
+        }
         __syncwarp();
-        const int T = *reinterpret_cast<volatile int*>(&s_tile[warp][slot]);
+        const int T = *reinterpret_cast<volatile int*>(&s_meta[warp][it & 7][0]);
         if (T < 0) break;
         mbar_wait(smem_u32(&s_bar[warp][slot]), use & 1u, nullptr);
         const uint32_t sl = my_ring + (uint32_t)slot * (uint32_t)slot_bytes;
-        const uint32_t base_w = *reinterpret_cast<volatile uint32_t*>(&s_basew[warp][slot]);
+        const uint32_t base_w = *reinterpret_cast<volatile uint32_t*>(&s_meta[warp][it & 7][1]) & ~3u;
         const long long blk0 = (long long)T * 32, blk = blk0 + lane;
+        if (P.debug & 32u) {  // timing experiment (wrong results): the data path alone
+            __syncwarp();
+            pslot = slot;
+            if (++slot == nstages) { slot = 0; use++; }
+            continue;
+        }
         // ---------------- my block ----------------
         const bool exists = blk < nblocks;
         int n = 0, nw = 0;
@@ -198,38 +298,68 @@ __global__ void __launch_bounds__(kComputeThreads, 1) blocks_filter_lane_kernel(
             const uint32_t wa_src = __shfl_sync(0xFFFFFFFFu, wa, src);
             const uint32_t ww = mine ? wa : wa_src;  // (a lane without a block of its own walks a good one with B = 0: every load stays in bounds)
             if (!mine) B = 0;
-            // rotation: lanes whose blocks start in the same bank start their walk at different places
-            const uint32_t S0 = __shfl_sync(0xFFFFFFFFu, stride, src);
-            const int rho = lane >> (6 - __ffs((int)(S0 | 32u)));  // lane / (32 / gcd(S0, 32)): 0 .. gcd - 1
-            const int rs = (nsuper & (nsuper - 1)) == 0 ? (rho & (nsuper - 1)) : rho % nsuper;
-            // ---------------- wide mini-block: d0 + the sum of its other 31 fields ----------------
-            const uint32_t wb = ww + 8u, mask = (1u << B) - 1u;
-            uint32_t d0, wsum = 0, wor = 0;
-            {
-                const uint32_t x0 = bswap32(lds32(wb));
-                d0 = x0 & mask;
-                int i = rho >= 31 ? 1 : 1 + rho;
-#pragma unroll 8
-                for (int fi = 0; fi < 31; fi++) {
-                    const uint32_t off = (uint32_t)i * B;
-                    const uint32_t a = wb + 4u * (off >> 5);
-                    const uint32_t f = __funnelshift_r(bswap32(lds32(a)), bswap32(lds32(a + 4u)), off) & mask;
-                    wsum += f;
-                    wor |= f;
-                    i = i == 31 ? 1 : i + 1;
+            uint32_t d0 = 0, rest = 0, wor = 0, bad = 0;
+            // the dense sorted column's shape with one B for the whole tile: everything from registers (lane_fixed)
+            const uint32_t B0 = __shfl_sync(0xFFFFFFFFu, B, src);
+            const bool fixed = n0 == 1024 && k == 1u && B0 >= (uint32_t)kLaneFixedMinB && B0 < 32u && __all_sync(0xFFFFFFFFu, !mine || B == B0);
+            if (fixed) {
+                const uint32_t S0 = B0 + 42u;  // words per block
+                const int rho = lane >> (6 - __ffs((int)(S0 | 32u)));  // lane / (32 / gcd(S0, 32)): 0 .. gcd - 1
+                const int rho7 = rho - 7 * ((rho * 37) >> 8);          // rho % 7
+                const uint32_t Mu = (wa_src >> 2) & 3u;
+                const bool chunks = (S0 & 3u) == 0u && __all_sync(0xFFFFFFFFu, ((ww >> 2) & 3u) == Mu);
+                uint32_t wsum = 0;
+                if (chunks) {
+                    switch (Mu) {
+                        case 0: switch (B0) { IMM3_LANE_WIDE_CHUNKS(0) default: break; } break;
+                        case 1: switch (B0) { IMM3_LANE_WIDE_CHUNKS(1) default: break; } break;
+                        case 2: switch (B0) { IMM3_LANE_WIDE_CHUNKS(2) default: break; } break;
+                        default: switch (B0) { IMM3_LANE_WIDE_CHUNKS(3) default: break; } break;
+                    }
+                } else {
+                    switch (B0) {
+                        IMM3_LANE_WIDE_ALL(-1)
+                        default: break;
+                    }
                 }
-            }
-            // ---------------- narrow mini-blocks ----------------
-            uint32_t bad = 0, nsum;
-            switch (k) {
-                case 0: nsum = lane_narrow<0>(ww, nsuper, B, rs, bad); break;
-                case 1: nsum = lane_narrow<1>(ww, nsuper, B, rs, bad); break;
-                case 2: nsum = lane_narrow<2>(ww, nsuper, B, rs, bad); break;
-                case 4: nsum = lane_narrow<4>(ww, nsuper, B, rs, bad); break;
-                default: nsum = lane_narrow<8>(ww, nsuper, B, rs, bad); break;
+                rest = wsum + lane_narrow_dense(ww, B0, rho7, bad);
+            } else {
+                // rotation: lanes whose blocks start in the same bank start their walk at different places
+                const uint32_t S0 = __shfl_sync(0xFFFFFFFFu, stride, src);
+                const int rho = lane >> (6 - __ffs((int)(S0 | 32u)));  // lane / (32 / gcd(S0, 32)): 0 .. gcd - 1
+                const int rs = (nsuper & (nsuper - 1)) == 0 ? (rho & (nsuper - 1)) : rho % nsuper;
+                // ---------------- wide mini-block: d0 + the sum of its other 31 fields ----------------
+                const uint32_t wb = ww + 8u, mask = (1u << B) - 1u;
+                uint32_t d0w, wsum = 0, wor_w = 0;
+                {
+                    const uint32_t x0 = bswap32(lds32(wb));
+                    d0w = x0 & mask;
+                    int i = rho >= 31 ? 1 : 1 + rho;
+#pragma unroll 8
+                    for (int fi = 0; fi < 31; fi++) {
+                        const uint32_t off = (uint32_t)i * B;
+                        const uint32_t a = wb + 4u * (off >> 5);
+                        const uint32_t f = __funnelshift_r(bswap32(lds32(a)), bswap32(lds32(a + 4u)), off) & mask;
+                        wsum += f;
+                        wor_w |= f;
+                        i = i == 31 ? 1 : i + 1;
+                    }
+                }
+                // ---------------- narrow mini-blocks ----------------
+                uint32_t nsum;
+                switch (k) {
+                    case 0: nsum = lane_narrow<0>(ww, nsuper, B, rs, bad); break;
+                    case 1: nsum = lane_narrow<1>(ww, nsuper, B, rs, bad); break;
+                    case 2: nsum = lane_narrow<2>(ww, nsuper, B, rs, bad); break;
+                    case 4: nsum = lane_narrow<4>(ww, nsuper, B, rs, bad); break;
+                    default: nsum = lane_narrow<8>(ww, nsuper, B, rs, bad); break;
+                }
+                d0 = d0w;
+                rest = wsum + nsum;
+                wor = wor_w;
             }
             // ---------------- decide ----------------
-            const uint32_t rest = wsum + nsum;                     // < 31 * 2^21 + 1023 * 255 if wor < 2^21
+            // (rest < 31 * 2^21 + 1023 * 255 if wor < 2^21)
             const uint32_t uf = d0 - lo, ul = uf + rest;           // first / last value of the block in the window's frame
             const bool mono = ul >= uf && wor < (1u << 21) && bad == 0u;
             const bool all = mono && ul <= span, none = mono && uf > span;
@@ -282,7 +412,7 @@ __global__ void __launch_bounds__(kComputeThreads, 1) blocks_filter_lane_kernel(
         if (S.is_last) ctrl->exited = 0;
     }
     __syncthreads();
-    if (S.is_last && P.scan_inline) {
+    if (S.is_last && warp < kComputeWarps && P.scan_inline) {
         __threadfence();
         scan_tile_counts(S, tile_cnt, tile_off, ntiles8, P.limit, ctrl);
     }

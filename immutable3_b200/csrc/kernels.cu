@@ -71,7 +71,7 @@ static cudaError_t configure_device() {
         IMM3_SET_SMEM(emit_stream_kernel);
         IMM3_SET_SMEM(blocks_filter_kernel);
         IMM3_SET_SMEM(blocks_filter_quad_kernel);
-        if ((e = cudaFuncSetAttribute(blocks_filter_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(blocks_filter_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024)) != cudaSuccess) return e;
         IMM3_SET_SMEM(block_stats_kernel);
         IMM3_SET_SMEM(agg_kernel);
         IMM3_SET_SMEM(blocks_emit_kernel<true>);
@@ -232,7 +232,7 @@ cudaError_t blocks_multi_occupancy(size_t filter_smem, size_t emit_smem, int* fi
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
     if (filter_blocks_per_sm) {
-        e = mode == 2   ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(filter_blocks_per_sm, blocks_filter_lane_kernel, kComputeThreads, filter_smem)
+        e = mode >= 2   ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(filter_blocks_per_sm, blocks_filter_lane_kernel, (mode >> 8) * 32, filter_smem)
             : mode == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(filter_blocks_per_sm, blocks_filter_quad_kernel, kComputeThreads + 32, filter_smem)
                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(filter_blocks_per_sm, blocks_filter_kernel, kComputeThreads + 32, filter_smem);
         if (e != cudaSuccess) return e;
@@ -244,7 +244,7 @@ cudaError_t launch_blocks_filter(const ScanPlan& plan, uint32_t* bitmapB, uint32
                                  cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    if (mode == 2) blocks_filter_lane_kernel<<<grid, kComputeThreads, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks, work);
+    if (mode >= 2) blocks_filter_lane_kernel<<<grid, (mode >> 8) * 32, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks, work);
     else if (mode == 1) blocks_filter_quad_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks, work);
     else blocks_filter_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks, work);
     return cudaGetLastError();
