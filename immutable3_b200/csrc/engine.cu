@@ -142,6 +142,7 @@ struct imm3_db {
     Buf h_agg_out;                           // pinned read-back of the compacted groups
     Buf d_work;                              // blocks_prune_kernel: work list of tiles for the filter kernel ([0] = count)
     Buf d_scan_part;                         // offset_scan_kernel: epoch-tagged chunk sums (zeroed when (re)allocated)
+    Buf d_tile_list;                         // offset_scan_kernel (block pipeline): the non-empty tiles, for the emit kernel
     uint32_t scan_epoch = 0;
     Buf d_trace;                             // IMM3_TRACE debugging buffer
     // Emit-kernel feedback: result density class (1 dense, 0 sparse) last seen for a query shape (table, filter
@@ -427,6 +428,7 @@ void free_device_side(imm3_db* db) {
     if (db->d_tile_off.p) cudaFree(db->d_tile_off.p);
     if (db->d_trace.p) cudaFree(db->d_trace.p);
     if (db->d_scan_part.p) cudaFree(db->d_scan_part.p);
+    if (db->d_tile_list.p) cudaFree(db->d_tile_list.p);
     if (db->d_work.p) cudaFree(db->d_work.p);
     if (db->d_agg_table.p) cudaFree(db->d_agg_table.p);
     if (db->d_agg_out.p) cudaFree(db->d_agg_out.p);
@@ -708,7 +710,7 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
             }
             pr->blocks_emit_smem = blocks_emit_smem_bytes(sp.npfor, sp.blk_words_cap);
             int occ_e = 0;
-            CUDA_TRY(blocks_multi_occupancy(pr->dyn_smem, pr->blocks_emit_smem, pr->hybrid ? nullptr : &occ, &occ_e, pr->lane ? (2 | (pr->lane_warps << 8)) : (pr->quad ? 1 : 0)));
+            CUDA_TRY(blocks_multi_occupancy(pr->dyn_smem, pr->blocks_emit_smem, pr->hybrid ? nullptr : &occ, &occ_e, pr->lane ? (2 | (pr->lane_warps << 8)) : (pr->quad ? 1 : 0), pr->hybrid));
             if (occ_e < 1) return fail(IMM3_ERR_CUDA, "block emit kernel does not fit on an SM (dynamic shared memory %zu bytes)", pr->blocks_emit_smem);
             pr->grid_blocks_emit = (int)std::max<int64_t>(1, std::min<int64_t>((t.nblocks + 7) / 8, (int64_t)db->num_sms * std::max(1, occ_e)));
             if (pr->hybrid) {
@@ -826,7 +828,11 @@ bool scan_inline_for(int64_t ntiles) {
     }
     return ntiles <= scan_inline_max_tiles();
 }
-int launch_scan_kernel(imm3_db* db, const ScanPlan& sp, int64_t ntiles, int* launches) {
+int launch_scan_kernel(imm3_db* db, const ScanPlan& sp, int64_t ntiles, int* launches, bool want_list = false) {
+    if (want_list) {
+        int rc = ensure_buf(&db->d_tile_list, (size_t)(ntiles + 16) * 4);
+        if (rc) return rc;
+    }
     const size_t nchunks = (size_t)((ntiles + 4095) / 4096);
     if (db->d_scan_part.cap < nchunks * 16) {
         if (db->d_scan_part.p) cudaFree(db->d_scan_part.p);
@@ -838,7 +844,7 @@ int launch_scan_kernel(imm3_db* db, const ScanPlan& sp, int64_t ntiles, int* lau
     }
     if (((++db->scan_epoch) & 0xFFFFFFu) == 0) ++db->scan_epoch;  // (tag 0 = never written)
     CUDA_TRY(launch_offset_scan((const uint32_t*)db->d_tile_cnt.p, (unsigned long long*)db->d_tile_off.p, ntiles, sp.limit, db->scan_epoch,
-                                (unsigned long long*)db->d_scan_part.p, db->d_ctrl, db->stream));
+                                (unsigned long long*)db->d_scan_part.p, db->d_ctrl, want_list ? (unsigned int*)db->d_tile_list.p : nullptr, db->stream));
     (*launches)++;
     return 0;
 }
@@ -872,7 +878,7 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
             have_mid = true;
         }
         if (pr->sp.nproj > 0) {
-            CUDA_TRY(launch_blocks_emit(pr->sp, pr->sp.bitmap, (const uint32_t*)db->d_span_cnt.p, (const unsigned long long*)db->d_tile_off.p,
+            CUDA_TRY(launch_blocks_emit(pr->sp, pr->sp.bitmap, (const uint32_t*)db->d_span_cnt.p, nullptr, (const unsigned long long*)db->d_tile_off.p,
                                         nblocks_use, db->d_ctrl, true, pdl, (int)std::min<int64_t>(pr->grid_blocks_emit, (nblocks_use + 7) / 8),
                                         pr->blocks_emit_smem, db->stream));
             (*launches)++;
@@ -893,6 +899,15 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
             if ((rc = ensure_buf(&db->d_work, (size_t)((nblocks + 7) / 8 + 2) * 4))) return rc;
             work = (const unsigned int*)db->d_work.p;
         }
+        if ((pr->sp.debug & 16u) && getenv("IMM3_TRACE")) {  // debugging: phase stamps (min / max over warps)
+            int rc0 = ensure_buf(&db->d_trace, (64 + 1024) * 8);
+            if (rc0) return rc0;
+            std::vector<unsigned long long> init(64 + 1024);
+            for (int i = 0; i < 64; i++) init[(size_t)i] = (i & 1) ? 0ull : ~0ull;
+            CUDA_TRY(cudaMemcpyAsync(db->d_trace.p, init.data(), init.size() * 8, cudaMemcpyHostToDevice, db->stream));
+            CUDA_TRY(cudaStreamSynchronize(db->stream));
+            pr->sp.trace = (unsigned long long*)db->d_trace.p;
+        }
         CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
         if (pr->prune) {
             // whole blocks decided from their min / max; only the tiles a window edge cuts through reach the filter kernel
@@ -907,7 +922,7 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
                                                : (pr->quad ? (int)std::max<int64_t>(1, std::min<int64_t>(pr->grid, (nblocks + 31) / 32)) : pr->grid),
                                       pr->dyn_smem, pr->lane ? (2 | (pr->lane_warps << 8)) : (pr->quad ? 1 : 0), work, db->stream));
         (*launches)++;
-        if (!pr->sp.scan_inline && (rc = launch_scan_kernel(db, pr->sp, ntiles, launches))) return rc;
+        if (!pr->sp.scan_inline && (rc = launch_scan_kernel(db, pr->sp, ntiles, launches, true))) return rc;
         const bool pdl = pr->sp.nproj > 0 && !getenv("IMM3_NO_PDL");
         if (!pdl) {
             CUDA_TRY(cudaEventRecord(db->ev_mid, db->stream));
@@ -915,6 +930,7 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         }
         if (pr->sp.nproj > 0) {
             CUDA_TRY(launch_blocks_emit(pr->sp, (const uint32_t*)db->d_bitmap.p, (const uint32_t*)db->d_span_cnt.p,
+                                        pr->sp.scan_inline ? nullptr : (const unsigned int*)db->d_tile_list.p,
                                         (const unsigned long long*)db->d_tile_off.p, nblocks, db->d_ctrl, false, pdl,
                                         (int)std::min<int64_t>(pr->grid_blocks_emit, (nblocks + 7) / 8), pr->blocks_emit_smem, db->stream));
             (*launches)++;
@@ -1031,11 +1047,19 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         unsigned long long h[64];
         CUDA_TRY(cudaMemcpy(h, pr->sp.trace, sizeof h, cudaMemcpyDeviceToHost));
         if (FILE* f = fopen(getenv("IMM3_TRACE"), "w")) {
-            const char* names[] = {"K1 entry", "K1 cta done", "K1 scan start", "K1 scan end", "K3s entry", "K3s first tile", "K3s cta done"};
-            for (int i = 0; i < 7; i++)
-                fprintf(f, "%-16s min %9.2f us  max %9.2f us\n", names[i], (double)(h[2 * i] - h[0]) / 1e3, (double)(h[2 * i + 1] - h[0]) / 1e3);
+            const char* names[] = {"K1 entry", "K1 cta done", "K1 scan start", "K1 scan end", "K3s entry", "K3s first tile", "K3s cta done", "-",
+                                   "K3b entry", "K3b dep ready", "K3b tiles seen", "K3b tile meta", "K3b block start", "K3b block done", "K3b warp done", "K3b words here", "K3b store start", "K3b store done"};
+            for (int i = 0; i < 18; i++)
+                if (h[2 * i] != ~0ull)
+                    fprintf(f, "%-16s min %9.2f us  max %9.2f us\n", names[i], (double)(h[2 * i] - h[0]) / 1e3, (double)(h[2 * i + 1] - h[0]) / 1e3);
             for (int i = 0; i < 8; i++)
                 if (h[32 + i] != ~0ull && h[32 + i] != 0) fprintf(f, "scan round %d after block scan: %9.2f us\n", i, (double)(h[32 + i] - h[0]) / 1e3);
+            if (pr->lane) {  // per CTA of the lane kernel: done time, SM, tiles decided
+                std::vector<unsigned long long> pc(1024);
+                if (cudaMemcpy(pc.data(), pr->sp.trace + 64, 1024 * 8, cudaMemcpyDeviceToHost) == cudaSuccess)
+                    for (int i = 0; i < 512 && pc[2 * i]; i++)
+                        fprintf(f, "cta %3d done %9.2f us  sm %3llu  tiles %llu\n", i, (double)(pc[2 * i] - h[0]) / 1e3, pc[2 * i + 1] >> 32, pc[2 * i + 1] & 0xFFFFFFFFull);
+            }
             fclose(f);
         }
     } else if (pr->sp.trace) {

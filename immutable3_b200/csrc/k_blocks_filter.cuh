@@ -401,7 +401,10 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) blocks_filter_kernel(
         __threadfence();
         const unsigned prev = atomicAdd(&ctrl->exited, 1u);
         S.is_last = prev == gridDim.x - 1;
-        if (S.is_last) ctrl->exited = 0;
+        if (S.is_last) {
+            ctrl->exited = 0;
+            ctrl->ticket2 = 0;  // (offset_scan_kernel counts the non-empty tiles of this query here)
+        }
     }
     __syncthreads();
     if (S.is_last && warp < kComputeWarps && P.scan_inline) {
@@ -771,7 +774,10 @@ __global__ void __launch_bounds__(kComputeThreads + 32, IMM3_QUAD_MIN_BLOCKS) bl
         __threadfence();
         const unsigned prev = atomicAdd(&ctrl->exited, 1u);
         S.is_last = prev == gridDim.x - 1;
-        if (S.is_last) ctrl->exited = 0;
+        if (S.is_last) {
+            ctrl->exited = 0;
+            ctrl->ticket2 = 0;  // (offset_scan_kernel counts the non-empty tiles of this query here)
+        }
     }
     __syncthreads();
     if (S.is_last && warp < kComputeWarps && P.scan_inline) {

@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(kLaneWarpsMax * 32, 1) blocks_filter_lane_kern
     __shared__ __align__(16) int s_meta[kLaneWarpsMax][8][4];  // per warp, a ring of work items: {32-block tile (-1: none), its first word offset, its end, -}
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) phase_stamp(P, 0);
     if (tid < kLaneWarpsMax * kLaneStages) mbar_init(smem_u32(&s_bar[0][0]) + 8u * (uint32_t)tid, 1);
     if (tid == 0) fence_mbar_init();
     __syncthreads();
@@ -404,12 +405,23 @@ __global__ void __launch_bounds__(kLaneWarpsMax * 32, 1) blocks_filter_lane_kern
         if (++slot == nstages) { slot = 0; use++; }
     }
 
+    if (lane == 0) phase_stamp(P, 2);
     __syncthreads();
     if (tid == 0) {
+        phase_stamp(P, 1);
+        if ((P.debug & 16u) && P.trace && blockIdx.x < 512) {  // debugging: when this CTA was done, and on which SM
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            P.trace[64 + 2 * blockIdx.x] = globaltimer_ns();
+            P.trace[64 + 2 * blockIdx.x + 1] = (unsigned long long)smid << 32;
+        }
         __threadfence();
         const unsigned prev = atomicAdd(&ctrl->exited, 1u);
         S.is_last = prev == gridDim.x - 1;
-        if (S.is_last) ctrl->exited = 0;
+        if (S.is_last) {
+            ctrl->exited = 0;
+            ctrl->ticket2 = 0;  // (offset_scan_kernel counts the non-empty tiles of this query here)
+        }
     }
     __syncthreads();
     if (S.is_last && warp < kComputeWarps && P.scan_inline) {

@@ -183,6 +183,82 @@ __device__ __forceinline__ uint32_t pfor_decode_warp(const uint32_t* __restrict_
     return base;
 }
 
+// A fully selected 1024-row block of the dense sorted shape - widths (B, 1, 1, 1), (1, 1, 1, 1) x 7, the shape the lane filter
+// kernel takes (k_blocks_lane.cuh) - decoded straight from global memory into the result column, no shared-memory staging:
+// four independent loads per lane (its header, its one-bit mini-block, the two words holding field `lane` of the wide
+// mini-block), two warp scans (the wide mini-block's values, the mini-blocks' carries), then row 32 m + lane =
+// carry(m) + popc(word(m) & low bits) - one coalesced store per mini-block.  B follows from the block's length and is
+// checked against header 0.  out: the block's first result row; scratch: 64 warp-private words of shared memory.
+struct DenseRegs {
+    uint32_t hraw, nraw, x0, x1;
+    int B;  // width of the wide mini-block if the block can have the dense shape, else -1
+};
+// ... the loads (issued as early as the block's word offsets are known: the caller overlaps them with the previous block)
+__device__ __forceinline__ DenseRegs dense_issue(const uint32_t* __restrict__ words, uint32_t wo0, uint32_t wo1, int n, int lane) {
+    DenseRegs r;
+    r.hraw = r.nraw = r.x0 = r.x1 = 0;
+    r.B = (int)(wo1 - wo0) - 42;
+    if (n != 1024 || r.B < 0 || r.B > 31) {
+        r.B = -1;
+        return r;
+    }
+    const int B = r.B;
+    const uint32_t* W = words + wo0;
+    const int hidx = lane == 0 ? 1 : 5 + B + 5 * ((lane & 7) - 1 < 0 ? 0 : (lane & 7) - 1);
+    const int nidx = 1 + B + 5 * (lane >> 2) + (lane & 3);  // (lane 0: unused)
+    const uint32_t off = (uint32_t)(lane * B);
+    r.hraw = __ldg(W + hidx);
+    r.nraw = __ldg(W + nidx);
+    r.x0 = __ldg(W + 2 + (off >> 5));
+    r.x1 = __ldg(W + 3 + (off >> 5));
+    return r;
+}
+// ... and the rest.  Returns false (nothing written) if the block does not have the dense shape.
+__device__ __forceinline__ bool dense_finish(const DenseRegs& r, uint32_t* __restrict__ out, int nn, int lane, uint32_t* scratch, uint32_t dbg = 0) {
+    if (r.B < 0) return false;
+    const int B = r.B;
+    const uint32_t off = (uint32_t)(lane * B);
+    const uint32_t hexp = lane == 0 ? (0x01010100u | (uint32_t)B) : 0x01010101u;
+    if (!__all_sync(0xFFFFFFFFu, lane >= 8 || r.hraw == hexp)) return false;
+    uint32_t v = __funnelshift_r(__byte_perm(r.x0, 0, 0x0123), __byte_perm(r.x1, 0, 0x0123), off) & ((1u << B) - 1u);  // field `lane`
+    const uint32_t X = __byte_perm(r.nraw, 0, 0x0123);
+    const uint32_t wide_total = __reduce_add_sync(0xFFFFFFFFu, v);       // the wide mini-block's last value
+    const uint32_t tot = lane == 0 ? wide_total : (uint32_t)__popc(X);  // what mini-block `lane` adds to the running value
+    uint32_t incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {  // (two independent scans, interleaved: the wide mini-block's values, the mini-blocks' carries)
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o), u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) {
+            v += t;
+            incl += u;
+        }
+    }
+    const uint32_t carry = incl - tot;  // value of the row before this lane's mini-block
+    const uint32_t low = (2u << lane) - 1u;
+    uint2* const pair = reinterpret_cast<uint2*>(scratch);  // (word, carry) of every mini-block: one broadcast LDS.64 per 32 rows
+    pair[lane] = make_uint2(X, carry);
+    __syncwarp();
+    uint32_t* const o = out + lane;
+    if (dbg & 64u) return true;  // timing experiment (wrong results): no stores
+    if (nn >= 1024) {
+        o[0] = v;
+#pragma unroll
+        for (int m = 1; m < 32; m++) {
+            const uint2 xc = pair[m];
+            o[32 * m] = xc.y + (uint32_t)__popc(xc.x & low);
+        }
+    } else {
+        if (lane < nn) o[0] = v;
+#pragma unroll 4
+        for (int m = 1; m < 32; m++) {
+            const uint2 xc = pair[m];
+            if (32 * m + lane < nn) o[32 * m] = xc.y + (uint32_t)__popc(xc.x & low);
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
 // Emit kernel of the block pipelines: one warp per reference block with at least one surviving row.
 //   ROWSPACE = false : bitmap written by blocks_filter_kernel (32 words per block, block-local alignment); a block's first
 //                      ordinal = tile offset + counts of the tile's earlier blocks.
@@ -193,8 +269,8 @@ __device__ __forceinline__ uint32_t pfor_decode_warp(const uint32_t* __restrict_
 // The block's surviving rows go to a warp-private selection vector; encoded columns of the select list are decoded once
 // into shared memory; rows are emitted 128 per round, each lane fetching 4 rows x all columns before its first store.
 template <bool ROWSPACE>
-__global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const __grid_constant__ ScanPlan P, const uint32_t* __restrict__ bitmap,
-                                                                           const uint32_t* __restrict__ cnts,
+__global__ void __launch_bounds__(kComputeThreads, ROWSPACE ? 3 : 2) blocks_emit_kernel(const __grid_constant__ ScanPlan P, const uint32_t* __restrict__ bitmap,
+                                                                           const uint32_t* __restrict__ cnts, const unsigned int* __restrict__ tile_list,
                                                                            const unsigned long long* __restrict__ tile_off, long long nblocks,
                                                                            const ScanCtrl* ctrl) {
     __shared__ ProjCol s_proj[kMaxProjCols];
@@ -208,8 +284,11 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const _
             if (tid == i) s_pfor[i] = P.pfor[i];
     }
     __syncthreads();
+    if (lane == 0) phase_stamp(P, 8);
     asm volatile("griddepcontrol.wait;" ::: "memory");  // launched as a programmatic dependent of the filter kernel: its results are final now
+    if (lane == 0) phase_stamp(P, 9);
     if (__ldcg(&ctrl->total) == 0ull) return;  // nothing survived the predicates
+    if (P.debug & 128u) return;                // timing experiment (no results): launch + prologue alone
     uint32_t* const Wb = reinterpret_cast<uint32_t*>(dyn_smem) + warp * blk_emit_warp_words(P.npfor, P.blk_words_cap);
     uint32_t* const vals0 = Wb + P.blk_words_cap;
     uint32_t* const bases = vals0 + P.npfor * kBlkVals;  // [slot][mini-block]: what to add to the stored prefix sums
@@ -217,102 +296,62 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const _
     const uint32_t sel_addr = smem_u32(sel_w);
     const long long warp0 = (long long)blockIdx.x * kComputeWarps + warp, nwarps = (long long)gridDim.x * kComputeWarps;
     unsigned used_slots = 0;  // encoded columns of the select list
+    unsigned ent0 = 0, ent1 = 0, ent2 = 0, ent3 = 0;  // per encoded column: the select-list entries that project it
     bool fused_ok = P.nproj <= 4;
     for (int pc = 0; pc < P.nproj; pc++) {
         if (s_proj[pc].pfor_slot >= 0) used_slots |= 1u << s_proj[pc].pfor_slot;
+        const int sl = s_proj[pc].pfor_slot;
+        ent0 |= sl == 0 ? 1u << pc : 0u;
+        ent1 |= sl == 1 ? 1u << pc : 0u;
+        ent2 |= sl == 2 ? 1u << pc : 0u;
+        ent3 |= sl == 3 ? 1u << pc : 0u;
         fused_ok = fused_ok && (s_proj[pc].width == 4 || s_proj[pc].width == 2 || s_proj[pc].width == 1);
     }
-    // block metadata in ONE round trip: lanes 0,1 = row ordinals, lanes 2+2s, 3+2s = word offsets of encoded column s
-    auto load_meta = [&](long long b) -> unsigned long long {
-        unsigned long long m = 0;
-        if (b < nblocks) {
-            if (lane < 2) m = P.row_start[b + lane];
-            else if (lane < 2 + 2 * P.npfor) m = s_pfor[(lane - 2) >> 1].word_off[b + (lane & 1)];
-        }
-        return m;
-    };
-    // A warp visits blocks warp0, warp0 + nwarps, ... (round robin, so that a clustered result spreads over all warps).
-    // Row space: the next block's metadata (its bits are found through R0) is in flight while this one is handled.
-    // Block-local bitmap: the counts of the warp's next 32 blocks are fetched in ONE round trip (a lane each) and only the
-    // non-empty ones (1 % of them for C4) are visited; those alone fetch their metadata and their tile's counts.
-    unsigned long long meta_n = ROWSPACE ? load_meta(warp0) : 0ull;
+    // One block with surviving rows: R0 / n = its first row / rows, myword = lane w's selection word (rows 32w ..), g = ordinal of
+    // its first surviving row, wo(slot, k) = first (k = 0) / end (k = 1) word of the block in encoded column `slot`.
+    auto emit_block = [&](long long R0, int n, uint32_t myword, long long g, auto wo, int prim, const DenseRegs& pre) {
+        if (g >= P.limit) return;
+        __syncwarp();  // (the previous block's readers are done with the scratch)
+        // selection vector of the block (ascending rows)
+        const int cnt = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(myword));
+        const int nn = (int)(P.limit - g < (long long)cnt ? P.limit - g : (long long)cnt);
+        // decode the encoded columns of the select list (every row survives: only those emit_dense_block does not take)
+        unsigned direct = 0;  // encoded columns already written by emit_dense_block
+        if (cnt == n) {
 #pragma unroll 1
-    for (long long it = 0;; it++) {
-        unsigned todo;  // blocks of this iteration still to handle (row space: bit 0)
-        const long long first = ROWSPACE ? warp0 + it * nwarps : warp0 + it * 32 * nwarps;  // block of lane 0 / of bit 0
-        if (first >= nblocks) break;
-        unsigned long long meta_it = 0;
-        if (ROWSPACE) {
-            meta_it = meta_n;
-            meta_n = load_meta(first + nwarps);
-            todo = 1u;
-        } else {
-            const long long b = first + lane * nwarps;
-            todo = __ballot_sync(0xFFFFFFFFu, b < nblocks && __ldg(cnts + b) != 0u);
-        }
-#pragma unroll 1
-        while (todo) {
-        const int src = __ffs((int)todo) - 1;
-        todo &= todo - 1u;
-        const long long blk = first + src * nwarps;
-        const unsigned long long meta = ROWSPACE ? meta_it : load_meta(blk);
-        unsigned tile_c = 0;                 // block-local: counts of the tile's blocks (lanes 0-7)
-        unsigned long long tile_o = 0;
-        if (!ROWSPACE) {
-            const long long t8 = blk & ~7ll;
-            tile_c = (lane < 8 && t8 + lane < nblocks) ? __ldg(cnts + t8 + lane) : 0u;
-            tile_o = __ldg(tile_off + (blk >> 3));
-        }
-        const long long R0 = (long long)__shfl_sync(0xFFFFFFFFu, meta, 0);
-        const int n = (int)((long long)__shfl_sync(0xFFFFFFFFu, meta, 1) - R0);
-        uint32_t myword;  // lane w: rows [32w, 32w+32) of the block
-        long long g;      // ordinal of the block's first surviving row
-        if (ROWSPACE) {
-            const long long bit0 = R0 + 32 * lane;
-            const uint32_t lo = __ldg(bitmap + (bit0 >> 5)), hi = __ldg(bitmap + (bit0 >> 5) + 1);
-            const long long span = R0 >> 10;
-            const uint32_t sw = __ldg(bitmap + span * 32 + lane);                        // R0's span, word `lane`
-            const unsigned sc = lane < (int)(span & 7) ? __ldg(cnts + (span & ~7ll) + lane) : 0u;  // earlier spans of the tile
-            const unsigned long long toff = __ldg(tile_off + (span >> 3));
-            myword = __funnelshift_r(lo, hi, (uint32_t)(bit0 & 31));
-            const int left = n - lane * 32;
-            myword &= left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
-            if (__ballot_sync(0xFFFFFFFFu, myword != 0u) == 0u) continue;
-            const long long wrow0 = (span << 10) + 32 * lane;  // first row of span word `lane`
-            const unsigned below = wrow0 + 32 <= R0 ? (unsigned)__popc(sw) : (wrow0 < R0 ? (unsigned)__popc(sw & ((1u << (int)(R0 - wrow0)) - 1u)) : 0u);
-            g = (long long)toff + __reduce_add_sync(0xFFFFFFFFu, sc + below);
-        } else {
-            g = (long long)tile_o + __reduce_add_sync(0xFFFFFFFFu, lane < (int)(blk & 7) ? tile_c : 0u);
-            // the filter kernel stores the 32 words of a block only if SOME of its rows survive; all of them: the count says so
-            const unsigned mycnt = __shfl_sync(0xFFFFFFFFu, tile_c, (int)(blk & 7));
-            if (mycnt == (unsigned)n) {
-                const int left = n - lane * 32;
-                myword = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
-            } else {
-                myword = __ldg(bitmap + blk * 32 + lane);
+            for (int pc = 0; pc < P.nproj; pc++) {
+                const int slot = s_proj[pc].pfor_slot;
+                if (slot < 0) continue;
+                bool done;
+                if (pc == prim) {  // (its loads were issued while the previous block was being written)
+                    done = dense_finish(pre, reinterpret_cast<uint32_t*>(s_proj[pc].out) + g, nn, lane, Wb, P.debug);
+                } else {
+                    const uint32_t wo0 = wo(slot, 0), wo1 = wo(slot, 1);
+                    const DenseRegs r = dense_issue(s_pfor[slot].words, wo0, wo1, n, lane);
+                    done = dense_finish(r, reinterpret_cast<uint32_t*>(s_proj[pc].out) + g, nn, lane, Wb);
+                }
+                if (done) direct |= 1u << pc;
             }
         }
-        if (g >= P.limit) continue;
-        __syncwarp();  // (the previous block's readers are done with the scratch)
-        // decode the encoded columns of the select list
 #pragma unroll 1
         for (int s = 0; s < P.npfor; s++) {
             if (!((used_slots >> s) & 1u)) continue;
-            const uint32_t wo0 = (uint32_t)__shfl_sync(0xFFFFFFFFu, meta, 2 + 2 * s);
-            const uint32_t wo1 = (uint32_t)__shfl_sync(0xFFFFFFFFu, meta, 3 + 2 * s);
+            {
+                const unsigned ent = s == 0 ? ent0 : (s == 1 ? ent1 : (s == 2 ? ent2 : ent3));
+                if (cnt == n && (ent & ~direct) == 0u) continue;  // every select-list entry of this column was written directly
+            }  // every select-list entry of this column was written directly
+            const uint32_t wo0 = wo(s, 0), wo1 = wo(s, 1);
             const uint32_t b = pfor_decode_warp(s_pfor[s].words, wo0, wo1, n, Wb, P.blk_words_cap, vals0 + s * kBlkVals, lane);
             bases[s * 32 + lane] = b;
             __syncwarp();
         }
-        // selection vector of the block (ascending rows)
-        const int cnt = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(myword));
-        const int nn = (int)(P.limit - g < (long long)cnt ? P.limit - g : (long long)cnt);
         if (cnt == n) {
             // every row of the block survives (the inside of a window on a sorted column): no selection vector - decoded
             // columns go out row by row (a coalesced store per 32 rows), dense columns are copied straight
 #pragma unroll 1
             for (int pc = 0; pc < P.nproj; pc++) {
                 const int w = s_proj[pc].width, slot = s_proj[pc].pfor_slot;
+                if ((direct >> pc) & 1u) continue;
                 if (slot >= 0) {
                     const uint32_t* vs = vals0 + slot * kBlkVals;
                     const uint32_t* bs = bases + slot * 32;
@@ -323,7 +362,7 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const _
                     copy_rows(s_proj[pc].base + R0 * w, s_proj[pc].out + g * w, nn * w, lane);
                 }
             }
-            continue;
+            return;
         }
         append_selection(myword, lane, sel_w, 0u);
         __syncwarp();
@@ -395,7 +434,173 @@ __global__ void __launch_bounds__(kComputeThreads, 3) blocks_emit_kernel(const _
                 }
             }
         }
+    };
+
+    if (ROWSPACE) {
+        // block metadata in ONE round trip: lanes 0,1 = row ordinals, lanes 2+2s, 3+2s = word offsets of encoded column s
+        auto load_meta = [&](long long b) -> unsigned long long {
+            unsigned long long m = 0;
+            if (b < nblocks) {
+                if (lane < 2) m = P.row_start[b + lane];
+                else if (lane < 2 + 2 * P.npfor) m = s_pfor[(lane - 2) >> 1].word_off[b + (lane & 1)];
+            }
+            return m;
+        };
+        // A warp visits blocks warp0, warp0 + nwarps, ... (round robin, so that a clustered result spreads over all warps);
+        // the next block's metadata (its bits are found through R0) is in flight while this one is handled.
+        unsigned long long meta_n = load_meta(warp0);
+#pragma unroll 1
+        for (long long blk = warp0; blk < nblocks; blk += nwarps) {
+            const unsigned long long meta = meta_n;
+            meta_n = load_meta(blk + nwarps);
+            const long long R0 = (long long)__shfl_sync(0xFFFFFFFFu, meta, 0);
+            const int n = (int)((long long)__shfl_sync(0xFFFFFFFFu, meta, 1) - R0);
+            const long long bit0 = R0 + 32 * lane;
+            const uint32_t lo = __ldg(bitmap + (bit0 >> 5)), hi = __ldg(bitmap + (bit0 >> 5) + 1);
+            const long long span = R0 >> 10;
+            const uint32_t sw = __ldg(bitmap + span * 32 + lane);                        // R0's span, word `lane`
+            const unsigned sc = lane < (int)(span & 7) ? __ldg(cnts + (span & ~7ll) + lane) : 0u;  // earlier spans of the tile
+            const unsigned long long toff = __ldg(tile_off + (span >> 3));
+            uint32_t myword = __funnelshift_r(lo, hi, (uint32_t)(bit0 & 31));
+            const int left = n - lane * 32;
+            myword &= left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+            if (__ballot_sync(0xFFFFFFFFu, myword != 0u) == 0u) continue;
+            const long long wrow0 = (span << 10) + 32 * lane;  // first row of span word `lane`
+            const unsigned below = wrow0 + 32 <= R0 ? (unsigned)__popc(sw) : (wrow0 < R0 ? (unsigned)__popc(sw & ((1u << (int)(R0 - wrow0)) - 1u)) : 0u);
+            const long long g = (long long)toff + __reduce_add_sync(0xFFFFFFFFu, sc + below);
+            emit_block(R0, n, myword, g, [&](int slot, int k) -> uint32_t { return (uint32_t)__shfl_sync(0xFFFFFFFFu, meta, 2 + 2 * slot + k); }, -1, DenseRegs{0, 0, 0, 0, -1});
         }
+    } else {
+        // Block-local bitmap.  A warp visits blocks warp0, warp0 + nwarps, ... (round robin, so that a clustered result spreads
+        // over all warps) in groups of 32, a lane each:
+        //   round trip 0: the counts of 8 such groups (eight loads in flight per lane) - or, on large tables where that scan of
+        //                 every block count would cost a million sector requests, entries of the non-empty-tile list;
+        //   round trip 1: every lane with a non-empty block fetches that block's metadata itself (row ordinals, word offsets,
+        //                 its tile's counts and offset) - one round trip for all the non-empty blocks of the group;
+        //   then the blocks one after the other, the loads of the next block's encoded words (dense_issue) in flight while
+        //   this one is decoded and written.
+        int prim = -1;  // the select-list entry whose loads are issued ahead: the first encoded column
+        for (int pc = P.nproj - 1; pc >= 0; pc--) prim = s_proj[pc].pfor_slot >= 0 ? pc : prim;
+        const int pslot = prim >= 0 ? s_proj[prim].pfor_slot : 0;
+        const uint32_t* const pwords = s_pfor[pslot].words;
+        // my block b (if cand): metadata in one round trip, then the group's non-empty blocks one after the other
+        auto process_group = [&](long long b, bool cand) {
+            // ---- round trip 1: my block's metadata ----
+            unsigned long long r0 = 0, r1 = 0, g = 0;
+            uint32_t w0a = 0, w1a = 0, w0b = 0, w1b = 0, w0c = 0, w1c = 0, w0d = 0, w1d = 0, mycnt = 0;
+            if (cand) {
+                r0 = P.row_start[b];
+                r1 = P.row_start[b + 1];
+                if (P.npfor > 0) { w0a = __ldg(s_pfor[0].word_off + b); w1a = __ldg(s_pfor[0].word_off + b + 1); }
+                if (P.npfor > 1) { w0b = __ldg(s_pfor[1].word_off + b); w1b = __ldg(s_pfor[1].word_off + b + 1); }
+                if (P.npfor > 2) { w0c = __ldg(s_pfor[2].word_off + b); w1c = __ldg(s_pfor[2].word_off + b + 1); }
+                if (P.npfor > 3) { w0d = __ldg(s_pfor[3].word_off + b); w1d = __ldg(s_pfor[3].word_off + b + 1); }
+                const uint4* tc = reinterpret_cast<const uint4*>(cnts + (b & ~7ll));
+                const uint4 ca = __ldg(tc), cb = __ldg(tc + 1);
+                g = __ldg(tile_off + (b >> 3));
+                const int j = (int)(b & 7);
+                const uint32_t c8[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    g += i < j ? c8[i] : 0u;
+                    mycnt = i == j ? c8[i] : mycnt;
+                }
+            }
+            const uint32_t pw0 = pslot == 0 ? w0a : (pslot == 1 ? w0b : (pslot == 2 ? w0c : w0d));
+            const uint32_t pw1 = pslot == 0 ? w1a : (pslot == 1 ? w1b : (pslot == 2 ? w1c : w1d));
+            const int myn = (int)(r1 - r0);
+            const bool ahead_ok = prim >= 0 && mycnt == (uint32_t)myn && (long long)g < P.limit;  // (per lane: my block can take the fast path)
+            // ... and nothing but that: the query projects this one encoded column and the LIMIT does not cut the block
+            const bool direct_ok = ahead_ok && P.nproj == 1 && (long long)g + myn <= P.limit;
+            if (lane == 0) phase_stamp(P, 11);
+            unsigned todo = __ballot_sync(0xFFFFFFFFu, cand && mycnt != 0u);
+            if (!todo) return;
+            // ---- the blocks, one after the other ----
+            int nsrc = __ffs((int)todo) - 1;
+            DenseRegs nx = {0, 0, 0, 0, -1};
+            if (__shfl_sync(0xFFFFFFFFu, (int)ahead_ok, nsrc))
+                nx = dense_issue(pwords, __shfl_sync(0xFFFFFFFFu, pw0, nsrc), __shfl_sync(0xFFFFFFFFu, pw1, nsrc), __shfl_sync(0xFFFFFFFFu, myn, nsrc), lane);
+#pragma unroll 1
+            while (todo) {
+                const int src = nsrc;
+                todo &= todo - 1u;
+                const DenseRegs cur = nx;
+                nx.B = -1;
+                if (todo) {
+                    nsrc = __ffs((int)todo) - 1;
+                    if (__shfl_sync(0xFFFFFFFFu, (int)ahead_ok, nsrc))
+                        nx = dense_issue(pwords, __shfl_sync(0xFFFFFFFFu, pw0, nsrc), __shfl_sync(0xFFFFFFFFu, pw1, nsrc), __shfl_sync(0xFFFFFFFFu, myn, nsrc), lane);
+                }
+                if (__shfl_sync(0xFFFFFFFFu, (int)direct_ok, src)) {
+                    const long long gd = (long long)__shfl_sync(0xFFFFFFFFu, g, src);
+                    __syncwarp();
+                    if (dense_finish(cur, reinterpret_cast<uint32_t*>(s_proj[0].out) + gd, 1024, lane, Wb, P.debug)) continue;
+                }
+                const long long blk = __shfl_sync(0xFFFFFFFFu, b, src);
+                const long long R0 = (long long)__shfl_sync(0xFFFFFFFFu, r0, src);
+                const int n = __shfl_sync(0xFFFFFFFFu, myn, src);
+                const long long gb = (long long)__shfl_sync(0xFFFFFFFFu, g, src);
+                // the filter kernel stores the 32 words of a block only if SOME of its rows survive; all of them: the count says so
+                uint32_t myword;
+                if (__shfl_sync(0xFFFFFFFFu, mycnt, src) == (unsigned)n) {
+                    const int left = n - lane * 32;
+                    myword = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+                } else {
+                    myword = __ldg(bitmap + blk * 32 + lane);
+                }
+                if (lane == 0) phase_stamp(P, 12);
+                emit_block(R0, n, myword, gb, [&](int slot, int k) -> uint32_t {
+                    const uint32_t x0 = slot == 0 ? w0a : (slot == 1 ? w0b : (slot == 2 ? w0c : w0d));
+                    const uint32_t x1 = slot == 0 ? w1a : (slot == 1 ? w1b : (slot == 2 ? w1c : w1d));
+                    return __shfl_sync(0xFFFFFFFFu, k ? x1 : x0, src);
+                }, cur.B >= 0 ? prim : -1, cur);
+                if (lane == 0) phase_stamp(P, 13);
+            }
+        };
+        const unsigned nlist = tile_list ? __ldcg(&ctrl->ticket2) : 0u;
+        if (tile_list) {
+            // large tables: offset_scan_kernel left the list of non-empty TILES; entry e = (list position e / 8, block e % 8 of
+            // that tile), entries warp0, warp0 + nwarps, ... are mine, 32 of them (a lane each) per step
+            const long long nent = (long long)nlist * 8;
+#pragma unroll 1
+            for (long long e0 = warp0; e0 < nent; e0 += 32 * nwarps) {
+                const long long e = e0 + lane * nwarps;
+                long long b = 0;
+                bool cand = e < nent;
+                if (cand) {
+                    b = (long long)__ldg(tile_list + (e >> 3)) * 8 + (e & 7);
+                    cand = b < nblocks;
+                }
+                if (lane == 0) phase_stamp(P, 10);
+                process_group(b, cand);
+            }
+        } else {
+#pragma unroll 1
+            for (long long it0 = 0;; it0 += 8) {
+                if (warp0 + it0 * 32 * nwarps >= nblocks) break;
+                unsigned mymask = 0;  // lane u: the non-empty blocks of group it0 + u
+                {
+                    unsigned c[8];
+                    const uint32_t* cp = cnts + warp0 + (it0 * 32 + lane) * nwarps;
+                    const long long left = nblocks - (warp0 + (it0 * 32 + lane) * nwarps);  // blocks from this lane's first one on
+                    const long long stride = 32 * nwarps;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) c[u] = (long long)u * stride < left ? __ldg(cp + u * stride) : 0u;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const unsigned bal = __ballot_sync(0xFFFFFFFFu, c[u] != 0u);
+                        if (lane == u) mymask = bal;
+                    }
+                }
+                if (lane == 0) phase_stamp(P, 10);
+#pragma unroll 1
+                for (int u = 0; u < 8; u++) {
+                    const unsigned m = __shfl_sync(0xFFFFFFFFu, mymask, u);
+                    if (!m) continue;
+                    process_group(warp0 + ((it0 + u) * 32 + lane) * nwarps, (m >> lane) & 1u);
+                }
+            }
+        }
+        if (lane == 0) phase_stamp(P, 14);
     }
 }
-

@@ -125,10 +125,11 @@ constexpr long long kScanInlineMaxTiles = 4 * kComputeThreads * 16;
 
 __global__ void __launch_bounds__(kComputeThreads) offset_scan_kernel(const uint32_t* __restrict__ tile_cnt, unsigned long long* __restrict__ tile_off,
                                                                      long long ntiles, long long limit, uint32_t epoch,
-                                                                     unsigned long long* __restrict__ partials, ScanCtrl* ctrl) {
+                                                                     unsigned long long* __restrict__ partials, ScanCtrl* ctrl,
+                                                                     unsigned int* __restrict__ tile_list) {
     constexpr int kRound = kComputeThreads * 16;
     __shared__ unsigned long long s_sum[kComputeWarps], s_dense[kComputeWarps], s_prev[kComputeWarps], s_prevd[kComputeWarps];
-    __shared__ unsigned int s_chunk;
+    __shared__ unsigned int s_chunk, s_nz[kComputeWarps], s_lbase;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");  // the filter kernel's tile counts are final
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -157,11 +158,32 @@ __global__ void __launch_bounds__(kComputeThreads) offset_scan_kernel(const uint
         carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
     dsum = __reduce_add_sync(0xFFFFFFFFu, dsum);
+    // (block pipeline) the non-empty tiles of this chunk go on a list - in any order: a tile's place in the result comes from
+    // tile_off - so that the emit kernel need not look at 977 K block counts to find the 1 % that have rows
+    unsigned nz = 0, nz_before = 0;
+    if (tile_list) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) nz += (c[j].x != 0u) + (c[j].y != 0u);
+        unsigned incl = nz;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        nz_before = incl - nz;
+        if (lane == 31) s_nz[warp] = incl;
+    }
     if (lane == 0) {
         s_sum[warp] = carry;
         s_dense[warp] = dsum;
     }
     __syncthreads();
+    if (tile_list && tid == 0) {
+        unsigned tot = 0;
+#pragma unroll
+        for (int w = 0; w < kComputeWarps; w++) tot += s_nz[w];
+        s_lbase = tot ? atomicAdd(&ctrl->ticket2, tot) : 0u;
+    }
     unsigned long long wbase = 0, chunk_total = 0, chunk_dense = 0;
 #pragma unroll
     for (int w = 0; w < kComputeWarps; w++) {
@@ -208,6 +230,17 @@ __global__ void __launch_bounds__(kComputeThreads) offset_scan_kernel(const uint
     for (int w = 0; w < kComputeWarps; w++) {
         base += s_prev[w];
         based += s_prevd[w];
+    }
+    if (tile_list) {  // (s_lbase was written before the barrier above)
+        unsigned pos = s_lbase + nz_before;
+#pragma unroll
+        for (int w = 0; w < kComputeWarps; w++) pos += w < warp ? s_nz[w] : 0u;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const unsigned i = (unsigned)(base_i + my0 + 64 * j);
+            if (c[j].x != 0u) tile_list[pos++] = i;
+            if (c[j].y != 0u) tile_list[pos++] = i + 1u;
+        }
     }
 #pragma unroll
     for (int j = 0; j < 8; j++) {

@@ -211,7 +211,7 @@ cudaError_t launch_agg(const AggPlan& a, const uint32_t* bitmap, const uint32_t*
 
 long long scan_inline_max_tiles() { return kScanInlineMaxTiles; }
 cudaError_t launch_offset_scan(const uint32_t* tile_cnt, unsigned long long* tile_off, long long ntiles, long long limit, uint32_t epoch,
-                               unsigned long long* partials, ScanCtrl* ctrl, cudaStream_t stream) {
+                               unsigned long long* partials, ScanCtrl* ctrl, unsigned int* tile_list, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)((ntiles + kComputeThreads * 16 - 1) / (kComputeThreads * 16)));
     cfg.blockDim = dim3(kComputeThreads);
@@ -221,14 +221,14 @@ cudaError_t launch_offset_scan(const uint32_t* tile_cnt, unsigned long long* til
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, offset_scan_kernel, tile_cnt, tile_off, ntiles, limit, epoch, partials, ctrl);
+    return cudaLaunchKernelEx(&cfg, offset_scan_kernel, tile_cnt, tile_off, ntiles, limit, epoch, partials, ctrl, tile_list);
 }
 
 size_t blocks_filter_smem_bytes(int nstaged, int tile_cap_bytes, int ring) { return (size_t)ring * (size_t)blk_filter_slot_bytes(nstaged, tile_cap_bytes); }
 int blocks_filter_slot_bytes(int nstaged, int tile_cap_bytes) { return blk_filter_slot_bytes(nstaged, tile_cap_bytes); }
 size_t blocks_emit_smem_bytes(int npfor, int words_cap) { return (size_t)kComputeWarps * blk_emit_warp_words(npfor, words_cap) * 4; }
 int blocks_filter_quad_slot_bytes(int tile_cap_bytes) { return kQuadHdrBytes + tile_cap_bytes; }
-cudaError_t blocks_multi_occupancy(size_t filter_smem, size_t emit_smem, int* filter_blocks_per_sm, int* emit_blocks_per_sm, int mode) {
+cudaError_t blocks_multi_occupancy(size_t filter_smem, size_t emit_smem, int* filter_blocks_per_sm, int* emit_blocks_per_sm, int mode, bool rowspace) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
     if (filter_blocks_per_sm) {
@@ -237,7 +237,8 @@ cudaError_t blocks_multi_occupancy(size_t filter_smem, size_t emit_smem, int* fi
                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(filter_blocks_per_sm, blocks_filter_kernel, kComputeThreads + 32, filter_smem);
         if (e != cudaSuccess) return e;
     }
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(emit_blocks_per_sm, blocks_emit_kernel<true>, kComputeThreads, emit_smem);
+    if (rowspace) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(emit_blocks_per_sm, blocks_emit_kernel<true>, kComputeThreads, emit_smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(emit_blocks_per_sm, blocks_emit_kernel<false>, kComputeThreads, emit_smem);
 }
 cudaError_t launch_blocks_filter(const ScanPlan& plan, uint32_t* bitmapB, uint32_t* blk_cnt, uint32_t* tile_cnt, unsigned long long* tile_off,
                                  ScanCtrl* ctrl, long long nblocks, int grid, size_t dyn_smem, int mode, const unsigned int* work,
@@ -249,7 +250,7 @@ cudaError_t launch_blocks_filter(const ScanPlan& plan, uint32_t* bitmapB, uint32
     else blocks_filter_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks, work);
     return cudaGetLastError();
 }
-cudaError_t launch_blocks_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* cnts, const unsigned long long* tile_off,
+cudaError_t launch_blocks_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* cnts, const unsigned int* tile_list, const unsigned long long* tile_off,
                                long long nblocks, const ScanCtrl* ctrl, bool rowspace, bool pdl, int grid, size_t dyn_smem, cudaStream_t stream) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
@@ -264,8 +265,8 @@ cudaError_t launch_blocks_emit(const ScanPlan& plan, const uint32_t* bitmap, con
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const long long nb = nblocks;
-    if (rowspace) return cudaLaunchKernelEx(&cfg, blocks_emit_kernel<true>, plan, bitmap, cnts, tile_off, nb, ctrl);
-    return cudaLaunchKernelEx(&cfg, blocks_emit_kernel<false>, plan, bitmap, cnts, tile_off, nb, ctrl);
+    if (rowspace) return cudaLaunchKernelEx(&cfg, blocks_emit_kernel<true>, plan, bitmap, cnts, tile_list, tile_off, nb, ctrl);
+    return cudaLaunchKernelEx(&cfg, blocks_emit_kernel<false>, plan, bitmap, cnts, tile_list, tile_off, nb, ctrl);
 }
 
 // The count exchange rides behind the query's last kernel as a programmatic dependent (its launch overlaps that kernel).
