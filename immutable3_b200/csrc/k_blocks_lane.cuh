@@ -276,9 +276,14 @@ __global__ void __launch_bounds__(kLaneWarpsMax * 32, 1) blocks_filter_lane_kern
             nw = (int)stride - 2;
             wa += 4u * (w0 - base_w);
         }
-        const int n0 = __shfl_sync(0xFFFFFFFFu, n, 0);
+        // the tile's shape is taken from its first block of whole super-blocks (NOT simply from lane 0: the 1-row tail block that
+        // ends every segment sits there in one tile of 32, and sending that whole tile through the quad routine cost its warp
+        // 25 us - the slow CTAs of every run)
+        const unsigned whole = __ballot_sync(0xFFFFFFFFu, exists && n > 0 && (n & 127) == 0 && nw >= 2);
+        const int lane0 = whole ? __ffs((int)whole) - 1 : 0;
+        const int n0 = whole ? __shfl_sync(0xFFFFFFFFu, n, lane0) : 0;
         const uint32_t h0raw = (exists && nw >= 2) ? lds32(wa + 4u) : 0xFFFFFFFFu;  // raw big-endian header 0: byte 0 = B, bytes 1..3 = the other widths
-        const uint32_t k = __shfl_sync(0xFFFFFFFFu, h0raw, 0) >> 24;
+        const uint32_t k = __shfl_sync(0xFFFFFFFFu, h0raw, lane0) >> 24;
         const int nsuper = n0 >> 7;
         unsigned cnt = 0;           // rows selected in my block
         unsigned c8_fallback = 0;   // (quad fallback: per 8-block tile counts are written there)
