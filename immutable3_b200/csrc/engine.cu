@@ -828,13 +828,13 @@ bool scan_inline_for(int64_t ntiles) {
     }
     return ntiles <= scan_inline_max_tiles();
 }
-int launch_scan_kernel(imm3_db* db, const ScanPlan& sp, int64_t ntiles, int* launches, bool want_list = false) {
+int prepare_scan_buffers(imm3_db* db, int64_t ntiles, bool want_list) {
     if (want_list) {
         int rc = ensure_buf(&db->d_tile_list, (size_t)(ntiles + 16) * 4);
         if (rc) return rc;
     }
     const size_t nchunks = (size_t)((ntiles + 4095) / 4096);
-    if (db->d_scan_part.cap < nchunks * 16) {
+    if (db->d_scan_part.cap < nchunks * 16 + 512) {  // (+ the scan-emit kernel's chunks-done counter, 128 bytes behind the sums)
         if (db->d_scan_part.p) cudaFree(db->d_scan_part.p);
         db->d_scan_part = Buf();
         const size_t cap = nchunks * 16 + 4096;
@@ -843,6 +843,15 @@ int launch_scan_kernel(imm3_db* db, const ScanPlan& sp, int64_t ntiles, int* lau
         db->d_scan_part.cap = cap;
     }
     if (((++db->scan_epoch) & 0xFFFFFFu) == 0) ++db->scan_epoch;  // (tag 0 = never written)
+    return 0;
+}
+int launch_scan_kernel(imm3_db* db, const ScanPlan& sp, int64_t ntiles, int* launches, bool want_list = false) {
+    {
+        int rc = prepare_scan_buffers(db, ntiles, want_list);
+        if (rc) return rc;
+    }
+    const size_t nchunks = (size_t)((ntiles + 4095) / 4096);
+    (void)nchunks;
     CUDA_TRY(launch_offset_scan((const uint32_t*)db->d_tile_cnt.p, (unsigned long long*)db->d_tile_off.p, ntiles, sp.limit, db->scan_epoch,
                                 (unsigned long long*)db->d_scan_part.p, db->d_ctrl, want_list ? (unsigned int*)db->d_tile_list.p : nullptr, db->stream));
     (*launches)++;
@@ -894,6 +903,14 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         if ((rc = ensure_buf(&db->d_tile_cnt, ntiles_pad * 4))) return rc;
         if ((rc = ensure_buf(&db->d_tile_off, ntiles_pad * 8))) return rc;
         pr->sp.scan_inline = (scan_inline_for(ntiles) && !(pr->lane && pr->lane_warps < 8)) ? 1 : 0;  // (the inline scan is written for 8 warps)
+        int fused_grid = 0;  // > 0: offset scan + emit as ONE kernel behind the filter kernel (one encoded column projected)
+        if (pr->sp.nproj == 1 && pr->sp.proj[0].pfor_slot >= 0 && !getenv("IMM3_NO_SCANEMIT")) {
+            CUDA_TRY(blocks_scan_emit_grid(db->num_sms, ntiles, &fused_grid));
+            if (fused_grid > 0) {
+                if ((rc = prepare_scan_buffers(db, ntiles, true))) return rc;
+                pr->sp.scan_inline = 0;
+            }
+        }
         const unsigned int* work = nullptr;
         if (pr->prune) {
             if ((rc = ensure_buf(&db->d_work, (size_t)((nblocks + 7) / 8 + 2) * 4))) return rc;
@@ -922,6 +939,19 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
                                                : (pr->quad ? (int)std::max<int64_t>(1, std::min<int64_t>(pr->grid, (nblocks + 31) / 32)) : pr->grid),
                                       pr->dyn_smem, pr->lane ? (2 | (pr->lane_warps << 8)) : (pr->quad ? 1 : 0), work, db->stream));
         (*launches)++;
+        if (fused_grid > 0) {
+            // one encoded column projected: offset scan + emit in one small-footprint kernel, resident while the filter kernel runs
+            const bool pdl = !getenv("IMM3_NO_PDL");
+            if (!pdl) {
+                CUDA_TRY(cudaEventRecord(db->ev_mid, db->stream));
+                have_mid = true;
+            }
+            CUDA_TRY(launch_blocks_scan_emit(pr->sp, (const uint32_t*)db->d_bitmap.p, (const uint32_t*)db->d_span_cnt.p, (const uint32_t*)db->d_tile_cnt.p,
+                                             (unsigned long long*)db->d_tile_off.p, nblocks, db->scan_epoch, (unsigned long long*)db->d_scan_part.p,
+                                             db->d_ctrl, (unsigned int*)db->d_tile_list.p, pdl, fused_grid, db->stream));
+            (*launches)++;
+            CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
+        } else {
         if (!pr->sp.scan_inline && (rc = launch_scan_kernel(db, pr->sp, ntiles, launches, true))) return rc;
         const bool pdl = pr->sp.nproj > 0 && !getenv("IMM3_NO_PDL");
         if (!pdl) {
@@ -936,6 +966,7 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
             (*launches)++;
         }
         CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
+        }
     } else if (pr->multipass) {
         if ((pr->sp.debug & 16u) && getenv("IMM3_TRACE")) {  // debugging: phase stamps (min / max over CTAs)
             int rc0 = ensure_buf(&db->d_trace, 64 * 8);

@@ -123,19 +123,17 @@ __device__ void scan_tile_counts(FilterShared& S, const uint32_t* tile_cnt, unsi
 // kScanInlineMaxTiles tiles; the CTA of the last chunk writes the total, the LIMIT clamp and the dense-tile row count.
 constexpr long long kScanInlineMaxTiles = 4 * kComputeThreads * 16;
 
-__global__ void __launch_bounds__(kComputeThreads) offset_scan_kernel(const uint32_t* __restrict__ tile_cnt, unsigned long long* __restrict__ tile_off,
-                                                                     long long ntiles, long long limit, uint32_t epoch,
-                                                                     unsigned long long* __restrict__ partials, ScanCtrl* ctrl,
-                                                                     unsigned int* __restrict__ tile_list) {
+struct ScanShared {
+    unsigned long long s_sum[kComputeWarps], s_dense[kComputeWarps], s_prev[kComputeWarps], s_prevd[kComputeWarps];
+    unsigned int chunk, s_nz[kComputeWarps], lbase;
+};
+// One chunk (4096 tile counts) of the offset scan, by a CTA of kComputeThreads threads (all of them call; contains barriers).
+__device__ __forceinline__ void offset_scan_chunk(ScanShared& SS, long long chunk, const uint32_t* __restrict__ tile_cnt,
+                                                  unsigned long long* __restrict__ tile_off, long long ntiles, long long limit, uint32_t epoch,
+                                                  unsigned long long* __restrict__ partials, ScanCtrl* ctrl, unsigned int* __restrict__ tile_list) {
     constexpr int kRound = kComputeThreads * 16;
-    __shared__ unsigned long long s_sum[kComputeWarps], s_dense[kComputeWarps], s_prev[kComputeWarps], s_prevd[kComputeWarps];
-    __shared__ unsigned int s_chunk, s_nz[kComputeWarps], s_lbase;
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");  // the filter kernel's tile counts are final
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_chunk = atomicAdd(&ctrl->ticket, 1u);
-    __syncthreads();
-    const long long chunk = s_chunk, nchunks = (ntiles + kRound - 1) / kRound, base_i = chunk * kRound;
+    const long long nchunks = (ntiles + kRound - 1) / kRound, base_i = chunk * kRound;
     const int my0 = warp * 512 + lane * 2;  // (same pair layout as scan_tile_counts: every access of a warp is coalesced)
     uint2 c[8];
 #pragma unroll
@@ -171,25 +169,25 @@ __global__ void __launch_bounds__(kComputeThreads) offset_scan_kernel(const uint
             if (lane >= o) incl += nb;
         }
         nz_before = incl - nz;
-        if (lane == 31) s_nz[warp] = incl;
+        if (lane == 31) SS.s_nz[warp] = incl;
     }
     if (lane == 0) {
-        s_sum[warp] = carry;
-        s_dense[warp] = dsum;
+        SS.s_sum[warp] = carry;
+        SS.s_dense[warp] = dsum;
     }
-    __syncthreads();
+    bar_sync(2, kComputeThreads);
     if (tile_list && tid == 0) {
         unsigned tot = 0;
 #pragma unroll
-        for (int w = 0; w < kComputeWarps; w++) tot += s_nz[w];
-        s_lbase = tot ? atomicAdd(&ctrl->ticket2, tot) : 0u;
+        for (int w = 0; w < kComputeWarps; w++) tot += SS.s_nz[w];
+        SS.lbase = tot ? atomicAdd(&ctrl->ticket2, tot) : 0u;
     }
     unsigned long long wbase = 0, chunk_total = 0, chunk_dense = 0;
 #pragma unroll
     for (int w = 0; w < kComputeWarps; w++) {
-        if (w < warp) wbase += s_sum[w];
-        chunk_total += s_sum[w];
-        chunk_dense += s_dense[w];
+        if (w < warp) wbase += SS.s_sum[w];
+        chunk_total += SS.s_sum[w];
+        chunk_dense += SS.s_dense[w];
     }
     constexpr unsigned long long kVal = (1ull << 40) - 1ull;
     const unsigned long long tag = (unsigned long long)(epoch & 0xFFFFFFu) << 40;
@@ -221,20 +219,20 @@ __global__ void __launch_bounds__(kComputeThreads) offset_scan_kernel(const uint
         prevd += __shfl_xor_sync(0xFFFFFFFFu, prevd, o);
     }
     if (lane == 0) {
-        s_prev[warp] = prev;
-        s_prevd[warp] = prevd;
+        SS.s_prev[warp] = prev;
+        SS.s_prevd[warp] = prevd;
     }
-    __syncthreads();
+    bar_sync(2, kComputeThreads);
     unsigned long long base = 0, based = 0;
 #pragma unroll
     for (int w = 0; w < kComputeWarps; w++) {
-        base += s_prev[w];
-        based += s_prevd[w];
+        base += SS.s_prev[w];
+        based += SS.s_prevd[w];
     }
-    if (tile_list) {  // (s_lbase was written before the barrier above)
-        unsigned pos = s_lbase + nz_before;
+    if (tile_list) {  // (SS.lbase was written before the barrier above)
+        unsigned pos = SS.lbase + nz_before;
 #pragma unroll
-        for (int w = 0; w < kComputeWarps; w++) pos += w < warp ? s_nz[w] : 0u;
+        for (int w = 0; w < kComputeWarps; w++) pos += w < warp ? SS.s_nz[w] : 0u;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const unsigned i = (unsigned)(base_i + my0 + 64 * j);
@@ -252,13 +250,26 @@ __global__ void __launch_bounds__(kComputeThreads) offset_scan_kernel(const uint
             *reinterpret_cast<ulonglong2*>(tile_off + i) = o;
         }
     }
-    __syncthreads();
+    bar_sync(2, kComputeThreads);
     if (is_final && tid == 0) {
         const unsigned long long total = base + chunk_total;
         tile_off[ntiles] = total;
         ctrl->total = total < (unsigned long long)limit ? total : (unsigned long long)limit;
         ctrl->dense_rows = based + chunk_dense;
     }
+}
+
+__global__ void __launch_bounds__(kComputeThreads) offset_scan_kernel(const uint32_t* __restrict__ tile_cnt, unsigned long long* __restrict__ tile_off,
+                                                                     long long ntiles, long long limit, uint32_t epoch,
+                                                                     unsigned long long* __restrict__ partials, ScanCtrl* ctrl,
+                                                                     unsigned int* __restrict__ tile_list) {
+    __shared__ ScanShared SS;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the filter kernel's tile counts are final
+    const int tid = threadIdx.x;
+    if (tid == 0) SS.chunk = atomicAdd(&ctrl->ticket, 1u);
+    __syncthreads();
+    offset_scan_chunk(SS, (long long)SS.chunk, tile_cnt, tile_off, ntiles, limit, epoch, partials, ctrl, tile_list);
     if (tid == 0) {
         __threadfence();
         const unsigned done = atomicAdd(&ctrl->exited, 1u);

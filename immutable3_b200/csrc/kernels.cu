@@ -33,6 +33,7 @@ namespace imm3 {
 #include "k_blocks_single.cuh"
 #include "k_multipass.cuh"
 #include "k_blocks_multi.cuh"
+#include "k_blocks_scanemit.cuh"
 #include "k_blocks_filter.cuh"
 #include "k_blocks_lane.cuh"
 #include "k_blocks_prune.cuh"
@@ -222,6 +223,35 @@ cudaError_t launch_offset_scan(const uint32_t* tile_cnt, unsigned long long* til
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, offset_scan_kernel, tile_cnt, tile_off, ntiles, limit, epoch, partials, ctrl, tile_list);
+}
+
+// Offset scan + emit in one kernel (one encoded column projected): a persistent grid of small CTAs, at least one per scan chunk.
+cudaError_t blocks_scan_emit_grid(int num_sms, long long ntiles8, int* grid) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blocks_scan_emit_kernel, kComputeThreads, 0);
+    if (e != cudaSuccess) return e;
+    const long long nchunks = (ntiles8 + kComputeThreads * 16 - 1) / (kComputeThreads * 16);
+    const long long g = (long long)num_sms * occ;
+    *grid = (occ >= 1 && nchunks <= g) ? (int)g : 0;  // 0: does not apply (every chunk CTA has to be resident)
+    return cudaSuccess;
+}
+cudaError_t launch_blocks_scan_emit(const ScanPlan& plan, const uint32_t* bitmapB, const uint32_t* blk_cnt, const uint32_t* tile_cnt,
+                                    unsigned long long* tile_off, long long nblocks, uint32_t epoch, unsigned long long* partials, ScanCtrl* ctrl,
+                                    unsigned int* tile_list, bool pdl, int grid, cudaStream_t stream) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kComputeThreads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, blocks_scan_emit_kernel, plan, bitmapB, blk_cnt, tile_cnt, tile_off, nblocks, epoch, partials, ctrl, tile_list);
 }
 
 size_t blocks_filter_smem_bytes(int nstaged, int tile_cap_bytes, int ring) { return (size_t)ring * (size_t)blk_filter_slot_bytes(nstaged, tile_cap_bytes); }

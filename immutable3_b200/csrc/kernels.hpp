@@ -29,6 +29,10 @@ cudaError_t launch_agg(const AggPlan& a, const uint32_t* bitmap, const uint32_t*
 long long scan_inline_max_tiles();
 cudaError_t launch_offset_scan(const uint32_t* tile_cnt, unsigned long long* tile_off, long long ntiles, long long limit, uint32_t epoch,
                                unsigned long long* partials, ScanCtrl* ctrl, unsigned int* tile_list, cudaStream_t stream);
+cudaError_t blocks_scan_emit_grid(int num_sms, long long ntiles8, int* grid);
+cudaError_t launch_blocks_scan_emit(const ScanPlan& plan, const uint32_t* bitmapB, const uint32_t* blk_cnt, const uint32_t* tile_cnt,
+                                    unsigned long long* tile_off, long long nblocks, uint32_t epoch, unsigned long long* partials, ScanCtrl* ctrl,
+                                    unsigned int* tile_list, bool pdl, int grid, cudaStream_t stream);
 size_t blocks_filter_smem_bytes(int nstaged, int tile_cap_bytes, int ring);
 int blocks_filter_slot_bytes(int nstaged, int tile_cap_bytes);
 size_t blocks_emit_smem_bytes(int npfor, int words_cap);
