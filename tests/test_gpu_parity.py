@@ -633,3 +633,67 @@ def test_offset_scan_kernel_on_large_and_small_tables(tmp_path_factory, world, m
             with eng.execute(Query("b32", Select("age", LT(3)), Project(["id"], lim))) as r:     # row-space filter + block emit
                 want = cb[ca < 3][:lim] if lim else cb[ca < 3]
                 assert r.nrows == len(want) and np.array_equal(r.column(0), want)
+
+
+@pytest.mark.parametrize("scanemit", [True, False])
+def test_dense_sorted_ids_at_every_start_width(tmp_path_factory, scanemit, monkeypatch):
+    """The lane-per-block filter kernel (k_blocks_lane.cuh) reads the wide first mini-block of a dense sorted block with its width
+    B folded into the code (B = 17 .. 31, LDS.128 chunks when blocks are 0 mod 4 words) and walks it generically below that;
+    blocks_scan_emit_kernel decodes the same shape straight from global memory.  Ids that start just below a power of two put
+    both widths into one tile; several segments put 1-row tail blocks at every lane; block size 72 words = the 8-way bank case.
+    Checked against numpy and - IMM3_NO_SCANEMIT=1 - through the general scan + emit kernels as well."""
+    from immutable3_b200.loader import SegmentWriter
+
+    if not scanemit:
+        monkeypatch.setenv("IMM3_NO_SCANEMIT", "1")
+    os.environ.pop("IMM3_PATH", None)
+    d = tmp_path_factory.mktemp("widths")
+    n = 140_001
+    rng = np.random.default_rng(3)
+    tables = {}
+    for i, base in enumerate([0, (1 << 17) - 3000, (1 << 22) - 5000, (1 << 26) - 9000, (1 << 29) - 40_000, (1 << 30) - 70_000, (1 << 31) - 140_001]):
+        ids = (np.arange(n, dtype=np.int64) + base).astype(np.int32)
+        with SegmentWriter(d, f"w{i}", ["id:PFOR_INT"], 1024, 14 + i) as w:  # 14 .. 20 blocks per segment (<= 10 segments: file-name order = id order): tail blocks at many lanes
+            w.append(ids)
+        tables[f"w{i}"] = ids
+    with SegmentManager(d) as sm:
+        eng = Engine(sm)
+        for name, ids in tables.items():
+            b = int(ids[0])
+            windows = [(b + 1000, b + 90_000), (b + 1023, b + 1025), (b + 1024 * 31, b + 1024 * 33 + 1), (b - 5, b + 5), (b + n - 3, b + n + 5),
+                       (b + 33_333, b + 33_334), (b - 10, b + n + 10), (b + 70_000, b + 70_000)]
+            windows += [tuple(sorted(int(x) for x in rng.integers(b, b + n, size=2))) for _ in range(4)]
+            for lo, hi in windows:
+                hi = min(hi, (1 << 31) - 1)  # (constants stay inside the Int range: the narrowing rules have their own test)
+                sel = conj(Select("id", GT(lo)), Select("id", LT(hi)))
+                want = ids[(ids.astype(np.int64) > lo) & (ids.astype(np.int64) < hi)]
+                for limit in (0, 10, 2000, 70_001):
+                    with eng.execute(Query(name, sel, Project(["id"], limit))) as got:
+                        exp = want if limit == 0 else want[:limit]
+                        assert got.nrows == len(exp), (name, lo, hi, limit, got.nrows, len(exp))
+                        assert np.array_equal(got.column(0), exp), (name, lo, hi, limit)
+
+
+def test_scan_emit_kernel_over_several_scan_chunks(tmp_path_factory):
+    """blocks_scan_emit_kernel with more than one scan chunk (3 M rows in blocks of 32 rows: 11.7 K tiles of 8 blocks, 3 chunks of
+    4096), sparse and dense windows, LIMIT cuts inside blocks - gaps of 0 .. 3 between ids give mini-blocks of widths 0 .. 2."""
+    from immutable3_b200.loader import SegmentWriter
+
+    os.environ.pop("IMM3_PATH", None)
+    d = tmp_path_factory.mktemp("chunks")
+    rng = np.random.default_rng(11)
+    n = 3_000_000
+    ids = np.cumsum(rng.integers(0, 4, size=n)).astype(np.int32)
+    with SegmentWriter(d, "c", ["id:PFOR_INT"], 32, 20_000) as w:
+        w.append(ids)
+    with SegmentManager(d) as sm:
+        eng = Engine(sm)
+        top = int(ids[-1])
+        for lo, hi in [(-1, top + 1), (top // 3, top // 3 + 50), (top // 2, top // 2 + 400_000), (top - 10, top + 10), (5, 6)]:
+            sel = conj(Select("id", GT(lo)), Select("id", LT(hi)))
+            want = ids[(ids > lo) & (ids < hi)]
+            for limit in (0, 1, 33, 5000, 1_000_001):
+                with eng.execute(Query("c", sel, Project(["id"], limit))) as got:
+                    exp = want if limit == 0 else want[:limit]
+                    assert got.nrows == len(exp), (lo, hi, limit, got.nrows, len(exp))
+                    assert np.array_equal(got.column(0), exp), (lo, hi, limit)
