@@ -60,6 +60,7 @@ inline double now_us() {
     return (double)ts.tv_sec * 1e6 + (double)ts.tv_nsec * 1e-3;
 }
 thread_local double g_t_launched = 0, g_t_synced = 0;  // stamps taken inside run_scan_once (last launch queued / GPU done)
+thread_local bool g_eager_times = false;               // two-phase LIMIT queries add their phases' device times up: no lazy reading
 
 // Grow-only cache of device / pinned-host buffers: result columns are handed back on
 // imm3_result_free and reused by the next query (cudaMalloc / cudaMallocHost cost milliseconds).
@@ -124,6 +125,8 @@ struct imm3_db {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
     ScanCtrl* d_ctrl = nullptr;   // first member of a device CtrlBlock (ScanCtrl + CommOut)
     CtrlBlock* h_ctrl = nullptr;  // pinned copy, refreshed once per launch sequence
+    unsigned long long pub_seq = 0;  // publish (plan.hpp): sequence number of the last query whose last kernel writes h_ctrl itself
+    unsigned long long ev_seq = 0, query_seq = 0;  // the query ev0 / ev1 were recorded for (device times are read lazily)
     int live_results = 0;         // imm3_result objects that still point at this db (imm3_close refuses while > 0)
     // Count exchange over NVLink peer memory (imm3_comm_*): the local mailbox, every rank's mailbox as mapped here.
     unsigned long long* d_mailbox = nullptr;
@@ -166,7 +169,8 @@ struct imm3_result {
     int64_t fetched = 0;
     int64_t pending = -1;        // rows of an imm3_result_fetch_async still in flight (-1 = none)
     cudaEvent_t copied = nullptr;  // recorded on the copy stream after the last device->host copy
-    double device_ms = 0;
+    double device_ms = 0;            // < 0: not read yet (timing_seq says which query's events hold it)
+    unsigned long long timing_seq = 0;
     double stage_ms[2] = {0, 0};
     double host_us[5] = {0, 0, 0, 0, 0};  // wall clock inside imm3_query_begin: plan, buffers + device plan, launches, wait for the GPU, epilogue
     int launches = 0;
@@ -791,9 +795,11 @@ int ensure_buf(Buf* b, size_t bytes) {
 // Launch the kernels of one query and wait for the match count.
 // Launch the count-exchange kernel of one round (every rank of the communicator must launch the same rounds in the same
 // order).  has_count = 0: this rank ran no kernel in this query (empty slice) and contributes 0.
-int launch_exchange(imm3_db* db, int64_t limit, int has_count) {
+int launch_exchange(imm3_db* db, int64_t limit, int has_count, unsigned long long pub_seq = 0) {
     CommPlan cp;
     std::memset(&cp, 0, sizeof cp);
+    cp.pub = pub_seq ? db->h_ctrl : nullptr;
+    cp.pub_seq = pub_seq;
     for (int i = 0; i < db->world; i++) cp.peer[i] = db->comm_peer[i];
     cp.rank = db->rank;
     cp.world = db->world;
@@ -862,6 +868,10 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
     bool have_mid = false;
     pr->sp.scan_inline = 1;
     *launches = 0;
+    // publish (plan.hpp): the query's last kernel writes the pinned control block itself and the host polls it
+    const bool publish_ok = !getenv("IMM3_NO_PUBLISH");
+    const unsigned long long pub_seq = ++db->pub_seq;
+    bool published = false;
     if (pr->block_mode && pr->hybrid) {
         // dense filter kernel over the row space -> block emit kernel (decodes only blocks with surviving rows)
         TableStore& t = *pr->table;
@@ -903,6 +913,7 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         if ((rc = ensure_buf(&db->d_tile_cnt, ntiles_pad * 4))) return rc;
         if ((rc = ensure_buf(&db->d_tile_off, ntiles_pad * 8))) return rc;
         pr->sp.scan_inline = (scan_inline_for(ntiles) && !(pr->lane && pr->lane_warps < 8)) ? 1 : 0;  // (the inline scan is written for 8 warps)
+        const bool publish_here = publish_ok && !(exchange && db->comm_on);  // (a sharded table: the exchange kernel publishes)
         int fused_grid = 0;  // > 0: offset scan + emit as ONE kernel behind the filter kernel (one encoded column projected)
         if (pr->sp.nproj == 1 && pr->sp.proj[0].pfor_slot >= 0 && !getenv("IMM3_NO_SCANEMIT")) {
             CUDA_TRY(blocks_scan_emit_grid(db->num_sms, ntiles, &fused_grid));
@@ -948,7 +959,9 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
             }
             CUDA_TRY(launch_blocks_scan_emit(pr->sp, (const uint32_t*)db->d_bitmap.p, (const uint32_t*)db->d_span_cnt.p, (const uint32_t*)db->d_tile_cnt.p,
                                              (unsigned long long*)db->d_tile_off.p, nblocks, db->scan_epoch, (unsigned long long*)db->d_scan_part.p,
-                                             db->d_ctrl, (unsigned int*)db->d_tile_list.p, pdl, fused_grid, db->stream));
+                                             db->d_ctrl, (unsigned int*)db->d_tile_list.p, pdl, fused_grid, db->stream,
+                                             publish_here ? db->h_ctrl : nullptr, publish_here ? pub_seq : 0));
+            published = publish_here;
             (*launches)++;
             CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
         } else {
@@ -1044,20 +1057,54 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
     if (exchange && db->comm_on) {
         // The per-rank counts are exchanged by the GPUs themselves (k_comm.cuh), behind the query's last kernel: no host
         // round trip between the kernels and the exchange, one synchronisation per query.
-        int rc = launch_exchange(db, pr->sp.limit, 1);
+        int rc = launch_exchange(db, pr->sp.limit, 1, publish_ok ? pub_seq : 0);
         if (rc) return rc;
         (*launches)++;
         CUDA_TRY(cudaEventRecord(db->ev1, db->stream));  // (re-recorded: the timed span now ends behind the exchange)
+        published = publish_ok;
     }
-    CUDA_TRY(cudaMemcpyAsync(db->h_ctrl, db->d_ctrl, sizeof(CtrlBlock), cudaMemcpyDeviceToHost, db->stream));
-    g_t_launched = now_us();
-    CUDA_TRY(cudaStreamSynchronize(db->stream));
-    g_t_synced = now_us();
+    db->ev_seq = ++db->query_seq;
+    if (published) {
+        g_t_launched = now_us();
+        const volatile unsigned long long* ps = &db->h_ctrl->pub_seq;
+        bool seen = false;
+        for (unsigned spins = 0;; spins++) {
+            const unsigned long long word = __atomic_load_n(ps, __ATOMIC_ACQUIRE);
+            if ((word >> 41) == (pub_seq & 0x7FFFFFull)) {
+                if (!(exchange && db->comm_on)) {  // (blocks_scan_emit_kernel packs what the host needs into the word itself)
+                    db->h_ctrl->c.total = word & ((1ull << 40) - 1ull);
+                    db->h_ctrl->c.error = (word >> 40) & 1u ? 1u : 0u;
+                    db->h_ctrl->c.dense_rows = 0;
+                }
+                seen = true;
+                break;
+            }
+            if ((spins & 0xFFFu) == 0xFFFu && now_us() - g_t_launched > 2e5) break;  // 0.2 s: something is wrong - ask the runtime
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        if (!seen) {  // (a kernel fault, or a peer that never came: the ordinary path reports it)
+            CUDA_TRY(cudaMemcpyAsync(db->h_ctrl, db->d_ctrl, sizeof(CtrlBlock) - sizeof(unsigned long long), cudaMemcpyDeviceToHost, db->stream));
+            CUDA_TRY(cudaStreamSynchronize(db->stream));
+        }
+        g_t_synced = now_us();
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(db->h_ctrl, db->d_ctrl, sizeof(CtrlBlock) - sizeof(unsigned long long), cudaMemcpyDeviceToHost, db->stream));
+        g_t_launched = now_us();
+        CUDA_TRY(cudaStreamSynchronize(db->stream));
+        g_t_synced = now_us();
+    }
     if (db->h_ctrl->c.error) return fail(IMM3_ERR_CUDA, "kernel watchdog fired (code %u)", db->h_ctrl->c.error);
     if (exchange && db->comm_on && db->h_ctrl->x.error)
         return fail(IMM3_ERR_COMM, "count exchange: a peer's count did not arrive within %llu ms (ranks must issue the same queries in the same order)",
                     db->comm_timeout_ns / 1000000ull);
     float f = 0;
+    if (published && !have_mid && !g_eager_times && !getenv("IMM3_EAGER_TIMES")) {
+        *ms = -1.0;  // read lazily (imm3_result_device_ms): the events complete a moment after the publish, waiting for them here costs 2-3 us
+        if (stage_ms) stage_ms[0] = -1.0, stage_ms[1] = 0;
+    } else {
+    if (published) CUDA_TRY(cudaEventSynchronize(db->ev1));
     CUDA_TRY(cudaEventElapsedTime(&f, db->ev0, db->ev1));
     *ms = f;
     if (stage_ms) {
@@ -1070,6 +1117,7 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
             stage_ms[0] = a;
             stage_ms[1] = b;
         }
+    }
     }
     *total = (int64_t)db->h_ctrl->c.total;
     if (pr->multipass && pr->sp.nproj > 0 && pr->emit_stage_bytes > 0)  // feedback for the next query of this shape
@@ -1118,6 +1166,10 @@ int run_scan(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launche
     const bool dense_prefix = !pr->block_mode && pr->multipass && pr->prefix_rows > 0;
     const bool two_phase = comm ? small_limit_policy(pr->lp) : (block_prefix || dense_prefix);
     if (!two_phase) return run_scan_once(db, pr, ms, total, launches, stage_ms, t.nblocks, comm);
+    struct EagerGuard {
+        EagerGuard() { g_eager_times = true; }
+        ~EagerGuard() { g_eager_times = false; }
+    } eager_guard;
     // phase A: the leading blocks / rows only
     const ScanPlan full = pr->sp;
     const int grid_full = pr->grid;
@@ -1440,6 +1492,7 @@ int imm3_query_begin(imm3_db* db, const char* table, const imm3_pred* preds, int
         pr.sp.bitmap = nullptr;
         t_dev = now_us();
         if ((rc = run_scan(db, &pr, &r->device_ms, &r->local_count, &r->launches, r->stage_ms))) { give_back(); return rc; }
+        r->timing_seq = db->ev_seq;
     } else if (db->comm_on && !pr.lp.always_empty) {
         // Empty slice (more ranks than segments): this rank still takes part in every round of the exchange.  (A predicate
         // that can never hold is a property of the query, known to every rank: nobody exchanges anything.)
@@ -1759,10 +1812,29 @@ int imm3_result_col_width(const imm3_result* r, int c) { return (r && c >= 0 && 
 const char* imm3_result_col_name(const imm3_result* r, int c) { return (r && c >= 0 && c < r->ncols) ? r->names[(size_t)c].c_str() : nullptr; }
 const void* imm3_result_col_data(const imm3_result* r, int c) { return (r && c >= 0 && c < r->ncols) ? r->h_cols[(size_t)c].p : nullptr; }
 const void* imm3_result_col_device(const imm3_result* r, int c) { return (r && c >= 0 && c < r->ncols && (size_t)c < r->d_cols.size()) ? r->d_cols[(size_t)c].p : nullptr; }
-double imm3_result_device_ms(const imm3_result* r) { return r ? r->device_ms : -1.0; }
+// Device times of a published query (plan.hpp) are read from the events on first use - as long as no later query has
+// recorded them again (then the figure is gone: -1).
+static void resolve_times(imm3_result* r) {
+    if (r->device_ms >= 0 || !r->db || r->timing_seq == 0 || r->db->ev_seq != r->timing_seq) return;
+    imm3_db* db = r->db;
+    if (use_device(db)) return;
+    float f = 0;
+    if (cudaEventSynchronize(db->ev1) != cudaSuccess || cudaEventElapsedTime(&f, db->ev0, db->ev1) != cudaSuccess) return;
+    r->device_ms = f;
+    r->stage_ms[0] = f;
+}
+double imm3_result_device_ms(const imm3_result* r) {
+    if (!r) return -1.0;
+    resolve_times(const_cast<imm3_result*>(r));
+    return r->device_ms;
+}
 int imm3_result_kernel_launches(const imm3_result* r) { return r ? r->launches : IMM3_ERR_INVALID_ARG; }
 double imm3_result_host_us(const imm3_result* r, int phase) { return (r && phase >= 0 && phase < 5) ? r->host_us[phase] : -1.0; }
-double imm3_result_stage_ms(const imm3_result* r, int stage) { return (r && stage >= 0 && stage < 2) ? r->stage_ms[stage] : -1.0; }
+double imm3_result_stage_ms(const imm3_result* r, int stage) {
+    if (!r || stage < 0 || stage >= 2) return -1.0;
+    resolve_times(const_cast<imm3_result*>(r));
+    return r->stage_ms[stage];
+}
 int64_t imm3_result_algorithmic_bytes(const imm3_result* r) { return r ? r->alg_bytes : IMM3_ERR_INVALID_ARG; }
 
 // Row.toString = xs.mkString("Row(", ",", ")")  (Record.scala:13)

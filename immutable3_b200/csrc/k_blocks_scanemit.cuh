@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kComputeThreads, 4) blocks_scan_emit_kernel(co
                                                                                 const uint32_t* __restrict__ blk_cnt, const uint32_t* __restrict__ tile_cnt,
                                                                                 unsigned long long* __restrict__ tile_off, long long nblocks, uint32_t epoch,
                                                                                 unsigned long long* __restrict__ partials, ScanCtrl* ctrl,
-                                                                                unsigned int* __restrict__ tile_list) {
+                                                                                unsigned int* __restrict__ tile_list, CtrlBlock* pub, unsigned long long pub_seq) {
     __shared__ ScanShared SS;
     __shared__ uint32_t s_scratch[kComputeWarps][128];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // (the count exchange of a sharded table rides behind)
@@ -309,6 +309,13 @@ __global__ void __launch_bounds__(kComputeThreads, 4) blocks_scan_emit_kernel(co
             ctrl->exited = 0;
             ctrl->ticket = 0;
             *done_ctr = 0;
+            if (pub) {  // publish (plan.hpp): no kernel follows - the host is polling its pinned copy of the control block.
+                // ONE posted 8-byte store carries everything it needs - [63:41] sequence, [40] watchdog fired, [39:0] rows - so the
+                // kernel does not have to wait for a system-scope fence before it ends
+                const unsigned long long word = ((pub_seq & 0x7FFFFFull) << 41) | (__ldcg(&ctrl->error) ? (1ull << 40) : 0ull) |
+                                                (__ldcg(&ctrl->total) & ((1ull << 40) - 1ull));
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&pub->pub_seq), "l"(word) : "memory");
+            }
         }
     }
 }

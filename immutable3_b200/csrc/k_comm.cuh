@@ -71,4 +71,24 @@ __global__ void __launch_bounds__(32) count_exchange_kernel(const __grid_constan
         out->error = any_late ? 1u : 0u;
         out->world = (unsigned)C.world;
     }
+    if (C.pub) {  // publish: the whole control block goes to the host's pinned copy, then the sequence number the host polls
+        volatile CtrlBlock* hp = C.pub;
+        if (lane < kMaxWorld) hp->x.counts[lane] = c;
+        if (lane == C.rank) {
+            const unsigned long long off = incl - c, lim = (unsigned long long)C.limit;
+            hp->x.g_offset = off;
+            hp->x.g_take = off >= lim ? 0ull : (lim - off < c ? lim - off : c);
+            hp->x.g_total = sum < lim ? sum : lim;
+            hp->x.error = any_late ? 1u : 0u;
+            hp->x.world = (unsigned)C.world;
+        }
+        if (lane == 0) {
+            hp->c.total = __ldcg(&ctrl->total);
+            hp->c.error = __ldcg(&ctrl->error);
+            hp->c.dense_rows = __ldcg(&ctrl->dense_rows);
+        }
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&C.pub->pub_seq), "l"((C.pub_seq & 0x7FFFFFull) << 41) : "memory");
+    }
 }

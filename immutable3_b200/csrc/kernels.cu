@@ -239,7 +239,7 @@ cudaError_t blocks_scan_emit_grid(int num_sms, long long ntiles8, int* grid) {
 }
 cudaError_t launch_blocks_scan_emit(const ScanPlan& plan, const uint32_t* bitmapB, const uint32_t* blk_cnt, const uint32_t* tile_cnt,
                                     unsigned long long* tile_off, long long nblocks, uint32_t epoch, unsigned long long* partials, ScanCtrl* ctrl,
-                                    unsigned int* tile_list, bool pdl, int grid, cudaStream_t stream) {
+                                    unsigned int* tile_list, bool pdl, int grid, cudaStream_t stream, CtrlBlock* pub, unsigned long long pub_seq) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
@@ -251,7 +251,7 @@ cudaError_t launch_blocks_scan_emit(const ScanPlan& plan, const uint32_t* bitmap
     attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, blocks_scan_emit_kernel, plan, bitmapB, blk_cnt, tile_cnt, tile_off, nblocks, epoch, partials, ctrl, tile_list);
+    return cudaLaunchKernelEx(&cfg, blocks_scan_emit_kernel, plan, bitmapB, blk_cnt, tile_cnt, tile_off, nblocks, epoch, partials, ctrl, tile_list, pub, pub_seq);
 }
 
 size_t blocks_filter_smem_bytes(int nstaged, int tile_cap_bytes, int ring) { return (size_t)ring * (size_t)blk_filter_slot_bytes(nstaged, tile_cap_bytes); }

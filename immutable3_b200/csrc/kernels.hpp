@@ -32,7 +32,8 @@ cudaError_t launch_offset_scan(const uint32_t* tile_cnt, unsigned long long* til
 cudaError_t blocks_scan_emit_grid(int num_sms, long long ntiles8, int* grid);
 cudaError_t launch_blocks_scan_emit(const ScanPlan& plan, const uint32_t* bitmapB, const uint32_t* blk_cnt, const uint32_t* tile_cnt,
                                     unsigned long long* tile_off, long long nblocks, uint32_t epoch, unsigned long long* partials, ScanCtrl* ctrl,
-                                    unsigned int* tile_list, bool pdl, int grid, cudaStream_t stream);
+                                    unsigned int* tile_list, bool pdl, int grid, cudaStream_t stream, CtrlBlock* pub = nullptr,
+                                    unsigned long long pub_seq = 0);
 size_t blocks_filter_smem_bytes(int nstaged, int tile_cap_bytes, int ring);
 int blocks_filter_slot_bytes(int nstaged, int tile_cap_bytes);
 size_t blocks_emit_smem_bytes(int npfor, int words_cap);
