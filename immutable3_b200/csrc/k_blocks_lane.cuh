@@ -275,7 +275,9 @@ __global__ void __launch_bounds__(kLaneWarpsMax * 32, 1) blocks_filter_lane_kern
             stride = w1 - w0;
             nw = (int)stride - 2;
             wa += 4u * (w0 - base_w);
+            IMM3_CHECK(ctrl, n >= 0 && nw >= 1 && wa + 4u * stride <= sl + (uint32_t)slot_bytes + 16u, 1);  // the block lies inside the ring slot
         }
+        IMM3_CHECK(ctrl, (long long)T < nct, 2);
         // the tile's shape is taken from its first block of whole super-blocks (NOT simply from lane 0: the 1-row tail block that
         // ends every segment sits there in one tile of 32, and sending that whole tile through the quad routine cost its warp
         // 25 us - the slow CTAs of every run)

@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(kComputeThreads, ROWSPACE ? 3 : 2) blocks_emit
         // selection vector of the block (ascending rows)
         const int cnt = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(myword));
         const int nn = (int)(P.limit - g < (long long)cnt ? P.limit - g : (long long)cnt);
+        IMM3_CHECK(ctrl, nn >= 0 && (unsigned long long)(g + nn) <= __ldcg(&ctrl->total) && n > 0 && n <= kBlkRows, 7);  // the block's rows fit the result
         // decode the encoded columns of the select list (every row survives: only those emit_dense_block does not take)
         unsigned direct = 0;  // encoded columns already written by emit_dense_block
         if (cnt == n) {
@@ -341,6 +342,7 @@ __global__ void __launch_bounds__(kComputeThreads, ROWSPACE ? 3 : 2) blocks_emit
                 if (cnt == n && (ent & ~direct) == 0u) continue;  // every select-list entry of this column was written directly
             }  // every select-list entry of this column was written directly
             const uint32_t wo0 = wo(s, 0), wo1 = wo(s, 1);
+            IMM3_CHECK(ctrl, wo1 >= wo0 + 3u && (int)(wo1 - wo0) <= P.blk_words_cap, 8);  // the block's words fit the decode scratch
             const uint32_t b = pfor_decode_warp(s_pfor[s].words, wo0, wo1, n, Wb, P.blk_words_cap, vals0 + s * kBlkVals, lane);
             bases[s * 32 + lane] = b;
             __syncwarp();

@@ -196,7 +196,9 @@ __device__ __forceinline__ void lean_emit(const ScanPlan& P, const uint32_t* __r
         long long b = 0;
         bool cand = e < nent;
         if (cand) {
-            b = (long long)__ldcg(tile_list + (e >> 3)) * 8 + (e & 7);
+            const unsigned t8 = __ldcg(tile_list + (e >> 3));
+            IMM3_CHECK(ctrl, (long long)t8 < P.ntiles, 4);  // a list entry is a tile of this table
+            b = (long long)t8 * 8 + (e & 7);
             cand = b < nblocks;
         }
         unsigned long long r0 = 0, r1 = 0, g = 0;
@@ -237,6 +239,7 @@ __device__ __forceinline__ void lean_emit(const ScanPlan& P, const uint32_t* __r
             const long long gb = (long long)__shfl_sync(0xFFFFFFFFu, g, src);
             const int nn = (int)(P.limit - gb < (long long)cnt ? P.limit - gb : (long long)cnt);
             uint32_t* const o = outc + gb;
+            IMM3_CHECK(ctrl, nn >= 0 && (unsigned long long)(gb + nn) <= __ldcg(&ctrl->total) && n > 0 && n <= 1024, 5);  // the block's rows fit the result
             // the filter kernel stores the 32 words of a block only if SOME of its rows survive; all of them: the count says so
             uint32_t S;
             if (cnt == (unsigned)n) {

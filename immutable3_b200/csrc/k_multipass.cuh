@@ -236,6 +236,7 @@ __device__ __forceinline__ void offset_scan_chunk(ScanShared& SS, long long chun
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const unsigned i = (unsigned)(base_i + my0 + 64 * j);
+            IMM3_CHECK(ctrl, (long long)pos + 2 <= ntiles + 2, 9);  // the list holds at most every tile
             if (c[j].x != 0u) tile_list[pos++] = i;
             if (c[j].y != 0u) tile_list[pos++] = i + 1u;
         }

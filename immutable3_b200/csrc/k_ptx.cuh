@@ -106,6 +106,20 @@ __device__ __noinline__ void watchdog_trap(ScanCtrl* ctrl, unsigned code) {
     __trap();
 }
 
+// Device-side bounds checks of the block pipeline, compiled in with -DIMM3_BOUNDS=1 (tests/test_bounds_build.py builds that
+// variant and runs queries through it): compute-sanitizer is not available on this pool, so the kernels check the indices
+// they derive from table metadata themselves - a failed check records 0x100 + its number in ScanCtrl::error and traps.
+#ifdef IMM3_BOUNDS
+#define IMM3_CHECK(ctrl, cond, code)                                              \
+    do {                                                                          \
+        if (!(cond)) watchdog_trap(const_cast<ScanCtrl*>(ctrl), 0x100u + (code)); \
+    } while (0)
+#else
+#define IMM3_CHECK(ctrl, cond, code) \
+    do {                             \
+    } while (0)
+#endif
+
 // try_wait with a suspend-time hint: the hardware parks the warp instead of having it spin through issue slots
 // that the working warps of the SM need.
 __device__ __forceinline__ bool mbar_try_wait_park(uint32_t bar, uint32_t parity) {

@@ -697,3 +697,42 @@ def test_scan_emit_kernel_over_several_scan_chunks(tmp_path_factory):
                     exp = want if limit == 0 else want[:limit]
                     assert got.nrows == len(exp), (lo, hi, limit, got.nrows, len(exp))
                     assert np.array_equal(got.column(0), exp), (lo, hi, limit)
+
+
+def test_baseline_table_at_100m_rows(tmp_path_factory):
+    """BASELINE.json's test_100m (100 M rows, B = 1024, S = 1000: 98 segments, file-name order 0, 1, 10, 11, ...) and its PFOR
+    twin at full size: C2, C3 and C4 against numpy evaluated on the files themselves (the oracle needs seconds per query here)."""
+    d = tmp_path_factory.mktemp("syn100m")
+    n = 100_000_000
+    nseg = (n + 1024 * 1000) // (1024 * 1000 + 1)
+    synth_write(d, "test_100m", n)
+    order = sorted(range(nseg), key=lambda i: f"id_{i}.dat")
+    age = np.concatenate([np.fromfile(d / "test_100m" / f"age_{i}.dat", np.int8) for i in order])
+    ids = np.concatenate([np.fromfile(d / "test_100m" / f"id_{i}.dat", "<i4") for i in order])
+    st = np.concatenate([np.fromfile(d / "test_100m" / f"state_{i}.dat", "S2") for i in order])
+    assert len(ids) == n
+    os.environ.pop("IMM3_PATH", None)
+    m = (age > 18) & (age < 30)
+    lo, hi = n // 2 - n // 200, n // 2 + n // 200
+    mm = (ids > lo) & (ids < hi)
+    with SegmentManager(d) as sm:
+        eng = Engine(sm)
+        with eng.execute(Query("test_100m", conj(Select("age", GT(18)), Select("age", LT(30))), Project(["id", "age"]))) as r:     # C2
+            assert r.nrows == int(m.sum()) and np.array_equal(r.column(0), ids[m]) and np.array_equal(r.column(1), age[m])
+        m3 = m & (st == b"CA")
+        with eng.execute(Query("test_100m", conj(Select("state", Match(["CA"])), Select("age", GT(18)), Select("age", LT(30))),
+                               Project(["id", "state", "age"]))) as r:                                                              # C3
+            assert r.nrows == int(m3.sum()) and np.array_equal(r.column(0), ids[m3]) and np.array_equal(r.column(2), age[m3])
+        with eng.execute(Query("test_100m", conj(Select("id", GT(lo)), Select("id", LT(hi))), Project(["id"]))) as r:              # C4, dense twin
+            assert np.array_equal(r.column(0), ids[mm])
+    del st
+    d2 = tmp_path_factory.mktemp("syn100p")
+    synth_write(d2, "test_1b", n, id_codec=L.CODEC_PFOR_INT)  # (same rows, id in the sorted-integer codec: the north-star table's schema)
+    with SegmentManager(d2) as sm:
+        eng = Engine(sm)
+        for limit in (0, 10, 123_457):
+            with eng.execute(Query("test_1b", conj(Select("id", GT(lo)), Select("id", LT(hi))), Project(["id"], limit))) as r:     # C4
+                exp = ids[mm] if limit == 0 else ids[mm][:limit]
+                assert np.array_equal(r.column(0), exp)
+        with eng.execute(Query("test_1b", conj(Select("age", GT(18)), Select("age", LT(30))), Project(["id", "age"]))) as r:       # C2 on the PFOR table
+            assert r.nrows == int(m.sum()) and np.array_equal(r.column(0), ids[m]) and np.array_equal(r.column(1), age[m])
