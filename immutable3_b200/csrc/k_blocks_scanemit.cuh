@@ -182,12 +182,11 @@ __device__ __noinline__ void emit_any_block(const uint32_t* __restrict__ W, int 
 // The emit phase: warps warp0, warp0 + nwarps, ... of `nwarps` take the entries of the non-empty-tile list.  scratch: 128
 // warp-private words of shared memory.  (Offsets, total and list were written earlier in the SAME kernel, by the
 // chunk CTAs: they are read through L2, never through the non-coherent path.)
-__device__ __forceinline__ void lean_emit(const ScanPlan& P, const uint32_t* __restrict__ bitmapB, const uint32_t* __restrict__ blk_cnt,
+__device__ __forceinline__ void lean_emit(const LeanPlan& P, const uint32_t* __restrict__ bitmapB, const uint32_t* __restrict__ blk_cnt,
                                           const unsigned long long* __restrict__ tile_off, long long nblocks, const ScanCtrl* ctrl,
                                           const unsigned int* __restrict__ tile_list, uint32_t* scratch, long long warp0, long long nwarps, int lane) {
-    const ProjCol pj = P.proj[0];
-    const PforCol pc = P.pfor[pj.pfor_slot <= 0 ? 0 : (pj.pfor_slot == 1 ? 1 : (pj.pfor_slot == 2 ? 2 : 3))];
-    uint32_t* const outc = reinterpret_cast<uint32_t*>(pj.out);
+    struct { const uint32_t* words; const uint32_t* word_off; } pc = {P.words, P.word_off};
+    uint32_t* const outc = reinterpret_cast<uint32_t*>(P.out);
     const long long nent = (long long)__ldcg(&ctrl->ticket2) * 8;
 #pragma unroll 1
     for (long long e0 = warp0; e0 < nent; e0 += 32 * nwarps) {
@@ -256,7 +255,7 @@ __device__ __forceinline__ void lean_emit(const ScanPlan& P, const uint32_t* __r
     }
 }
 
-__global__ void __launch_bounds__(kComputeThreads, 4) blocks_scan_emit_kernel(const __grid_constant__ ScanPlan P, const uint32_t* __restrict__ bitmapB,
+__global__ void __launch_bounds__(kComputeThreads, 4) blocks_scan_emit_kernel(const __grid_constant__ LeanPlan P, const uint32_t* __restrict__ bitmapB,
                                                                                 const uint32_t* __restrict__ blk_cnt, const uint32_t* __restrict__ tile_cnt,
                                                                                 unsigned long long* __restrict__ tile_off, long long nblocks, uint32_t epoch,
                                                                                 unsigned long long* __restrict__ partials, ScanCtrl* ctrl,
@@ -265,8 +264,6 @@ __global__ void __launch_bounds__(kComputeThreads, 4) blocks_scan_emit_kernel(co
     __shared__ uint32_t s_scratch[kComputeWarps][128];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // (the count exchange of a sharded table rides behind)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const ProjCol pj = P.proj[0];
-    const PforCol pc = P.pfor[pj.pfor_slot <= 0 ? 0 : (pj.pfor_slot == 1 ? 1 : (pj.pfor_slot == 2 ? 2 : 3))];
     const long long ntiles8 = P.ntiles;
     const unsigned nchunks = (unsigned)((ntiles8 + kComputeThreads * 16 - 1) / (kComputeThreads * 16));
     // chunks done: a counter on a cache line of its own behind the chunk sums (hundreds of CTAs poll it while the chunk CTAs

@@ -32,7 +32,8 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
                  : "memory");
 }
 // Debugging (IMM3_DEBUG bit 4 + IMM3_TRACE): phase stamps of the multi-pass kernels, min and max over CTAs per event.
-__device__ __forceinline__ void phase_stamp(const ScanPlan& P, int ev) {
+template <class PlanT>
+__device__ __forceinline__ void phase_stamp(const PlanT& P, int ev) {
     if ((P.debug & 16u) && P.trace) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

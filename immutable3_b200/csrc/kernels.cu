@@ -251,7 +251,18 @@ cudaError_t launch_blocks_scan_emit(const ScanPlan& plan, const uint32_t* bitmap
     attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, blocks_scan_emit_kernel, plan, bitmapB, blk_cnt, tile_cnt, tile_off, nblocks, epoch, partials, ctrl, tile_list, pub, pub_seq);
+    LeanPlan lp;
+    const int slot = plan.proj[0].pfor_slot;
+    lp.row_start = plan.row_start;
+    lp.words = plan.pfor[slot].words;
+    lp.word_off = plan.pfor[slot].word_off;
+    lp.out = plan.proj[0].out;
+    lp.limit = plan.limit;
+    lp.ntiles = plan.ntiles;
+    lp.trace = plan.trace;
+    lp.debug = plan.debug;
+    lp.pad = 0;
+    return cudaLaunchKernelEx(&cfg, blocks_scan_emit_kernel, lp, bitmapB, blk_cnt, tile_cnt, tile_off, nblocks, epoch, partials, ctrl, tile_list, pub, pub_seq);
 }
 
 size_t blocks_filter_smem_bytes(int nstaged, int tile_cap_bytes, int ring) { return (size_t)ring * (size_t)blk_filter_slot_bytes(nstaged, tile_cap_bytes); }

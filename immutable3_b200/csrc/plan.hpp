@@ -86,6 +86,19 @@ struct ScanPlan {
     uint8_t lits[kLitPoolBytes];
 };
 
+// What blocks_scan_emit_kernel needs of a plan (k_blocks_scanemit.cuh): a parameter block of 72 bytes instead of ScanPlan's 4 KB.
+struct LeanPlan {
+    const uint64_t* row_start;   // nblocks + 1 canonical row ordinals
+    const uint32_t* words;       // the projected encoded column: big-endian word stream ...
+    const uint32_t* word_off;    // ... and one word offset per block (+ 1)
+    uint8_t* out;                // result column (int32 values)
+    int64_t limit;               // rows wanted (INT64_MAX = unlimited)
+    int64_t ntiles;              // 8-block tiles
+    unsigned long long* trace;   // debugging (IMM3_DEBUG=16 + IMM3_TRACE), else nullptr
+    uint32_t debug;
+    uint32_t pad;
+};
+
 // Block pruning (k_blocks_prune.cuh): exact signed min / max of every block of an encoded INT column, computed on the GPU
 // when the table is opened, and the plan of the kernel that decides whole blocks from them.
 struct alignas(8) BlockStat {
