@@ -259,6 +259,40 @@ __device__ __forceinline__ bool dense_finish(const DenseRegs& r, uint32_t* __res
     return true;
 }
 
+// ... or kept in a form that gives ANY row's value in O(1), for blocks of which only some rows are wanted (a scattered
+// predicate on another column: 10 % of the rows of every block): area[0 .. 31] = the wide mini-block's values, area[32 + 2m],
+// area[33 + 2m] = mini-block m's word and the value before it.  No unpacking of 1024 values, no 4.6 KB of stores.
+__device__ __forceinline__ bool dense_prepare(const DenseRegs& r, uint32_t* area, int lane) {
+    if (r.B < 0) return false;
+    const int B = r.B;
+    const uint32_t off = (uint32_t)(lane * B);
+    const uint32_t hexp = lane == 0 ? (0x01010100u | (uint32_t)B) : 0x01010101u;
+    if (!__all_sync(0xFFFFFFFFu, lane >= 8 || r.hraw == hexp)) return false;
+    uint32_t v = __funnelshift_r(__byte_perm(r.x0, 0, 0x0123), __byte_perm(r.x1, 0, 0x0123), off) & ((1u << B) - 1u);  // field `lane`
+    const uint32_t X = __byte_perm(r.nraw, 0, 0x0123);
+    const uint32_t wide_total = __reduce_add_sync(0xFFFFFFFFu, v);
+    const uint32_t tot = lane == 0 ? wide_total : (uint32_t)__popc(X);
+    uint32_t incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o), u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) {
+            v += t;
+            incl += u;
+        }
+    }
+    area[lane] = v;
+    reinterpret_cast<uint2*>(area + 32)[lane] = make_uint2(X, incl - tot);
+    __syncwarp();
+    return true;
+}
+__device__ __forceinline__ uint32_t dense_value(const uint32_t* area, int row) {
+    const int m = row >> 5, j = row & 31;
+    const uint2 xc = reinterpret_cast<const uint2*>(area + 32)[m];
+    const uint32_t v = xc.y + (uint32_t)__popc(xc.x & ((2u << j) - 1u));
+    return m == 0 ? area[j] : v;
+}
+
 // Emit kernel of the block pipelines: one warp per reference block with at least one surviving row.
 //   ROWSPACE = false : bitmap written by blocks_filter_kernel (32 words per block, block-local alignment); a block's first
 //                      ordinal = tile offset + counts of the tile's earlier blocks.
@@ -317,7 +351,8 @@ __global__ void __launch_bounds__(kComputeThreads, ROWSPACE ? 3 : 2) blocks_emit
         const int nn = (int)(P.limit - g < (long long)cnt ? P.limit - g : (long long)cnt);
         IMM3_CHECK(ctrl, nn >= 0 && (unsigned long long)(g + nn) <= __ldcg(&ctrl->total) && n > 0 && n <= kBlkRows, 7);  // the block's rows fit the result
         // decode the encoded columns of the select list (every row survives: only those emit_dense_block does not take)
-        unsigned direct = 0;  // encoded columns already written by emit_dense_block
+        unsigned direct = 0;       // encoded columns already written by emit_dense_block
+        unsigned dense_slots = 0;  // encoded columns held in dense_prepare's form (partially selected blocks)
         if (cnt == n) {
 #pragma unroll 1
             for (int pc = 0; pc < P.nproj; pc++) {
@@ -342,6 +377,13 @@ __global__ void __launch_bounds__(kComputeThreads, ROWSPACE ? 3 : 2) blocks_emit
                 if (cnt == n && (ent & ~direct) == 0u) continue;  // every select-list entry of this column was written directly
             }  // every select-list entry of this column was written directly
             const uint32_t wo0 = wo(s, 0), wo1 = wo(s, 1);
+            if (cnt != n) {  // some rows only: the dense sorted shape needs no unpacking at all (dense_value)
+                const DenseRegs dr = dense_issue(s_pfor[s].words, wo0, wo1, n, lane);
+                if (dense_prepare(dr, vals0 + s * kBlkVals, lane)) {
+                    dense_slots |= 1u << s;
+                    continue;
+                }
+            }
             IMM3_CHECK(ctrl, wo1 >= wo0 + 3u && (int)(wo1 - wo0) <= P.blk_words_cap, 8);  // the block's words fit the decode scratch
             const uint32_t b = pfor_decode_warp(s_pfor[s].words, wo0, wo1, n, Wb, P.blk_words_cap, vals0 + s * kBlkVals, lane);
             bases[s * 32 + lane] = b;
@@ -385,8 +427,13 @@ __global__ void __launch_bounds__(kComputeThreads, ROWSPACE ? 3 : 2) blocks_emit
                         if (slot >= 0) {
                             const uint32_t* vs = vals0 + slot * kBlkVals;
                             const uint32_t* bs = bases + slot * 32;
+                            if ((dense_slots >> slot) & 1u) {
 #pragma unroll
-                            for (int r = 0; r < 4; r++) v[r][pc] = idx[r] >= 0 ? vs[(idx[r] >> 5) * kBlkLane + (idx[r] & 31)] + bs[idx[r] >> 5] : 0u;
+                                for (int r = 0; r < 4; r++) v[r][pc] = idx[r] >= 0 ? dense_value(vs, idx[r]) : 0u;
+                            } else {
+#pragma unroll
+                                for (int r = 0; r < 4; r++) v[r][pc] = idx[r] >= 0 ? vs[(idx[r] >> 5) * kBlkLane + (idx[r] & 31)] + bs[idx[r] >> 5] : 0u;
+                            }
                         } else {
                             const uint8_t* cbase = s_proj[pc].base + R0 * w;
                             if (w == 4) {
@@ -428,7 +475,8 @@ __global__ void __launch_bounds__(kComputeThreads, ROWSPACE ? 3 : 2) blocks_emit
                     const int row = (int)lds_cell<uint16_t>(sel_addr + 2u * (uint32_t)i);
                     uint8_t* o = s_proj[pc].out + (g + i) * w;
                     if (slot >= 0) {
-                        *reinterpret_cast<uint32_t*>(o) = vals0[slot * kBlkVals + (row >> 5) * kBlkLane + (row & 31)] + bases[slot * 32 + (row >> 5)];
+                        *reinterpret_cast<uint32_t*>(o) = ((dense_slots >> slot) & 1u) ? dense_value(vals0 + slot * kBlkVals, row)
+                                                                                      : vals0[slot * kBlkVals + (row >> 5) * kBlkLane + (row & 31)] + bases[slot * 32 + (row >> 5)];
                     } else {
                         const uint8_t* src = s_proj[pc].base + (R0 + row) * w;
                         for (int b = 0; b < w; b++) o[b] = __ldg(src + b);
