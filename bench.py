@@ -63,11 +63,15 @@ WORKLOADS = {
     "x_all": ("X select id, age (no predicate)", "dense"),
     "x_1pct": ("X select id, age where age = 7", "dense"),
     **{f"x_lt{t}": (f"C5 scattered: select id, age where age < {t} ({t} %)", "dense") for t in (1, 2, 3, 4, 5, 6, 8, 10, 25, 50)},
-    **{f"c5p_lt{t}": (f"C5 scattered on test_1b: select id, age where age < {t} ({t} %)", "pfor") for t in (1, 10, 50)},
-    **{f"c5p_lt{t}_limit10": (f"C5 scattered on test_1b: select id, age where age < {t} limit 10", "pfor") for t in (1, 10)},
+    **{f"c5p_lt{t}": (f"C5 scattered on test_1b: select id, age where age < {t} ({t} %)", "pfor") for t in (1, 10, 50, 100)},
+    **{f"c5p_lt{t}_limit10": (f"C5 scattered on test_1b: select id, age where age < {t} limit 10", "pfor") for t in (1, 10, 50, 100)},
     **{f"c5w_{n}": (f"C5 id window {p} of test_1b: select id where (id > L and id < H)", "pfor")
        for n, p in (("001", "0.01%"), ("01", "0.1%"), ("1", "1%"), ("10", "10%"), ("50", "50%"), ("100", "100%"))},
+    **{f"c5w_{n}_limit10": (f"C5 id window {p} of test_1b: select id where (id > L and id < H) limit 10", "pfor")
+       for n, p in (("001", "0.01%"), ("01", "0.1%"), ("1", "1%"), ("10", "10%"), ("50", "50%"), ("100", "100%"))},
 }
+# --sweep: BASELINE.json configs[4] - selectivity 0.01 % .. 100 % on test_1b, LIMIT 10 vs none, at N GPUs
+SWEEP = [f"c5w_{n}" for n in ("001", "01", "1", "10", "50", "100")] + [f"c5p_lt{t}" for t in (1, 10, 50, 100)] + ["c5_rare"]
 # what the default run measures besides the headline: (record name, workload, table rows)
 AGG_SPECS = {  # workload -> (predicates, aggregates as (op, col) with op 0 = count, 1 = min, 2 = max, group-by columns)
     "agg": ([("age", 1, 18)], [(1, "age"), (2, "age")], ["state"]),
@@ -82,8 +86,8 @@ def query_spec(workload: str, total_rows: int):
     """(predicates as (col, op, value), projection, limit) - plain data, shared by both arms."""
     GT, LT, EQ, MATCH = 1, 2, 3, 4
     age_range = [("age", GT, 18), ("age", LT, 30)]
-    if workload in ("c4", "c4dense", "c4_limit10") or workload in WINDOW_FRAC:
-        frac = WINDOW_FRAC.get(workload, 0.01)
+    if workload in ("c4", "c4dense", "c4_limit10") or workload.replace("_limit10", "") in WINDOW_FRAC:
+        frac = WINDOW_FRAC.get(workload.replace("_limit10", ""), 0.01)
         half = int(total_rows * frac / 2)
         lo, hi = total_rows // 2 - half, total_rows // 2 + half
         if frac >= 1.0:
@@ -331,6 +335,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="C5: the selectivity sweep on test_1b (id windows 0.01 % .. 100 %, age < t, state + age), "
+                    "LIMIT 10 vs none, instead of the headline run; one JSON line with a `sweep` table")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-tma", action="store_true", help="direct-load variant of the dense kernels (A/B)")
     ap.add_argument("--cpu-steps", type=int, default=2)
@@ -515,13 +521,57 @@ def main():
         ok = got == want and (limit > 0 or take == oracle_result.nrows) and offset == sum(counts[:rank])
         return bool(ok)
 
+    # ---- C5: the selectivity sweep (its own JSON line; the headline protocol per point, fewer steps) ----
+    if args.sweep:
+        total = args.rows * (world if args.scaling == "weak" else 1)
+        table = []
+        peak, peak_src = measured_peak()
+        for wl in SWEEP:
+            for lim in ("", "_limit10"):
+                name = wl + lim
+                try:
+                    rec, _, sctx = measure(name, total, max(5, args.steps // 2), 3, prune=True)  # (the library's defaults: pruning on)
+                    row = {"point": name, "query": WORKLOADS[name][0], "result_rows": rec["result_rows"], "selectivity": rec["result_rows"] / total if not lim else None,
+                           "wall_ms": rec["ms_per_step"], "device_ms": rec["device_ms"]["median"], "rows_per_s": rec["value"],
+                           "gpu_launches_per_query": rec["gpu_launches"] / max(1, rec["steps"]) / world, "roofline_frac_rank0": rec["roofline"]["frac"],
+                           "algorithmic_bytes_rank0": rec["roofline"]["algorithmic_bytes_per_launch"]}
+                    if not lim and name.startswith("c5w_"):  # id windows: also the plain scan (every block decided from its encoded bytes)
+                        rec2, _, _ = measure(name, total, max(5, args.steps // 2), 3, prune=False)
+                        row["unpruned"] = {"wall_ms": rec2["ms_per_step"], "device_ms": rec2["device_ms"]["median"], "rows_per_s": rec2["value"],
+                                           "roofline_frac_rank0": rec2["roofline"]["frac"]}
+                    if not args.no_verify and rec["result_rows"] <= 50_000_000:
+                        ok = verify(load_oracle(), name, total, sctx, max(1, cores // world))
+                        if world > 1:
+                            everyone = [None] * world
+                            dist.all_gather_object(everyone, ok)
+                            ok = all(everyone)
+                        row["result_equal"] = ok
+                    table.append(row)
+                except Exception as e:
+                    table.append({"point": name, "error": repr(e)})
+        if rank == 0:
+            pts = [r for r in table if "rows_per_s" in r]
+            print(json.dumps({"metric": METRIC, "value": statistics.median([r["rows_per_s"] for r in pts]) if pts else None, "unit": "rows/s", "n_gpus": world,
+                              "steps": max(5, args.steps // 2), "warmup": 3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+                              "dtype": "u8", "data": "synthetic",
+                              "config": {"workload": "C5 selectivity sweep on test_1b (id:PFOR_INT, state:DENSE_STRING:2, age:DENSE_TINYINT), LIMIT 10 vs none",
+                                         "rows_total": total, "segments": nsegments(total), "sharding": "contiguous canonical segment slices, one per GPU",
+                                         "l2": "flushed between steps", "value_is": "median rows/s over the sweep points (wall: barrier -> query + count exchange done)",
+                                         "peak_gbs": peak, "peak_source": peak_src},
+                              "sweep": table}))
+        for v in opened.values():
+            v[0].close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
     # ---- headline: value = wall (barrier -> query + exchange done), K steps ----
     total = args.rows * (world if args.scaling == "weak" else 1)
     head, clocks, ctx = measure(args.workload, total, args.steps, args.warmup, sample_clocks=True)
     sm, eng, d, table, tinfo, query, prep, local_rows, take = ctx
     open_s, gen_s = opened[(WORKLOADS[args.workload][1], total)][5:7]
     agg_head = args.workload in AGG_SPECS
-    st0, st1 = (None, None) if agg_head else stage_times(eng, prep)
+    st0, st1 = (None, None) if (agg_head or os.environ.get("IMM3_BENCH_NO_STAGES")) else stage_times(eng, prep)
     kind = WORKLOADS[args.workload][1]
     on_pfor_filter = kind == "pfor" and any(l.col == "id" for l in flatten_select(query.select))
     kname = ("filter_kernel -> agg_kernel -> agg_compact_kernel" if agg_head else

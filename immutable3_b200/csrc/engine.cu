@@ -146,6 +146,7 @@ struct imm3_db {
     Buf d_work;                              // blocks_prune_kernel: work list of tiles for the filter kernel ([0] = count)
     Buf d_scan_part;                         // offset_scan_kernel: epoch-tagged chunk sums (zeroed when (re)allocated)
     Buf d_tile_list;                         // offset_scan_kernel (block pipeline): the non-empty tiles, for the emit kernel
+    Buf d_grp_sum;                           // blocks_group_emit_kernel: match counts per group of 1024 blocks (zero between queries)
     uint32_t scan_epoch = 0;
     Buf d_trace;                             // IMM3_TRACE debugging buffer
     // Emit-kernel feedback: result density class (1 dense, 0 sparse) last seen for a query shape (table, filter
@@ -433,6 +434,7 @@ void free_device_side(imm3_db* db) {
     if (db->d_trace.p) cudaFree(db->d_trace.p);
     if (db->d_scan_part.p) cudaFree(db->d_scan_part.p);
     if (db->d_tile_list.p) cudaFree(db->d_tile_list.p);
+    if (db->d_grp_sum.p) cudaFree(db->d_grp_sum.p);
     if (db->d_work.p) cudaFree(db->d_work.p);
     if (db->d_agg_table.p) cudaFree(db->d_agg_table.p);
     if (db->d_agg_out.p) cudaFree(db->d_agg_out.p);
@@ -908,20 +910,32 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         const int64_t nblocks = nblocks_use, ntiles = pr->sp.ntiles;
         int rc;
         if ((rc = ensure_buf(&db->d_bitmap, (size_t)(nblocks * 32 + 2) * 4))) return rc;
-        if ((rc = ensure_buf(&db->d_span_cnt, (size_t)(nblocks + 8) * 4))) return rc;
+        if ((rc = ensure_buf(&db->d_span_cnt, (size_t)(nblocks + 8 + 1024) * 4))) return rc;  // (+ whole 16-byte loads of a group's counts)
         const size_t ntiles_pad = ((size_t)ntiles + 4095) / 4096 * 4096 + 16;  // whole rounds of the offset scan
         if ((rc = ensure_buf(&db->d_tile_cnt, ntiles_pad * 4))) return rc;
         if ((rc = ensure_buf(&db->d_tile_off, ntiles_pad * 8))) return rc;
         pr->sp.scan_inline = (scan_inline_for(ntiles) && !(pr->lane && pr->lane_warps < 8)) ? 1 : 0;  // (the inline scan is written for 8 warps)
         const bool publish_here = publish_ok && !(exchange && db->comm_on);  // (a sharded table: the exchange kernel publishes)
         int fused_grid = 0;  // > 0: offset scan + emit as ONE kernel behind the filter kernel (one encoded column projected)
+        int group_grid = 0, ngroups = 0;  // > 0: no offset scan at all - blocks_group_emit_kernel behind the lane kernel
         if (pr->sp.nproj == 1 && pr->sp.proj[0].pfor_slot >= 0 && !getenv("IMM3_NO_SCANEMIT")) {
-            CUDA_TRY(blocks_scan_emit_grid(db->num_sms, ntiles, &fused_grid));
-            if (fused_grid > 0) {
-                if ((rc = prepare_scan_buffers(db, ntiles, true))) return rc;
+            if (pr->lane && !getenv("IMM3_NO_GROUPEMIT")) CUDA_TRY(blocks_group_emit_grid(db->num_sms, nblocks, &group_grid, &ngroups));
+            if (group_grid > 0) {
+                if (!db->d_grp_sum.p) {
+                    CUDA_TRY(cudaMalloc(&db->d_grp_sum.p, blocks_group_sum_bytes()));
+                    db->d_grp_sum.cap = blocks_group_sum_bytes();
+                    CUDA_TRY(cudaMemsetAsync(db->d_grp_sum.p, 0, db->d_grp_sum.cap, db->stream));
+                }
                 pr->sp.scan_inline = 0;
+            } else {
+                CUDA_TRY(blocks_scan_emit_grid(db->num_sms, ntiles, &fused_grid));
+                if (fused_grid > 0) {
+                    if ((rc = prepare_scan_buffers(db, ntiles, true))) return rc;
+                    pr->sp.scan_inline = 0;
+                }
             }
         }
+        uint32_t* const grp_sum = group_grid > 0 ? (uint32_t*)db->d_grp_sum.p : nullptr;
         const unsigned int* work = nullptr;
         if (pr->prune) {
             if ((rc = ensure_buf(&db->d_work, (size_t)((nblocks + 7) / 8 + 2) * 4))) return rc;
@@ -941,16 +955,28 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
             // whole blocks decided from their min / max; only the tiles a window edge cuts through reach the filter kernel
             CUDA_TRY(cudaMemsetAsync(db->d_work.p, 0, 4, db->stream));
             CUDA_TRY(launch_blocks_prune(pr->pp, t.d_row_start, nblocks, ntiles, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
-                                         (unsigned int*)db->d_work.p, db->num_sms, db->stream));
+                                         (unsigned int*)db->d_work.p, db->num_sms, db->stream, grp_sum));
             (*launches)++;
         }
         CUDA_TRY(launch_blocks_filter(pr->sp, (uint32_t*)db->d_bitmap.p, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
                                       (unsigned long long*)db->d_tile_off.p, db->d_ctrl, nblocks,
                                       pr->lane ? (int)std::max<int64_t>(1, std::min<int64_t>(pr->grid, (nblocks + 32 * pr->lane_warps - 1) / (32 * pr->lane_warps)))
                                                : (pr->quad ? (int)std::max<int64_t>(1, std::min<int64_t>(pr->grid, (nblocks + 31) / 32)) : pr->grid),
-                                      pr->dyn_smem, pr->lane ? (2 | (pr->lane_warps << 8)) : (pr->quad ? 1 : 0), work, db->stream));
+                                      pr->dyn_smem, pr->lane ? (2 | (pr->lane_warps << 8)) : (pr->quad ? 1 : 0), work, db->stream, grp_sum));
         (*launches)++;
-        if (fused_grid > 0) {
+        if (group_grid > 0) {
+            // one encoded column projected, lane kernel in front: every emit warp finds its rows from the group sums - no scan
+            const bool pdl = !getenv("IMM3_NO_PDL");
+            if (!pdl) {
+                CUDA_TRY(cudaEventRecord(db->ev_mid, db->stream));
+                have_mid = true;
+            }
+            CUDA_TRY(launch_blocks_group_emit(pr->sp, (const uint32_t*)db->d_bitmap.p, (const uint32_t*)db->d_span_cnt.p, grp_sum, nblocks, ngroups,
+                                              db->d_ctrl, pdl, group_grid, db->stream, publish_here ? db->h_ctrl : nullptr, publish_here ? pub_seq : 0));
+            published = publish_here;
+            (*launches)++;
+            CUDA_TRY(cudaEventRecord(db->ev1, db->stream));
+        } else if (fused_grid > 0) {
             // one encoded column projected: offset scan + emit in one small-footprint kernel, resident while the filter kernel runs
             const bool pdl = !getenv("IMM3_NO_PDL");
             if (!pdl) {

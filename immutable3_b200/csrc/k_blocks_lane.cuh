@@ -167,7 +167,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __global__ void __launch_bounds__(kLaneWarpsMax * 32, 1) blocks_filter_lane_kernel(const __grid_constant__ ScanPlan P, uint32_t* __restrict__ bitmapB,
                                                                                 uint32_t* __restrict__ blk_cnt, uint32_t* __restrict__ tile_cnt,
                                                                                 unsigned long long* __restrict__ tile_off, ScanCtrl* ctrl,
-                                                                                long long nblocks, const unsigned int* __restrict__ work) {
+                                                                                long long nblocks, const unsigned int* __restrict__ work, uint32_t* __restrict__ grp_sum) {
     __shared__ FilterShared S;
     __shared__ unsigned long long s_bar[kLaneWarpsMax][kLaneStages];
     __shared__ __align__(16) int s_meta[kLaneWarpsMax][8][4];  // per warp, a ring of work items: {32-block tile (-1: none), its first word offset, its end, -}
@@ -407,6 +407,11 @@ __global__ void __launch_bounds__(kLaneWarpsMax * 32, 1) blocks_filter_lane_kern
         if (!counted) c8 = c8_fallback;
         const long long t8 = (blk0 >> 3) + (lane >> 3);
         if ((lane & 7) == 0 && t8 < ntiles8) tile_cnt[t8] = c8;
+        if (grp_sum) {  // blocks_group_emit_kernel follows: this tile's rows join the sum of its group of 1024 blocks (fire and forget)
+            unsigned c32 = c8 + __shfl_xor_sync(0xFFFFFFFFu, c8, 8);
+            c32 += __shfl_xor_sync(0xFFFFFFFFu, c32, 16);
+            if (lane == 0 && c32 != 0u) atomicAdd(grp_sum + (blk0 >> 10), c32);
+        }
         __syncwarp();
         pslot = slot;
         if (++slot == nstages) { slot = 0; use++; }

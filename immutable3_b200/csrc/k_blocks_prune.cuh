@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kComputeThreads) block_stats_kernel(PforCol pc
 // One lane per block, one warp per 32 consecutive blocks.  work[0] = number of listed tiles, work[1 ..] = their indices.
 __global__ void __launch_bounds__(kComputeThreads) blocks_prune_kernel(const __grid_constant__ PrunePlan Q, const uint64_t* __restrict__ row_start,
                                                                       long long nblocks, long long ntiles8, uint32_t* __restrict__ blk_cnt,
-                                                                      uint32_t* __restrict__ tile_cnt, unsigned int* __restrict__ work) {
+                                                                      uint32_t* __restrict__ tile_cnt, unsigned int* __restrict__ work, uint32_t* __restrict__ grp_sum) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long ngroups32 = (nblocks + 31) >> 5;
@@ -86,5 +86,10 @@ __global__ void __launch_bounds__(kComputeThreads) blocks_prune_kernel(const __g
         c8 += __shfl_xor_sync(0xFFFFFFFFu, c8, 2);
         c8 += __shfl_xor_sync(0xFFFFFFFFu, c8, 4);
         if (!listed && (lane & 7) == 0 && T * 4 + (lane >> 3) < ntiles8) tile_cnt[T * 4 + (lane >> 3)] = c8;
+        if (grp_sum && Q.group_shift == 5) {  // (blocks_group_emit_kernel follows; a listed tile is counted by the filter kernel)
+            unsigned c32 = c8 + __shfl_xor_sync(0xFFFFFFFFu, c8, 8);
+            c32 += __shfl_xor_sync(0xFFFFFFFFu, c32, 16);
+            if (lane == 0 && !listed && c32 != 0u) atomicAdd(grp_sum + (T >> 5), c32);
+        }
     }
 }

@@ -34,6 +34,7 @@ namespace imm3 {
 #include "k_multipass.cuh"
 #include "k_blocks_multi.cuh"
 #include "k_blocks_scanemit.cuh"
+#include "k_blocks_groupemit.cuh"
 #include "k_blocks_filter.cuh"
 #include "k_blocks_lane.cuh"
 #include "k_blocks_prune.cuh"
@@ -176,10 +177,10 @@ cudaError_t launch_block_stats(const PforCol& pc, const uint64_t* row_start, lon
     return cudaGetLastError();
 }
 cudaError_t launch_blocks_prune(const PrunePlan& q, const uint64_t* row_start, long long nblocks, long long ntiles8, uint32_t* blk_cnt,
-                                uint32_t* tile_cnt, unsigned int* work, int num_sms, cudaStream_t stream) {
+                                uint32_t* tile_cnt, unsigned int* work, int num_sms, cudaStream_t stream, uint32_t* grp_sum) {
     const long long groups = (nblocks + 31) / 32;
     const long long grid = std::max<long long>(1, std::min<long long>((groups + kComputeWarps - 1) / kComputeWarps, (long long)num_sms * 8));
-    blocks_prune_kernel<<<(unsigned)grid, kComputeThreads, 0, stream>>>(q, row_start, nblocks, ntiles8, blk_cnt, tile_cnt, work);
+    blocks_prune_kernel<<<(unsigned)grid, kComputeThreads, 0, stream>>>(q, row_start, nblocks, ntiles8, blk_cnt, tile_cnt, work, grp_sum);
     return cudaGetLastError();
 }
 
@@ -265,6 +266,47 @@ cudaError_t launch_blocks_scan_emit(const ScanPlan& plan, const uint32_t* bitmap
     return cudaLaunchKernelEx(&cfg, blocks_scan_emit_kernel, lp, bitmapB, blk_cnt, tile_cnt, tile_off, nblocks, epoch, partials, ctrl, tile_list, pub, pub_seq);
 }
 
+// Emit without an offset scan (k_blocks_groupemit.cuh): a persistent grid of small CTAs next to the filter kernel.
+int blocks_group_emit_max_groups() { return kGrpMaxGroups; }
+size_t blocks_group_sum_bytes() { return (size_t)kGrpSumWords * 4; }
+cudaError_t blocks_group_emit_grid(int num_sms, long long nblocks, int* grid, int* ngroups) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blocks_group_emit_kernel, kComputeThreads, 0);
+    if (e != cudaSuccess) return e;
+    const long long ng = (nblocks + (1ll << kGrpShift) - 1) >> kGrpShift;
+    *ngroups = (int)std::min<long long>(ng, kGrpMaxGroups);
+    *grid = (occ >= 1 && ng <= kGrpMaxGroups) ? num_sms * occ : 0;  // 0: does not apply
+    return cudaSuccess;
+}
+cudaError_t launch_blocks_group_emit(const ScanPlan& plan, const uint32_t* bitmapB, const uint32_t* blk_cnt, uint32_t* grp_sum, long long nblocks,
+                                     int ngroups, ScanCtrl* ctrl, bool pdl, int grid, cudaStream_t stream, CtrlBlock* pub, unsigned long long pub_seq) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kComputeThreads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LeanPlan lp;
+    const int slot = plan.proj[0].pfor_slot;
+    lp.row_start = plan.row_start;
+    lp.words = plan.pfor[slot].words;
+    lp.word_off = plan.pfor[slot].word_off;
+    lp.out = plan.proj[0].out;
+    lp.limit = plan.limit;
+    lp.ntiles = plan.ntiles;
+    lp.trace = plan.trace;
+    lp.debug = plan.debug;
+    lp.pad = 0;
+    return cudaLaunchKernelEx(&cfg, blocks_group_emit_kernel, lp, bitmapB, blk_cnt, grp_sum, nblocks, ngroups, ctrl, pub, pub_seq);
+}
+
 size_t blocks_filter_smem_bytes(int nstaged, int tile_cap_bytes, int ring) { return (size_t)ring * (size_t)blk_filter_slot_bytes(nstaged, tile_cap_bytes); }
 int blocks_filter_slot_bytes(int nstaged, int tile_cap_bytes) { return blk_filter_slot_bytes(nstaged, tile_cap_bytes); }
 size_t blocks_emit_smem_bytes(int npfor, int words_cap) { return (size_t)kComputeWarps * blk_emit_warp_words(npfor, words_cap) * 4; }
@@ -283,10 +325,10 @@ cudaError_t blocks_multi_occupancy(size_t filter_smem, size_t emit_smem, int* fi
 }
 cudaError_t launch_blocks_filter(const ScanPlan& plan, uint32_t* bitmapB, uint32_t* blk_cnt, uint32_t* tile_cnt, unsigned long long* tile_off,
                                  ScanCtrl* ctrl, long long nblocks, int grid, size_t dyn_smem, int mode, const unsigned int* work,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, uint32_t* grp_sum) {
     cudaError_t e = configure_once();
     if (e != cudaSuccess) return e;
-    if (mode >= 2) blocks_filter_lane_kernel<<<grid, (mode >> 8) * 32, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks, work);
+    if (mode >= 2) blocks_filter_lane_kernel<<<grid, (mode >> 8) * 32, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks, work, grp_sum);
     else if (mode == 1) blocks_filter_quad_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks, work);
     else blocks_filter_kernel<<<grid, kComputeThreads + 32, dyn_smem, stream>>>(plan, bitmapB, blk_cnt, tile_cnt, tile_off, ctrl, nblocks, work);
     return cudaGetLastError();

@@ -34,6 +34,12 @@ cudaError_t launch_blocks_scan_emit(const ScanPlan& plan, const uint32_t* bitmap
                                     unsigned long long* tile_off, long long nblocks, uint32_t epoch, unsigned long long* partials, ScanCtrl* ctrl,
                                     unsigned int* tile_list, bool pdl, int grid, cudaStream_t stream, CtrlBlock* pub = nullptr,
                                     unsigned long long pub_seq = 0);
+int blocks_group_emit_max_groups();
+size_t blocks_group_sum_bytes();
+cudaError_t blocks_group_emit_grid(int num_sms, long long nblocks, int* grid, int* ngroups);
+cudaError_t launch_blocks_group_emit(const ScanPlan& plan, const uint32_t* bitmapB, const uint32_t* blk_cnt, uint32_t* grp_sum, long long nblocks,
+                                     int ngroups, ScanCtrl* ctrl, bool pdl, int grid, cudaStream_t stream, CtrlBlock* pub = nullptr,
+                                     unsigned long long pub_seq = 0);
 size_t blocks_filter_smem_bytes(int nstaged, int tile_cap_bytes, int ring);
 int blocks_filter_slot_bytes(int nstaged, int tile_cap_bytes);
 size_t blocks_emit_smem_bytes(int npfor, int words_cap);
@@ -41,11 +47,11 @@ int blocks_filter_quad_slot_bytes(int tile_cap_bytes);
 cudaError_t blocks_multi_occupancy(size_t filter_smem, size_t emit_smem, int* filter_blocks_per_sm, int* emit_blocks_per_sm, int mode, bool rowspace);  // mode 0: lane = mini-block, 1: quad, 2 | warps << 8: lane = block with that many warps per CTA
 cudaError_t launch_blocks_filter(const ScanPlan& plan, uint32_t* bitmapB, uint32_t* blk_cnt, uint32_t* tile_cnt, unsigned long long* tile_off,
                                  ScanCtrl* ctrl, long long nblocks, int grid, size_t dyn_smem, int mode, const unsigned int* work,
-                                 cudaStream_t stream);
+                                 cudaStream_t stream, uint32_t* grp_sum = nullptr);  // grp_sum: blocks_group_emit_kernel follows (lane mode only)
 cudaError_t launch_block_stats(const PforCol& pc, const uint64_t* row_start, long long nblocks, int words_cap, int num_sms, BlockStat* stats,
                                cudaStream_t stream);
 cudaError_t launch_blocks_prune(const PrunePlan& q, const uint64_t* row_start, long long nblocks, long long ntiles8, uint32_t* blk_cnt,
-                                uint32_t* tile_cnt, unsigned int* work, int num_sms, cudaStream_t stream);
+                                uint32_t* tile_cnt, unsigned int* work, int num_sms, cudaStream_t stream, uint32_t* grp_sum = nullptr);
 // rowspace: the bitmap / counts come from the dense filter kernel (row space), not from blocks_filter_kernel (block-local)
 cudaError_t launch_blocks_emit(const ScanPlan& plan, const uint32_t* bitmap, const uint32_t* cnts, const unsigned int* tile_list, const unsigned long long* tile_off,
                                long long nblocks, const ScanCtrl* ctrl, bool rowspace, bool pdl, int grid, size_t dyn_smem,

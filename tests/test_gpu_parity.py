@@ -674,11 +674,15 @@ def test_dense_sorted_ids_at_every_start_width(tmp_path_factory, scanemit, monke
                         assert np.array_equal(got.column(0), exp), (name, lo, hi, limit)
 
 
-def test_scan_emit_kernel_over_several_scan_chunks(tmp_path_factory):
+@pytest.mark.parametrize("groupemit", [True, False])
+def test_scan_emit_kernel_over_several_scan_chunks(tmp_path_factory, groupemit, monkeypatch):
     """blocks_scan_emit_kernel with more than one scan chunk (3 M rows in blocks of 32 rows: 11.7 K tiles of 8 blocks, 3 chunks of
-    4096), sparse and dense windows, LIMIT cuts inside blocks - gaps of 0 .. 3 between ids give mini-blocks of widths 0 .. 2."""
+    4096), sparse and dense windows, LIMIT cuts inside blocks - gaps of 0 .. 3 between ids give mini-blocks of widths 0 .. 2.
+    By default blocks_group_emit_kernel serves these queries (92 groups of 1024 blocks); IMM3_NO_GROUPEMIT=1 keeps the scan-emit kernel."""
     from immutable3_b200.loader import SegmentWriter
 
+    if not groupemit:
+        monkeypatch.setenv("IMM3_NO_GROUPEMIT", "1")
     os.environ.pop("IMM3_PATH", None)
     d = tmp_path_factory.mktemp("chunks")
     rng = np.random.default_rng(11)
@@ -697,6 +701,66 @@ def test_scan_emit_kernel_over_several_scan_chunks(tmp_path_factory):
                     exp = want if limit == 0 else want[:limit]
                     assert got.nrows == len(exp), (lo, hi, limit, got.nrows, len(exp))
                     assert np.array_equal(got.column(0), exp), (lo, hi, limit)
+
+
+@pytest.mark.parametrize("prune", [True, False])
+def test_group_emit_kernel_many_blocks_per_cta(tmp_path_factory, prune, monkeypatch):
+    """blocks_group_emit_kernel (k_blocks_groupemit.cuh): 8 M rows in blocks of 32 rows = 250 K blocks in 245 groups - a CTA's share
+    of a group exceeds its 256-entry queue (several rounds), CTA ranges span group boundaries, LIMIT cuts fall inside blocks and
+    on block / group boundaries; a second table whose every block is partially selected (bitmap words for every block); both
+    with and without block pruning (the prune kernel adds the group sums of the blocks it decides)."""
+    from immutable3_b200.loader import SegmentWriter
+
+    if not prune:
+        monkeypatch.setenv("IMM3_NO_PRUNE", "1")
+    os.environ.pop("IMM3_PATH", None)
+    d = tmp_path_factory.mktemp("groups")
+    rng = np.random.default_rng(23)
+    n = 8_000_000
+    ids = np.cumsum(rng.integers(0, 3, size=n)).astype(np.int32)
+    with SegmentWriter(d, "g", ["id:PFOR_INT"], 32, 50_000) as w:
+        w.append(ids)
+    m = 600_000
+    saw = ((np.arange(m) % 64) * 3 + (np.arange(m) // 64) % 2).astype(np.int32)  # every 32-row block holds half a ramp
+    with SegmentWriter(d, "saw", ["id:PFOR_INT"], 32, 3_000) as w:
+        w.append(saw)
+    with SegmentManager(d) as sm:
+        eng = Engine(sm)
+        top = int(ids[-1])
+        for lo, hi in [(-1, top + 1), (top // 4, 3 * (top // 4)), (top // 2, top // 2 + 70), (int(ids[32 * 1024 * 7]) - 1, int(ids[32 * 1024 * 9]))]:
+            sel = conj(Select("id", GT(lo)), Select("id", LT(hi)))
+            want = ids[(ids > lo) & (ids < hi)]
+            for limit in (0, 1, 32 * 1024, 32 * 1024 + 5, 4_000_000):
+                with eng.execute(Query("g", sel, Project(["id"], limit))) as got:
+                    exp = want if limit == 0 else want[:limit]
+                    assert got.nrows == len(exp), (lo, hi, limit, got.nrows, len(exp))
+                    assert np.array_equal(got.column(0), exp), (lo, hi, limit)
+        for lo, hi in [(20, 170), (-1, 50), (95, 97), (190, 1000)]:
+            sel = conj(Select("id", GT(lo)), Select("id", LT(hi)))
+            want = saw[(saw > lo) & (saw < hi)]
+            for limit in (0, 77, 100_000):
+                with eng.execute(Query("saw", sel, Project(["id"], limit))) as got:
+                    exp = want if limit == 0 else want[:limit]
+                    assert got.nrows == len(exp), ("saw", lo, hi, limit, got.nrows, len(exp))
+                    assert np.array_equal(got.column(0), exp), ("saw", lo, hi, limit)
+    if prune:
+        return
+    # more than 1024 groups (34 M rows in blocks of 32): the group sums do not fit the kernel's shared-memory copy - eight per
+    # thread in the CTA's scan, look-aheads from global memory
+    big = np.cumsum(rng.integers(0, 2, size=34_000_000)).astype(np.int32)
+    with SegmentWriter(d, "big", ["id:PFOR_INT"], 32, 200_000) as w:
+        w.append(big)
+    with SegmentManager(d) as sm:
+        eng = Engine(sm)
+        top = int(big[-1])
+        for lo, hi in [(top // 2, top // 2 + 300_000), (top - 5000, top + 1), (-1, 9), (int(big[32 * 1024 * 1030]) - 1, int(big[32 * 1024 * 1031]))]:
+            sel = conj(Select("id", GT(lo)), Select("id", LT(hi)))
+            want = big[(big > lo) & (big < hi)]
+            for limit in (0, 100_000):
+                with eng.execute(Query("big", sel, Project(["id"], limit))) as got:
+                    exp = want if limit == 0 else want[:limit]
+                    assert got.nrows == len(exp), ("big", lo, hi, limit, got.nrows, len(exp))
+                    assert np.array_equal(got.column(0), exp), ("big", lo, hi, limit)
 
 
 def test_baseline_table_at_100m_rows(tmp_path_factory):
