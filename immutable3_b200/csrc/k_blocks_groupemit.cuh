@@ -288,25 +288,28 @@ __global__ void __launch_bounds__(kComputeThreads, 4) blocks_group_emit_kernel(c
     }
     if (lane == 0) phase_stamp(P, 14);
 
-    // ---------------- 3. last CTA out ----------------
+    // ---------------- 3. last CTA out (warp 0 alone: the other warps leave) ----------------
     __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        const unsigned done = atomicAdd(&ctrl->exited, 1u);
-        GS.is_last = done == gridDim.x - 1 ? 1u : 0u;
-    }
-    __syncthreads();
-    if (GS.is_last) {  // every CTA has read the group sums: they are the next query's again
-        for (int i = tid; i < ngroups; i += kComputeThreads) grp_sum[i] = 0u;
-        if (tid == 0) {
-            ctrl->exited = 0;
-            ctrl->ticket = 0;
-            ctrl->ticket2 = 0;
-            ctrl->total = want;
-            ctrl->dense_rows = 0;
-            if (pub) {  // publish (plan.hpp): no kernel follows - the host is polling its pinned copy of the control block
-                const unsigned long long word = ((pub_seq & 0x7FFFFFull) << 41) | (__ldcg(&ctrl->error) ? (1ull << 40) : 0ull) | (want & ((1ull << 40) - 1ull));
-                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&pub->pub_seq), "l"(word) : "memory");
+    if (warp == 0) {
+        unsigned last = 0;
+        if (lane == 0) {  // release: this CTA's rows are written (the barrier above makes that cumulative); acquire: so are everybody else's
+            unsigned done;
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(done) : "l"(&ctrl->exited) : "memory");
+            last = done == gridDim.x - 1 ? 1u : 0u;
+        }
+        last = __shfl_sync(0xFFFFFFFFu, last, 0);
+        if (last) {  // every CTA has read the group sums: they are the next query's again
+            for (int i = lane; i < ngroups; i += 32) grp_sum[i] = 0u;
+            if (lane == 0) {
+                ctrl->exited = 0;
+                ctrl->ticket = 0;
+                ctrl->ticket2 = 0;
+                ctrl->total = want;
+                ctrl->dense_rows = 0;
+                if (pub) {  // publish (plan.hpp): no kernel follows - the host is polling its pinned copy of the control block
+                    const unsigned long long word = ((pub_seq & 0x7FFFFFull) << 41) | (__ldcg(&ctrl->error) ? (1ull << 40) : 0ull) | (want & ((1ull << 40) - 1ull));
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&pub->pub_seq), "l"(word) : "memory");
+                }
             }
         }
     }

@@ -427,12 +427,16 @@ __global__ void __launch_bounds__(kLaneWarpsMax * 32, 1) blocks_filter_lane_kern
             P.trace[64 + 2 * blockIdx.x] = globaltimer_ns();
             P.trace[64 + 2 * blockIdx.x + 1] = (unsigned long long)smid << 32;
         }
-        __threadfence();
-        const unsigned prev = atomicAdd(&ctrl->exited, 1u);
-        S.is_last = prev == gridDim.x - 1;
-        if (S.is_last) {
-            ctrl->exited = 0;
-            ctrl->ticket2 = 0;  // (offset_scan_kernel counts the non-empty tiles of this query here)
+        if (grp_sum) {
+            S.is_last = 0;  // blocks_group_emit_kernel follows: it needs nothing from a last CTA, and nobody waits here for a fence + an atomic
+        } else {
+            __threadfence();
+            const unsigned prev = atomicAdd(&ctrl->exited, 1u);
+            S.is_last = prev == gridDim.x - 1;
+            if (S.is_last) {
+                ctrl->exited = 0;
+                ctrl->ticket2 = 0;  // (offset_scan_kernel counts the non-empty tiles of this query here)
+            }
         }
     }
     __syncthreads();

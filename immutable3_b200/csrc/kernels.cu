@@ -277,6 +277,7 @@ cudaError_t blocks_group_emit_grid(int num_sms, long long nblocks, int* grid, in
     if (e != cudaSuccess) return e;
     const long long ng = (nblocks + (1ll << kGrpShift) - 1) >> kGrpShift;
     *ngroups = (int)std::min<long long>(ng, kGrpMaxGroups);
+    if (const char* e = getenv("IMM3_GE_CTAS")) occ = std::max(1, std::min(occ, atoi(e)));  // experiment: CTAs per SM
     *grid = (occ >= 1 && ng <= kGrpMaxGroups) ? num_sms * occ : 0;  // 0: does not apply
     return cudaSuccess;
 }

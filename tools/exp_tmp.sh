@@ -1,5 +1,6 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-IMM3_BENCH_NO_STAGES=1 IMM3_DEBUG=16 IMM3_TRACE=gpurun_out/trace_ge3.txt python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --no-secondary --no-verify > gpurun_out/trace_ge3.log 2>&1
-head -11 gpurun_out/trace_ge3.txt
-tools/ab_c4.sh "IMM3_X=0" "IMM3_NO_GROUPEMIT=1"
-AB_ARGS="--workload c4_limit10" tools/ab_c4.sh "IMM3_X=0"
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517"
+$T bench.py --gpus 8 --sweep --steps 10 > gpurun_out/sweep_n8.json 2> gpurun_out/sweep_n8.err
+tail -c 300 gpurun_out/sweep_n8.err
+$T bench.py --gpus 8 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err
+tail -c 300 gpurun_out/bench_n8.err
+tail -c 1500 gpurun_out/bench_n8.json | head -c 600
