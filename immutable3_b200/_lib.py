@@ -61,6 +61,7 @@ SIGNATURES = {
     "imm3_sync": (C.c_int, [_P]),
     "imm3_query": (C.c_int, [_P, C.c_char_p, C.POINTER(Pred), C.c_int, _STRS, C.c_int, C.c_int64, _PP]),
     "imm3_query_begin": (C.c_int, [_P, C.c_char_p, C.POINTER(Pred), C.c_int, _STRS, C.c_int, C.c_int64, _PP]),
+    "imm3_query_begin_dnf": (C.c_int, [_P, C.c_char_p, C.POINTER(Pred), C.POINTER(C.c_int32), C.c_int, _STRS, C.c_int, C.c_int64, _PP]),
     "imm3_result_local_count": (C.c_int64, [_P]),
     "imm3_comm_local_handle": (C.c_int, [_P, _P]),
     "imm3_comm_connect": (C.c_int, [_P, _P, C.c_int]),

@@ -481,6 +481,9 @@ struct Prepared {
     ScanPlan sp;
     size_t dyn_smem = 0;
     int grid = 0;
+    // real OR (imm3_query_begin_dnf): the second and later conjunctions of the disjunction - their filter kernels run behind this
+    // plan's and OR their rows into its bitmap; counts, offsets and the emit kernels then see the union
+    std::vector<std::unique_ptr<Prepared>> or_terms;
 };
 
 const char* kernel_name(const imm3_db* db, const TableStore& t, const LogicalPlan& lp, bool* block_mode) {
@@ -866,6 +869,25 @@ int launch_scan_kernel(imm3_db* db, const ScanPlan& sp, int64_t ntiles, int* lau
     return 0;
 }
 
+// Real OR: the filter kernels of the later terms, behind the first term's (same bitmap, same span / tile counts: every pass
+// rewrites the counts of the union so far; only the last pass may run the inline offset scan).
+int launch_or_terms(imm3_db* db, Prepared* pr, int scan_inline, int* launches) {
+    for (size_t i = 0; i < pr->or_terms.size(); i++) {
+        Prepared* tm = pr->or_terms[i].get();
+        tm->sp.bitmap = pr->sp.bitmap;
+        tm->sp.or_accumulate = 1;
+        tm->sp.nrows = pr->sp.nrows;
+        tm->sp.ntiles = pr->sp.ntiles;
+        tm->sp.limit = pr->sp.limit;
+        tm->sp.debug = pr->sp.debug;
+        tm->sp.scan_inline = (i + 1 == pr->or_terms.size()) ? scan_inline : 0;
+        CUDA_TRY(launch_filter(tm->sp, tm->sp.bitmap, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p, (unsigned long long*)db->d_tile_off.p,
+                               db->d_ctrl, (int)std::max<int64_t>(1, std::min<int64_t>(tm->grid, tm->sp.ntiles)), tm->dyn_smem, db->stream));
+        (*launches)++;
+    }
+    return 0;
+}
+
 int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* launches, double* stage_ms, int64_t nblocks_use, bool exchange) {
     bool have_mid = false;
     pr->sp.scan_inline = 1;
@@ -887,11 +909,14 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         const size_t ntiles_pad = ((size_t)ntiles + 4095) / 4096 * 4096 + 16;  // whole rounds of the offset scan
         if ((rc = ensure_buf(&db->d_tile_cnt, ntiles_pad * 4))) return rc;
         if ((rc = ensure_buf(&db->d_tile_off, ntiles_pad * 8))) return rc;
-        pr->sp.scan_inline = (pr->sp.nfilter == 0 || scan_inline_for(ntiles)) ? 1 : 0;
+        const int scan_inline_h = (pr->sp.nfilter == 0 || scan_inline_for(ntiles)) ? 1 : 0;
+        pr->sp.scan_inline = pr->or_terms.empty() ? scan_inline_h : 0;
         CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
         CUDA_TRY(launch_filter(pr->sp, pr->sp.bitmap, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
                                (unsigned long long*)db->d_tile_off.p, db->d_ctrl, pr->grid, pr->dyn_smem, db->stream));
         *launches = 1;
+        if ((rc = launch_or_terms(db, pr, scan_inline_h, launches))) return rc;
+        pr->sp.scan_inline = scan_inline_h;
         if (!pr->sp.scan_inline && (rc = launch_scan_kernel(db, pr->sp, ntiles, launches))) return rc;
         const bool pdl = pr->sp.nproj > 0 && !getenv("IMM3_NO_PDL");  // (no event may sit between a kernel and its programmatic dependent)
         if (!pdl) {
@@ -1040,11 +1065,14 @@ int run_scan_once(imm3_db* db, Prepared* pr, double* ms, int64_t* total, int* la
         }
         const bool only_stream = stream_ok && hint == 1, only_gather = stream_ok && hint == 0;
         const bool pdl = pr->sp.nproj > 0 && !getenv("IMM3_NO_PDL");  // the first emit kernel launched is a programmatic dependent
-        pr->sp.scan_inline = (pr->sp.nfilter == 0 || scan_inline_for(nsub)) ? 1 : 0;
+        const int scan_inline_d = (pr->sp.nfilter == 0 || scan_inline_for(nsub)) ? 1 : 0;
+        pr->sp.scan_inline = pr->or_terms.empty() ? scan_inline_d : 0;
         CUDA_TRY(cudaEventRecord(db->ev0, db->stream));
         CUDA_TRY(launch_filter(pr->sp, pr->sp.bitmap, (uint32_t*)db->d_span_cnt.p, (uint32_t*)db->d_tile_cnt.p,
                                (unsigned long long*)db->d_tile_off.p, db->d_ctrl, pr->grid, pr->dyn_smem, db->stream));
         *launches = 1;
+        if ((rc = launch_or_terms(db, pr, scan_inline_d, launches))) return rc;
+        pr->sp.scan_inline = scan_inline_d;
         if (!pr->sp.scan_inline && (rc = launch_scan_kernel(db, pr->sp, nsub, launches))) return rc;
         // The streaming emit kernel is launched as a programmatic dependent of the filter kernel (its prologue overlaps the
         // filter kernel's tail), so no event may sit between the two; IMM3_NO_PDL=1 restores per-stage timing.
@@ -1482,13 +1510,26 @@ int imm3_explain(imm3_db* db, const char* table, const imm3_pred* preds, int npr
     return 0;
 }
 
-int imm3_query_begin(imm3_db* db, const char* table, const imm3_pred* preds, int npreds, const char* const* proj_cols,
-                     int nproj, int64_t limit, imm3_result** out) {
+// One conjunction (imm3_query_begin) or a disjunction of conjunctions (imm3_query_begin_dnf): terms[i] = (predicates, count).
+static int query_begin_terms(imm3_db* db, const char* table, const std::vector<std::pair<const imm3_pred*, int>>& terms,
+                             const char* const* proj_cols, int nproj, int64_t limit, imm3_result** out) {
     if (!db || !out) return fail(IMM3_ERR_INVALID_ARG, "imm3_query_begin: NULL argument");
     const double t_in = now_us();
-    Prepared pr;
-    int rc = prepare(db, table, preds, npreds, proj_cols, nproj, limit, &pr);  // validation before any device work
-    if (rc) return rc;
+    // validation before any device work; a term that can never hold (a wrong-length literal, an empty range) drops out of a
+    // disjunction; the first term that can hold carries the query, the others only add their filter kernels
+    std::vector<std::unique_ptr<Prepared>> prepared;
+    int rc = 0;
+    for (auto& tm : terms) {
+        std::unique_ptr<Prepared> p(new Prepared());
+        if ((rc = prepare(db, table, tm.first, tm.second, proj_cols, nproj, limit, p.get()))) return rc;
+        prepared.push_back(std::move(p));
+    }
+    size_t main_i = 0;
+    while (main_i + 1 < prepared.size() && prepared[main_i]->lp.always_empty) main_i++;
+    Prepared& pr = *prepared[main_i];
+    std::vector<std::unique_ptr<Prepared>> extra;
+    for (size_t i = main_i + 1; i < prepared.size(); i++)
+        if (!prepared[i]->lp.always_empty) extra.push_back(std::move(prepared[i]));
     if ((rc = use_device(db))) return rc;
     const double t_plan = now_us();
     double t_dev = t_plan;
@@ -1516,6 +1557,21 @@ int imm3_query_begin(imm3_db* db, const char* table, const imm3_pred* preds, int
         if ((rc = fill_scan_plan(db, &pr))) { give_back(); return rc; }
         for (int i = 0; i < r->ncols; i++) pr.sp.proj[i].out = (uint8_t*)r->d_cols[(size_t)i].p;
         pr.sp.bitmap = nullptr;
+        if (!extra.empty()) {
+            // real OR: every term's predicates are decided by the row-space filter kernel (dense columns); a disjunction over
+            // an encoded column would need the block filter kernels to accumulate as well - not built
+            auto row_space = [](const Prepared& p) { return p.block_mode ? (p.blocks_multi && p.hybrid) : p.multipass; };
+            bool ok = row_space(pr);
+            for (auto& tm : extra) {
+                if ((rc = fill_scan_plan(db, tm.get()))) { give_back(); return rc; }
+                ok = ok && row_space(*tm);
+            }
+            if (!ok) {
+                give_back();
+                return fail(IMM3_ERR_UNSUPPORTED, "imm3_query_begin_dnf: a disjunction needs every predicate on a dense (DENSE_INT / DENSE_TINYINT / DENSE_STRING) column");
+            }
+            pr.or_terms = std::move(extra);
+        }
         t_dev = now_us();
         if ((rc = run_scan(db, &pr, &r->device_ms, &r->local_count, &r->launches, r->stage_ms))) { give_back(); return rc; }
         r->timing_seq = db->ev_seq;
@@ -1547,11 +1603,16 @@ int imm3_query_begin(imm3_db* db, const char* table, const imm3_pred* preds, int
     {
         int64_t a = 0, per_row = 0;
         std::vector<int> seen;
-        for (auto& f : pr.lp.filters) {
-            const ColumnStore& c = t.cols[(size_t)f.col_idx];
-            a += c.encoded_bytes + (c.meta.codec == IMM3_CODEC_PFOR_INT ? 4 * t.nblocks : 0);
-            seen.push_back(f.col_idx);
-        }
+        auto count_filters = [&](const LogicalPlan& lp) {
+            for (auto& f : lp.filters) {
+                if (std::find(seen.begin(), seen.end(), f.col_idx) != seen.end()) continue;  // (a column several terms of a disjunction test: once)
+                const ColumnStore& c = t.cols[(size_t)f.col_idx];
+                a += c.encoded_bytes + (c.meta.codec == IMM3_CODEC_PFOR_INT ? 4 * t.nblocks : 0);
+                seen.push_back(f.col_idx);
+            }
+        };
+        count_filters(pr.lp);
+        for (auto& tm : pr.or_terms) count_filters(tm->lp);
         for (int ci : pr.lp.proj) {
             per_row += t.cols[(size_t)ci].meta.width;
             if (std::find(seen.begin(), seen.end(), ci) == seen.end()) {
@@ -1574,6 +1635,26 @@ int imm3_query_begin(imm3_db* db, const char* table, const imm3_pred* preds, int
     }
     *out = r.release();
     return 0;
+}
+
+int imm3_query_begin(imm3_db* db, const char* table, const imm3_pred* preds, int npreds, const char* const* proj_cols,
+                     int nproj, int64_t limit, imm3_result** out) {
+    if (npreds < 0 || (npreds > 0 && !preds)) return fail(IMM3_ERR_INVALID_ARG, "imm3_query_begin: predicates");
+    return query_begin_terms(db, table, {{preds, npreds}}, proj_cols, nproj, limit, out);
+}
+
+int imm3_query_begin_dnf(imm3_db* db, const char* table, const imm3_pred* preds, const int32_t* term_sizes, int nterms,
+                         const char* const* proj_cols, int nproj, int64_t limit, imm3_result** out) {
+    if (!term_sizes || nterms < 1 || nterms > IMM3_MAX_OR_TERMS) return fail(IMM3_ERR_INVALID_ARG, "imm3_query_begin_dnf: 1 .. %d terms", IMM3_MAX_OR_TERMS);
+    std::vector<std::pair<const imm3_pred*, int>> terms;
+    int at = 0;
+    for (int i = 0; i < nterms; i++) {
+        if (term_sizes[i] < 0 || (term_sizes[i] > 0 && !preds)) return fail(IMM3_ERR_INVALID_ARG, "imm3_query_begin_dnf: term %d", i);
+        if (term_sizes[i] == 0) return query_begin_terms(db, table, {{nullptr, 0}}, proj_cols, nproj, limit, out);  // `... or true`: every row
+        terms.push_back({preds + at, term_sizes[i]});
+        at += term_sizes[i];
+    }
+    return query_begin_terms(db, table, terms, proj_cols, nproj, limit, out);
 }
 
 int64_t imm3_result_local_count(const imm3_result* r) { return r ? r->local_count : IMM3_ERR_INVALID_ARG; }

@@ -401,6 +401,7 @@ __global__ void __launch_bounds__(kComputeThreads + 32, 4) filter_kernel(const _
 #pragma unroll 1
                 for (int i = 0; i < nf; i++) dense_eval_filter<1, STAGED>(S.filter[i], S.lits, stage_addr, tile * kTile, warp * 1024, lane, &m);
             }
+            if (P.or_accumulate) m |= __ldcg(bm_w);  // real OR (imm3_query_begin_dnf): this term's rows join those of the terms before it
             *bm_w = m;
             const unsigned c = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(m));
             if (lane == 0) {

@@ -79,6 +79,7 @@ struct ScanPlan {
     int32_t scan_inline;     // 1: the filter kernel's last CTA turns the tile counts into offsets; 0: offset_scan_kernel does (large tables)
     uint32_t pfor_filter_mask;  // blocks_filter_kernel: PFOR slots that carry a predicate (their tiles are staged)
     int32_t words_per_lane;  // multi-pass filter kernel: W (tile = 8192 * W rows)
+    int32_t or_accumulate;   // filter kernel: OR this conjunction's bits into the bitmap already there (second and later terms of a disjunction)
     uint32_t debug;          // IMM3_DEBUG env bits (timing experiments only; bit 0: skip the look-back -> WRONG offsets)
     FilterCol filter[kMaxFilterCols];
     ProjCol proj[kMaxProjCols];

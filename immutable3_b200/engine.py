@@ -156,6 +156,28 @@ def flatten_select(sel: SelectADT) -> List[Select]:
     raise TypeError(f"not a SelectADT: {sel!r}")
 
 
+MAX_OR_TERMS = 16  # IMM3_MAX_OR_TERMS
+
+
+def select_dnf(sel: SelectADT) -> List[List[Select]]:
+    """The select tree in disjunctive normal form - what `a or b` MEANS, as opposed to what the reference does with it
+    (flatten_select above).  A list of conjunctions, each a list of leaves in application order; [[]] = no predicate.
+    And distributes over Or: And(Or(a, b), c) -> [[a, c], [b, c]]."""
+    if isinstance(sel, Or):
+        terms = select_dnf(sel.op1) + select_dnf(sel.op2)
+    elif isinstance(sel, And):
+        terms = [l + r for l in select_dnf(sel.op1) for r in select_dnf(sel.op2)]
+    elif isinstance(sel, Select):
+        terms = [[sel]]
+    elif sel is NoSelect or isinstance(sel, _NoSelect):
+        terms = [[]]
+    else:
+        raise TypeError(f"not a SelectADT: {sel!r}")
+    if len(terms) > MAX_OR_TERMS:
+        raise L.Imm3Error(L.ERR_UNSUPPORTED, f"the select tree expands to {len(terms)} conjunctions (at most {MAX_OR_TERMS})")
+    return terms
+
+
 def _pred_array(leaves: Sequence[Select]):
     """imm3_pred[] + the ctypes objects that must stay alive while it is used."""
     n = len(leaves)
@@ -499,17 +521,36 @@ class Engine:
         L.check(self._lib.imm3_query_begin(self.sm.handle, p[0], p[1], p[2], p[3], p[4], p[5], C.byref(out)))
         return Result(out, self._lib, self.sm)
 
-    def execute(self, query: Query) -> Result:
-        """Engine.execute: the rows of the query in canonical order (iterate for Row objects)."""
+    def execute(self, query: Query, real_or: bool = False) -> Result:
+        """Engine.execute: the rows of the query in canonical order (iterate for Row objects).  `real_or=True` evaluates
+        Or as a disjunction (imm3_query_begin_dnf) instead of the reference's Or == And (Engine.scala:236-245)."""
         if isinstance(query.project, ProjectAgg):
             return self._call_agg(query)
+        if real_or:
+            r = self.begin(query, real_or=True)
+            return r.fetch(r.take)
         return self._call(self._lib.imm3_query, query)
 
-    def begin(self, query: Query) -> Result:
+    def begin(self, query: Query, real_or: bool = False) -> Result:
         """First phase of a sharded query: kernels done, local match count known, nothing fetched."""
         if isinstance(query.project, ProjectAgg):
             return self._call_agg(query)
+        if real_or:
+            return self._call_dnf(query)
         return self._call(self._lib.imm3_query_begin, query)
+
+    def _call_dnf(self, query: Query) -> Result:
+        if not isinstance(query.project, Project):
+            raise L.Imm3Error(L.ERR_UNSUPPORTED, "only Project queries are on the scan/filter/project path")
+        terms = select_dnf(query.select)
+        preds, _, keep = _pred_array([leaf for t in terms for leaf in t])
+        sizes = (C.c_int32 * len(terms))(*[len(t) for t in terms])
+        proj = L.cstr_array(list(query.project.cols))
+        out = C.c_void_p()
+        L.check(self._lib.imm3_query_begin_dnf(self.sm.handle, query.table.encode(), preds, sizes, len(terms),
+                                               C.cast(proj, C.POINTER(C.c_char_p)), len(query.project.cols), int(query.project.limit), C.byref(out)))
+        del keep
+        return Result(out, self._lib, self.sm)
 
     def _call_agg(self, query: Query) -> Result:
         """Engine.execute, ProjectAgg branch (Engine.scala:200-232): one row per group, group columns then aggregates."""

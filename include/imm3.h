@@ -150,6 +150,20 @@ int imm3_query_begin(imm3_db* db, const char* table, const imm3_pred* preds, int
                      const char* const* proj_cols, int nproj, int64_t limit, imm3_result** out);
 int64_t imm3_result_local_count(const imm3_result* r);
 
+/* ---- Real OR (an EXTENSION: not the reference's behaviour) ----
+ * The reference parses `a or b` into Or(a, b) (Query.scala:13) and then drops the tag: PipelineThread.runOps applies every
+ * leaf as a conjunction (Engine.scala:236-245), so imm3_query / imm3_query_begin evaluate Or exactly like And - that is
+ * what parity with the reference means, and what the Scala engine's callers get today.  This entry point is the
+ * disjunction the query language promises, for the maintainer who fixes that: the select tree in disjunctive normal
+ * form, `nterms` conjunctions laid out back to back in `preds`, term i holding term_sizes[i] predicates
+ * (sum = length of preds; a term of size 0 is `true`).  A row survives if it satisfies EVERY predicate of AT LEAST ONE
+ * term.  Rows, order, LIMIT and the sharded count exchange are those of imm3_query_begin.  Each term runs the filter
+ * kernel once and ORs its rows into the selection bitmap, so every predicate has to sit on a dense column
+ * (IMM3_ERR_UNSUPPORTED otherwise); a term that can never hold (wrong-length literal, empty range) drops out. */
+#define IMM3_MAX_OR_TERMS 16
+int imm3_query_begin_dnf(imm3_db* db, const char* table, const imm3_pred* preds, const int32_t* term_sizes, int nterms,
+                         const char* const* proj_cols, int nproj, int64_t limit, imm3_result** out);
+
 /* ---- The fan-in across GPUs: ResultQueueOp (ResultQueue.scala:7-56) + the queue of Engine.scala:166,190-196 ----
  * The reference funnels every worker's batches through one queue; across segment-sharded GPUs the ordered
  * concatenation and the LIMIT cut need only the match count of every rank (global order = rank order).  The GPUs

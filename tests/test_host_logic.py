@@ -216,3 +216,24 @@ def test_sql_grammar(db):
     assert _sql_status(sm, "select min(age) from t")[0] == L.ERR_UNSUPPORTED                             # ProjectAgg: out of scope
     assert _sql_status(sm, "select id from nope")[0] == L.ERR_NOT_FOUND
     assert _sql_status(sm, "select id from t where state > 3")[0] == L.ERR_UNSUPPORTED
+
+
+def test_select_tree_in_disjunctive_normal_form():
+    """select_dnf (real OR, imm3_query_begin_dnf): And distributes over Or, leaves keep their application order, NoSelect is `true`."""
+    from immutable3_b200 import select_dnf
+
+    a, b, c, d_ = Select("age", GT(1)), Select("age", LT(9)), Select("state", Match(["CA"])), Select("id", EQ(4))
+    assert select_dnf(NoSelect) == [[]]
+    assert select_dnf(a) == [[a]]
+    assert select_dnf(And(a, b)) == [[a, b]]
+    assert select_dnf(Or(a, b)) == [[a], [b]]
+    assert select_dnf(And(Or(a, b), c)) == [[a, c], [b, c]]
+    assert select_dnf(And(Or(a, b), Or(c, d_))) == [[a, c], [a, d_], [b, c], [b, d_]]
+    assert select_dnf(Or(And(a, b), And(c, Or(d_, a)))) == [[a, b], [c, d_], [c, a]]
+    assert select_dnf(Or(a, NoSelect)) == [[a], []]
+    big = a
+    for _ in range(5):
+        big = And(Or(big, b), Or(c, d_))
+    with pytest.raises(Imm3Error) as e:
+        select_dnf(big)
+    assert e.value.status == L.ERR_UNSUPPORTED
