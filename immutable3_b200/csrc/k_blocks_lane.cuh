@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(kLaneWarpsMax * 32, 1) blocks_filter_lane_kern
     // for the items ahead, one step each per tile decided, none of which it ever waits for: S1 fetch the item's tile id
     // (pruned queries: from the work list), S2 fetch the tile's first / end word offset, S3 issue its bulk copies.  The
     // fetches are 4-byte cp.async into s_meta - a plain load would stall the warp at the first touch of its register.
+    const uint64_t pol_stream = l2_policy_evict_first();  // the column is streamed exactly once (IMM3_DEBUG bit 256: default policy)
     auto S1 = [&](int q) {
         const long long k = (long long)gw + (long long)q * nwarps;
         const uint32_t e = meta_addr + 16u * (uint32_t)(q & 7);
@@ -228,7 +229,8 @@ __global__ void __launch_bounds__(kLaneWarpsMax * 32, 1) blocks_filter_lane_kern
             mbar_arrive_expect_tx(bar, 272u + 144u + nb);
             tma_load_1d(dst, P.row_start + b0, 272u, bar);
             tma_load_1d(dst + (uint32_t)kQuadWoOff, pc.word_off + b0, 144u, bar);
-            tma_load_1d(dst + (uint32_t)kQuadHdrBytes, pc.words + base_w, nb, bar);
+            if (!(P.debug & 256u)) tma_load_1d_hint(dst + (uint32_t)kQuadHdrBytes, pc.words + base_w, nb, bar, pol_stream);
+            else tma_load_1d(dst + (uint32_t)kQuadHdrBytes, pc.words + base_w, nb, bar);
         }
     };
     if (lane == 0) {
@@ -267,12 +269,13 @@ __global__ void __launch_bounds__(kLaneWarpsMax * 32, 1) blocks_filter_lane_kern
         // ---------------- my block ----------------
         const bool exists = blk < nblocks;
         int n = 0, nw = 0;
-        uint32_t wa = sl + (uint32_t)kQuadHdrBytes, stride = 0;
+        uint32_t wa = sl + (uint32_t)kQuadHdrBytes, stride = 0, gw0 = 0;
         if (exists) {
             const unsigned long long r0 = lds_cell<unsigned long long>(sl + 8u * (uint32_t)lane), r1 = lds_cell<unsigned long long>(sl + 8u * (uint32_t)lane + 8u);
             const uint32_t w0 = lds32(sl + (uint32_t)kQuadWoOff + 4u * (uint32_t)lane), w1 = lds32(sl + (uint32_t)kQuadWoOff + 4u * (uint32_t)lane + 4u);
             n = (int)(r1 - r0);
             stride = w1 - w0;
+            gw0 = w0;
             nw = (int)stride - 2;
             wa += 4u * (w0 - base_w);
             IMM3_CHECK(ctrl, n >= 0 && nw >= 1 && wa + 4u * stride <= sl + (uint32_t)slot_bytes + 16u, 1);  // the block lies inside the ring slot
@@ -411,6 +414,16 @@ __global__ void __launch_bounds__(kLaneWarpsMax * 32, 1) blocks_filter_lane_kern
             unsigned c32 = c8 + __shfl_xor_sync(0xFFFFFFFFu, c8, 8);
             c32 += __shfl_xor_sync(0xFFFFFFFFu, c32, 16);
             if (lane == 0 && c32 != 0u) atomicAdd(grp_sum + (blk0 >> 10), c32);
+            // ... and what the emit kernel will read of it - the selected blocks' words, the tile's row ordinals and word offsets - is
+            // touched again so that it outlives the rest of this kernel's stream in L2 (the stream itself is marked evict-first)
+            if (!(P.debug & 512u) && c32 != 0u && counted) {  // (IMM3_DEBUG bit 512 switches it off)
+                if (cnt != 0u) {
+                    const char* a = reinterpret_cast<const char*>(pc.words + gw0);
+                    for (uint32_t o = 0; o < 4u * stride; o += 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + o));
+                }
+                if (lane < 3) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(P.row_start + blk0) + 128 * lane));
+                else if (lane < 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(pc.word_off + blk0) + 128 * (lane - 3)));
+            }
         }
         __syncwarp();
         pslot = slot;
