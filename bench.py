@@ -579,14 +579,14 @@ def main():
     kind = WORKLOADS[args.workload][1]
     on_pfor_filter = kind == "pfor" and any(l.col == "id" for l in flatten_select(query.select))
     kname = ("filter_kernel -> agg_kernel -> agg_compact_kernel" if agg_head else
-             ("blocks_filter_lane_kernel (sorted-int codec, one lane per block, per-warp TMA rings) -> blocks_scan_emit_kernel (offset scan + emit)"
+             ("blocks_filter_lane_kernel (sorted-int codec, one lane per block, per-warp TMA rings) -> blocks_group_emit_kernel (emit from per-group sums, no offset scan)"
               if list(query.project.cols) == ["id"] else
               "blocks_filter_lane_kernel (sorted-int codec, one lane per block) [-> offset_scan_kernel] -> blocks_emit_kernel") if on_pfor_filter else
              "filter_kernel (row space) -> blocks_emit_kernel" if kind == "pfor" else "filter_kernel -> emit_stream_kernel | emit_kernel")
     roofline = head.pop("roofline")
     tr = recorded_traffic(f"{args.workload}_{total}") if world == 1 else None
     roofline.update({"kernel": kname + " (one query = one launch of each; timed together with CUDA events)",
-                     "stage_ms_mean": {"filter (+ offset scan where it is a kernel of its own)": st0, "emit (scan + emit for blocks_scan_emit_kernel)": st1,
+                     "stage_ms_mean": {"filter (+ offset scan where it is a kernel of its own)": st0, "emit (blocks_group_emit_kernel on the headline path)": st1,
                                        "note": "from an extra IMM3_NO_PDL=1 pass (kernels serialised, an event between them)"},
                      "traffic": tr["bytes"] if tr else None, "traffic_source": ("ncu capture " + tr["source"]) if tr else None})
 

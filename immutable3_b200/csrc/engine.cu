@@ -716,6 +716,9 @@ int fill_scan_plan(imm3_db* db, Prepared* pr) {
                 pr->pp.nfilter = sp.nfilter;
                 pr->pp.group_shift = pr->quad ? 5 : 3;
                 pr->prune = ok;
+                // a pruned scan decides whole blocks from 8 bytes each: the whole slice costs what a prefix would - no prefix phase (with a
+                // communicator phase A then is this rank's whole slice and phase B the count exchange alone: the protocol is unchanged)
+                if (ok) pr->prefix_blocks = 0;
             }
             pr->blocks_emit_smem = blocks_emit_smem_bytes(sp.npfor, sp.blk_words_cap);
             int occ_e = 0;
