@@ -7,10 +7,12 @@
 // 160-166) and merges the per-segment maps in ProjectAggregateQueueOp (ProjectAggregateQueue.scala:21-45).  Here:
 //   filter_kernel            the same K1 as every query: selection bitmap + span / tile counts (nothing is projected)
 //   agg_kernel               one warp per 1024-row span with selected rows: the span's selection vector (append_selection),
-//                            then 32 selected rows at a time - a lane gathers its row's group cells (packed into a 64-bit
-//                            key) and aggregate inputs, lanes with equal keys combine through MATCH.ANY + REDUX, one lane
-//                            per distinct key updates the CTA's shared-memory hash table; when the CTA has no tile left,
-//                            its groups are merged into the global table with atomics
+//                            then 64 selected rows per iteration (two steps of 32, the gathers of both issued before the
+//                            first update) - a lane gathers its row's group cells (packed into a 64-bit key) and aggregate
+//                            inputs and updates its group in the WARP's own shared-memory hash table: the slot is found
+//                            with one load when the group exists, MIN / MAX read the slot first and only issue an atomic
+//                            when the row improves it (after the first rows of a group almost never), COUNT is one native
+//                            32-bit shared-memory atomic; warps fold into one table per CTA, CTAs into the global table
 //   agg_compact_kernel       occupied slots of the global table -> a dense array (any order; the host sorts the groups by
 //                            the canonical ordinal of their first row, the order the reference reports them in with one
 //                            worker) and clears the table for the next query
@@ -26,27 +28,38 @@ __device__ __forceinline__ uint32_t agg_hash(unsigned long long k) {
     return (uint32_t)k;
 }
 
-// Per-WARP hash tables in shared memory: a group is updated by one lane per 32-row step (the leader of the lanes that hold
-// its key), so inside a warp's own table the values need no atomics at all - only claiming a fresh slot does (two new keys
-// may want the same slot in one step).  With one table per CTA, a low-cardinality group-by (51 states) serialised every
+// Per-WARP hash tables in shared memory.  With one table per CTA, a low-cardinality group-by (51 states) serialised every
 // warp of the SM on the same few shared-memory words: 5.2 ms for the reference's example on 100 M rows.
+// MIN and MAX share one update: a MIN column is kept as the MAX of the complemented inputs (~x reverses the order of int32
+// without overflow), so both are "read the slot, atomicMax only if the row beats it"; the value is complemented back when
+// the table leaves shared memory.
 constexpr int kAggWarpSlots = 128;
-struct AggWarpTable {
+constexpr int kAggWarpSlotBits = 7;
+template <int NA>
+struct AggWarpTableT {
     unsigned long long key[kAggWarpSlots];
     unsigned long long first_row[kAggWarpSlots];
-    int val[kMaxAggs][kAggWarpSlots];  // 32-bit: native shared-memory atomics (a warp counts far fewer than 2^32 rows; min / max inputs are int32 / int8)
+    int val[NA][kAggWarpSlots];  // 32-bit: native shared-memory atomics (a CTA counts far fewer than 2^32 rows; min / max inputs are int32 / int8)
 };
-
-// Slot of `key` in a shared-memory table (claimed if new), -1 if `max_probe` slots in a row are taken by other keys.
+// Home slot in a shared-memory table: two 32-bit multiplies, the top bits of their XOR.
+__device__ __forceinline__ uint32_t agg_home_slot(unsigned long long k) {
+    return (((uint32_t)k * 0x9E3779B1u) ^ ((uint32_t)(k >> 32) * 0x85EBCA6Bu)) >> (32 - kAggWarpSlotBits);
+}
+// Slot of `key` in a shared-memory table (linear probing from its home slot; bit 8 of the result = the slot was claimed by
+// this call), -1 if `max_probe` slots in a row are taken by other keys.
 __device__ __forceinline__ int agg_smem_slot(unsigned long long* keys, unsigned long long key, int max_probe) {
-    uint32_t h = agg_hash(key) & (kAggWarpSlots - 1);
-    for (int p = 0; p < max_probe; p++, h = (h + 1) & (kAggWarpSlots - 1)) {
-        unsigned long long cur = keys[h];
+    uint32_t h = agg_home_slot(key);
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&keys[h]);
+    if (cur == key) return (int)h;  // (nearly every row after a group's first)
+    for (int p = 0; p < max_probe; p++) {
         if (cur == kAggEmpty) {
             const unsigned long long old = atomicCAS(&keys[h], kAggEmpty, key);
-            cur = old == kAggEmpty ? key : old;
+            if (old == kAggEmpty) return (int)h | 0x100;
+            cur = old;
         }
         if (cur == key) return (int)h;
+        h = (h + 1) & (kAggWarpSlots - 1);
+        cur = *reinterpret_cast<volatile unsigned long long*>(&keys[h]);
     }
     return -1;
 }
@@ -73,8 +86,9 @@ __device__ __forceinline__ void agg_update(long long* v, int op, long long x) {
 }
 __device__ __forceinline__ long long agg_identity(int op) { return op == kAggCount ? 0ll : (op == kAggMin ? LLONG_MAX : LLONG_MIN); }
 
-__device__ __forceinline__ void agg_to_global(AggEntry* table, uint32_t slots, unsigned int* overflow, unsigned long long key, unsigned long long fr,
-                                              const long long* x, const AggCol* aggs, int naggs) {
+// One group's partial (x[a]: a count, or an extreme as int64) into the global table.
+__device__ __noinline__ void agg_to_global(AggEntry* table, uint32_t slots, unsigned int* overflow, unsigned long long key, unsigned long long fr,
+                                           const long long* x, const AggCol* aggs, int naggs) {
     const int gs = agg_global_slot(table, slots, key);
     if (gs < 0) {
         atomicExch(overflow, 1u);
@@ -83,30 +97,91 @@ __device__ __forceinline__ void agg_to_global(AggEntry* table, uint32_t slots, u
     atomicMin(&table[gs].first_row, fr);
     for (int a = 0; a < naggs; a++) agg_update(&table[gs].val[a], aggs[a].op, x[a]);
 }
+// A shared-memory value (COUNT: the count; MIN: max of ~x; MAX: max of x) as the int64 the global table holds.
+__device__ __forceinline__ long long agg_smem_value(int op, int v) { return op == kAggCount ? (long long)(unsigned int)v : (long long)(op == kAggMin ? ~v : v); }
 
-__global__ void __launch_bounds__(kComputeThreads, 2) agg_kernel(const __grid_constant__ AggPlan A, const uint32_t* __restrict__ bitmap,
+// NG = group-by columns (0, 1, 2 exact; 4 = A.ngroup of them, up to 4), NA = aggregates (1 .. 4 exact; 8 = A.naggs of them, up to 8):
+// the loops over the plan are unrolled with compile-time indices into the kernel's parameter block, so the per-column
+// descriptors are constant-bank operands - nothing about the query is decoded per row and nothing of it lives in registers.
+template <int NG, int NA>
+__global__ void __launch_bounds__(kComputeThreads, 3) agg_kernel(const __grid_constant__ AggPlan A, const uint32_t* __restrict__ bitmap,
                                                                   const uint32_t* __restrict__ span_cnt, AggEntry* __restrict__ table,
                                                                   unsigned int* __restrict__ overflow, const ScanCtrl* ctrl) {
+    using WarpTable = AggWarpTableT<NA>;
     extern __shared__ __align__(128) uint8_t agg_smem[];
-    AggWarpTable* const tables = reinterpret_cast<AggWarpTable*>(agg_smem);
-    unsigned short* const sel_all = reinterpret_cast<unsigned short*>(agg_smem + kComputeWarps * sizeof(AggWarpTable));
-    __shared__ AggCol s_agg[kMaxAggs];
-    __shared__ GroupCol s_group[kMaxGroupCols];
+    WarpTable* const tables = reinterpret_cast<WarpTable*>(agg_smem);
+    unsigned short* const sel_all = reinterpret_cast<unsigned short*>(agg_smem + kComputeWarps * sizeof(WarpTable));
+    __shared__ AggCol s_agg[kMaxAggs];  // (for the cold paths only: a row or a table entry that goes to the global table)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #pragma unroll
     for (int i = 0; i < kMaxAggs; i++)
         if (tid == i) s_agg[i] = A.agg[i];
-#pragma unroll
-    for (int i = 0; i < kMaxGroupCols; i++)
-        if (tid == 32 + i) s_group[i] = A.group[i];
-    __syncthreads();
-    AggWarpTable& T = tables[warp];
+    const int naggs = NA == 8 ? A.naggs : NA, ngroup = NG == 4 ? A.ngroup : NG;
+    WarpTable& T = tables[warp];
     for (int i = lane; i < kAggWarpSlots; i += 32) {
         T.key[i] = kAggEmpty;
         T.first_row[i] = ~0ull;
-        for (int a = 0; a < A.naggs; a++) T.val[a][i] = s_agg[a].op == kAggCount ? 0 : (s_agg[a].op == kAggMin ? INT_MAX : INT_MIN);
+#pragma unroll
+        for (int a = 0; a < NA; a++) T.val[a][i] = A.agg[a].op == kAggCount ? 0 : INT_MIN;
     }
-    __syncwarp();
+    __syncthreads();
+
+    // the group key and the aggregate inputs of one row (MIN inputs complemented)
+    auto gather = [&](long long row, unsigned long long& key, int (&x)[NA]) {
+        key = 0;
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+            if (NG == 4 && g >= ngroup) break;
+            const int w = A.group[g].width;
+            const uint8_t* src = A.group[g].base + row * w;
+            unsigned long long cell = 0;
+            if (w == 2) cell = __ldg(reinterpret_cast<const unsigned short*>(src));
+            else if (w == 1) cell = __ldg(src);
+            else if (w == 4) cell = __ldg(reinterpret_cast<const uint32_t*>(src));
+            else
+                for (int b = 0; b < w; b++) cell |= (unsigned long long)__ldg(src + b) << (8 * b);
+            key |= cell << A.group[g].key_shift;
+        }
+#pragma unroll
+        for (int a = 0; a < NA; a++) {
+            x[a] = 0;
+            if (NA == 8 && a >= naggs) break;
+            const int op = A.agg[a].op;
+            if (op != kAggCount) {
+                const int v = A.agg[a].width == 4 ? (int)__ldg(reinterpret_cast<const uint32_t*>(A.agg[a].base) + row) : (int)(signed char)__ldg(A.agg[a].base + row);
+                x[a] = op == kAggMin ? ~v : v;
+            }
+        }
+    };
+    // one row into its group of the warp's table (all 32 lanes call this; `live` lanes carry a row)
+    auto apply = [&](bool live, long long row, unsigned long long key, const int (&x)[NA]) {
+        int slot = -1;
+        if (live) slot = agg_smem_slot(T.key, key, 16);
+        // rows reach a warp in ascending order: a group's first row is in the step that creates its slot (maybe on another
+        // lane than the one that claimed it) - only such a step touches first_row
+        if (__any_sync(0xFFFFFFFFu, slot >= 0x100)) {
+            if (slot >= 0) {
+                slot &= 0xFF;
+                atomicMin(&T.first_row[slot], (unsigned long long)row);
+            }
+        }
+        if (!live) return;
+        if (slot >= 0) {
+#pragma unroll
+            for (int a = 0; a < NA; a++) {
+                if (NA == 8 && a >= naggs) break;
+                int* const v = &T.val[a][slot];
+                if (A.agg[a].op == kAggCount) atomicAdd(reinterpret_cast<unsigned int*>(v), 1u);
+                else if (x[a] > *reinterpret_cast<volatile int*>(v)) atomicMax(v, x[a]);  // (a stale read is only ever too low: at worst one atomic too many)
+            }
+        } else {  // the warp's table is full
+            long long xl[kMaxAggs];
+#pragma unroll
+            for (int a = 0; a < NA; a++) xl[a] = A.agg[a].op == kAggCount ? 1ll : (long long)(A.agg[a].op == kAggMin ? ~x[a] : x[a]);
+            agg_to_global(table, A.table_slots, overflow, key, (unsigned long long)row, xl, s_agg, naggs);
+        }
+    };
+
     asm volatile("griddepcontrol.wait;" ::: "memory");  // the filter kernel's bitmap and counts are final
     if (__ldcg(&ctrl->total) != 0ull) {
         unsigned short* const sel_w = sel_all + warp * 1024;
@@ -119,74 +194,40 @@ __global__ void __launch_bounds__(kComputeThreads, 2) agg_kernel(const __grid_co
             append_selection(m, lane, sel_w, 0u);
             __syncwarp();
             const long long row0 = span * 1024;
-            for (unsigned i0 = 0; i0 < n; i0 += 32) {
-                const bool live = i0 + lane < n;
-                const long long row = row0 + (live ? sel_w[i0 + lane] : 0);
-                unsigned long long key = 0;
-                for (int gcol = 0; gcol < A.ngroup; gcol++) {
-                    const GroupCol gc = s_group[gcol];
-                    unsigned long long cell = 0;
-                    const uint8_t* src = gc.base + row * gc.width;
-                    if (gc.width == 2) cell = __ldg(reinterpret_cast<const unsigned short*>(src));
-                    else if (gc.width == 4) cell = __ldg(reinterpret_cast<const uint32_t*>(src));
-                    else
-                        for (int b = 0; b < gc.width; b++) cell |= (unsigned long long)__ldg(src + b) << (8 * b);
-                    key |= cell << gc.key_shift;
-                }
-                long long x[kMaxAggs];
-#pragma unroll
-                for (int a = 0; a < kMaxAggs; a++) {
-                    x[a] = 0;
-                    if (a < A.naggs) {
-                        const AggCol ac = s_agg[a];
-                        if (ac.op == kAggCount) x[a] = 1;
-                        else x[a] = ac.width == 4 ? (long long)(int)__ldg(reinterpret_cast<const uint32_t*>(ac.base) + row) : (long long)(signed char)__ldg(ac.base + row);
-                    }
-                }
-                // every lane updates its group in the warp's table with native 32-bit shared-memory atomics.  (Combining the lanes
-                // of a key first - MATCH.ANY + REDUX per distinct key - was 10x slower: with ~20 distinct keys per 32 rows the
-                // partial-mask reductions run one after the other.)
-                if (live) {
-                    const int slot = agg_smem_slot(T.key, key, 16);
-                    if (slot >= 0) {
-                        // rows reach a warp in ascending order: only the step that creates the group can lower first_row
-                        if ((unsigned long long)row < *reinterpret_cast<volatile unsigned long long*>(&T.first_row[slot])) atomicMin(&T.first_row[slot], (unsigned long long)row);
-#pragma unroll
-                        for (int a = 0; a < kMaxAggs; a++) {
-                            if (a < A.naggs) {
-                                const int op = s_agg[a].op;
-                                if (op == kAggCount) atomicAdd(reinterpret_cast<unsigned int*>(&T.val[a][slot]), 1u);
-                                else if (op == kAggMin) atomicMin(&T.val[a][slot], (int)x[a]);
-                                else atomicMax(&T.val[a][slot], (int)x[a]);
-                            }
-                        }
-                    } else {
-                        agg_to_global(table, A.table_slots, overflow, key, (unsigned long long)row, x, s_agg, A.naggs);  // the warp's table is full
-                    }
-                }
+            for (unsigned i0 = 0; i0 < n; i0 += 64) {  // two steps of 32 rows: the gathers of both are in flight before the first update
+                const bool live0 = i0 + lane < n, live1 = i0 + 32 + lane < n;
+                const long long r0 = row0 + (live0 ? sel_w[i0 + lane] : 0), r1 = row0 + (live1 ? sel_w[i0 + 32 + lane] : 0);
+                unsigned long long k0 = 0, k1 = 0;
+                int x0[NA], x1[NA];
+                if (live0) gather(r0, k0, x0);
+                if (live1) gather(r1, k1, x1);
+                apply(live0, r0, k0, x0);
+                if (i0 + 32 < n) apply(live1, r1, k1, x1);
             }
         }
     }
-    // the CTA's warps fold their tables into warp 0's (shared-memory atomics now: several writers), which goes to the global table
+    // the CTA's warps fold their tables into warp 0's (several writers now: atomics throughout), which goes to the global table
     __syncthreads();
-    AggWarpTable& T0 = tables[0];
+    WarpTable& T0 = tables[0];
     if (warp > 0) {
         for (int i = lane; i < kAggWarpSlots; i += 32) {
             const unsigned long long key = T.key[i];
             if (key == kAggEmpty) continue;
-            long long x[kMaxAggs];
-            for (int a = 0; a < A.naggs; a++) x[a] = s_agg[a].op == kAggCount ? (long long)(unsigned int)T.val[a][i] : (long long)T.val[a][i];
-            const int slot = agg_smem_slot(T0.key, key, kAggWarpSlots);
+            int slot = agg_smem_slot(T0.key, key, kAggWarpSlots);
             if (slot >= 0) {
+                slot &= 0xFF;
                 atomicMin(&T0.first_row[slot], T.first_row[i]);
-                for (int a = 0; a < A.naggs; a++) {
-                    const int op = s_agg[a].op;
-                    if (op == kAggCount) atomicAdd(reinterpret_cast<unsigned int*>(&T0.val[a][slot]), (unsigned int)T.val[a][i]);  // (a CTA counts < 2^32 rows)
-                    else if (op == kAggMin) atomicMin(&T0.val[a][slot], T.val[a][i]);
+#pragma unroll
+                for (int a = 0; a < NA; a++) {
+                    if (NA == 8 && a >= naggs) break;
+                    if (A.agg[a].op == kAggCount) atomicAdd(reinterpret_cast<unsigned int*>(&T0.val[a][slot]), (unsigned int)T.val[a][i]);
                     else atomicMax(&T0.val[a][slot], T.val[a][i]);
                 }
             } else {
-                agg_to_global(table, A.table_slots, overflow, key, T.first_row[i], x, s_agg, A.naggs);
+                long long xl[kMaxAggs];
+#pragma unroll
+                for (int a = 0; a < NA; a++) xl[a] = agg_smem_value(A.agg[a].op, T.val[a][i]);
+                agg_to_global(table, A.table_slots, overflow, key, T.first_row[i], xl, s_agg, naggs);
             }
         }
     }
@@ -194,9 +235,10 @@ __global__ void __launch_bounds__(kComputeThreads, 2) agg_kernel(const __grid_co
     for (int i = tid; i < kAggWarpSlots; i += kComputeThreads) {
         const unsigned long long key = T0.key[i];
         if (key == kAggEmpty) continue;
-        long long x[kMaxAggs];
-        for (int a = 0; a < A.naggs; a++) x[a] = s_agg[a].op == kAggCount ? (long long)(unsigned int)T0.val[a][i] : (long long)T0.val[a][i];
-        agg_to_global(table, A.table_slots, overflow, key, T0.first_row[i], x, s_agg, A.naggs);
+        long long xl[kMaxAggs];
+#pragma unroll
+        for (int a = 0; a < NA; a++) xl[a] = agg_smem_value(A.agg[a].op, T0.val[a][i]);
+        agg_to_global(table, A.table_slots, overflow, key, T0.first_row[i], xl, s_agg, naggs);
     }
 }
 

@@ -75,7 +75,6 @@ static cudaError_t configure_device() {
         IMM3_SET_SMEM(blocks_filter_quad_kernel);
         if ((e = cudaFuncSetAttribute(blocks_filter_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024)) != cudaSuccess) return e;
         IMM3_SET_SMEM(block_stats_kernel);
-        IMM3_SET_SMEM(agg_kernel);
         IMM3_SET_SMEM(blocks_emit_kernel<true>);
         IMM3_SET_SMEM(blocks_emit_kernel<false>);
         IMM3_SET_SMEM(emit_general_kernel);
@@ -194,19 +193,38 @@ cudaError_t launch_agg_init(AggEntry* table, uint32_t slots, const AggPlan& a, u
     agg_init_kernel<<<(slots + kComputeThreads - 1) / kComputeThreads, kComputeThreads, 0, stream>>>(table, slots, ops, counters);
     return cudaGetLastError();
 }
-cudaError_t launch_agg(const AggPlan& a, const uint32_t* bitmap, const uint32_t* span_cnt, AggEntry* table, AggEntry* out, unsigned int* counters,
-                       const ScanCtrl* ctrl, int num_sms, cudaStream_t stream) {
-    cudaError_t e = configure_once();
-    if (e != cudaSuccess) return e;
-    const size_t smem = (size_t)kComputeWarps * sizeof(AggWarpTable) + (size_t)kComputeWarps * 1024 * 2;
+template <int NG, int NA>
+static cudaError_t launch_agg_as(const AggPlan& a, const uint32_t* bitmap, const uint32_t* span_cnt, AggEntry* table, unsigned int* overflow,
+                                 const ScanCtrl* ctrl, int num_sms, cudaStream_t stream) {
+    const size_t smem = (size_t)kComputeWarps * sizeof(AggWarpTableT<NA>) + (size_t)kComputeWarps * 1024 * 2;
+    cudaError_t e = cudaSuccess;
+    // (a per-device attribute, set per launch: one driver call per aggregation query)
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(agg_kernel<NG, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, agg_kernel, kComputeThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, agg_kernel<NG, NA>, kComputeThreads, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorInvalidConfiguration;
     const long long nspans = a.ntiles * 8;
     const long long grid = std::max<long long>(1, std::min<long long>((nspans + kComputeWarps - 1) / kComputeWarps, (long long)num_sms * occ));
-    agg_kernel<<<(unsigned)grid, kComputeThreads, smem, stream>>>(a, bitmap, span_cnt, table, counters + 1, ctrl);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    agg_kernel<NG, NA><<<(unsigned)grid, kComputeThreads, smem, stream>>>(a, bitmap, span_cnt, table, overflow, ctrl);
+    return cudaGetLastError();
+}
+cudaError_t launch_agg(const AggPlan& a, const uint32_t* bitmap, const uint32_t* span_cnt, AggEntry* table, AggEntry* out, unsigned int* counters,
+                       const ScanCtrl* ctrl, int num_sms, cudaStream_t stream) {
+    cudaError_t e = configure_once();
+    if (e != cudaSuccess) return e;
+    // the instantiation for this query's shape: exact for <= 2 group-by columns and 1 .. 4 aggregates, the general forms beyond
+    const int ng = a.ngroup <= 2 ? a.ngroup : 4, na = (a.naggs >= 1 && a.naggs <= 4) ? a.naggs : 8;
+#define IMM3_AGG_CASE(NG, NA) \
+    if (ng == NG && na == NA) e = launch_agg_as<NG, NA>(a, bitmap, span_cnt, table, counters + 1, ctrl, num_sms, stream)
+#define IMM3_AGG_ROW(NG) IMM3_AGG_CASE(NG, 1); else IMM3_AGG_CASE(NG, 2); else IMM3_AGG_CASE(NG, 3); else IMM3_AGG_CASE(NG, 4); else IMM3_AGG_CASE(NG, 8)
+    if (ng == 0) { IMM3_AGG_ROW(0); }
+    else if (ng == 1) { IMM3_AGG_ROW(1); }
+    else if (ng == 2) { IMM3_AGG_ROW(2); }
+    else { IMM3_AGG_ROW(4); }
+#undef IMM3_AGG_ROW
+#undef IMM3_AGG_CASE
+    if (e != cudaSuccess) return e;
     agg_compact_kernel<<<(a.table_slots + kComputeThreads - 1) / kComputeThreads, kComputeThreads, 0, stream>>>(table, a.table_slots, out, counters);
     return cudaGetLastError();
 }
