@@ -196,7 +196,7 @@ cudaError_t launch_agg_init(AggEntry* table, uint32_t slots, const AggPlan& a, u
 template <int NG, int NA>
 static cudaError_t launch_agg_as(const AggPlan& a, const uint32_t* bitmap, const uint32_t* span_cnt, AggEntry* table, unsigned int* overflow,
                                  const ScanCtrl* ctrl, int num_sms, cudaStream_t stream) {
-    const size_t smem = (size_t)kComputeWarps * sizeof(AggWarpTableT<NA>) + (size_t)kComputeWarps * 1024 * 2;
+    const size_t smem = agg_smem_bytes(NA);
     cudaError_t e = cudaSuccess;
     // (a per-device attribute, set per launch: one driver call per aggregation query)
     if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(agg_kernel<NG, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
