@@ -411,15 +411,17 @@ __global__ void __launch_bounds__(kComputeThreads, ROWSPACE ? 3 : 2) blocks_emit
         append_selection(myword, lane, sel_w, 0u);
         __syncwarp();
         if (fused_ok) {
-#pragma unroll 1
-            for (int b0 = 0; b0 < nn; b0 += 128) {
-                int idx[4];  // row within the block, -1 = no row
+            // R rows per lane and round; a block with few surviving rows (a scattered 1 % predicate leaves ~10 of 1024) takes the
+            // R = 1 instantiation: a quarter of the (predicated-off) gathers and stores of the 4-row form
+            auto emit_rows = [&](auto rtag, int b0) {
+                constexpr int R = decltype(rtag)::value;
+                int idx[R];  // row within the block, -1 = no row
 #pragma unroll
-                for (int r = 0; r < 4; r++) {
+                for (int r = 0; r < R; r++) {
                     const int i = b0 + lane + 32 * r;
                     idx[r] = i < nn ? (int)lds_cell<uint16_t>(sel_addr + 2u * (uint32_t)i) : -1;
                 }
-                uint32_t v[4][4];
+                uint32_t v[R][4];
 #pragma unroll
                 for (int pc = 0; pc < 4; pc++) {
                     if (pc < P.nproj) {
@@ -429,22 +431,22 @@ __global__ void __launch_bounds__(kComputeThreads, ROWSPACE ? 3 : 2) blocks_emit
                             const uint32_t* bs = bases + slot * 32;
                             if ((dense_slots >> slot) & 1u) {
 #pragma unroll
-                                for (int r = 0; r < 4; r++) v[r][pc] = idx[r] >= 0 ? dense_value(vs, idx[r]) : 0u;
+                                for (int r = 0; r < R; r++) v[r][pc] = idx[r] >= 0 ? dense_value(vs, idx[r]) : 0u;
                             } else {
 #pragma unroll
-                                for (int r = 0; r < 4; r++) v[r][pc] = idx[r] >= 0 ? vs[(idx[r] >> 5) * kBlkLane + (idx[r] & 31)] + bs[idx[r] >> 5] : 0u;
+                                for (int r = 0; r < R; r++) v[r][pc] = idx[r] >= 0 ? vs[(idx[r] >> 5) * kBlkLane + (idx[r] & 31)] + bs[idx[r] >> 5] : 0u;
                             }
                         } else {
                             const uint8_t* cbase = s_proj[pc].base + R0 * w;
                             if (w == 4) {
 #pragma unroll
-                                for (int r = 0; r < 4; r++) v[r][pc] = idx[r] >= 0 ? __ldg(reinterpret_cast<const uint32_t*>(cbase) + idx[r]) : 0u;
+                                for (int r = 0; r < R; r++) v[r][pc] = idx[r] >= 0 ? __ldg(reinterpret_cast<const uint32_t*>(cbase) + idx[r]) : 0u;
                             } else if (w == 1) {
 #pragma unroll
-                                for (int r = 0; r < 4; r++) v[r][pc] = idx[r] >= 0 ? (uint32_t)__ldg(cbase + idx[r]) : 0u;
+                                for (int r = 0; r < R; r++) v[r][pc] = idx[r] >= 0 ? (uint32_t)__ldg(cbase + idx[r]) : 0u;
                             } else {
 #pragma unroll
-                                for (int r = 0; r < 4; r++)
+                                for (int r = 0; r < R; r++)
                                     v[r][pc] = idx[r] >= 0 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(cbase) + idx[r]) : 0u;
                             }
                         }
@@ -456,7 +458,7 @@ __global__ void __launch_bounds__(kComputeThreads, ROWSPACE ? 3 : 2) blocks_emit
                         const int w = s_proj[pc].width;
                         uint8_t* obase = s_proj[pc].out + (g + b0 + lane) * w;
 #pragma unroll
-                        for (int r = 0; r < 4; r++) {
+                        for (int r = 0; r < R; r++) {
                             if (idx[r] >= 0) {
                                 if (w == 4) reinterpret_cast<uint32_t*>(obase)[32 * r] = v[r][pc];
                                 else if (w == 1) obase[32 * r] = (uint8_t)v[r][pc];
@@ -465,6 +467,11 @@ __global__ void __launch_bounds__(kComputeThreads, ROWSPACE ? 3 : 2) blocks_emit
                         }
                     }
                 }
+            };
+#pragma unroll 1
+            for (int b0 = 0; b0 < nn; b0 += 128) {
+                if (nn - b0 <= 32) emit_rows(std::integral_constant<int, 1>{}, b0);
+                else emit_rows(std::integral_constant<int, 4>{}, b0);
             }
         } else {
             // any select list: column by column, a row per lane
@@ -496,13 +503,8 @@ __global__ void __launch_bounds__(kComputeThreads, ROWSPACE ? 3 : 2) blocks_emit
             }
             return m;
         };
-        // A warp visits blocks warp0, warp0 + nwarps, ... (round robin, so that a clustered result spreads over all warps);
-        // the next block's metadata (its bits are found through R0) is in flight while this one is handled.
-        unsigned long long meta_n = load_meta(warp0);
-#pragma unroll 1
-        for (long long blk = warp0; blk < nblocks; blk += nwarps) {
-            const unsigned long long meta = meta_n;
-            meta_n = load_meta(blk + nwarps);
+        // One block (its metadata in `meta`): the bits of its rows, its first result ordinal, emit_block.
+        auto handle = [&](unsigned long long meta) {
             const long long R0 = (long long)__shfl_sync(0xFFFFFFFFu, meta, 0);
             const int n = (int)((long long)__shfl_sync(0xFFFFFFFFu, meta, 1) - R0);
             const long long bit0 = R0 + 32 * lane;
@@ -514,11 +516,51 @@ __global__ void __launch_bounds__(kComputeThreads, ROWSPACE ? 3 : 2) blocks_emit
             uint32_t myword = __funnelshift_r(lo, hi, (uint32_t)(bit0 & 31));
             const int left = n - lane * 32;
             myword &= left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
-            if (__ballot_sync(0xFFFFFFFFu, myword != 0u) == 0u) continue;
+            if (__ballot_sync(0xFFFFFFFFu, myword != 0u) == 0u) return;
             const long long wrow0 = (span << 10) + 32 * lane;  // first row of span word `lane`
             const unsigned below = wrow0 + 32 <= R0 ? (unsigned)__popc(sw) : (wrow0 < R0 ? (unsigned)__popc(sw & ((1u << (int)(R0 - wrow0)) - 1u)) : 0u);
             const long long g = (long long)toff + __reduce_add_sync(0xFFFFFFFFu, sc + below);
             emit_block(R0, n, myword, g, [&](int slot, int k) -> uint32_t { return (uint32_t)__shfl_sync(0xFFFFFFFFu, meta, 2 + 2 * slot + k); }, -1, DenseRegs{0, 0, 0, 0, -1});
+        };
+        // A warp visits blocks warp0, warp0 + nwarps, ... (round robin, so that a clustered result spreads over all warps).
+        if (__ldcg(&ctrl->total) < (unsigned long long)nblocks && !(P.debug & 2048u)) {
+            // Fewer surviving rows than blocks: most blocks are empty.  32 blocks at a time, a lane each, are tested through the
+            // counts of the (at most two) 1024-row spans they overlap - two loads per lane instead of a warp-wide visit per
+            // block; the warp then handles the blocks that may hold rows, the next one's metadata in flight.
+#pragma unroll 1
+            for (long long b0 = warp0; b0 < nblocks; b0 += 32 * nwarps) {
+                const long long b = b0 + lane * nwarps;
+                bool cand = b < nblocks;
+                if (cand) {
+                    const unsigned long long r0 = P.row_start[b], r1 = P.row_start[b + 1];
+                    const long long s0 = (long long)(r0 >> 10), s1 = (long long)((r1 - 1) >> 10);
+                    const unsigned c = __ldg(cnts + s0) + (s1 != s0 ? __ldg(cnts + s1) : 0u);
+                    cand = c != 0u;
+                }
+                unsigned todo = __ballot_sync(0xFFFFFFFFu, cand);
+                if (!todo) continue;
+                int nsrc = __ffs((int)todo) - 1;
+                unsigned long long meta_n = load_meta(__shfl_sync(0xFFFFFFFFu, b, nsrc));
+#pragma unroll 1
+                while (todo) {
+                    todo &= todo - 1u;
+                    const unsigned long long meta = meta_n;
+                    if (todo) {
+                        nsrc = __ffs((int)todo) - 1;
+                        meta_n = load_meta(__shfl_sync(0xFFFFFFFFu, b, nsrc));
+                    }
+                    handle(meta);
+                }
+            }
+        } else {
+            // ... every block in turn, the next block's metadata (its bits are found through R0) in flight while this one is handled
+            unsigned long long meta_n = load_meta(warp0);
+#pragma unroll 1
+            for (long long blk = warp0; blk < nblocks; blk += nwarps) {
+                const unsigned long long meta = meta_n;
+                meta_n = load_meta(blk + nwarps);
+                handle(meta);
+            }
         }
     } else {
         // Block-local bitmap.  A warp visits blocks warp0, warp0 + nwarps, ... (round robin, so that a clustered result spreads

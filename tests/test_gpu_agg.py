@@ -80,6 +80,12 @@ def test_aggregates_match_the_oracle(world):
     check_agg(orc, eng, "one", NoSelect, [Count("id"), Min("age")], ["state"])
     check_agg(orc, eng, "p", Select("age", GT(90)), [Count("age"), Max("age")], ["state"])                # encoded table, dense predicate
     check_agg(orc, eng, "t", NoSelect, [Count("id")], ["id"])                                             # 50 000 groups: the CTA tables overflow
+    # every instantiation of agg_kernel<NG, NA>: 0 / 1 / 2 / "up to 4" group-by columns x 1 .. 4 / "up to 8" aggregates
+    many = [Count("id"), Min("id"), Max("id"), Min("age"), Max("age"), Count("state"), Max("big"), Min("big")]
+    for gb in ([], ["state"], ["state", "age"], ["zip", "state", "age"], ["age", "state", "age", "state"]):
+        for na in (1, 2, 3, 4, 5, 8):
+            check_agg(orc, eng, "wide", Select("age", GT(3)), many[:na], gb)
+            check_agg(orc, eng, "wide", Select("age", EQ(5)), many[8 - na:], gb)                          # sparse selection, MIN / MAX first
 
 
 def test_aggregate_errors_are_status_codes(world, monkeypatch):
