@@ -296,6 +296,18 @@ def config_dict(args, workload, total_rows, world, extra=None):
     return c
 
 
+def protocol_keys(args, result_rows):
+    """The measurement-protocol part of `config`: the same dict in both arms (--impl ours / reference), so that the two lines
+    describe one configuration; what is specific to an arm says which arm it is about."""
+    return {"l2": "GPU arm: flushed between steps (512 MiB %s pass); reference arm: the table is larger than every host cache"
+                  % os.environ.get("IMM3_BENCH_FLUSH", "read"),
+            "kernel_variant": "direct" if args.no_tma else "tma", "block_pruning": False,
+            "timed": "GPU arm: wall: host barrier (ranks released at one instant of the host clock) -> imm3_query_begin returns (all kernels + "
+                     "on-device count exchange + one sync); median of K steps of the max over ranks.  Reference arm: wall clock around one "
+                     "whole-table query on all host threads; median of K steps",
+            "result_rows": result_rows}
+
+
 def reference_arm(args):
     """The reference's own CPU path - as far as it can exist here: the Scala engine cannot run (no JVM), so this is the
     oracle port on all host cores, same table, same query, same --steps/--warmup.  No product code is imported."""
@@ -311,7 +323,7 @@ def reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": config_dict(args, args.workload, total, world),
+        "config": config_dict(args, args.workload, total, world, protocol_keys(args, res.nrows)),
         "cpu_baseline": {"value": v, "unit": "rows/s", "cores": cores, "kind": "port",
                          "sample": f"whole table ({rows} rows) per step, one task per segment on {cores} threads (Engine.scala:176-180); "
                                    "CPU restatement of the reference path - the Scala engine itself cannot run here (no JVM)"},
@@ -680,10 +692,7 @@ def main():
             "metric": METRIC, "value": head["value"], "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": config_dict(args, args.workload, total, world, {
-                "l2": "flushed between steps (512 MiB %s pass)" % flush_mode, "kernel_variant": "direct" if args.no_tma else "tma",
-                "block_pruning": False, "timed": "wall: host barrier (ranks released at one instant of the host clock) -> imm3_query_begin returns (all kernels + on-device count exchange + one sync); median of K steps of the max over ranks",
-                "result_rows": head["result_rows"]}),
+            "config": config_dict(args, args.workload, total, world, protocol_keys(args, head["result_rows"])),
             "clocks": clocks, "timing": {k: head[k] for k in ("wall_ms", "device_ms", "host_overhead_us", "host_phase_us_rank0")},
             "e2e": e2e, "e2e_resident": e2e_res, "gpu_launches": head["gpu_launches"], "roofline": roofline, "cpu_baseline": cpu,
             "result_equal": result_equal, "workloads": secondary, "open_s": open_s,
