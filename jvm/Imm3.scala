@@ -13,6 +13,8 @@ object Imm3 {
   val open       = h("imm3_open",        FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS))
   val close      = h("imm3_close",       FunctionDescriptor.of(JAVA_INT, ADDRESS))
   val query      = h("imm3_query",       FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, JAVA_LONG, ADDRESS))
+  // imm3_query_agg(db, table, preds, npreds, aggs, naggs, group_cols, ngroup, &out): ProjectAggOp + ProjectAggregateQueueOp
+  val queryAgg   = h("imm3_query_agg",   FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS))
   val nrows      = h("imm3_result_nrows",     FunctionDescriptor.of(JAVA_LONG, ADDRESS))
   val ncols      = h("imm3_result_ncols",     FunctionDescriptor.of(JAVA_INT, ADDRESS))
   val colType    = h("imm3_result_col_type",  FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT))
@@ -25,6 +27,8 @@ object Imm3 {
   val PRED: MemoryLayout = MemoryLayout.structLayout(
     ADDRESS.withName("col"), JAVA_INT.withName("op"), MemoryLayout.paddingLayout(4),
     JAVA_DOUBLE.withName("num"), ADDRESS.withName("strs"), JAVA_INT.withName("nstrs"), MemoryLayout.paddingLayout(4))
+  // struct imm3_agg { const char* col; int32 op; }  op: 0 count, 1 min, 2 max (imm3_agg_op)
+  val AGG: MemoryLayout = MemoryLayout.structLayout(ADDRESS.withName("col"), JAVA_INT.withName("op"), MemoryLayout.paddingLayout(4))
   // struct imm3_open_opts { int32 device, rank, world; uint32 flags; }
   val OPTS: MemoryLayout = MemoryLayout.structLayout(JAVA_INT, JAVA_INT, JAVA_INT, JAVA_INT)
 }
