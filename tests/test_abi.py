@@ -48,3 +48,14 @@ def test_open_without_a_gpu_fails_loudly_not_silently(tmp_path):
     with pytest.raises(Imm3Error) as e:
         SegmentManager(tmp_path)
     assert e.value.status == L.ERR_CUDA and "no CPU fallback" in e.value.message
+
+
+def test_struct_layouts_match_the_jvm_binding():
+    """The offsets jvm/Imm3.scala and INTEGRATION.md hard-code (Panama structLayout / p.set(..., offset, ...)) are the C ABI's."""
+    P, A, O = L.Pred, L.Agg, L.OpenOpts
+    assert (P.col.offset, P.op.offset, P.num.offset, P.strs.offset, P.nstrs.offset, ctypes.sizeof(P)) == (0, 8, 16, 24, 32, 40)
+    assert (A.col.offset, A.op.offset, ctypes.sizeof(A)) == (0, 8, 16)
+    assert (O.device.offset, O.rank.offset, O.world.offset, O.flags.offset, ctypes.sizeof(O)) == (0, 4, 8, 12, 16)
+    scala = open(os.path.join(ROOT, "jvm", "Imm3.scala")).read()
+    for sym in ("imm3_open", "imm3_close", "imm3_query", "imm3_query_agg", "imm3_result_nrows", "imm3_result_col_data", "imm3_result_free", "imm3_last_error"):
+        assert f'"{sym}"' in scala and sym in L.SIGNATURES, sym
